@@ -1,0 +1,115 @@
+"""The oracle (oracle/wb_oracle.py) against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import wb_oracle as orc
+
+from conftest import GOLDEN
+
+RTOL = 1e-8  # the reference's own regression tolerance (tests/common_comparers.py:186-189)
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def fe():
+    return orc.OracleSystem.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+
+
+@pytest.fixture(scope="module")
+def te():
+    return orc.OracleSystem.from_npz(os.path.join(GOLDEN, "te_system.npz"))
+
+
+def test_cRvec_shifted(fe):
+    f = np.load(os.path.join(GOLDEN, "fe_system.npz"))
+    # floating point (goes through reduced coordinates in the reference): not index work
+    assert np.abs(fe.cRvec_shifted - f["cRvec_shifted"]).max() < 1e-13
+    assert fe.cell_volume == pytest.approx(float(f["cell_volume"]), rel=1e-15)
+
+
+def test_kgrid_bit_exact():
+    g = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    shifts, factors = orc.K_list([2, 2, 2], [2, 2, 2])
+    assert np.array_equal(shifts, g["K_list_Kp_fullBZ"])
+    assert np.array_equal(factors, g["K_list_factor"])
+    assert np.array_equal(orc.points_FFT([2, 2, 2]), g["points_FFT"])
+    b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
+    assert np.array_equal(orc.kpoints_all(b["NKFFT"], b["dK"]), b["kpoints_all"])
+
+
+def test_block_stages(fe):
+    b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
+    data = orc.OracleDataK(fe, b["dK"], b["NKFFT"])
+    assert relerr(data.HH_K, b["HH_K"]) < 1e-13
+    assert relerr(data.E_K, b["E_K"]) < 1e-13
+    assert relerr(data.delE_K, b["delE_K"]) < 1e-11
+    assert relerr(np.abs(data.Xbar("Ham", 1)), b["absV"]) < 1e-9
+    assert relerr(np.abs(data.Xbar("AA")), b["absA"]) < 1e-9
+    # FFT path == explicit DFT (as tests/test_data_k.py does for the reference)
+    slow = orc.r_to_k_slow(fe.XX_R["AA"], fe.iRvec, b["NKFFT"], b["dK"], True)
+    fast = orc.r_to_k(fe.XX_R["AA"], fe.iRvec, b["NKFFT"], b["dK"], True)
+    assert relerr(fast, slow) < 1e-13
+
+
+BLOCK_CASES = dict(
+    ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}),
+    ahc_kramers=("AHC", dict(degen_Kramers=True)), ahc_thresh=("AHC", dict(degen_thresh=0.05)),
+    morb_thresh=("Morb", dict(degen_thresh=0.05)),
+    bcd_thresh=("BerryDipole_FermiSurf", dict(degen_thresh=0.05)),
+    gme_orb_thresh=("GME_orb_FermiSurf", dict(degen_thresh=0.05)),
+    gme_spin_thresh=("GME_spin_FermiSurf", dict(degen_thresh=0.05)),
+)
+
+
+@pytest.mark.parametrize("case", sorted(BLOCK_CASES))
+def test_block_calculators(fe, case):
+    b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
+    data = orc.OracleDataK(fe, b["dK"], b["NKFFT"])
+    name, kw = BLOCK_CASES[case]
+    got = orc.CALCULATORS[name](data, b["Efermi"], **kw)
+    assert got.shape == b["block_" + case].shape
+    assert relerr(got, b["block_" + case]) < RTOL
+
+
+def test_fe_run_vs_upstream_golden(fe):
+    """Full run on the reference's own test grid; compared with the data of the reference's
+    golden files Fe_W90-*_iter-0000.npz (copied into the fixture by make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    Ef = g["Efermi"]
+    calcs = dict(ahc=("AHC", Ef, {}), dos=("DOS", Ef, {}), cumdos=("CumDOS", Ef, {}), Morb=("Morb", Ef, {}),
+                 spin=("Spin", Ef, {}))
+    res = orc.run(fe, [2, 2, 2], [2, 2, 2], calcs)
+    for q in calcs:
+        assert relerr(res[q], g["upstream_golden_" + q]) < RTOL, q
+        assert relerr(res[q], g[q]) < RTOL, q
+
+
+def test_fe_run_other_quantities(fe):
+    g = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    Ef = g["Efermi"]
+    calcs = dict(ahc_int=("AHC", Ef, dict(kwargs_formula=dict(external_terms=False))),
+                 berry_dipole_fsurf=("BerryDipole_FermiSurf", Ef, {}),
+                 gme_orb_fsurf=("GME_orb_FermiSurf", Ef, {}),
+                 gme_spin_fsurf=("GME_spin_FermiSurf", Ef, {}))
+    res = orc.run(fe, [2, 2, 2], [2, 2, 2], calcs)
+    for q in calcs:
+        assert relerr(res[q], g[q]) < RTOL, q
+
+
+def test_te_run(te):
+    g = np.load(os.path.join(GOLDEN, "golden_te_nk4.npz"))
+    Ef = g["Efermi"]
+    calcs = dict(berry_dipole_fsurf=("BerryDipole_FermiSurf", Ef, {}),
+                 gme_orb_fsurf=("GME_orb_FermiSurf", Ef, {}),
+                 gme_spin_fsurf=("GME_spin_FermiSurf", Ef, {}),
+                 dos=("DOS", Ef, {}), cumdos=("CumDOS", Ef, {}))
+    # (AHC and Morb vanish by time-reversal symmetry in Te: the fixture holds only rounding noise)
+    res = orc.run(te, [2, 2, 2], [2, 2, 3], calcs)
+    for q in calcs:
+        assert relerr(res[q], g[q]) < RTOL, q
