@@ -1,0 +1,137 @@
+/*
+ * wbgpu.h -- C-ABI of the B200-native k-grid evaluation library (libwbgpu.so).
+ *
+ * This is the drop-in boundary for the hot path of wannier-berri
+ *   wannierberri.fourier + data_K + formula + calculators.static   (SURVEY.md section 8).
+ * The reference is pure Python; the binding a maintainer adds is a ctypes.CDLL stub
+ * (see INTEGRATION.md).  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - complex128 arrays are passed as `const double*` with (re, im) interleaved, C order;
+ *   - every function returns 0 on success, non-zero on error; `wbgpu_last_error()` returns a
+ *     human readable description of the last error on the calling thread;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails;
+ *   - a context is used from one host thread at a time (the reference is single threaded per
+ *     process, run_grid.py:258-265); different contexts may be used concurrently.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/wannierberri):
+ *   wbgpu_create / wbgpu_set_R_matrix  <- System_R.get_R_mat, .rvec.iRvec, .rvec.cRvec_shifted
+ *                                         (system/system_R.py:106-115, fourier/rvectors.py:351-369)
+ *   wbgpu_plan                         <- Data_K_R.__init__ / Rvectors.set_fft_R_to_k
+ *                                         (data_K/data_K_R.py:11-22, fourier/rvectors.py:443-475)
+ *   wbgpu_static_scan(_dev)            <- paralfunc + StaticCalculator.__call__ over a list of K-blocks
+ *                                         (run_grid.py:258-265,59-72; calculators/static.py:60-169)
+ *   wbgpu_eig                          <- Data_K.E_K (data_K/data_K.py:211-218)
+ *   wbgpu_xk                           <- Rvectors.R_to_k / FFT_R_to_k.__call__
+ *                                         (fourier/rvectors.py:496-506, fourier/fft.py:133-192)
+ *   wbgpu_band_traces                  <- Formula_ln.trace per band group (formula/formula.py:76-79)
+ */
+#ifndef WBGPU_H
+#define WBGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wbgpu_ctx wbgpu_ctx;
+
+/* formulae (formula/covariant.py) */
+enum {
+    WBGPU_IDENTITY = 0,   /* Identity        covariant.py:10-22   rank 0 */
+    WBGPU_OMEGA = 1,      /* Omega           covariant.py:161-203 rank 1 */
+    WBGPU_MORB_HPM = 2,   /* Morb_Hpm(+1)    covariant.py:424-449 rank 1, non-additive */
+    WBGPU_VEL_OMEGA = 3,  /* VelOmega        covariant.py:798-802 rank 2 */
+    WBGPU_VEL_HPLUS = 4,  /* VelHplus        covariant.py:805-809 rank 2 */
+    WBGPU_VEL_SPIN = 5,   /* VelSpin         covariant.py:812-814 rank 2 */
+    WBGPU_SPIN = 6,       /* Spin            covariant.py:331-335 rank 1 */
+    WBGPU_NFORMULA = 7
+};
+
+/* R-space matrices a context can hold (System_R._XX_R keys) */
+enum { WBGPU_HAM = 0, WBGPU_AA = 1, WBGPU_BB = 2, WBGPU_CC = 3, WBGPU_SS = 4, WBGPU_NKEYS = 5 };
+
+/* Wannier-gauge k-space channels that wbgpu_xk can return (parity probe) */
+enum {
+    WBGPU_CH_HAM = 0,     /* H(k)            hermitised   [nk][nw][nw]    */
+    WBGPU_CH_DHAM = 1,    /* d_a H(k)        as is        [nk][nw][nw][3] */
+    WBGPU_CH_AA = 2,      /* A_a(k)          hermitised   [nk][nw][nw][3] */
+    WBGPU_CH_ROTAA = 3,   /* (curl A)_c(k)   hermitised   [nk][nw][nw][3] */
+    WBGPU_CH_BB = 4,      /* B_a(k)          as is        [nk][nw][nw][3] */
+    WBGPU_CH_CC = 5,      /* C_c(k)          as is        [nk][nw][nw][3] */
+    WBGPU_CH_SS = 6       /* S_a(k)          hermitised   [nk][nw][nw][3] */
+};
+
+/* One Fermi-level scan = one StaticCalculator.__call__ (calculators/static.py:26-169),
+ * tetra=False, k_resolved=False, select_bands=None. */
+typedef struct wbgpu_scan_spec {
+    int32_t formula;         /* WBGPU_*                                                     */
+    int32_t fder;            /* 0 Fermi sea, 1..3 derivatives of f (static.py:137-147)        */
+    int32_t nEF;             /* len(Efermi)                                                  */
+    int32_t degen_Kramers;   /* calculator.py:20                                             */
+    int32_t internal_terms;  /* formula.py:11-29                                             */
+    int32_t external_terms;
+    double Ef_first;         /* Efermi[0]                                                    */
+    double Ef_last;          /* Efermi[-1]                                                   */
+    double dEF;              /* Efermi[1]-Efermi[0]  (0.001 if nEF == 1), static.py:55       */
+    double degen_thresh;     /* calculator.py:20                                             */
+    double factor;           /* constant_factor (or its sign), hole_like already applied     */
+} wbgpu_scan_spec;
+
+const char* wbgpu_last_error(void);
+int wbgpu_version(void);
+/* number of CUDA devices visible (0 when there is none); never fails */
+int wbgpu_device_count(void);
+
+/* Create a context on CUDA device `device` for a system with `nw` Wannier functions and `nR`
+ * lattice vectors.  iRvec[nR][3] (int32), cRvec_shifted[nR][nw][nw][3] = R + t_j - t_i (Angstrom).
+ * All inputs are HOST pointers and are copied.  `stream` is a cudaStream_t (NULL = default). */
+int wbgpu_create(wbgpu_ctx** ctx, int device, int nw, int nR, const int32_t* iRvec,
+                 const double* cRvec_shifted, double cell_volume, void* stream);
+int wbgpu_destroy(wbgpu_ctx* ctx);
+
+/* Copy one R-space matrix to the device: X_R[nR][nw][nw][ncart] complex128, ncart = 1 (Ham) or 3. */
+int wbgpu_set_R_matrix(wbgpu_ctx* ctx, int key, const double* X_R, int ncart);
+
+/* Fix the FFT sub-grid NKFFT[3] and the set of formulae that will be evaluated
+ * (formula_mask = OR of 1<<WBGPU_*), `external_terms` = whether any of them needs AA/BB/CC
+ * channels.  Builds the device-resident Fourier tables and sizes the workspace for at most
+ * `max_kpoints_per_launch` k-points per kernel batch (0 = choose from free memory). */
+int wbgpu_plan(wbgpu_ctx* ctx, const int32_t NKFFT[3], uint32_t formula_mask, int external_terms,
+               int64_t max_kpoints_per_launch);
+
+/* Evaluate `nspec` Fermi scans over `nblocks` K-blocks:  out = sum_b weight[b] * scan(block b).
+ * dK[nblocks][3] = Kpoint.Kp_fullBZ, weight[nblocks] = Kpoint.factor (HOST pointers).
+ * out: concatenation over specs of data[nEF][3^rank] float64 (HOST pointer), already divided by
+ * cell_volume and nk and multiplied by spec.factor (static.py:149-155).
+ * Host<->device copies happen inside the call. */
+int wbgpu_static_scan(wbgpu_ctx* ctx, int nblocks, const double* dK, const double* weight,
+                      const wbgpu_scan_spec* specs, int nspec, double* out);
+/* Same with dK / weight / out resident in device memory (DEVICE pointers); asynchronous on the
+ * context's stream. */
+int wbgpu_static_scan_dev(wbgpu_ctx* ctx, int nblocks, const double* dK_dev, const double* weight_dev,
+                          const wbgpu_scan_spec* specs, int nspec, double* out_dev);
+/* number of float64 values one spec writes */
+int64_t wbgpu_spec_size(const wbgpu_scan_spec* spec);
+
+/* Parity probes (HOST output pointers). One K-block each. */
+int wbgpu_kpoints(wbgpu_ctx* ctx, const double dK[3], double* kpoints /*[nk][3]*/);
+int wbgpu_eig(wbgpu_ctx* ctx, const double dK[3], double* E /*[nk][nw]*/, double* U /*[nk][nw][nw] c128 or NULL*/);
+int wbgpu_xk(wbgpu_ctx* ctx, const double dK[3], int channel, double* X /*complex128, see enum*/);
+/* per-k, per-band-group traces of a formula: E_label[nk][nw], value[nk][nw][3^rank]; slot b is
+ * used iff a kept group starts at band b (label -inf for the Fermi-sea group), else label=+inf */
+int wbgpu_band_traces(wbgpu_ctx* ctx, const double dK[3], const wbgpu_scan_spec* spec,
+                      double* E_label, double* value);
+
+/* counters since context creation */
+int64_t wbgpu_kernel_launches(const wbgpu_ctx* ctx);
+/* last eigensolver launch: max Jacobi sweeps over k-points (diagnostic) */
+int wbgpu_last_eig_sweeps(const wbgpu_ctx* ctx);
+/* set / get which eigensolver is used: 0 = automatic, 1 = Jacobi (generic), 2 = Householder+QL */
+int wbgpu_set_option(wbgpu_ctx* ctx, const char* name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WBGPU_H */

@@ -1,0 +1,249 @@
+"""Parity of the CUDA path (through the C-ABI of libwbgpu.so) against the oracle and against the
+fixtures generated from the unmodified reference.  Needs a B200: `pytest -m gpu`.
+
+Tolerances: 1e-8 relative to the max-norm over the Fermi axis for integrated quantities and for
+eigenvalues (BASELINE.json north_star; the reference's own regression tolerance,
+tests/common_comparers.py:186-189); bit-exact for the k-grid."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+
+
+def relerr(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def wb():
+    import wannierberri_b200 as wb
+    from wannierberri_b200 import _lib
+    assert _lib.lib().wbgpu_device_count() > 0, "no CUDA device: the GPU tests cannot run (no CPU fallback exists)"
+    return wb
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import wb_oracle
+    return wb_oracle
+
+
+@pytest.fixture(scope="module")
+def fe(wb):
+    return wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+
+
+@pytest.fixture(scope="module")
+def te(wb):
+    return wb.System_R.from_npz(os.path.join(GOLDEN, "te_system.npz"))
+
+
+@pytest.fixture(scope="module")
+def fe_orc(orc):
+    return orc.OracleSystem.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+
+
+@pytest.fixture(scope="module")
+def te_orc(orc):
+    return orc.OracleSystem.from_npz(os.path.join(GOLDEN, "te_system.npz"))
+
+
+ALL = None
+
+
+def all_formulae():
+    from wannierberri_b200 import _lib
+    return [_lib.IDENTITY, _lib.OMEGA]
+
+
+def test_kpoints_bit_exact(wb, fe, orc):
+    b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
+    eng = wb.Engine(fe)
+    eng.plan(b["NKFFT"], all_formulae())
+    assert np.array_equal(eng.kpoints(b["dK"]), b["kpoints_all"])
+    for NKFFT, dK in (([4, 5, 6], [0.013, 0.0, 0.07]), ([12, 12, 12], [1 / 48, 2 / 48, 3 / 48]), ([1, 1, 7], [0.99, 0.5, 1 / 3])):
+        eng.plan(NKFFT, all_formulae())
+        assert np.array_equal(eng.kpoints(dK), orc.kpoints_all(NKFFT, dK))
+
+
+@pytest.mark.parametrize("NKFFT,dK", [([3, 3, 3], [1 / 6, 0., 1 / 12]), ([2, 2, 2], [0., 0., 0.]),
+                                      ([4, 6, 5], [0.01, 0.02, 0.03]), ([12, 12, 12], [1 / 48, 0, 3 / 48])])
+def test_r_to_k(wb, fe, fe_orc, orc, NKFFT, dK):
+    """Separable pruned DFT == the reference's scatter + ifftn (fourier/fft.py:133-192), all channels."""
+    eng = wb.Engine(fe)
+    eng.plan(NKFFT, all_formulae())
+    data = orc.OracleDataK(fe_orc, dK, NKFFT)
+    T = fe_orc.cRvec_shifted
+    H = eng.xk(dK, "Ham")
+    assert relerr(H, data.HH_K) < 1e-13
+    dH = eng.xk(dK, "dHam")
+    assert relerr(dH, data._R_to_k(orc.derivative(fe_orc.XX_R["Ham"], T), False)) < 1e-13
+    A = eng.xk(dK, "AA")
+    assert relerr(A, data._R_to_k(fe_orc.XX_R["AA"], True)) < 1e-13
+    O = eng.xk(dK, "rotAA")
+    assert relerr(O, data._R_to_k(data._rotAA_R(), True)) < 1e-13
+
+
+@pytest.mark.parametrize("which", ["fe", "te"])
+def test_eigh(wb, fe, te, fe_orc, te_orc, orc, which):
+    sysg, syso = (fe, fe_orc) if which == "fe" else (te, te_orc)
+    NKFFT, dK = [4, 4, 4], [0.02, 0.05, 0.11]
+    eng = wb.Engine(sysg)
+    eng.plan(NKFFT, all_formulae())
+    E, U = eng.eig(dK, vectors=True)
+    data = orc.OracleDataK(syso, dK, NKFFT)
+    assert relerr(E, data.E_K) < 1e-12
+    assert np.all(np.diff(E, axis=1) >= 0)
+    H = data.HH_K
+    resid = np.abs(np.einsum("kij,kjn->kin", H, U) - U * E[:, None, :]).max()
+    assert resid < 1e-11 * np.abs(H).max()
+    unit = np.abs(np.einsum("kin,kim->knm", U.conj(), U) - np.eye(sysg.num_wann)).max()
+    assert unit < 1e-12
+
+
+def test_eigh_golden_block(wb, fe):
+    b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
+    eng = wb.Engine(fe)
+    eng.plan(b["NKFFT"], all_formulae())
+    assert relerr(eng.eig(b["dK"]), b["E_K"]) < 1e-12
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(degen_thresh=0.05), dict(degen_Kramers=True),
+                                dict(kwargs_formula=dict(external_terms=False)),
+                                dict(kwargs_formula=dict(internal_terms=False))])
+def test_omega_band_traces(wb, fe, fe_orc, orc, kw):
+    """Per-k, per-band-group traces of Omega against the oracle's Formula.trace with the same groups."""
+    b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
+    NKFFT, dK, Ef = b["NKFFT"], b["dK"], b["Efermi"]
+    calc = wb.calculators.static.AHC(Efermi=Ef, **kw)
+    eng = wb.Engine(fe)
+    eng.plan(NKFFT, all_formulae())
+    lab, val = eng.band_traces(dK, calc.specs()[0])
+    data = orc.OracleDataK(fe_orc, dK, NKFFT)
+    form = orc.Omega(data, **kw.get("kwargs_formula", {}))
+    nw = fe.num_wann
+    scale = 0.
+    worst = 0.
+    for ik in range(data.nk):
+        groups = orc.band_groups(data.E_K[ik], calc.EFmin, calc.EFmax, calc.degen_thresh, calc.degen_Kramers, sea=True)
+        starts = {n[0] for n in groups}
+        assert set(np.where(np.isfinite(lab[ik]) | (lab[ik] == -np.inf))[0]) == starts
+        for (a, e), E in groups.items():
+            inn = np.arange(a, e)
+            out = np.concatenate((np.arange(0, a), np.arange(e, nw)))
+            ref = form.trace(ik, inn, out)
+            assert (lab[ik, a] == E) or abs(lab[ik, a] - E) < 1e-9
+            worst = max(worst, np.abs(val[ik, a] - ref).max())
+            scale = max(scale, np.abs(ref).max())
+    assert worst < RTOL * scale
+
+
+BLOCK_CASES = dict(
+    ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}),
+    ahc_kramers=("AHC", dict(degen_Kramers=True)), ahc_thresh=("AHC", dict(degen_thresh=0.05)),
+)
+
+
+@pytest.mark.parametrize("case", sorted(BLOCK_CASES))
+def test_block_calculators_vs_reference(wb, fe, case):
+    """calc(Data_K_R) for one K-block against the reference's output (fixture)."""
+    b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
+    grid = wb.Grid(fe, NKdiv=[2, 2, 2], NKFFT=b["NKFFT"])
+    data = wb.Data_K_R(fe, dK=b["dK"], grid=grid)
+    name, kw = BLOCK_CASES[case]
+    res = getattr(wb.calculators.static, name)(Efermi=b["Efermi"], **kw)(data)
+    assert res.data.shape == b["block_" + case].shape
+    assert relerr(res.data, b["block_" + case]) < RTOL
+
+
+def test_run_fe_vs_upstream_golden(wb, fe):
+    """run() on the reference's own test grid against the data of the reference's golden files
+    tests/reference/integrate_files/Fe_W90-{ahc,dos,cumdos}_iter-0000.npz."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    Ef = g["Efermi"]
+    st = wb.calculators.static
+    calcs = dict(ahc=st.AHC(Efermi=Ef), dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef),
+                 ahc_int=st.AHC(Efermi=Ef, kwargs_formula={"external_terms": False}))
+    res = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), calcs)
+    for q in ("ahc", "dos", "cumdos"):
+        assert relerr(res.results[q].data, g["upstream_golden_" + q]) < RTOL, q
+    assert relerr(res.results["ahc_int"].data, g["ahc_int"]) < RTOL
+
+
+def test_run_fe_wide_window(wb, fe):
+    """BASELINE config-1 style scan (1001 Fermi levels over 12..22 eV) on an 8^3 grid."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_nk8.npz"))
+    Ef = g["Efermi"]
+    st = wb.calculators.static
+    calcs = dict(ahc=st.AHC(Efermi=Ef), dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef))
+    res = wb.run(fe, wb.Grid(fe, NK=[8, 8, 8], NKFFT=[4, 4, 4]), calcs)
+    for q in calcs:
+        assert relerr(res.results[q].data, g[q]) < RTOL, q
+
+
+def test_run_te(wb, te):
+    g = np.load(os.path.join(GOLDEN, "golden_te_nk4.npz"))
+    Ef = g["Efermi"]
+    st = wb.calculators.static
+    calcs = dict(dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef))
+    res = wb.run(te, wb.Grid(te, NK=[4, 4, 6], NKFFT=[2, 2, 3]), calcs)
+    for q in calcs:
+        assert relerr(res.results[q].data, g[q]) < RTOL, q
+
+
+def test_grid_split_independence(wb, fe):
+    """Size-independent property: the result depends only on NKdiv x NKFFT (docs/source/benchmark.rst:26-30),
+    and a shard-wise evaluation adds up to the whole (linearity in the K-block weights)."""
+    Ef = np.linspace(12., 22., 201)
+    st = wb.calculators.static
+    calcs = dict(ahc=st.AHC(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef))
+    ref = wb.run(fe, wb.Grid(fe, NKdiv=[1, 1, 1], NKFFT=[12, 12, 12]), calcs)
+    for div, fft in (([2, 2, 2], [6, 6, 6]), ([4, 4, 4], [3, 3, 3]), ([3, 2, 6], [4, 6, 2])):
+        res = wb.run(fe, wb.Grid(fe, NKdiv=div, NKFFT=fft), calcs)
+        for q in calcs:
+            assert relerr(res.results[q].data, ref.results[q].data) < 1e-9, (q, div)
+    # sum rule: far above all bands CumDOS counts every band
+    top = st.CumDOS(Efermi=np.array([100., 101.]))
+    r = wb.run(fe, wb.Grid(fe, NKdiv=[2, 2, 2], NKFFT=[3, 3, 3]), dict(c=top))
+    assert np.allclose(r.results["c"].data, fe.num_wann, rtol=0, atol=1e-12)
+
+
+def test_shards_add_up(wb, fe):
+    from wannierberri_b200.run import shard_bounds
+    Ef = np.linspace(15., 19., 41)
+    st = wb.calculators.static
+    grid = wb.Grid(fe, NKdiv=[3, 3, 3], NKFFT=[3, 3, 3])
+    specs = st.AHC(Efermi=Ef).specs() + st.DOS(Efermi=Ef).specs()
+    eng = wb.Engine(fe)
+    eng.plan(grid.FFT, [s.formula for s in specs], max_kpoints_per_launch=27 * 4)  # forces several launches
+    shifts, factors = grid.K_arrays()
+    whole = eng.scan(shifts, factors, specs)
+    parts = None
+    for r in range(4):
+        lo, hi = shard_bounds(len(factors), r, 4)
+        p = eng.scan(shifts[lo:hi], factors[lo:hi], specs)
+        parts = p if parts is None else [a + b for a, b in zip(parts, p)]
+    for a, b in zip(whole, parts):
+        assert relerr(a, b) < 1e-11
+
+
+def test_errors(wb, fe):
+    from wannierberri_b200 import _lib
+    st = wb.calculators.static
+    eng = wb.Engine(fe)
+    with pytest.raises(ValueError):
+        eng.scan(np.zeros((1, 3)), np.ones(1), st.DOS(Efermi=np.linspace(0, 1, 3)).specs())  # not planned
+    eng.plan([2, 2, 2], [_lib.IDENTITY])
+    with pytest.raises(ValueError):
+        eng.scan(np.zeros((1, 3)), np.ones(1), st.AHC(Efermi=np.linspace(0, 1, 3)).specs())  # not in the plan
+    with pytest.raises(NotImplementedError):
+        st.AHC(Efermi=np.linspace(0, 1, 3), tetra=True)
+    with pytest.raises(ValueError):
+        bare = wb.System_R(fe.real_lattice, fe.rvec.iRvec, fe.wannier_centers_cart)
+        bare.get_R_mat("Ham")

@@ -1,0 +1,97 @@
+"""ctypes binding of libwbgpu.so (include/wbgpu.h).  No CPU fallback: if the shared library is
+missing, or there is no CUDA device when a context is created, this raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwbgpu.so")
+
+# enums of include/wbgpu.h
+IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN = range(7)
+FORMULA_RANK = {IDENTITY: 0, OMEGA: 1, MORB_HPM: 1, SPIN: 1, VEL_OMEGA: 2, VEL_HPLUS: 2, VEL_SPIN: 2}
+KEYS = {"Ham": 0, "AA": 1, "BB": 2, "CC": 3, "SS": 4}
+CHANNELS = {"Ham": 0, "dHam": 1, "AA": 2, "rotAA": 3, "BB": 4, "CC": 5, "SS": 6}
+
+
+class ScanSpec(C.Structure):
+    _fields_ = [("formula", C.c_int32), ("fder", C.c_int32), ("nEF", C.c_int32), ("degen_Kramers", C.c_int32),
+                ("internal_terms", C.c_int32), ("external_terms", C.c_int32),
+                ("Ef_first", C.c_double), ("Ef_last", C.c_double), ("dEF", C.c_double),
+                ("degen_thresh", C.c_double), ("factor", C.c_double)]
+
+    @property
+    def size(self):
+        return int(self.nEF) * 3 ** FORMULA_RANK[int(self.formula)]
+
+    @property
+    def shape(self):
+        return (int(self.nEF),) + (3,) * FORMULA_RANK[int(self.formula)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libwbgpu.so (built in-tree by `__graft_entry__.build()` / `python -m wannierberri_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m wannierberri_b200.build` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pd = C.POINTER(C.c_double)
+    L.wbgpu_last_error.restype = C.c_char_p
+    L.wbgpu_version.restype = C.c_int
+    L.wbgpu_device_count.restype = C.c_int
+    L.wbgpu_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.POINTER(i32), pd, dbl, vp]
+    L.wbgpu_destroy.argtypes = [vp]
+    L.wbgpu_set_R_matrix.argtypes = [vp, C.c_int, pd, C.c_int]
+    L.wbgpu_plan.argtypes = [vp, C.POINTER(i32), C.c_uint32, C.c_int, i64]
+    L.wbgpu_static_scan.argtypes = [vp, C.c_int, pd, pd, C.POINTER(ScanSpec), C.c_int, pd]
+    L.wbgpu_static_scan_dev.argtypes = [vp, C.c_int, vp, vp, C.POINTER(ScanSpec), C.c_int, vp]
+    L.wbgpu_spec_size.argtypes = [C.POINTER(ScanSpec)]
+    L.wbgpu_spec_size.restype = i64
+    L.wbgpu_kpoints.argtypes = [vp, pd, pd]
+    L.wbgpu_eig.argtypes = [vp, pd, pd, pd]
+    L.wbgpu_xk.argtypes = [vp, pd, C.c_int, pd]
+    L.wbgpu_band_traces.argtypes = [vp, pd, C.POINTER(ScanSpec), pd, pd]
+    L.wbgpu_kernel_launches.argtypes = [vp]
+    L.wbgpu_kernel_launches.restype = i64
+    L.wbgpu_last_eig_sweeps.argtypes = [vp]
+    L.wbgpu_set_option.argtypes = [vp, C.c_char_p, i64]
+    for name in ("wbgpu_create", "wbgpu_destroy", "wbgpu_set_R_matrix", "wbgpu_plan", "wbgpu_static_scan",
+                 "wbgpu_static_scan_dev", "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_band_traces",
+                 "wbgpu_last_eig_sweeps", "wbgpu_set_option"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+EXPORTED = ["wbgpu_last_error", "wbgpu_version", "wbgpu_device_count", "wbgpu_create", "wbgpu_destroy",
+            "wbgpu_set_R_matrix", "wbgpu_plan", "wbgpu_static_scan", "wbgpu_static_scan_dev", "wbgpu_spec_size",
+            "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_band_traces", "wbgpu_kernel_launches",
+            "wbgpu_last_eig_sweeps", "wbgpu_set_option"]
+
+
+def check(status):
+    """Map a non-zero status to the Python exception the reference would raise."""
+    if status == 0:
+        return
+    msg = lib().wbgpu_last_error().decode()
+    if "not implemented" in msg:
+        raise NotImplementedError(msg)
+    if msg.startswith("CUDA error") or "no CUDA device" in msg:
+        raise RuntimeError(msg)
+    raise ValueError(msg)
+
+
+def dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)

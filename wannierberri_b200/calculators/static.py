@@ -1,0 +1,241 @@
+"""Static (Fermi-level scan) calculators with the constructor interface of the reference
+(calculators/static.py:26-58 and calculator.py:20): same class names, same keyword arguments, same
+post-operations.  A calculator here does no arithmetic on k-points itself: it declares the scans
+(`specs()`) that the GPU engine must evaluate and combines their outputs (`combine()`), exactly
+mirroring what `__call__` of the reference class composes."""
+from copy import copy
+
+import numpy as np
+
+from .. import factors
+from .. import _lib
+from .._lib import ScanSpec
+from ..result import EnergyResult
+
+_TR_INV = {  # transformTR, transformInv of the formulae (covariant.py)
+    _lib.IDENTITY: ("ident", "ident"), _lib.OMEGA: ("odd", "ident"), _lib.MORB_HPM: ("odd", "ident"),
+    _lib.SPIN: ("odd", "ident"), _lib.VEL_OMEGA: ("ident", "odd"), _lib.VEL_HPLUS: ("ident", "odd"),
+    _lib.VEL_SPIN: ("ident", "odd"),
+}
+
+
+class Calculator:
+
+    def __init__(self, degen_thresh=1e-4, degen_Kramers=False, save_mode="bin+txt", print_comment=False):
+        self.degen_thresh = degen_thresh
+        self.degen_Kramers = degen_Kramers
+        self.save_mode = save_mode
+        if not hasattr(self, "comment"):
+            self.comment = self.__doc__ if self.__doc__ is not None else "calculator not described"
+        if print_comment:
+            print(self.comment)
+
+    allow_path = False
+    allow_grid = True
+
+
+class StaticCalculator(Calculator):
+
+    def __init__(self, Efermi, tetra=False, smoother=None, constant_factor=1., use_factor=True, kwargs_formula=None,
+                 Emin=-np.inf, Emax=np.inf, hole_like=False, k_resolved=False, Formula=None, fder=None,
+                 select_bands=None, **kwargs):
+        super().__init__(**kwargs)
+        self.Efermi = np.array(Efermi)
+        if self.Efermi.ndim != 1 or len(self.Efermi) < 1:
+            raise ValueError("Efermi must be a 1-d array")
+        if tetra:
+            raise NotImplementedError("tetra=True is not implemented on the GPU path (SURVEY.md section 8(f), next-2)")
+        if k_resolved:
+            raise NotImplementedError("k_resolved=True is not implemented on the GPU path")
+        if select_bands is not None:
+            raise NotImplementedError("select_bands is not implemented on the GPU path")
+        if smoother is not None:
+            raise NotImplementedError("smoothers are post-processing, out of scope of the GPU path")
+        if Emin != -np.inf or Emax != np.inf:
+            raise NotImplementedError("Emin/Emax band selection is not implemented on the GPU path")
+        self.kwargs_formula = copy(kwargs_formula) if kwargs_formula is not None else {}
+        unknown = set(self.kwargs_formula) - {"internal_terms", "external_terms"}
+        if unknown:
+            raise NotImplementedError(f"kwargs_formula {sorted(unknown)} are not implemented on the GPU path")
+        self.use_factor = use_factor
+        self.hole_like = hole_like
+        self.tetra, self.smoother, self.k_resolved, self.select_bands = tetra, smoother, k_resolved, select_bands
+        if Formula is not None:
+            self.Formula = Formula
+        if fder is not None:
+            self.fder = fder
+        assert hasattr(self, "fder"), "fder not set"
+        assert hasattr(self, "Formula"), "Formula not set"
+        if self.fder not in (0, 1, 2, 3):
+            raise NotImplementedError(f"Derivatives  d^{self.fder}f/dE^{self.fder} is not implemented")
+        self.constant_factor = constant_factor
+        if self.hole_like and self.fder == 0:
+            self.constant_factor *= -1
+        # static.py:54-58
+        self.extraEf = 0 if self.fder == 0 else 1 if self.fder in (1, 2) else 2
+        self.dEF = self.Efermi[1] - self.Efermi[0] if len(self.Efermi) > 1 else 0.001
+        self.EFmin = self.Efermi[0] - self.extraEf * self.dEF
+        self.EFmax = self.Efermi[-1] + self.extraEf * self.dEF
+        self.nEF_extra = self.Efermi.shape[0] + 2 * self.extraEf
+
+    # ---- what the engine must evaluate
+    def _spec(self, formula=None, fder=None):
+        f = self.Formula if formula is None else formula
+        factor = self.constant_factor if self.use_factor else float(np.sign(self.constant_factor))
+        return ScanSpec(formula=f, fder=self.fder if fder is None else fder, nEF=len(self.Efermi),
+                        degen_Kramers=int(bool(self.degen_Kramers)),
+                        internal_terms=int(bool(self.kwargs_formula.get("internal_terms", True))),
+                        external_terms=int(bool(self.kwargs_formula.get("external_terms", True))),
+                        Ef_first=float(self.Efermi[0]), Ef_last=float(self.Efermi[-1]), dEF=float(self.dEF),
+                        degen_thresh=float(self.degen_thresh), factor=float(factor))
+
+    def specs(self):
+        return [self._spec()]
+
+    def combine(self, arrays, cell_volume):
+        return arrays[0]
+
+    @property
+    def external_terms(self):
+        return bool(self.kwargs_formula.get("external_terms", True))
+
+    def result(self, arrays, cell_volume):
+        tr, inv = _TR_INV[self.Formula]
+        return EnergyResult(self.Efermi, self.combine(arrays, cell_volume), transformTR=tr, transformInv=inv,
+                            comment=self.comment, save_mode=self.save_mode)
+
+    def __call__(self, data_K):
+        """Per-K-block evaluation with the reference's calling convention `calc(data_K)`; `data_K` is a
+        `wannierberri_b200.Data_K_R` (GPU resident).  static.py:60-169."""
+        arrays = data_K.scan(self.specs(), external_terms=self.external_terms)
+        return self.result(arrays, data_K.cell_volume)
+
+
+class _DOS(StaticCalculator):
+
+    def __init__(self, fder, **kwargs):
+        self.Formula = _lib.IDENTITY
+        self.fder = fder
+        super().__init__(**kwargs)
+
+    def combine(self, arrays, cell_volume):  # static.py:199-200
+        return arrays[0] * cell_volume
+
+
+class DOS(_DOS):
+    r"""Density of states"""
+
+    def __init__(self, **kwargs):
+        super().__init__(fder=1, **kwargs)
+
+
+class CumDOS(_DOS):
+    r"""Cumulative density of states"""
+
+    def __init__(self, **kwargs):
+        super().__init__(fder=0, **kwargs)
+
+
+class Spin(StaticCalculator):
+    r"""Spin per unit cell (dimensionless)"""
+
+    def __init__(self, **kwargs):
+        self.Formula = _lib.SPIN
+        self.fder = 0
+        super().__init__(**kwargs)
+
+    def combine(self, arrays, cell_volume):
+        return arrays[0] * cell_volume
+
+
+class AHC(StaticCalculator):
+    r"""Anomalous Hall conductivity (:math:`s^3 \cdot A^2 / (kg \cdot m^3) = S/m`)
+
+        | Output: :math:`O = -e^2/\hbar \int [dk] \Omega f`"""
+
+    def __init__(self, constant_factor=factors.factor_ahc, **kwargs):
+        self.Formula = _lib.OMEGA
+        self.fder = 0
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+class Morb(StaticCalculator):
+    r"""Orbital magnetic moment per unit cell (:math:`\mu_B`)
+
+        | Output: :math:`M = -\int [dk] (H + G - 2E_f \cdot \Omega) f`"""
+
+    def __init__(self, constant_factor=-factors.eV_au / factors.bohr ** 2, **kwargs):
+        self.Formula = _lib.MORB_HPM
+        self.fder = 0
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+    def specs(self):  # static.py:238-247: Hplus and AHC(constant_factor=same)
+        return [self._spec(), self._spec(formula=_lib.OMEGA)]
+
+    def combine(self, arrays, cell_volume):
+        Hplus, Om = arrays
+        return (Hplus - 2 * Om * self.Efermi[:, None]) * cell_volume
+
+
+class BerryDipole_FermiSurf(StaticCalculator):
+    r"""Berry curvature dipole (dimensionless)
+
+        | Output: :math:`D_{\beta\delta} = -\int [dk] v_\beta \Omega_\delta f'`"""
+
+    def __init__(self, **kwargs):
+        self.Formula = _lib.VEL_OMEGA
+        self.fder = 1
+        super().__init__(**kwargs)
+
+
+class GME_orb_FermiSurf(StaticCalculator):
+    r"""Gyrotropic tensor orbital part (:math:`A`), Fermi surface integral
+
+        | Output: :math:`K^{orb}_{\alpha :\mu} = \int [dk] v_\alpha m^{orb}_\mu f'`"""
+
+    def __init__(self, constant_factor=factors.factor_gme_orb, **kwargs):
+        self.Formula = _lib.VEL_HPLUS
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+    def specs(self):  # static.py:273-281
+        return [self._spec(), self._spec(formula=_lib.VEL_OMEGA)]
+
+    def combine(self, arrays, cell_volume):
+        Hplus, Om = arrays
+        return Hplus - 2 * Om * self.Efermi[:, None, None]
+
+
+class GME_spin_FermiSurf(StaticCalculator):
+    r"""Gyrotropic tensor spin part (:math:`A`), Fermi surface integral
+
+        | Output: :math:`K^{spin}_{\alpha :\mu} = \tau \int [dk] v_\alpha s_\mu f'`"""
+
+    def __init__(self, constant_factor=factors.factor_gme_spin, **kwargs):
+        self.Formula = _lib.VEL_SPIN
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+_BY_NAME = {c.__name__: c for c in (DOS, CumDOS, Spin, AHC, Morb, BerryDipole_FermiSurf, GME_orb_FermiSurf,
+                                    GME_spin_FermiSurf)}
+
+
+def adapt(calc):
+    """Accept a calculator of this package, or an instance of the reference's class of the same name
+    (recognised by class name; its public attributes are copied)."""
+    if isinstance(calc, StaticCalculator):
+        return calc
+    name = type(calc).__name__
+    if name not in _BY_NAME:
+        raise ValueError(f"calculator {name} is not available on the GPU path")
+    kw = dict(Efermi=np.array(calc.Efermi), tetra=calc.tetra, smoother=calc.smoother, use_factor=calc.use_factor,
+              kwargs_formula=calc.kwargs_formula, hole_like=False, k_resolved=calc.k_resolved,
+              select_bands=calc.select_bands, degen_thresh=calc.degen_thresh, degen_Kramers=calc.degen_Kramers,
+              save_mode=calc.save_mode)
+    if name not in ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf"):
+        kw["constant_factor"] = calc.constant_factor  # hole_like sign already folded in by the reference
+    new = _BY_NAME[name](**kw)
+    if name in ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf"):
+        new.constant_factor = calc.constant_factor
+    return new

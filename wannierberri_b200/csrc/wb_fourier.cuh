@@ -1,0 +1,167 @@
+// R -> k transform as a pruned, separable 3-D DFT.
+//
+// Reference: Rvectors.apply_expdK / derivative / R_to_k (fourier/rvectors.py:477-506) and
+// FFT_R_to_k.__call__ (fourier/fft.py:133-192).  Same mathematics, different algorithm:
+//   X(k) = sum_R X_R exp(2 pi i R.(kappa + dK)),   kappa = (m0/N0, m1/N1, m2/N2)
+// factorises over the three lattice directions because the K-block shift dK enters the phase
+// exactly like kappa does.  The R-vectors live in a small box (n0 x n1 x n2, 7^3 for bcc Fe), so
+// three passes of a dense n_d -> N_d transform along one axis cost ~(n0+...) complex MACs per
+// output element instead of nR = 95 for the direct sum, with perfectly coalesced traffic: the
+// innermost ("inner") index of every pass is the packed matrix-element index of the record.
+//
+// The R-space table is built once per plan (wb_build_rtable_kernel): derivative (x i(R+t_j-t_i)),
+// curl of A and the hermitisation  X -> (X + X^dagger)/2  are linear and commute with the
+// transform, so they are applied in R-space and only the upper triangle of hermitised channels
+// is ever transformed.
+#pragma once
+#include "wb_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// R-space table:  table[(r0*n1 + r1)*n2 + r2][e],  r_d = R_d - rmin_d,  e = record element.
+// One thread per (iR, i, j).  Accumulates with atomics (runs once per plan; duplicates in iRvec
+// and the R <-> -R folding of the hermitisation both add up, like the scatter-add of fft.py:177).
+// ------------------------------------------------------------------------------------------
+struct WbRInputs {
+    const cplx* Ham;   // [nR][nw][nw]
+    const cplx* AA;    // [nR][nw][nw][3]
+    const cplx* BB;
+    const cplx* CC;
+    const cplx* SS;
+    const double* T;   // [nR][nw][nw][3]  cRvec_shifted
+    const int* iRvec;  // [nR][3]
+};
+
+__device__ __forceinline__ void atomic_cadd(cplx* p, cplx v) {
+    atomicAdd(&p->x, v.x);
+    atomicAdd(&p->y, v.y);
+}
+
+// add X_R[i][j] to a hermitised channel: half to (R; i,j) if i<=j, half conj to (-R; j,i) if j<=i
+__device__ __forceinline__ void add_herm(cplx* table, long cellR, long cellmR, int E, int off, int i, int j,
+                                         int nw, cplx v) {
+    if (i <= j) atomic_cadd(&table[cellR * E + off + tri_index(i, j, nw)], cscale(0.5, v));
+    if (j <= i) atomic_cadd(&table[cellmR * E + off + tri_index(j, i, nw)], cscale(0.5, cconj(v)));
+}
+
+__global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rmin, int3 nbox, cplx* table) {
+    const int nw = L.nw;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)nR * nw * nw;
+    if (idx >= total) return;
+    int j = idx % nw;
+    int i = (idx / nw) % nw;
+    int iR = idx / ((long)nw * nw);
+    int R0 = in.iRvec[3 * iR], R1 = in.iRvec[3 * iR + 1], R2 = in.iRvec[3 * iR + 2];
+    long cellR = ((long)(R0 - rmin.x) * nbox.y + (R1 - rmin.y)) * nbox.z + (R2 - rmin.z);
+    long cellmR = ((long)(-R0 - rmin.x) * nbox.y + (-R1 - rmin.y)) * nbox.z + (-R2 - rmin.z);
+    const int E = L.E;
+    double T[3];
+    for (int a = 0; a < 3; a++) T[a] = in.T[idx * 3 + a];
+
+    if (in.Ham) {
+        cplx h = in.Ham[idx];
+        add_herm(table, cellR, cellmR, E, L.off_H, i, j, nw, h);
+        if (L.off_dH[0] >= 0) {
+            for (int a = 0; a < 3; a++)  // i * T_a * H   (rvectors.py:487-494)
+                atomic_cadd(&table[cellR * E + L.off_dH[a] + i * nw + j], cmake(-T[a] * h.y, T[a] * h.x));
+        }
+    }
+    if (in.AA && L.off_A[0] >= 0) {
+        cplx A[3];
+        for (int a = 0; a < 3; a++) {
+            A[a] = in.AA[idx * 3 + a];
+            add_herm(table, cellR, cellmR, E, L.off_A[a], i, j, nw, A[a]);
+        }
+        if (L.off_O[0] >= 0) {
+            for (int c = 0; c < 3; c++) {  // i (T_alpha A_beta - T_beta A_alpha)   (data_K_R.py:48-51)
+                int al = WB_ALPHA(c), be = WB_BETA(c);
+                cplx d = cmake(T[al] * A[be].x - T[be] * A[al].x, T[al] * A[be].y - T[be] * A[al].y);
+                add_herm(table, cellR, cellmR, E, L.off_O[c], i, j, nw, cmake(-d.y, d.x));
+            }
+        }
+    }
+    if (in.BB && L.off_B[0] >= 0)
+        for (int a = 0; a < 3; a++) atomic_cadd(&table[cellR * E + L.off_B[a] + i * nw + j], in.BB[idx * 3 + a]);
+    if (in.CC && L.off_C[0] >= 0)
+        for (int a = 0; a < 3; a++) atomic_cadd(&table[cellR * E + L.off_C[a] + i * nw + j], in.CC[idx * 3 + a]);
+    if (in.SS && L.off_S[0] >= 0)
+        for (int a = 0; a < 3; a++) add_herm(table, cellR, cellmR, E, L.off_S[a], i, j, nw, in.SS[idx * 3 + a]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Twiddles  W_d[b][k][r] = exp(2 pi i (rmin_d + r) (k / N_d + dK[b][d]))
+// The k/N part is reduced exactly in integers (mod N) before going to floating point.
+// ------------------------------------------------------------------------------------------
+__global__ void wb_twiddle_kernel(const double* __restrict__ dK, int nb, int N, int n, int rmin, int d,
+                                  cplx* __restrict__ W) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)nb * N * n;
+    if (idx >= total) return;
+    int r = idx % n;
+    int k = (idx / n) % N;
+    int b = idx / ((long)n * N);
+    int R = rmin + r;
+    int rk = (int)((((long)R * k) % N + N) % N);
+    double frac = (double)rk / (double)N + (double)R * dK[3 * b + d];
+    double s, c;
+    sincospi(2.0 * frac, &s, &c);
+    W[idx] = cmake(c, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// One pass of the separable transform along one axis:
+//   out[b][o][k][t] = sum_r W[b][k][r] * in[b][o][r][t]      o < outer, r < n, k < N, t < S
+// Thread = one inner index t and KC consecutive outputs k; the block shares (b, o, k-chunk), so
+// the twiddles are a warp-uniform broadcast from shared memory and every global access is a fully
+// coalesced 16-byte-per-lane stream.  4*KC DFMA per 16-byte load.
+// ------------------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(256)
+wb_axis_dft_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, const cplx* __restrict__ W,
+                   int n, int N, long S, int outer, long in_bstride, long out_bstride) {
+    extern __shared__ cplx w_s[];  // [KC][n]
+    const int nchunk = (N + KC - 1) / KC;
+    const int o = blockIdx.y / nchunk;
+    const int k0 = (blockIdx.y % nchunk) * KC;
+    const int b = blockIdx.z;
+    for (int x = threadIdx.x; x < KC * n; x += blockDim.x) {
+        int kk = x / n, r = x % n;
+        w_s[x] = (k0 + kk < N) ? W[((long)b * N + (k0 + kk)) * n + r] : cmake(0., 0.);
+    }
+    __syncthreads();
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S) return;
+    const cplx* src = in + (long)b * in_bstride + (long)o * n * S + t;
+    cplx acc[KC];
+#pragma unroll
+    for (int kk = 0; kk < KC; kk++) acc[kk] = cmake(0., 0.);
+    for (int r = 0; r < n; r++) {
+        cplx v = __ldg(src + (long)r * S);
+#pragma unroll
+        for (int kk = 0; kk < KC; kk++) cfma(acc[kk], w_s[kk * n + r], v);
+    }
+    cplx* dst = out + (long)b * out_bstride + ((long)o * N + k0) * S + t;
+#pragma unroll
+    for (int kk = 0; kk < KC; kk++)
+        if (k0 + kk < N) dst[(long)kk * S] = acc[kk];
+}
+
+// k-points of a K-block, bit-identical to the reference:
+//   points_FFT = ix * (1./N)   (grid/grid.py:68-75) ;  kpoints_all = (points_FFT + dK) % 1  (data_K.py:146-151)
+__global__ void wb_kpoints_kernel(const double* __restrict__ dK, int3 N, double* __restrict__ kpts) {
+    int ik = blockIdx.x * blockDim.x + threadIdx.x;
+    int nk = N.x * N.y * N.z;
+    if (ik >= nk) return;
+    int iz = ik % N.z, iy = (ik / N.z) % N.y, ix = ik / (N.z * N.y);
+    int idx[3] = {ix, iy, iz};
+    int NN[3] = {N.x, N.y, N.z};
+    for (int d = 0; d < 3; d++) {
+        double dk = 1. / (double)NN[d];
+        double v = __dmul_rn((double)idx[d], dk);
+        v = __dadd_rn(v, dK[d]);
+        // python's float % 1 for v >= 0 is fmod(v, 1); for v < 0 it adds 1 when the remainder is non-zero
+        double m = fmod(v, 1.0);
+        if (m < 0) m = __dadd_rn(m, 1.0);
+        kpts[3 * ik + d] = m;
+    }
+}

@@ -1,0 +1,576 @@
+// libwbgpu.so -- C-ABI (include/wbgpu.h) and host-side orchestration of the sm_100a kernels.
+//
+// One context = one System_R replica resident on one GPU.  A scan call walks the K-block list in
+// batches ("launches") sized to the workspace: twiddles -> 3 axis passes of the separable R->k
+// transform -> eigensolver -> rotation+formula events -> histogram accumulation; the per-spec
+// histograms stay on the device until the last batch, then one finalize kernel per spec.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/wbgpu.h"
+#include "wb_common.cuh"
+#include "wb_fourier.cuh"
+#include "wb_eigh_jacobi.cuh"
+#include "wb_groups.cuh"
+#include "wb_rotate_formula.cuh"
+#include "wb_scan.cuh"
+
+static thread_local std::string g_err;
+
+static int set_err(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return set_err("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__,  \
+                           cudaGetErrorString(e__));                                                 \
+    } while (0)
+
+struct wbgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int nw = 0, nR = 0;
+    double cell_volume = 0;
+    int* d_iRvec = nullptr;
+    double* d_T = nullptr;
+    cplx* d_XR[WBGPU_NKEYS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int3 rmin{0, 0, 0}, nbox{1, 1, 1};
+    // plan
+    bool planned = false;
+    int N[3] = {1, 1, 1};
+    uint32_t mask = 0;
+    int external = 1;
+    WbLayout L;
+    cplx* d_table = nullptr;
+    long nk_block = 1;
+    int nb_max = 1;  // K-blocks per launch
+    // workspace
+    cplx* d_W[3] = {nullptr, nullptr, nullptr};
+    cplx *d_Z = nullptr, *d_Y = nullptr, *d_X = nullptr, *d_U = nullptr;
+    double *d_E = nullptr, *d_evlabel = nullptr, *d_evval = nullptr;
+    double *d_hist = nullptr, *d_cum = nullptr;
+    size_t hist_cap = 0;
+    double *d_dK = nullptr, *d_weight = nullptr, *d_out = nullptr;
+    size_t dK_cap = 0, out_cap = 0;
+    int* d_sweeps = nullptr;
+    int last_sweeps = 0;
+    int64_t launches = 0;
+    int eig_method = 0;
+    int smem_optin = 0;
+};
+
+static void free_plan(wbgpu_ctx* c) {
+    cudaFree(c->d_table);
+    for (int d = 0; d < 3; d++) cudaFree(c->d_W[d]);
+    cudaFree(c->d_Z); cudaFree(c->d_Y); cudaFree(c->d_X); cudaFree(c->d_U);
+    cudaFree(c->d_E); cudaFree(c->d_evlabel); cudaFree(c->d_evval);
+    c->d_table = nullptr;
+    for (int d = 0; d < 3; d++) c->d_W[d] = nullptr;
+    c->d_Z = c->d_Y = c->d_X = c->d_U = nullptr;
+    c->d_E = c->d_evlabel = c->d_evval = nullptr;
+    c->planned = false;
+}
+
+extern "C" const char* wbgpu_last_error(void) { return g_err.c_str(); }
+extern "C" int wbgpu_version(void) { return 100; }
+extern "C" int wbgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int wbgpu_create(wbgpu_ctx** out, int device, int nw, int nR, const int32_t* iRvec,
+                            const double* cRvec_shifted, double cell_volume, void* stream) {
+    if (!out || !iRvec || !cRvec_shifted) return set_err("wbgpu_create: null pointer argument");
+    if (nw < 1 || nw > 128) return set_err("wbgpu_create: num_wann=%d outside the supported range 1..128", nw);
+    if (nR < 1) return set_err("wbgpu_create: nR=%d", nR);
+    int ndev = wbgpu_device_count();
+    if (ndev == 0) return set_err("wbgpu_create: no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err("wbgpu_create: device %d out of range (have %d)", device, ndev);
+    CK(cudaSetDevice(device));
+    wbgpu_ctx* c = new wbgpu_ctx();
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    c->nw = nw;
+    c->nR = nR;
+    c->cell_volume = cell_volume;
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int i = 0; i < nR; i++)
+        for (int d = 0; d < 3; d++) {
+            // the box is symmetric under R -> -R so that hermitisation can be done in R-space
+            int a = abs(iRvec[3 * i + d]);
+            hi[d] = std::max(hi[d], a);
+            lo[d] = std::min(lo[d], -a);
+        }
+    c->rmin = make_int3(lo[0], lo[1], lo[2]);
+    c->nbox = make_int3(hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, hi[2] - lo[2] + 1);
+    CK(cudaMalloc(&c->d_iRvec, sizeof(int) * 3 * nR));
+    CK(cudaMalloc(&c->d_T, sizeof(double) * 3 * (size_t)nR * nw * nw));
+    CK(cudaMemcpy(c->d_iRvec, iRvec, sizeof(int) * 3 * nR, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_T, cRvec_shifted, sizeof(double) * 3 * (size_t)nR * nw * nw, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_sweeps, sizeof(int)));
+    CK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    *out = c;
+    return 0;
+}
+
+extern "C" int wbgpu_destroy(wbgpu_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_plan(c);
+    cudaFree(c->d_iRvec); cudaFree(c->d_T); cudaFree(c->d_sweeps);
+    for (int k = 0; k < WBGPU_NKEYS; k++) cudaFree(c->d_XR[k]);
+    cudaFree(c->d_hist); cudaFree(c->d_cum); cudaFree(c->d_dK); cudaFree(c->d_weight); cudaFree(c->d_out);
+    delete c;
+    return 0;
+}
+
+extern "C" int wbgpu_set_R_matrix(wbgpu_ctx* c, int key, const double* X_R, int ncart) {
+    if (!c || !X_R) return set_err("wbgpu_set_R_matrix: null pointer argument");
+    if (key < 0 || key >= WBGPU_NKEYS) return set_err("wbgpu_set_R_matrix: unknown key %d", key);
+    int want = (key == WBGPU_HAM) ? 1 : 3;
+    if (ncart != want) return set_err("wbgpu_set_R_matrix: key %d needs ncart=%d, got %d", key, want, ncart);
+    CK(cudaSetDevice(c->device));
+    size_t bytes = sizeof(cplx) * (size_t)c->nR * c->nw * c->nw * ncart;
+    if (!c->d_XR[key]) CK(cudaMalloc(&c->d_XR[key], bytes));
+    CK(cudaMemcpy(c->d_XR[key], X_R, bytes, cudaMemcpyHostToDevice));
+    c->planned = false;  // tables must be rebuilt
+    return 0;
+}
+
+extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) return set_err("wbgpu_set_option: null pointer argument");
+    if (!strcmp(name, "eig_method")) { c->eig_method = (int)value; return 0; }
+    return set_err("wbgpu_set_option: unknown option '%s'", name);
+}
+
+extern "C" int64_t wbgpu_kernel_launches(const wbgpu_ctx* c) { return c ? c->launches : 0; }
+extern "C" int wbgpu_last_eig_sweeps(const wbgpu_ctx* c) { return c ? c->last_sweeps : 0; }
+
+static int formula_rank(int f) {
+    switch (f) {
+        case WBGPU_IDENTITY: return 0;
+        case WBGPU_OMEGA: case WBGPU_MORB_HPM: case WBGPU_SPIN: return 1;
+        case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: return 2;
+    }
+    return -1;
+}
+static int formula_ncomp(int f) {
+    int r = formula_rank(f);
+    return r == 0 ? 1 : r == 1 ? 3 : 9;
+}
+static int fder_extra(int fder) { return fder == 0 ? 0 : (fder <= 2 ? 1 : 2); }
+
+extern "C" int64_t wbgpu_spec_size(const wbgpu_scan_spec* s) {
+    if (!s || formula_rank(s->formula) < 0) return -1;
+    return (int64_t)s->nEF * formula_ncomp(s->formula);
+}
+
+static WbWindow make_window(const wbgpu_scan_spec& s) {
+    WbWindow w;
+    int extra = fder_extra(s.fder);
+    w.dEF = s.dEF;
+    w.EFmin = s.Ef_first - extra * s.dEF;  // static.py:56-57
+    w.EFmax = s.Ef_last + extra * s.dEF;
+    w.nEFx = s.nEF + 2 * extra;
+    w.degen_thresh = s.degen_thresh;
+    w.degen_Kramers = s.degen_Kramers;
+    w.sea = (s.fder == 0);
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------ plan
+extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula_mask, int external_terms,
+                          int64_t max_kpoints_per_launch) {
+    if (!c || !NKFFT) return set_err("wbgpu_plan: null pointer argument");
+    for (int d = 0; d < 3; d++)
+        if (NKFFT[d] < 1) return set_err("wbgpu_plan: NKFFT[%d]=%d", d, NKFFT[d]);
+    if (!c->d_XR[WBGPU_HAM]) return set_err("wbgpu_plan: R-matrix 'Ham' is not set");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_plan(c);
+    const int nw = c->nw;
+    const uint32_t m = formula_mask;
+    auto has = [&](int f) { return (m >> f) & 1u; };
+    bool need_dH = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
+                   has(WBGPU_VEL_SPIN);
+    bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS);
+    bool need_A = berry && external_terms;
+    bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS)) && external_terms;
+    bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN);
+    if (need_A && !c->d_XR[WBGPU_AA]) return set_err("wbgpu_plan: R-matrix 'AA' is not set (needed for external terms)");
+    if (need_BC && (!c->d_XR[WBGPU_BB] || !c->d_XR[WBGPU_CC])) return set_err("wbgpu_plan: R-matrices 'BB','CC' are not set");
+    if (need_S && !c->d_XR[WBGPU_SS]) return set_err("wbgpu_plan: R-matrix 'SS' is not set");
+
+    WbLayout L;
+    L.nw = nw;
+    L.ntri = nw * (nw + 1) / 2;
+    int off = 0;
+    auto take = [&](bool herm) { int o = off; off += herm ? L.ntri : nw * nw; return o; };
+    L.off_H = take(true);
+    for (int a = 0; a < 3; a++) L.off_dH[a] = need_dH ? take(false) : -1;
+    for (int a = 0; a < 3; a++) L.off_A[a] = need_A ? take(true) : -1;
+    for (int a = 0; a < 3; a++) L.off_O[a] = need_A ? take(true) : -1;
+    for (int a = 0; a < 3; a++) L.off_B[a] = need_BC ? take(false) : -1;
+    for (int a = 0; a < 3; a++) L.off_C[a] = need_BC ? take(false) : -1;
+    for (int a = 0; a < 3; a++) L.off_S[a] = need_S ? take(true) : -1;
+    L.E = off;
+    c->L = L;
+    c->mask = m;
+    c->external = external_terms;
+    for (int d = 0; d < 3; d++) c->N[d] = NKFFT[d];
+    c->nk_block = (long)NKFFT[0] * NKFFT[1] * NKFFT[2];
+
+    // R-space table
+    size_t ncell = (size_t)c->nbox.x * c->nbox.y * c->nbox.z;
+    CK(cudaMalloc(&c->d_table, sizeof(cplx) * ncell * L.E));
+    CK(cudaMemsetAsync(c->d_table, 0, sizeof(cplx) * ncell * L.E, c->stream));
+    WbRInputs in;
+    in.Ham = c->d_XR[WBGPU_HAM];
+    in.AA = need_A ? c->d_XR[WBGPU_AA] : nullptr;
+    in.BB = need_BC ? c->d_XR[WBGPU_BB] : nullptr;
+    in.CC = need_BC ? c->d_XR[WBGPU_CC] : nullptr;
+    in.SS = need_S ? c->d_XR[WBGPU_SS] : nullptr;
+    in.T = c->d_T;
+    in.iRvec = c->d_iRvec;
+    long total = (long)c->nR * nw * nw;
+    wb_build_rtable_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(in, L, c->nR, c->rmin, c->nbox, c->d_table);
+    c->launches++;
+    CK(cudaGetLastError());
+
+    // workspace: bytes per k-point of one launch
+    const int n0 = c->nbox.x, n1 = c->nbox.y, n2 = c->nbox.z;
+    const double N0 = NKFFT[0], N1 = NKFFT[1];
+    double per_k = 16.0 * L.E * (1.0 + n0 / N0 + (double)n0 * n1 / (N0 * N1)) + 16.0 * nw * nw + 8.0 * nw * 11 + 64;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    long kmax = (long)(0.45 * (double)free_b / per_k);
+    long want = max_kpoints_per_launch > 0 ? (long)max_kpoints_per_launch : 262144;
+    kmax = std::min(kmax, want);
+    long nb = std::max(1L, kmax / c->nk_block);
+    nb = std::min(nb, 65535L);
+    c->nb_max = (int)nb;
+    size_t nkl = (size_t)nb * c->nk_block;
+    if ((double)nkl * per_k > 0.9 * (double)free_b)
+        return set_err("wbgpu_plan: one K-block of %ld k-points needs %.1f GB, only %.1f GB free", c->nk_block,
+                       nkl * per_k / 1e9, free_b / 1e9);
+    int nbx[3] = {n0, n1, n2};
+    for (int d = 0; d < 3; d++) CK(cudaMalloc(&c->d_W[d], sizeof(cplx) * nb * NKFFT[d] * nbx[d]));
+    CK(cudaMalloc(&c->d_Z, sizeof(cplx) * nb * (size_t)n0 * n1 * NKFFT[2] * L.E));
+    CK(cudaMalloc(&c->d_Y, sizeof(cplx) * nb * (size_t)n0 * NKFFT[1] * NKFFT[2] * L.E));
+    CK(cudaMalloc(&c->d_X, sizeof(cplx) * nkl * L.E));
+    CK(cudaMalloc(&c->d_U, sizeof(cplx) * nkl * nw * nw));
+    CK(cudaMalloc(&c->d_E, sizeof(double) * nkl * nw));
+    CK(cudaMalloc(&c->d_evlabel, sizeof(double) * nkl * nw));
+    CK(cudaMalloc(&c->d_evval, sizeof(double) * nkl * nw * 9));
+    CK(cudaStreamSynchronize(c->stream));
+    c->planned = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ stages
+static int pick_kc(int N) {
+    for (int kc = 10; kc >= 4; kc--)
+        if (N % kc == 0) return kc;
+    if (N <= 10) return N;
+    return 8;
+}
+
+template <int KC>
+static void launch_axis(wbgpu_ctx* c, const cplx* in, cplx* out, const cplx* W, int n, int N, long S, int outer,
+                        long in_bs, long out_bs, int nb) {
+    int nchunk = (N + KC - 1) / KC;
+    dim3 grid((unsigned)((S + 255) / 256), (unsigned)(outer * nchunk), (unsigned)nb);
+    wb_axis_dft_kernel<KC><<<grid, 256, sizeof(cplx) * KC * n, c->stream>>>(in, out, W, n, N, S, outer, in_bs, out_bs);
+    c->launches++;
+}
+
+static int axis_dft(wbgpu_ctx* c, const cplx* in, cplx* out, const cplx* W, int n, int N, long S, int outer,
+                    long in_bs, long out_bs, int nb) {
+    if ((long)outer * ((N + 3) / 4) > 65535) return set_err("axis_dft: grid.y overflow");
+    switch (pick_kc(N)) {
+#define WB_CASE(K) case K: launch_axis<K>(c, in, out, W, n, N, S, outer, in_bs, out_bs, nb); break;
+        WB_CASE(1) WB_CASE(2) WB_CASE(3) WB_CASE(4) WB_CASE(5) WB_CASE(6) WB_CASE(7) WB_CASE(8) WB_CASE(9) WB_CASE(10)
+#undef WB_CASE
+        default: return set_err("axis_dft: bad KC");
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// R->k for `nb` K-blocks whose shifts are dK_dev[nb][3]: fills c->d_X[nb][nk][E]
+static int run_fourier(wbgpu_ctx* c, const double* dK_dev, int nb) {
+    const int n[3] = {c->nbox.x, c->nbox.y, c->nbox.z};
+    const int rm[3] = {c->rmin.x, c->rmin.y, c->rmin.z};
+    const int* N = c->N;
+    const long E = c->L.E;
+    for (int d = 0; d < 3; d++) {
+        long total = (long)nb * N[d] * n[d];
+        wb_twiddle_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(dK_dev, nb, N[d], n[d], rm[d], d, c->d_W[d]);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    // axis 2: table[r0][r1][r2][e] -> Z[b][r0][r1][k2][e]
+    if (axis_dft(c, c->d_table, c->d_Z, c->d_W[2], n[2], N[2], E, n[0] * n[1], 0, (long)n[0] * n[1] * N[2] * E, nb)) return 1;
+    // axis 1: -> Y[b][r0][k1][k2][e]
+    if (axis_dft(c, c->d_Z, c->d_Y, c->d_W[1], n[1], N[1], (long)N[2] * E, n[0], (long)n[0] * n[1] * N[2] * E,
+                 (long)n[0] * N[1] * N[2] * E, nb)) return 1;
+    // axis 0: -> X[b][k0][k1][k2][e]
+    if (axis_dft(c, c->d_Y, c->d_X, c->d_W[0], n[0], N[0], (long)N[1] * N[2] * E, 1, (long)n[0] * N[1] * N[2] * E,
+                 (long)N[0] * N[1] * N[2] * E, nb)) return 1;
+    return 0;
+}
+
+static int run_eigh(wbgpu_ctx* c, long nk, bool want_U) {
+    const int nw = c->nw;
+    CK(cudaMemsetAsync(c->d_sweeps, 0, sizeof(int), c->stream));
+    {
+        constexpr int WARPS = 4;
+        int npair = (nw + 1) / 2;
+        size_t smem = sizeof(cplx) * WARPS * (size_t)(2 * nw * (nw + 1) + 2 * npair + nw);
+        if ((int)smem > c->smem_optin) return set_err("eigh(Jacobi): num_wann=%d needs %zu B shared memory", nw, smem);
+        CK(cudaFuncSetAttribute(wb_eigh_jacobi_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long nblk = std::min((nk + WARPS - 1) / WARPS, 148L * 64);
+        wb_eigh_jacobi_kernel<WARPS><<<(unsigned)nblk, WARPS * 32, smem, c->stream>>>(c->d_X, c->L, nk, c->d_E,
+                                                                                 want_U ? c->d_U : nullptr, c->d_sweeps);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int run_events(wbgpu_ctx* c, const wbgpu_scan_spec& s, long nk) {
+    const int nw = c->nw;
+    WbWindow win = make_window(s);
+    if (s.formula == WBGPU_IDENTITY) {
+        int per = ((nw * (2 * 8 + 2 * 2)) + 7) / 8 * 8;
+        int nt = 64;
+        wb_identity_events_kernel<<<(unsigned)((nk + nt - 1) / nt), nt, (size_t)per * nt, c->stream>>>(c->d_E, nw, nk, win, c->d_evlabel,
+                                                                                                 c->d_evval);
+        c->launches++;
+    } else if (s.formula == WBGPU_OMEGA) {
+        if (c->L.off_dH[0] < 0 || (s.external_terms && c->L.off_A[0] < 0))
+            return set_err("scan: the plan does not hold the channels formula %d needs", s.formula);
+        constexpr int NT = 128;
+        size_t smem = sizeof(cplx) * (size_t)(9 * nw * nw + 3 * nw) + sizeof(double) * 5 * nw + sizeof(short) * 2 * nw + 16;
+        if ((int)smem > c->smem_optin) return set_err("rotate(generic): num_wann=%d needs %zu B shared memory", nw, smem);
+        CK(cudaFuncSetAttribute(wb_omega_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WbFormulaFlags fl{s.formula, s.internal_terms, s.external_terms};
+        long nblk = std::min(nk, 148L * 32);
+        wb_omega_events_kernel<NT><<<(unsigned)nblk, NT, smem, c->stream>>>(c->d_X, c->L, nk, c->d_E, c->d_U, win, fl,
+                                                                        c->d_evlabel, c->d_evval);
+        c->launches++;
+    } else {
+        return set_err("scan: formula %d is not implemented on the GPU path yet", s.formula);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int ensure(double** p, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    cudaFree(*p);
+    *p = nullptr;
+    CK(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+static int check_spec(const wbgpu_ctx* c, const wbgpu_scan_spec& s) {
+    if (formula_rank(s.formula) < 0) return set_err("scan: unknown formula %d", s.formula);
+    if (s.fder < 0 || s.fder > 3) return set_err("scan: Derivatives d^%df/dE^%d is not implemented", s.fder, s.fder);
+    if (s.nEF < 1) return set_err("scan: nEF=%d", s.nEF);
+    if (!(s.dEF > 0)) return set_err("scan: dEF must be positive (Efermi must be an increasing uniform grid)");
+    if (!((c->mask >> s.formula) & 1u)) return set_err("scan: formula %d was not declared in wbgpu_plan", s.formula);
+    return 0;
+}
+
+extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK_dev, const double* weight_dev,
+                                     const wbgpu_scan_spec* specs, int nspec, double* out_dev) {
+    if (!c || !dK_dev || !weight_dev || !specs || !out_dev) return set_err("wbgpu_static_scan: null pointer argument");
+    if (!c->planned) return set_err("wbgpu_static_scan: call wbgpu_plan first");
+    if (nblocks < 0 || nspec < 1) return set_err("wbgpu_static_scan: nblocks=%d nspec=%d", nblocks, nspec);
+    CK(cudaSetDevice(c->device));
+    std::vector<size_t> hoff(nspec + 1, 0);
+    size_t cum_max = 0;
+    for (int i = 0; i < nspec; i++) {
+        if (check_spec(c, specs[i])) return 1;
+        WbWindow w = make_window(specs[i]);
+        size_t sz = (size_t)(w.nEFx + 1) * formula_ncomp(specs[i].formula);
+        hoff[i + 1] = hoff[i] + sz;
+        cum_max = std::max(cum_max, sz);
+    }
+    size_t need = sizeof(double) * (hoff[nspec] + cum_max);
+    if (ensure(&c->d_hist, &c->hist_cap, need)) return 1;
+    CK(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * hoff[nspec], c->stream));
+    double* d_cum = c->d_hist + hoff[nspec];
+    const int nw = c->nw;
+    bool need_U = false;
+    for (int i = 0; i < nspec; i++) need_U |= (specs[i].formula != WBGPU_IDENTITY);
+
+    for (int b0 = 0; b0 < nblocks; b0 += c->nb_max) {
+        int nb = std::min(c->nb_max, nblocks - b0);
+        long nk = (long)nb * c->nk_block;
+        if (run_fourier(c, dK_dev + 3 * (size_t)b0, nb)) return 1;
+        if (run_eigh(c, nk, need_U)) return 1;
+        for (int i = 0; i < nspec; i++) {
+            const wbgpu_scan_spec& s = specs[i];
+            if (run_events(c, s, nk)) return 1;
+            WbWindow w = make_window(s);
+            int ncomp = formula_ncomp(s.formula);
+            size_t hbytes = sizeof(double) * (size_t)(w.nEFx + 1) * ncomp;
+            int use_smem = hbytes <= 96 * 1024;
+            if (use_smem)
+                CK(cudaFuncSetAttribute(wb_scan_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            long nslots = nk * nw;
+            long nblk = std::min((nslots + 255) / 256, 148L * 2);
+            wb_scan_accumulate_kernel<<<(unsigned)nblk, 256, use_smem ? hbytes : 0, c->stream>>>(
+                c->d_evlabel, c->d_evval, nslots, (int)(c->nk_block * nw), weight_dev + b0, ncomp, w, c->d_hist + hoff[i], use_smem);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    size_t ooff = 0;
+    for (int i = 0; i < nspec; i++) {
+        const wbgpu_scan_spec& s = specs[i];
+        WbWindow w = make_window(s);
+        int ncomp = formula_ncomp(s.formula);
+        double scale = s.factor / (c->cell_volume * (double)c->nk_block);
+        wb_scan_finalize_kernel<<<(ncomp + 31) / 32, 32, 0, c->stream>>>(c->d_hist + hoff[i], d_cum, ncomp, w.nEFx, s.nEF, s.fder,
+                                                                       s.dEF, scale, out_dev + ooff);
+        c->launches++;
+        ooff += (size_t)s.nEF * ncomp;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int wbgpu_static_scan(wbgpu_ctx* c, int nblocks, const double* dK, const double* weight,
+                                 const wbgpu_scan_spec* specs, int nspec, double* out) {
+    if (!c || !dK || !weight || !specs || !out) return set_err("wbgpu_static_scan: null pointer argument");
+    CK(cudaSetDevice(c->device));
+    size_t nout = 0;
+    for (int i = 0; i < nspec; i++) {
+        int64_t sz = wbgpu_spec_size(&specs[i]);
+        if (sz < 0) return set_err("scan: unknown formula %d", specs[i].formula);
+        nout += (size_t)sz;
+    }
+    if (ensure(&c->d_dK, &c->dK_cap, sizeof(double) * 4 * (size_t)std::max(nblocks, 1))) return 1;
+    if (ensure(&c->d_out, &c->out_cap, sizeof(double) * nout)) return 1;
+    double* d_w = c->d_dK + 3 * (size_t)std::max(nblocks, 1);
+    CK(cudaMemcpyAsync(c->d_dK, dK, sizeof(double) * 3 * nblocks, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_w, weight, sizeof(double) * nblocks, cudaMemcpyHostToDevice, c->stream));
+    if (wbgpu_static_scan_dev(c, nblocks, c->d_dK, d_w, specs, nspec, c->d_out)) return 1;
+    CK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ probes
+static int probe_prepare(wbgpu_ctx* c, const double dK[3]) {
+    if (!c || !dK) return set_err("probe: null pointer argument");
+    if (!c->planned) return set_err("probe: call wbgpu_plan first");
+    CK(cudaSetDevice(c->device));
+    if (ensure(&c->d_dK, &c->dK_cap, sizeof(double) * 4)) return 1;
+    CK(cudaMemcpyAsync(c->d_dK, dK, sizeof(double) * 3, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int wbgpu_kpoints(wbgpu_ctx* c, const double dK[3], double* kpoints) {
+    if (!kpoints) return set_err("wbgpu_kpoints: null pointer argument");
+    if (probe_prepare(c, dK)) return 1;
+    long nk = c->nk_block;
+    if (ensure(&c->d_out, &c->out_cap, sizeof(double) * 3 * nk)) return 1;
+    wb_kpoints_kernel<<<(unsigned)((nk + 127) / 128), 128, 0, c->stream>>>(c->d_dK, make_int3(c->N[0], c->N[1], c->N[2]), c->d_out);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(kpoints, c->d_out, sizeof(double) * 3 * nk, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int wbgpu_eig(wbgpu_ctx* c, const double dK[3], double* E, double* U) {
+    if (!E) return set_err("wbgpu_eig: null pointer argument");
+    if (probe_prepare(c, dK)) return 1;
+    long nk = c->nk_block;
+    if (run_fourier(c, c->d_dK, 1)) return 1;
+    if (run_eigh(c, nk, U != nullptr)) return 1;
+    CK(cudaMemcpyAsync(E, c->d_E, sizeof(double) * nk * c->nw, cudaMemcpyDeviceToHost, c->stream));
+    if (U) CK(cudaMemcpyAsync(U, c->d_U, sizeof(cplx) * nk * c->nw * c->nw, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->last_sweeps, c->d_sweeps, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int wbgpu_xk(wbgpu_ctx* c, const double dK[3], int channel, double* X) {
+    if (!X) return set_err("wbgpu_xk: null pointer argument");
+    if (probe_prepare(c, dK)) return 1;
+    const WbLayout& L = c->L;
+    const int nw = c->nw;
+    const int* offs = nullptr;
+    bool herm = false;
+    int ncart = 3;
+    switch (channel) {
+        case WBGPU_CH_HAM: offs = &L.off_H; herm = true; ncart = 1; break;
+        case WBGPU_CH_DHAM: offs = L.off_dH; break;
+        case WBGPU_CH_AA: offs = L.off_A; herm = true; break;
+        case WBGPU_CH_ROTAA: offs = L.off_O; herm = true; break;
+        case WBGPU_CH_BB: offs = L.off_B; break;
+        case WBGPU_CH_CC: offs = L.off_C; break;
+        case WBGPU_CH_SS: offs = L.off_S; herm = true; break;
+        default: return set_err("wbgpu_xk: unknown channel %d", channel);
+    }
+    if (offs[0] < 0) return set_err("wbgpu_xk: channel %d is not part of the current plan", channel);
+    long nk = c->nk_block;
+    if (run_fourier(c, c->d_dK, 1)) return 1;
+    std::vector<cplx> rec((size_t)nk * L.E);
+    CK(cudaMemcpyAsync(rec.data(), c->d_X, sizeof(cplx) * rec.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cplx* out = (cplx*)X;  // unpacking of the parity probe's output (layout only, no arithmetic)
+    for (long ik = 0; ik < nk; ik++)
+        for (int i = 0; i < nw; i++)
+            for (int j = 0; j < nw; j++)
+                for (int a = 0; a < ncart; a++) {
+                    const cplx* r = rec.data() + ik * L.E + offs[a];
+                    cplx v;
+                    if (!herm) v = r[i * nw + j];
+                    else if (i <= j) v = r[tri_index(i, j, nw)];
+                    else { v = r[tri_index(j, i, nw)]; v.y = -v.y; }
+                    out[((ik * nw + i) * nw + j) * ncart + a] = v;
+                }
+    return 0;
+}
+
+extern "C" int wbgpu_band_traces(wbgpu_ctx* c, const double dK[3], const wbgpu_scan_spec* spec, double* E_label,
+                                 double* value) {
+    if (!spec || !E_label || !value) return set_err("wbgpu_band_traces: null pointer argument");
+    if (probe_prepare(c, dK)) return 1;
+    if (check_spec(c, *spec)) return 1;
+    long nk = c->nk_block;
+    int ncomp = formula_ncomp(spec->formula);
+    if (run_fourier(c, c->d_dK, 1)) return 1;
+    if (run_eigh(c, nk, true)) return 1;
+    CK(cudaMemsetAsync(c->d_evval, 0, sizeof(double) * nk * c->nw * ncomp, c->stream));
+    if (run_events(c, *spec, nk)) return 1;
+    CK(cudaMemcpyAsync(E_label, c->d_evlabel, sizeof(double) * nk * c->nw, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(value, c->d_evval, sizeof(double) * nk * c->nw * ncomp, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}

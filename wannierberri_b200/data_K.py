@@ -1,0 +1,55 @@
+"""GPU-resident per-K-block state with the constructor signature of the reference's `Data_K_R`
+(data_K/data_K.py:73-83, data_K_R.py:11-22): `cls(system, dK=Kpoint.Kp_fullBZ, grid=grid, Kpoint=Kpoint, **parameters_K)`,
+so it can be passed as `data_k_class` and calculators can be called on it one K-block at a time."""
+import numpy as np
+
+from .engine import Engine
+
+_ENGINES = {}
+
+
+def engine_for(system, device=0):
+    key = (id(system), device)
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(system, device=device)
+    return _ENGINES[key]
+
+
+class Data_K_R:
+
+    def __init__(self, system, dK, grid, Kpoint=None, device=0, **parameters_K):
+        unknown = set(parameters_K) - {"fftlib"}
+        if unknown:
+            raise NotImplementedError(f"parameters_K {sorted(unknown)} are not implemented on the GPU path")
+        self.system = system
+        self.grid = grid
+        self.Kpoint = Kpoint
+        self.dK = np.array(dK, dtype=float)
+        self.NKFFT = np.array(grid.FFT, dtype=int)
+        self.nk = int(np.prod(self.NKFFT))
+        self.num_wann = system.num_wann
+        self.cell_volume = system.cell_volume
+        self.force_internal_terms_only = getattr(system, "force_internal_terms_only", False)
+        self.engine = engine_for(system, device)
+
+    def _plan(self, formulae, external_terms=True):
+        from . import _lib
+        self.engine.plan(self.NKFFT, set(formulae) | {_lib.IDENTITY}, external_terms=external_terms)
+
+    def scan(self, specs, external_terms=True):
+        if self.force_internal_terms_only:
+            for s in specs:
+                s.external_terms = 0
+            external_terms = False
+        self._plan([s.formula for s in specs], external_terms)
+        return self.engine.scan(self.dK[None, :], np.ones(1), specs)
+
+    @property
+    def kpoints_all(self):
+        self._plan([])
+        return self.engine.kpoints(self.dK)
+
+    @property
+    def E_K(self):
+        self._plan([])
+        return self.engine.eig(self.dK)

@@ -1,0 +1,11 @@
+"""Physical prefactors multiplying the final arrays on the host (reference: factors.py:1-25),
+from scipy.constants like the reference."""
+from scipy.constants import elementary_charge, hbar, electron_mass, physical_constants, angstrom
+
+bohr_magneton = elementary_charge * hbar / (2 * electron_mass)
+bohr = physical_constants['Bohr radius'][0] / angstrom
+eV_au = physical_constants['electron volt-hartree relationship'][0]
+factor_morb_evA2_to_muB = -(elementary_charge * angstrom ** 2) * elementary_charge / (2 * hbar) / bohr_magneton
+factor_gme_orb = factor_morb_evA2_to_muB * bohr_magneton / angstrom ** 2
+factor_gme_spin = -bohr_magneton / angstrom ** 2
+factor_ahc = -(elementary_charge ** 2 / hbar / angstrom)

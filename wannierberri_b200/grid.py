@@ -1,0 +1,90 @@
+"""k-grid: NK = NKdiv x NKFFT, the K-block list and the FFT sub-grid (bit-exact restatement of
+grid/grid.py:68-75,149-172,196-266 and grid/Kpoint.py:75-77 of the reference, without symmetry
+reduction -- symmetry-reduced K-lists built by the reference's own Grid are accepted by `run()`)."""
+import warnings
+
+import numpy as np
+
+
+def _one2three(x):
+    if x is None:
+        return None
+    if isinstance(x, (int, np.integer)):
+        return np.array([x, x, x], dtype=int)
+    x = np.array(x, dtype=int)
+    assert x.shape == (3,)
+    return x
+
+
+class KpointBZ:
+    """One K-block: `K` (reduced coordinates of the K-grid), shift of the FFT sub-grid `Kp_fullBZ`,
+    weight `factor` (grid/Kpoint.py:20-38,75-77)."""
+
+    def __init__(self, K, dK, NKFFT, factor, refinement_level=0):
+        self.K = np.copy(K)
+        self.dK = np.copy(dK)
+        self.NKFFT = np.copy(NKFFT)
+        self.factor = factor
+        self.refinement_level = refinement_level
+
+    @property
+    def Kp_fullBZ(self):
+        return self.K / self.NKFFT
+
+
+class Grid:
+
+    def __init__(self, system=None, NK=None, NKFFT=None, NKdiv=None, length=None, use_symmetry=False):
+        NKdiv, NKFFT, NK = _one2three(NKdiv), _one2three(NKFFT), _one2three(NK)
+        if length is not None and NK is None:
+            recip = 2 * np.pi * np.linalg.inv(system.real_lattice).T
+            NK = np.array(np.round(length / (2 * np.pi) * np.linalg.norm(recip, axis=1)), dtype=int)
+        if (NKdiv is not None) and (NKFFT is not None):
+            pass
+        elif NK is not None:
+            if NKFFT is None:
+                # autoNK (grid.py:196-212) without point-group constraints: the smallest FFT grid
+                # between NKFFT_recommended and 2x that whose multiple is closest to NK
+                rec = np.array(system.NKFFT_recommended)
+                cands = np.array([[x, y, z] for x in range(rec[0], 2 * rec[0]) for y in range(rec[1], 2 * rec[1])
+                                  for z in range(rec[2], 2 * rec[2])])
+                div = np.array(np.round(NK[None, :] / cands), dtype=int)
+                div[div <= 0] = 1
+                change = div * cands / NK[None, :]
+                change[change > 1] = 1. / change[change > 1]
+                NKFFT = cands[np.argmax(change.min(axis=1))]
+            NKdiv = np.array(np.round(NK / NKFFT), dtype=int)
+            NKdiv[NKdiv <= 0] = 1
+        else:
+            raise ValueError("you need to specify either NK or a pair (NKdiv,NKFFT) or (NK,NKFFT)."
+                             f"found NK={NK}, NKdiv={NKdiv}, NKFFT={NKFFT} ")
+        if NK is not None and not np.all(NK == NKFFT * NKdiv):
+            warnings.warn(f" the requested k-grid {NK} was adjusted to {NKFFT * NKdiv}. ")
+        self.div = NKdiv
+        self.FFT = NKFFT
+
+    @property
+    def dense(self):
+        return self.div * self.FFT
+
+    @property
+    def points_FFT(self):
+        dkx, dky, dkz = 1. / self.FFT
+        ix, iy, iz = np.meshgrid(np.arange(self.FFT[0]), np.arange(self.FFT[1]), np.arange(self.FFT[2]), indexing="ij")
+        return np.stack([ix.ravel() * dkx, iy.ravel() * dky, iz.ravel() * dkz], axis=1)
+
+    def K_arrays(self):
+        """(Kp_fullBZ[nK,3], factor[nK]) of the full K-list, x-major / z-fastest, same floating
+        point operations as the reference: K = [x,y,z] * (1./div); Kp_fullBZ = K / FFT."""
+        dK = 1. / self.div
+        factor = 1. / np.prod(self.div)
+        x, y, z = np.meshgrid(np.arange(self.div[0]), np.arange(self.div[1]), np.arange(self.div[2]), indexing="ij")
+        K = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1) * dK[None, :]
+        return K / self.FFT[None, :], np.full(K.shape[0], factor)
+
+    def get_K_list(self, use_symmetry=False, k_batch=None):
+        if use_symmetry:
+            raise NotImplementedError("symmetry-reduced K-lists are built by the reference's Grid; pass that grid to run()")
+        dK = 1. / self.div
+        shifts, factors = self.K_arrays()
+        return [KpointBZ(K=s * self.FFT, dK=dK, NKFFT=self.FFT, factor=f) for s, f in zip(shifts, factors)]

@@ -1,0 +1,104 @@
+"""`run()` with the signature of the reference (run_grid.py:118-142).  The K-block loop
+(`process`, run_grid.py:32-115) and its Ray fan-out are replaced by: shard the K-block list over the
+ranks of `torch.distributed` (one process per GPU), evaluate each shard with ONE call into
+libwbgpu.so, combine with ONE all-reduce of the Fermi-scan arrays."""
+import numpy as np
+
+from .calculators.static import adapt
+from .data_K import engine_for
+from .result import ResultDict
+from .system import as_system
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except ImportError:
+        pass
+    return None
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous chunk [lo, hi) of n K-blocks for `rank` of `world`."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def k_list_arrays(grid, use_irred_kpt):
+    """(Kp_fullBZ[nK,3], factor[nK]) from this package's Grid or from the reference's."""
+    if hasattr(grid, "K_arrays") and not use_irred_kpt:
+        return grid.K_arrays()
+    K_list = grid.get_K_list(use_symmetry=use_irred_kpt)
+    return (np.array([K.Kp_fullBZ for K in K_list], dtype=float).reshape(-1, 3),
+            np.array([K.factor for K in K_list], dtype=float))
+
+
+def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetrize=False, fout_name="result",
+        suffix="", parameters_K=None, file_Klist_path=None, restart=False, allow_restart=False, dump_results=False,
+        restart_iteration=-1, Klist_part=10, parallel=True, print_Kpoints=False, adpt_mesh=2, adpt_fac=1,
+        print_progress_step_time=5, print_progress_step_percent=1, data_k_class=None, k_batch=50,
+        device=None, write_files=False):
+    """Integrate `calculators` over the k-grid.  Returns a `ResultDict` of `EnergyResult`.
+
+    Not implemented on the GPU path (raise, never fall back to a CPU loop): adaptive refinement,
+    restart files, symmetrisation of the result."""
+    if adpt_num_iter != 0:
+        raise NotImplementedError("adaptive refinement needs per-K-block results (SURVEY.md section 8(f), next-3)")
+    if restart or allow_restart or dump_results:
+        raise NotImplementedError("restart / dump_results are not implemented on the GPU path")
+    if symmetrize:
+        raise NotImplementedError("symmetrize=True: apply system.pointgroup.symmetrize() of the reference to the result")
+    if parameters_K:
+        raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
+    system = as_system(system)
+    calcs = {}
+    for key, c in calculators.items():
+        c = adapt(c)
+        if not c.allow_grid:
+            raise ValueError(f"Calculator {key} is not compatible with a grid")
+        calcs[key] = c
+
+    dist = _dist() if parallel else None
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    if device is None:
+        import torch
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+    shifts, factors = k_list_arrays(grid, use_irred_kpt)
+    lo, hi = shard_bounds(len(factors), rank, world)
+
+    specs, owner = [], []
+    for key, c in calcs.items():
+        for s in c.specs():
+            if getattr(system, "force_internal_terms_only", False):
+                s.external_terms = 0
+            specs.append(s)
+            owner.append(key)
+    external = any(s.external_terms for s in specs)
+    engine = engine_for(system, device)
+    engine.plan(np.array(grid.FFT, dtype=int), {int(s.formula) for s in specs}, external_terms=external)
+    arrays = engine.scan(shifts[lo:hi], factors[lo:hi], specs)
+
+    if dist and world > 1:
+        import torch
+        flat = np.concatenate([a.ravel() for a in arrays])
+        dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(flat).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        flat = t.cpu().numpy()
+        off = 0
+        for i, a in enumerate(arrays):
+            arrays[i] = flat[off:off + a.size].reshape(a.shape)
+            off += a.size
+
+    results = {}
+    for key, c in calcs.items():
+        mine = [a for a, o in zip(arrays, owner) if o == key]
+        results[key] = c.result(mine, system.cell_volume)
+    res = ResultDict(results)
+    if write_files and rank == 0:
+        res.savedata(prefix=fout_name, suffix=suffix, i_iter=0)
+    return res

@@ -1,0 +1,81 @@
+"""Input container mirroring the part of `System_R` that the hot path reads
+(reference: system/system_R.py:83,106-175; system/system.py:173-181; fourier/rvectors.py:351-369).
+
+Model construction (Wannier90 / tb.dat readers, symmetrisation, ...) is out of scope: build the
+system with the reference and hand it to `run()` -- any object with `.rvec.iRvec`,
+`.rvec.cRvec_shifted`, `.get_R_mat(key)`, `.has_R_mat(key)`, `.num_wann`, `.cell_volume` is accepted
+(see `as_system`) -- or load the arrays with `System_R.from_arrays / from_npz`."""
+import numpy as np
+
+
+class _Rvec:
+    """The two attributes of `Rvectors` that the path needs."""
+
+    def __init__(self, iRvec, cRvec_shifted):
+        self.iRvec = np.ascontiguousarray(iRvec, dtype=np.int32)
+        self.cRvec_shifted = np.ascontiguousarray(cRvec_shifted, dtype=np.float64)
+        self.nRvec = self.iRvec.shape[0]
+
+
+class System_R:
+
+    def __init__(self, real_lattice, iRvec, wannier_centers_cart, force_internal_terms_only=False, periodic=(True,) * 3):
+        self.real_lattice = np.array(real_lattice, dtype=float)
+        self.wannier_centers_cart = np.array(wannier_centers_cart, dtype=float)
+        self.num_wann = self.wannier_centers_cart.shape[0]
+        self.periodic = np.array(periodic, dtype=bool)
+        self.force_internal_terms_only = force_internal_terms_only
+        self.is_phonon = False
+        iRvec = np.array(iRvec, dtype=int)
+        t = self.wannier_centers_cart
+        cR = iRvec.dot(self.real_lattice)
+        # R + t_j - t_i   (rvectors.py:355-369)
+        self.rvec = _Rvec(iRvec, cR[:, None, None, :] + (t[None, :, :] - t[:, None, :])[None])
+        self._XX_R = {}
+
+    # --- system_R.py:106-175
+    def set_R_mat(self, key, value, reset=False):
+        value = np.ascontiguousarray(value, dtype=np.complex128)
+        if value.shape[:3] != (self.rvec.nRvec, self.num_wann, self.num_wann):
+            raise ValueError(f"R-matrix {key} has shape {value.shape}, expected "
+                             f"({self.rvec.nRvec},{self.num_wann},{self.num_wann},...)")
+        if key in self._XX_R and not reset:
+            raise RuntimeError(f"setting {key} for the second time without explicit permission. smth is wrong")
+        self._XX_R[key] = value
+
+    def get_R_mat(self, key):
+        try:
+            return self._XX_R[key]
+        except KeyError:
+            raise ValueError(f"The real-space matrix elements '{key}' are not set in the system")
+
+    def has_R_mat(self, key):
+        return key in self._XX_R
+
+    @property
+    def cell_volume(self):
+        return abs(np.linalg.det(self.real_lattice))
+
+    @property
+    def NKFFT_recommended(self):
+        """system_R.py:591-597: 1 + 2 max|R_i|."""
+        return 2 * np.abs(self.rvec.iRvec).max(axis=0) + 1
+
+    @classmethod
+    def from_npz(cls, path):
+        """Load the compact fixture format written by tests/golden/make_golden.py."""
+        f = np.load(path)
+        s = cls(f["real_lattice"], f["iRvec"], f["wannier_centers_cart"])
+        for k in f.files:
+            if k.startswith("XX_R_"):
+                s.set_R_mat(k[5:], f[k])
+        return s
+
+
+def as_system(obj):
+    """Accept this package's `System_R` or the reference's (duck typing on the attributes read by
+    the path: SURVEY.md section 2, row 9)."""
+    for attr in ("rvec", "get_R_mat", "has_R_mat", "num_wann", "cell_volume"):
+        if not hasattr(obj, attr):
+            raise ValueError(f"system object lacks attribute '{attr}' needed by the GPU path")
+    return obj
