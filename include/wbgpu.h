@@ -124,6 +124,22 @@ int wbgpu_xk(wbgpu_ctx* ctx, const double dK[3], int channel, double* X /*comple
 int wbgpu_band_traces(wbgpu_ctx* ctx, const double dK[3], const wbgpu_scan_spec* spec,
                       double* E_label, double* value);
 
+/* stages of one batch of K-blocks, for wbgpu_stage_times */
+enum {
+    WBGPU_STAGE_FOURIER = 0,  /* twiddles + 3 axis passes of the R->k transform */
+    WBGPU_STAGE_EIGH = 1,     /* batched Hermitian eigensolver */
+    WBGPU_STAGE_ROTATE = 2,   /* U^dagger X U + formula -> band-group events */
+    WBGPU_STAGE_IDENTITY = 3, /* band groups of the Identity formula */
+    WBGPU_STAGE_SCAN = 4,     /* histogram accumulation */
+    WBGPU_NSTAGES = 5
+};
+/* With option "timing" = 1 every stage of every batch is bracketed by CUDA events on the context's
+ * stream; accumulated device milliseconds and the number of timed stage instances since the option
+ * was set.  ms[WBGPU_NSTAGES], calls[WBGPU_NSTAGES]. */
+int wbgpu_stage_times(const wbgpu_ctx* ctx, double* ms, int64_t* calls);
+/* FP64 peak probes for the roofline denominator: kind 0 = DFMA, 1 = DMMA (mma.sync m8n8k4). TFLOP/s. */
+int wbgpu_fp64_peak(int device, int kind, double* tflops);
+
 /* counters since context creation */
 int64_t wbgpu_kernel_launches(const wbgpu_ctx* ctx);
 /* last eigensolver launch: max Jacobi sweeps over k-points (diagnostic) */

@@ -21,6 +21,7 @@
 #include "wb_groups.cuh"
 #include "wb_rotate_formula.cuh"
 #include "wb_scan.cuh"
+#include "wb_probe.cuh"
 
 static thread_local std::string g_err;
 
@@ -73,7 +74,42 @@ struct wbgpu_ctx {
     int64_t launches = 0;
     int eig_method = 0;
     int smem_optin = 0;
+    // optional per-stage device timing (option "timing"): events around each stage of each batch
+    int timing = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, int>> ev_used;  // (stage, index of start event); stop = index + 1
+    size_t ev_next = 0;
+    double stage_ms[WBGPU_NSTAGES] = {0, 0, 0, 0, 0};
+    int64_t stage_calls[WBGPU_NSTAGES] = {0, 0, 0, 0, 0};
 };
+
+static void stage_begin(wbgpu_ctx* c, int stage) {
+    if (!c->timing) return;
+    while (c->ev_pool.size() < c->ev_next + 2) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+    }
+    c->ev_used.push_back({stage, (int)c->ev_next});
+    cudaEventRecord(c->ev_pool[c->ev_next], c->stream);
+}
+static void stage_end(wbgpu_ctx* c) {
+    if (!c->timing) return;
+    cudaEventRecord(c->ev_pool[c->ev_next + 1], c->stream);
+    c->ev_next += 2;
+}
+static void stage_collect(wbgpu_ctx* c) {
+    if (!c->timing || c->ev_used.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& u : c->ev_used) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev_pool[u.second], c->ev_pool[u.second + 1]);
+        c->stage_ms[u.first] += ms;
+        c->stage_calls[u.first]++;
+    }
+    c->ev_used.clear();
+    c->ev_next = 0;
+}
 
 static void free_plan(wbgpu_ctx* c) {
     cudaFree(c->d_table);
@@ -158,6 +194,11 @@ extern "C" int wbgpu_set_R_matrix(wbgpu_ctx* c, int key, const double* X_R, int 
 extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return set_err("wbgpu_set_option: null pointer argument");
     if (!strcmp(name, "eig_method")) { c->eig_method = (int)value; return 0; }
+    if (!strcmp(name, "timing")) {
+        c->timing = (int)value;
+        for (int i = 0; i < WBGPU_NSTAGES; i++) { c->stage_ms[i] = 0; c->stage_calls[i] = 0; }
+        return 0;
+    }
     return set_err("wbgpu_set_option: unknown option '%s'", name);
 }
 
@@ -428,11 +469,18 @@ extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK
     for (int b0 = 0; b0 < nblocks; b0 += c->nb_max) {
         int nb = std::min(c->nb_max, nblocks - b0);
         long nk = (long)nb * c->nk_block;
+        stage_begin(c, WBGPU_STAGE_FOURIER);
         if (run_fourier(c, dK_dev + 3 * (size_t)b0, nb)) return 1;
+        stage_end(c);
+        stage_begin(c, WBGPU_STAGE_EIGH);
         if (run_eigh(c, nk, need_U)) return 1;
+        stage_end(c);
         for (int i = 0; i < nspec; i++) {
             const wbgpu_scan_spec& s = specs[i];
+            stage_begin(c, s.formula == WBGPU_IDENTITY ? WBGPU_STAGE_IDENTITY : WBGPU_STAGE_ROTATE);
             if (run_events(c, s, nk)) return 1;
+            stage_end(c);
+            stage_begin(c, WBGPU_STAGE_SCAN);
             WbWindow w = make_window(s);
             int ncomp = formula_ncomp(s.formula);
             size_t hbytes = sizeof(double) * (size_t)(w.nEFx + 1) * ncomp;
@@ -444,6 +492,7 @@ extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK
             wb_scan_accumulate_kernel<<<(unsigned)nblk, 256, use_smem ? hbytes : 0, c->stream>>>(
                 c->d_evlabel, c->d_evval, nslots, (int)(c->nk_block * nw), weight_dev + b0, ncomp, w, c->d_hist + hoff[i], use_smem);
             c->launches++;
+            stage_end(c);
             CK(cudaGetLastError());
         }
     }
@@ -459,6 +508,46 @@ extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK
         ooff += (size_t)s.nEF * ncomp;
     }
     CK(cudaGetLastError());
+    stage_collect(c);
+    return 0;
+}
+
+extern "C" int wbgpu_stage_times(const wbgpu_ctx* c, double* ms, int64_t* calls) {
+    if (!c || !ms || !calls) return set_err("wbgpu_stage_times: null pointer argument");
+    for (int i = 0; i < WBGPU_NSTAGES; i++) { ms[i] = c->stage_ms[i]; calls[i] = c->stage_calls[i]; }
+    return 0;
+}
+
+// FP64 peak probes: kind 0 = DFMA (vector pipe), 1 = DMMA (mma.sync.m8n8k4.f64).  Returns TFLOP/s.
+extern "C" int wbgpu_fp64_peak(int device, int kind, double* tflops) {
+    if (!tflops) return set_err("wbgpu_fp64_peak: null pointer argument");
+    if (wbgpu_device_count() == 0) return set_err("wbgpu_fp64_peak: no CUDA device available");
+    CK(cudaSetDevice(device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* d_out;
+    CK(cudaMalloc(&d_out, 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    constexpr int CH = 8;
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0));
+        if (kind == 0) wb_dfma_probe_kernel<CH><<<blocks, threads>>>(d_out, iters, 1.0000001, 1e-9);
+        else wb_dmma_probe_kernel<CH><<<blocks, threads>>>(d_out, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = (kind == 0) ? 2.0 * CH * iters * (double)blocks * threads
+                                   : 2.0 * 8 * 8 * 4 * CH * iters * (double)blocks * (threads / 32);
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *tflops = best;
     return 0;
 }
 
