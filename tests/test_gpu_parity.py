@@ -107,6 +107,28 @@ def test_eigh(wb, fe, te, fe_orc, te_orc, orc, which):
     assert unit < 1e-12
 
 
+@pytest.mark.parametrize("nw,degenerate", [(1, False), (2, False), (3, False), (8, True), (9, False), (16, False),
+                                           (17, False), (24, True), (32, False), (33, False), (40, False)])
+def test_eigh_sizes_and_degeneracies(wb, nw, degenerate):
+    """Both eigensolvers (Householder+QL for nw <= 32, Jacobi otherwise / on request) against LAPACK on
+    random Hermitian models, including exactly degenerate spectra."""
+    sysg = wb.synthetic_system(nw, rmax=1, seed=nw, matrices=("Ham",), degenerate_pairs=degenerate)
+    NKFFT, dK = [3, 2, 4], [0.03, 0.01, 0.2]
+    from wannierberri_b200 import _lib
+    for method in ((2, 1) if nw <= 32 else (1,)):
+        eng = wb.Engine(sysg)
+        eng.set_option("eig_method", method)
+        eng.plan(NKFFT, [_lib.IDENTITY])
+        E, U = eng.eig(dK, vectors=True)
+        H = eng.xk(dK, "Ham")
+        Eref = np.linalg.eigvalsh(H)
+        assert relerr(E, Eref) < 1e-12, (nw, method)
+        resid = np.abs(np.einsum("kij,kjn->kin", H, U) - U * E[:, None, :]).max()
+        assert resid < 1e-11 * max(np.abs(H).max(), 1.), (nw, method, resid)
+        unit = np.abs(np.einsum("kin,kim->knm", U.conj(), U) - np.eye(nw)).max()
+        assert unit < 1e-12, (nw, method, unit)
+
+
 def test_eigh_golden_block(wb, fe):
     b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
     eng = wb.Engine(fe)

@@ -1,0 +1,127 @@
+"""CPU-only tests: the C-ABI library loads and exports what include/wbgpu.h declares, the host logic
+(grid, calculators, sharding, multi-rank reduction over gloo) behaves like the reference's."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+import wannierberri_b200 as wb
+from wannierberri_b200 import _lib
+from wannierberri_b200.run import shard_bounds
+
+
+def test_library_exports_header_symbols():
+    header = open(os.path.join(ROOT, "include", "wbgpu.h")).read()
+    declared = set(re.findall(r"\b(wbgpu_[A-Za-z0-9_]+)\s*\(", header))
+    declared -= {"wbgpu_ctx"}
+    assert declared, "no declarations parsed"
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/wbgpu.h but not exported by libwbgpu.so"
+    assert set(_lib.EXPORTED) <= declared
+    assert L.wbgpu_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly."""
+    if _lib.lib().wbgpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        wb.Engine(fe)
+    with pytest.raises(RuntimeError):
+        wb.run(fe, wb.Grid(fe, NK=4, NKFFT=2), dict(dos=wb.calculators.static.DOS(Efermi=np.linspace(0, 1, 3))))
+
+
+def test_grid_bit_exact():
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+    g = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    grid = wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2])
+    assert list(grid.div) == [2, 2, 2] and list(grid.FFT) == [2, 2, 2]
+    shifts, factors = grid.K_arrays()
+    assert np.array_equal(shifts, g["K_list_Kp_fullBZ"])
+    assert np.array_equal(factors, g["K_list_factor"])
+    assert np.array_equal(grid.points_FFT, g["points_FFT"])
+    K = grid.get_K_list()
+    assert np.array_equal(np.array([k.Kp_fullBZ for k in K]), g["K_list_Kp_fullBZ"])
+    # awkward sizes: same floating point operations as the oracle's restatement of grid.py
+    from oracle import wb_oracle as orc
+    for div, fft in (([3, 5, 7], [4, 6, 9]), ([20, 20, 20], [20, 20, 20]), ([1, 1, 1], [12, 12, 12])):
+        s, f = wb.Grid(fe, NKdiv=div, NKFFT=fft).K_arrays()
+        so, fo = orc.K_list(div, fft)
+        assert np.array_equal(s, so) and np.array_equal(f, fo)
+        assert np.array_equal(wb.Grid(fe, NKdiv=div, NKFFT=fft).points_FFT, orc.points_FFT(fft))
+
+
+def test_grid_determineNK():
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+    assert list(fe.NKFFT_recommended) == [7, 7, 7]
+    g = wb.Grid(fe, NK=48, NKFFT=12)
+    assert list(g.div) == [4, 4, 4] and list(g.dense) == [48, 48, 48]
+    with pytest.warns(UserWarning):
+        g = wb.Grid(fe, NK=50, NKFFT=12)
+    assert list(g.dense) == [48, 48, 48]
+    with pytest.raises(ValueError):
+        wb.Grid(fe)
+    g = wb.Grid(fe, NK=56)
+    assert np.all(g.dense == 56)
+
+
+def test_calculator_windows_and_errors():
+    st = wb.calculators.static
+    Ef = np.linspace(12., 22., 1001)
+    a = st.AHC(Efermi=Ef)
+    s = a.specs()[0]
+    assert (s.formula, s.fder, s.nEF) == (_lib.OMEGA, 0, 1001)
+    assert a.EFmin == Ef[0] and a.nEF_extra == 1001
+    d = st.DOS(Efermi=Ef)
+    assert d.nEF_extra == 1003 and d.EFmin == Ef[0] - (Ef[1] - Ef[0])
+    m = st.Morb(Efermi=Ef)
+    assert [x.formula for x in m.specs()] == [_lib.MORB_HPM, _lib.OMEGA]
+    assert st.AHC(Efermi=Ef, hole_like=True).constant_factor == -a.constant_factor
+    assert st.AHC(Efermi=Ef, use_factor=False).specs()[0].factor == -1.0
+    for bad in (dict(tetra=True), dict(k_resolved=True), dict(select_bands=[1]), dict(Emin=0.)):
+        with pytest.raises(NotImplementedError):
+            st.AHC(Efermi=Ef, **bad)
+    with pytest.raises(ValueError):
+        st.AHC(Efermi=5.0)
+
+
+def test_shard_bounds():
+    for n in (0, 1, 7, 64, 8000):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                lo, hi = shard_bounds(n, r, world)
+                got += list(range(lo, hi))
+            assert got == list(range(n))
+
+
+def test_result_algebra():
+    E = np.linspace(0, 1, 5)
+    a = wb.EnergyResult(E, np.ones((5, 3)))
+    b = (a * 2 + a) - a
+    assert np.allclose(b.data, 2.0)
+    assert (None + a if False else a.__radd__(None)) is a
+    with pytest.raises(RuntimeError):
+        a + wb.EnergyResult(E + 1, np.ones((5, 3)))
+    d = a.as_dict()
+    assert set(d) >= {"data", "Energies_0", "E_titles", "rank", "transformTR", "transformInv", "comment"}
+
+
+def test_two_rank_gloo_run():
+    """world_size=2 over gloo on CPU: K-block sharding + one all-reduce reproduces the fixture.
+    The GPU engine is replaced by a test double that evaluates shards with the oracle."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29577")
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2"], env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert "PARITY OK" in outs[0]

@@ -21,8 +21,9 @@ __device__ __forceinline__ void rr_pair(int n, int s, int m, int& p, int& q) {
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-wb_eigh_jacobi_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, double* __restrict__ Eout,
-                      cplx* __restrict__ Uout, int* __restrict__ max_sweeps) {
+wb_eigh_jacobi_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk_in, double* __restrict__ Eout,
+                      cplx* __restrict__ Uout, int* __restrict__ max_sweeps, const int* __restrict__ list,
+                      const int* __restrict__ nlist) {
     extern __shared__ cplx smem_j[];
     const int nw = L.nw;
     const int ld = nw + 1;  // padded leading dimension
@@ -36,7 +37,10 @@ wb_eigh_jacobi_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, double*
     cplx* rot_ph = rot_cs + npair;     // e^{i phi}
     double* ev = (double*)(rot_ph + npair);
 
-    for (long ik = (long)blockIdx.x * WARPS + warp; ik < nk; ik += (long)gridDim.x * WARPS) {
+    // either all k-points k0 .. k0+nk_in-1, or the ones listed in list[0 .. *nlist-1] (relative to k0)
+    const long nk = list ? (long)(*nlist) : nk_in;
+    for (long idx = (long)blockIdx.x * WARPS + warp; idx < nk; idx += (long)gridDim.x * WARPS) {
+        const long ik = k0 + (list ? (long)list[idx] : idx);
         const cplx* H = rec + ik * L.E + L.off_H;
         double nrm2 = 0.;
         for (int x = lane; x < nw * nw; x += 32) {

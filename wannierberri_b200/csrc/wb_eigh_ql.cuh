@@ -1,0 +1,302 @@
+// Batched complex Hermitian eigensolver for nw <= 32: Householder tridiagonalisation + implicit
+// QL + back-transformation, split so that every phase keeps all 32 lanes (or as many as the
+// matrix size allows) on USEFUL FP64 work and nothing scalar is replicated across a warp:
+//
+//   K1  wb_tridiag_kernel      warp per k-point, lane i = row i of A held in REGISTERS (static
+//                              indexing, fully unrolled).  A -> (d, e, tau, Householder vectors).
+//   K2  wb_tql_kernel          THREAD per k-point: implicit-shift QL on the real tridiagonal
+//                              (d, e); the Givens rotations (c, s) of every sweep are streamed
+//                              to memory instead of being applied to a matrix.
+//   K3  wb_eigvec_kernel       warp per k-point, lane i = row i of Z (real, registers): replay the
+//                              rotation stream; sort; transpose through shared memory; lane j = column j:
+//                              apply the Householder reflectors in reverse; write E (ascending), U.
+//
+// Replaces  E_K, UU_K = np.linalg.eigh(HH_K)   (data_K/data_K.py:211-218, 309-322).  The maths is the
+// classic zhetd2 + tql2 + zunm2l sequence (LAPACK / EISPACK), restated for this layout.
+// A k-point whose QL iteration exceeds the stream capacity is flagged and re-solved by the
+// Jacobi kernel (wb_eigh_jacobi.cuh).
+#pragma once
+#include "wb_common.cuh"
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ cplx shfl_c(cplx v, int src) {
+    return cmake(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+// ------------------------------------------------------------------------------------------ K1
+// Output: d[ik][nw], e[ik][nw] (e[nw-1] = 0), tau[ik][nw], V = A rows (Householder vector k in
+// column k, rows k+2..nw-1) written to Vout[ik][nw][nw].
+template <int NWP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+wb_tridiag_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, double* __restrict__ dout,
+                  double* __restrict__ eout, cplx* __restrict__ tauout, cplx* __restrict__ Vout) {
+    __shared__ cplx vs_all[WARPS][32];
+    __shared__ cplx ws_all[WARPS][32];
+    const int nw = L.nw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    cplx* vs = vs_all[warp];
+    cplx* ws = ws_all[warp];
+    long t = (long)blockIdx.x * WARPS + warp;
+    if (t >= nk) return;
+    long ik = k0 + t;
+    const cplx* H = rec + ik * L.E + L.off_H;
+    cplx a[NWP];
+#pragma unroll
+    for (int j = 0; j < NWP; j++) {
+        a[j] = cmake(0., 0.);
+        if (j < nw && lane < nw) {
+            a[j] = (lane <= j) ? H[tri_index(lane, j, nw)] : cconj(H[tri_index(j, lane, nw)]);
+            if (j == lane) a[j].y = 0.;
+        }
+    }
+    double* d = dout + t * nw;
+    double* e = eout + t * nw;
+    cplx* tau_o = tauout + t * nw;
+#pragma unroll
+    for (int k = 0; k < NWP - 1; k++) {
+        if (k < nw - 1) {  // uniform
+            cplx xk = a[k];  // column k: element of row `lane`
+            double sq = (lane > k + 1 && lane < nw) ? (xk.x * xk.x + xk.y * xk.y) : 0.;
+            double xnorm2 = warp_sum(sq);
+            cplx alpha = shfl_c(xk, k + 1);
+            cplx tau = cmake(0., 0.);
+            double beta = alpha.x;
+            cplx v = cmake(0., 0.);
+            if (xnorm2 != 0. || alpha.y != 0.) {  // zlarfg
+                beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xnorm2), alpha.x);
+                tau = cmake((beta - alpha.x) / beta, -alpha.y / beta);
+                cplx den = cmake(alpha.x - beta, alpha.y);
+                double dn = 1. / (den.x * den.x + den.y * den.y);
+                cplx scale = cmake(den.x * dn, -den.y * dn);
+                if (lane > k + 1 && lane < nw) v = cmul(xk, scale);
+            }
+            if (lane == k + 1) v = cmake(1., 0.);
+            const bool active = (tau.x != 0. || tau.y != 0.);  // uniform
+            if (active) {
+                vs[lane] = v;
+                __syncwarp();
+                // x = tau * A v   (rows > k)
+                cplx x = cmake(0., 0.);
+#pragma unroll
+                for (int j = k + 1; j < NWP; j++)
+                    if (j < nw) cfma(x, a[j], vs[j]);
+                x = cmul(tau, x);
+                if (lane <= k || lane >= nw) x = cmake(0., 0.);
+                // dot = x^H v
+                cplx pd = cconjmul(x, v);
+                cplx dot = cmake(warp_sum(pd.x), warp_sum(pd.y));
+                cplx al2 = cscale(-0.5, cmul(tau, dot));
+                cplx w = cadd(x, cmul(al2, v));
+                ws[lane] = w;
+                __syncwarp();
+                // A -= v w^H + w v^H
+                if (lane > k && lane < nw) {
+#pragma unroll
+                    for (int j = k + 1; j < NWP; j++)
+                        if (j < nw) {
+                            cplx t1 = cmulc(v, ws[j]);
+                            cplx t2 = cmulc(w, vs[j]);
+                            a[j].x -= t1.x + t2.x;
+                            a[j].y -= t1.y + t2.y;
+                        }
+                }
+                __syncwarp();
+            }
+            // store the Householder vector in place (rows > k+1 of column k)
+            if (lane > k + 1) a[k] = v;
+            if (lane == k) d[k] = a[k].x;
+            if (lane == 0) { e[k] = beta; tau_o[k] = tau; }
+        }
+    }
+    if (lane == nw - 1) {
+#pragma unroll
+        for (int j = 0; j < NWP; j++)
+            if (j == nw - 1) d[j] = a[j].x;
+    }
+    if (lane == 0) { e[nw - 1] = 0.; tau_o[nw - 1] = cmake(0., 0.); }
+    if (lane < nw) {
+        cplx* Vrow = Vout + (ik * nw + lane) * nw;
+#pragma unroll
+        for (int j = 0; j < NWP; j++)
+            if (j < nw) Vrow[j] = a[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2
+// Implicit QL with Wilkinson-type shift (EISPACK tql2 / "tqli").  Thread per k-point.
+// Stream: rot[ik][capR] (c, s) in application order; hdr[ik][capS] = l | (m << 8) per sweep;
+// nsweep[ik] = number of sweeps, or -1 on overflow / non-convergence (=> Jacobi fallback).
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_tql_kernel(int nw, long nk, double* __restrict__ dio, const double* __restrict__ ein,
+              double2* __restrict__ rot, int capR, int* __restrict__ hdr, int capS, int* __restrict__ nsweep) {
+    extern __shared__ double smem_q[];  // d[nw][NT], e[nw][NT]
+    double* d = smem_q + threadIdx.x;
+    double* e = smem_q + (size_t)nw * NT + threadIdx.x;
+    long t = (long)blockIdx.x * NT + threadIdx.x;
+    if (t >= nk) return;
+    for (int i = 0; i < nw; i++) {
+        d[i * NT] = dio[t * nw + i];
+        e[i * NT] = ein[t * nw + i];
+    }
+    double2* myrot = rot + (size_t)t * capR;
+    int* myhdr = hdr + (size_t)t * capS;
+    int nr = 0, ns = 0;
+    bool fail = false;
+    for (int l = 0; l < nw && !fail; l++) {
+        int iter = 0;
+        while (true) {
+            int m = l;
+            for (; m < nw - 1; m++) {
+                double dd = fabs(d[m * NT]) + fabs(d[(m + 1) * NT]);
+                if (fabs(e[m * NT]) + dd == dd) break;
+            }
+            if (m == l) break;
+            if (++iter > 40 || ns >= capS || nr + (m - l) > capR) { fail = true; break; }
+            double el = e[l * NT];
+            double g = (d[(l + 1) * NT] - d[l * NT]) / (2. * el);
+            double r = hypot(g, 1.);
+            g = d[m * NT] - d[l * NT] + el / (g + copysign(r, g));
+            double s = 1., c = 1., p = 0.;
+            myhdr[ns++] = l | (m << 8);
+            int i = m - 1;
+            for (; i >= l; i--) {
+                double f = s * e[i * NT];
+                double b = c * e[i * NT];
+                r = hypot(f, g);
+                e[(i + 1) * NT] = r;
+                if (r == 0.) {  // recover from underflow: identity rotations for the rest of the sweep
+                    d[(i + 1) * NT] -= p;
+                    e[m * NT] = 0.;
+                    break;
+                }
+                s = f / r;
+                c = g / r;
+                g = d[(i + 1) * NT] - p;
+                r = (d[i * NT] - g) * s + 2. * c * b;
+                p = s * r;
+                d[(i + 1) * NT] = g + p;
+                g = c * r - b;
+                myrot[nr++] = make_double2(c, s);
+            }
+            if (i >= l) {  // broke out early: pad the sweep with identity rotations
+                for (; i >= l; i--) myrot[nr++] = make_double2(1., 0.);
+                continue;
+            }
+            d[l * NT] -= p;
+            e[l * NT] = g;
+            e[m * NT] = 0.;
+        }
+    }
+    for (int i = 0; i < nw; i++) dio[t * nw + i] = d[i * NT];
+    nsweep[t] = fail ? -1 : ns;
+}
+
+// ------------------------------------------------------------------------------------------ K3
+template <int NWP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+wb_eigvec_kernel(int nw, long k0, long nk, const double* __restrict__ dvals, const cplx* __restrict__ tauin,
+                 const double2* __restrict__ rot, int capR, const int* __restrict__ hdr, int capS,
+                 const int* __restrict__ nsweep, double* __restrict__ Eout, cplx* __restrict__ VU,
+                 int* __restrict__ fail_list, int* __restrict__ nfail) {
+    extern __shared__ cplx smem_v[];
+    // per warp: V[nw][nw] (Householder vectors), Zs[nw][nw+1] doubles (transpose), cs[32], tau[nw]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = nw * nw + (nw * (nw + 1) + 1) / 2 + 32 + nw;
+    cplx* V = smem_v + (size_t)warp * per_warp;
+    double* Zs = (double*)(V + nw * nw);
+    double2* cs = (double2*)(V + nw * nw + (nw * (nw + 1) + 1) / 2);
+    cplx* taus = (cplx*)(cs + 32);
+    long t = (long)blockIdx.x * WARPS + warp;
+    if (t >= nk) return;
+    long ik = k0 + t;
+    const int ns = nsweep[t];
+    if (ns < 0) {
+        if (lane == 0) fail_list[atomicAdd(nfail, 1)] = (int)t;
+        return;
+    }
+    // stage Householder data
+    for (int x = lane; x < nw * nw; x += 32) V[x] = VU[ik * nw * nw + x];
+    if (lane < nw) taus[lane] = tauin[t * nw + lane];
+    // ---- replay the rotation stream on Z = I (lane = row)
+    double z[NWP];
+#pragma unroll
+    for (int j = 0; j < NWP; j++) z[j] = (j == lane) ? 1. : 0.;
+    const double2* myrot = rot + (size_t)t * capR;
+    const int* myhdr = hdr + (size_t)t * capS;
+    int r0 = 0;
+    int h = (ns > 0) ? myhdr[0] : 0;
+    for (int s = 0; s < ns; s++) {
+        int l = h & 255, m = h >> 8;
+        int cnt = m - l;
+        __syncwarp();
+        if (lane < cnt) cs[lane] = myrot[r0 + lane];
+        if (s + 1 < ns) h = myhdr[s + 1];
+        __syncwarp();
+        r0 += cnt;
+#pragma unroll
+        for (int ii = 0; ii < NWP - 1; ii++) {
+            const int i = NWP - 2 - ii;
+            if (i < m && i >= l) {  // uniform
+                double2 q = cs[m - 1 - i];
+                double f = z[i + 1];
+                z[i + 1] = q.y * z[i] + q.x * f;
+                z[i] = q.x * z[i] - q.y * f;
+            }
+        }
+    }
+    // ---- sort: rank of eigenvalue `lane`
+    double myd = (lane < nw) ? dvals[t * nw + lane] : CUDART_INF;
+    int rank = 0;
+    for (int j = 0; j < nw; j++) {
+        double dj = __shfl_sync(0xffffffffu, myd, j);
+        rank += (dj < myd) || (dj == myd && j < lane);
+    }
+    if (lane < nw) Eout[ik * nw + rank] = myd;
+    // ---- transpose: lane j takes column j of Z
+    const int ldz = nw + 1;
+    __syncwarp();
+    if (lane < nw) {
+#pragma unroll
+        for (int j = 0; j < NWP; j++)
+            if (j < nw) Zs[lane * ldz + j] = z[j];
+    }
+    __syncwarp();
+    cplx u[NWP];
+#pragma unroll
+    for (int i = 0; i < NWP; i++) u[i] = cmake((i < nw && lane < nw) ? Zs[i * ldz + lane] : 0., 0.);
+    // ---- back-transformation  u <- H(0) H(1) ... H(nw-2) u   (apply in reverse order)
+#pragma unroll
+    for (int kk = 0; kk < NWP - 1; kk++) {
+        const int k = NWP - 2 - kk;
+        if (k < nw - 1) {
+            cplx tau = taus[k];
+            if (tau.x != 0. || tau.y != 0.) {  // uniform
+                cplx sdot = u[k + 1];  // v[k+1] = 1
+#pragma unroll
+                for (int i = k + 2; i < NWP; i++)
+                    if (i < nw) cfma_conj(sdot, V[i * nw + k], u[i]);
+                cplx ts = cmul(tau, sdot);
+                u[k + 1] = csub(u[k + 1], ts);
+#pragma unroll
+                for (int i = k + 2; i < NWP; i++)
+                    if (i < nw) {
+                        cplx vv = V[i * nw + k];
+                        u[i].x -= ts.x * vv.x - ts.y * vv.y;
+                        u[i].y -= ts.x * vv.y + ts.y * vv.x;
+                    }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < nw) {
+        cplx* Uo = VU + ik * nw * nw;
+#pragma unroll
+        for (int i = 0; i < NWP; i++)
+            if (i < nw) Uo[i * nw + rank] = u[i];
+    }
+}

@@ -18,6 +18,7 @@
 #include "wb_common.cuh"
 #include "wb_fourier.cuh"
 #include "wb_eigh_jacobi.cuh"
+#include "wb_eigh_ql.cuh"
 #include "wb_groups.cuh"
 #include "wb_rotate_formula.cuh"
 #include "wb_scan.cuh"
@@ -70,6 +71,14 @@ struct wbgpu_ctx {
     double *d_dK = nullptr, *d_weight = nullptr, *d_out = nullptr;
     size_t dK_cap = 0, out_cap = 0;
     int* d_sweeps = nullptr;
+    // Householder+QL eigensolver work space (per sub-batch of eig_chunk k-points)
+    long eig_chunk = 0;
+    int capR = 0, capS = 0;
+    double *d_dw = nullptr, *d_ew = nullptr;
+    cplx* d_tau = nullptr;
+    double2* d_rot = nullptr;
+    int *d_hdr = nullptr, *d_nsweep = nullptr, *d_faillist = nullptr, *d_nfail = nullptr;
+    int64_t eig_fallbacks = 0;
     int last_sweeps = 0;
     int64_t launches = 0;
     int eig_method = 0;
@@ -116,6 +125,10 @@ static void free_plan(wbgpu_ctx* c) {
     for (int d = 0; d < 3; d++) cudaFree(c->d_W[d]);
     cudaFree(c->d_Z); cudaFree(c->d_Y); cudaFree(c->d_X); cudaFree(c->d_U);
     cudaFree(c->d_E); cudaFree(c->d_evlabel); cudaFree(c->d_evval);
+    cudaFree(c->d_dw); cudaFree(c->d_ew); cudaFree(c->d_tau); cudaFree(c->d_rot); cudaFree(c->d_hdr);
+    cudaFree(c->d_nsweep); cudaFree(c->d_faillist); cudaFree(c->d_nfail);
+    c->d_dw = c->d_ew = nullptr; c->d_tau = nullptr; c->d_rot = nullptr;
+    c->d_hdr = c->d_nsweep = c->d_faillist = c->d_nfail = nullptr;
     c->d_table = nullptr;
     for (int d = 0; d < 3; d++) c->d_W[d] = nullptr;
     c->d_Z = c->d_Y = c->d_X = c->d_U = nullptr;
@@ -321,6 +334,20 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     CK(cudaMalloc(&c->d_E, sizeof(double) * nkl * nw));
     CK(cudaMalloc(&c->d_evlabel, sizeof(double) * nkl * nw));
     CK(cudaMalloc(&c->d_evval, sizeof(double) * nkl * nw * 9));
+    if (nw <= 32) {
+        c->eig_chunk = std::min<long>((long)nkl, 65536);
+        c->capR = 2 * nw * nw + 32;
+        c->capS = 6 * nw + 8;
+        size_t ch = (size_t)c->eig_chunk;
+        CK(cudaMalloc(&c->d_dw, sizeof(double) * ch * nw));
+        CK(cudaMalloc(&c->d_ew, sizeof(double) * ch * nw));
+        CK(cudaMalloc(&c->d_tau, sizeof(cplx) * ch * nw));
+        CK(cudaMalloc(&c->d_rot, sizeof(double2) * ch * c->capR));
+        CK(cudaMalloc(&c->d_hdr, sizeof(int) * ch * c->capS));
+        CK(cudaMalloc(&c->d_nsweep, sizeof(int) * ch));
+        CK(cudaMalloc(&c->d_faillist, sizeof(int) * ch));
+        CK(cudaMalloc(&c->d_nfail, sizeof(int)));
+    }
     CK(cudaStreamSynchronize(c->stream));
     c->planned = true;
     return 0;
@@ -379,21 +406,57 @@ static int run_fourier(wbgpu_ctx* c, const double* dK_dev, int nb) {
     return 0;
 }
 
+static int launch_jacobi(wbgpu_ctx* c, long k0, long nk, bool want_U, const int* list, const int* nlist, long nblk_cap) {
+    const int nw = c->nw;
+    constexpr int WARPS = 4;
+    int npair = (nw + 1) / 2;
+    size_t smem = sizeof(cplx) * WARPS * (size_t)(2 * nw * (nw + 1) + 2 * npair + nw);
+    if ((int)smem > c->smem_optin) return set_err("eigh(Jacobi): num_wann=%d needs %zu B shared memory", nw, smem);
+    CK(cudaFuncSetAttribute(wb_eigh_jacobi_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long nblk = std::min((nk + WARPS - 1) / WARPS, nblk_cap);
+    wb_eigh_jacobi_kernel<WARPS><<<(unsigned)nblk, WARPS * 32, smem, c->stream>>>(c->d_X, c->L, k0, nk, c->d_E,
+                                                                             want_U ? c->d_U : nullptr, c->d_sweeps, list, nlist);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int NWP>
+static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
+    const int nw = c->nw;
+    constexpr int WARPS = 4, NT2 = 128;
+    CK(cudaMemsetAsync(c->d_nfail, 0, sizeof(int), c->stream));
+    wb_tridiag_kernel<NWP, WARPS><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, 0, c->stream>>>(
+        c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U);
+    size_t smem2 = sizeof(double) * 2 * nw * NT2;
+    wb_tql_kernel<NT2><<<(unsigned)((nk + NT2 - 1) / NT2), NT2, smem2, c->stream>>>(nw, nk, c->d_dw, c->d_ew, c->d_rot, c->capR,
+                                                                             c->d_hdr, c->capS, c->d_nsweep);
+    size_t smem3 = sizeof(cplx) * WARPS * (size_t)(nw * nw + (nw * (nw + 1) + 1) / 2 + 32 + nw);
+    CK(cudaFuncSetAttribute(wb_eigvec_kernel<NWP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    wb_eigvec_kernel<NWP, WARPS><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, smem3, c->stream>>>(
+        nw, k0, nk, c->d_dw, c->d_tau, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep, c->d_E, c->d_U, c->d_faillist,
+        c->d_nfail);
+    c->launches += 3;
+    CK(cudaGetLastError());
+    // k-points whose QL iteration did not fit the stream: re-solve with Jacobi (normally none)
+    return launch_jacobi(c, k0, nk, true, c->d_faillist, c->d_nfail, 148);
+}
+
 static int run_eigh(wbgpu_ctx* c, long nk, bool want_U) {
     const int nw = c->nw;
     CK(cudaMemsetAsync(c->d_sweeps, 0, sizeof(int), c->stream));
-    {
-        constexpr int WARPS = 4;
-        int npair = (nw + 1) / 2;
-        size_t smem = sizeof(cplx) * WARPS * (size_t)(2 * nw * (nw + 1) + 2 * npair + nw);
-        if ((int)smem > c->smem_optin) return set_err("eigh(Jacobi): num_wann=%d needs %zu B shared memory", nw, smem);
-        CK(cudaFuncSetAttribute(wb_eigh_jacobi_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        long nblk = std::min((nk + WARPS - 1) / WARPS, 148L * 64);
-        wb_eigh_jacobi_kernel<WARPS><<<(unsigned)nblk, WARPS * 32, smem, c->stream>>>(c->d_X, c->L, nk, c->d_E,
-                                                                                 want_U ? c->d_U : nullptr, c->d_sweeps);
-        c->launches++;
+    bool use_ql = (nw <= 32) && (c->eig_method != 1);
+    if (c->eig_method == 2 && nw > 32) return set_err("eigh: Householder+QL path needs num_wann <= 32");
+    if (!use_ql) return launch_jacobi(c, 0, nk, want_U, nullptr, nullptr, 148L * 64);
+    for (long k0 = 0; k0 < nk; k0 += c->eig_chunk) {
+        long n = std::min(c->eig_chunk, nk - k0);
+        int rc;
+        if (nw <= 8) rc = launch_ql<8>(c, k0, n);
+        else if (nw <= 16) rc = launch_ql<16>(c, k0, n);
+        else if (nw <= 24) rc = launch_ql<24>(c, k0, n);
+        else rc = launch_ql<32>(c, k0, n);
+        if (rc) return rc;
     }
-    CK(cudaGetLastError());
     return 0;
 }
 

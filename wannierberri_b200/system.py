@@ -72,6 +72,51 @@ class System_R:
         return s
 
 
+def synthetic_system(num_wann, rmax=2, seed=20261017, lattice_const=4.0, matrices=("Ham", "AA"), degenerate_pairs=False):
+    """Seeded random tight-binding model: all R with every
+    component in -rmax..rmax on a cubic lattice, X_R = (G + iG') exp(-|R|) with X(-R) = X(R)^dagger
+    enforced, AA scaled by 0.1 with zero on-site diagonal, centres uniform in the cell.
+    `degenerate_pairs` doubles every level exactly (H = 1_2 (x) H_half) -- a stress test for the
+    eigensolver and the degenerate-group logic."""
+    rng = np.random.default_rng(seed)
+    rr = np.arange(-rmax, rmax + 1)
+    iRvec = np.array([[x, y, z] for x in rr for y in rr for z in rr], dtype=int)
+    nR = len(iRvec)
+    lattice = np.eye(3) * lattice_const
+    nh = num_wann // 2 if degenerate_pairs else num_wann
+    centres = rng.random((nh, 3)) * lattice_const
+    if degenerate_pairs:
+        assert num_wann % 2 == 0
+        centres = np.concatenate([centres, centres])
+    index = {tuple(R): i for i, R in enumerate(iRvec)}
+    decay = np.exp(-np.linalg.norm(iRvec, axis=1))
+
+    def herm_field(ncart):
+        shape = (nR, nh, nh) + ((3,) if ncart == 3 else ())
+        X = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) * decay.reshape((nR,) + (1,) * (len(shape) - 1))
+        Xd = np.empty_like(X)
+        for R, i in index.items():
+            Xd[i] = X[index[tuple(-np.array(R))]].swapaxes(0, 1).conj()
+        X = 0.5 * (X + Xd)
+        if degenerate_pairs:
+            big = np.zeros((nR, num_wann, num_wann) + shape[3:], dtype=complex)
+            big[:, :nh, :nh] = X
+            big[:, nh:, nh:] = X
+            X = big
+        return X
+
+    s = System_R(lattice, iRvec, centres)
+    for key in matrices:
+        X = herm_field(1 if key == "Ham" else 3)
+        if key != "Ham":
+            X *= 0.1
+            i0 = index[(0, 0, 0)]
+            for n in range(num_wann):
+                X[i0, n, n] = 0
+        s.set_R_mat(key, X)
+    return s
+
+
 def as_system(obj):
     """Accept this package's `System_R` or the reference's (duck typing on the attributes read by
     the path: SURVEY.md section 2, row 9)."""
