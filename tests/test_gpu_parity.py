@@ -136,15 +136,17 @@ def test_eigh_golden_block(wb, fe):
     assert relerr(eng.eig(b["dK"]), b["E_K"]) < 1e-12
 
 
+@pytest.mark.parametrize("rotate_method", [1, 2])
 @pytest.mark.parametrize("kw", [dict(), dict(degen_thresh=0.05), dict(degen_Kramers=True),
                                 dict(kwargs_formula=dict(external_terms=False)),
                                 dict(kwargs_formula=dict(internal_terms=False))])
-def test_omega_band_traces(wb, fe, fe_orc, orc, kw):
+def test_omega_band_traces(wb, fe, fe_orc, orc, kw, rotate_method):
     """Per-k, per-band-group traces of Omega against the oracle's Formula.trace with the same groups."""
     b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
     NKFFT, dK, Ef = b["NKFFT"], b["dK"], b["Efermi"]
     calc = wb.calculators.static.AHC(Efermi=Ef, **kw)
     eng = wb.Engine(fe)
+    eng.set_option("rotate_method", rotate_method)  # 1 = generic shared-memory kernel, 2 = DMMA kernel
     eng.plan(NKFFT, all_formulae())
     lab, val = eng.band_traces(dK, calc.specs()[0])
     data = orc.OracleDataK(fe_orc, dK, NKFFT)
@@ -182,6 +184,22 @@ def test_block_calculators_vs_reference(wb, fe, case):
     res = getattr(wb.calculators.static, name)(Efermi=b["Efermi"], **kw)(data)
     assert res.data.shape == b["block_" + case].shape
     assert relerr(res.data, b["block_" + case]) < RTOL
+
+
+@pytest.mark.parametrize("nw", [5, 8, 12, 16, 20, 24])
+def test_omega_synthetic_sizes(wb, orc, nw):
+    """AHC scan on seeded random models of several sizes (DMMA kernel variants for nw <= 20, generic above)
+    against the oracle; one K-block."""
+    sysg = wb.synthetic_system(nw, rmax=1, seed=100 + nw)
+    syso = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
+                            {k: sysg.get_R_mat(k) for k in ("Ham", "AA")})
+    NKFFT, dK = [3, 3, 2], [0.05, 0.11, 0.02]
+    Ef = np.linspace(-3., 3., 61)
+    grid = wb.Grid(sysg, NKdiv=[1, 1, 1], NKFFT=NKFFT)
+    data = wb.Data_K_R(sysg, dK=dK, grid=grid)
+    got = wb.calculators.static.AHC(Efermi=Ef)(data).data
+    ref = orc.AHC(orc.OracleDataK(syso, dK, NKFFT), Ef)
+    assert relerr(got, ref) < RTOL
 
 
 def test_run_fe_vs_upstream_golden(wb, fe):

@@ -21,6 +21,7 @@
 #include "wb_eigh_ql.cuh"
 #include "wb_groups.cuh"
 #include "wb_rotate_formula.cuh"
+#include "wb_rotate_dmma.cuh"
 #include "wb_scan.cuh"
 #include "wb_probe.cuh"
 
@@ -82,6 +83,7 @@ struct wbgpu_ctx {
     int last_sweeps = 0;
     int64_t launches = 0;
     int eig_method = 0;
+    int rotate_method = 0;  // 0 = automatic, 1 = generic shared-memory DFMA kernel, 2 = DMMA kernel
     int smem_optin = 0;
     // optional per-stage device timing (option "timing"): events around each stage of each batch
     int timing = 0;
@@ -207,6 +209,7 @@ extern "C" int wbgpu_set_R_matrix(wbgpu_ctx* c, int key, const double* X_R, int 
 extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return set_err("wbgpu_set_option: null pointer argument");
     if (!strcmp(name, "eig_method")) { c->eig_method = (int)value; return 0; }
+    if (!strcmp(name, "rotate_method")) { c->rotate_method = (int)value; return 0; }
     if (!strcmp(name, "timing")) {
         c->timing = (int)value;
         for (int i = 0; i < WBGPU_NSTAGES; i++) { c->stage_ms[i] = 0; c->stage_calls[i] = 0; }
@@ -424,13 +427,21 @@ static int launch_jacobi(wbgpu_ctx* c, long k0, long nk, bool want_U, const int*
 template <int NWP>
 static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
     const int nw = c->nw;
-    constexpr int WARPS = 4, NT2 = 128;
+    constexpr int WARPS = 4;
     CK(cudaMemsetAsync(c->d_nfail, 0, sizeof(int), c->stream));
     wb_tridiag_kernel<NWP, WARPS><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, 0, c->stream>>>(
         c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U);
-    size_t smem2 = sizeof(double) * 2 * nw * NT2;
-    wb_tql_kernel<NT2><<<(unsigned)((nk + NT2 - 1) / NT2), NT2, smem2, c->stream>>>(nw, nk, c->d_dw, c->d_ew, c->d_rot, c->capR,
-                                                                             c->d_hdr, c->capS, c->d_nsweep);
+    CK(cudaGetLastError());
+    if (nw <= 24) {
+        constexpr int NT2 = 128;
+        wb_tql_kernel<NT2><<<(unsigned)((nk + NT2 - 1) / NT2), NT2, sizeof(double) * 2 * nw * NT2, c->stream>>>(
+            nw, nk, c->d_dw, c->d_ew, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep);
+    } else {
+        constexpr int NT2 = 64;
+        wb_tql_kernel<NT2><<<(unsigned)((nk + NT2 - 1) / NT2), NT2, sizeof(double) * 2 * nw * NT2, c->stream>>>(
+            nw, nk, c->d_dw, c->d_ew, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep);
+    }
+    CK(cudaGetLastError());
     size_t smem3 = sizeof(cplx) * WARPS * (size_t)(nw * nw + (nw * (nw + 1) + 1) / 2 + 32 + nw);
     CK(cudaFuncSetAttribute(wb_eigvec_kernel<NWP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     wb_eigvec_kernel<NWP, WARPS><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, smem3, c->stream>>>(
@@ -465,21 +476,43 @@ static int run_events(wbgpu_ctx* c, const wbgpu_scan_spec& s, long nk) {
     WbWindow win = make_window(s);
     if (s.formula == WBGPU_IDENTITY) {
         int per = ((nw * (2 * 8 + 2 * 2)) + 7) / 8 * 8;
-        int nt = 64;
+        int nt = nw <= 32 ? 64 : 32;
+        if ((size_t)per * nt > 48 * 1024)
+            CK(cudaFuncSetAttribute(wb_identity_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, per * nt));
         wb_identity_events_kernel<<<(unsigned)((nk + nt - 1) / nt), nt, (size_t)per * nt, c->stream>>>(c->d_E, nw, nk, win, c->d_evlabel,
                                                                                                  c->d_evval);
         c->launches++;
     } else if (s.formula == WBGPU_OMEGA) {
         if (c->L.off_dH[0] < 0 || (s.external_terms && c->L.off_A[0] < 0))
             return set_err("scan: the plan does not hold the channels formula %d needs", s.formula);
-        constexpr int NT = 128;
-        size_t smem = sizeof(cplx) * (size_t)(9 * nw * nw + 3 * nw) + sizeof(double) * 5 * nw + sizeof(short) * 2 * nw + 16;
-        if ((int)smem > c->smem_optin) return set_err("rotate(generic): num_wann=%d needs %zu B shared memory", nw, smem);
-        CK(cudaFuncSetAttribute(wb_omega_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         WbFormulaFlags fl{s.formula, s.internal_terms, s.external_terms};
         long nblk = std::min(nk, 148L * 32);
-        wb_omega_events_kernel<NT><<<(unsigned)nblk, NT, smem, c->stream>>>(c->d_X, c->L, nk, c->d_E, c->d_U, win, fl,
-                                                                        c->d_evlabel, c->d_evval);
+        bool dmma = (nw <= 20) && (c->rotate_method != 1);
+        if (c->rotate_method == 2 && nw > 20) return set_err("rotate: the DMMA kernel needs num_wann <= 20");
+        if (dmma) {
+#define WB_DMMA_CASE(KS, MT2)                                                                                         \
+    {                                                                                                                 \
+        size_t smem = wb_dmma_smem_bytes(nw, KS);                                                                     \
+        CK(cudaFuncSetAttribute(wb_omega_events_dmma_kernel<KS, MT2>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                (int)smem));                                                                          \
+        wb_omega_events_dmma_kernel<KS, MT2><<<(unsigned)nblk, 128, smem, c->stream>>>(c->d_X, c->L, nk, c->d_E, c->d_U, \
+                                                                                   win, fl, c->d_evlabel, c->d_evval); \
+    }
+            if (nw <= 4) WB_DMMA_CASE(2, 1)
+            else if (nw <= 8) WB_DMMA_CASE(4, 2)
+            else if (nw <= 12) WB_DMMA_CASE(6, 3)
+            else if (nw <= 16) WB_DMMA_CASE(8, 4)
+            else if (nw <= 18) WB_DMMA_CASE(9, 5)
+            else WB_DMMA_CASE(10, 5)
+#undef WB_DMMA_CASE
+        } else {
+            constexpr int NT = 128;
+            size_t smem = sizeof(cplx) * (size_t)(9 * nw * nw + 3 * nw) + sizeof(double) * 5 * nw + sizeof(short) * 2 * nw + 16;
+            if ((int)smem > c->smem_optin) return set_err("rotate(generic): num_wann=%d needs %zu B shared memory", nw, smem);
+            CK(cudaFuncSetAttribute(wb_omega_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            wb_omega_events_kernel<NT><<<(unsigned)nblk, NT, smem, c->stream>>>(c->d_X, c->L, nk, c->d_E, c->d_U, win, fl,
+                                                                            c->d_evlabel, c->d_evval);
+        }
         c->launches++;
     } else {
         return set_err("scan: formula %d is not implemented on the GPU path yet", s.formula);
