@@ -47,3 +47,50 @@ __device__ inline void wb_band_groups(const double* E, int nw, const WbWindow& w
         }
     }
 }
+
+// Same decisions, evaluated by one full warp for nw <= 32 (lane n = band n; E in shared memory):
+// borders -> 64-bit ballot mask, group start / end by bit scans.  Keeps the per-k-point band-group
+// logic off the critical path of the rotation kernels (the serial version costs ~nw dependent
+// shared-memory round trips on a single thread while the rest of the CTA waits at a barrier).
+__device__ inline void wb_band_groups_warp(const double* Es, int nw, const WbWindow& w, short* g1, short* g2,
+                                           double* label, int lane) {
+    const unsigned full = 0xffffffffu;
+    double En = (lane < nw) ? Es[lane] : CUDART_INF;
+    bool brd = false;
+    if (lane < nw) {
+        brd = (lane == 0) || (En - Es[lane - 1] > w.degen_thresh);
+        if (w.degen_Kramers && (lane & 1)) brd = false;
+    }
+    unsigned long long B = __ballot_sync(full, brd);
+    if (!(w.degen_Kramers && (nw & 1))) B |= (1ull << nw);
+    int a = -1, b = -1;
+    bool kept = false;
+    if (lane < nw) {
+        unsigned long long lo = B & ((2ull << lane) - 1ull);  // borders at positions <= lane (bit 0 is always set)
+        a = 63 - __clzll((long long)lo);
+        unsigned long long hi = B >> (lane + 1);
+        if (hi) {
+            b = lane + __ffsll((long long)hi);
+            kept = (Es[b - 1] >= w.EFmin) && (Es[a] <= w.EFmax);
+        }
+    }
+    unsigned keptstart = __ballot_sync(full, kept && lane == a);
+    int first_kept = keptstart ? (__ffs(keptstart) - 1) : -1;
+    int G1 = kept ? a : -1, G2 = kept ? b : -1;
+    double lab = CUDART_INF;
+    if (kept && lane == a) {
+        double s = Es[a];
+        for (int n = a + 1; n < b; n++) s += Es[n];
+        lab = s / (double)(b - a);
+    }
+    if (w.sea) {
+        unsigned below = __ballot_sync(full, lane < nw && En < w.EFmin);
+        int bandmax = below ? (32 - __clz(below)) : 0;
+        if (first_kept >= 0) bandmax = min(bandmax, first_kept);
+        if (bandmax > 0) {
+            if (lane < bandmax) { G1 = 0; G2 = bandmax; }
+            if (lane == 0) lab = -CUDART_INF;
+        }
+    }
+    if (lane < nw) { g1[lane] = (short)G1; g2[lane] = (short)G2; label[lane] = lab; }
+}

@@ -24,12 +24,38 @@ __device__ __forceinline__ void wb_dmma(double& d0, double& d1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// ---- TMA 1-D bulk copy + mbarrier helpers (cp.async.bulk -> SASS UBLKCP)
+__device__ __forceinline__ uint32_t wb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wb_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(wb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void wb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(wb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wb_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     wb_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(wb_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void wb_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(wb_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 struct WbDmmaDims {
     int K2;    // 4*KS  (real-ified, padded inner dimension)
     int ldx;   // leading dimension of Xs (doubles)
     int ldy;   // leading dimension of Yp (doubles)
     int ldc;   // leading dimension of Cs rows (doubles)
     int mrows; // 3*nw rounded up to 8
+    int stage; // doubles per staging buffer (one channel triple, full matrices)
 };
 
 __host__ __device__ inline int wb_pad_ld(int n) {  // smallest ld >= n with ld % 16 in {4, 12}: conflict-free 64-bit fragment loads
@@ -45,58 +71,111 @@ __host__ __device__ inline WbDmmaDims wb_dmma_dims(int nw, int KS) {
     d.ldy = wb_pad_ld(nw);
     d.ldc = (nw + 1) / 2 * 2;
     d.mrows = (3 * nw + 7) / 8 * 8;
+    d.stage = 6 * nw * nw;
     return d;
 }
 
 __host__ inline size_t wb_dmma_smem_bytes(int nw, int KS) {
     WbDmmaDims d = wb_dmma_dims(nw, KS);
-    size_t dbl = 2 * (size_t)nw * nw                 // Us
+    size_t dbl = 2 * (size_t)d.stage                 // staging ring: 2 channel triples
+                 + 2 * 2 * (size_t)nw * nw           // U, double buffered
                  + (size_t)d.mrows * d.ldx           // Xs
                  + (size_t)3 * d.K2 * d.ldy          // Yp
                  + (size_t)12 * nw * d.ldc           // Cs: 6 matrices, planar re/im
                  + 2 * 3 * (size_t)nw                // Od
-                 + 5 * (size_t)nw;                   // Es, label, rows[3]
-    return dbl * sizeof(double) + 2 * nw * sizeof(short) + 16;
+                 + 5 * (size_t)nw                    // Es, label, rows[3]
+                 + 8;                                // 4 mbarriers
+    return dbl * sizeof(double) + 2 * nw * sizeof(short) + (size_t)(nw * (nw + 1) / 2) * 2 * sizeof(short) + 32;
 }
 
+// One CTA walks k-points blockIdx.x, blockIdx.x + gridDim.x, ...  Per k-point the "items" are the channel
+// triples dH | A | curl A (contiguous in the record).  A two-deep ring of staging buffers is filled by TMA
+// bulk copies issued two items ahead, so the HBM/L2 latency of item i+2 hides behind the MMAs of items i, i+1.
 template <int KS, int MT2>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 2)
 wb_omega_events_dmma_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, const double* __restrict__ Eall,
                             const cplx* __restrict__ Uall, WbWindow win, WbFormulaFlags fl,
                             double* __restrict__ ev_label, double* __restrict__ ev_val) {
-    extern __shared__ double smem_d[];
+    extern __shared__ __align__(16) double smem_d[];
     constexpr int NT = 128;
     const int nw = L.nw, n2 = nw * nw;
     const WbDmmaDims D = wb_dmma_dims(nw, KS);
-    cplx* Us = (cplx*)smem_d;
-    double* Xs = smem_d + 2 * n2;
+    double* stg = smem_d;                              // [2][stage]
+    cplx* Ustg = (cplx*)(stg + 2 * D.stage);           // [2][n2]
+    double* Xs = (double*)(Ustg + 2 * n2);
     double* Yp = Xs + D.mrows * D.ldx;
     double* Cs = Yp + 3 * D.K2 * D.ldy;
     cplx* Od = (cplx*)(Cs + 12 * nw * D.ldc);
     double* Es = (double*)(Od + 3 * nw);
     double* label = Es + nw;
     double* rows = label + nw;
-    short* g1 = (short*)(rows + 3 * nw);
+    uint64_t* bars = (uint64_t*)(rows + 3 * nw);       // [0..1] staging ring, [2..3] U
+    short* g1 = (short*)(bars + 4);
     short* g2 = g1 + nw;
-    double* Rc = Xs;  // [3][n2] pair terms; aliases Xs/Yp, free after the rotations
+    short* lut = g2 + nw;                              // packed index -> (i, j)
+    double* Rc = Xs;  // [3][n2] pair terms; aliases Xs, free after the rotations
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     // per-lane sign relating the A2 fragments (step 2) to the B1 fragments (step 1)
     const int signmask = ((g ^ q) & 1) ? (int)0x80000000 : 0;
     const int ntile3 = (3 * nw + 7) / 8;   // tiles over the stacked 3*nw dimension
+    const int nitem = fl.external_terms ? 3 : 1;
+    const uint32_t item_bytes[3] = {(uint32_t)(3 * n2 * 16), (uint32_t)(3 * L.ntri * 16), (uint32_t)(3 * L.ntri * 16)};
+    const int item_off[3] = {L.off_dH[0], L.off_A[0], L.off_O[0]};
 
     // zero the padding that enters the K (inner) dimension once; X/Y loads never touch it
     for (int x = threadIdx.x; x < D.mrows * D.ldx; x += NT) Xs[x] = 0.;
     for (int x = threadIdx.x; x < 3 * D.K2 * D.ldy; x += NT) Yp[x] = 0.;
+    for (int i = threadIdx.x; i < nw; i += NT)
+        for (int j = i; j < nw; j++) {
+            lut[2 * tri_index(i, j, nw)] = (short)i;
+            lut[2 * tri_index(i, j, nw) + 1] = (short)j;
+        }
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 4; b++) wb_mbar_init(&bars[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     __syncthreads();
 
-    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
-        const cplx* r = rec + ik * L.E;
-        for (int x = threadIdx.x; x < n2; x += NT) Us[x] = Uall[ik * n2 + x];
-        for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
+    const long nmine = (blockIdx.x < nk) ? (nk - 1 - blockIdx.x) / gridDim.x + 1 : 0;  // k-points of this CTA
+    const long nitems_total = nmine * nitem;
+    // producer (thread 0): issue the copy of global item `gi` (k-point gi / nitem, triple gi % nitem)
+    auto issue_item = [&](long gi) {
+        long ik = blockIdx.x + (gi / nitem) * (long)gridDim.x;
+        int tr = (int)(gi % nitem);
+        int b = (int)(gi & 1);
+        wb_mbar_expect_tx(&bars[b], item_bytes[tr]);
+        wb_bulk_g2s(stg + (size_t)b * D.stage, rec + ik * L.E + item_off[tr], item_bytes[tr], &bars[b]);
+    };
+    auto issue_U = [&](long kl) {  // kl = local k-point counter
+        long ik = blockIdx.x + kl * (long)gridDim.x;
+        int b = (int)(kl & 1);
+        wb_mbar_expect_tx(&bars[2 + b], (uint32_t)(n2 * 16));
+        wb_bulk_g2s(Ustg + (size_t)b * n2, Uall + ik * n2, (uint32_t)(n2 * 16), &bars[2 + b]);
+    };
+    if (threadIdx.x == 0 && nmine > 0) {
+        issue_U(0);
+        issue_item(0);
+        if (nitems_total > 1) issue_item(1);
+    }
+    double Enext = 0.;
+    if (nmine > 0 && threadIdx.x < nw) Enext = Eall[(long)blockIdx.x * nw + threadIdx.x];
+
+    long gi = 0;
+    for (long kl = 0; kl < nmine; kl++) {
+        const long ik = blockIdx.x + kl * (long)gridDim.x;
+        const cplx* Us = Ustg + (size_t)(kl & 1) * n2;
+        if (threadIdx.x < nw) Es[threadIdx.x] = Enext;
+        if (kl + 1 < nmine) {  // prefetch for the next k-point: E into registers, U by TMA
+            if (threadIdx.x < nw) Enext = Eall[(ik + gridDim.x) * nw + threadIdx.x];
+            if (threadIdx.x == 0) issue_U(kl + 1);
+        }
+        wb_mbar_wait(&bars[2 + (kl & 1)], (uint32_t)((kl >> 1) & 1));
         __syncthreads();
-        if (threadIdx.x == 0) wb_band_groups(Es, nw, win, g1, g2, label);
+        if (nw <= 32) {
+            if (threadIdx.x < 32) wb_band_groups_warp(Es, nw, win, g1, g2, label, threadIdx.x);
+        } else if (threadIdx.x == 0) wb_band_groups(Es, nw, win, g1, g2, label);
         // B1 fragments: element (kk = 4s + q, nn = 8t + g)
         double Bf[KS][MT2];
 #pragma unroll
@@ -107,38 +186,37 @@ wb_omega_events_dmma_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, c
                 int j = kk >> 1, l = nn >> 1;
                 double v = 0.;
                 if (j < nw && l < nw) {
-                    cplx u = Us[j * nw + l];
+                    const double* u = (const double*)&Us[j * nw + l];
                     int pk = kk & 1, pn = nn & 1;
-                    v = (pk == pn) ? u.x : (pk ? -u.y : u.y);
+                    v = (pk == pn) ? u[0] : (pk ? -u[1] : u[1]);
                 }
                 Bf[s][t] = v;
             }
 
-        for (int trip = 0; trip < 3; trip++) {
-            if (trip > 0 && !fl.external_terms) break;
-            const int* offs = trip == 0 ? L.off_dH : (trip == 1 ? L.off_A : L.off_O);
+        for (int trip = 0; trip < nitem; trip++, gi++) {
             const bool herm = trip > 0;
-            // ---- load the three matrices of this channel as full real-ified rows
+            const int b = (int)(gi & 1);
+            const cplx* src = (const cplx*)(stg + (size_t)b * D.stage);
+            wb_mbar_wait(&bars[b], (uint32_t)((gi >> 1) & 1));
+            // ---- unpack the three matrices of this channel into full real-ified rows
             if (!herm) {
                 for (int x = threadIdx.x; x < 3 * n2; x += NT) {
-                    int m = x / n2, e = x % n2;
-                    int i = e / nw, j = e % nw;
-                    cplx v = r[offs[m] + e];
-                    *(double2*)&Xs[(m * nw + i) * D.ldx + 2 * j] = v;
+                    int m = x / n2, e = x - m * n2;
+                    int i = e / nw, j = e - i * nw;
+                    *(double2*)&Xs[(m * nw + i) * D.ldx + 2 * j] = src[x];
                 }
             } else {
                 for (int x = threadIdx.x; x < 3 * L.ntri; x += NT) {
-                    int m = x / L.ntri, e = x % L.ntri;
-                    // invert the packed index: row i such that tri_index(i, i) <= e
-                    int i = 0;
-                    while (i + 1 < nw && tri_index(i + 1, i + 1, nw) <= e) i++;
-                    int j = i + (e - tri_index(i, i, nw));
-                    cplx v = r[offs[m] + e];
+                    int m = x / L.ntri, e = x - m * L.ntri;
+                    int i = lut[2 * e], j = lut[2 * e + 1];
+                    cplx v = src[x];
                     *(double2*)&Xs[(m * nw + i) * D.ldx + 2 * j] = v;
                     if (i != j) *(double2*)&Xs[(m * nw + j) * D.ldx + 2 * i] = cconj(v);
                 }
             }
             __syncthreads();
+            // staging buffer b is free again: refill it with the item two ahead
+            if (threadIdx.x == 0 && gi + 2 < nitems_total) issue_item(gi + 2);
             // ---- step 1: Y = X U
             for (int mt = warp; mt < ntile3; mt += 4) {
                 double acc[MT2][2];
@@ -153,7 +231,7 @@ wb_omega_events_dmma_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, c
                 }
                 int row = 8 * mt + g;
                 if (row < 3 * nw) {
-                    int m = row / nw, i = row % nw;
+                    int m = row / nw, i = row - m * nw;
                     double* y0 = Yp + (m * D.K2 + 2 * i) * D.ldy;
 #pragma unroll
                     for (int t = 0; t < MT2; t++) {
@@ -166,7 +244,7 @@ wb_omega_events_dmma_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, c
             if (trip == 2) {
                 // diagonal of Obar:  sum_i conj(U[i][n]) Y_c[i][n]
                 for (int x = threadIdx.x; x < 3 * nw; x += NT) {
-                    int c = x / nw, n = x % nw;
+                    int c = x / nw, n = x - c * nw;
                     cplx acc = cmake(0., 0.);
                     const double* y = Yp + (c * D.K2) * D.ldy + n;
                     for (int i = 0; i < nw; i++)
@@ -185,28 +263,26 @@ wb_omega_events_dmma_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, c
                     const double* bcol = Yp + (mb * D.K2 + q) * D.ldy + lb;
 #pragma unroll
                     for (int s = 0; s < KS; s++) {
-                        double b = bcol[4 * s * D.ldy];
+                        double bv = bcol[4 * s * D.ldy];
 #pragma unroll
                         for (int t = 0; t < MT2; t++) {
                             // sign flip on the high word (integer pipe, keeps the FP64 pipe for the MMAs)
                             double a = __hiloint2double(__double2hiint(Bf[s][t]) ^ signmask, __double2loint(Bf[s][t]));
-                            wb_dmma(acc[t][0], acc[t][1], a, b);
+                            wb_dmma(acc[t][0], acc[t][1], a, bv);
                         }
                     }
                     // lane holds Ctilde[rr = 8t + g][cc0 = 8nt + 2q + {0,1}]
+                    int c0 = 8 * nt + 2 * q;
+                    int m0 = c0 / nw, l0 = c0 - m0 * nw;
+                    int c1 = c0 + 1;
+                    int m1 = c1 / nw, l1 = c1 - m1 * nw;
 #pragma unroll
                     for (int t = 0; t < MT2; t++) {
                         int rr = 8 * t + g;
                         int n = rr >> 1, p = rr & 1;
                         if (n < nw) {
-#pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                int c0 = 8 * nt + 2 * q + h;
-                                if (c0 < 3 * nw) {
-                                    int m = c0 / nw, l = c0 % nw;
-                                    Cs[(((trip * 3 + m) * 2 + p) * nw + n) * D.ldc + l] = acc[t][h];
-                                }
-                            }
+                            if (c0 < 3 * nw) Cs[(((trip * 3 + m0) * 2 + p) * nw + n) * D.ldc + l0] = acc[t][0];
+                            if (c1 < 3 * nw) Cs[(((trip * 3 + m1) * 2 + p) * nw + n) * D.ldc + l1] = acc[t][1];
                         }
                     }
                 }

@@ -77,7 +77,9 @@ wb_omega_events_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, const 
         for (int x = threadIdx.x; x < n2; x += NT) Us[x] = Uall[ik * n2 + x];
         for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
         __syncthreads();
-        if (threadIdx.x == 0) wb_band_groups(Es, nw, win, g1, g2, label);
+        if (nw <= 32) {
+            if (threadIdx.x < 32) wb_band_groups_warp(Es, nw, win, g1, g2, label, threadIdx.x);
+        } else if (threadIdx.x == 0) wb_band_groups(Es, nw, win, g1, g2, label);
         // rotations (the block-wide barriers inside also publish the groups)
         for (int a = 0; a < 3; a++) {
             wb_load_channel<NT>(r, L.off_dH[a], false, Xs, nw);
