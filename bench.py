@@ -115,7 +115,7 @@ def _oracle_init():
     _oracle_block.sys = orc.OracleSystem.from_npz(FE)
 
 
-def cpu_baseline_1core(nkfft=(6, 6, 6)):
+def cpu_baseline_1core(nkfft=(16, 16, 16)):
     """oracle on 1 core, one K-block of the same workload (same system, same 2000 Fermi levels)."""
     _oracle_init()
     t0 = time.perf_counter()
@@ -127,13 +127,13 @@ def cpu_baseline_1core(nkfft=(6, 6, 6)):
 
 
 def run_reference_arm(args):
-    """`--impl reference`: the CPU port on all host cores; each step = one K-block of 6^3 k-points per core."""
+    """`--impl reference`: the CPU port on all host cores; each step = one K-block of 8^3 k-points per core."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    nkfft = [6, 6, 6]
+    nkfft = [8, 8, 8]
     rng = np.random.default_rng(0)
     with mp.Pool(cores, initializer=_oracle_init) as pool:
         def step():
