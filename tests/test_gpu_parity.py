@@ -62,6 +62,47 @@ def all_formulae():
     return [_lib.IDENTITY, _lib.OMEGA]
 
 
+FORMULA_CASES = ["Omega", "Morb_Hpm", "Spin", "VelOmega", "VelHplus", "VelSpin"]
+
+
+@pytest.mark.parametrize("thresh", [1e-4, 0.05])
+@pytest.mark.parametrize("name", FORMULA_CASES)
+def test_formula_band_traces(wb, fe, fe_orc, orc, name, thresh):
+    """Per-k, per-band-group values of every formula against the oracle's Formula classes evaluated with the
+    reference's additive / non-additive loop (static.py:102-117), same groups."""
+    from wannierberri_b200 import _lib
+    from wannierberri_b200._lib import ScanSpec
+    code = dict(Omega=_lib.OMEGA, Morb_Hpm=_lib.MORB_HPM, Spin=_lib.SPIN, VelOmega=_lib.VEL_OMEGA,
+                VelHplus=_lib.VEL_HPLUS, VelSpin=_lib.VEL_SPIN)[name]
+    b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
+    NKFFT, dK = b["NKFFT"], b["dK"]
+    fder = 0 if name in ("Omega", "Morb_Hpm", "Spin") else 1
+    Ef = np.linspace(14., 20., 31)
+    dEF = Ef[1] - Ef[0]
+    spec = ScanSpec(formula=code, fder=fder, nEF=len(Ef), degen_Kramers=0, internal_terms=1, external_terms=1,
+                    Ef_first=Ef[0], Ef_last=Ef[-1], dEF=dEF, degen_thresh=thresh, factor=1.0)
+    eng = wb.Engine(fe)
+    eng.plan(NKFFT, [_lib.IDENTITY, code])
+    lab, val = eng.band_traces(dK, spec)
+    data = orc.OracleDataK(fe_orc, dK, NKFFT)
+    form = getattr(orc, name)(data)
+    nw = fe.num_wann
+    EFmin, EFmax = Ef[0] - fder * dEF, Ef[-1] + fder * dEF
+    worst = scale = 0.
+    for ik in range(data.nk):
+        groups = orc.band_groups(data.E_K[ik], EFmin, EFmax, thresh, False, sea=(fder == 0))
+        if form.additive:
+            vals = {n: form.trace(ik, np.arange(n[0], n[1]), np.concatenate((np.arange(0, n[0]), np.arange(n[1], nw))))
+                    for n in groups}
+        else:
+            edge = {x: form.trace(ik, np.arange(0, x), np.arange(x, nw)) for n in groups for x in n}
+            vals = {n: edge[n[1]] - edge[n[0]] for n in groups}
+        for n, ref in vals.items():
+            worst = max(worst, np.abs(val[ik, n[0]] - ref).max())
+            scale = max(scale, np.abs(ref).max())
+    assert worst < RTOL * scale
+
+
 def test_kpoints_bit_exact(wb, fe, orc):
     b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
     eng = wb.Engine(fe)
@@ -169,8 +210,12 @@ def test_omega_band_traces(wb, fe, fe_orc, orc, kw, rotate_method):
 
 
 BLOCK_CASES = dict(
-    ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}),
+    ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}),
     ahc_kramers=("AHC", dict(degen_Kramers=True)), ahc_thresh=("AHC", dict(degen_thresh=0.05)),
+    morb_thresh=("Morb", dict(degen_thresh=0.05)),
+    bcd_thresh=("BerryDipole_FermiSurf", dict(degen_thresh=0.05)),
+    gme_orb_thresh=("GME_orb_FermiSurf", dict(degen_thresh=0.05)),
+    gme_spin_thresh=("GME_spin_FermiSurf", dict(degen_thresh=0.05)),
 )
 
 
@@ -209,11 +254,24 @@ def test_run_fe_vs_upstream_golden(wb, fe):
     Ef = g["Efermi"]
     st = wb.calculators.static
     calcs = dict(ahc=st.AHC(Efermi=Ef), dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef),
-                 ahc_int=st.AHC(Efermi=Ef, kwargs_formula={"external_terms": False}))
+                 Morb=st.Morb(Efermi=Ef), spin=st.Spin(Efermi=Ef))
     res = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), calcs)
-    for q in ("ahc", "dos", "cumdos"):
+    for q in calcs:
         assert relerr(res.results[q].data, g["upstream_golden_" + q]) < RTOL, q
-    assert relerr(res.results["ahc_int"].data, g["ahc_int"]) < RTOL
+
+
+def test_run_fe_other_quantities(wb, fe):
+    """Quantities without an upstream golden file: against a live run of the reference (fixture)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    Ef = g["Efermi"]
+    st = wb.calculators.static
+    calcs = dict(ahc_int=st.AHC(Efermi=Ef, kwargs_formula={"external_terms": False}),
+                 berry_dipole_fsurf=st.BerryDipole_FermiSurf(Efermi=Ef),
+                 gme_orb_fsurf=st.GME_orb_FermiSurf(Efermi=Ef),
+                 gme_spin_fsurf=st.GME_spin_FermiSurf(Efermi=Ef))
+    res = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), calcs)
+    for q in calcs:
+        assert relerr(res.results[q].data, g[q]) < RTOL, q
 
 
 def test_run_fe_wide_window(wb, fe):
@@ -231,7 +289,10 @@ def test_run_te(wb, te):
     g = np.load(os.path.join(GOLDEN, "golden_te_nk4.npz"))
     Ef = g["Efermi"]
     st = wb.calculators.static
-    calcs = dict(dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef))
+    calcs = dict(dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef),
+                 berry_dipole_fsurf=st.BerryDipole_FermiSurf(Efermi=Ef),
+                 gme_orb_fsurf=st.GME_orb_FermiSurf(Efermi=Ef),
+                 gme_spin_fsurf=st.GME_spin_FermiSurf(Efermi=Ef))
     res = wb.run(te, wb.Grid(te, NK=[4, 4, 6], NKFFT=[2, 2, 3]), calcs)
     for q in calcs:
         assert relerr(res.results[q].data, g[q]) < RTOL, q

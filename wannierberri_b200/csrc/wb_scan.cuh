@@ -32,8 +32,8 @@ __global__ void wb_identity_events_kernel(const double* __restrict__ Eall, int n
 
 // hist[(nEFx + 1)][ncomp]: row 0 = "below" (label < EFmin), row 1 + iEf = bin iEf.
 __global__ void __launch_bounds__(256)
-wb_scan_accumulate_kernel(const double* __restrict__ ev_label, const double* __restrict__ ev_val, long nslots,
-                          int slots_per_block /* nk_block * nw */, const double* __restrict__ weight,
+wb_scan_accumulate_kernel(const double* __restrict__ ev_label, const double* __restrict__ ev_val, int ev_stride,
+                          long nslots, int slots_per_block /* nk_block * nw */, const double* __restrict__ weight,
                           int ncomp, WbWindow win, double* __restrict__ hist, int use_smem) {
     extern __shared__ double hist_s[];
     const int nrow = win.nEFx + 1;
@@ -55,7 +55,7 @@ wb_scan_accumulate_kernel(const double* __restrict__ ev_label, const double* __r
             row = 1 + iEf;
         } else continue;
         double w = weight[s / slots_per_block];
-        for (int c = 0; c < ncomp; c++) atomicAdd(&h[row * ncomp + c], w * ev_val[s * ncomp + c]);
+        for (int c = 0; c < ncomp; c++) atomicAdd(&h[row * ncomp + c], w * ev_val[s * ev_stride + c]);
     }
     if (use_smem) {
         __syncthreads();

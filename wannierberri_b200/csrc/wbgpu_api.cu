@@ -22,6 +22,7 @@
 #include "wb_groups.cuh"
 #include "wb_rotate_formula.cuh"
 #include "wb_rotate_dmma.cuh"
+#include "wb_events_generic.cuh"
 #include "wb_scan.cuh"
 #include "wb_probe.cuh"
 
@@ -83,6 +84,7 @@ struct wbgpu_ctx {
     int last_sweeps = 0;
     int64_t launches = 0;
     int eig_method = 0;
+    int ev_ncmax = 1;
     int rotate_method = 0;  // 0 = automatic, 1 = generic shared-memory DFMA kernel, 2 = DMMA kernel
     int smem_optin = 0;
     // optional per-stage device timing (option "timing"): events around each stage of each batch
@@ -336,7 +338,15 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     CK(cudaMalloc(&c->d_U, sizeof(cplx) * nkl * nw * nw));
     CK(cudaMalloc(&c->d_E, sizeof(double) * nkl * nw));
     CK(cudaMalloc(&c->d_evlabel, sizeof(double) * nkl * nw));
-    CK(cudaMalloc(&c->d_evval, sizeof(double) * nkl * nw * 9));
+    {
+        int ncmax = 1;
+        int sum = 0;
+        for (int f = 1; f < WBGPU_NFORMULA; f++)
+            if ((m >> f) & 1u) sum += formula_ncomp(f);
+        ncmax = std::max(ncmax, sum);
+        c->ev_ncmax = ncmax;
+        CK(cudaMalloc(&c->d_evval, sizeof(double) * nkl * nw * ncmax));
+    }
     if (nw <= 32) {
         c->eig_chunk = std::min<long>((long)nkl, 65536);
         c->capR = 2 * nw * nw + 32;
@@ -471,10 +481,62 @@ static int run_eigh(wbgpu_ctx* c, long nk, bool want_U) {
     return 0;
 }
 
-static int run_events(wbgpu_ctx* c, const wbgpu_scan_spec& s, long nk) {
+// Specs that share the Fermi window, the degeneracy rules and the term flags are evaluated from ONE pass over
+// the rotated matrices ("event group"): e.g. AHC + Morb (Omega, Morb_Hpm, Omega) or the three Fermi-surface
+// tensors of BASELINE config 3.
+struct EvGroup {
+    WbWindow win;
+    WbEventLayout ev;
+    std::vector<int> specs;
+};
+
+static bool same_window(const WbWindow& a, const WbWindow& b) {
+    return a.EFmin == b.EFmin && a.EFmax == b.EFmax && a.dEF == b.dEF && a.degen_thresh == b.degen_thresh &&
+           a.degen_Kramers == b.degen_Kramers && a.sea == b.sea && a.nEFx == b.nEFx;
+}
+
+static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec) {
+    std::vector<EvGroup> groups;
+    for (int i = 0; i < nspec; i++) {
+        const wbgpu_scan_spec& s = specs[i];
+        WbWindow w = make_window(s);
+        bool ident = (s.formula == WBGPU_IDENTITY);
+        int found = -1;
+        for (size_t g = 0; g < groups.size(); g++) {
+            EvGroup& G = groups[g];
+            bool g_ident = (G.ev.mask == 1);
+            if (g_ident != ident || !same_window(G.win, w)) continue;
+            if (!ident && (G.ev.internal_terms != s.internal_terms || G.ev.external_terms != s.external_terms)) continue;
+            found = (int)g;
+            break;
+        }
+        if (found < 0) {
+            EvGroup G;
+            G.win = w;
+            G.ev.mask = 0;
+            G.ev.NC = 0;
+            for (int f = 0; f < 8; f++) G.ev.off[f] = 0;
+            G.ev.internal_terms = s.internal_terms;
+            G.ev.external_terms = s.external_terms;
+            groups.push_back(G);
+            found = (int)groups.size() - 1;
+        }
+        EvGroup& G = groups[found];
+        if (!((G.ev.mask >> s.formula) & 1)) {
+            G.ev.mask |= 1 << s.formula;
+            G.ev.off[s.formula] = G.ev.NC;
+            G.ev.NC += formula_ncomp(s.formula);
+        }
+        G.specs.push_back(i);
+    }
+    return groups;
+}
+
+static int run_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
     const int nw = c->nw;
-    WbWindow win = make_window(s);
-    if (s.formula == WBGPU_IDENTITY) {
+    const WbWindow& win = G.win;
+    if (G.ev.NC > c->ev_ncmax) return set_err("scan: event buffer too small (plan/scan formula mismatch)");
+    if (G.ev.mask == 1) {
         int per = ((nw * (2 * 8 + 2 * 2)) + 7) / 8 * 8;
         int nt = nw <= 32 ? 64 : 32;
         if ((size_t)per * nt > 48 * 1024)
@@ -482,14 +544,21 @@ static int run_events(wbgpu_ctx* c, const wbgpu_scan_spec& s, long nk) {
         wb_identity_events_kernel<<<(unsigned)((nk + nt - 1) / nt), nt, (size_t)per * nt, c->stream>>>(c->d_E, nw, nk, win, c->d_evlabel,
                                                                                                  c->d_evval);
         c->launches++;
-    } else if (s.formula == WBGPU_OMEGA) {
-        if (c->L.off_dH[0] < 0 || (s.external_terms && c->L.off_A[0] < 0))
-            return set_err("scan: the plan does not hold the channels formula %d needs", s.formula);
-        WbFormulaFlags fl{s.formula, s.internal_terms, s.external_terms};
-        long nblk = std::min(nk, 148L * 32);
-        bool dmma = (nw <= 20) && (c->rotate_method != 1);
-        if (c->rotate_method == 2 && nw > 20) return set_err("rotate: the DMMA kernel needs num_wann <= 20");
-        if (dmma) {
+        CK(cudaGetLastError());
+        return 0;
+    }
+    WbNeeds need = wb_needs(G.ev.mask, G.ev.external_terms);
+    const WbLayout& L = c->L;
+    if ((need.V && L.off_dH[0] < 0) || (need.A && L.off_A[0] < 0) || (need.B && L.off_B[0] < 0) ||
+        ((need.Oblk || need.Odiag) && L.off_O[0] < 0) || ((need.Cblk || need.Cdiag) && L.off_C[0] < 0) ||
+        ((need.Sblk || need.Sdiag) && L.off_S[0] < 0))
+        return set_err("scan: the plan does not hold the channels that formula mask 0x%x needs", G.ev.mask);
+    long nblk = std::min(nk, 148L * 32);
+    bool omega_only = (G.ev.mask == (1 << WBGPU_OMEGA));
+    bool dmma = omega_only && (nw <= 20) && (c->rotate_method != 1);
+    if (c->rotate_method == 2 && !dmma) return set_err("rotate: the DMMA kernel covers Omega with num_wann <= 20 only");
+    if (dmma) {
+        WbFormulaFlags fl{WBGPU_OMEGA, G.ev.internal_terms, G.ev.external_terms};
 #define WB_DMMA_CASE(KS, MT2)                                                                                         \
     {                                                                                                                 \
         size_t smem = wb_dmma_smem_bytes(nw, KS);                                                                     \
@@ -498,25 +567,24 @@ static int run_events(wbgpu_ctx* c, const wbgpu_scan_spec& s, long nk) {
         wb_omega_events_dmma_kernel<KS, MT2><<<(unsigned)nblk, 128, smem, c->stream>>>(c->d_X, c->L, nk, c->d_E, c->d_U, \
                                                                                    win, fl, c->d_evlabel, c->d_evval); \
     }
-            if (nw <= 4) WB_DMMA_CASE(2, 1)
-            else if (nw <= 8) WB_DMMA_CASE(4, 2)
-            else if (nw <= 12) WB_DMMA_CASE(6, 3)
-            else if (nw <= 16) WB_DMMA_CASE(8, 4)
-            else if (nw <= 18) WB_DMMA_CASE(9, 5)
-            else WB_DMMA_CASE(10, 5)
+        if (nw <= 4) WB_DMMA_CASE(2, 1)
+        else if (nw <= 8) WB_DMMA_CASE(4, 2)
+        else if (nw <= 12) WB_DMMA_CASE(6, 3)
+        else if (nw <= 16) WB_DMMA_CASE(8, 4)
+        else if (nw <= 18) WB_DMMA_CASE(9, 5)
+        else WB_DMMA_CASE(10, 5)
 #undef WB_DMMA_CASE
-        } else {
-            constexpr int NT = 128;
-            size_t smem = sizeof(cplx) * (size_t)(9 * nw * nw + 3 * nw) + sizeof(double) * 5 * nw + sizeof(short) * 2 * nw + 16;
-            if ((int)smem > c->smem_optin) return set_err("rotate(generic): num_wann=%d needs %zu B shared memory", nw, smem);
-            CK(cudaFuncSetAttribute(wb_omega_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            wb_omega_events_kernel<NT><<<(unsigned)nblk, NT, smem, c->stream>>>(c->d_X, c->L, nk, c->d_E, c->d_U, win, fl,
-                                                                            c->d_evlabel, c->d_evval);
-        }
-        c->launches++;
     } else {
-        return set_err("scan: formula %d is not implemented on the GPU path yet", s.formula);
+        constexpr int NT = 128;
+        size_t smem = wb_generic_smem_bytes(nw, G.ev.mask, G.ev.external_terms);
+        if ((int)smem > c->smem_optin)
+            return set_err("rotate(generic): num_wann=%d with formula mask 0x%x needs %zu B shared memory (max %d)", nw,
+                           G.ev.mask, smem, c->smem_optin);
+        CK(cudaFuncSetAttribute(wb_events_generic_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wb_events_generic_kernel<NT><<<(unsigned)nblk, NT, smem, c->stream>>>(c->d_X, c->L, nk, c->d_E, c->d_U, win, G.ev,
+                                                                          c->d_evlabel, c->d_evval);
     }
+    c->launches++;
     CK(cudaGetLastError());
     return 0;
 }
@@ -561,6 +629,7 @@ extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK
     const int nw = c->nw;
     bool need_U = false;
     for (int i = 0; i < nspec; i++) need_U |= (specs[i].formula != WBGPU_IDENTITY);
+    std::vector<EvGroup> groups = make_groups(specs, nspec);
 
     for (int b0 = 0; b0 < nblocks; b0 += c->nb_max) {
         int nb = std::min(c->nb_max, nblocks - b0);
@@ -571,23 +640,25 @@ extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK
         stage_begin(c, WBGPU_STAGE_EIGH);
         if (run_eigh(c, nk, need_U)) return 1;
         stage_end(c);
-        for (int i = 0; i < nspec; i++) {
-            const wbgpu_scan_spec& s = specs[i];
-            stage_begin(c, s.formula == WBGPU_IDENTITY ? WBGPU_STAGE_IDENTITY : WBGPU_STAGE_ROTATE);
-            if (run_events(c, s, nk)) return 1;
+        for (const EvGroup& G : groups) {
+            stage_begin(c, G.ev.mask == 1 ? WBGPU_STAGE_IDENTITY : WBGPU_STAGE_ROTATE);
+            if (run_events(c, G, nk)) return 1;
             stage_end(c);
             stage_begin(c, WBGPU_STAGE_SCAN);
-            WbWindow w = make_window(s);
-            int ncomp = formula_ncomp(s.formula);
-            size_t hbytes = sizeof(double) * (size_t)(w.nEFx + 1) * ncomp;
-            int use_smem = hbytes <= 96 * 1024;
-            if (use_smem)
-                CK(cudaFuncSetAttribute(wb_scan_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            long nslots = nk * nw;
-            long nblk = std::min((nslots + 255) / 256, 148L * 2);
-            wb_scan_accumulate_kernel<<<(unsigned)nblk, 256, use_smem ? hbytes : 0, c->stream>>>(
-                c->d_evlabel, c->d_evval, nslots, (int)(c->nk_block * nw), weight_dev + b0, ncomp, w, c->d_hist + hoff[i], use_smem);
-            c->launches++;
+            for (int i : G.specs) {
+                const wbgpu_scan_spec& s = specs[i];
+                int ncomp = formula_ncomp(s.formula);
+                size_t hbytes = sizeof(double) * (size_t)(G.win.nEFx + 1) * ncomp;
+                int use_smem = hbytes <= 96 * 1024;
+                if (use_smem)
+                    CK(cudaFuncSetAttribute(wb_scan_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                long nslots = nk * nw;
+                long nblk = std::min((nslots + 255) / 256, 148L * 2);
+                wb_scan_accumulate_kernel<<<(unsigned)nblk, 256, use_smem ? hbytes : 0, c->stream>>>(
+                    c->d_evlabel, c->d_evval + G.ev.off[s.formula], G.ev.NC, nslots, (int)(c->nk_block * nw), weight_dev + b0,
+                    ncomp, G.win, c->d_hist + hoff[i], use_smem);
+                c->launches++;
+            }
             stage_end(c);
             CK(cudaGetLastError());
         }
@@ -753,7 +824,8 @@ extern "C" int wbgpu_band_traces(wbgpu_ctx* c, const double dK[3], const wbgpu_s
     if (run_fourier(c, c->d_dK, 1)) return 1;
     if (run_eigh(c, nk, true)) return 1;
     CK(cudaMemsetAsync(c->d_evval, 0, sizeof(double) * nk * c->nw * ncomp, c->stream));
-    if (run_events(c, *spec, nk)) return 1;
+    std::vector<EvGroup> groups = make_groups(spec, 1);
+    if (run_events(c, groups[0], nk)) return 1;
     CK(cudaMemcpyAsync(E_label, c->d_evlabel, sizeof(double) * nk * c->nw, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(value, c->d_evval, sizeof(double) * nk * c->nw * ncomp, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
