@@ -30,13 +30,14 @@ __device__ __forceinline__ cplx shfl_c(cplx v, int src) {
 // ------------------------------------------------------------------------------------------ K1
 // Output: d[ik][nw], e[ik][nw] (e[nw-1] = 0), tau[ik][nw], V = A rows (Householder vector k in
 // column k, rows k+2..nw-1) written to Vout[ik][nw][nw].
-template <int NWP, int WARPS>
+// EXACT: nw == NWP is known at compile time, every bounds guard folds away.
+template <int NWP, int WARPS, bool EXACT>
 __global__ void __launch_bounds__(WARPS * 32)
 wb_tridiag_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, double* __restrict__ dout,
                   double* __restrict__ eout, cplx* __restrict__ tauout, cplx* __restrict__ Vout) {
     __shared__ cplx vs_all[WARPS][32];
     __shared__ cplx ws_all[WARPS][32];
-    const int nw = L.nw;
+    const int nw = EXACT ? NWP : L.nw;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     cplx* vs = vs_all[warp];
     cplx* ws = ws_all[warp];
@@ -80,11 +81,14 @@ wb_tridiag_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, do
                 vs[lane] = v;
                 __syncwarp();
                 // x = tau * A v   (rows > k)
-                cplx x = cmake(0., 0.);
+                cplx x0 = cmake(0., 0.), x1 = cmake(0., 0.);  // two chains: halves the dependent-FMA latency
 #pragma unroll
                 for (int j = k + 1; j < NWP; j++)
-                    if (j < nw) cfma(x, a[j], vs[j]);
-                x = cmul(tau, x);
+                    if (j < nw) {
+                        if ((j - k) & 1) cfma(x0, a[j], vs[j]);
+                        else cfma(x1, a[j], vs[j]);
+                    }
+                cplx x = cmul(tau, cadd(x0, x1));
                 if (lane <= k || lane >= nw) x = cmake(0., 0.);
                 // dot = x^H v
                 cplx pd = cconjmul(x, v);
@@ -197,14 +201,15 @@ wb_tql_kernel(int nw, long nk, double* __restrict__ dio, const double* __restric
 }
 
 // ------------------------------------------------------------------------------------------ K3
-template <int NWP, int WARPS>
+template <int NWP, int WARPS, bool EXACT>
 __global__ void __launch_bounds__(WARPS * 32)
-wb_eigvec_kernel(int nw, long k0, long nk, const double* __restrict__ dvals, const cplx* __restrict__ tauin,
+wb_eigvec_kernel(int nw_rt, long k0, long nk, const double* __restrict__ dvals, const cplx* __restrict__ tauin,
                  const double2* __restrict__ rot, int capR, const int* __restrict__ hdr, int capS,
                  const int* __restrict__ nsweep, double* __restrict__ Eout, cplx* __restrict__ VU,
                  int* __restrict__ fail_list, int* __restrict__ nfail) {
     extern __shared__ cplx smem_v[];
     // per warp: V[nw][nw] (Householder vectors), Zs[nw][nw+1] doubles (transpose), cs[32], tau[nw]
+    const int nw = EXACT ? NWP : nw_rt;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_warp = nw * nw + (nw * (nw + 1) + 1) / 2 + 32 + nw;
     cplx* V = smem_v + (size_t)warp * per_warp;
@@ -277,10 +282,14 @@ wb_eigvec_kernel(int nw, long k0, long nk, const double* __restrict__ dvals, con
             cplx tau = taus[k];
             if (tau.x != 0. || tau.y != 0.) {  // uniform
                 cplx sdot = u[k + 1];  // v[k+1] = 1
+                cplx sdot1 = cmake(0., 0.);
 #pragma unroll
                 for (int i = k + 2; i < NWP; i++)
-                    if (i < nw) cfma_conj(sdot, V[i * nw + k], u[i]);
-                cplx ts = cmul(tau, sdot);
+                    if (i < nw) {
+                        if ((i - k) & 1) cfma_conj(sdot1, V[i * nw + k], u[i]);
+                        else cfma_conj(sdot, V[i * nw + k], u[i]);
+                    }
+                cplx ts = cmul(tau, cadd(sdot, sdot1));
                 u[k + 1] = csub(u[k + 1], ts);
 #pragma unroll
                 for (int i = k + 2; i < NWP; i++)

@@ -434,12 +434,12 @@ static int launch_jacobi(wbgpu_ctx* c, long k0, long nk, bool want_U, const int*
     return 0;
 }
 
-template <int NWP>
+template <int NWP, bool EXACT>
 static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
     const int nw = c->nw;
     constexpr int WARPS = 4;
     CK(cudaMemsetAsync(c->d_nfail, 0, sizeof(int), c->stream));
-    wb_tridiag_kernel<NWP, WARPS><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, 0, c->stream>>>(
+    wb_tridiag_kernel<NWP, WARPS, EXACT><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, 0, c->stream>>>(
         c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U);
     CK(cudaGetLastError());
     if (nw <= 24) {
@@ -453,8 +453,8 @@ static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
     }
     CK(cudaGetLastError());
     size_t smem3 = sizeof(cplx) * WARPS * (size_t)(nw * nw + (nw * (nw + 1) + 1) / 2 + 32 + nw);
-    CK(cudaFuncSetAttribute(wb_eigvec_kernel<NWP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    wb_eigvec_kernel<NWP, WARPS><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, smem3, c->stream>>>(
+    CK(cudaFuncSetAttribute(wb_eigvec_kernel<NWP, WARPS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    wb_eigvec_kernel<NWP, WARPS, EXACT><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, smem3, c->stream>>>(
         nw, k0, nk, c->d_dw, c->d_tau, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep, c->d_E, c->d_U, c->d_faillist,
         c->d_nfail);
     c->launches += 3;
@@ -472,10 +472,14 @@ static int run_eigh(wbgpu_ctx* c, long nk, bool want_U) {
     for (long k0 = 0; k0 < nk; k0 += c->eig_chunk) {
         long n = std::min(c->eig_chunk, nk - k0);
         int rc;
-        if (nw <= 8) rc = launch_ql<8>(c, k0, n);
-        else if (nw <= 16) rc = launch_ql<16>(c, k0, n);
-        else if (nw <= 24) rc = launch_ql<24>(c, k0, n);
-        else rc = launch_ql<32>(c, k0, n);
+        if (nw == 18) rc = launch_ql<18, true>(c, k0, n);
+        else if (nw == 16) rc = launch_ql<16, true>(c, k0, n);
+        else if (nw == 24) rc = launch_ql<24, true>(c, k0, n);
+        else if (nw == 32) rc = launch_ql<32, true>(c, k0, n);
+        else if (nw <= 8) rc = launch_ql<8, false>(c, k0, n);
+        else if (nw <= 16) rc = launch_ql<16, false>(c, k0, n);
+        else if (nw <= 24) rc = launch_ql<24, false>(c, k0, n);
+        else rc = launch_ql<32, false>(c, k0, n);
         if (rc) return rc;
     }
     return 0;
