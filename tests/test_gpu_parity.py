@@ -177,7 +177,7 @@ def test_eigh_golden_block(wb, fe):
     assert relerr(eng.eig(b["dK"]), b["E_K"]) < 1e-12
 
 
-@pytest.mark.parametrize("rotate_method", [1, 2])
+@pytest.mark.parametrize("rotate_method", [1, 2, 3])
 @pytest.mark.parametrize("kw", [dict(), dict(degen_thresh=0.05), dict(degen_Kramers=True),
                                 dict(kwargs_formula=dict(external_terms=False)),
                                 dict(kwargs_formula=dict(internal_terms=False))])
@@ -187,7 +187,7 @@ def test_omega_band_traces(wb, fe, fe_orc, orc, kw, rotate_method):
     NKFFT, dK, Ef = b["NKFFT"], b["dK"], b["Efermi"]
     calc = wb.calculators.static.AHC(Efermi=Ef, **kw)
     eng = wb.Engine(fe)
-    eng.set_option("rotate_method", rotate_method)  # 1 = generic shared-memory kernel, 2 = DMMA kernel
+    eng.set_option("rotate_method", rotate_method)  # 1 = generic shared-memory kernel, 2 = runtime-nw DMMA kernel, 3 = compile-time-NW DMMA kernel
     eng.plan(NKFFT, all_formulae())
     lab, val = eng.band_traces(dK, calc.specs()[0])
     data = orc.OracleDataK(fe_orc, dK, NKFFT)

@@ -23,6 +23,7 @@
 #include "wb_rotate_formula.cuh"
 #include "wb_rotate_dmma.cuh"
 #include "wb_events_generic.cuh"
+#include "wb_rotate_mma.cuh"
 #include "wb_scan.cuh"
 #include "wb_probe.cuh"
 
@@ -536,6 +537,35 @@ static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec)
     return groups;
 }
 
+template <int NW>
+static int launch_mma_t(wbgpu_ctx* c, const EvGroup& G, long nk, WbMmaPlan P) {
+    size_t smem = wb_mma_smem_bytes<NW>(P);
+    if ((int)smem > c->smem_optin) return -1;
+    CK(cudaFuncSetAttribute(wb_events_mma_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    long nblk = std::min(nk, (long)sms * 2);
+    wb_events_mma_kernel<NW><<<(unsigned)nblk, 128, smem, c->stream>>>(c->d_X, c->L, P, nk, c->d_E, c->d_U, G.win, G.ev,
+                                                                   c->d_evlabel, c->d_evval);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// returns -1 when this kernel does not cover the request
+static int launch_mma_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
+    WbMmaPlan P;
+#define WB_MMA_CASE(NWC)                                                                            \
+    case NWC:                                                                                       \
+        if (!wb_mma_make_plan<NWC>(c->L, G.ev.mask, G.ev.external_terms, &P)) return -1;            \
+        return launch_mma_t<NWC>(c, G, nk, P);
+    switch (c->nw) {
+        WB_MMA_CASE(18)
+        default: return -1;
+    }
+#undef WB_MMA_CASE
+}
+
 static int run_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
     const int nw = c->nw;
     const WbWindow& win = G.win;
@@ -557,6 +587,12 @@ static int run_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
         ((need.Oblk || need.Odiag) && L.off_O[0] < 0) || ((need.Cblk || need.Cdiag) && L.off_C[0] < 0) ||
         ((need.Sblk || need.Sdiag) && L.off_S[0] < 0))
         return set_err("scan: the plan does not hold the channels that formula mask 0x%x needs", G.ev.mask);
+    // compile-time-NW tensor-core kernel (Omega and/or Morb_Hpm)
+    if (c->rotate_method == 0 || c->rotate_method == 3) {
+        int rc = launch_mma_events(c, G, nk);
+        if (rc >= 0) return rc;
+        if (c->rotate_method == 3) return set_err("rotate: the NW-templated DMMA kernel does not cover num_wann=%d, mask 0x%x", nw, G.ev.mask);
+    }
     long nblk = std::min(nk, 148L * 32);
     bool omega_only = (G.ev.mask == (1 << WBGPU_OMEGA));
     bool dmma = omega_only && (nw <= 20) && (c->rotate_method != 1);
