@@ -17,6 +17,7 @@
 // Jacobi kernel (wb_eigh_jacobi.cuh).
 #pragma once
 #include "wb_common.cuh"
+#include "wb_tma.cuh"
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -197,57 +198,71 @@ wb_tql_kernel(int nw, long nk, double* __restrict__ dio, const double* __restric
         }
     }
     for (int i = 0; i < nw; i++) dio[t * nw + i] = d[i * NT];
-    nsweep[t] = fail ? -1 : ns;
+    nsweep[t] = fail ? -1 : (ns | (nr << 12));   // sweeps | rotations << 12
 }
 
 // ------------------------------------------------------------------------------------------ K3
+// Per warp: ONE set of TMA bulk copies brings the Householder vectors, tau, the sweep headers and the whole
+// rotation stream of the k-point into shared memory (a single exposed latency instead of one per sweep).
+__host__ __device__ inline int wb_eigvec_smem_per_warp(int nw, int capR, int capS) {  // in 16-byte units
+    return nw * nw + (nw * (nw + 1) + 1) / 2 + nw + capR + (capS + 3) / 4 + 1;
+}
+
 template <int NWP, int WARPS, bool EXACT>
 __global__ void __launch_bounds__(WARPS * 32)
 wb_eigvec_kernel(int nw_rt, long k0, long nk, const double* __restrict__ dvals, const cplx* __restrict__ tauin,
                  const double2* __restrict__ rot, int capR, const int* __restrict__ hdr, int capS,
                  const int* __restrict__ nsweep, double* __restrict__ Eout, cplx* __restrict__ VU,
                  int* __restrict__ fail_list, int* __restrict__ nfail) {
-    extern __shared__ cplx smem_v[];
-    // per warp: V[nw][nw] (Householder vectors), Zs[nw][nw+1] doubles (transpose), cs[32], tau[nw]
+    extern __shared__ __align__(16) cplx smem_v[];
+    // per warp: V[nw][nw] (Householder vectors), Zs[nw][nw+1] doubles (transpose), tau[nw], rot[capR], hdr[capS], mbarrier
     const int nw = EXACT ? NWP : nw_rt;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = nw * nw + (nw * (nw + 1) + 1) / 2 + 32 + nw;
+    const int per_warp = wb_eigvec_smem_per_warp(nw, capR, capS);
     cplx* V = smem_v + (size_t)warp * per_warp;
     double* Zs = (double*)(V + nw * nw);
-    double2* cs = (double2*)(V + nw * nw + (nw * (nw + 1) + 1) / 2);
-    cplx* taus = (cplx*)(cs + 32);
+    cplx* taus = V + nw * nw + (nw * (nw + 1) + 1) / 2;
+    const double2* rots = (const double2*)(taus + nw);
+    const int* hdrs = (const int*)(rots + capR);
+    uint64_t* bar = (uint64_t*)(hdrs + (capS + 3) / 4 * 4);
     long t = (long)blockIdx.x * WARPS + warp;
     if (t >= nk) return;
     long ik = k0 + t;
-    const int ns = nsweep[t];
-    if (ns < 0) {
+    const int nsr = nsweep[t];
+    if (nsr < 0) {
         if (lane == 0) fail_list[atomicAdd(nfail, 1)] = (int)t;
         return;
     }
-    // stage Householder data
-    for (int x = lane; x < nw * nw; x += 32) V[x] = VU[ik * nw * nw + x];
-    if (lane < nw) taus[lane] = tauin[t * nw + lane];
+    const int ns = nsr & 4095, nr = nsr >> 12;
+    if (lane == 0) {
+        wb_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        const uint32_t bV = (uint32_t)(nw * nw * 16), bT = (uint32_t)(nw * 16), bR = (uint32_t)(nr * 16),
+                       bH = (uint32_t)((ns + 3) / 4 * 16);
+        wb_mbar_expect_tx(bar, bV + bT + bR + bH);
+        wb_bulk_g2s(V, VU + ik * nw * nw, bV, bar);
+        wb_bulk_g2s(taus, tauin + t * nw, bT, bar);
+        if (bR) wb_bulk_g2s((void*)rots, rot + (size_t)t * capR, bR, bar);
+        if (bH) wb_bulk_g2s((void*)hdrs, hdr + (size_t)t * capS, bH, bar);
+    }
+    double myd = (lane < nw) ? dvals[t * nw + lane] : CUDART_INF;
+    __syncwarp();
+    wb_mbar_wait(bar, 0);
     // ---- replay the rotation stream on Z = I (lane = row)
     double z[NWP];
 #pragma unroll
     for (int j = 0; j < NWP; j++) z[j] = (j == lane) ? 1. : 0.;
-    const double2* myrot = rot + (size_t)t * capR;
-    const int* myhdr = hdr + (size_t)t * capS;
     int r0 = 0;
-    int h = (ns > 0) ? myhdr[0] : 0;
     for (int s = 0; s < ns; s++) {
-        int l = h & 255, m = h >> 8;
-        int cnt = m - l;
-        __syncwarp();
-        if (lane < cnt) cs[lane] = myrot[r0 + lane];
-        if (s + 1 < ns) h = myhdr[s + 1];
-        __syncwarp();
-        r0 += cnt;
+        const int h = hdrs[s];
+        const int l = h & 255, m = h >> 8;
+        const double2* cs = rots + r0 + (m - 1);   // rotation of index i sits at cs[-i]
+        r0 += m - l;
 #pragma unroll
         for (int ii = 0; ii < NWP - 1; ii++) {
             const int i = NWP - 2 - ii;
             if (i < m && i >= l) {  // uniform
-                double2 q = cs[m - 1 - i];
+                double2 q = cs[-i];
                 double f = z[i + 1];
                 z[i + 1] = q.y * z[i] + q.x * f;
                 z[i] = q.x * z[i] - q.y * f;
@@ -255,7 +270,6 @@ wb_eigvec_kernel(int nw_rt, long k0, long nk, const double* __restrict__ dvals, 
         }
     }
     // ---- sort: rank of eigenvalue `lane`
-    double myd = (lane < nw) ? dvals[t * nw + lane] : CUDART_INF;
     int rank = 0;
     for (int j = 0; j < nw; j++) {
         double dj = __shfl_sync(0xffffffffu, myd, j);

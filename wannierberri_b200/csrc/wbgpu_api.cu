@@ -351,7 +351,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     if (nw <= 32) {
         c->eig_chunk = std::min<long>((long)nkl, 65536);
         c->capR = 2 * nw * nw + 32;
-        c->capS = 6 * nw + 8;
+        c->capS = (6 * nw + 8 + 3) / 4 * 4;  // 16-byte granular (bulk copies)
         size_t ch = (size_t)c->eig_chunk;
         CK(cudaMalloc(&c->d_dw, sizeof(double) * ch * nw));
         CK(cudaMalloc(&c->d_ew, sizeof(double) * ch * nw));
@@ -453,9 +453,11 @@ static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
             nw, nk, c->d_dw, c->d_ew, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep);
     }
     CK(cudaGetLastError());
-    size_t smem3 = sizeof(cplx) * WARPS * (size_t)(nw * nw + (nw * (nw + 1) + 1) / 2 + 32 + nw);
-    CK(cudaFuncSetAttribute(wb_eigvec_kernel<NWP, WARPS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    wb_eigvec_kernel<NWP, WARPS, EXACT><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, smem3, c->stream>>>(
+    constexpr int EW = 2;  // warps per CTA of the eigenvector kernel (19.6 KB of shared memory per warp at nw = 18)
+    size_t smem3 = sizeof(cplx) * EW * (size_t)wb_eigvec_smem_per_warp(nw, c->capR, c->capS);
+    if ((int)smem3 > c->smem_optin) return set_err("eigh(QL): num_wann=%d needs %zu B shared memory", nw, smem3);
+    CK(cudaFuncSetAttribute(wb_eigvec_kernel<NWP, EW, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    wb_eigvec_kernel<NWP, EW, EXACT><<<(unsigned)((nk + EW - 1) / EW), EW * 32, smem3, c->stream>>>(
         nw, k0, nk, c->d_dw, c->d_tau, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep, c->d_E, c->d_U, c->d_faillist,
         c->d_nfail);
     c->launches += 3;
