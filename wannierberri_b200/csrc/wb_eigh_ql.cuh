@@ -38,20 +38,24 @@ wb_tridiag_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, do
                   double* __restrict__ eout, cplx* __restrict__ tauout, cplx* __restrict__ Vout) {
     __shared__ cplx vs_all[WARPS][32];
     __shared__ cplx ws_all[WARPS][32];
+    __shared__ cplx hs_all[WARPS][NWP * (NWP + 1) / 2];   // packed upper triangle of H, staged coalesced
     const int nw = EXACT ? NWP : L.nw;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     cplx* vs = vs_all[warp];
     cplx* ws = ws_all[warp];
+    cplx* hs = hs_all[warp];
     long t = (long)blockIdx.x * WARPS + warp;
     if (t >= nk) return;
     long ik = k0 + t;
     const cplx* H = rec + ik * L.E + L.off_H;
+    for (int x = lane; x < nw * (nw + 1) / 2; x += 32) hs[x] = H[x];
+    __syncwarp();
     cplx a[NWP];
 #pragma unroll
     for (int j = 0; j < NWP; j++) {
         a[j] = cmake(0., 0.);
         if (j < nw && lane < nw) {
-            a[j] = (lane <= j) ? H[tri_index(lane, j, nw)] : cconj(H[tri_index(j, lane, nw)]);
+            a[j] = (lane <= j) ? hs[tri_index(lane, j, nw)] : cconj(hs[tri_index(j, lane, nw)]);
             if (j == lane) a[j].y = 0.;
         }
     }
@@ -70,7 +74,8 @@ wb_tridiag_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, do
             cplx v = cmake(0., 0.);
             if (xnorm2 != 0. || alpha.y != 0.) {  // zlarfg
                 beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xnorm2), alpha.x);
-                tau = cmake((beta - alpha.x) / beta, -alpha.y / beta);
+                const double binv = 1. / beta;
+                tau = cmake((beta - alpha.x) * binv, -alpha.y * binv);
                 cplx den = cmake(alpha.x - beta, alpha.y);
                 double dn = 1. / (den.x * den.x + den.y * den.y);
                 cplx scale = cmake(den.x * dn, -den.y * dn);
@@ -103,10 +108,15 @@ wb_tridiag_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, do
 #pragma unroll
                     for (int j = k + 1; j < NWP; j++)
                         if (j < nw) {
-                            cplx t1 = cmulc(v, ws[j]);
-                            cplx t2 = cmulc(w, vs[j]);
-                            a[j].x -= t1.x + t2.x;
-                            a[j].y -= t1.y + t2.y;
+                            const cplx wj = ws[j], vj = vs[j];   // a -= v conj(w_j) + w conj(v_j): 8 FMA
+                            a[j].x = fma(-v.x, wj.x, a[j].x);
+                            a[j].y = fma(-v.y, wj.x, a[j].y);
+                            a[j].x = fma(-v.y, wj.y, a[j].x);
+                            a[j].y = fma(v.x, wj.y, a[j].y);
+                            a[j].x = fma(-w.x, vj.x, a[j].x);
+                            a[j].y = fma(-w.y, vj.x, a[j].y);
+                            a[j].x = fma(-w.y, vj.y, a[j].x);
+                            a[j].y = fma(w.x, vj.y, a[j].y);
                         }
                 }
                 __syncwarp();
@@ -172,15 +182,17 @@ wb_tql_kernel(int nw, long nk, double* __restrict__ dio, const double* __restric
             for (; i >= l; i--) {
                 double f = s * e[i * NT];
                 double b = c * e[i * NT];
-                r = hypot(f, g);
+                r = sqrt(f * f + g * g);
+                if (!(r > 1e-140 && r < 1e140)) r = hypot(f, g);   // out of the safe range of the plain formula
                 e[(i + 1) * NT] = r;
                 if (r == 0.) {  // recover from underflow: identity rotations for the rest of the sweep
                     d[(i + 1) * NT] -= p;
                     e[m * NT] = 0.;
                     break;
                 }
-                s = f / r;
-                c = g / r;
+                const double rinv = 1. / r;
+                s = f * rinv;
+                c = g * rinv;
                 g = d[(i + 1) * NT] - p;
                 r = (d[i * NT] - g) * s + 2. * c * b;
                 p = s * r;
