@@ -146,6 +146,61 @@ wb_axis_dft_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, const cp
         if (k0 + kk < N) dst[(long)kk * S] = acc[kk];
 }
 
+// ------------------------------------------------------------------------------------------
+// Axes 1 and 0 in ONE pass:
+//   X[b][k0][k1][t] = sum_{r0} W0[b][k0][r0] * ( sum_{r1} W1[b][k1][r1] * Z[b][r0][r1][t] ),   t < S2 = N2 * E
+// The intermediate Y[r0][k1][..] of the separable transform never goes to memory: a CTA stages the Z tile of TB
+// inner indices (n0*n1*TB complex, read once, L2 resident) in shared memory and writes all N0*N1 outputs of those
+// indices, so the only HBM stream is the k-space record X itself (the algorithmic 16*E bytes per k-point).
+// Thread = one inner index; KC accumulators over k0; twiddles are warp-uniform shared-memory broadcasts.
+// ------------------------------------------------------------------------------------------
+template <int KC, int TB>
+__global__ void __launch_bounds__(TB)
+wb_axis10_fused_kernel(const cplx* __restrict__ Z, cplx* __restrict__ X, const cplx* __restrict__ W1,
+                       const cplx* __restrict__ W0, int n0, int n1, int N0, int N1, long S2, long z_bstride,
+                       long x_bstride) {
+    extern __shared__ cplx sm_f[];
+    const int nchunk = (N0 + KC - 1) / KC;
+    cplx* Zs = sm_f;                          // [n0*n1][TB]
+    cplx* W1s = Zs + (size_t)n0 * n1 * TB;    // [N1][n1]
+    cplx* W0s = W1s + N1 * n1;                // [nchunk*KC][n0], zero beyond N0
+    const int b = blockIdx.z;
+    const long t = (long)blockIdx.x * TB + threadIdx.x;
+    for (int x = threadIdx.x; x < N1 * n1; x += TB) W1s[x] = W1[(long)b * N1 * n1 + x];
+    for (int x = threadIdx.x; x < nchunk * KC * n0; x += TB)
+        W0s[x] = (x < N0 * n0) ? W0[(long)b * N0 * n0 + x] : cmake(0., 0.);
+    const cplx* zsrc = Z + (long)b * z_bstride + t;
+    for (int x = 0; x < n0 * n1; x++) Zs[x * TB + threadIdx.x] = (t < S2) ? __ldg(zsrc + (long)x * S2) : cmake(0., 0.);
+    __syncthreads();
+    if (t >= S2) return;
+    cplx* dst = X + (long)b * x_bstride + t;
+    for (int k1 = 0; k1 < N1; k1++) {
+        const cplx* w1 = W1s + k1 * n1;
+        for (int c0 = 0; c0 < N0; c0 += KC) {
+            cplx acc[KC];
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) acc[kk] = cmake(0., 0.);
+            const cplx* w0 = W0s + c0 * n0;
+            for (int r0 = 0; r0 < n0; r0++) {
+                const cplx* zrow = Zs + (size_t)r0 * n1 * TB + threadIdx.x;
+                cplx y0 = cmake(0., 0.), y1 = cmake(0., 0.);
+                int r1 = 0;
+                for (; r1 + 1 < n1; r1 += 2) {
+                    cfma(y0, w1[r1], zrow[r1 * TB]);
+                    cfma(y1, w1[r1 + 1], zrow[(r1 + 1) * TB]);
+                }
+                if (r1 < n1) cfma(y0, w1[r1], zrow[r1 * TB]);
+                const cplx y = cadd(y0, y1);
+#pragma unroll
+                for (int kk = 0; kk < KC; kk++) cfma(acc[kk], w0[kk * n0 + r0], y);
+            }
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++)
+                if (c0 + kk < N0) dst[((long)(c0 + kk) * N1 + k1) * S2] = acc[kk];
+        }
+    }
+}
+
 // k-points of a K-block, bit-identical to the reference:
 //   points_FFT = ix * (1./N)   (grid/grid.py:68-75) ;  kpoints_all = (points_FFT + dK) % 1  (data_K.py:146-151)
 __global__ void wb_kpoints_kernel(const double* __restrict__ dK, int3 N, double* __restrict__ kpts) {

@@ -67,18 +67,31 @@ wb_scan_accumulate_kernel(const double* __restrict__ ev_label, const double* __r
 }
 
 // restot[e] = below + sum_{e' <= e} hist[e'] ; stencil (static.py:137-147) ; * scale.
-// One thread per component; the Fermi axis (<= a few thousand) is walked serially.
-__global__ void wb_scan_finalize_kernel(const double* __restrict__ hist, double* __restrict__ cum, int ncomp,
-                                        int nEFx, int nEF, int fder, double dEF, double scale,
-                                        double* __restrict__ out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncomp) return;
-    double run = hist[c];
-    for (int e = 0; e < nEFx; e++) {
+// One CTA per component: chunked running sum over the Fermi axis (thread = contiguous chunk, chunk offsets by a
+// serial pass over 256 partial sums), then the finite-difference stencil.
+__global__ void __launch_bounds__(256)
+wb_scan_finalize_kernel(const double* __restrict__ hist, double* __restrict__ cum, int ncomp, int nEFx, int nEF,
+                        int fder, double dEF, double scale, double* __restrict__ out) {
+    __shared__ double part[256];
+    const int c = blockIdx.x;
+    const int per = (nEFx + 255) / 256;
+    const int e0 = threadIdx.x * per, e1 = min(e0 + per, nEFx);
+    double s = 0.;
+    for (int e = e0; e < e1; e++) s += hist[(1 + e) * ncomp + c];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = hist[c];  // "below" row
+        for (int i = 0; i < 256; i++) { double v = part[i]; part[i] = run; run += v; }
+    }
+    __syncthreads();
+    double run = part[threadIdx.x];
+    for (int e = e0; e < e1; e++) {
         run += hist[(1 + e) * ncomp + c];
         cum[e * ncomp + c] = run;
     }
-    for (int e = 0; e < nEF; e++) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < nEF; e += 256) {
         double v;
         if (fder == 0) v = cum[e * ncomp + c];
         else if (fder == 1) v = (cum[(e + 2) * ncomp + c] - cum[e * ncomp + c]) / (2. * dEF);

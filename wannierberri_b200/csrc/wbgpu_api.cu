@@ -86,6 +86,7 @@ struct wbgpu_ctx {
     int64_t launches = 0;
     int eig_method = 0;
     int ev_ncmax = 1;
+    int fourier_method = 0; // 0 = axes 1 and 0 fused (when the tile fits), 1 = three separate axis passes
     int rotate_method = 0;  // 0 = automatic, 1 = generic shared-memory DFMA kernel, 2 = DMMA kernel
     int smem_optin = 0;
     // optional per-stage device timing (option "timing"): events around each stage of each batch
@@ -213,6 +214,7 @@ extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return set_err("wbgpu_set_option: null pointer argument");
     if (!strcmp(name, "eig_method")) { c->eig_method = (int)value; return 0; }
     if (!strcmp(name, "rotate_method")) { c->rotate_method = (int)value; return 0; }
+    if (!strcmp(name, "fourier_method")) { c->fourier_method = (int)value; return 0; }
     if (!strcmp(name, "timing")) {
         c->timing = (int)value;
         for (int i = 0; i < WBGPU_NSTAGES; i++) { c->stage_ms[i] = 0; c->stage_calls[i] = 0; }
@@ -397,6 +399,42 @@ static int axis_dft(wbgpu_ctx* c, const cplx* in, cplx* out, const cplx* W, int 
     return 0;
 }
 
+template <int KC, int TB>
+static int launch_fused10(wbgpu_ctx* c, int nb, size_t smem) {
+    const int n0 = c->nbox.x, n1 = c->nbox.y;
+    const int* N = c->N;
+    const long S2 = (long)N[2] * c->L.E;
+    CK(cudaFuncSetAttribute(wb_axis10_fused_kernel<KC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((S2 + TB - 1) / TB), 1, (unsigned)nb);
+    wb_axis10_fused_kernel<KC, TB><<<grid, TB, smem, c->stream>>>(c->d_Z, c->d_X, c->d_W[1], c->d_W[0], n0, n1, N[0], N[1], S2,
+                                                              (long)n0 * n1 * S2, (long)N[0] * N[1] * S2);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// returns -1 when the fused kernel does not apply
+static int fused_axis10(wbgpu_ctx* c, int nb) {
+    const int n0 = c->nbox.x, n1 = c->nbox.y;
+    const int* N = c->N;
+    const int KC = N[0] <= 8 ? 8 : N[0] <= 12 ? 12 : N[0] <= 16 ? 16 : 20;
+    const int nchunk = (N[0] + KC - 1) / KC;
+    auto smem_for = [&](int TB) { return sizeof(cplx) * ((size_t)n0 * n1 * TB + (size_t)N[1] * n1 + (size_t)nchunk * KC * n0); };
+    int TB = 128;
+    while (TB >= 32 && smem_for(TB) > 110 * 1024) TB /= 2;
+    if (TB < 32) return -1;
+    size_t smem = smem_for(TB);
+#define WB_F10(KCV)                                                     \
+    if (KC == KCV) {                                                    \
+        if (TB == 128) return launch_fused10<KCV, 128>(c, nb, smem);    \
+        if (TB == 64) return launch_fused10<KCV, 64>(c, nb, smem);      \
+        return launch_fused10<KCV, 32>(c, nb, smem);                    \
+    }
+    WB_F10(8) WB_F10(12) WB_F10(16) WB_F10(20)
+#undef WB_F10
+    return -1;
+}
+
 // R->k for `nb` K-blocks whose shifts are dK_dev[nb][3]: fills c->d_X[nb][nk][E]
 static int run_fourier(wbgpu_ctx* c, const double* dK_dev, int nb) {
     const int n[3] = {c->nbox.x, c->nbox.y, c->nbox.z};
@@ -411,6 +449,12 @@ static int run_fourier(wbgpu_ctx* c, const double* dK_dev, int nb) {
     CK(cudaGetLastError());
     // axis 2: table[r0][r1][r2][e] -> Z[b][r0][r1][k2][e]
     if (axis_dft(c, c->d_table, c->d_Z, c->d_W[2], n[2], N[2], E, n[0] * n[1], 0, (long)n[0] * n[1] * N[2] * E, nb)) return 1;
+    // axes 1 and 0 fused: Z -> X[b][k0][k1][k2][e] without the intermediate Y (falls back to two passes when the
+    // Z tile of even 32 inner indices does not fit shared memory)
+    if (c->fourier_method != 1) {
+        int rc = fused_axis10(c, nb);
+        if (rc >= 0) return rc;
+    }
     // axis 1: -> Y[b][r0][k1][k2][e]
     if (axis_dft(c, c->d_Z, c->d_Y, c->d_W[1], n[1], N[1], (long)N[2] * E, n[0], (long)n[0] * n[1] * N[2] * E,
                  (long)n[0] * N[1] * N[2] * E, nb)) return 1;
@@ -711,7 +755,7 @@ extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK
         WbWindow w = make_window(s);
         int ncomp = formula_ncomp(s.formula);
         double scale = s.factor / (c->cell_volume * (double)c->nk_block);
-        wb_scan_finalize_kernel<<<(ncomp + 31) / 32, 32, 0, c->stream>>>(c->d_hist + hoff[i], d_cum, ncomp, w.nEFx, s.nEF, s.fder,
+        wb_scan_finalize_kernel<<<ncomp, 256, 0, c->stream>>>(c->d_hist + hoff[i], d_cum, ncomp, w.nEFx, s.nEF, s.fder,
                                                                        s.dEF, scale, out_dev + ooff);
         c->launches++;
         ooff += (size_t)s.nEF * ncomp;
