@@ -141,6 +141,139 @@ wb_tridiag_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, do
     }
 }
 
+// ------------------------------------------------------------------------------------------ K1b
+// Same reduction with TWO k-points per warp (16 lanes each) for 16 < NW <= 18: the last 16 rows of the matrix
+// live on the 16 lanes; the R0 = NW - 16 leading rows are never needed explicitly -- row 0 is never active, row 1
+// is active in step 0 only, where its elements are the conjugates of column 1 held by the other rows and all that
+// survives of it is its updated diagonal.  Twice the lane utilisation of wb_tridiag_kernel.
+__device__ __forceinline__ double half_sum(double v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+wb_tridiag2_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, double* __restrict__ dout,
+                   double* __restrict__ eout, cplx* __restrict__ tauout, cplx* __restrict__ Vout) {
+    static_assert(NW > 16 && NW <= 18, "two leading rows at most are handled implicitly");
+    constexpr int R0 = NW - 16, NTRI = NW * (NW + 1) / 2;
+    __shared__ cplx vs_all[WARPS * 2][NW];
+    __shared__ cplx ws_all[WARPS * 2][NW];
+    __shared__ cplx hs_all[WARPS * 2][NTRI];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = lane >> 4, hl = lane & 15, hbase = lane & 16;
+    const int row = hl + R0;
+    cplx* vs = vs_all[warp * 2 + half];
+    cplx* ws = ws_all[warp * 2 + half];
+    cplx* hs = hs_all[warp * 2 + half];
+    long t = ((long)blockIdx.x * WARPS + warp) * 2 + half;
+    const bool live = t < nk;
+    if (!live) t = nk - 1;   // the idle half mirrors the last k-point and writes nothing
+    const long ik = k0 + t;
+    const cplx* H = rec + ik * L.E + L.off_H;
+    for (int x = hl; x < NTRI; x += 16) hs[x] = H[x];
+    __syncwarp();
+    cplx a[NW];
+#pragma unroll
+    for (int j = 0; j < NW; j++) {
+        a[j] = (row <= j) ? hs[tri_index(row, j, NW)] : cconj(hs[tri_index(j, row, NW)]);
+        if (j == row) a[j].y = 0.;
+    }
+    double a11 = (R0 == 2) ? hs[tri_index(1, 1, NW)].x : 0.;   // diagonal of the implicit row 1
+    double* d = dout + t * NW;
+    double* e = eout + t * NW;
+    cplx* tau_o = tauout + t * NW;
+    if (live && hl == 0) d[0] = hs[0].x;   // row 0 is never touched (R0 >= 1)
+#pragma unroll
+    for (int k = 0; k < NW - 1; k++) {
+        const bool step0 = (R0 == 2 && k == 0);   // the pivot row k+1 = 1 is implicit
+        cplx xk = a[k];
+        double sq = (row > k + 1) ? (xk.x * xk.x + xk.y * xk.y) : 0.;
+        double xnorm2 = half_sum(sq);
+        cplx alpha;
+        if (step0) alpha = cconj(hs[tri_index(0, 1, NW)]);
+        else alpha = cmake(__shfl_sync(0xffffffffu, xk.x, hbase + (k + 1 - R0)), __shfl_sync(0xffffffffu, xk.y, hbase + (k + 1 - R0)));
+        cplx tau = cmake(0., 0.);
+        double beta = alpha.x;
+        cplx v = cmake(0., 0.);
+        if (xnorm2 != 0. || alpha.y != 0.) {  // zlarfg
+            beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xnorm2), alpha.x);
+            const double binv = 1. / beta;
+            tau = cmake((beta - alpha.x) * binv, -alpha.y * binv);
+            cplx den = cmake(alpha.x - beta, alpha.y);
+            double dn = 1. / (den.x * den.x + den.y * den.y);
+            cplx scale = cmake(den.x * dn, -den.y * dn);
+            if (row > k + 1) v = cmul(xk, scale);
+        }
+        if (row == k + 1) v = cmake(1., 0.);
+        const bool active = (tau.x != 0. || tau.y != 0.);  // uniform within the half-warp
+        // (both halves run the body; an inactive half works on tau = 0, which leaves its matrix unchanged)
+        {
+            __syncwarp();
+            if (row > k) vs[row] = v;
+            if (step0 && hl == 0) vs[1] = cmake(1., 0.);
+            __syncwarp();
+            // x = tau * A v   (rows > k)
+            cplx x0 = cmake(0., 0.), x1 = cmake(0., 0.);
+#pragma unroll
+            for (int j = k + 1; j < NW; j++) {
+                if ((j - k) & 1) cfma(x0, a[j], vs[j]);
+                else cfma(x1, a[j], vs[j]);
+            }
+            cplx x = cmul(tau, cadd(x0, x1));
+            if (row <= k) x = cmake(0., 0.);
+            cplx xh = cmake(0., 0.);   // x of the implicit row 1 (step 0):  tau (a11 + sum_rows conj(a[row][1]) v[row])
+            if (step0) {
+                cplx p = cconjmul(a[1], v);
+                xh = cmul(tau, cmake(a11 + half_sum(p.x), half_sum(p.y)));
+            }
+            // dot = x^H v
+            cplx pd = cconjmul(x, v);
+            cplx dot = cmake(half_sum(pd.x), half_sum(pd.y));
+            if (step0) { dot.x += xh.x; dot.y -= xh.y; }   // conj(xh) * 1
+            cplx al2 = cscale(-0.5, cmul(tau, dot));
+            cplx w = cadd(x, cmul(al2, v));
+            if (row > k) ws[row] = w;
+            if (step0) {
+                cplx wh = cadd(xh, al2);
+                if (hl == 0) ws[1] = wh;
+                a11 -= 2. * wh.x;
+            }
+            __syncwarp();
+            // A -= v w^H + w v^H
+            if (active && row > k) {
+#pragma unroll
+                for (int j = k + 1; j < NW; j++) {
+                    const cplx wj = ws[j], vj = vs[j];
+                    a[j].x = fma(-v.x, wj.x, a[j].x);
+                    a[j].y = fma(-v.y, wj.x, a[j].y);
+                    a[j].x = fma(-v.y, wj.y, a[j].x);
+                    a[j].y = fma(v.x, wj.y, a[j].y);
+                    a[j].x = fma(-w.x, vj.x, a[j].x);
+                    a[j].y = fma(-w.y, vj.x, a[j].y);
+                    a[j].x = fma(-w.y, vj.y, a[j].x);
+                    a[j].y = fma(w.x, vj.y, a[j].y);
+                }
+            }
+        }
+        // store the Householder vector in place (rows > k+1 of column k)
+        if (row > k + 1) a[k] = v;
+        if (live) {
+            if (row == k && k >= R0) d[k] = a[k].x;
+            if (R0 == 2 && k == 1 && hl == 0) d[1] = a11;
+            if (hl == 0) { e[k] = beta; tau_o[k] = tau; }
+        }
+    }
+    if (live) {
+        if (row == NW - 1) d[NW - 1] = a[NW - 1].x;
+        if (hl == 0) { e[NW - 1] = 0.; tau_o[NW - 1] = cmake(0., 0.); }
+        cplx* Vrow = Vout + (ik * NW + row) * NW;
+#pragma unroll
+        for (int j = 0; j < NW; j++) Vrow[j] = a[j];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K2
 // Implicit QL with Wilkinson-type shift (EISPACK tql2 / "tqli").  Thread per k-point.
 // Stream: rot[ik][capR] (c, s) in application order; hdr[ik][capS] = l | (m << 8) per sweep;

@@ -154,8 +154,8 @@ wb_axis_dft_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, const cp
 // indices, so the only HBM stream is the k-space record X itself (the algorithmic 16*E bytes per k-point).
 // Thread = one inner index; KC accumulators over k0; twiddles are warp-uniform shared-memory broadcasts.
 // ------------------------------------------------------------------------------------------
-template <int KC, int TB>
-__global__ void __launch_bounds__(TB)
+template <int KC, int TB, int KSPLIT>
+__global__ void __launch_bounds__(TB * KSPLIT)
 wb_axis10_fused_kernel(const cplx* __restrict__ Z, cplx* __restrict__ X, const cplx* __restrict__ W1,
                        const cplx* __restrict__ W0, int n0, int n1, int N0, int N1, long S2, long z_bstride,
                        long x_bstride) {
@@ -164,17 +164,20 @@ wb_axis10_fused_kernel(const cplx* __restrict__ Z, cplx* __restrict__ X, const c
     cplx* Zs = sm_f;                          // [n0*n1][TB]
     cplx* W1s = Zs + (size_t)n0 * n1 * TB;    // [N1][n1]
     cplx* W0s = W1s + N1 * n1;                // [nchunk*KC][n0], zero beyond N0
+    // thread = (inner index el, share h of the k1 range): KSPLIT threads per inner index keep more warps in flight
     const int b = blockIdx.z;
-    const long t = (long)blockIdx.x * TB + threadIdx.x;
-    for (int x = threadIdx.x; x < N1 * n1; x += TB) W1s[x] = W1[(long)b * N1 * n1 + x];
-    for (int x = threadIdx.x; x < nchunk * KC * n0; x += TB)
+    const int el = threadIdx.x % TB, h = threadIdx.x / TB;
+    const long t = (long)blockIdx.x * TB + el;
+    for (int x = threadIdx.x; x < N1 * n1; x += TB * KSPLIT) W1s[x] = W1[(long)b * N1 * n1 + x];
+    for (int x = threadIdx.x; x < nchunk * KC * n0; x += TB * KSPLIT)
         W0s[x] = (x < N0 * n0) ? W0[(long)b * N0 * n0 + x] : cmake(0., 0.);
     const cplx* zsrc = Z + (long)b * z_bstride + t;
-    for (int x = 0; x < n0 * n1; x++) Zs[x * TB + threadIdx.x] = (t < S2) ? __ldg(zsrc + (long)x * S2) : cmake(0., 0.);
+    for (int x = h; x < n0 * n1; x += KSPLIT) Zs[x * TB + el] = (t < S2) ? __ldg(zsrc + (long)x * S2) : cmake(0., 0.);
     __syncthreads();
     if (t >= S2) return;
     cplx* dst = X + (long)b * x_bstride + t;
-    for (int k1 = 0; k1 < N1; k1++) {
+    const int k1lo = (int)((long)N1 * h / KSPLIT), k1hi = (int)((long)N1 * (h + 1) / KSPLIT);
+    for (int k1 = k1lo; k1 < k1hi; k1++) {
         const cplx* w1 = W1s + k1 * n1;
         for (int c0 = 0; c0 < N0; c0 += KC) {
             cplx acc[KC];
@@ -182,7 +185,7 @@ wb_axis10_fused_kernel(const cplx* __restrict__ Z, cplx* __restrict__ X, const c
             for (int kk = 0; kk < KC; kk++) acc[kk] = cmake(0., 0.);
             const cplx* w0 = W0s + c0 * n0;
             for (int r0 = 0; r0 < n0; r0++) {
-                const cplx* zrow = Zs + (size_t)r0 * n1 * TB + threadIdx.x;
+                const cplx* zrow = Zs + (size_t)r0 * n1 * TB + el;
                 cplx y0 = cmake(0., 0.), y1 = cmake(0., 0.);
                 int r1 = 0;
                 for (; r1 + 1 < n1; r1 += 2) {

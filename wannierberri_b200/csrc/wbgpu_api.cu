@@ -321,6 +321,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     const int n0 = c->nbox.x, n1 = c->nbox.y, n2 = c->nbox.z;
     const double N0 = NKFFT[0], N1 = NKFFT[1];
     double per_k = 16.0 * L.E * (1.0 + n0 / N0 + (double)n0 * n1 / (N0 * N1)) + 16.0 * nw * nw + 8.0 * nw * 11 + 64;
+    if (nw <= 32) per_k += 16.0 * (2 * nw * nw + 32) + 4.0 * (6 * nw + 12) + 32.0 * nw + 16;  // QL rotation stream etc.
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     long kmax = (long)(0.45 * (double)free_b / per_k);
@@ -351,7 +352,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
         CK(cudaMalloc(&c->d_evval, sizeof(double) * nkl * nw * ncmax));
     }
     if (nw <= 32) {
-        c->eig_chunk = std::min<long>((long)nkl, 65536);
+        c->eig_chunk = std::min<long>((long)nkl, 262144);  // thread-per-k QL needs many k-points in flight
         c->capR = 2 * nw * nw + 32;
         c->capS = (6 * nw + 8 + 3) / 4 * 4;  // 16-byte granular (bulk copies)
         size_t ch = (size_t)c->eig_chunk;
@@ -401,12 +402,13 @@ static int axis_dft(wbgpu_ctx* c, const cplx* in, cplx* out, const cplx* W, int 
 
 template <int KC, int TB>
 static int launch_fused10(wbgpu_ctx* c, int nb, size_t smem) {
+    constexpr int KSPLIT = 256 / TB;
     const int n0 = c->nbox.x, n1 = c->nbox.y;
     const int* N = c->N;
     const long S2 = (long)N[2] * c->L.E;
-    CK(cudaFuncSetAttribute(wb_axis10_fused_kernel<KC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(wb_axis10_fused_kernel<KC, TB, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((S2 + TB - 1) / TB), 1, (unsigned)nb);
-    wb_axis10_fused_kernel<KC, TB><<<grid, TB, smem, c->stream>>>(c->d_Z, c->d_X, c->d_W[1], c->d_W[0], n0, n1, N[0], N[1], S2,
+    wb_axis10_fused_kernel<KC, TB, KSPLIT><<<grid, TB * KSPLIT, smem, c->stream>>>(c->d_Z, c->d_X, c->d_W[1], c->d_W[0], n0, n1, N[0], N[1], S2,
                                                               (long)n0 * n1 * S2, (long)N[0] * N[1] * S2);
     c->launches++;
     CK(cudaGetLastError());
@@ -484,8 +486,17 @@ static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
     const int nw = c->nw;
     constexpr int WARPS = 4;
     CK(cudaMemsetAsync(c->d_nfail, 0, sizeof(int), c->stream));
-    wb_tridiag_kernel<NWP, WARPS, EXACT><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, 0, c->stream>>>(
-        c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U);
+    if constexpr (EXACT && NWP > 16 && NWP <= 18) {
+        if (c->eig_method != 3)   // two k-points per warp
+            wb_tridiag2_kernel<NWP, WARPS><<<(unsigned)((nk + 2 * WARPS - 1) / (2 * WARPS)), WARPS * 32, 0, c->stream>>>(
+                c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U);
+        else
+            wb_tridiag_kernel<NWP, WARPS, EXACT><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, 0, c->stream>>>(
+                c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U);
+    } else {
+        wb_tridiag_kernel<NWP, WARPS, EXACT><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, 0, c->stream>>>(
+            c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U);
+    }
     CK(cudaGetLastError());
     if (nw <= 24) {
         constexpr int NT2 = 128;
@@ -513,7 +524,7 @@ static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
 static int run_eigh(wbgpu_ctx* c, long nk, bool want_U) {
     const int nw = c->nw;
     CK(cudaMemsetAsync(c->d_sweeps, 0, sizeof(int), c->stream));
-    bool use_ql = (nw <= 32) && (c->eig_method != 1);
+    bool use_ql = (nw <= 32) && (c->eig_method != 1);  // 2 = QL, 3 = QL with the one-k-point-per-warp reduction
     if (c->eig_method == 2 && nw > 32) return set_err("eigh: Householder+QL path needs num_wann <= 32");
     if (!use_ql) return launch_jacobi(c, 0, nk, want_U, nullptr, nullptr, 148L * 64);
     for (long k0 = 0; k0 < nk; k0 += c->eig_chunk) {
