@@ -5,18 +5,19 @@
 #include <cmath>
 #include "wb_rotate_mma.cuh"
 template <int DBG>
-float run(const cplx* X, WbLayout L, WbMmaPlan P, long nk, const double* E, const cplx* U, double* lab, double* val) {
+float run(const cplx* X, WbLayout L, WbMmaPlan P, long nk, const double* E, const cplx* U, double* lab, double* val, int ctas = 296,
+          size_t extra_smem = 0) {
     constexpr int NW = 18;
     WbWindow win{12., 22., 0.005, 1e-4, 0, 1, 2000};
     WbEventLayout ev{};
     ev.mask = 2; ev.NC = 3; ev.internal_terms = 1; ev.external_terms = 1;
-    size_t smem = wb_mma_smem_bytes<NW>(P);
+    size_t smem = wb_mma_smem_bytes<NW>(P) + extra_smem;
     cudaFuncSetAttribute(wb_events_mma_kernel<NW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9;
     for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(e0);
-        wb_events_mma_kernel<NW, DBG><<<296, 128, smem>>>(X, L, P, nk, E, U, win, ev, lab, val);
+        wb_events_mma_kernel<NW, DBG><<<ctas, 128, smem>>>(X, L, P, nk, E, U, win, ev, lab, val);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); best = fminf(best, ms);
     }
@@ -25,6 +26,7 @@ float run(const cplx* X, WbLayout L, WbMmaPlan P, long nk, const double* E, cons
     return best;
 }
 int main() {
+    setvbuf(stdout, NULL, _IONBF, 0);
     constexpr int NW = 18;
     long nk = 128000;
     WbLayout L; L.nw = NW; L.ntri = NW * (NW + 1) / 2;
@@ -53,5 +55,9 @@ int main() {
     run<2>(X, L, P, nk, E, U, lab, val);
     run<3>(X, L, P, nk, E, U, lab, val);
     run<4>(X, L, P, nk, E, U, lab, val);
+    printf("one CTA per SM:\n");
+    run<0>(X, L, P, nk, E, U, lab, val, 148, 90 * 1024);
+    run<1>(X, L, P, nk, E, U, lab, val, 148, 90 * 1024);
+    run<3>(X, L, P, nk, E, U, lab, val, 148, 90 * 1024);
     return 0;
 }

@@ -149,14 +149,17 @@ def test_eigh(wb, fe, te, fe_orc, te_orc, orc, which):
 
 
 @pytest.mark.parametrize("nw,degenerate", [(1, False), (2, False), (3, False), (8, True), (9, False), (16, False),
-                                           (17, False), (24, True), (32, False), (33, False), (40, False)])
+                                           (17, False), (18, False), (18, True), (24, True), (32, False), (33, False),
+                                           (40, False)])
 def test_eigh_sizes_and_degeneracies(wb, nw, degenerate):
     """Both eigensolvers (Householder+QL for nw <= 32, Jacobi otherwise / on request) against LAPACK on
     random Hermitian models, including exactly degenerate spectra."""
     sysg = wb.synthetic_system(nw, rmax=1, seed=nw, matrices=("Ham",), degenerate_pairs=degenerate)
-    NKFFT, dK = [3, 2, 4], [0.03, 0.01, 0.2]
+    # nw = 18 also exercises the two-k-points-per-warp reduction (method 2) against the one-per-warp kernel
+    # (method 3), on an odd number of k-points
+    NKFFT, dK = ([3, 1, 3] if nw == 18 else [3, 2, 4]), [0.03, 0.01, 0.2]
     from wannierberri_b200 import _lib
-    for method in ((2, 1) if nw <= 32 else (1,)):
+    for method in ((2, 3, 1) if nw == 18 else (2, 1) if nw <= 32 else (1,)):
         eng = wb.Engine(sysg)
         eng.set_option("eig_method", method)
         eng.plan(NKFFT, [_lib.IDENTITY])

@@ -232,7 +232,6 @@ wb_events_mma_kernel(const cplx* __restrict__ rec, WbLayout L, WbMmaPlan P, long
                     Bf[s][t] = v;
                 }
         }
-
         for (int it = 0; it < nitem; it++) {
             const double* src = smem_m + P.soff[it];
             double* Y = Yp + (it & 1) * K2 * LDY;
