@@ -65,9 +65,10 @@ def all_formulae():
 FORMULA_CASES = ["Omega", "Morb_Hpm", "Spin", "VelOmega", "VelHplus", "VelSpin"]
 
 
+@pytest.mark.parametrize("rotate_method", [0, 1, 4])
 @pytest.mark.parametrize("thresh", [1e-4, 0.05])
 @pytest.mark.parametrize("name", FORMULA_CASES)
-def test_formula_band_traces(wb, fe, fe_orc, orc, name, thresh):
+def test_formula_band_traces(wb, fe, fe_orc, orc, name, thresh, rotate_method):
     """Per-k, per-band-group values of every formula against the oracle's Formula classes evaluated with the
     reference's additive / non-additive loop (static.py:102-117), same groups."""
     from wannierberri_b200 import _lib
@@ -82,6 +83,8 @@ def test_formula_band_traces(wb, fe, fe_orc, orc, name, thresh):
     spec = ScanSpec(formula=code, fder=fder, nEF=len(Ef), degen_Kramers=0, internal_terms=1, external_terms=1,
                     Ef_first=Ef[0], Ef_last=Ef[-1], dEF=dEF, degen_thresh=thresh, factor=1.0)
     eng = wb.Engine(fe)
+    # 0 = automatic choice, 1 = shared-memory DFMA kernel, 4 = batched DMMA GEMM to global memory + formula kernel
+    eng.set_option("rotate_method", rotate_method)
     eng.plan(NKFFT, [_lib.IDENTITY, code])
     lab, val = eng.band_traces(dK, spec)
     data = orc.OracleDataK(fe_orc, dK, NKFFT)
@@ -180,7 +183,7 @@ def test_eigh_golden_block(wb, fe):
     assert relerr(eng.eig(b["dK"]), b["E_K"]) < 1e-12
 
 
-@pytest.mark.parametrize("rotate_method", [1, 2, 3])
+@pytest.mark.parametrize("rotate_method", [1, 2, 3, 4])
 @pytest.mark.parametrize("kw", [dict(), dict(degen_thresh=0.05), dict(degen_Kramers=True),
                                 dict(kwargs_formula=dict(external_terms=False)),
                                 dict(kwargs_formula=dict(internal_terms=False))])
@@ -234,10 +237,10 @@ def test_block_calculators_vs_reference(wb, fe, case):
     assert relerr(res.data, b["block_" + case]) < RTOL
 
 
-@pytest.mark.parametrize("nw", [5, 8, 12, 16, 20, 24])
+@pytest.mark.parametrize("nw", [5, 8, 12, 16, 20, 24, 27, 32])
 def test_omega_synthetic_sizes(wb, orc, nw):
-    """AHC scan on seeded random models of several sizes (DMMA kernel variants for nw <= 20, generic above)
-    against the oracle; one K-block."""
+    """AHC scan on seeded random models of several sizes (DMMA kernel variants for nw <= 20, batched DMMA GEMM
+    above) against the oracle; one K-block."""
     sysg = wb.synthetic_system(nw, rmax=1, seed=100 + nw)
     syso = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
                             {k: sysg.get_R_mat(k) for k in ("Ham", "AA")})

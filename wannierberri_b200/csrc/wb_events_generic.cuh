@@ -54,6 +54,208 @@ __host__ inline size_t wb_generic_smem_bytes(int nw, int mask, int external) {
     return cplx_el * sizeof(cplx) + dbl * sizeof(double) + 2 * nw * sizeof(short) + 64;
 }
 
+// Pointers to the rotated matrices of one k-point ([3][nw][nw] blocks, or [3][nw] rotated diagonals) and the
+// work arrays of the formula stage.  The matrices may live in shared memory (wb_events_generic_kernel) or in
+// global memory (wb_events_xbar_kernel, after the batched DMMA rotation of wb_rotate_gemm.cuh).
+struct WbRotated {
+    const cplx *Vb, *Ab, *Bb, *Ob, *Cb, *Sb;   // full blocks
+    const cplx *Od, *Cd, *Sd;                  // diagonals (used when the corresponding block is absent)
+    const double* Es;
+    const double* label;
+    double *rows, *prod, *Tedge;
+    double* Mx;                                // [3][nw*nw] scratch of the non-additive Morb evaluation
+    const short *g1, *g2;
+};
+
+// Formula stage: band-group traces of every requested formula -> events of k-point ik.  All threads of the CTA
+// call it after the rotated matrices are visible; it ends WITHOUT a trailing barrier.
+template <int NT>
+__device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNeeds& need, int nw, long ik,
+                                                  const WbEventLayout& ev, double* __restrict__ ev_label,
+                                                  double* __restrict__ ev_val) {
+    const int n2 = nw * nw;
+    const cplx *Vb = R.Vb, *Ab = R.Ab, *Bb = R.Bb, *Ob = R.Ob, *Cb = R.Cb, *Sb = R.Sb, *Od = R.Od, *Cd = R.Cd, *Sd = R.Sd;
+    const double *Es = R.Es, *label = R.label;
+    double *rows = R.rows, *prod = R.prod, *Tedge = R.Tedge;
+    const short *g1 = R.g1, *g2 = R.g2;
+    const bool f_omega = (ev.mask >> 1) & 1, f_morb = (ev.mask >> 2) & 1, f_vo = (ev.mask >> 3) & 1,
+               f_vh = (ev.mask >> 4) & 1, f_vs = (ev.mask >> 5) & 1, f_spin = (ev.mask >> 6) & 1;
+    const bool internal = ev.internal_terms, external = ev.external_terms;
+    // diagonal accessors that work for both storage modes
+    auto Odg = [&](int c, int n) { return need.Oblk ? Ob[c * n2 + n * nw + n] : Od[c * nw + n]; };
+    auto Cdg = [&](int c, int n) { return need.Cblk ? Cb[c * n2 + n * nw + n] : Cd[c * nw + n]; };
+    auto Sdg = [&](int c, int n) { return need.Sblk ? Sb[c * n2 + n * nw + n] : Sd[c * nw + n]; };
+    auto Dm = [&](int a, int n, int l) {  // D_nl,a = -Vbar_nl,a / (E_n - E_l)
+        return cscale(-wb_deinv(Es[n], Es[l]), Vb[a * n2 + n * nw + l]);
+    };
+
+    // ---- S-type sums for a pair (M, Lb) of one group [ga, gb), component c:
+    //   S  = -i sum_l D_Ml,al D_lL,be + 1/2 O_ML - sum_l D_Ml,al A_lL,be + sum_l D_Ml,be A_lL,al - i sum_m A_Mm,al A_mL,be
+    //   Sh = same with E_l, C, B, E_m  (Morb_H)
+    auto S_pair = [&](int M, int Lb, int ga, int gb, int c, bool want_h, cplx& S, cplx& Sh) {
+        const int al = WB_ALPHA(c), be = WB_BETA(c);
+        S = cmake(0., 0.);
+        Sh = cmake(0., 0.);
+        for (int l = 0; l < nw; l++) {
+            if (l >= ga && l < gb) continue;
+            cplx DMa = Dm(al, M, l), DMb = Dm(be, M, l);
+            if (internal) {
+                cplx z = cmul(DMa, Dm(be, l, Lb));  // -i z
+                S.x += z.y; S.y -= z.x;
+                if (want_h) { Sh.x += Es[l] * z.y; Sh.y -= Es[l] * z.x; }
+            }
+            if (external) {
+                cplx z = csub(cmul(DMb, Ab[al * n2 + l * nw + Lb]), cmul(DMa, Ab[be * n2 + l * nw + Lb]));
+                S = cadd(S, z);
+                if (want_h) {
+                    cplx zh = csub(cmul(DMb, Bb[al * n2 + l * nw + Lb]), cmul(DMa, Bb[be * n2 + l * nw + Lb]));
+                    Sh = cadd(Sh, zh);
+                }
+            }
+        }
+        if (external) {
+            for (int m = ga; m < gb; m++) {
+                cplx z = cmul(Ab[al * n2 + M * nw + m], Ab[be * n2 + m * nw + Lb]);  // -i z
+                S.x += z.y; S.y -= z.x;
+                if (want_h) { Sh.x += Es[m] * z.y; Sh.y -= Es[m] * z.x; }
+            }
+            cplx o = (M == Lb) ? Odg(c, M) : (need.Oblk ? Ob[c * n2 + M * nw + Lb] : cmake(0., 0.));
+            S.x += 0.5 * o.x; S.y += 0.5 * o.y;
+            if (want_h) {
+                cplx cc = (M == Lb) ? Cdg(c, M) : (need.Cblk ? Cb[c * n2 + M * nw + Lb] : cmake(0., 0.));
+                Sh.x += 0.5 * cc.x; Sh.y += 0.5 * cc.y;
+            }
+        }
+    };
+
+    // ---- additive traces and products: one thread per (band M, component c)
+    for (int x = threadIdx.x; x < 3 * nw; x += NT) {
+        int c = x / nw, M = x % nw;
+        double tr_omega = 0.;
+        double pv[3] = {0., 0., 0.}, ph[3] = {0., 0., 0.}, ps[3] = {0., 0., 0.};
+        if (g1[M] >= 0) {
+            const int ga = g1[M], gb = g2[M];
+            if (f_omega) {
+                cplx S, Sh;
+                S_pair(M, M, ga, gb, c, false, S, Sh);
+                tr_omega = 2. * S.x;
+            }
+            if (f_vo || f_vh) {
+                for (int Lb = ga; Lb < gb; Lb++) {
+                    cplx S1, Sh1, S2, Sh2;
+                    S_pair(M, Lb, ga, gb, c, f_vh, S1, Sh1);
+                    if (Lb == M) { S2 = S1; Sh2 = Sh1; }
+                    else S_pair(Lb, M, ga, gb, c, f_vh, S2, Sh2);
+                    cplx Om = cadd(S1, cconj(S2));  // Omega_c[M, Lb]
+                    cplx F = Om;
+                    for (int a = 0; a < 3; a++) {  // sum_L V_LM,a F[M,L]  -> contribution of row M
+                        cplx v = Vb[a * n2 + Lb * nw + M];
+                        pv[a] += cmul(v, Om).x;
+                    }
+                    if (f_vh) {
+                        cplx Hh = cadd(Sh1, cconj(Sh2));
+                        double eav = 0.5 * (Es[M] + Es[Lb]);
+                        F = cmake(Hh.x + eav * Om.x, Hh.y + eav * Om.y);
+                        for (int a = 0; a < 3; a++) ph[a] += cmul(Vb[a * n2 + Lb * nw + M], F).x;
+                    }
+                }
+            }
+            if (f_vs) {
+                for (int Lb = ga; Lb < gb; Lb++)
+                    for (int a = 0; a < 3; a++) ps[a] += cmul(Vb[a * n2 + Lb * nw + M], Sb[c * n2 + M * nw + Lb]).x;
+            }
+        }
+        rows[c * nw + M] = tr_omega;
+        for (int a = 0; a < 3; a++) {  // component (a, b = c) of the rank-2 products
+            prod[M * 27 + a * 3 + c] = pv[a];
+            prod[M * 27 + 9 + a * 3 + c] = ph[a];
+            prod[M * 27 + 18 + a * 3 + c] = ps[a];
+        }
+    }
+    // ---- non-additive Morb_Hpm (static.py:109-117): T(x) = trace with inn = 0..x-1, out = x..nw-1,
+    //      value of group (a, b) = T(b) - T(a).  With the pair quantities
+    //        G[n,l]   = (E_l+E_n) Re(-i D_nl,al D_ln,be) + Re(-D_nl,al B_ln,be + D_nl,be B_ln,al)
+    //                   + E_n Re(-D_nl,al A_ln,be + D_nl,be A_ln,al)                      (n in inn, l in out)
+    //        Gin[n,m] = (E_m+E_n) Re(-i A_nm,al A_mn,be)                                  (n, m in inn)
+    //        dg[n]    = 1/2 Re C_nn + 1/2 E_n Re O_nn
+    //      T(x) = 2 [ sum_{n<x<=l} G[n,l] + sum_{n,m<x} Gin[n,m] + sum_{n<x} dg[n] ].
+    //      One matrix Mx holds G in its upper triangle, Gin[n,m]+Gin[m,n] in the lower, Gin[n,n]+dg[n] on the diagonal.
+    if (f_morb) {
+        __syncthreads();
+        double* Mx = R.Mx;
+        for (int x = threadIdx.x; x < n2; x += NT) {
+            int n = x / nw, l = x % nw;
+            for (int c = 0; c < 3; c++) {
+                const int al = WB_ALPHA(c), be = WB_BETA(c);
+                double v = 0.;
+                if (n < l) {
+                    cplx Dna = Dm(al, n, l), Dnb = Dm(be, n, l);
+                    if (internal) v += (Es[l] + Es[n]) * cmul(Dna, Dm(be, l, n)).y;
+                    if (external) {
+                        v += -cmul(Dna, Bb[be * n2 + l * nw + n]).x + cmul(Dnb, Bb[al * n2 + l * nw + n]).x;
+                        v += Es[n] * (-cmul(Dna, Ab[be * n2 + l * nw + n]).x + cmul(Dnb, Ab[al * n2 + l * nw + n]).x);
+                    }
+                } else if (external) {
+                    // here (row n, col l) with l <= n holds the in-part of the pair {l, n}
+                    double q1 = (Es[l] + Es[n]) * cmul(Ab[al * n2 + n * nw + l], Ab[be * n2 + l * nw + n]).y;
+                    if (n == l) v = q1 + 0.5 * Cdg(c, n).x + 0.5 * Es[n] * Odg(c, n).x;
+                    else v = q1 + (Es[l] + Es[n]) * cmul(Ab[al * n2 + l * nw + n], Ab[be * n2 + n * nw + l]).y;
+                }
+                Mx[c * n2 + x] = v;
+            }
+        }
+        __syncthreads();
+        for (int y = threadIdx.x; y < 3 * (nw + 1); y += NT) {
+            int c = y / (nw + 1), xe = y % (nw + 1);
+            double t = 0.;
+            bool is_edge = (xe == nw) || (xe < nw && g1[xe] == xe) || (xe > 0 && g2[xe - 1] == xe);
+            if (is_edge) {
+                for (int n = 0; n < xe; n++) {
+                    for (int l = xe; l < nw; l++) t += Mx[c * n2 + n * nw + l];
+                    for (int m = 0; m <= n; m++) t += Mx[c * n2 + n * nw + m];
+                }
+            }
+            Tedge[c * (nw + 1) + xe] = 2. * t;
+        }
+    }
+    __syncthreads();
+    // ---- events
+    for (int x = threadIdx.x; x < nw; x += NT) {
+        double lab = label[x];
+        ev_label[ik * nw + x] = lab;
+        if (lab != CUDART_INF) {
+            const int b = g2[x];
+            double* out = ev_val + (ik * nw + x) * ev.NC;
+            if (f_omega)
+                for (int c = 0; c < 3; c++) {
+                    double s = 0.;
+                    for (int n = x; n < b; n++) s += rows[c * nw + n];
+                    out[ev.off[1] + c] = s;
+                }
+            if (f_morb)
+                for (int c = 0; c < 3; c++) out[ev.off[2] + c] = Tedge[c * (nw + 1) + b] - Tedge[c * (nw + 1) + x];
+            if (f_spin)
+                for (int c = 0; c < 3; c++) {
+                    double s = 0.;
+                    for (int n = x; n < b; n++) s += Sdg(c, n).x;
+                    out[ev.off[6] + c] = s;
+                }
+            if (f_vo || f_vh || f_vs)
+                for (int ab = 0; ab < 9; ab++) {
+                    double so = 0., sh = 0., ss = 0.;
+                    for (int n = x; n < b; n++) {
+                        so += prod[n * 27 + ab];
+                        sh += prod[n * 27 + 9 + ab];
+                        ss += prod[n * 27 + 18 + ab];
+                    }
+                    if (f_vo) out[ev.off[3] + ab] = so;
+                    if (f_vh) out[ev.off[4] + ab] = sh;
+                    if (f_vs) out[ev.off[5] + ab] = ss;
+                }
+        }
+    }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT)
 wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, const double* __restrict__ Eall,
@@ -82,9 +284,6 @@ wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, cons
     double* Tedge = prod + 27 * nw;    // [3][nw+1] cumulative non-additive traces
     short* g1 = (short*)(Tedge + 3 * (nw + 1));
     short* g2 = g1 + nw;
-    const bool f_omega = (ev.mask >> 1) & 1, f_morb = (ev.mask >> 2) & 1, f_vo = (ev.mask >> 3) & 1,
-               f_vh = (ev.mask >> 4) & 1, f_vs = (ev.mask >> 5) & 1, f_spin = (ev.mask >> 6) & 1;
-    const bool internal = ev.internal_terms, external = ev.external_terms;
 
     for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
         const cplx* r = rec + ik * L.E;
@@ -129,179 +328,12 @@ wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, cons
         if (need.Cdiag) rotate_diag(L.off_C, false, Cd);
         if (need.Sdiag) rotate_diag(L.off_S, true, Sd);
         __syncthreads();
-        // diagonal accessors that work for both storage modes
-        auto Odg = [&](int c, int n) { return need.Oblk ? Ob[c * n2 + n * nw + n] : Od[c * nw + n]; };
-        auto Cdg = [&](int c, int n) { return need.Cblk ? Cb[c * n2 + n * nw + n] : Cd[c * nw + n]; };
-        auto Sdg = [&](int c, int n) { return need.Sblk ? Sb[c * n2 + n * nw + n] : Sd[c * nw + n]; };
-        auto Dm = [&](int a, int n, int l) {  // D_nl,a = -Vbar_nl,a / (E_n - E_l)
-            return cscale(-wb_deinv(Es[n], Es[l]), Vb[a * n2 + n * nw + l]);
-        };
-
-        // ---- S-type sums for a pair (M, Lb) of one group [ga, gb), component c:
-        //   S  = -i sum_l D_Ml,al D_lL,be + 1/2 O_ML - sum_l D_Ml,al A_lL,be + sum_l D_Ml,be A_lL,al - i sum_m A_Mm,al A_mL,be
-        //   Sh = same with E_l, C, B, E_m  (Morb_H)
-        auto S_pair = [&](int M, int Lb, int ga, int gb, int c, bool want_h, cplx& S, cplx& Sh) {
-            const int al = WB_ALPHA(c), be = WB_BETA(c);
-            S = cmake(0., 0.);
-            Sh = cmake(0., 0.);
-            for (int l = 0; l < nw; l++) {
-                if (l >= ga && l < gb) continue;
-                cplx DMa = Dm(al, M, l), DMb = Dm(be, M, l);
-                if (internal) {
-                    cplx z = cmul(DMa, Dm(be, l, Lb));  // -i z
-                    S.x += z.y; S.y -= z.x;
-                    if (want_h) { Sh.x += Es[l] * z.y; Sh.y -= Es[l] * z.x; }
-                }
-                if (external) {
-                    cplx z = csub(cmul(DMb, Ab[al * n2 + l * nw + Lb]), cmul(DMa, Ab[be * n2 + l * nw + Lb]));
-                    S = cadd(S, z);
-                    if (want_h) {
-                        cplx zh = csub(cmul(DMb, Bb[al * n2 + l * nw + Lb]), cmul(DMa, Bb[be * n2 + l * nw + Lb]));
-                        Sh = cadd(Sh, zh);
-                    }
-                }
-            }
-            if (external) {
-                for (int m = ga; m < gb; m++) {
-                    cplx z = cmul(Ab[al * n2 + M * nw + m], Ab[be * n2 + m * nw + Lb]);  // -i z
-                    S.x += z.y; S.y -= z.x;
-                    if (want_h) { Sh.x += Es[m] * z.y; Sh.y -= Es[m] * z.x; }
-                }
-                cplx o = (M == Lb) ? Odg(c, M) : (need.Oblk ? Ob[c * n2 + M * nw + Lb] : cmake(0., 0.));
-                S.x += 0.5 * o.x; S.y += 0.5 * o.y;
-                if (want_h) {
-                    cplx cc = (M == Lb) ? Cdg(c, M) : (need.Cblk ? Cb[c * n2 + M * nw + Lb] : cmake(0., 0.));
-                    Sh.x += 0.5 * cc.x; Sh.y += 0.5 * cc.y;
-                }
-            }
-        };
-
-        // ---- additive traces and products: one thread per (band M, component c)
-        for (int x = threadIdx.x; x < 3 * nw; x += NT) {
-            int c = x / nw, M = x % nw;
-            double tr_omega = 0.;
-            double pv[3] = {0., 0., 0.}, ph[3] = {0., 0., 0.}, ps[3] = {0., 0., 0.};
-            if (g1[M] >= 0) {
-                const int ga = g1[M], gb = g2[M];
-                if (f_omega) {
-                    cplx S, Sh;
-                    S_pair(M, M, ga, gb, c, false, S, Sh);
-                    tr_omega = 2. * S.x;
-                }
-                if (f_vo || f_vh) {
-                    for (int Lb = ga; Lb < gb; Lb++) {
-                        cplx S1, Sh1, S2, Sh2;
-                        S_pair(M, Lb, ga, gb, c, f_vh, S1, Sh1);
-                        if (Lb == M) { S2 = S1; Sh2 = Sh1; }
-                        else S_pair(Lb, M, ga, gb, c, f_vh, S2, Sh2);
-                        cplx Om = cadd(S1, cconj(S2));  // Omega_c[M, Lb]
-                        cplx F = Om;
-                        for (int a = 0; a < 3; a++) {  // sum_L V_LM,a F[M,L]  -> contribution of row M
-                            cplx v = Vb[a * n2 + Lb * nw + M];
-                            pv[a] += cmul(v, Om).x;
-                        }
-                        if (f_vh) {
-                            cplx Hh = cadd(Sh1, cconj(Sh2));
-                            double eav = 0.5 * (Es[M] + Es[Lb]);
-                            F = cmake(Hh.x + eav * Om.x, Hh.y + eav * Om.y);
-                            for (int a = 0; a < 3; a++) ph[a] += cmul(Vb[a * n2 + Lb * nw + M], F).x;
-                        }
-                    }
-                }
-                if (f_vs) {
-                    for (int Lb = ga; Lb < gb; Lb++)
-                        for (int a = 0; a < 3; a++) ps[a] += cmul(Vb[a * n2 + Lb * nw + M], Sb[c * n2 + M * nw + Lb]).x;
-                }
-            }
-            rows[c * nw + M] = tr_omega;
-            for (int a = 0; a < 3; a++) {  // component (a, b = c) of the rank-2 products
-                prod[M * 27 + a * 3 + c] = pv[a];
-                prod[M * 27 + 9 + a * 3 + c] = ph[a];
-                prod[M * 27 + 18 + a * 3 + c] = ps[a];
-            }
-        }
-        // ---- non-additive Morb_Hpm (static.py:109-117): T(x) = trace with inn = 0..x-1, out = x..nw-1,
-        //      value of group (a, b) = T(b) - T(a).  With the pair quantities
-        //        G[n,l]   = (E_l+E_n) Re(-i D_nl,al D_ln,be) + Re(-D_nl,al B_ln,be + D_nl,be B_ln,al)
-        //                   + E_n Re(-D_nl,al A_ln,be + D_nl,be A_ln,al)                      (n in inn, l in out)
-        //        Gin[n,m] = (E_m+E_n) Re(-i A_nm,al A_mn,be)                                  (n, m in inn)
-        //        dg[n]    = 1/2 Re C_nn + 1/2 E_n Re O_nn
-        //      T(x) = 2 [ sum_{n<x<=l} G[n,l] + sum_{n,m<x} Gin[n,m] + sum_{n<x} dg[n] ].
-        //      One matrix Mx holds G in its upper triangle, Gin[n,m]+Gin[m,n] in the lower, Gin[n,n]+dg[n] on the diagonal.
-        if (f_morb) {
-            __syncthreads();
-            double* Mx = (double*)Xs;  // [3][n2] doubles = 1.5 n2 complex: Xs and half of Ys, both free now
-            for (int x = threadIdx.x; x < n2; x += NT) {
-                int n = x / nw, l = x % nw;
-                for (int c = 0; c < 3; c++) {
-                    const int al = WB_ALPHA(c), be = WB_BETA(c);
-                    double v = 0.;
-                    if (n < l) {
-                        cplx Dna = Dm(al, n, l), Dnb = Dm(be, n, l);
-                        if (internal) v += (Es[l] + Es[n]) * cmul(Dna, Dm(be, l, n)).y;
-                        if (external) {
-                            v += -cmul(Dna, Bb[be * n2 + l * nw + n]).x + cmul(Dnb, Bb[al * n2 + l * nw + n]).x;
-                            v += Es[n] * (-cmul(Dna, Ab[be * n2 + l * nw + n]).x + cmul(Dnb, Ab[al * n2 + l * nw + n]).x);
-                        }
-                    } else if (external) {
-                        // here (row n, col l) with l <= n holds the in-part of the pair {l, n}
-                        double q1 = (Es[l] + Es[n]) * cmul(Ab[al * n2 + n * nw + l], Ab[be * n2 + l * nw + n]).y;
-                        if (n == l) v = q1 + 0.5 * Cdg(c, n).x + 0.5 * Es[n] * Odg(c, n).x;
-                        else v = q1 + (Es[l] + Es[n]) * cmul(Ab[al * n2 + l * nw + n], Ab[be * n2 + n * nw + l]).y;
-                    }
-                    Mx[c * n2 + x] = v;
-                }
-            }
-            __syncthreads();
-            for (int y = threadIdx.x; y < 3 * (nw + 1); y += NT) {
-                int c = y / (nw + 1), xe = y % (nw + 1);
-                double t = 0.;
-                bool is_edge = (xe == nw) || (xe < nw && g1[xe] == xe) || (xe > 0 && g2[xe - 1] == xe);
-                if (is_edge) {
-                    for (int n = 0; n < xe; n++) {
-                        for (int l = xe; l < nw; l++) t += Mx[c * n2 + n * nw + l];
-                        for (int m = 0; m <= n; m++) t += Mx[c * n2 + n * nw + m];
-                    }
-                }
-                Tedge[c * (nw + 1) + xe] = 2. * t;
-            }
-        }
-        __syncthreads();
-        // ---- events
-        for (int x = threadIdx.x; x < nw; x += NT) {
-            double lab = label[x];
-            ev_label[ik * nw + x] = lab;
-            if (lab != CUDART_INF) {
-                const int b = g2[x];
-                double* out = ev_val + (ik * nw + x) * ev.NC;
-                if (f_omega)
-                    for (int c = 0; c < 3; c++) {
-                        double s = 0.;
-                        for (int n = x; n < b; n++) s += rows[c * nw + n];
-                        out[ev.off[1] + c] = s;
-                    }
-                if (f_morb)
-                    for (int c = 0; c < 3; c++) out[ev.off[2] + c] = Tedge[c * (nw + 1) + b] - Tedge[c * (nw + 1) + x];
-                if (f_spin)
-                    for (int c = 0; c < 3; c++) {
-                        double s = 0.;
-                        for (int n = x; n < b; n++) s += Sdg(c, n).x;
-                        out[ev.off[6] + c] = s;
-                    }
-                if (f_vo || f_vh || f_vs)
-                    for (int ab = 0; ab < 9; ab++) {
-                        double so = 0., sh = 0., ss = 0.;
-                        for (int n = x; n < b; n++) {
-                            so += prod[n * 27 + ab];
-                            sh += prod[n * 27 + 9 + ab];
-                            ss += prod[n * 27 + 18 + ab];
-                        }
-                        if (f_vo) out[ev.off[3] + ab] = so;
-                        if (f_vh) out[ev.off[4] + ab] = sh;
-                        if (f_vs) out[ev.off[5] + ab] = ss;
-                    }
-            }
-        }
+        WbRotated R;
+        R.Vb = Vb; R.Ab = Ab; R.Bb = Bb; R.Ob = Ob; R.Cb = Cb; R.Sb = Sb; R.Od = Od; R.Cd = Cd; R.Sd = Sd;
+        R.Es = Es; R.label = label; R.rows = rows; R.prod = prod; R.Tedge = Tedge;
+        R.Mx = (double*)Xs;   // [3][n2] doubles = 1.5 n2 complex: Xs and half of Ys, both free now
+        R.g1 = g1; R.g2 = g2;
+        wb_formula_events<NT>(R, need, nw, ik, ev, ev_label, ev_val);
         __syncthreads();
     }
 }

@@ -1,0 +1,201 @@
+// Eigenbasis rotation  Xbar = U^dagger X U  for ANY num_wann (<= 128) as a batched complex GEMM pair on the FP64
+// tensor cores (mma.sync.m8n8k4.f64), results to global memory:  xbar[k][channel][nw][nw].
+//
+// Reference: Data_K._rotate (data_K/data_K.py:130-132) = einsum('kba,kbc...,kcd->kad...').
+//
+// This is the size-generic companion of wb_rotate_mma.cuh (compile-time num_wann, everything in shared memory):
+// it serves num_wann > 20, the rank-2 Fermi-surface formulae and the Kubo path, whose rotated matrices do not fit
+// one CTA's shared memory.  One CTA = (column panel of TN = 8 NTL columns, channel, k-point):
+//   phase 1   Y[:, panel] = X U[:, panel]           K loop over chunks of KC, operands staged in shared memory;
+//             a hermitian channel (upper triangle packed in the record) is expanded by the loader;
+//   phase 2   C[:, panel] = U^H Y[:, panel]         Y never leaves shared memory.
+// A complex product is four real DMMAs on the (re, im) components of complex128 fragments, which are read as
+// 16-byte shared-memory loads; the row strides (KC + 4, TN + 2 complex) make every fragment load conflict free.
+// Warp w owns the 8-row tiles w, w + 4 of every 64-row chunk.
+#pragma once
+#include "wb_common.cuh"
+
+struct WbChanList {
+    int n;
+    int off[18];    // record offset (complex elements) of the matrix
+    int herm[18];   // upper-triangle packed
+};
+
+__device__ __forceinline__ void wb_dmma_acc(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+
+template <int NTL, int KC>
+__host__ __device__ constexpr int wb_gemm_ldp() { return 8 * NTL + 2; }
+
+template <int NTL, int KC>
+__host__ inline size_t wb_gemm_smem_bytes(int nw) {
+    int nwp = (nw + KC - 1) / KC * KC;
+    return sizeof(cplx) * ((size_t)nwp * wb_gemm_ldp<NTL, KC>() + 64 * (KC + 4) + (size_t)KC * wb_gemm_ldp<NTL, KC>());
+}
+
+template <int NTL, int KC>
+__global__ void __launch_bounds__(128)
+wb_rotate_gemm_kernel(const cplx* __restrict__ rec, long recE, WbChanList ch, int nw, long nk,
+                      const cplx* __restrict__ Uall, cplx* __restrict__ xbar) {
+    constexpr int TN = 8 * NTL, LDP = wb_gemm_ldp<NTL, KC>(), LDA = KC + 4;
+    extern __shared__ __align__(16) cplx smem_r[];
+    const int nwp = (nw + KC - 1) / KC * KC;
+    cplx* Yp = smem_r;                      // [nwp][LDP]
+    cplx* As = Yp + (size_t)nwp * LDP;      // [64][LDA]
+    cplx* Bs = As + 64 * LDA;               // [KC][LDP]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int l0 = blockIdx.x * TN;
+    const int ic = blockIdx.y;
+    const int off = ch.off[ic];
+    const bool herm = ch.herm[ic];
+    const int n2 = nw * nw;
+
+    for (long ik = blockIdx.z; ik < nk; ik += gridDim.z) {
+        const cplx* r = rec + ik * recE;
+        const cplx* U = Uall + ik * n2;
+        for (int x = threadIdx.x; x < (nwp - nw) * LDP; x += 128) Yp[(size_t)nw * LDP + x] = cmake(0., 0.);
+#pragma unroll 1
+        for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+            for (int m0 = 0; m0 < nw; m0 += 64) {
+                double are[2][NTL][2], aim[2][NTL][2];
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int t = 0; t < NTL; t++) are[i][t][0] = are[i][t][1] = aim[i][t][0] = aim[i][t][1] = 0.;
+                const bool act0 = m0 + 8 * warp < nw, act1 = m0 + 8 * (warp + 4) < nw;
+#pragma unroll 1
+                for (int j0 = 0; j0 < nw; j0 += KC) {
+                    __syncthreads();
+                    if (phase == 0) {
+                        // As[r][c] = X[m0 + r][j0 + c];  Bs[r][c] = U[j0 + r][l0 + c]
+                        for (int x = threadIdx.x; x < 64 * KC; x += 128) {
+                            const int c = x % KC, rr = x / KC;
+                            const int m = m0 + rr, j = j0 + c;
+                            cplx v = cmake(0., 0.);
+                            if (m < nw && j < nw) v = herm ? load_herm(r, off, m, j, nw) : r[off + m * nw + j];
+                            As[rr * LDA + c] = v;
+                        }
+                        for (int x = threadIdx.x; x < KC * TN; x += 128) {
+                            const int c = x % TN, rr = x / TN;
+                            const int j = j0 + rr, l = l0 + c;
+                            Bs[rr * LDP + c] = (j < nw && l < nw) ? U[j * nw + l] : cmake(0., 0.);
+                        }
+                    } else {
+                        // As[r][c] = conj(U[j0 + c][m0 + r])
+                        for (int x = threadIdx.x; x < 64 * KC; x += 128) {
+                            const int rr = x % 64, c = x / 64;
+                            const int n = m0 + rr, i = j0 + c;
+                            cplx v = cmake(0., 0.);
+                            if (n < nw && i < nw) v = cconj(U[i * nw + n]);
+                            As[rr * LDA + c] = v;
+                        }
+                    }
+                    __syncthreads();
+                    const cplx* Bsrc = (phase == 0) ? Bs : Yp + (size_t)j0 * LDP;
+#pragma unroll
+                    for (int kk = 0; kk < KC; kk += 4) {
+                        cplx b[NTL];
+#pragma unroll
+                        for (int t = 0; t < NTL; t++) b[t] = Bsrc[(kk + q) * LDP + 8 * t + g];
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            if (i == 0 ? act0 : act1) {
+                                const cplx a = As[(8 * (warp + 4 * i) + g) * LDA + kk + q];
+#pragma unroll
+                                for (int t = 0; t < NTL; t++) {
+                                    wb_dmma_acc(are[i][t][0], are[i][t][1], a.x, b[t].x);
+                                    wb_dmma_acc(are[i][t][0], are[i][t][1], -a.y, b[t].y);
+                                    wb_dmma_acc(aim[i][t][0], aim[i][t][1], a.x, b[t].y);
+                                    wb_dmma_acc(aim[i][t][0], aim[i][t][1], a.y, b[t].x);
+                                }
+                            }
+                        }
+                    }
+                }
+                // epilogue: lane holds rows m0 + 8 (warp + 4 i) + g, columns 8 t + 2 q + {0, 1}
+                if (phase == 0) {
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const int m = m0 + 8 * (warp + 4 * i) + g;
+                        if (m < nw) {
+#pragma unroll
+                            for (int t = 0; t < NTL; t++) {
+                                Yp[(size_t)m * LDP + 8 * t + 2 * q] = cmake(are[i][t][0], aim[i][t][0]);
+                                Yp[(size_t)m * LDP + 8 * t + 2 * q + 1] = cmake(are[i][t][1], aim[i][t][1]);
+                            }
+                        }
+                    }
+                } else {
+                    cplx* out = xbar + ((size_t)ik * ch.n + ic) * n2;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const int n = m0 + 8 * (warp + 4 * i) + g;
+                        if (n < nw) {
+#pragma unroll
+                            for (int t = 0; t < NTL; t++) {
+                                const int l = l0 + 8 * t + 2 * q;
+                                if (l < nw) out[n * nw + l] = cmake(are[i][t][0], aim[i][t][0]);
+                                if (l + 1 < nw) out[n * nw + l + 1] = cmake(are[i][t][1], aim[i][t][1]);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();   // Y panel complete (phase 0) / everybody done with it (phase 1)
+        }
+    }
+}
+
+// Formula stage on rotated matrices held in global memory: one CTA per k-point.
+// xbar[k][nch][nw][nw]; the channel triples are ordered V | A | B | O | C | S (those present).
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall, WbWindow win,
+                      WbEventLayout ev, double* __restrict__ mx_scratch, double* __restrict__ ev_label,
+                      double* __restrict__ ev_val) {
+    extern __shared__ __align__(16) double smem_x[];
+    const int n2 = nw * nw;
+    WbNeeds need = wb_needs(ev.mask, ev.external_terms);
+    // everything that is needed at all is rotated in full here
+    need.Oblk = need.Oblk || need.Odiag;
+    need.Cblk = need.Cblk || need.Cdiag;
+    need.Sblk = need.Sblk || need.Sdiag;
+    need.Odiag = need.Cdiag = need.Sdiag = false;
+    double* Es = smem_x;
+    double* label = Es + nw;
+    double* rows = label + nw;
+    double* prod = rows + 3 * nw;
+    double* Tedge = prod + 27 * nw;
+    short* g1 = (short*)(Tedge + 3 * (nw + 1));
+    short* g2 = g1 + nw;
+    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
+        __syncthreads();
+        if (nw <= 32) {
+            if (threadIdx.x < 32) wb_band_groups_warp(Es, nw, win, g1, g2, label, threadIdx.x);
+        } else if (threadIdx.x == 0) wb_band_groups(Es, nw, win, g1, g2, label);
+        __syncthreads();
+        const cplx* p = xbar + (size_t)ik * nch * n2;
+        WbRotated R;
+        R.Vb = p; if (need.V) p += 3 * n2;
+        R.Ab = p; if (need.A) p += 3 * n2;
+        R.Bb = p; if (need.B) p += 3 * n2;
+        R.Ob = p; if (need.Oblk) p += 3 * n2;
+        R.Cb = p; if (need.Cblk) p += 3 * n2;
+        R.Sb = p; if (need.Sblk) p += 3 * n2;
+        R.Od = R.Cd = R.Sd = nullptr;
+        R.Es = Es; R.label = label; R.rows = rows; R.prod = prod; R.Tedge = Tedge;
+        R.Mx = mx_scratch + (size_t)blockIdx.x * 3 * n2;
+        R.g1 = g1; R.g2 = g2;
+        wb_formula_events<NT>(R, need, nw, ik, ev, ev_label, ev_val);
+        __syncthreads();
+    }
+}
+
+__host__ inline size_t wb_xbar_events_smem_bytes(int nw) {
+    return sizeof(double) * ((size_t)2 * nw + 3 * nw + 27 * nw + 3 * (nw + 1)) + 2 * nw * sizeof(short) + 64;
+}

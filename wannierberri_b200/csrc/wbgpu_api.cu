@@ -24,6 +24,7 @@
 #include "wb_rotate_dmma.cuh"
 #include "wb_events_generic.cuh"
 #include "wb_rotate_mma.cuh"
+#include "wb_rotate_gemm.cuh"
 #include "wb_scan.cuh"
 #include "wb_probe.cuh"
 
@@ -74,6 +75,11 @@ struct wbgpu_ctx {
     double *d_dK = nullptr, *d_weight = nullptr, *d_out = nullptr;
     size_t dK_cap = 0, out_cap = 0;
     int* d_sweeps = nullptr;
+    // rotated matrices in global memory (generic DMMA GEMM path), per sub-batch of k-points
+    double* d_xbar = nullptr;
+    size_t xbar_cap = 0;
+    double* d_mx = nullptr;
+    size_t mx_cap = 0;
     // Householder+QL eigensolver work space (per sub-batch of eig_chunk k-points)
     long eig_chunk = 0;
     int capR = 0, capS = 0;
@@ -87,7 +93,8 @@ struct wbgpu_ctx {
     int eig_method = 0;
     int ev_ncmax = 1;
     int fourier_method = 0; // 0 = axes 1 and 0 fused (when the tile fits), 1 = three separate axis passes
-    int rotate_method = 0;  // 0 = automatic, 1 = generic shared-memory DFMA kernel, 2 = DMMA kernel
+    int rotate_method = 0;  // 0 = automatic, 1 = generic shared-memory DFMA kernel, 2 = DMMA kernel (Omega, nw <= 20),
+                            // 3 = compile-time-NW DMMA kernel, 4 = batched DMMA GEMM to global memory + formula kernel
     int smem_optin = 0;
     // optional per-stage device timing (option "timing"): events around each stage of each batch
     int timing = 0;
@@ -192,6 +199,7 @@ extern "C" int wbgpu_destroy(wbgpu_ctx* c) {
     free_plan(c);
     cudaFree(c->d_iRvec); cudaFree(c->d_T); cudaFree(c->d_sweeps);
     for (int k = 0; k < WBGPU_NKEYS; k++) cudaFree(c->d_XR[k]);
+    cudaFree(c->d_xbar); cudaFree(c->d_mx);
     cudaFree(c->d_hist); cudaFree(c->d_cum); cudaFree(c->d_dK); cudaFree(c->d_weight); cudaFree(c->d_out);
     delete c;
     return 0;
@@ -623,6 +631,73 @@ static int launch_mma_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
 #undef WB_MMA_CASE
 }
 
+static int ensure(double** p, size_t* cap, size_t need);
+
+template <int NTL, int KC>
+static int launch_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n) {
+    const int nw = c->nw;
+    size_t smem = wb_gemm_smem_bytes<NTL, KC>(nw);
+    if ((int)smem > c->smem_optin) return set_err("rotate(gemm): num_wann=%d needs %zu B shared memory", nw, smem);
+    CK(cudaFuncSetAttribute(wb_rotate_gemm_kernel<NTL, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((nw + 8 * NTL - 1) / (8 * NTL)), (unsigned)ch.n, (unsigned)std::min(n, 16384L));
+    wb_rotate_gemm_kernel<NTL, KC><<<grid, 128, smem, c->stream>>>(c->d_X + (size_t)k0 * c->L.E, (long)c->L.E, ch, nw, n,
+                                                                 c->d_U + (size_t)k0 * nw * nw, (cplx*)c->d_xbar);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// U^dagger X U of the listed channels for k-points [k0, k0 + n) -> c->d_xbar[n][ch.n][nw][nw]
+static int rotate_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n) {
+    const int nw = c->nw;
+    if (nw <= 8) return launch_gemm<1, 8>(c, ch, k0, n);
+    if (nw <= 16) return launch_gemm<2, 8>(c, ch, k0, n);
+    if (nw <= 24) return launch_gemm<3, 8>(c, ch, k0, n);
+    return launch_gemm<4, 16>(c, ch, k0, n);
+}
+
+static long xbar_chunk(wbgpu_ctx* c, int nch, long nk) {
+    double per_k = 16.0 * nch * c->nw * c->nw;
+    long chunk = (long)(3.0e9 / per_k);
+    return std::max(1L, std::min(chunk, nk));
+}
+
+// generic path: batched DMMA rotation to global memory, then the formula kernel
+static int run_events_xbar(wbgpu_ctx* c, const EvGroup& G, long nk) {
+    const int nw = c->nw;
+    const WbLayout& L = c->L;
+    WbNeeds need = wb_needs(G.ev.mask, G.ev.external_terms);
+    WbChanList ch;
+    ch.n = 0;
+    auto add3 = [&](const int* offs, bool herm) {
+        for (int a = 0; a < 3; a++) { ch.off[ch.n] = offs[a]; ch.herm[ch.n] = herm; ch.n++; }
+    };
+    if (need.V) add3(L.off_dH, false);
+    if (need.A) add3(L.off_A, true);
+    if (need.B) add3(L.off_B, false);
+    if (need.Oblk || need.Odiag) add3(L.off_O, true);
+    if (need.Cblk || need.Cdiag) add3(L.off_C, false);
+    if (need.Sblk || need.Sdiag) add3(L.off_S, true);
+    const long chunk = xbar_chunk(c, ch.n, nk);
+    if (ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * nw * nw)) return 1;
+    constexpr int NT = 128;
+    const long nblk_max = 148L * 8;
+    if (ensure(&c->d_mx, &c->mx_cap, sizeof(double) * (size_t)nblk_max * 3 * nw * nw)) return 1;
+    size_t smem = wb_xbar_events_smem_bytes(nw);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(wb_events_xbar_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (long k0 = 0; k0 < nk; k0 += chunk) {
+        long n = std::min(chunk, nk - k0);
+        if (rotate_gemm(c, ch, k0, n)) return 1;
+        long nblk = std::min(n, nblk_max);
+        wb_events_xbar_kernel<NT><<<(unsigned)nblk, NT, smem, c->stream>>>((const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, G.win, G.ev,
+                                                                       c->d_mx, c->d_evlabel + k0 * nw,
+                                                                       c->d_evval + (size_t)k0 * nw * G.ev.NC);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
 static int run_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
     const int nw = c->nw;
     const WbWindow& win = G.win;
@@ -652,8 +727,9 @@ static int run_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
     }
     long nblk = std::min(nk, 148L * 32);
     bool omega_only = (G.ev.mask == (1 << WBGPU_OMEGA));
-    bool dmma = omega_only && (nw <= 20) && (c->rotate_method != 1);
+    bool dmma = omega_only && (nw <= 20) && (c->rotate_method != 1) && (c->rotate_method != 4);
     if (c->rotate_method == 2 && !dmma) return set_err("rotate: the DMMA kernel covers Omega with num_wann <= 20 only");
+    if (c->rotate_method == 4 || (c->rotate_method == 0 && !dmma)) return run_events_xbar(c, G, nk);
     if (dmma) {
         WbFormulaFlags fl{WBGPU_OMEGA, G.ev.internal_terms, G.ev.external_terms};
 #define WB_DMMA_CASE(KS, MT2)                                                                                         \
