@@ -153,16 +153,18 @@ def test_eigh(wb, fe, te, fe_orc, te_orc, orc, which):
 
 @pytest.mark.parametrize("nw,degenerate", [(1, False), (2, False), (3, False), (8, True), (9, False), (16, False),
                                            (17, False), (18, False), (18, True), (24, True), (32, False), (33, False),
-                                           (40, False)])
+                                           (40, False), (40, True), (64, False), (96, True), (127, False),
+                                           (128, False)])
 def test_eigh_sizes_and_degeneracies(wb, nw, degenerate):
-    """Both eigensolvers (Householder+QL for nw <= 32, Jacobi otherwise / on request) against LAPACK on
-    random Hermitian models, including exactly degenerate spectra."""
+    """The eigensolvers (Householder+QL: warp per k-point for nw <= 32, CTA per k-point for nw <= 128; Jacobi on
+    request where it fits shared memory) against LAPACK on random Hermitian models, including exactly
+    degenerate spectra."""
     sysg = wb.synthetic_system(nw, rmax=1, seed=nw, matrices=("Ham",), degenerate_pairs=degenerate)
     # nw = 18 also exercises the two-k-points-per-warp reduction (method 2) against the one-per-warp kernel
     # (method 3), on an odd number of k-points
     NKFFT, dK = ([3, 1, 3] if nw == 18 else [3, 2, 4]), [0.03, 0.01, 0.2]
     from wannierberri_b200 import _lib
-    for method in ((2, 3, 1) if nw == 18 else (2, 1) if nw <= 32 else (1,)):
+    for method in ((2, 3, 1) if nw == 18 else (2, 1) if nw <= 32 else (0, 1) if nw <= 40 else (0,)):
         eng = wb.Engine(sysg)
         eng.set_option("eig_method", method)
         eng.plan(NKFFT, [_lib.IDENTITY])
@@ -251,6 +253,24 @@ def test_omega_synthetic_sizes(wb, orc, nw):
     got = wb.calculators.static.AHC(Efermi=Ef)(data).data
     ref = orc.AHC(orc.OracleDataK(syso, dK, NKFFT), Ef)
     assert relerr(got, ref) < RTOL
+
+
+@pytest.mark.parametrize("nw", [40, 64, 128])
+def test_large_num_wann(wb, orc, nw):
+    """BASELINE config 5 in miniature (many Wannier functions, Ham + AA): eigenvalues, DOS / CumDOS and the
+    tensor-core rotation + Berry curvature (AHC) against the oracle; one small K-block."""
+    sysg = wb.synthetic_system(nw, rmax=1, seed=500 + nw)
+    syso = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
+                            {k: sysg.get_R_mat(k) for k in ("Ham", "AA")})
+    NKFFT, dK = [2, 1, 2], [0.05, 0.11, 0.02]
+    Ef = np.linspace(-4., 4., 41)
+    grid = wb.Grid(sysg, NKdiv=[1, 1, 1], NKFFT=NKFFT)
+    data = wb.Data_K_R(sysg, dK=dK, grid=grid)
+    odata = orc.OracleDataK(syso, dK, NKFFT)
+    st = wb.calculators.static
+    assert relerr(st.DOS(Efermi=Ef)(data).data, orc.DOS(odata, Ef)) < RTOL
+    assert relerr(st.CumDOS(Efermi=Ef)(data).data, orc.CumDOS(odata, Ef)) < RTOL
+    assert relerr(st.AHC(Efermi=Ef)(data).data, orc.AHC(odata, Ef)) < RTOL
 
 
 def test_run_fe_vs_upstream_golden(wb, fe):

@@ -1,0 +1,322 @@
+// Batched complex Hermitian eigensolver for 32 < nw <= 128: the same zhetd2 + tql2 + zunm2l sequence as
+// wb_eigh_ql.cuh, with ONE CTA PER K-POINT for the two matrix phases (the matrix lives in shared memory):
+//
+//   K1L  wb_tridiag_cta_kernel   packed lower triangle of H(k) in shared memory (132 KB at nw = 128), thread pair per
+//                                row; Hermitian matvec + rank-2 update per Householder step.
+//   K2   wb_tql_kernel           (wb_eigh_ql.cuh) thread per k-point implicit QL, streams its Givens rotations.
+//   K3L  wb_eigvec_cta_kernel    real Z (nw x nw doubles, 128 KB at nw = 128) in shared memory, thread = row: replay of
+//                                the rotation stream; sort; back-transformation by the Householder reflectors in
+//                                panels of 16 eigenvectors; writes E (ascending) and U.
+//
+// Replaces  E_K, UU_K = np.linalg.eigh(HH_K)   (data_K/data_K.py:211-218, 309-322).
+#pragma once
+#include "wb_common.cuh"
+#include "wb_eigh_ql.cuh"
+
+// start of column j of a packed lower triangle stored column by column (== tri_index(j, j, n))
+__device__ __forceinline__ int wb_cs(int j, int n) { return j * n - (j * (j - 1)) / 2; }
+
+// sum of (a, b) over the CTA; `red` holds 2 x 32 double2, `phase` alternates between the two halves so that
+// back-to-back reductions need one barrier each
+__device__ __forceinline__ double2 wb_block_sum2(double a, double b, double2* red, int& phase, int nwarps) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    double2* buf = red + phase * 32;
+    if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = make_double2(a, b);
+    __syncthreads();
+    double2 s = make_double2(0., 0.);
+    for (int w = 0; w < nwarps; w++) { s.x += buf[w].x; s.y += buf[w].y; }
+    phase ^= 1;
+    return s;
+}
+
+__host__ inline size_t wb_tridiag_cta_smem_bytes(int n) {
+    return sizeof(cplx) * ((size_t)n * (n + 1) / 2 + 4 * (size_t)n) + sizeof(double2) * 64;
+}
+
+// Output: d[t][n], e[t][n] (e[n-1] = 0), tau[t][n], Vh[t][k][i] = component i (> k+1) of Householder vector k.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_tridiag_cta_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, double* __restrict__ dout,
+                      double* __restrict__ eout, cplx* __restrict__ tauout, cplx* __restrict__ Vh) {
+    extern __shared__ __align__(16) cplx smem_t[];
+    const int n = L.nw, ntri = n * (n + 1) / 2;
+    constexpr int RN = NT / 2;          // rows per pass: thread pair (row, half)
+    cplx* P = smem_t;                   // packed lower triangle, column major
+    cplx* vs = P + ntri;                // [n]
+    cplx* ws = vs + n;                  // [n]
+    cplx* xs = ws + n;                  // [2][n] partial matvec sums
+    double2* red = (double2*)(xs + 2 * n);
+    const int row = threadIdx.x % RN, half = threadIdx.x / RN;
+    const int nwarps = NT / 32;
+    int phase = 0;
+    for (long t = blockIdx.x; t < nk; t += gridDim.x) {
+        const long ik = k0 + t;
+        const cplx* H = rec + ik * L.E + L.off_H;
+        __syncthreads();
+        // record: H(i, j), i <= j at tri_index(i, j) = cs(i) + j - i; lower triangle L(r, j) = conj(H(j, r))
+        for (int x = threadIdx.x; x < ntri; x += NT) P[x] = cconj(H[x]);
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += NT) P[wb_cs(j, n)].y = 0.;
+        double* d = dout + t * n;
+        double* e = eout + t * n;
+        cplx* tau_o = tauout + t * n;
+        for (int k = 0; k < n - 1; k++) {
+            __syncthreads();
+            const int csk = wb_cs(k, n);
+            // ---- zlarfg on column k, rows k+1..n-1
+            double sq = 0.;
+            for (int r = k + 2 + threadIdx.x; r < n; r += NT) {
+                cplx x = P[csk + r - k];
+                sq += x.x * x.x + x.y * x.y;
+            }
+            const double xnorm2 = wb_block_sum2(sq, 0., red, phase, nwarps).x;
+            const cplx alpha = P[csk + 1];
+            cplx tau = cmake(0., 0.);
+            double beta = alpha.x;
+            cplx scale = cmake(0., 0.);
+            if (xnorm2 != 0. || alpha.y != 0.) {
+                beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xnorm2), alpha.x);
+                const double binv = 1. / beta;
+                tau = cmake((beta - alpha.x) * binv, -alpha.y * binv);
+                cplx den = cmake(alpha.x - beta, alpha.y);
+                double dn = 1. / (den.x * den.x + den.y * den.y);
+                scale = cmake(den.x * dn, -den.y * dn);
+            }
+            const bool active = (tau.x != 0. || tau.y != 0.);  // uniform
+            __syncthreads();   // everybody has read alpha / column k
+            for (int r = k + 1 + threadIdx.x; r < n; r += NT) {
+                cplx v = (r == k + 1) ? cmake(1., 0.) : cmul(P[csk + r - k], scale);
+                vs[r] = v;
+                if (r > k + 1) P[csk + r - k] = v;   // the Householder vector stays in place
+            }
+            if (threadIdx.x == 0) { d[k] = P[csk].x; e[k] = beta; tau_o[k] = tau; }
+            if (!active) continue;
+            __syncthreads();
+            // ---- x = tau A v  (rows > k): row r = sum_{j=k+1..r} L(r,j) v_j + sum_{i>r} conj(L(i,r)) v_i
+            const int m = n - k - 1;              // elements per row
+            const int mh = (m + 1) >> 1;
+            for (int rb = 0; rb < n; rb += RN) {
+                const int r = rb + row;
+                if (r > k && r < n) {
+                    const int e0 = half * mh, e1 = min(m, e0 + mh);
+                    const int rowcnt = r - k;
+                    cplx a0 = cmake(0., 0.), a1 = cmake(0., 0.);
+                    {
+                        const int ea = e0, eb = min(e1, rowcnt);
+                        int j = k + 1 + ea;
+                        int cj = wb_cs(j, n);
+                        for (int ee = ea; ee < eb; ee++, j++) {
+                            cfma((ee & 1) ? a1 : a0, P[cj + r - j], vs[j]);
+                            cj += n - j;
+                        }
+                    }
+                    {
+                        const int ea = max(e0, rowcnt), eb = e1;
+                        const int csr = wb_cs(r, n);
+                        for (int ee = ea; ee < eb; ee++) {
+                            const int i = r + 1 + ee - rowcnt;
+                            cfma_conj((ee & 1) ? a1 : a0, P[csr + i - r], vs[i]);
+                        }
+                    }
+                    xs[half * n + r] = cadd(a0, a1);
+                }
+            }
+            __syncthreads();
+            cplx xr[(128 + NT - 1) / NT];   // rows of this thread (n <= 128)
+            double pdx = 0., pdy = 0.;
+#pragma unroll
+            for (int u = 0; u < (128 + NT - 1) / NT; u++) {
+                const int r = threadIdx.x + u * NT;
+                xr[u] = cmake(0., 0.);
+                if (r > k && r < n) {
+                    xr[u] = cmul(tau, cadd(xs[r], xs[n + r]));
+                    cplx pd = cconjmul(xr[u], vs[r]);
+                    pdx += pd.x;
+                    pdy += pd.y;
+                }
+            }
+            const double2 dot = wb_block_sum2(pdx, pdy, red, phase, nwarps);
+            const cplx al2 = cscale(-0.5, cmul(tau, cmake(dot.x, dot.y)));
+#pragma unroll
+            for (int u = 0; u < (128 + NT - 1) / NT; u++) {
+                const int r = threadIdx.x + u * NT;
+                if (r > k && r < n) ws[r] = cadd(xr[u], cmul(al2, vs[r]));
+            }
+            __syncthreads();
+            // ---- L(r, j) -= v_r conj(w_j) + w_r conj(v_j),  k < j <= r
+            for (int rb = 0; rb < n; rb += RN) {
+                const int r = rb + row;
+                if (r > k && r < n) {
+                    const int cnt = r - k, ch = (cnt + 1) >> 1;
+                    const int ja = k + 1 + half * ch, jb = min(r + 1, ja + ch);
+                    const cplx v = vs[r], w = ws[r];
+                    int cj = wb_cs(ja, n);
+                    for (int j = ja; j < jb; j++) {
+                        const cplx wj = ws[j], vj = vs[j];
+                        cplx a = P[cj + r - j];
+                        a.x = fma(-v.x, wj.x, a.x);
+                        a.y = fma(-v.y, wj.x, a.y);
+                        a.x = fma(-v.y, wj.y, a.x);
+                        a.y = fma(v.x, wj.y, a.y);
+                        a.x = fma(-w.x, vj.x, a.x);
+                        a.y = fma(-w.y, vj.x, a.y);
+                        a.x = fma(-w.y, vj.y, a.x);
+                        a.y = fma(w.x, vj.y, a.y);
+                        P[cj + r - j] = a;
+                        cj += n - j;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            d[n - 1] = P[wb_cs(n - 1, n)].x;
+            e[n - 1] = 0.;
+            tau_o[n - 1] = cmake(0., 0.);
+        }
+        cplx* Vt = Vh + (size_t)t * n * n;
+        for (int k = 0; k < n - 2; k++) {
+            const int csk = wb_cs(k, n);
+            for (int i = k + 2 + threadIdx.x; i < n; i += NT) Vt[k * n + i] = P[csk + i - k];
+        }
+    }
+}
+
+__host__ inline size_t wb_eigvec_cta_smem_bytes(int n) {
+    const int ldu = n | 1;
+    return sizeof(double) * (((size_t)n * n + 1) & ~(size_t)1) + sizeof(cplx) * ((size_t)16 * ldu + 2 * n + n + 2 * 128) +
+           sizeof(double) * n + sizeof(int) * 2 * n + 16;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, const cplx* __restrict__ tauin,
+                     const cplx* __restrict__ Vh, const double2* __restrict__ rot, int capR, const int* __restrict__ hdr,
+                     int capS, const int* __restrict__ nsweep, int want_U, double* __restrict__ Eout,
+                     cplx* __restrict__ Uout, int* __restrict__ nfail) {
+    static_assert(NT == 128, "thread = row of Z, n <= 128; 16 panel columns x 8 row slices");
+    extern __shared__ __align__(16) double smem_e[];
+    const int ldu = n | 1;
+    double* Zs = smem_e;                          // [col][row]
+    cplx* up = (cplx*)(Zs + (((size_t)n * n + 1) & ~(size_t)1));   // [16][ldu]
+    cplx* vbuf = up + 16 * ldu;                   // [2][n]
+    cplx* taus = vbuf + 2 * n;                    // [n]
+    double2* rs = (double2*)(taus + n);           // [2][128]
+    double* dsm = (double*)(rs + 2 * 128);        // [n]
+    int* rank = (int*)(dsm + n);                  // [n]
+    int* inv = rank + n;                          // [n]
+    const int tid = threadIdx.x;
+    for (long t = blockIdx.x; t < nk; t += gridDim.x) {
+        const long ik = k0 + t;
+        const int nsr = nsweep[t];
+        if (nsr < 0) {   // uniform
+            if (tid == 0) atomicAdd(nfail, 1);
+            continue;
+        }
+        const int ns = nsr & 4095;
+        __syncthreads();
+        if (tid < n) { dsm[tid] = dvals[t * n + tid]; taus[tid] = tauin[t * n + tid]; }
+        if (want_U) {
+            for (int x = tid; x < n * n; x += NT) Zs[x] = 0.;
+            __syncthreads();
+            if (tid < n) Zs[tid * n + tid] = 1.;
+            // ---- replay the rotation stream (thread = row of Z)
+            const double2* myrot = rot + (size_t)t * capR;
+            const int* myhdr = hdr + (size_t)t * capS;
+            int r0 = 0;
+            if (ns > 0) {
+                const int h = myhdr[0];
+                const int len = (h >> 8) - (h & 255);
+                if (tid < len) rs[tid] = myrot[tid];
+            }
+            for (int s = 0; s < ns; s++) {
+                const int h = myhdr[s];
+                const int l = h & 255, m = h >> 8, len = m - l;
+                __syncthreads();
+                if (s + 1 < ns) {
+                    const int h2 = myhdr[s + 1];
+                    const int len2 = (h2 >> 8) - (h2 & 255);
+                    if (tid < len2) rs[((s + 1) & 1) * 128 + tid] = myrot[r0 + len + tid];
+                }
+                if (tid < n) {
+                    const double2* q = rs + (s & 1) * 128;
+                    double carry = Zs[m * n + tid];
+                    for (int i = m - 1; i >= l; i--) {
+                        const double2 cs = q[m - 1 - i];
+                        const double zi = Zs[i * n + tid];
+                        Zs[(i + 1) * n + tid] = cs.y * zi + cs.x * carry;
+                        carry = cs.x * zi - cs.y * carry;
+                    }
+                    Zs[l * n + tid] = carry;
+                }
+                r0 += len;
+            }
+        }
+        __syncthreads();
+        // ---- sort
+        if (tid < n) {
+            const double myd = dsm[tid];
+            int rk = 0;
+            for (int j = 0; j < n; j++) {
+                const double dj = dsm[j];
+                rk += (dj < myd) || (dj == myd && j < tid);
+            }
+            rank[tid] = rk;
+            inv[rk] = tid;
+            Eout[ik * n + rk] = myd;
+        }
+        if (!want_U) continue;
+        __syncthreads();
+        // ---- back-transformation  u <- H(0) H(1) ... H(n-2) u  in panels of 16 eigenvectors (sorted order)
+        const cplx* Vt = Vh + (size_t)t * n * n;
+        const int c = tid >> 3, sl = tid & 7;
+        for (int p0 = 0; p0 < n; p0 += 16) {
+            __syncthreads();
+            for (int x = tid; x < 16 * n; x += NT) {
+                const int cc = x / n, i = x - cc * n;
+                up[cc * ldu + i] = cmake((p0 + cc < n) ? Zs[inv[p0 + cc] * n + i] : 0., 0.);
+            }
+            {   // reflector n-2 into vbuf[0]
+                const int k = n - 2;
+                for (int i = tid; i < n; i += NT)
+                    vbuf[i] = (i > k + 1) ? Vt[k * n + i] : ((i == k + 1) ? cmake(1., 0.) : cmake(0., 0.));
+            }
+            int cur = 0;
+            for (int k = n - 2; k >= 0; k--, cur ^= 1) {
+                __syncthreads();
+                if (k > 0) {   // prefetch reflector k-1 into the other buffer
+                    cplx* nb = vbuf + (cur ^ 1) * n;
+                    const int k1 = k - 1;
+                    for (int i = tid; i < n; i += NT)
+                        nb[i] = (i > k1 + 1) ? Vt[k1 * n + i] : ((i == k1 + 1) ? cmake(1., 0.) : cmake(0., 0.));
+                }
+                const cplx tau = taus[k];
+                if (tau.x == 0. && tau.y == 0.) continue;   // uniform
+                const cplx* v = vbuf + cur * n;
+                cplx* u = up + c * ldu;
+                cplx sd = cmake(0., 0.);
+                for (int i = k + 1 + sl; i < n; i += 8) cfma_conj(sd, v[i], u[i]);
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    sd.x += __shfl_xor_sync(0xffffffffu, sd.x, o);
+                    sd.y += __shfl_xor_sync(0xffffffffu, sd.y, o);
+                }
+                const cplx ts = cmul(tau, sd);
+                for (int i = k + 1 + sl; i < n; i += 8) {
+                    const cplx vv = v[i];
+                    cplx uu = u[i];
+                    uu.x -= ts.x * vv.x - ts.y * vv.y;
+                    uu.y -= ts.x * vv.y + ts.y * vv.x;
+                    u[i] = uu;
+                }
+            }
+            __syncthreads();
+            cplx* Uo = Uout + (size_t)ik * n * n;
+            for (int x = tid; x < 16 * n; x += NT) {
+                const int cc = x & 15, i = x >> 4;
+                if (p0 + cc < n) Uo[i * n + p0 + cc] = up[cc * ldu + i];
+            }
+        }
+    }
+}

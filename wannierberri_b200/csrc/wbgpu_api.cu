@@ -19,6 +19,7 @@
 #include "wb_fourier.cuh"
 #include "wb_eigh_jacobi.cuh"
 #include "wb_eigh_ql.cuh"
+#include "wb_eigh_large.cuh"
 #include "wb_groups.cuh"
 #include "wb_rotate_formula.cuh"
 #include "wb_rotate_dmma.cuh"
@@ -85,6 +86,7 @@ struct wbgpu_ctx {
     int capR = 0, capS = 0;
     double *d_dw = nullptr, *d_ew = nullptr;
     cplx* d_tau = nullptr;
+    cplx* d_Vh = nullptr;   // Householder vectors, reflector-major (nw > 32)
     double2* d_rot = nullptr;
     int *d_hdr = nullptr, *d_nsweep = nullptr, *d_faillist = nullptr, *d_nfail = nullptr;
     int64_t eig_fallbacks = 0;
@@ -138,7 +140,8 @@ static void free_plan(wbgpu_ctx* c) {
     for (int d = 0; d < 3; d++) cudaFree(c->d_W[d]);
     cudaFree(c->d_Z); cudaFree(c->d_Y); cudaFree(c->d_X); cudaFree(c->d_U);
     cudaFree(c->d_E); cudaFree(c->d_evlabel); cudaFree(c->d_evval);
-    cudaFree(c->d_dw); cudaFree(c->d_ew); cudaFree(c->d_tau); cudaFree(c->d_rot); cudaFree(c->d_hdr);
+    cudaFree(c->d_dw); cudaFree(c->d_ew); cudaFree(c->d_tau); cudaFree(c->d_rot); cudaFree(c->d_hdr); cudaFree(c->d_Vh);
+    c->d_Vh = nullptr;
     cudaFree(c->d_nsweep); cudaFree(c->d_faillist); cudaFree(c->d_nfail);
     c->d_dw = c->d_ew = nullptr; c->d_tau = nullptr; c->d_rot = nullptr;
     c->d_hdr = c->d_nsweep = c->d_faillist = c->d_nfail = nullptr;
@@ -359,10 +362,15 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
         c->ev_ncmax = ncmax;
         CK(cudaMalloc(&c->d_evval, sizeof(double) * nkl * nw * ncmax));
     }
-    if (nw <= 32) {
-        c->eig_chunk = std::min<long>((long)nkl, 262144);  // thread-per-k QL needs many k-points in flight
+    {
         c->capR = 2 * nw * nw + 32;
         c->capS = (6 * nw + 8 + 3) / 4 * 4;  // 16-byte granular (bulk copies)
+        if (nw <= 32) c->eig_chunk = std::min<long>((long)nkl, 262144);  // thread-per-k QL needs many k-points in flight
+        else {
+            // rotation stream + reflector-major Householder vectors: <= 6 GB per sub-batch
+            double per = 16.0 * c->capR + 16.0 * nw * nw + 4.0 * c->capS + 40.0 * nw;
+            c->eig_chunk = std::max(1L, std::min<long>((long)nkl, (long)(6.0e9 / per)));
+        }
         size_t ch = (size_t)c->eig_chunk;
         CK(cudaMalloc(&c->d_dw, sizeof(double) * ch * nw));
         CK(cudaMalloc(&c->d_ew, sizeof(double) * ch * nw));
@@ -372,6 +380,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
         CK(cudaMalloc(&c->d_nsweep, sizeof(int) * ch));
         CK(cudaMalloc(&c->d_faillist, sizeof(int) * ch));
         CK(cudaMalloc(&c->d_nfail, sizeof(int)));
+        if (nw > 32) CK(cudaMalloc(&c->d_Vh, sizeof(cplx) * ch * nw * nw));
     }
     CK(cudaStreamSynchronize(c->stream));
     c->planned = true;
@@ -529,11 +538,54 @@ static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
     return launch_jacobi(c, k0, nk, true, c->d_faillist, c->d_nfail, 148);
 }
 
+// nw > 32: CTA-per-k-point tridiagonalisation and back-transformation around the thread-per-k-point QL
+static int launch_ql_large(wbgpu_ctx* c, long k0, long nk, bool want_U) {
+    const int nw = c->nw;
+    CK(cudaMemsetAsync(c->d_nfail, 0, sizeof(int), c->stream));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    constexpr int NT1 = 256;
+    size_t smem1 = wb_tridiag_cta_smem_bytes(nw);
+    if ((int)smem1 > c->smem_optin) return set_err("eigh: num_wann=%d needs %zu B shared memory", nw, smem1);
+    CK(cudaFuncSetAttribute(wb_tridiag_cta_kernel<NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    int per_sm1 = std::max(1, std::min(4, (int)((size_t)c->smem_optin / smem1)));
+    wb_tridiag_cta_kernel<NT1><<<(unsigned)std::min(nk, (long)sms * per_sm1), NT1, smem1, c->stream>>>(
+        c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_Vh);
+    CK(cudaGetLastError());
+    constexpr int NT2 = 32;
+    size_t smem2 = sizeof(double) * 2 * nw * NT2;
+    CK(cudaFuncSetAttribute(wb_tql_kernel<NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    wb_tql_kernel<NT2><<<(unsigned)((nk + NT2 - 1) / NT2), NT2, smem2, c->stream>>>(nw, nk, c->d_dw, c->d_ew, c->d_rot, c->capR,
+                                                                                 c->d_hdr, c->capS, c->d_nsweep);
+    CK(cudaGetLastError());
+    constexpr int NT3 = 128;
+    size_t smem3 = wb_eigvec_cta_smem_bytes(nw);
+    if ((int)smem3 > c->smem_optin) return set_err("eigh: num_wann=%d needs %zu B shared memory", nw, smem3);
+    CK(cudaFuncSetAttribute(wb_eigvec_cta_kernel<NT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    int per_sm3 = std::max(1, std::min(4, (int)((size_t)c->smem_optin / smem3)));
+    wb_eigvec_cta_kernel<NT3><<<(unsigned)std::min(nk, (long)sms * per_sm3), NT3, smem3, c->stream>>>(
+        nw, k0, nk, c->d_dw, c->d_tau, c->d_Vh, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep, want_U ? 1 : 0, c->d_E,
+        c->d_U, c->d_nfail);
+    c->launches += 3;
+    CK(cudaGetLastError());
+    // there is no second solver for these sizes: a QL iteration that did not converge is an error
+    int nfail = 0;
+    CK(cudaMemcpyAsync(&nfail, c->d_nfail, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (nfail) return set_err("eigh: the QL iteration did not converge for %d k-point(s)", nfail);
+    return 0;
+}
+
 static int run_eigh(wbgpu_ctx* c, long nk, bool want_U) {
     const int nw = c->nw;
     CK(cudaMemsetAsync(c->d_sweeps, 0, sizeof(int), c->stream));
-    bool use_ql = (nw <= 32) && (c->eig_method != 1);  // 2 = QL, 3 = QL with the one-k-point-per-warp reduction
-    if (c->eig_method == 2 && nw > 32) return set_err("eigh: Householder+QL path needs num_wann <= 32");
+    if (nw > 32) {
+        if (c->eig_method == 1) return launch_jacobi(c, 0, nk, want_U, nullptr, nullptr, 148L * 64);
+        for (long k0 = 0; k0 < nk; k0 += c->eig_chunk)
+            if (launch_ql_large(c, k0, std::min(c->eig_chunk, nk - k0), want_U)) return 1;
+        return 0;
+    }
+    bool use_ql = (c->eig_method != 1);  // 2 = QL, 3 = QL with the one-k-point-per-warp reduction
     if (!use_ql) return launch_jacobi(c, 0, nk, want_U, nullptr, nullptr, 148L * 64);
     for (long k0 = 0; k0 < nk; k0 += c->eig_chunk) {
         long n = std::min(c->eig_chunk, nk - k0);
