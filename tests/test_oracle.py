@@ -113,3 +113,40 @@ def test_te_run(te):
     res = orc.run(te, [2, 2, 2], [2, 2, 3], calcs)
     for q in calcs:
         assert relerr(res[q], g[q]) < RTOL, q
+
+
+# ---------------------------------------------------------------------------------------- Kubo path
+KUBO_CASES = dict(
+    ref_optcond=("OpticalConductivity", dict(smr_fixed_width=0.20, smr_type="Gaussian"), True),
+    lor_optcond=("OpticalConductivity", dict(smr_fixed_width=0.1, smr_type="Lorentzian"), False),
+    lor_optcond_thresh=("OpticalConductivity", dict(smr_fixed_width=0.1, smr_type="Lorentzian", degen_thresh=0.05), False),
+    lor_optcond_int=("OpticalConductivity", dict(smr_fixed_width=0.1, smr_type="Lorentzian", external_terms=False), False),
+    gau_optcond=("OpticalConductivity", dict(smr_fixed_width=0.15, smr_type="Gaussian"), False),
+    lor_jdos=("JDOS", dict(smr_fixed_width=0.1, smr_type="Lorentzian"), False),
+    gau_jdos=("JDOS", dict(smr_fixed_width=0.15, smr_type="Gaussian"), False),
+)
+
+
+def kubo_axes(g, ref_axes):
+    return (g["ref_Efermi"], g["ref_omega"]) if ref_axes else (g["Efermi"], g["omega"])
+
+
+@pytest.mark.parametrize("case", sorted(KUBO_CASES))
+def test_kubo_block_vs_reference(fe, case):
+    """DynamicCalculator.__call__ for one K-block (fixture written by make_golden_kubo.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_kubo.npz"))
+    name, kw, ref_axes = KUBO_CASES[case]
+    Ef, om = kubo_axes(g, ref_axes)
+    data = orc.OracleDataK(fe, g["block_dK"], g["block_NKFFT"])
+    got = orc.CALCULATORS[name](data, Ef, omega=om, **kw)
+    assert got.shape == g["block_" + case].shape
+    assert relerr(got, g["block_" + case]) < RTOL
+
+
+def test_kubo_run_vs_upstream_golden(fe):
+    """The reference's own regression file Fe_W90-opt_conductivity_iter-0000.npz (tests/test_run.py:290-305)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_kubo.npz"))
+    name, kw, _ = KUBO_CASES["ref_optcond"]
+    res = orc.run(fe, [2, 2, 2], [2, 2, 2], dict(oc=(name, g["ref_Efermi"], dict(omega=g["ref_omega"], **kw))))
+    assert relerr(res["oc"], g["upstream_golden_opt_conductivity"]) < RTOL
+    assert relerr(res["oc"], g["run_ref_optcond"]) < RTOL
