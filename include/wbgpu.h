@@ -25,6 +25,8 @@
  *   wbgpu_xk                           <- Rvectors.R_to_k / FFT_R_to_k.__call__
  *                                         (fourier/rvectors.py:496-506, fourier/fft.py:133-192)
  *   wbgpu_band_traces                  <- Formula_ln.trace per band group (formula/formula.py:76-79)
+ *   wbgpu_kubo_scan                    <- paralfunc + DynamicCalculator.__call__ over a list of K-blocks
+ *                                         (run_grid.py:258-265; calculators/dynamic.py:26-114,146-196)
  */
 #ifndef WBGPU_H
 #define WBGPU_H
@@ -46,7 +48,9 @@ enum {
     WBGPU_VEL_HPLUS = 4,  /* VelHplus        covariant.py:805-809 rank 2 */
     WBGPU_VEL_SPIN = 5,   /* VelSpin         covariant.py:812-814 rank 2 */
     WBGPU_SPIN = 6,       /* Spin            covariant.py:331-335 rank 1 */
-    WBGPU_NFORMULA = 7
+    WBGPU_KUBO = 7,       /* plan flag only: channels of the Kubo path (dH, and A with external terms),
+                             Formula_OptCond calculators/dynamic.py:170-181 */
+    WBGPU_NFORMULA = 8
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */
@@ -115,6 +119,28 @@ int wbgpu_static_scan_dev(wbgpu_ctx* ctx, int nblocks, const double* dK_dev, con
 /* number of float64 values one spec writes */
 int64_t wbgpu_spec_size(const wbgpu_scan_spec* spec);
 
+/* One (Efermi x omega) scan = one DynamicCalculator.__call__ (calculators/dynamic.py:26-114) at kBT = 0. */
+enum { WBGPU_KUBO_OPTCOND = 0,  /* OpticalConductivity dynamic.py:184-196: complex128 data[nEF][nomega][3][3] */
+       WBGPU_KUBO_JDOS = 1 };   /* JDOS                dynamic.py:146-162: float64    data[nEF][nomega]       */
+typedef struct wbgpu_kubo_spec {
+    int32_t kind;            /* WBGPU_KUBO_*                                   */
+    int32_t nEF, nomega;
+    int32_t smr_type;        /* 0 = Lorentzian, 1 = Gaussian (dynamic.py:49-54) */
+    int32_t degen_Kramers;
+    int32_t external_terms;  /* kwargs_formula (formula.py:11-29)               */
+    double smr_fixed_width;
+    double degen_thresh;
+    double factor;           /* constant_factor                                */
+} wbgpu_kubo_spec;
+/* number of float64 values the scan writes (complex counted as 2) */
+int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* spec);
+/* out = sum_b weight[b] * scan(block b).  Efermi[nEF] (ascending) and omega[nomega]: HOST pointers; out: HOST
+ * pointer, layout of the reference's EnergyResult.data: [nEF][nomega][3][3] complex128 (re, im interleaved) or
+ * [nEF][nomega] float64, already multiplied by factor / (nk * cell_volume) (dynamic.py:101).
+ * The plan must include WBGPU_KUBO. */
+int wbgpu_kubo_scan(wbgpu_ctx* ctx, int nblocks, const double* dK, const double* weight, const wbgpu_kubo_spec* spec,
+                    const double* Efermi, const double* omega, double* out);
+
 /* Parity probes (HOST output pointers). One K-block each. */
 int wbgpu_kpoints(wbgpu_ctx* ctx, const double dK[3], double* kpoints /*[nk][3]*/);
 int wbgpu_eig(wbgpu_ctx* ctx, const double dK[3], double* E /*[nk][nw]*/, double* U /*[nk][nw][nw] c128 or NULL*/);
@@ -130,7 +156,7 @@ enum {
     WBGPU_STAGE_EIGH = 1,     /* batched Hermitian eigensolver */
     WBGPU_STAGE_ROTATE = 2,   /* U^dagger X U + formula -> band-group events */
     WBGPU_STAGE_IDENTITY = 3, /* band groups of the Identity formula */
-    WBGPU_STAGE_SCAN = 4,     /* histogram accumulation */
+    WBGPU_STAGE_SCAN = 4,     /* histogram accumulation (static) / entries + accumulation (Kubo) */
     WBGPU_NSTAGES = 5
 };
 /* With option "timing" = 1 every stage of every batch is bracketed by CUDA events on the context's

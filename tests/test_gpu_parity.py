@@ -273,6 +273,71 @@ def test_large_num_wann(wb, orc, nw):
     assert relerr(st.AHC(Efermi=Ef)(data).data, orc.AHC(odata, Ef)) < RTOL
 
 
+# ---------------------------------------------------------------------------------------- Kubo path
+KUBO_CASES = dict(
+    ref_optcond=("OpticalConductivity", dict(smr_fixed_width=0.20, smr_type="Gaussian"), True),
+    lor_optcond=("OpticalConductivity", dict(smr_fixed_width=0.1, smr_type="Lorentzian"), False),
+    lor_optcond_thresh=("OpticalConductivity", dict(smr_fixed_width=0.1, smr_type="Lorentzian", degen_thresh=0.05), False),
+    lor_optcond_int=("OpticalConductivity", dict(smr_fixed_width=0.1, smr_type="Lorentzian",
+                                                 kwargs_formula=dict(external_terms=False)), False),
+    gau_optcond=("OpticalConductivity", dict(smr_fixed_width=0.15, smr_type="Gaussian"), False),
+    lor_jdos=("JDOS", dict(smr_fixed_width=0.1, smr_type="Lorentzian"), False),
+    gau_jdos=("JDOS", dict(smr_fixed_width=0.15, smr_type="Gaussian"), False),
+)
+
+
+@pytest.mark.parametrize("case", sorted(KUBO_CASES))
+def test_kubo_block_vs_reference(wb, fe, case):
+    """DynamicCalculator.__call__(Data_K_R) for one K-block against the reference's output (fixture written by
+    tests/golden/make_golden_kubo.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_kubo.npz"))
+    name, kw, ref_axes = KUBO_CASES[case]
+    Ef, om = (g["ref_Efermi"], g["ref_omega"]) if ref_axes else (g["Efermi"], g["omega"])
+    grid = wb.Grid(fe, NKdiv=[2, 2, 2], NKFFT=g["block_NKFFT"])
+    data = wb.Data_K_R(fe, dK=g["block_dK"], grid=grid)
+    res = getattr(wb.calculators.dynamic, name)(Efermi=Ef, omega=om, **kw)(data)
+    assert res.data.shape == g["block_" + case].shape
+    assert relerr(res.data, g["block_" + case]) < RTOL
+
+
+def test_kubo_run_vs_upstream_golden(wb, fe):
+    """run() with Kubo and static calculators together on the reference's test grid, against the reference's own
+    golden file Fe_W90-opt_conductivity_iter-0000.npz (tests/test_run.py:290-305) and the other fixtures."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_kubo.npz"))
+    g4 = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    dyn, st = wb.calculators.dynamic, wb.calculators.static
+    calcs = {"ahc": st.AHC(Efermi=g4["Efermi"])}
+    for case, (name, kw, ref_axes) in KUBO_CASES.items():
+        Ef, om = (g["ref_Efermi"], g["ref_omega"]) if ref_axes else (g["Efermi"], g["omega"])
+        calcs[case] = getattr(dyn, name)(Efermi=Ef, omega=om, **kw)
+    grid = wb.Grid(fe, NKdiv=[2, 2, 2], NKFFT=[2, 2, 2])
+    res = wb.run(fe, grid, calcs)
+    assert relerr(res.results["ref_optcond"].data, g["upstream_golden_opt_conductivity"]) < RTOL
+    assert relerr(res.results["ahc"].data, g4["upstream_golden_ahc"]) < RTOL
+    for case in KUBO_CASES:
+        assert relerr(res.results[case].data, g["run_" + case]) < RTOL, case
+
+
+@pytest.mark.parametrize("nw,nEF,nom", [(32, 60, 40), (12, 1500, 3), (40, 5, 7)])
+def test_kubo_synthetic(wb, orc, nw, nEF, nom):
+    """BASELINE config 4 in miniature (synthetic 32-WF model, Lorentzian, kBT = 0) and the tiling corner cases of the
+    accumulation kernel (several omega tiles; an Efermi axis that does not fit one shared-memory tile) against
+    the oracle."""
+    sysg = wb.synthetic_system(nw, rmax=1, seed=700 + nw)
+    syso = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
+                            {k: sysg.get_R_mat(k) for k in ("Ham", "AA")})
+    NKFFT, dK = [2, 2, 2], [0.05, 0.11, 0.02]
+    Ef, om = np.linspace(-1., 1., nEF), np.linspace(0., 5., nom)
+    grid = wb.Grid(sysg, NKdiv=[1, 1, 1], NKFFT=NKFFT)
+    data = wb.Data_K_R(sysg, dK=dK, grid=grid)
+    odata = orc.OracleDataK(syso, dK, NKFFT)
+    kw = dict(smr_fixed_width=0.1, smr_type="Lorentzian")
+    got = wb.calculators.dynamic.OpticalConductivity(Efermi=Ef, omega=om, **kw)(data).data
+    assert relerr(got, orc.OpticalConductivity(odata, Ef, omega=om, **kw)) < RTOL
+    got = wb.calculators.dynamic.JDOS(Efermi=Ef, omega=om, **kw)(data).data
+    assert relerr(got, orc.JDOS(odata, Ef, omega=om, **kw)) < RTOL
+
+
 def test_run_fe_vs_upstream_golden(wb, fe):
     """run() on the reference's own test grid against the data of the reference's golden files
     tests/reference/integrate_files/Fe_W90-{ahc,dos,cumdos}_iter-0000.npz."""

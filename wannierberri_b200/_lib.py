@@ -9,7 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwbgpu.so")
 
 # enums of include/wbgpu.h
-IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN = range(7)
+IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN, KUBO = range(8)
+KUBO_OPTCOND, KUBO_JDOS = 0, 1
 FORMULA_RANK = {IDENTITY: 0, OMEGA: 1, MORB_HPM: 1, SPIN: 1, VEL_OMEGA: 2, VEL_HPLUS: 2, VEL_SPIN: 2}
 KEYS = {"Ham": 0, "AA": 1, "BB": 2, "CC": 3, "SS": 4}
 CHANNELS = {"Ham": 0, "dHam": 1, "AA": 2, "rotAA": 3, "BB": 4, "CC": 5, "SS": 6}
@@ -28,6 +29,16 @@ class ScanSpec(C.Structure):
     @property
     def shape(self):
         return (int(self.nEF),) + (3,) * FORMULA_RANK[int(self.formula)]
+
+
+class KuboSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("nEF", C.c_int32), ("nomega", C.c_int32), ("smr_type", C.c_int32),
+                ("degen_Kramers", C.c_int32), ("external_terms", C.c_int32),
+                ("smr_fixed_width", C.c_double), ("degen_thresh", C.c_double), ("factor", C.c_double)]
+
+    @property
+    def shape(self):
+        return (int(self.nEF), int(self.nomega)) + ((3, 3) if int(self.kind) == KUBO_OPTCOND else ())
 
 
 _lib = None
@@ -55,6 +66,9 @@ def lib():
     L.wbgpu_static_scan_dev.argtypes = [vp, C.c_int, vp, vp, C.POINTER(ScanSpec), C.c_int, vp]
     L.wbgpu_spec_size.argtypes = [C.POINTER(ScanSpec)]
     L.wbgpu_spec_size.restype = i64
+    L.wbgpu_kubo_size.argtypes = [C.POINTER(KuboSpec)]
+    L.wbgpu_kubo_size.restype = i64
+    L.wbgpu_kubo_scan.argtypes = [vp, C.c_int, pd, pd, C.POINTER(KuboSpec), pd, pd, pd]
     L.wbgpu_kpoints.argtypes = [vp, pd, pd]
     L.wbgpu_eig.argtypes = [vp, pd, pd, pd]
     L.wbgpu_xk.argtypes = [vp, pd, C.c_int, pd]
@@ -67,7 +81,7 @@ def lib():
     L.wbgpu_fp64_peak.argtypes = [C.c_int, C.c_int, pd]
     for name in ("wbgpu_create", "wbgpu_destroy", "wbgpu_set_R_matrix", "wbgpu_plan", "wbgpu_static_scan",
                  "wbgpu_static_scan_dev", "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_band_traces",
-                 "wbgpu_last_eig_sweeps", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak"):
+                 "wbgpu_last_eig_sweeps", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak", "wbgpu_kubo_scan"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -76,7 +90,8 @@ def lib():
 EXPORTED = ["wbgpu_last_error", "wbgpu_version", "wbgpu_device_count", "wbgpu_create", "wbgpu_destroy",
             "wbgpu_set_R_matrix", "wbgpu_plan", "wbgpu_static_scan", "wbgpu_static_scan_dev", "wbgpu_spec_size",
             "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_band_traces", "wbgpu_kernel_launches",
-            "wbgpu_last_eig_sweeps", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak"]
+            "wbgpu_last_eig_sweeps", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak", "wbgpu_kubo_size",
+            "wbgpu_kubo_scan"]
 
 
 def check(status):

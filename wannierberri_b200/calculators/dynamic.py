@@ -1,0 +1,98 @@
+"""Kubo (Efermi x omega) calculators with the constructor interface of the reference
+(calculators/dynamic.py:26-57): same class names and keyword arguments.  Like the static calculators they do no
+arithmetic on k-points: `spec()` declares the scan that libwbgpu.so evaluates (wbgpu_kubo_scan)."""
+from copy import copy
+
+import numpy as np
+
+from .. import factors
+from .. import _lib
+from .._lib import KuboSpec
+from ..result import EnergyResult
+from .static import Calculator
+
+
+class DynamicCalculator(Calculator):
+
+    kind = None
+    dtype = complex
+
+    def __init__(self, Efermi=None, omega=None, kBT=0, smr_fixed_width=0.1, smr_type='Lorentzian',
+                 kwargs_formula=None, dtype=None, **kwargs):
+        super().__init__(**kwargs)
+        self.Efermi = np.array(Efermi, dtype=float).reshape(-1)
+        self.omega = np.array(omega, dtype=float).reshape(-1)
+        if kBT != 0:
+            raise NotImplementedError("kBT > 0 is not implemented on the GPU path (the Fermi factor is no longer an "
+                                      "interval of the Efermi axis)")
+        if smr_type not in ("Lorentzian", "Gaussian"):
+            raise ValueError(f"Invalid smearing type {smr_type}")  # dynamic.py:54
+        if len(self.Efermi) > 1 and not np.all(np.diff(self.Efermi) > 0):
+            raise NotImplementedError("Efermi must be strictly ascending on the GPU path")
+        self.kBT = kBT
+        self.smr_fixed_width = smr_fixed_width
+        self.smr_type = smr_type
+        self.kwargs_formula = copy(kwargs_formula) if kwargs_formula is not None else {}
+        unknown = set(self.kwargs_formula) - {"external_terms"}
+        if unknown:
+            raise NotImplementedError(f"kwargs_formula {sorted(unknown)} are not implemented on the GPU path")
+        self.constant_factor = 1.
+
+    @property
+    def external_terms(self):
+        return bool(self.kwargs_formula.get("external_terms", True))
+
+    def spec(self):
+        return KuboSpec(kind=self.kind, nEF=len(self.Efermi), nomega=len(self.omega),
+                        smr_type=0 if self.smr_type == "Lorentzian" else 1,
+                        degen_Kramers=int(bool(self.degen_Kramers)), external_terms=int(self.external_terms),
+                        smr_fixed_width=float(self.smr_fixed_width), degen_thresh=float(self.degen_thresh),
+                        factor=float(self.constant_factor))
+
+    def result(self, data):
+        return EnergyResult([self.Efermi, self.omega], data, transformTR=self.transformTR,
+                            transformInv=self.transformInv, E_titles=("Efermi", "omega"), comment=self.comment,
+                            save_mode=self.save_mode, smoothers=(None, None))
+
+    def __call__(self, data_K):
+        """`calc(data_K)` for one K-block (dynamic.py:71-114)."""
+        return self.result(data_K.kubo_scan(self.spec(), self.Efermi, self.omega))
+
+
+class JDOS(DynamicCalculator):
+    r"""Joint Density of States"""
+    kind = _lib.KUBO_JDOS
+    dtype = float
+    transformTR, transformInv = "ident", "ident"
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.sigma = self.smr_fixed_width
+
+
+class OpticalConductivity(DynamicCalculator):
+    r"""Optical conductivity :math:`\sigma_{ab}(\omega)` (Kubo-Greenwood), S/m"""
+    kind = _lib.KUBO_OPTCOND
+    transformTR, transformInv = "trans", "ident"
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.constant_factor = factors.factor_opt
+
+
+_BY_NAME = {c.__name__: c for c in (JDOS, OpticalConductivity)}
+
+
+def adapt(calc):
+    """Accept a calculator of this package or an instance of the reference's class of the same name."""
+    if isinstance(calc, DynamicCalculator):
+        return calc
+    name = type(calc).__name__
+    if name not in _BY_NAME:
+        raise ValueError(f"calculator {name} is not available on the GPU path")
+    new = _BY_NAME[name](Efermi=np.array(calc.Efermi), omega=np.array(calc.omega), kBT=calc.kBT,
+                         smr_fixed_width=calc.smr_fixed_width, smr_type=calc.smr_type,
+                         kwargs_formula=calc.kwargs_formula, degen_thresh=calc.degen_thresh,
+                         degen_Kramers=calc.degen_Kramers, save_mode=calc.save_mode)
+    new.constant_factor = calc.constant_factor
+    return new

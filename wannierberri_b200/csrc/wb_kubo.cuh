@@ -1,0 +1,271 @@
+// Kubo (frequency x Fermi-level) scans: OpticalConductivity and JDOS of the reference's DynamicCalculator.
+//
+// Reference: DynamicCalculator.__call__ (calculators/dynamic.py:71-114) evaluates, per k-point, a dense
+//   restot[omega, Ef, ab] += sum_pairs factor_omega[omega, pair] * factor_Efermi[pair, Ef] * matrix_elements[pair, ab]
+// over all ordered pairs of degenerate band groups.  At kBT = 0 the Fermi factor f(E2) - f(E1) of a pair with
+// group energies lo < hi is -1 (+1 for the reversed pair) exactly on the Fermi levels lo <= Ef < hi and zero
+// elsewhere, so a pair touches an INTERVAL [s, e) of the (sorted) Efermi array.  Here:
+//   wb_kubo_entries_kernel     (CTA per k-point) band groups (data_K.py:172-186 with the window -inf..inf), the
+//                              unordered pairs with a non-empty interval, their matrix elements
+//                              M[ab] = i sum_{m in lo-group, n in hi-group} A_mn,a A_nm,b with the generalised Berry
+//                              connection A = Abar + i D_H (data_K.py:328-334; Formula_OptCond, dynamic.py:170-181)
+//                              from the rotated matrices of wb_rotate_gemm.cuh -> a compact entry list per k-point;
+//   wb_kubo_accumulate_kernel  CTA = (tile of omega, tile of Ef, slice of k-points): the accumulator
+//                              D[omega][Ef][ab] lives in SHARED memory; every entry adds X = -W1 M[ab] + W2 M[ba] at
+//                              bin s and subtracts it at bin e (difference form); one thread owns one (omega, ab,
+//                              re|im) column, so there are no atomics in the loop; a running sum over Ef at the end
+//                              turns the differences into values, which are added to the global array;
+//   wb_kubo_finalize_kernel    scale and transpose to the reference's layout [Ef][omega][3][3].
+// The reference's dense contraction costs n_omega * n_pair * n_Ef * 9 multiply-adds per k-point; this form
+// n_omega * n_pair * 9 * 2.
+#pragma once
+#include "wb_common.cuh"
+#include "wb_groups.cuh"
+#include "wb_rotate_formula.cuh"
+
+constexpr int WB_KUBO_ENT = 20;    // doubles per entry: Delta | (s, e) | M[9] complex
+constexpr int WB_KUBO_CHUNK = 16;  // entries staged per step of the accumulation kernel
+
+struct WbKuboParams {
+    int kind;        // 0 = optical conductivity, 1 = JDOS
+    int smr_type;    // 0 = Lorentzian, 1 = Gaussian
+    int external;    // external terms (Abar) in A_H
+    int nEF, nomega;
+    double eta;      // smr_fixed_width
+    double EFmin, EFmax, wlo, whi;   // JDOS.nonzero (dynamic.py:160-162): Efermi.min/max, omega.min - 5 eta, omega.max + 5 eta
+};
+
+// first index i with Ef[i] >= E  (Ef ascending):  f(E) = (E <= Ef[i]) switches on there (utility.py:172-175)
+__device__ __forceinline__ int wb_lower_bound(const double* __restrict__ Ef, int n, double E) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (Ef[mid] >= E) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+__host__ inline size_t wb_kubo_entries_smem_bytes(int nw) {
+    int cap = nw * (nw - 1) / 2;
+    return sizeof(double) * (3 * (size_t)nw) + sizeof(int) * ((size_t)nw + 4) + sizeof(short) * (4 * (size_t)nw) +
+           sizeof(ushort2) * (size_t)(cap + 1) + 64;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, long kofs, const double* __restrict__ Eall,
+                       WbWindow win, WbKuboParams P, const double* __restrict__ Ef, const double* __restrict__ weight,
+                       long nk_block, double* __restrict__ entries, int* __restrict__ count, int cap) {
+    extern __shared__ __align__(16) double smem_k[];
+    double* Es = smem_k;
+    double* label = Es + nw;
+    double* gE = label + nw;
+    int* gidx = (int*)(gE + nw);
+    int* misc = gidx + nw;            // [0] = ng, [1] = nvalid
+    short* g1 = (short*)(misc + 4);
+    short* g2 = g1 + nw;
+    short* gs = g2 + nw;
+    short* ge = gs + nw;
+    ushort2* plist = (ushort2*)(ge + nw + ((4 * nw) & 1));
+    plist = (ushort2*)(((uintptr_t)plist + 3) & ~(uintptr_t)3);
+    const int n2 = nw * nw;
+    const int lane = threadIdx.x & 31;
+    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        __syncthreads();
+        for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            wb_band_groups(Es, nw, win, g1, g2, label);
+            int ng = 0;
+            for (int n = 0; n < nw; n++)
+                if (g1[n] == n) { gs[ng] = (short)n; ge[ng] = g2[n]; gE[ng] = label[n]; ng++; }
+            misc[0] = ng;
+        }
+        __syncthreads();
+        const int ng = misc[0];
+        for (int g = threadIdx.x; g < ng; g += NT) gidx[g] = wb_lower_bound(Ef, P.nEF, gE[g]);
+        __syncthreads();
+        // ---- pairs lo-group i < hi-group j with a non-empty Fermi interval, compacted in (i, j) order by one warp
+        if (threadIdx.x < 32) {
+            int slot = 0;
+            for (int i = 0; i < ng; i++) {
+                const int si = gidx[i];
+                const double lo = gE[i];
+                for (int j0 = i + 1; j0 < ng; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool valid = false;
+                    if (j < ng) {
+                        valid = si < gidx[j];
+                        if (valid && P.kind == 1) {
+                            const double hi = gE[j];
+                            const double d = hi - lo, dm = lo - hi;
+                            const bool nz1 = (hi < P.EFmax) && (lo > P.EFmin) && (P.wlo < d) && (d < P.whi);
+                            const bool nz2 = (lo < P.EFmax) && (hi > P.EFmin) && (P.wlo < dm) && (dm < P.whi);
+                            valid = nz1 || nz2;
+                        }
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+                    if (valid) {
+                        const int pos = slot + __popc(mask & ((1u << lane) - 1u));
+                        if (pos < cap) plist[pos] = make_ushort2((unsigned short)i, (unsigned short)j);
+                    }
+                    slot += __popc(mask);
+                }
+            }
+            if (lane == 0) misc[1] = min(slot, cap);
+        }
+        __syncthreads();
+        const int nvalid = misc[1];
+        if (threadIdx.x == 0) count[ik] = nvalid;
+        const double wgt = weight[(kofs + ik) / nk_block];
+        double* ent = entries + (size_t)ik * cap * WB_KUBO_ENT;
+        const cplx* Vb = xbar + (size_t)ik * nch * n2;
+        const cplx* Ab = Vb + 3 * n2;
+        const int per = (P.kind == 0) ? 9 : 1;
+        for (int x = threadIdx.x; x < nvalid * per; x += NT) {
+            const int slot = x / per, ab = x - slot * per;
+            const ushort2 pr = plist[slot];
+            const int i = pr.x, j = pr.y;
+            double* e = ent + (size_t)slot * WB_KUBO_ENT;
+            if (ab == 0) {
+                e[0] = gE[j] - gE[i];
+                e[1] = __longlong_as_double(((long long)gidx[j] << 32) | (unsigned)gidx[i]);
+            }
+            if (P.kind == 1) {
+                const double lo = gE[i], hi = gE[j];
+                const double d = hi - lo, dm = lo - hi;
+                const bool nz1 = (hi < P.EFmax) && (lo > P.EFmin) && (P.wlo < d) && (d < P.whi);
+                const bool nz2 = (lo < P.EFmax) && (hi > P.EFmin) && (P.wlo < dm) && (dm < P.whi);
+                e[2] = wgt * (double)((ge[i] - gs[i]) * (ge[j] - gs[j]));
+                e[3] = (double)((nz1 ? 1 : 0) | (nz2 ? 2 : 0));
+            } else {
+                const int a = ab / 3, b = ab - 3 * a;
+                cplx acc = cmake(0., 0.);
+                for (int m = gs[i]; m < ge[i]; m++)
+                    for (int n = gs[j]; n < ge[j]; n++) {
+                        // A_mn,a = Abar_mn,a + i D_mn,a,  D_mn,a = -Vbar_mn,a / (E_m - E_n)
+                        const double inv = wb_deinv(Es[m], Es[n]);
+                        const cplx Vmn = Vb[a * n2 + m * nw + n], Vnm = Vb[b * n2 + n * nw + m];
+                        cplx Amn = cmake(inv * Vmn.y, -inv * Vmn.x);     // i * (-inv V)
+                        cplx Anm = cmake(-inv * Vnm.y, inv * Vnm.x);     // i * (+inv V): 1/(E_n - E_m) = -inv
+                        if (P.external) {
+                            Amn = cadd(Amn, Ab[a * n2 + m * nw + n]);
+                            Anm = cadd(Anm, Ab[b * n2 + n * nw + m]);
+                        }
+                        cfma(acc, Amn, Anm);
+                    }
+                e[2 + 2 * ab] = -wgt * acc.y;   // i * acc
+                e[3 + 2 * ab] = wgt * acc.x;
+            }
+        }
+    }
+}
+
+// factor_omega of OpticalConductivity (dynamic.py:191-196) without the (E2 - E1) prefactor: 1/(d - i eta), the
+// imaginary part replaced by pi * Gaussian(d) for smr_type != Lorentzian
+__device__ __forceinline__ cplx wb_kubo_cfac(double d, double eta, int smr_type) {
+    const double den = 1. / (d * d + eta * eta);
+    if (smr_type == 0) return cmake(d * den, eta * den);
+    double g = 0.;
+    if (fabs(d) < eta * sqrt(200.0)) g = 1.0 / (sqrt(CUDART_PI) * eta) * exp(-(d / eta) * (d / eta));
+    return cmake(d * den, CUDART_PI * g);
+}
+__device__ __forceinline__ double wb_kubo_smear(double x, double eta, int smr_type) {
+    if (smr_type == 0) return 1.0 / (CUDART_PI * eta) * eta * eta / (x * x + eta * eta);
+    if (fabs(x) < eta * sqrt(200.0)) return 1.0 / (sqrt(CUDART_PI) * eta) * exp(-(x / eta) * (x / eta));
+    return 0.;
+}
+
+__host__ inline size_t wb_kubo_acc_smem_bytes(int kind, int wt, int eft) {
+    const int NC = kind == 0 ? 18 : 1;
+    return sizeof(double) * ((size_t)wt * eft * NC + WB_KUBO_CHUNK * WB_KUBO_ENT + (size_t)WB_KUBO_CHUNK * wt * 4);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(1024)
+wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restrict__ count, int cap, long nk,
+                          WbKuboParams P, const double* __restrict__ omega, int wt, int eft, double* __restrict__ Dglob) {
+    constexpr int NC = KIND == 0 ? 18 : 1;
+    extern __shared__ __align__(16) double smem_a[];
+    double* D = smem_a;                                   // [wt][eft][NC]
+    double* ent = D + (size_t)wt * eft * NC;              // [CHUNK][ENT]
+    double* Wb = ent + WB_KUBO_CHUNK * WB_KUBO_ENT;       // [CHUNK][wt][4]
+    const int w0 = blockIdx.x * wt, nwt = min(wt, P.nomega - w0);
+    const int t0 = blockIdx.y * eft, t1 = min(P.nEF, t0 + eft);
+    const int tid = threadIdx.x, NT = blockDim.x;
+    for (int x = tid; x < wt * eft * NC; x += NT) D[x] = 0.;
+    const int iw = tid / NC, c = tid - iw * NC;
+    const bool owner = tid < nwt * NC;
+    const int ab = c >> 1, ri = c & 1, ba = (ab % 3) * 3 + ab / 3;
+    for (long ik = blockIdx.z; ik < nk; ik += gridDim.z) {
+        const int cnt = count[ik];
+        const double* src = entries + (size_t)ik * cap * WB_KUBO_ENT;
+        for (int p0 = 0; p0 < cnt; p0 += WB_KUBO_CHUNK) {
+            const int np = min(WB_KUBO_CHUNK, cnt - p0);
+            __syncthreads();
+            for (int x = tid; x < np * WB_KUBO_ENT; x += NT) ent[x] = src[(size_t)p0 * WB_KUBO_ENT + x];
+            __syncthreads();
+            // ---- phase A: frequency factors of (entry, omega)
+            for (int x = tid; x < np * nwt; x += NT) {
+                const int p = x / nwt, w = x - p * nwt;
+                const double dl = ent[p * WB_KUBO_ENT], om = omega[w0 + w];
+                double* o = Wb + ((size_t)p * wt + w) * 4;
+                if (KIND == 0) {
+                    const cplx c1 = wb_kubo_cfac(dl - om, P.eta, P.smr_type);
+                    const cplx c2 = wb_kubo_cfac(-dl - om, P.eta, P.smr_type);
+                    o[0] = dl * c1.x; o[1] = dl * c1.y;      // pair (lo, hi): (E2 - E1) = +Delta
+                    o[2] = -dl * c2.x; o[3] = -dl * c2.y;    // pair (hi, lo)
+                } else {
+                    const int fl = (int)ent[p * WB_KUBO_ENT + 3];
+                    o[0] = (fl & 1) ? wb_kubo_smear(dl - om, P.eta, P.smr_type) : 0.;    // E1 - E2 = +Delta
+                    o[1] = (fl & 2) ? wb_kubo_smear(-dl - om, P.eta, P.smr_type) : 0.;
+                }
+            }
+            __syncthreads();
+            // ---- phase B: thread = (omega, component): difference-form update of its own column
+            if (owner) {
+                double* col = D + (size_t)iw * eft * NC + c;
+                for (int p = 0; p < np; p++) {
+                    const double* e = ent + p * WB_KUBO_ENT;
+                    const long long se = __double_as_longlong(e[1]);
+                    const int s = max((int)(se & 0xffffffffll), t0), en = min((int)(se >> 32), t1);
+                    if (s >= en) continue;
+                    const double* W = Wb + ((size_t)p * wt + iw) * 4;
+                    double X;
+                    if (KIND == 0) {
+                        // pair (lo, hi): Fermi factor -1, M[ab];  pair (hi, lo): +1, M[ba]
+                        const double Mr = e[2 + 2 * ab], Mi = e[3 + 2 * ab], Nr = e[2 + 2 * ba], Ni = e[3 + 2 * ba];
+                        if (ri == 0) X = -(W[0] * Mr - W[1] * Mi) + (W[2] * Nr - W[3] * Ni);
+                        else X = -(W[0] * Mi + W[1] * Mr) + (W[2] * Ni + W[3] * Nr);
+                    } else {
+                        X = (W[0] - W[1]) * e[2];   // (hi, lo): +1;  (lo, hi): -1
+                    }
+                    col[(size_t)(s - t0) * NC] += X;
+                    if (en < t1) col[(size_t)(en - t0) * NC] -= X;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (owner) {
+        const double* col = D + (size_t)iw * eft * NC + c;
+        double run = 0.;
+        for (int b = 0; b < t1 - t0; b++) {
+            run += col[(size_t)b * NC];
+            if (run != 0.) atomicAdd(Dglob + ((size_t)(w0 + iw) * P.nEF + t0 + b) * NC + c, run);
+        }
+    }
+}
+
+// out[iEf][iw][NC] = scale * D[iw][iEf][NC]
+__global__ void wb_kubo_finalize_kernel(const double* __restrict__ D, int nomega, int nEF, int NC, double scale,
+                                        double* __restrict__ out) {
+    const long total = (long)nomega * nEF * NC;
+    for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(x % NC);
+        const long r = x / NC;
+        const int w = (int)(r % nomega), f = (int)(r / nomega);
+        out[x] = scale * D[((size_t)w * nEF + f) * NC + c];
+    }
+}

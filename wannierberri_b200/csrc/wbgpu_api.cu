@@ -27,6 +27,7 @@
 #include "wb_rotate_mma.cuh"
 #include "wb_rotate_gemm.cuh"
 #include "wb_scan.cuh"
+#include "wb_kubo.cuh"
 #include "wb_probe.cuh"
 
 static thread_local std::string g_err;
@@ -81,6 +82,11 @@ struct wbgpu_ctx {
     size_t xbar_cap = 0;
     double* d_mx = nullptr;
     size_t mx_cap = 0;
+    // Kubo path: entry lists of a sub-batch, global accumulator, axes
+    double* d_kent = nullptr;
+    size_t kent_cap = 0;
+    double* d_kacc = nullptr;
+    size_t kacc_cap = 0;
     // Householder+QL eigensolver work space (per sub-batch of eig_chunk k-points)
     long eig_chunk = 0;
     int capR = 0, capS = 0;
@@ -202,7 +208,7 @@ extern "C" int wbgpu_destroy(wbgpu_ctx* c) {
     free_plan(c);
     cudaFree(c->d_iRvec); cudaFree(c->d_T); cudaFree(c->d_sweeps);
     for (int k = 0; k < WBGPU_NKEYS; k++) cudaFree(c->d_XR[k]);
-    cudaFree(c->d_xbar); cudaFree(c->d_mx);
+    cudaFree(c->d_xbar); cudaFree(c->d_mx); cudaFree(c->d_kent); cudaFree(c->d_kacc);
     cudaFree(c->d_hist); cudaFree(c->d_cum); cudaFree(c->d_dK); cudaFree(c->d_weight); cudaFree(c->d_out);
     delete c;
     return 0;
@@ -283,8 +289,8 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     const uint32_t m = formula_mask;
     auto has = [&](int f) { return (m >> f) & 1u; };
     bool need_dH = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
-                   has(WBGPU_VEL_SPIN);
-    bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS);
+                   has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO);
+    bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) || has(WBGPU_KUBO);
     bool need_A = berry && external_terms;
     bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS)) && external_terms;
     bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN);
@@ -300,7 +306,8 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     L.off_H = take(true);
     for (int a = 0; a < 3; a++) L.off_dH[a] = need_dH ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_A[a] = need_A ? take(true) : -1;
-    for (int a = 0; a < 3; a++) L.off_O[a] = need_A ? take(true) : -1;
+    bool need_O = need_A && (has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS));
+    for (int a = 0; a < 3; a++) L.off_O[a] = need_O ? take(true) : -1;
     for (int a = 0; a < 3; a++) L.off_B[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_C[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_S[a] = need_S ? take(true) : -1;
@@ -356,7 +363,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     {
         int ncmax = 1;
         int sum = 0;
-        for (int f = 1; f < WBGPU_NFORMULA; f++)
+        for (int f = 1; f < WBGPU_KUBO; f++)
             if ((m >> f) & 1u) sum += formula_ncomp(f);
         ncmax = std::max(ncmax, sum);
         c->ev_ncmax = ncmax;
@@ -961,6 +968,129 @@ extern "C" int wbgpu_static_scan(wbgpu_ctx* c, int nblocks, const double* dK, co
     if (wbgpu_static_scan_dev(c, nblocks, c->d_dK, d_w, specs, nspec, c->d_out)) return 1;
     CK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------ Kubo
+extern "C" int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* s) {
+    if (!s || s->nEF < 1 || s->nomega < 1) return -1;
+    if (s->kind == WBGPU_KUBO_OPTCOND) return (int64_t)s->nEF * s->nomega * 18;
+    if (s->kind == WBGPU_KUBO_JDOS) return (int64_t)s->nEF * s->nomega;
+    return -1;
+}
+
+extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, const double* weight, const wbgpu_kubo_spec* spec,
+                               const double* Efermi, const double* omega, double* out) {
+    if (!c || !dK || !weight || !spec || !Efermi || !omega || !out) return set_err("wbgpu_kubo_scan: null pointer argument");
+    if (!c->planned) return set_err("wbgpu_kubo_scan: call wbgpu_plan first");
+    const int64_t nout = wbgpu_kubo_size(spec);
+    if (nout < 0) return set_err("wbgpu_kubo_scan: bad spec (kind=%d nEF=%d nomega=%d)", spec->kind, spec->nEF, spec->nomega);
+    if (spec->smr_type != 0 && spec->smr_type != 1) return set_err("wbgpu_kubo_scan: Invalid smearing type %d", spec->smr_type);
+    if (!(spec->smr_fixed_width > 0)) return set_err("wbgpu_kubo_scan: smr_fixed_width must be positive");
+    const bool optcond = spec->kind == WBGPU_KUBO_OPTCOND;
+    const WbLayout& L = c->L;
+    if (optcond && (!((c->mask >> WBGPU_KUBO) & 1u) || L.off_dH[0] < 0 || (spec->external_terms && L.off_A[0] < 0)))
+        return set_err("wbgpu_kubo_scan: the plan does not hold the channels of the Kubo path (declare WBGPU_KUBO)");
+    for (int i = 1; i < spec->nEF; i++)
+        if (!(Efermi[i] > Efermi[i - 1])) return set_err("wbgpu_kubo_scan: Efermi must be strictly ascending");
+    CK(cudaSetDevice(c->device));
+    const int nw = c->nw, nEF = spec->nEF, nom = spec->nomega, NC = optcond ? 18 : 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+
+    WbKuboParams P;
+    P.kind = spec->kind; P.smr_type = spec->smr_type; P.external = spec->external_terms; P.nEF = nEF; P.nomega = nom;
+    P.eta = spec->smr_fixed_width;
+    P.EFmin = Efermi[0]; P.EFmax = Efermi[nEF - 1];
+    double wmin = omega[0], wmax = omega[0];
+    for (int i = 1; i < nom; i++) { wmin = std::min(wmin, omega[i]); wmax = std::max(wmax, omega[i]); }
+    P.wlo = wmin - 5 * spec->smr_fixed_width;
+    P.whi = wmax + 5 * spec->smr_fixed_width;
+    WbWindow win;
+    win.EFmin = -INFINITY; win.EFmax = INFINITY; win.dEF = 1.; win.degen_thresh = spec->degen_thresh;
+    win.degen_Kramers = spec->degen_Kramers; win.sea = 0; win.nEFx = nEF;
+
+    // device copies: dK | weight | Efermi | omega, accumulator D[nomega][nEF][NC] + output
+    const int nbk = std::max(nblocks, 1);
+    if (ensure(&c->d_dK, &c->dK_cap, sizeof(double) * (4 * (size_t)nbk + nEF + nom))) return 1;
+    double* d_w = c->d_dK + 3 * (size_t)nbk;
+    double* d_Ef = d_w + nbk;
+    double* d_om = d_Ef + nEF;
+    CK(cudaMemcpyAsync(c->d_dK, dK, sizeof(double) * 3 * nblocks, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_w, weight, sizeof(double) * nblocks, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_Ef, Efermi, sizeof(double) * nEF, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_om, omega, sizeof(double) * nom, cudaMemcpyHostToDevice, c->stream));
+    const size_t nacc = (size_t)nom * nEF * NC;
+    if (ensure(&c->d_kacc, &c->kacc_cap, sizeof(double) * 2 * nacc)) return 1;
+    CK(cudaMemsetAsync(c->d_kacc, 0, sizeof(double) * nacc, c->stream));
+
+    // tiles of the accumulation kernel: D tile [wt][eft][NC] in <= 160 KB of shared memory
+    const size_t budget = 160 * 1024;
+    int eft = nEF, wt = (int)(budget / (sizeof(double) * (size_t)nEF * NC));
+    if (wt < 1) { wt = 1; eft = (int)(budget / (sizeof(double) * NC)); }
+    wt = std::min(wt, std::min(nom, optcond ? 14 : 256));
+    const int nthreads = std::max(64, (wt * NC + 31) / 32 * 32);
+    const int nwtile = (nom + wt - 1) / wt, neftile = (nEF + eft - 1) / eft;
+    const size_t smem_acc = wb_kubo_acc_smem_bytes(spec->kind, wt, eft);
+    if (optcond) CK(cudaFuncSetAttribute(wb_kubo_accumulate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc));
+    else CK(cudaFuncSetAttribute(wb_kubo_accumulate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc));
+
+    WbChanList ch;
+    ch.n = 0;
+    if (optcond) {
+        for (int a = 0; a < 3; a++) { ch.off[ch.n] = L.off_dH[a]; ch.herm[ch.n] = 0; ch.n++; }
+        if (spec->external_terms)
+            for (int a = 0; a < 3; a++) { ch.off[ch.n] = L.off_A[a]; ch.herm[ch.n] = 1; ch.n++; }
+    }
+    const int cap = std::max(1, nw * (nw - 1) / 2);
+    const size_t smem_ent = wb_kubo_entries_smem_bytes(nw);
+    if (smem_ent > 48 * 1024)
+        CK(cudaFuncSetAttribute(wb_kubo_entries_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ent));
+
+    for (int b0 = 0; b0 < nblocks; b0 += c->nb_max) {
+        const int nb = std::min(c->nb_max, nblocks - b0);
+        const long nk = (long)nb * c->nk_block;
+        stage_begin(c, WBGPU_STAGE_FOURIER);
+        if (run_fourier(c, c->d_dK + 3 * (size_t)b0, nb)) return 1;
+        stage_end(c);
+        stage_begin(c, WBGPU_STAGE_EIGH);
+        if (run_eigh(c, nk, optcond)) return 1;
+        stage_end(c);
+        long chunk = std::min(nk, std::max(1L, (long)(3.0e9 / (8.0 * WB_KUBO_ENT * cap))));
+        if (optcond) chunk = std::min(chunk, xbar_chunk(c, ch.n, nk));
+        if (optcond && ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * nw * nw)) return 1;
+        if (ensure(&c->d_kent, &c->kent_cap, sizeof(double) * (size_t)chunk * cap * WB_KUBO_ENT + sizeof(int) * (size_t)chunk + 16)) return 1;
+        int* d_count = (int*)(c->d_kent + (size_t)chunk * cap * WB_KUBO_ENT);
+        for (long k0 = 0; k0 < nk; k0 += chunk) {
+            const long n = std::min(chunk, nk - k0);
+            if (optcond) {
+                stage_begin(c, WBGPU_STAGE_ROTATE);
+                if (rotate_gemm(c, ch, k0, n)) return 1;
+                stage_end(c);
+            }
+            stage_begin(c, WBGPU_STAGE_SCAN);
+            wb_kubo_entries_kernel<128><<<(unsigned)std::min(n, (long)sms * 8), 128, smem_ent, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, k0, c->d_E + k0 * nw, win, P, d_Ef, d_w + b0, c->nk_block, c->d_kent, d_count, cap);
+            const int nsplit = (int)std::max(1L, std::min(n, (long)((2 * sms + nwtile * neftile - 1) / (nwtile * neftile))));
+            dim3 grid((unsigned)nwtile, (unsigned)neftile, (unsigned)nsplit);
+            if (optcond)
+                wb_kubo_accumulate_kernel<0><<<grid, nthreads, smem_acc, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, wt, eft, c->d_kacc);
+            else
+                wb_kubo_accumulate_kernel<1><<<grid, nthreads, smem_acc, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, wt, eft, c->d_kacc);
+            c->launches += 2;
+            stage_end(c);
+            CK(cudaGetLastError());
+        }
+    }
+    const double scale = spec->factor / (c->cell_volume * (double)c->nk_block);
+    wb_kubo_finalize_kernel<<<(unsigned)std::min<size_t>((nacc + 255) / 256, 1184), 256, 0, c->stream>>>(c->d_kacc, nom, nEF, NC, scale,
+                                                                                                    c->d_kacc + nacc);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, c->d_kacc + nacc, sizeof(double) * nacc, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    stage_collect(c);
     return 0;
 }
 

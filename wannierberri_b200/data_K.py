@@ -44,6 +44,13 @@ class Data_K_R:
         self._plan([s.formula for s in specs], external_terms)
         return self.engine.scan(self.dK[None, :], np.ones(1), specs)
 
+    def kubo_scan(self, spec, Efermi, omega):
+        from . import _lib
+        if self.force_internal_terms_only:
+            spec.external_terms = 0
+        self._plan([_lib.KUBO], bool(spec.external_terms))
+        return self.engine.kubo_scan(self.dK[None, :], np.ones(1), spec, Efermi, omega)
+
     @property
     def kpoints_all(self):
         self._plan([])

@@ -86,6 +86,20 @@ class Engine:
                                             C.c_void_p(weight_dev.data_ptr()), arr, len(specs),
                                             C.c_void_p(out_dev.data_ptr())))
 
+    def kubo_scan(self, dK, weight, spec, Efermi, omega):
+        """One (Efermi x omega) scan over a list of K-blocks: `[nEF, nomega, 3, 3]` complex (optical conductivity)
+        or `[nEF, nomega]` float (JDOS)."""
+        dK = as_f64(dK).reshape(-1, 3)
+        weight = as_f64(weight).reshape(-1)
+        Efermi, omega = as_f64(Efermi), as_f64(omega)
+        assert weight.shape[0] == dK.shape[0] and len(Efermi) == spec.nEF and len(omega) == spec.nomega
+        out = np.zeros(int(self._L.wbgpu_kubo_size(C.byref(spec))))
+        check(self._L.wbgpu_kubo_scan(self._ctx, dK.shape[0], dptr(dK), dptr(weight), C.byref(spec), dptr(Efermi),
+                                      dptr(omega), dptr(out)))
+        if int(spec.kind) == _lib.KUBO_OPTCOND:
+            return out.view(np.complex128).reshape(spec.shape)
+        return out.reshape(spec.shape)
+
     # ------------------------------------------------------------------ parity probes
     def kpoints(self, dK):
         dK = as_f64(dK)

@@ -9,3 +9,4 @@ factor_morb_evA2_to_muB = -(elementary_charge * angstrom ** 2) * elementary_char
 factor_gme_orb = factor_morb_evA2_to_muB * bohr_magneton / angstrom ** 2
 factor_gme_spin = -bohr_magneton / angstrom ** 2
 factor_ahc = -(elementary_charge ** 2 / hbar / angstrom)
+factor_opt = -factor_ahc

@@ -4,7 +4,9 @@ ranks of `torch.distributed` (one process per GPU), evaluate each shard with ONE
 libwbgpu.so, combine with ONE all-reduce of the Fermi-scan arrays."""
 import numpy as np
 
-from .calculators.static import adapt
+from .calculators.static import adapt as adapt_static
+from .calculators import dynamic as _dyn
+from . import _lib
 from .data_K import engine_for
 from .result import ResultDict
 from .system import as_system
@@ -54,12 +56,13 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
     if parameters_K:
         raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
     system = as_system(system)
-    calcs = {}
+    calcs, dyn_calcs = {}, {}
     for key, c in calculators.items():
-        c = adapt(c)
+        dynamic = isinstance(c, _dyn.DynamicCalculator) or type(c).__name__ in _dyn._BY_NAME
+        c = _dyn.adapt(c) if dynamic else adapt_static(c)
         if not c.allow_grid:
             raise ValueError(f"Calculator {key} is not compatible with a grid")
-        calcs[key] = c
+        (dyn_calcs if dynamic else calcs)[key] = c
 
     dist = _dist() if parallel else None
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
@@ -77,10 +80,23 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
                 s.external_terms = 0
             specs.append(s)
             owner.append(key)
-    external = any(s.external_terms for s in specs)
+    internal_only = getattr(system, "force_internal_terms_only", False)
+    kspecs = {}
+    for key, c in dyn_calcs.items():
+        ks = c.spec()
+        if internal_only:
+            ks.external_terms = 0
+        kspecs[key] = ks
+    external = any(s.external_terms for s in specs) or any(ks.external_terms for ks in kspecs.values())
+    formulae = {int(s.formula) for s in specs} | ({_lib.KUBO} if kspecs else set()) | {_lib.IDENTITY}
     engine = engine_for(system, device)
-    engine.plan(np.array(grid.FFT, dtype=int), {int(s.formula) for s in specs}, external_terms=external)
-    arrays = engine.scan(shifts[lo:hi], factors[lo:hi], specs)
+    engine.plan(np.array(grid.FFT, dtype=int), formulae, external_terms=external)
+    arrays = engine.scan(shifts[lo:hi], factors[lo:hi], specs) if specs else []
+    # Kubo scans: one call each (their accumulators are large; they do not share the event pass of the static scans)
+    karrays = [engine.kubo_scan(shifts[lo:hi], factors[lo:hi], ks, dyn_calcs[key].Efermi, dyn_calcs[key].omega)
+               for key, ks in kspecs.items()]
+    nstatic = len(arrays)
+    arrays = arrays + [np.ascontiguousarray(a).view(np.float64) for a in karrays]
 
     if dist and world > 1:
         import torch
@@ -96,8 +112,10 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
 
     results = {}
     for key, c in calcs.items():
-        mine = [a for a, o in zip(arrays, owner) if o == key]
+        mine = [a for a, o in zip(arrays[:nstatic], owner) if o == key]
         results[key] = c.result(mine, system.cell_volume)
+    for (key, c), a, raw in zip(dyn_calcs.items(), arrays[nstatic:], karrays):
+        results[key] = c.result(a.view(raw.dtype).reshape(raw.shape))
     res = ResultDict(results)
     if write_files and rank == 0:
         res.savedata(prefix=fout_name, suffix=suffix, i_iter=0)
