@@ -4,18 +4,20 @@
 //   restot[omega, Ef, ab] += sum_pairs factor_omega[omega, pair] * factor_Efermi[pair, Ef] * matrix_elements[pair, ab]
 // over all ordered pairs of degenerate band groups.  At kBT = 0 the Fermi factor f(E2) - f(E1) of a pair with
 // group energies lo < hi is -1 (+1 for the reversed pair) exactly on the Fermi levels lo <= Ef < hi and zero
-// elsewhere, so a pair touches an INTERVAL [s, e) of the (sorted) Efermi array.  Here:
+// elsewhere: with s_g = first index of the (ascending) Efermi array with Ef >= E_g, the pair {i < j} contributes
+//   X_ij(omega, ab) = -W1 M_ij[ab] + W2 M_ij[ba]      on the bins  s_i <= bin < s_j .
+// In difference form along Efermi that is  +X_ij at bin s_i  and  -X_ij at bin s_j, i.e. per GROUP t one value
+//   Y_t = sum_{u > t, s_u > s_t} X_tu - sum_{u < t, s_u < s_t} X_ut      added at bin s_t,
+// which is accumulated in REGISTERS over the partners u and costs one global reduction per (group, omega, ab).
 //   wb_kubo_entries_kernel     (CTA per k-point) band groups (data_K.py:172-186 with the window -inf..inf), the
-//                              unordered pairs with a non-empty interval, their matrix elements
+//                              oriented visits (t, u) in owner order, their matrix elements
 //                              M[ab] = i sum_{m in lo-group, n in hi-group} A_mn,a A_nm,b with the generalised Berry
 //                              connection A = Abar + i D_H (data_K.py:328-334; Formula_OptCond, dynamic.py:170-181)
-//                              from the rotated matrices of wb_rotate_gemm.cuh -> a compact entry list per k-point;
-//   wb_kubo_accumulate_kernel  CTA = (tile of omega, tile of Ef, slice of k-points): the accumulator
-//                              D[omega][Ef][ab] lives in SHARED memory; every entry adds X = -W1 M[ab] + W2 M[ba] at
-//                              bin s and subtracts it at bin e (difference form); one thread owns one (omega, ab,
-//                              re|im) column, so there are no atomics in the loop; a running sum over Ef at the end
-//                              turns the differences into values, which are added to the global array;
-//   wb_kubo_finalize_kernel    scale and transpose to the reference's layout [Ef][omega][3][3].
+//                              from the rotated matrices of wb_rotate_gemm.cuh, sign and K-block weight folded in;
+//   wb_kubo_accumulate_kernel  CTA = (tile of omega, slice of k-points); thread = (omega, ab, re|im).  Entries are
+//                              staged in shared memory in chunks, the frequency factors W of (entry, omega) are
+//                              computed once per chunk and shared by the 18 components;
+//   wb_kubo_finalize_kernel    running sum over Efermi, scale, transpose to the reference's [Ef][omega][3][3].
 // The reference's dense contraction costs n_omega * n_pair * n_Ef * 9 multiply-adds per k-point; this form
 // n_omega * n_pair * 9 * 2.
 #pragma once
@@ -23,8 +25,9 @@
 #include "wb_groups.cuh"
 #include "wb_rotate_formula.cuh"
 
-constexpr int WB_KUBO_ENT = 20;    // doubles per entry: Delta | (s, e) | M[9] complex
-constexpr int WB_KUBO_CHUNK = 16;  // entries staged per step of the accumulation kernel
+constexpr int WB_KUBO_ENT = 20;    // doubles per entry: Delta | owner bin | M[9] complex (signed, weighted)
+constexpr int WB_KUBO_CHUNK = 32;  // entries staged per step of the accumulation kernel
+constexpr int WB_KUBO_WT = 32;     // omega values per CTA of the accumulation kernel
 
 struct WbKuboParams {
     int kind;        // 0 = optical conductivity, 1 = JDOS
@@ -47,7 +50,7 @@ __device__ __forceinline__ int wb_lower_bound(const double* __restrict__ Ef, int
 }
 
 __host__ inline size_t wb_kubo_entries_smem_bytes(int nw) {
-    int cap = nw * (nw - 1) / 2;
+    int cap = nw * (nw - 1);
     return sizeof(double) * (3 * (size_t)nw) + sizeof(int) * ((size_t)nw + 4) + sizeof(short) * (4 * (size_t)nw) +
            sizeof(ushort2) * (size_t)(cap + 1) + 64;
 }
@@ -86,19 +89,20 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
         const int ng = misc[0];
         for (int g = threadIdx.x; g < ng; g += NT) gidx[g] = wb_lower_bound(Ef, P.nEF, gE[g]);
         __syncthreads();
-        // ---- pairs lo-group i < hi-group j with a non-empty Fermi interval, compacted in (i, j) order by one warp
+        // ---- oriented visits (owner group t, partner u) with a non-empty Fermi interval, compacted in (t, u) order
+        //      by one warp; owners whose bin lies beyond the last Fermi level never contribute
         if (threadIdx.x < 32) {
             int slot = 0;
-            for (int i = 0; i < ng; i++) {
-                const int si = gidx[i];
-                const double lo = gE[i];
-                for (int j0 = i + 1; j0 < ng; j0 += 32) {
-                    const int j = j0 + lane;
+            for (int t = 0; t < ng; t++) {
+                const int st = gidx[t];
+                if (st >= P.nEF) break;   // s is monotone in the group index
+                for (int u0 = 0; u0 < ng; u0 += 32) {
+                    const int u = u0 + lane;
                     bool valid = false;
-                    if (j < ng) {
-                        valid = si < gidx[j];
+                    if (u < ng && u != t) {
+                        valid = (u > t) ? (st < gidx[u]) : (gidx[u] < st);
                         if (valid && P.kind == 1) {
-                            const double hi = gE[j];
+                            const double lo = gE[min(t, u)], hi = gE[max(t, u)];
                             const double d = hi - lo, dm = lo - hi;
                             const bool nz1 = (hi < P.EFmax) && (lo > P.EFmin) && (P.wlo < d) && (d < P.whi);
                             const bool nz2 = (lo < P.EFmax) && (hi > P.EFmin) && (P.wlo < dm) && (dm < P.whi);
@@ -108,7 +112,7 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
                     const unsigned mask = __ballot_sync(0xffffffffu, valid);
                     if (valid) {
                         const int pos = slot + __popc(mask & ((1u << lane) - 1u));
-                        if (pos < cap) plist[pos] = make_ushort2((unsigned short)i, (unsigned short)j);
+                        if (pos < cap) plist[pos] = make_ushort2((unsigned short)t, (unsigned short)u);
                     }
                     slot += __popc(mask);
                 }
@@ -126,18 +130,19 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
         for (int x = threadIdx.x; x < nvalid * per; x += NT) {
             const int slot = x / per, ab = x - slot * per;
             const ushort2 pr = plist[slot];
-            const int i = pr.x, j = pr.y;
+            const int i = min(pr.x, pr.y), j = max(pr.x, pr.y);   // lo, hi group
+            const double sw = (pr.y > pr.x) ? wgt : -wgt;         // +X at the bin of the lower group, -X at the upper
             double* e = ent + (size_t)slot * WB_KUBO_ENT;
             if (ab == 0) {
                 e[0] = gE[j] - gE[i];
-                e[1] = __longlong_as_double(((long long)gidx[j] << 32) | (unsigned)gidx[i]);
+                e[1] = (double)gidx[pr.x];
             }
             if (P.kind == 1) {
                 const double lo = gE[i], hi = gE[j];
                 const double d = hi - lo, dm = lo - hi;
                 const bool nz1 = (hi < P.EFmax) && (lo > P.EFmin) && (P.wlo < d) && (d < P.whi);
                 const bool nz2 = (lo < P.EFmax) && (hi > P.EFmin) && (P.wlo < dm) && (dm < P.whi);
-                e[2] = wgt * (double)((ge[i] - gs[i]) * (ge[j] - gs[j]));
+                e[2] = sw * (double)((ge[i] - gs[i]) * (ge[j] - gs[j]));
                 e[3] = (double)((nz1 ? 1 : 0) | (nz2 ? 2 : 0));
             } else {
                 const int a = ab / 3, b = ab - 3 * a;
@@ -155,8 +160,8 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
                         }
                         cfma(acc, Amn, Anm);
                     }
-                e[2 + 2 * ab] = -wgt * acc.y;   // i * acc
-                e[3 + 2 * ab] = wgt * acc.x;
+                e[2 + 2 * ab] = -sw * acc.y;   // i * acc
+                e[3 + 2 * ab] = sw * acc.x;
             }
         }
     }
@@ -177,95 +182,81 @@ __device__ __forceinline__ double wb_kubo_smear(double x, double eta, int smr_ty
     return 0.;
 }
 
-__host__ inline size_t wb_kubo_acc_smem_bytes(int kind, int wt, int eft) {
-    const int NC = kind == 0 ? 18 : 1;
-    return sizeof(double) * ((size_t)wt * eft * NC + WB_KUBO_CHUNK * WB_KUBO_ENT + (size_t)WB_KUBO_CHUNK * wt * 4);
-}
-
 template <int KIND>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__((KIND == 0 ? 18 : 1) * WB_KUBO_WT)
 wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restrict__ count, int cap, long nk,
-                          WbKuboParams P, const double* __restrict__ omega, int wt, int eft, double* __restrict__ Dglob) {
-    constexpr int NC = KIND == 0 ? 18 : 1;
-    extern __shared__ __align__(16) double smem_a[];
-    double* D = smem_a;                                   // [wt][eft][NC]
-    double* ent = D + (size_t)wt * eft * NC;              // [CHUNK][ENT]
-    double* Wb = ent + WB_KUBO_CHUNK * WB_KUBO_ENT;       // [CHUNK][wt][4]
-    const int w0 = blockIdx.x * wt, nwt = min(wt, P.nomega - w0);
-    const int t0 = blockIdx.y * eft, t1 = min(P.nEF, t0 + eft);
-    const int tid = threadIdx.x, NT = blockDim.x;
-    for (int x = tid; x < wt * eft * NC; x += NT) D[x] = 0.;
+                          WbKuboParams P, const double* __restrict__ omega, double* __restrict__ Dglob) {
+    constexpr int NC = KIND == 0 ? 18 : 1, WT = WB_KUBO_WT, NT = NC * WT;
+    __shared__ __align__(16) double ent[WB_KUBO_CHUNK * WB_KUBO_ENT];
+    __shared__ __align__(16) double Wb[WB_KUBO_CHUNK * WT * 4];
+    const int w0 = blockIdx.x * WT, nwt = min(WT, P.nomega - w0);
+    const int tid = threadIdx.x;
     const int iw = tid / NC, c = tid - iw * NC;
-    const bool owner = tid < nwt * NC;
+    const bool owner = iw < nwt;
     const int ab = c >> 1, ri = c & 1, ba = (ab % 3) * 3 + ab / 3;
-    for (long ik = blockIdx.z; ik < nk; ik += gridDim.z) {
+    double* const col = Dglob + ((size_t)(w0 + iw) * P.nEF) * NC + c;
+    for (long ik = blockIdx.y; ik < nk; ik += gridDim.y) {
         const int cnt = count[ik];
         const double* src = entries + (size_t)ik * cap * WB_KUBO_ENT;
+        double Y = 0.;
+        int curbin = -1;
         for (int p0 = 0; p0 < cnt; p0 += WB_KUBO_CHUNK) {
             const int np = min(WB_KUBO_CHUNK, cnt - p0);
             __syncthreads();
             for (int x = tid; x < np * WB_KUBO_ENT; x += NT) ent[x] = src[(size_t)p0 * WB_KUBO_ENT + x];
             __syncthreads();
-            // ---- phase A: frequency factors of (entry, omega)
+            // ---- phase A: frequency factors of (entry, omega), shared by the components
             for (int x = tid; x < np * nwt; x += NT) {
                 const int p = x / nwt, w = x - p * nwt;
                 const double dl = ent[p * WB_KUBO_ENT], om = omega[w0 + w];
-                double* o = Wb + ((size_t)p * wt + w) * 4;
+                double* o = Wb + (p * WT + w) * 4;
                 if (KIND == 0) {
                     const cplx c1 = wb_kubo_cfac(dl - om, P.eta, P.smr_type);
                     const cplx c2 = wb_kubo_cfac(-dl - om, P.eta, P.smr_type);
-                    o[0] = dl * c1.x; o[1] = dl * c1.y;      // pair (lo, hi): (E2 - E1) = +Delta
-                    o[2] = -dl * c2.x; o[3] = -dl * c2.y;    // pair (hi, lo)
+                    o[0] = dl * c1.x; o[1] = dl * c1.y;      // pair (lo, hi): (E2 - E1) = +Delta, Fermi factor -1
+                    o[2] = -dl * c2.x; o[3] = -dl * c2.y;    // pair (hi, lo): Fermi factor +1
                 } else {
                     const int fl = (int)ent[p * WB_KUBO_ENT + 3];
-                    o[0] = (fl & 1) ? wb_kubo_smear(dl - om, P.eta, P.smr_type) : 0.;    // E1 - E2 = +Delta
-                    o[1] = (fl & 2) ? wb_kubo_smear(-dl - om, P.eta, P.smr_type) : 0.;
+                    o[0] = (fl & 1) ? wb_kubo_smear(dl - om, P.eta, P.smr_type) : 0.;    // (hi, lo): E1 - E2 = +Delta
+                    o[1] = (fl & 2) ? wb_kubo_smear(-dl - om, P.eta, P.smr_type) : 0.;   // (lo, hi)
                 }
             }
             __syncthreads();
-            // ---- phase B: thread = (omega, component): difference-form update of its own column
+            // ---- phase B: thread = (omega, component): register accumulation per owner bin
             if (owner) {
-                double* col = D + (size_t)iw * eft * NC + c;
                 for (int p = 0; p < np; p++) {
                     const double* e = ent + p * WB_KUBO_ENT;
-                    const long long se = __double_as_longlong(e[1]);
-                    const int s = max((int)(se & 0xffffffffll), t0), en = min((int)(se >> 32), t1);
-                    if (s >= en) continue;
-                    const double* W = Wb + ((size_t)p * wt + iw) * 4;
-                    double X;
-                    if (KIND == 0) {
-                        // pair (lo, hi): Fermi factor -1, M[ab];  pair (hi, lo): +1, M[ba]
-                        const double Mr = e[2 + 2 * ab], Mi = e[3 + 2 * ab], Nr = e[2 + 2 * ba], Ni = e[3 + 2 * ba];
-                        if (ri == 0) X = -(W[0] * Mr - W[1] * Mi) + (W[2] * Nr - W[3] * Ni);
-                        else X = -(W[0] * Mi + W[1] * Mr) + (W[2] * Ni + W[3] * Nr);
-                    } else {
-                        X = (W[0] - W[1]) * e[2];   // (hi, lo): +1;  (lo, hi): -1
+                    const int bin = (int)e[1];
+                    if (bin != curbin) {   // uniform
+                        if (curbin >= 0 && Y != 0.) atomicAdd(col + (size_t)curbin * NC, Y);
+                        curbin = bin;
+                        Y = 0.;
                     }
-                    col[(size_t)(s - t0) * NC] += X;
-                    if (en < t1) col[(size_t)(en - t0) * NC] -= X;
+                    const double* W = Wb + (p * WT + iw) * 4;
+                    if (KIND == 0) {
+                        const double Mr = e[2 + 2 * ab], Mi = e[3 + 2 * ab], Nr = e[2 + 2 * ba], Ni = e[3 + 2 * ba];
+                        if (ri == 0) Y += -(W[0] * Mr - W[1] * Mi) + (W[2] * Nr - W[3] * Ni);
+                        else Y += -(W[0] * Mi + W[1] * Mr) + (W[2] * Ni + W[3] * Nr);
+                    } else {
+                        Y += (W[0] - W[1]) * e[2];
+                    }
                 }
             }
         }
-    }
-    __syncthreads();
-    if (owner) {
-        const double* col = D + (size_t)iw * eft * NC + c;
-        double run = 0.;
-        for (int b = 0; b < t1 - t0; b++) {
-            run += col[(size_t)b * NC];
-            if (run != 0.) atomicAdd(Dglob + ((size_t)(w0 + iw) * P.nEF + t0 + b) * NC + c, run);
-        }
+        if (owner && curbin >= 0 && Y != 0.) atomicAdd(col + (size_t)curbin * NC, Y);
     }
 }
 
-// out[iEf][iw][NC] = scale * D[iw][iEf][NC]
+// D holds differences along Efermi: out[iEf][iw][NC] = scale * sum_{f <= iEf} D[iw][f][NC]
 __global__ void wb_kubo_finalize_kernel(const double* __restrict__ D, int nomega, int nEF, int NC, double scale,
                                         double* __restrict__ out) {
-    const long total = (long)nomega * nEF * NC;
+    const long total = (long)nomega * NC;
     for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(x % NC);
-        const long r = x / NC;
-        const int w = (int)(r % nomega), f = (int)(r / nomega);
-        out[x] = scale * D[((size_t)w * nEF + f) * NC + c];
+        const int c = (int)(x % NC), w = (int)(x / NC);
+        double run = 0.;
+        for (int f = 0; f < nEF; f++) {
+            run += D[((size_t)w * nEF + f) * NC + c];
+            out[((size_t)f * nomega + w) * NC + c] = scale * run;
+        }
     }
 }

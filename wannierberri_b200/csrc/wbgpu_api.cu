@@ -1025,16 +1025,8 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     if (ensure(&c->d_kacc, &c->kacc_cap, sizeof(double) * 2 * nacc)) return 1;
     CK(cudaMemsetAsync(c->d_kacc, 0, sizeof(double) * nacc, c->stream));
 
-    // tiles of the accumulation kernel: D tile [wt][eft][NC] in <= 160 KB of shared memory
-    const size_t budget = 160 * 1024;
-    int eft = nEF, wt = (int)(budget / (sizeof(double) * (size_t)nEF * NC));
-    if (wt < 1) { wt = 1; eft = (int)(budget / (sizeof(double) * NC)); }
-    wt = std::min(wt, std::min(nom, optcond ? 14 : 256));
-    const int nthreads = std::max(64, (wt * NC + 31) / 32 * 32);
-    const int nwtile = (nom + wt - 1) / wt, neftile = (nEF + eft - 1) / eft;
-    const size_t smem_acc = wb_kubo_acc_smem_bytes(spec->kind, wt, eft);
-    if (optcond) CK(cudaFuncSetAttribute(wb_kubo_accumulate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc));
-    else CK(cudaFuncSetAttribute(wb_kubo_accumulate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc));
+    const int nwtile = (nom + WB_KUBO_WT - 1) / WB_KUBO_WT;
+    const int nthreads = NC * WB_KUBO_WT;
 
     WbChanList ch;
     ch.n = 0;
@@ -1043,7 +1035,7 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
         if (spec->external_terms)
             for (int a = 0; a < 3; a++) { ch.off[ch.n] = L.off_A[a]; ch.herm[ch.n] = 1; ch.n++; }
     }
-    const int cap = std::max(1, nw * (nw - 1) / 2);
+    const int cap = std::max(1, nw * (nw - 1));
     const size_t smem_ent = wb_kubo_entries_smem_bytes(nw);
     if (smem_ent > 48 * 1024)
         CK(cudaFuncSetAttribute(wb_kubo_entries_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ent));
@@ -1072,19 +1064,19 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
             stage_begin(c, WBGPU_STAGE_SCAN);
             wb_kubo_entries_kernel<128><<<(unsigned)std::min(n, (long)sms * 8), 128, smem_ent, c->stream>>>(
                 (const cplx*)c->d_xbar, ch.n, nw, n, k0, c->d_E + k0 * nw, win, P, d_Ef, d_w + b0, c->nk_block, c->d_kent, d_count, cap);
-            const int nsplit = (int)std::max(1L, std::min(n, (long)((2 * sms + nwtile * neftile - 1) / (nwtile * neftile))));
-            dim3 grid((unsigned)nwtile, (unsigned)neftile, (unsigned)nsplit);
+            const int nsplit = (int)std::max(1L, std::min(n, (long)((6 * sms + nwtile - 1) / nwtile)));
+            dim3 grid((unsigned)nwtile, (unsigned)nsplit);
             if (optcond)
-                wb_kubo_accumulate_kernel<0><<<grid, nthreads, smem_acc, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, wt, eft, c->d_kacc);
+                wb_kubo_accumulate_kernel<0><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
             else
-                wb_kubo_accumulate_kernel<1><<<grid, nthreads, smem_acc, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, wt, eft, c->d_kacc);
+                wb_kubo_accumulate_kernel<1><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
             c->launches += 2;
             stage_end(c);
             CK(cudaGetLastError());
         }
     }
     const double scale = spec->factor / (c->cell_volume * (double)c->nk_block);
-    wb_kubo_finalize_kernel<<<(unsigned)std::min<size_t>((nacc + 255) / 256, 1184), 256, 0, c->stream>>>(c->d_kacc, nom, nEF, NC, scale,
+    wb_kubo_finalize_kernel<<<(unsigned)(((size_t)nom * NC + 127) / 128), 128, 0, c->stream>>>(c->d_kacc, nom, nEF, NC, scale,
                                                                                                     c->d_kacc + nacc);
     c->launches++;
     CK(cudaGetLastError());
