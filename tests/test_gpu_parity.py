@@ -217,6 +217,27 @@ def test_omega_band_traces(wb, fe, fe_orc, orc, kw, rotate_method):
     assert worst < RTOL * scale
 
 
+@pytest.mark.parametrize("rotate_method", [0, 1, 2, 4])
+def test_dh_full_channel_path(wb, fe, rotate_method):
+    """d_a H is hermitian in R-space for the Fe system, so the plan packs it as triangles; the full-matrix path
+    (what a system without that symmetry gets, option dh_packed = 0) must give the same AHC / Morb."""
+    b = np.load(os.path.join(GOLDEN, "golden_fe_block.npz"))
+    st = wb.calculators.static
+    specs = st.AHC(Efermi=b["Efermi"]).specs() + (st.Morb(Efermi=b["Efermi"]).specs() if rotate_method != 2 else [])
+    out = []
+    for packed in (1, 0):
+        eng = wb.Engine(fe)
+        eng.set_option("dh_packed", packed)
+        eng.set_option("rotate_method", rotate_method)
+        eng.plan(b["NKFFT"], [s.formula for s in specs])
+        out.append(eng.scan(b["dK"][None, :], np.ones(1), specs))
+        V = eng.xk(b["dK"], "dHam")
+        assert np.abs(V - V.conj().transpose(0, 2, 1, 3)).max() < 1e-12 * np.abs(V).max()
+        eng.close()
+    for a, r in zip(*out):
+        assert relerr(a, r) < 1e-11
+
+
 BLOCK_CASES = dict(
     ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}),
     ahc_kramers=("AHC", dict(degen_Kramers=True)), ahc_thresh=("AHC", dict(degen_thresh=0.05)),

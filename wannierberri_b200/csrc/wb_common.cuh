@@ -50,7 +50,8 @@ struct WbLayout {
     int ntri;        // nw(nw+1)/2
     int E;           // record length (complex elements)
     int off_H;       // hermitian
-    int off_dH[3];   // full
+    int dH_herm;     // d_a H is hermitian in R-space (checked at plan time): its channels are packed like H
+    int off_dH[3];   // full, or upper triangle if dH_herm
     int off_A[3];    // hermitian
     int off_O[3];    // hermitian  (curl A)
     int off_B[3];    // full

@@ -318,7 +318,7 @@ wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, cons
                 __syncthreads();
             }
         };
-        if (need.V) rotate_full(L.off_dH, false, Vb);
+        if (need.V) rotate_full(L.off_dH, L.dH_herm, Vb);
         if (need.A) rotate_full(L.off_A, true, Ab);
         if (need.B) rotate_full(L.off_B, false, Bb);
         if (need.Oblk) rotate_full(L.off_O, true, Ob);

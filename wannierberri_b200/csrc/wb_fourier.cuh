@@ -62,8 +62,11 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
         cplx h = in.Ham[idx];
         add_herm(table, cellR, cellmR, E, L.off_H, i, j, nw, h);
         if (L.off_dH[0] >= 0) {
-            for (int a = 0; a < 3; a++)  // i * T_a * H   (rvectors.py:487-494)
-                atomic_cadd(&table[cellR * E + L.off_dH[a] + i * nw + j], cmake(-T[a] * h.y, T[a] * h.x));
+            for (int a = 0; a < 3; a++) {  // i * T_a * H   (rvectors.py:487-494)
+                const cplx d = cmake(-T[a] * h.y, T[a] * h.x);
+                if (L.dH_herm) add_herm(table, cellR, cellmR, E, L.off_dH[a], i, j, nw, d);
+                else atomic_cadd(&table[cellR * E + L.off_dH[a] + i * nw + j], d);
+            }
         }
     }
     if (in.AA && L.off_A[0] >= 0) {
@@ -86,6 +89,45 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
         for (int a = 0; a < 3; a++) atomic_cadd(&table[cellR * E + L.off_C[a] + i * nw + j], in.CC[idx * 3 + a]);
     if (in.SS && L.off_S[0] >= 0)
         for (int a = 0; a < 3; a++) add_herm(table, cellR, cellmR, E, L.off_S[a], i, j, nw, in.SS[idx * 3 + a]);
+}
+
+// Is  d_a H_R = i (R + t_j - t_i)_a H_R  hermitian, i.e. dH(R; i, j) == conj(dH(-R; j, i))?  The reference does not
+// hermitise this channel (data_K_R.py:84-87), so it may only be packed as a triangle when the input has the
+// symmetry.  cellmap[cell] = index of the R-vector in that cell of the bounding box (-1: none, -2: duplicated).
+// out[0] = max |asymmetry|, out[1] = max |dH|  (as bit patterns of non-negative doubles -> atomicMax).
+__global__ void wb_dH_herm_check_kernel(const cplx* __restrict__ Ham, const double* __restrict__ T, const int* __restrict__ iRvec,
+                                        const int* __restrict__ cellmap, int nR, int nw, int3 rmin, int3 nbox,
+                                        unsigned long long* out) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)nR * nw * nw;
+    if (idx >= total) return;
+    int j = idx % nw;
+    int i = (idx / nw) % nw;
+    int iR = idx / ((long)nw * nw);
+    int R0 = iRvec[3 * iR], R1 = iRvec[3 * iR + 1], R2 = iRvec[3 * iR + 2];
+    long cellR = ((long)(R0 - rmin.x) * nbox.y + (R1 - rmin.y)) * nbox.z + (R2 - rmin.z);
+    long cellmR = ((long)(-R0 - rmin.x) * nbox.y + (-R1 - rmin.y)) * nbox.z + (-R2 - rmin.z);
+    const int jR = cellmap[cellmR];
+    const bool dup = (cellmap[cellR] == -2) || (jR == -2);
+    const cplx h = Ham[idx];
+    double asym = 0., mag = 0.;
+    for (int a = 0; a < 3; a++) {
+        const double t = T[idx * 3 + a];
+        const cplx d = cmake(-t * h.y, t * h.x);
+        cplx dm = cmake(0., 0.);
+        if (jR >= 0) {
+            const long idm = ((long)jR * nw + j) * nw + i;
+            const cplx hm = Ham[idm];
+            const double tm = T[idm * 3 + a];
+            dm = cmake(-tm * hm.y, tm * hm.x);
+        }
+        // d == conj(dm) ?
+        asym = fmax(asym, fmax(fabs(d.x - dm.x), fabs(d.y + dm.y)));
+        mag = fmax(mag, fmax(fabs(d.x), fabs(d.y)));
+    }
+    if (dup) asym = CUDART_INF;
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(asym));
+    atomicMax(&out[1], (unsigned long long)__double_as_longlong(mag));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -97,7 +97,8 @@ wb_omega_events_dmma_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, c
     const int signmask = ((g ^ q) & 1) ? (int)0x80000000 : 0;
     const int ntile3 = (3 * nw + 7) / 8;   // tiles over the stacked 3*nw dimension
     const int nitem = fl.external_terms ? 3 : 1;
-    const uint32_t item_bytes[3] = {(uint32_t)(3 * n2 * 16), (uint32_t)(3 * L.ntri * 16), (uint32_t)(3 * L.ntri * 16)};
+    const uint32_t item_bytes[3] = {(uint32_t)(3 * (L.dH_herm ? L.ntri : n2) * 16), (uint32_t)(3 * L.ntri * 16),
+                                    (uint32_t)(3 * L.ntri * 16)};
     const int item_off[3] = {L.off_dH[0], L.off_A[0], L.off_O[0]};
 
     // zero the padding that enters the K (inner) dimension once; X/Y loads never touch it
@@ -170,7 +171,7 @@ wb_omega_events_dmma_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, c
             }
 
         for (int trip = 0; trip < nitem; trip++, gi++) {
-            const bool herm = trip > 0;
+            const bool herm = trip > 0 || L.dH_herm;
             const int b = (int)(gi & 1);
             const cplx* src = (const cplx*)(stg + (size_t)b * D.stage);
             wb_mbar_wait(&bars[b], (uint32_t)((gi >> 1) & 1));

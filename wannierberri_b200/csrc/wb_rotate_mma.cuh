@@ -102,7 +102,7 @@ inline bool wb_mma_make_plan(const WbLayout& L, int mask, int external, WbMmaPla
         P->slot[n] = s;
         n++;
     };
-    add(L.off_dH[0], false, slot); slot += 3;
+    add(L.off_dH[0], L.dH_herm, slot); slot += 3;
     if (external) {
         add(L.off_A[0], true, slot); slot += 3;
         if (morb) { add(L.off_B[0], false, slot); slot += 3; }

@@ -104,6 +104,8 @@ struct wbgpu_ctx {
     int rotate_method = 0;  // 0 = automatic, 1 = generic shared-memory DFMA kernel, 2 = DMMA kernel (Omega, nw <= 20),
                             // 3 = compile-time-NW DMMA kernel, 4 = batched DMMA GEMM to global memory + formula kernel
     int smem_optin = 0;
+    int dh_packed = 1;      // 1 = pack d_a H as a triangle when it is hermitian in R-space, 0 = never
+    std::vector<int> h_iRvec;
     // optional per-stage device timing (option "timing"): events around each stage of each batch
     int timing = 0;
     std::vector<cudaEvent_t> ev_pool;
@@ -195,6 +197,7 @@ extern "C" int wbgpu_create(wbgpu_ctx** out, int device, int nw, int nR, const i
     CK(cudaMalloc(&c->d_T, sizeof(double) * 3 * (size_t)nR * nw * nw));
     CK(cudaMemcpy(c->d_iRvec, iRvec, sizeof(int) * 3 * nR, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_T, cRvec_shifted, sizeof(double) * 3 * (size_t)nR * nw * nw, cudaMemcpyHostToDevice));
+    c->h_iRvec.assign(iRvec, iRvec + 3 * (size_t)nR);
     CK(cudaMalloc(&c->d_sweeps, sizeof(int)));
     CK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     *out = c;
@@ -232,6 +235,7 @@ extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "eig_method")) { c->eig_method = (int)value; return 0; }
     if (!strcmp(name, "rotate_method")) { c->rotate_method = (int)value; return 0; }
     if (!strcmp(name, "fourier_method")) { c->fourier_method = (int)value; return 0; }
+    if (!strcmp(name, "dh_packed")) { c->dh_packed = (int)value; c->planned = false; return 0; }
     if (!strcmp(name, "timing")) {
         c->timing = (int)value;
         for (int i = 0; i < WBGPU_NSTAGES; i++) { c->stage_ms[i] = 0; c->stage_calls[i] = 0; }
@@ -298,13 +302,42 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     if (need_BC && (!c->d_XR[WBGPU_BB] || !c->d_XR[WBGPU_CC])) return set_err("wbgpu_plan: R-matrices 'BB','CC' are not set");
     if (need_S && !c->d_XR[WBGPU_SS]) return set_err("wbgpu_plan: R-matrix 'SS' is not set");
 
+    // ---- is d_a H hermitian in R-space?  (then its three channels are transformed and stored as triangles)
+    int dH_herm = 0;
+    if (need_dH && c->dh_packed) {
+        const size_t ncell0 = (size_t)c->nbox.x * c->nbox.y * c->nbox.z;
+        std::vector<int> cellmap(ncell0, -1);
+        for (int iR = 0; iR < c->nR; iR++) {
+            const int* R = &c->h_iRvec[3 * (size_t)iR];
+            size_t cell = ((size_t)(R[0] - c->rmin.x) * c->nbox.y + (R[1] - c->rmin.y)) * c->nbox.z + (R[2] - c->rmin.z);
+            cellmap[cell] = (cellmap[cell] == -1) ? iR : -2;
+        }
+        int* d_map = nullptr;
+        unsigned long long* d_res = nullptr;
+        CK(cudaMalloc(&d_map, sizeof(int) * ncell0));
+        CK(cudaMalloc(&d_res, 16));
+        CK(cudaMemcpyAsync(d_map, cellmap.data(), sizeof(int) * ncell0, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(d_res, 0, 16, c->stream));
+        long tot = (long)c->nR * nw * nw;
+        wb_dH_herm_check_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, c->stream>>>(c->d_XR[WBGPU_HAM], c->d_T, c->d_iRvec, d_map, c->nR,
+                                                                                   nw, c->rmin, c->nbox, d_res);
+        c->launches++;
+        double res[2] = {0, 0};
+        CK(cudaMemcpyAsync(res, d_res, 16, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(d_map);
+        cudaFree(d_res);
+        dH_herm = (res[0] <= 1e-13 * res[1]) ? 1 : 0;
+    }
+
     WbLayout L;
     L.nw = nw;
     L.ntri = nw * (nw + 1) / 2;
+    L.dH_herm = dH_herm;
     int off = 0;
     auto take = [&](bool herm) { int o = off; off += herm ? L.ntri : nw * nw; return o; };
     L.off_H = take(true);
-    for (int a = 0; a < 3; a++) L.off_dH[a] = need_dH ? take(false) : -1;
+    for (int a = 0; a < 3; a++) L.off_dH[a] = need_dH ? take(dH_herm) : -1;
     for (int a = 0; a < 3; a++) L.off_A[a] = need_A ? take(true) : -1;
     bool need_O = need_A && (has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS));
     for (int a = 0; a < 3; a++) L.off_O[a] = need_O ? take(true) : -1;
@@ -731,7 +764,7 @@ static int run_events_xbar(wbgpu_ctx* c, const EvGroup& G, long nk) {
     auto add3 = [&](const int* offs, bool herm) {
         for (int a = 0; a < 3; a++) { ch.off[ch.n] = offs[a]; ch.herm[ch.n] = herm; ch.n++; }
     };
-    if (need.V) add3(L.off_dH, false);
+    if (need.V) add3(L.off_dH, L.dH_herm);
     if (need.A) add3(L.off_A, true);
     if (need.B) add3(L.off_B, false);
     if (need.Oblk || need.Odiag) add3(L.off_O, true);
@@ -1031,7 +1064,7 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     WbChanList ch;
     ch.n = 0;
     if (optcond) {
-        for (int a = 0; a < 3; a++) { ch.off[ch.n] = L.off_dH[a]; ch.herm[ch.n] = 0; ch.n++; }
+        for (int a = 0; a < 3; a++) { ch.off[ch.n] = L.off_dH[a]; ch.herm[ch.n] = L.dH_herm; ch.n++; }
         if (spec->external_terms)
             for (int a = 0; a < 3; a++) { ch.off[ch.n] = L.off_A[a]; ch.herm[ch.n] = 1; ch.n++; }
     }
@@ -1132,7 +1165,7 @@ extern "C" int wbgpu_xk(wbgpu_ctx* c, const double dK[3], int channel, double* X
     int ncart = 3;
     switch (channel) {
         case WBGPU_CH_HAM: offs = &L.off_H; herm = true; ncart = 1; break;
-        case WBGPU_CH_DHAM: offs = L.off_dH; break;
+        case WBGPU_CH_DHAM: offs = L.off_dH; herm = L.dH_herm; break;
         case WBGPU_CH_AA: offs = L.off_A; herm = true; break;
         case WBGPU_CH_ROTAA: offs = L.off_O; herm = true; break;
         case WBGPU_CH_BB: offs = L.off_B; break;
