@@ -12,12 +12,12 @@ float run(const cplx* X, WbLayout L, WbMmaPlan P, long nk, const double* E, cons
     WbEventLayout ev{};
     ev.mask = 2; ev.NC = 3; ev.internal_terms = 1; ev.external_terms = 1;
     size_t smem = wb_mma_smem_bytes<NW>(P) + extra_smem;
-    cudaFuncSetAttribute(wb_events_mma_kernel<NW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(wb_events_mma_kernel<NW, false, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9;
     for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(e0);
-        wb_events_mma_kernel<NW, DBG><<<ctas, 128, smem>>>(X, L, P, nk, E, U, win, ev, lab, val);
+        wb_events_mma_kernel<NW, false, DBG><<<ctas, 128, smem>>>(X, L, P, nk, E, U, win, ev, lab, val);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); best = fminf(best, ms);
     }

@@ -104,6 +104,7 @@ struct wbgpu_ctx {
     int rotate_method = 0;  // 0 = automatic, 1 = generic shared-memory DFMA kernel, 2 = DMMA kernel (Omega, nw <= 20),
                             // 3 = compile-time-NW DMMA kernel, 4 = batched DMMA GEMM to global memory + formula kernel
     int smem_optin = 0;
+    int rotate_trim = 1;    // 1 = form only the needed columns of the rotated matrices when they are hermitian
     int dh_packed = 1;      // 1 = pack d_a H as a triangle when it is hermitian in R-space, 0 = never
     std::vector<int> h_iRvec;
     // optional per-stage device timing (option "timing"): events around each stage of each batch
@@ -235,6 +236,7 @@ extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "eig_method")) { c->eig_method = (int)value; return 0; }
     if (!strcmp(name, "rotate_method")) { c->rotate_method = (int)value; return 0; }
     if (!strcmp(name, "fourier_method")) { c->fourier_method = (int)value; return 0; }
+    if (!strcmp(name, "rotate_trim")) { c->rotate_trim = (int)value; return 0; }
     if (!strcmp(name, "dh_packed")) { c->dh_packed = (int)value; c->planned = false; return 0; }
     if (!strcmp(name, "timing")) {
         c->timing = (int)value;
@@ -694,16 +696,16 @@ static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec)
     return groups;
 }
 
-template <int NW>
+template <int NW, bool TRIM>
 static int launch_mma_t(wbgpu_ctx* c, const EvGroup& G, long nk, WbMmaPlan P) {
     size_t smem = wb_mma_smem_bytes<NW>(P);
     if ((int)smem > c->smem_optin) return -1;
-    CK(cudaFuncSetAttribute(wb_events_mma_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(wb_events_mma_kernel<NW, TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     long nblk = std::min(nk, (long)sms * 2);
-    wb_events_mma_kernel<NW><<<(unsigned)nblk, 128, smem, c->stream>>>(c->d_X, c->L, P, nk, c->d_E, c->d_U, G.win, G.ev,
-                                                                   c->d_evlabel, c->d_evval);
+    wb_events_mma_kernel<NW, TRIM><<<(unsigned)nblk, 128, smem, c->stream>>>(c->d_X, c->L, P, nk, c->d_E, c->d_U, G.win, G.ev,
+                                                                         c->d_evlabel, c->d_evval);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -715,7 +717,7 @@ static int launch_mma_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
 #define WB_MMA_CASE(NWC)                                                                            \
     case NWC:                                                                                       \
         if (!wb_mma_make_plan<NWC>(c->L, G.ev.mask, G.ev.external_terms, &P)) return -1;            \
-        return launch_mma_t<NWC>(c, G, nk, P);
+        return (c->L.dH_herm && c->rotate_trim) ? launch_mma_t<NWC, true>(c, G, nk, P) : launch_mma_t<NWC, false>(c, G, nk, P);
     switch (c->nw) {
         WB_MMA_CASE(18)
         default: return -1;
