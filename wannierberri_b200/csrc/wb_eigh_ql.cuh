@@ -153,7 +153,7 @@ __device__ __forceinline__ double half_sum(double v) {
 }
 
 template <int NW, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 4)
 wb_tridiag2_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, double* __restrict__ dout,
                    double* __restrict__ eout, cplx* __restrict__ tauout, cplx* __restrict__ Vout) {
     static_assert(NW > 16 && NW <= 18, "two leading rows at most are handled implicitly");
@@ -350,7 +350,7 @@ wb_tql_kernel(int nw, long nk, double* __restrict__ dio, const double* __restric
 // Per warp: ONE set of TMA bulk copies brings the Householder vectors, tau, the sweep headers and the whole
 // rotation stream of the k-point into shared memory (a single exposed latency instead of one per sweep).
 __host__ __device__ inline int wb_eigvec_smem_per_warp(int nw, int capR, int capS) {  // in 16-byte units
-    return nw * nw + (nw * (nw + 1) + 1) / 2 + nw + capR + (capS + 3) / 4 + 1;
+    return nw * nw + nw + capR + (capS + 3) / 4 + 1;   // (the transpose buffer aliases the rotation stream)
 }
 
 template <int NWP, int WARPS, bool EXACT>
@@ -360,14 +360,15 @@ wb_eigvec_kernel(int nw_rt, long k0, long nk, const double* __restrict__ dvals, 
                  const int* __restrict__ nsweep, double* __restrict__ Eout, cplx* __restrict__ VU,
                  int* __restrict__ fail_list, int* __restrict__ nfail) {
     extern __shared__ __align__(16) cplx smem_v[];
-    // per warp: V[nw][nw] (Householder vectors), Zs[nw][nw+1] doubles (transpose), tau[nw], rot[capR], hdr[capS], mbarrier
+    // per warp: V[nw][nw] (Householder vectors), tau[nw], rot[capR], hdr[capS], mbarrier; the transpose buffer
+    // Zs[nw][nw+1] doubles reuses the rotation stream, which is dead after the replay (nw(nw+1) <= 2 capR)
     const int nw = EXACT ? NWP : nw_rt;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_warp = wb_eigvec_smem_per_warp(nw, capR, capS);
     cplx* V = smem_v + (size_t)warp * per_warp;
-    double* Zs = (double*)(V + nw * nw);
-    cplx* taus = V + nw * nw + (nw * (nw + 1) + 1) / 2;
+    cplx* taus = V + nw * nw;
     const double2* rots = (const double2*)(taus + nw);
+    double* Zs = (double*)rots;
     const int* hdrs = (const int*)(rots + capR);
     uint64_t* bar = (uint64_t*)(hdrs + (capS + 3) / 4 * 4);
     long t = (long)blockIdx.x * WARPS + warp;
