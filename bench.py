@@ -290,8 +290,16 @@ def main():
         dur = stage_ms[dominant] / max(stage_calls[dominant], 1) * 1e-3
         achieved = FLOPS_PER_K[dominant] * k_per_launch / dur / 1e12
         peak64 = max(fp64.values())
-        roofline = {"kernel": dominant, "bound": "fp64", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
-                    "frac": achieved / peak64, "traffic": None,
+        traffic = None
+        try:  # dram bytes of the dominant kernel from the committed ncu --set full capture, scaled to this launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if dominant == "rotate":
+                traffic = tj["bytes_per_kpoint"] * k_per_launch
+        except (OSError, KeyError):
+            pass
+        roofline = {"kernel": dominant, "bound": "tensor", "pipe": "FP64 tensor (mma.sync.m8n8k4.f64)", "achieved": achieved,
+                    "peak": peak64, "unit": "TFLOP/s", "frac": achieved / peak64, "traffic": traffic,
+                    "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per k-point x k-points per launch)",
                     "peak_source": f"measured in this run: DFMA {fp64['dfma']:.1f}, DMMA(m8n8k4) {fp64['dmma']:.1f} TFLOP/s",
                     "algorithmic_flops_per_k": FLOPS_PER_K[dominant], "avg_launch_ms": dur * 1e3,
                     "kpoints_per_launch": k_per_launch}

@@ -150,3 +150,28 @@ def test_kubo_run_vs_upstream_golden(fe):
     res = orc.run(fe, [2, 2, 2], [2, 2, 2], dict(oc=(name, g["ref_Efermi"], dict(omega=g["ref_omega"], **kw))))
     assert relerr(res["oc"], g["upstream_golden_opt_conductivity"]) < RTOL
     assert relerr(res["oc"], g["run_ref_optcond"]) < RTOL
+
+
+# ---------------------------------------------------------------------------------------- tetrahedron method
+TETRA_CASES = dict(
+    ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}), spin=("Spin", {}),
+    ahc_thresh=("AHC", dict(degen_thresh=0.05)), bcd=("BerryDipole_FermiSurf", {}), gme_spin=("GME_spin_FermiSurf", {}),
+)
+
+
+def test_tetra_corner_energies(fe):
+    g = np.load(os.path.join(GOLDEN, "golden_fe_tetra.npz"))
+    data = orc.OracleDataK(fe, g["block_dK"], g["block_NKFFT"], NKdiv=g["block_NKdiv"])
+    assert np.array_equal(data.dK_cell, g["block_dK_cell"])
+    assert relerr(data.E_K_corners_parallel(), g["block_E_corners"]) < 1e-12
+
+
+@pytest.mark.parametrize("case", sorted(TETRA_CASES))
+def test_tetra_block_vs_reference(fe, case):
+    """StaticCalculator(tetra=True).__call__ for one K-block (fixture written by make_golden_tetra.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_tetra.npz"))
+    name, kw = TETRA_CASES[case]
+    data = orc.OracleDataK(fe, g["block_dK"], g["block_NKFFT"], NKdiv=g["block_NKdiv"])
+    got = orc.CALCULATORS[name](data, g["Efermi"], tetra=True, **kw)
+    assert got.shape == g["block_" + case].shape
+    assert relerr(got, g["block_" + case]) < RTOL
