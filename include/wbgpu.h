@@ -21,6 +21,7 @@
  *                                         (data_K/data_K_R.py:11-22, fourier/rvectors.py:443-475)
  *   wbgpu_static_scan(_dev)            <- paralfunc + StaticCalculator.__call__ over a list of K-blocks
  *                                         (run_grid.py:258-265,59-72; calculators/static.py:60-169)
+ *   wbgpu_static_scan_tetra            <- the same with tetra=True (Data_K.tetraWeights, grid/tetrahedron.py)
  *   wbgpu_eig                          <- Data_K.E_K (data_K/data_K.py:211-218)
  *   wbgpu_xk                           <- Rvectors.R_to_k / FFT_R_to_k.__call__
  *                                         (fourier/rvectors.py:496-506, fourier/fft.py:133-192)
@@ -118,6 +119,12 @@ int wbgpu_static_scan_dev(wbgpu_ctx* ctx, int nblocks, const double* dK_dev, con
                           const wbgpu_scan_spec* specs, int nspec, double* out_dev);
 /* number of float64 values one spec writes */
 int64_t wbgpu_spec_size(const wbgpu_scan_spec* spec);
+/* The same scans with the tetrahedron method on grid K-blocks, StaticCalculator(tetra=True) with KpointBZparallel
+ * (calculators/static.py:84-91,121-127; grid/tetrahedron.py:15-128,165-268; data_K/data_K_R.py:120-141):
+ * dK_cell[3] = Kpoint.dK_fullBZ, the edge of the cell around every k-point (1 / (NKdiv * NKFFT)); the Fermi levels
+ * are Ef_first + i * dEF.  The band energies at the 8 cell corners are evaluated inside the call.  HOST pointers. */
+int wbgpu_static_scan_tetra(wbgpu_ctx* ctx, int nblocks, const double* dK, const double* weight, const double* dK_cell,
+                            const wbgpu_scan_spec* specs, int nspec, double* out);
 
 /* One (Efermi x omega) scan = one DynamicCalculator.__call__ (calculators/dynamic.py:26-114) at kBT = 0. */
 enum { WBGPU_KUBO_OPTCOND = 0,  /* OpticalConductivity dynamic.py:184-196: complex128 data[nEF][nomega][3][3] */

@@ -359,6 +359,45 @@ def test_kubo_synthetic(wb, orc, nw, nEF, nom):
     assert relerr(got, orc.JDOS(odata, Ef, omega=om, **kw)) < RTOL
 
 
+# ---------------------------------------------------------------------------------------- tetrahedron method
+TETRA_CASES = dict(
+    ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}), spin=("Spin", {}),
+    ahc_thresh=("AHC", dict(degen_thresh=0.05)), bcd=("BerryDipole_FermiSurf", {}), gme_spin=("GME_spin_FermiSurf", {}),
+)
+# Fermi-sea quantities (der = 0): the north-star tolerance.  Fermi-surface quantities (der = 1): the reference
+# evaluates the derivative of the tetrahedron occupation as a cubic in E_F whose coefficients cancel by (E/dE)^2 ~ 1e7;
+# a 1e-15 relative change of the corner energies moves ITS result by 1-3e-8 (tests/test_oracle.py::
+# test_tetra_derivative_conditioning), and the corner eigenvalues of any two eigensolvers differ by more than that.
+TETRA_RTOL = dict(dos=1e-6, bcd=1e-6, gme_spin=1e-6)
+
+
+@pytest.mark.parametrize("case", sorted(TETRA_CASES))
+def test_tetra_block_vs_reference(wb, fe, case):
+    """StaticCalculator(tetra=True)(Data_K_R) for one K-block against the reference's output (fixture written by
+    tests/golden/make_golden_tetra.py): corner energies, tetrahedron band groups and weights on the GPU."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_tetra.npz"))
+    name, kw = TETRA_CASES[case]
+    grid = wb.Grid(fe, NKdiv=g["block_NKdiv"], NKFFT=g["block_NKFFT"])
+    data = wb.Data_K_R(fe, dK=g["block_dK"], grid=grid)
+    res = getattr(wb.calculators.static, name)(Efermi=g["Efermi"], tetra=True, **kw)(data)
+    assert res.data.shape == g["block_" + case].shape
+    assert relerr(res.data, g["block_" + case]) < TETRA_RTOL.get(case, RTOL)
+
+
+def test_tetra_run_vs_reference(wb, fe):
+    """run() mixing tetrahedron and plain calculators on a whole (small) grid against the reference's run()."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_tetra.npz"))
+    g4 = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    st = wb.calculators.static
+    calcs = {case: getattr(st, name)(Efermi=g["Efermi"], tetra=True, **kw) for case, (name, kw) in TETRA_CASES.items()}
+    calcs["plain_ahc"] = st.AHC(Efermi=g4["Efermi"])
+    grid = wb.Grid(fe, NKdiv=[2, 2, 2], NKFFT=[2, 2, 2])
+    res = wb.run(fe, grid, calcs)
+    for case in TETRA_CASES:
+        assert relerr(res.results[case].data, g["run_" + case]) < TETRA_RTOL.get(case, RTOL), case
+    assert relerr(res.results["plain_ahc"].data, g4["upstream_golden_ahc"]) < RTOL
+
+
 def test_run_fe_vs_upstream_golden(wb, fe):
     """run() on the reference's own test grid against the data of the reference's golden files
     tests/reference/integrate_files/Fe_W90-{ahc,dos,cumdos}_iter-0000.npz."""
@@ -456,7 +495,9 @@ def test_errors(wb, fe):
     with pytest.raises(ValueError):
         eng.scan(np.zeros((1, 3)), np.ones(1), st.AHC(Efermi=np.linspace(0, 1, 3)).specs())  # not in the plan
     with pytest.raises(NotImplementedError):
-        st.AHC(Efermi=np.linspace(0, 1, 3), tetra=True)
+        st.AHC(Efermi=np.linspace(0, 1, 3), tetra=True, hole_like=True)
+    with pytest.raises(NotImplementedError):
+        wb.calculators.dynamic.OpticalConductivity(Efermi=np.linspace(0, 1, 3), omega=np.linspace(0, 1, 3), kBT=0.01)
     with pytest.raises(ValueError):
         bare = wb.System_R(fe.real_lattice, fe.rvec.iRvec, fe.wannier_centers_cart)
         bare.get_R_mat("Ham")

@@ -175,3 +175,22 @@ def test_tetra_block_vs_reference(fe, case):
     got = orc.CALCULATORS[name](data, g["Efermi"], tetra=True, **kw)
     assert got.shape == g["block_" + case].shape
     assert relerr(got, g["block_" + case]) < RTOL
+
+
+def test_tetra_derivative_conditioning(fe):
+    """The reference's der >= 1 tetrahedron weights are a cubic in E_F with heavily cancelling coefficients
+    (grid/tetrahedron.py:53-78): a relative perturbation of 1e-15 of the corner energies -- below what any two
+    eigensolvers agree to -- changes a Fermi-surface integral by ~1e-8, a Fermi-sea integral (closed form) by ~1e-15.
+    This is why the GPU parity tests use 1e-6 for the der = 1 tetrahedron cases and 1e-8 for everything else."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_tetra.npz"))
+
+    def run(pert):
+        data = orc.OracleDataK(fe, g["block_dK"], g["block_NKFFT"], NKdiv=g["block_NKdiv"])
+        E0 = data.E_K_corners_parallel()
+        Ep = E0 * (1 + pert * np.random.default_rng(1).standard_normal(E0.shape))
+        data.E_K_corners_parallel = lambda: Ep
+        return (orc.CALCULATORS["GME_spin_FermiSurf"](data, g["Efermi"], tetra=True),
+                orc.CALCULATORS["AHC"](data, g["Efermi"], tetra=True))
+    (s0, a0), (s1, a1) = run(0.), run(1e-15)
+    assert relerr(a1, a0) < 1e-12
+    assert 1e-10 < relerr(s1, s0) < 1e-6

@@ -43,8 +43,8 @@ class StaticCalculator(Calculator):
         self.Efermi = np.array(Efermi)
         if self.Efermi.ndim != 1 or len(self.Efermi) < 1:
             raise ValueError("Efermi must be a 1-d array")
-        if tetra:
-            raise NotImplementedError("tetra=True is not implemented on the GPU path (SURVEY.md section 8(f), next-2)")
+        if tetra and hole_like:
+            raise NotImplementedError("tetra=True with hole_like (inverse Fermi sea, der=-1) is not implemented on the GPU path")
         if k_resolved:
             raise NotImplementedError("k_resolved=True is not implemented on the GPU path")
         if select_bands is not None:
@@ -107,7 +107,7 @@ class StaticCalculator(Calculator):
     def __call__(self, data_K):
         """Per-K-block evaluation with the reference's calling convention `calc(data_K)`; `data_K` is a
         `wannierberri_b200.Data_K_R` (GPU resident).  static.py:60-169."""
-        arrays = data_K.scan(self.specs(), external_terms=self.external_terms)
+        arrays = data_K.scan(self.specs(), external_terms=self.external_terms, tetra=self.tetra)
         return self.result(arrays, data_K.cell_volume)
 
 

@@ -10,11 +10,48 @@ struct WbWindow {
     int degen_Kramers;
     int sea;                   // fder == 0
     int nEFx;                  // nEF_extra
+    // tetrahedron method (grid/tetrahedron.py:140-162 with Ebandmin / Ebandmax): per-band minimum / maximum of the
+    // energy over the k-point's cell (centre + 8 corners), [nk][nw]; nullptr = plain rule on the centre energies
+    const double* Ebmin;
+    const double* Ebmax;
 };
 
 // For every band n: g1[n], g2[n] = [ib1, ib2) of the kept group (or of the Fermi-sea group) that
 // contains it, or g1[n] = -1.  label[ib1] = group label energy (mean of E, or -inf for the sea
 // group), label = +inf for slots where no group starts.  Serial, O(nw); E ascending.
+// tetrahedron variant: emin / emax = this k-point's rows of WbWindow::Ebmin / Ebmax.
+__device__ inline void wb_band_groups_tetra(const double* E, const double* __restrict__ emin, const double* __restrict__ emax,
+                                            int nw, const WbWindow& w, short* g1, short* g2, double* label) {
+    for (int n = 0; n < nw; n++) { g1[n] = -1; g2[n] = -1; label[n] = CUDART_INF; }
+    int prev = -1, first_kept = -1;
+    for (int pos = 0; pos <= nw; pos++) {
+        bool border = (pos == 0) || (pos == nw) || (E[pos] - E[pos - 1] > w.degen_thresh);
+        if (w.degen_Kramers && (pos & 1)) border = false;
+        if (!border) continue;
+        if (prev >= 0) {
+            const int a = prev, b = pos;
+            double mx = emax[a], mn = emin[a], s = E[a];
+            for (int n = a + 1; n < b; n++) { mx = fmax(mx, emax[n]); mn = fmin(mn, emin[n]); s += E[n]; }
+            if (mx >= w.EFmin && mn <= w.EFmax) {   // get_bands_in_range
+                label[a] = s / (double)(b - a);
+                for (int n = a; n < b; n++) { g1[n] = (short)a; g2[n] = (short)b; }
+                if (first_kept < 0) first_kept = a;
+            }
+        }
+        prev = pos;
+    }
+    if (w.sea) {   // get_bands_below_range(eFermi[0], Ebandmax = Emax)
+        int bandmax = 0;
+        for (int n = 0; n < nw; n++)
+            if (emax[n] < w.EFmin) bandmax = n + 1;
+        if (first_kept >= 0) bandmax = min(bandmax, first_kept);
+        if (bandmax > 0) {
+            label[0] = -CUDART_INF;
+            for (int n = 0; n < bandmax; n++) { g1[n] = 0; g2[n] = (short)bandmax; }
+        }
+    }
+}
+
 __device__ inline void wb_band_groups(const double* E, int nw, const WbWindow& w, short* g1, short* g2,
                                       double* label) {
     for (int n = 0; n < nw; n++) { g1[n] = -1; g2[n] = -1; label[n] = CUDART_INF; }

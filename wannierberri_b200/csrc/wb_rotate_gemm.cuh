@@ -175,7 +175,9 @@ wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
     for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
         for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
         __syncthreads();
-        if (nw <= 32) {
+        if (win.Ebmin) {
+            if (threadIdx.x == 0) wb_band_groups_tetra(Es, win.Ebmin + ik * nw, win.Ebmax + ik * nw, nw, win, g1, g2, label);
+        } else if (nw <= 32) {
             if (threadIdx.x < 32) wb_band_groups_warp(Es, nw, win, g1, g2, label, threadIdx.x);
         } else if (threadIdx.x == 0) wb_band_groups(Es, nw, win, g1, g2, label);
         __syncthreads();

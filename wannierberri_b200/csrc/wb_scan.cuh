@@ -23,7 +23,8 @@ __global__ void wb_identity_events_kernel(const double* __restrict__ Eall, int n
     long ik = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ik >= nk) return;
     for (int n = 0; n < nw; n++) E[n] = Eall[ik * nw + n];
-    wb_band_groups(E, nw, win, g1, g2, label);
+    if (win.Ebmin) wb_band_groups_tetra(E, win.Ebmin + ik * nw, win.Ebmax + ik * nw, nw, win, g1, g2, label);
+    else wb_band_groups(E, nw, win, g1, g2, label);
     for (int n = 0; n < nw; n++) {
         ev_label[ik * nw + n] = label[n];
         if (label[n] != CUDART_INF) ev_val[ik * nw + n] = (double)(g2[n] - n);

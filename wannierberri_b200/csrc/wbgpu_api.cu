@@ -28,6 +28,7 @@
 #include "wb_rotate_gemm.cuh"
 #include "wb_scan.cuh"
 #include "wb_kubo.cuh"
+#include "wb_tetra.cuh"
 #include "wb_probe.cuh"
 
 static thread_local std::string g_err;
@@ -87,6 +88,10 @@ struct wbgpu_ctx {
     size_t kent_cap = 0;
     double* d_kacc = nullptr;
     size_t kacc_cap = 0;
+    // tetrahedron method: H-only R-space table, corner energies [8][nkl][nw], per-band min / max over the cell
+    cplx* d_tableH = nullptr;
+    double* d_Ec = nullptr;
+    size_t Ec_cap = 0;
     // Householder+QL eigensolver work space (per sub-batch of eig_chunk k-points)
     long eig_chunk = 0;
     int capR = 0, capS = 0;
@@ -146,6 +151,8 @@ static void stage_collect(wbgpu_ctx* c) {
 
 static void free_plan(wbgpu_ctx* c) {
     cudaFree(c->d_table);
+    cudaFree(c->d_tableH);
+    c->d_tableH = nullptr;
     for (int d = 0; d < 3; d++) cudaFree(c->d_W[d]);
     cudaFree(c->d_Z); cudaFree(c->d_Y); cudaFree(c->d_X); cudaFree(c->d_U);
     cudaFree(c->d_E); cudaFree(c->d_evlabel); cudaFree(c->d_evval);
@@ -212,7 +219,7 @@ extern "C" int wbgpu_destroy(wbgpu_ctx* c) {
     free_plan(c);
     cudaFree(c->d_iRvec); cudaFree(c->d_T); cudaFree(c->d_sweeps);
     for (int k = 0; k < WBGPU_NKEYS; k++) cudaFree(c->d_XR[k]);
-    cudaFree(c->d_xbar); cudaFree(c->d_mx); cudaFree(c->d_kent); cudaFree(c->d_kacc);
+    cudaFree(c->d_xbar); cudaFree(c->d_mx); cudaFree(c->d_kent); cudaFree(c->d_kacc); cudaFree(c->d_Ec);
     cudaFree(c->d_hist); cudaFree(c->d_cum); cudaFree(c->d_dK); cudaFree(c->d_weight); cudaFree(c->d_out);
     delete c;
     return 0;
@@ -278,6 +285,7 @@ static WbWindow make_window(const wbgpu_scan_spec& s) {
     w.degen_thresh = s.degen_thresh;
     w.degen_Kramers = s.degen_Kramers;
     w.sea = (s.fder == 0);
+    w.Ebmin = w.Ebmax = nullptr;
     return w;
 }
 
@@ -541,7 +549,7 @@ static int launch_jacobi(wbgpu_ctx* c, long k0, long nk, bool want_U, const int*
 }
 
 template <int NWP, bool EXACT>
-static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
+static int launch_ql(wbgpu_ctx* c, long k0, long nk, bool want_U) {
     const int nw = c->nw;
     constexpr int WARPS = 4;
     CK(cudaMemsetAsync(c->d_nfail, 0, sizeof(int), c->stream));
@@ -567,6 +575,13 @@ static int launch_ql(wbgpu_ctx* c, long k0, long nk) {
             nw, nk, c->d_dw, c->d_ew, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep);
     }
     CK(cudaGetLastError());
+    if (!want_U) {   // eigenvalues only: sort the QL output, no replay / back-transformation
+        wb_eig_sort_kernel<<<(unsigned)((nk + 127) / 128), 128, 0, c->stream>>>(nw, k0, nk, c->d_dw, c->d_nsweep, c->d_E,
+                                                                             c->d_faillist, c->d_nfail);
+        c->launches += 3;
+        CK(cudaGetLastError());
+        return launch_jacobi(c, k0, nk, false, c->d_faillist, c->d_nfail, 148);
+    }
     constexpr int EW = 2;  // warps per CTA of the eigenvector kernel (19.6 KB of shared memory per warp at nw = 18)
     size_t smem3 = sizeof(cplx) * EW * (size_t)wb_eigvec_smem_per_warp(nw, c->capR, c->capS);
     if ((int)smem3 > c->smem_optin) return set_err("eigh(QL): num_wann=%d needs %zu B shared memory", nw, smem3);
@@ -632,14 +647,14 @@ static int run_eigh(wbgpu_ctx* c, long nk, bool want_U) {
     for (long k0 = 0; k0 < nk; k0 += c->eig_chunk) {
         long n = std::min(c->eig_chunk, nk - k0);
         int rc;
-        if (nw == 18) rc = launch_ql<18, true>(c, k0, n);
-        else if (nw == 16) rc = launch_ql<16, true>(c, k0, n);
-        else if (nw == 24) rc = launch_ql<24, true>(c, k0, n);
-        else if (nw == 32) rc = launch_ql<32, true>(c, k0, n);
-        else if (nw <= 8) rc = launch_ql<8, false>(c, k0, n);
-        else if (nw <= 16) rc = launch_ql<16, false>(c, k0, n);
-        else if (nw <= 24) rc = launch_ql<24, false>(c, k0, n);
-        else rc = launch_ql<32, false>(c, k0, n);
+        if (nw == 18) rc = launch_ql<18, true>(c, k0, n, want_U);
+        else if (nw == 16) rc = launch_ql<16, true>(c, k0, n, want_U);
+        else if (nw == 24) rc = launch_ql<24, true>(c, k0, n, want_U);
+        else if (nw == 32) rc = launch_ql<32, true>(c, k0, n, want_U);
+        else if (nw <= 8) rc = launch_ql<8, false>(c, k0, n, want_U);
+        else if (nw <= 16) rc = launch_ql<16, false>(c, k0, n, want_U);
+        else if (nw <= 24) rc = launch_ql<24, false>(c, k0, n, want_U);
+        else rc = launch_ql<32, false>(c, k0, n, want_U);
         if (rc) return rc;
     }
     return 0;
@@ -656,7 +671,7 @@ struct EvGroup {
 
 static bool same_window(const WbWindow& a, const WbWindow& b) {
     return a.EFmin == b.EFmin && a.EFmax == b.EFmax && a.dEF == b.dEF && a.degen_thresh == b.degen_thresh &&
-           a.degen_Kramers == b.degen_Kramers && a.sea == b.sea && a.nEFx == b.nEFx;
+           a.degen_Kramers == b.degen_Kramers && a.sea == b.sea && a.nEFx == b.nEFx && a.Ebmin == b.Ebmin;
 }
 
 static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec) {
@@ -783,7 +798,9 @@ static int run_events_xbar(wbgpu_ctx* c, const EvGroup& G, long nk) {
         long n = std::min(chunk, nk - k0);
         if (rotate_gemm(c, ch, k0, n)) return 1;
         long nblk = std::min(n, nblk_max);
-        wb_events_xbar_kernel<NT><<<(unsigned)nblk, NT, smem, c->stream>>>((const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, G.win, G.ev,
+        WbWindow wloc = G.win;
+        if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
+        wb_events_xbar_kernel<NT><<<(unsigned)nblk, NT, smem, c->stream>>>((const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, G.ev,
                                                                        c->d_mx, c->d_evlabel + k0 * nw,
                                                                        c->d_evval + (size_t)k0 * nw * G.ev.NC);
         c->launches++;
@@ -813,6 +830,7 @@ static int run_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
         ((need.Oblk || need.Odiag) && L.off_O[0] < 0) || ((need.Cblk || need.Cdiag) && L.off_C[0] < 0) ||
         ((need.Sblk || need.Sdiag) && L.off_S[0] < 0))
         return set_err("scan: the plan does not hold the channels that formula mask 0x%x needs", G.ev.mask);
+    if (G.win.Ebmin) return run_events_xbar(c, G, nk);   // tetrahedron band groups: size-generic path
     // compile-time-NW tensor-core kernel (Omega and/or Morb_Hpm)
     if (c->rotate_method == 0 || c->rotate_method == 3) {
         int rc = launch_mma_events(c, G, nk);
@@ -1007,6 +1025,151 @@ extern "C" int wbgpu_static_scan(wbgpu_ctx* c, int nblocks, const double* dK, co
 }
 
 
+
+// ------------------------------------------------------------------------------------------ tetrahedron method
+extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* dK, const double* weight, const double* dK_cell,
+                                       const wbgpu_scan_spec* specs, int nspec, double* out) {
+    if (!c || !dK || !weight || !dK_cell || !specs || !out) return set_err("wbgpu_static_scan_tetra: null pointer argument");
+    if (!c->planned) return set_err("wbgpu_static_scan_tetra: call wbgpu_plan first");
+    if (nblocks < 0 || nspec < 1) return set_err("wbgpu_static_scan_tetra: nblocks=%d nspec=%d", nblocks, nspec);
+    CK(cudaSetDevice(c->device));
+    const int nw = c->nw;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    size_t nout = 0;
+    std::vector<size_t> hoff(nspec + 1, 0);
+    for (int i = 0; i < nspec; i++) {
+        if (check_spec(c, specs[i])) return 1;
+        size_t sz = (size_t)specs[i].nEF * formula_ncomp(specs[i].formula);
+        hoff[i + 1] = hoff[i] + 2 * sz;   // direct | suffix
+        nout += sz;
+    }
+    if (ensure(&c->d_hist, &c->hist_cap, sizeof(double) * hoff[nspec])) return 1;
+    CK(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * hoff[nspec], c->stream));
+    if (ensure(&c->d_out, &c->out_cap, sizeof(double) * nout)) return 1;
+    // H-only R-space table for the corner energies
+    WbLayout LH;
+    LH.nw = nw; LH.ntri = nw * (nw + 1) / 2; LH.E = LH.ntri; LH.off_H = 0; LH.dH_herm = 0;
+    for (int a = 0; a < 3; a++) LH.off_dH[a] = LH.off_A[a] = LH.off_O[a] = LH.off_B[a] = LH.off_C[a] = LH.off_S[a] = -1;
+    const size_t ncell = (size_t)c->nbox.x * c->nbox.y * c->nbox.z;
+    if (!c->d_tableH) {
+        CK(cudaMalloc(&c->d_tableH, sizeof(cplx) * ncell * LH.E));
+        CK(cudaMemsetAsync(c->d_tableH, 0, sizeof(cplx) * ncell * LH.E, c->stream));
+        WbRInputs in;
+        in.Ham = c->d_XR[WBGPU_HAM];
+        in.AA = in.BB = in.CC = in.SS = nullptr;
+        in.T = c->d_T;
+        in.iRvec = c->d_iRvec;
+        long total = (long)c->nR * nw * nw;
+        wb_build_rtable_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(in, LH, c->nR, c->rmin, c->nbox, c->d_tableH);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    // shifts of the centre and of the 8 corners k +- dK_cell/2 (data_K_R.py:120-141): [9][nblocks][3] | weight
+    const int nbk = std::max(nblocks, 1);
+    std::vector<double> hdk((size_t)27 * nbk + nbk);
+    for (int b = 0; b < nblocks; b++) {
+        for (int d = 0; d < 3; d++) hdk[3 * (size_t)b + d] = dK[3 * b + d];
+        for (int cr = 0; cr < 8; cr++) {
+            const int bit[3] = {(cr >> 2) & 1, (cr >> 1) & 1, cr & 1};
+            for (int d = 0; d < 3; d++)
+                hdk[3 * ((size_t)(1 + cr) * nbk + b) + d] = dK[3 * b + d] + (bit[d] ? 0.5 : -0.5) * dK_cell[d];
+        }
+        hdk[(size_t)27 * nbk + b] = weight[b];
+    }
+    if (ensure(&c->d_dK, &c->dK_cap, sizeof(double) * hdk.size())) return 1;
+    CK(cudaMemcpyAsync(c->d_dK, hdk.data(), sizeof(double) * hdk.size(), cudaMemcpyHostToDevice, c->stream));
+    const double* d_w = c->d_dK + (size_t)27 * nbk;
+    const size_t nkl = (size_t)c->nb_max * c->nk_block;
+    if (ensure(&c->d_Ec, &c->Ec_cap, sizeof(double) * 10 * nkl * nw)) return 1;
+    double* d_Ebmin = c->d_Ec + 8 * nkl * nw;
+    double* d_Ebmax = d_Ebmin + nkl * nw;
+    bool need_U = false;
+    for (int i = 0; i < nspec; i++) need_U |= (specs[i].formula != WBGPU_IDENTITY);
+
+    // event groups with the tetrahedron window: [Efermi[0], Efermi[-1]], no widening (tetrahedron.py:232-241)
+    std::vector<wbgpu_scan_spec> tsp(specs, specs + nspec);
+    std::vector<EvGroup> groups = make_groups(tsp.data(), nspec);
+    for (EvGroup& G : groups) {
+        const wbgpu_scan_spec& s0 = specs[G.specs[0]];
+        G.win.EFmin = s0.Ef_first;
+        G.win.EFmax = s0.Ef_first + (s0.nEF - 1) * s0.dEF;
+        if (s0.nEF > 1) G.win.EFmax = s0.Ef_last;
+        G.win.nEFx = s0.nEF;
+        G.win.Ebmin = d_Ebmin;
+        G.win.Ebmax = d_Ebmax;
+    }
+
+    for (int b0 = 0; b0 < nblocks; b0 += c->nb_max) {
+        const int nb = std::min(c->nb_max, nblocks - b0);
+        const long nk = (long)nb * c->nk_block;
+        // ---- corner energies: H-only transform + eigenvalues at the 8 shifted grids
+        stage_begin(c, WBGPU_STAGE_EIGH);
+        {
+            const WbLayout Lsave = c->L;
+            cplx* const tsave = c->d_table;
+            c->L = LH;
+            c->d_table = c->d_tableH;
+            int rc = 0;
+            for (int cr = 0; cr < 8 && !rc; cr++) {
+                rc = run_fourier(c, c->d_dK + 3 * ((size_t)(1 + cr) * nbk + b0), nb);
+                if (!rc) rc = run_eigh(c, nk, false);
+                if (!rc && cudaMemcpyAsync(c->d_Ec + (size_t)cr * nkl * nw, c->d_E, sizeof(double) * nk * nw, cudaMemcpyDeviceToDevice,
+                                           c->stream) != cudaSuccess)
+                    rc = set_err("wbgpu_static_scan_tetra: device copy failed");
+            }
+            c->L = Lsave;
+            c->d_table = tsave;
+            if (rc) return 1;
+        }
+        stage_end(c);
+        stage_begin(c, WBGPU_STAGE_FOURIER);
+        if (run_fourier(c, c->d_dK + 3 * (size_t)b0, nb)) return 1;
+        stage_end(c);
+        stage_begin(c, WBGPU_STAGE_EIGH);
+        if (run_eigh(c, nk, need_U)) return 1;
+        wb_tetra_minmax_kernel<<<(unsigned)((nk * nw + 255) / 256), 256, 0, c->stream>>>(c->d_E, c->d_Ec, (long)(nkl * nw), nk * nw,
+                                                                                       d_Ebmin, d_Ebmax);
+        c->launches++;
+        stage_end(c);
+        for (const EvGroup& G : groups) {
+            stage_begin(c, G.ev.mask == 1 ? WBGPU_STAGE_IDENTITY : WBGPU_STAGE_ROTATE);
+            if (run_events(c, G, nk)) return 1;
+            stage_end(c);
+            stage_begin(c, WBGPU_STAGE_SCAN);
+            for (int i : G.specs) {
+                const wbgpu_scan_spec& s = specs[i];
+                const int ncomp = formula_ncomp(s.formula);
+                const int use_smem = 2 * sizeof(double) * (size_t)s.nEF * ncomp <= 96 * 1024;
+                const size_t smem = wb_tetra_acc_smem_bytes(nw, s.nEF, ncomp, use_smem);
+                if (smem > 48 * 1024)
+                    CK(cudaFuncSetAttribute(wb_tetra_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const long nblk = std::min(nk, (long)sms * 2);
+                wb_tetra_accumulate_kernel<<<(unsigned)nblk, 128, smem, c->stream>>>(
+                    c->d_evval + G.ev.off[s.formula], G.ev.NC, nw, nk, c->nk_block, c->d_E, c->d_Ec, (long)(nkl * nw), G.win, d_w + b0,
+                    ncomp, s.fder, s.nEF, s.Ef_first, s.dEF, c->d_hist + hoff[i], use_smem);
+                c->launches++;
+            }
+            stage_end(c);
+            CK(cudaGetLastError());
+        }
+    }
+    size_t ooff = 0;
+    for (int i = 0; i < nspec; i++) {
+        const wbgpu_scan_spec& s = specs[i];
+        const int ncomp = formula_ncomp(s.formula);
+        const double scale = s.factor / (c->cell_volume * (double)c->nk_block);
+        wb_tetra_finalize_kernel<<<1, 32, 0, c->stream>>>(c->d_hist + hoff[i], s.nEF, ncomp, scale, c->d_out + ooff);
+        c->launches++;
+        ooff += (size_t)s.nEF * ncomp;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    stage_collect(c);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ Kubo
 extern "C" int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* s) {
     if (!s || s->nEF < 1 || s->nomega < 1) return -1;
@@ -1045,6 +1208,7 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     WbWindow win;
     win.EFmin = -INFINITY; win.EFmax = INFINITY; win.dEF = 1.; win.degen_thresh = spec->degen_thresh;
     win.degen_Kramers = spec->degen_Kramers; win.sea = 0; win.nEFx = nEF;
+    win.Ebmin = win.Ebmax = nullptr;
 
     // device copies: dK | weight | Efermi | omega, accumulator D[nomega][nEF][NC] + output
     const int nbk = std::max(nblocks, 1);

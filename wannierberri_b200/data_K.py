@@ -36,12 +36,16 @@ class Data_K_R:
         from . import _lib
         self.engine.plan(self.NKFFT, set(formulae) | {_lib.IDENTITY}, external_terms=external_terms)
 
-    def scan(self, specs, external_terms=True):
+    def scan(self, specs, external_terms=True, tetra=False):
         if self.force_internal_terms_only:
             for s in specs:
                 s.external_terms = 0
             external_terms = False
         self._plan([s.formula for s in specs], external_terms)
+        if tetra:
+            # KpointBZparallel.dK_fullBZ (grid/Kpoint.py:107-109)
+            dK_cell = 1. / (np.array(self.grid.div, dtype=float) * np.array(self.grid.FFT, dtype=float))
+            return self.engine.scan_tetra(self.dK[None, :], np.ones(1), dK_cell, specs)
         return self.engine.scan(self.dK[None, :], np.ones(1), specs)
 
     def kubo_scan(self, spec, Efermi, omega):

@@ -77,6 +77,21 @@ class Engine:
             off += s.size
         return res
 
+    def scan_tetra(self, dK, weight, dK_cell, specs):
+        """`scan()` with the tetrahedron method: `dK_cell` = Kpoint.dK_fullBZ = 1 / (NKdiv * NKFFT)."""
+        dK = as_f64(dK).reshape(-1, 3)
+        weight = as_f64(weight).reshape(-1)
+        dK_cell = as_f64(dK_cell).reshape(3)
+        arr = (ScanSpec * len(specs))(*specs)
+        out = np.zeros(sum(s.size for s in specs))
+        check(self._L.wbgpu_static_scan_tetra(self._ctx, dK.shape[0], dptr(dK), dptr(weight), dptr(dK_cell), arr,
+                                              len(specs), dptr(out)))
+        res, off = [], 0
+        for s in specs:
+            res.append(out[off:off + s.size].reshape(s.shape).copy())
+            off += s.size
+        return res
+
     def scan_dev(self, dK_dev, weight_dev, specs, out_dev):
         """Device-resident variant: torch CUDA tensors (float64) for dK[nb,3], weight[nb], out[sum sizes];
         asynchronous on the context's stream."""

@@ -73,13 +73,13 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
     shifts, factors = k_list_arrays(grid, use_irred_kpt)
     lo, hi = shard_bounds(len(factors), rank, world)
 
-    specs, owner = [], []
+    specs, owner, tspecs, towner = [], [], [], []
     for key, c in calcs.items():
         for s in c.specs():
             if getattr(system, "force_internal_terms_only", False):
                 s.external_terms = 0
-            specs.append(s)
-            owner.append(key)
+            (tspecs if c.tetra else specs).append(s)
+            (towner if c.tetra else owner).append(key)
     internal_only = getattr(system, "force_internal_terms_only", False)
     kspecs = {}
     for key, c in dyn_calcs.items():
@@ -87,11 +87,15 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
         if internal_only:
             ks.external_terms = 0
         kspecs[key] = ks
-    external = any(s.external_terms for s in specs) or any(ks.external_terms for ks in kspecs.values())
-    formulae = {int(s.formula) for s in specs} | ({_lib.KUBO} if kspecs else set()) | {_lib.IDENTITY}
+    external = any(s.external_terms for s in specs + tspecs) or any(ks.external_terms for ks in kspecs.values())
+    formulae = {int(s.formula) for s in specs + tspecs} | ({_lib.KUBO} if kspecs else set()) | {_lib.IDENTITY}
     engine = engine_for(system, device)
     engine.plan(np.array(grid.FFT, dtype=int), formulae, external_terms=external)
     arrays = engine.scan(shifts[lo:hi], factors[lo:hi], specs) if specs else []
+    if tspecs:  # tetrahedron method: the cell around every k-point is KpointBZparallel.dK_fullBZ
+        dK_cell = 1. / (np.array(grid.div, dtype=float) * np.array(grid.FFT, dtype=float))
+        arrays = arrays + engine.scan_tetra(shifts[lo:hi], factors[lo:hi], dK_cell, tspecs)
+        owner = owner + towner
     # Kubo scans: one call each (their accumulators are large; they do not share the event pass of the static scans)
     karrays = [engine.kubo_scan(shifts[lo:hi], factors[lo:hi], ks, dyn_calcs[key].Efermi, dyn_calcs[key].omega)
                for key, ks in kspecs.items()]
