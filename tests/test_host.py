@@ -85,7 +85,7 @@ def test_calculator_windows_and_errors():
     assert [x.formula for x in m.specs()] == [_lib.MORB_HPM, _lib.OMEGA]
     assert st.AHC(Efermi=Ef, hole_like=True).constant_factor == -a.constant_factor
     assert st.AHC(Efermi=Ef, use_factor=False).specs()[0].factor == -1.0
-    for bad in (dict(tetra=True), dict(k_resolved=True), dict(select_bands=[1]), dict(Emin=0.)):
+    for bad in (dict(tetra=True, hole_like=True), dict(k_resolved=True), dict(select_bands=[1]), dict(Emin=0.)):
         with pytest.raises(NotImplementedError):
             st.AHC(Efermi=Ef, **bad)
     with pytest.raises(ValueError):
