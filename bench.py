@@ -183,9 +183,21 @@ def main():
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if world > 1:
+        # NCCL prints its version banner on stdout at the first collective: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            t = torch.zeros(1, device=dev)
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     system = wb.System_R.from_npz(FE)
     st = wb.calculators.static
