@@ -117,6 +117,11 @@ int wbgpu_static_scan(wbgpu_ctx* ctx, int nblocks, const double* dK, const doubl
  * context's stream. */
 int wbgpu_static_scan_dev(wbgpu_ctx* ctx, int nblocks, const double* dK_dev, const double* weight_dev,
                           const wbgpu_scan_spec* specs, int nspec, double* out_dev);
+/* Per-K-block results, what adaptive refinement needs (Kpoint.set_result / .max, run_grid.py:59-72,343-375;
+ * grid/Kpoint.py:35-38,85-92): out[nblocks][total], total = sum of wbgpu_spec_size over the specs; block b holds
+ * the scans of K-block b alone (no weight).  HOST pointers. */
+int wbgpu_static_scan_blocks(wbgpu_ctx* ctx, int nblocks, const double* dK, const wbgpu_scan_spec* specs, int nspec,
+                             double* out);
 /* number of float64 values one spec writes */
 int64_t wbgpu_spec_size(const wbgpu_scan_spec* spec);
 /* The same scans with the tetrahedron method on grid K-blocks, StaticCalculator(tetra=True) with KpointBZparallel

@@ -398,6 +398,31 @@ def test_tetra_run_vs_reference(wb, fe):
     assert relerr(res.results["plain_ahc"].data, g4["upstream_golden_ahc"]) < RTOL
 
 
+def test_adaptive_refinement(wb, fe, orc):
+    """run(adpt_num_iter > 0): per-K-block results from the GPU + the reference's refinement loop, against the
+    reference's own run() on a model without symmetry (fixture of tests/golden/make_golden_adpt.py); per-K-block
+    results must also add up to the weighted scan."""
+    g = np.load(os.path.join(GOLDEN, "golden_synth_adpt.npz"))
+    sysg = wb.synthetic_system(6, rmax=1, seed=4242)
+    st = wb.calculators.static
+    for n_iter in (0, 1, 3):
+        calcs = dict(ahc=st.AHC(Efermi=g["Efermi"]), dos=st.DOS(Efermi=g["Efermi"]))
+        grid = wb.Grid(sysg, NKdiv=[2, 2, 2], NKFFT=[3, 3, 3])
+        res = wb.run(sysg, grid, calcs, adpt_num_iter=n_iter, adpt_fac=2, adpt_mesh=2) if n_iter else wb.run(sysg, grid, calcs)
+        for q in calcs:
+            assert relerr(res.results[q].data, g[f"iter{n_iter}_{q}"]) < RTOL, (n_iter, q)
+    # blocks add up (Fe, more K-blocks than one launch holds when max_kpoints_per_launch is small)
+    specs = st.AHC(Efermi=g["Efermi"] + 17.).specs() + st.DOS(Efermi=g["Efermi"] + 17.).specs()
+    eng = wb.Engine(fe)
+    eng.plan([2, 2, 2], [s.formula for s in specs], max_kpoints_per_launch=24)
+    shifts, factors = wb.Grid(fe, NKdiv=[2, 2, 2], NKFFT=[2, 2, 2]).K_arrays()
+    whole = eng.scan(shifts, factors, specs)
+    blocks = eng.scan_blocks(shifts, specs)
+    for w, b in zip(whole, blocks):
+        assert b.shape[0] == len(factors)
+        assert relerr(np.tensordot(factors, b, axes=(0, 0)), w) < 1e-12
+
+
 def test_run_fe_vs_upstream_golden(wb, fe):
     """run() on the reference's own test grid against the data of the reference's golden files
     tests/reference/integrate_files/Fe_W90-{ahc,dos,cumdos}_iter-0000.npz."""

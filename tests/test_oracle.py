@@ -194,3 +194,23 @@ def test_tetra_derivative_conditioning(fe):
     (s0, a0), (s1, a1) = run(0.), run(1e-15)
     assert relerr(a1, a0) < 1e-12
     assert 1e-10 < relerr(s1, s0) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------- adaptive refinement
+def synth_adpt_system():
+    from wannierberri_b200.system import synthetic_system  # array generator only (no GPU involved)
+    g = synthetic_system(6, rmax=1, seed=4242)
+    return g, orc.OracleSystem(g.rvec.iRvec, g.real_lattice, g.wannier_centers_cart,
+                               {k: g.get_R_mat(k) for k in ("Ham", "AA")})
+
+
+def test_adaptive_refinement_vs_reference():
+    """The refinement loop (run_grid.py:303-387) against the reference's run(adpt_num_iter = 0, 1, 3) on a model
+    without symmetry (fixture written by tests/golden/make_golden_adpt.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_synth_adpt.npz"))
+    _, syso = synth_adpt_system()
+    calcs = dict(ahc=("AHC", g["Efermi"], {}), dos=("DOS", g["Efermi"], {}))
+    hist = orc.run_adaptive(syso, [2, 2, 2], [3, 3, 3], calcs, adpt_num_iter=3, adpt_mesh=2, adpt_fac=2)
+    for n_iter in (0, 1, 3):
+        for q in calcs:
+            assert relerr(hist[n_iter][q], g[f"iter{n_iter}_{q}"]) < RTOL, (n_iter, q)

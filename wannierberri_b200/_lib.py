@@ -64,6 +64,7 @@ def lib():
     L.wbgpu_plan.argtypes = [vp, C.POINTER(i32), C.c_uint32, C.c_int, i64]
     L.wbgpu_static_scan.argtypes = [vp, C.c_int, pd, pd, C.POINTER(ScanSpec), C.c_int, pd]
     L.wbgpu_static_scan_dev.argtypes = [vp, C.c_int, vp, vp, C.POINTER(ScanSpec), C.c_int, vp]
+    L.wbgpu_static_scan_blocks.argtypes = [vp, C.c_int, pd, C.POINTER(ScanSpec), C.c_int, pd]
     L.wbgpu_static_scan_tetra.argtypes = [vp, C.c_int, pd, pd, pd, C.POINTER(ScanSpec), C.c_int, pd]
     L.wbgpu_spec_size.argtypes = [C.POINTER(ScanSpec)]
     L.wbgpu_spec_size.restype = i64
@@ -83,7 +84,7 @@ def lib():
     for name in ("wbgpu_create", "wbgpu_destroy", "wbgpu_set_R_matrix", "wbgpu_plan", "wbgpu_static_scan",
                  "wbgpu_static_scan_dev", "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_band_traces",
                  "wbgpu_last_eig_sweeps", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak", "wbgpu_kubo_scan",
-                 "wbgpu_static_scan_tetra"):
+                 "wbgpu_static_scan_tetra", "wbgpu_static_scan_blocks"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -93,7 +94,7 @@ EXPORTED = ["wbgpu_last_error", "wbgpu_version", "wbgpu_device_count", "wbgpu_cr
             "wbgpu_set_R_matrix", "wbgpu_plan", "wbgpu_static_scan", "wbgpu_static_scan_dev", "wbgpu_spec_size",
             "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_band_traces", "wbgpu_kernel_launches",
             "wbgpu_last_eig_sweeps", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak", "wbgpu_kubo_size",
-            "wbgpu_kubo_scan", "wbgpu_static_scan_tetra"]
+            "wbgpu_kubo_scan", "wbgpu_static_scan_tetra", "wbgpu_static_scan_blocks"]
 
 
 def check(status):

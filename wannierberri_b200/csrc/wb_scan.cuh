@@ -32,18 +32,26 @@ __global__ void wb_identity_events_kernel(const double* __restrict__ Eall, int n
 }
 
 // hist[(nEFx + 1)][ncomp]: row 0 = "below" (label < EFmin), row 1 + iEf = bin iEf.
+// per_block_stride > 0: one histogram PER K-BLOCK (blockIdx.y = K-block of this launch, weight 1) at
+// hist + blockIdx.y * per_block_stride -- the per-K-point results that adaptive refinement needs (run_grid.py:59-72).
 __global__ void __launch_bounds__(256)
 wb_scan_accumulate_kernel(const double* __restrict__ ev_label, const double* __restrict__ ev_val, int ev_stride,
                           long nslots, int slots_per_block /* nk_block * nw */, const double* __restrict__ weight,
-                          int ncomp, WbWindow win, double* __restrict__ hist, int use_smem) {
+                          int ncomp, WbWindow win, double* __restrict__ hist, int use_smem, long per_block_stride) {
     extern __shared__ double hist_s[];
     const int nrow = win.nEFx + 1;
+    long s_begin = 0, s_end = nslots;
+    if (per_block_stride > 0) {
+        s_begin = (long)blockIdx.y * slots_per_block;
+        s_end = s_begin + slots_per_block;
+        hist += (size_t)blockIdx.y * per_block_stride;
+    }
     if (use_smem) {
         for (int x = threadIdx.x; x < nrow * ncomp; x += blockDim.x) hist_s[x] = 0.;
         __syncthreads();
     }
     double* h = use_smem ? hist_s : hist;
-    for (long s = (long)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += (long)gridDim.x * blockDim.x) {
+    for (long s = s_begin + (long)blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += (long)gridDim.x * blockDim.x) {
         double E = ev_label[s];
         if (E == CUDART_INF) continue;
         int row;
@@ -55,7 +63,7 @@ wb_scan_accumulate_kernel(const double* __restrict__ ev_label, const double* __r
             if (iEf >= win.nEFx) continue;  // restot[iEf:] is empty
             row = 1 + iEf;
         } else continue;
-        double w = weight[s / slots_per_block];
+        double w = (per_block_stride > 0) ? 1. : weight[s / slots_per_block];
         for (int c = 0; c < ncomp; c++) atomicAdd(&h[row * ncomp + c], w * ev_val[s * ev_stride + c]);
     }
     if (use_smem) {
@@ -70,11 +78,16 @@ wb_scan_accumulate_kernel(const double* __restrict__ ev_label, const double* __r
 // restot[e] = below + sum_{e' <= e} hist[e'] ; stencil (static.py:137-147) ; * scale.
 // One CTA per component: chunked running sum over the Fermi axis (thread = contiguous chunk, chunk offsets by a
 // serial pass over 256 partial sums), then the finite-difference stencil.
+// blockIdx.y = K-block in the per-K-block mode (strides of hist / cum / out between K-blocks), else 0.
 __global__ void __launch_bounds__(256)
 wb_scan_finalize_kernel(const double* __restrict__ hist, double* __restrict__ cum, int ncomp, int nEFx, int nEF,
-                        int fder, double dEF, double scale, double* __restrict__ out) {
+                        int fder, double dEF, double scale, double* __restrict__ out, long hist_stride, long cum_stride,
+                        long out_stride) {
     __shared__ double part[256];
     const int c = blockIdx.x;
+    hist += (size_t)blockIdx.y * hist_stride;
+    cum += (size_t)blockIdx.y * cum_stride;
+    out += (size_t)blockIdx.y * out_stride;
     const int per = (nEFx + 255) / 256;
     const int e0 = threadIdx.x * per, e1 = min(e0 + per, nEFx);
     double s = 0.;

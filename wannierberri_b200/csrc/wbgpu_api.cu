@@ -892,29 +892,45 @@ static int check_spec(const wbgpu_ctx* c, const wbgpu_scan_spec& s) {
     return 0;
 }
 
-extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK_dev, const double* weight_dev,
-                                     const wbgpu_scan_spec* specs, int nspec, double* out_dev) {
-    if (!c || !dK_dev || !weight_dev || !specs || !out_dev) return set_err("wbgpu_static_scan: null pointer argument");
+// out_dev: [total] (weighted sum over the K-blocks), or [nblocks][total] in the per-K-block mode (weights ignored)
+static int static_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, const double* weight_dev,
+                            const wbgpu_scan_spec* specs, int nspec, double* out_dev, bool per_block) {
+    if (!c || !dK_dev || !specs || !out_dev || (!per_block && !weight_dev)) return set_err("wbgpu_static_scan: null pointer argument");
     if (!c->planned) return set_err("wbgpu_static_scan: call wbgpu_plan first");
     if (nblocks < 0 || nspec < 1) return set_err("wbgpu_static_scan: nblocks=%d nspec=%d", nblocks, nspec);
     CK(cudaSetDevice(c->device));
-    std::vector<size_t> hoff(nspec + 1, 0);
+    std::vector<size_t> hoff(nspec + 1, 0), ooffs(nspec + 1, 0);
     size_t cum_max = 0;
     for (int i = 0; i < nspec; i++) {
         if (check_spec(c, specs[i])) return 1;
         WbWindow w = make_window(specs[i]);
         size_t sz = (size_t)(w.nEFx + 1) * formula_ncomp(specs[i].formula);
         hoff[i + 1] = hoff[i] + sz;
+        ooffs[i + 1] = ooffs[i] + (size_t)specs[i].nEF * formula_ncomp(specs[i].formula);
         cum_max = std::max(cum_max, sz);
     }
-    size_t need = sizeof(double) * (hoff[nspec] + cum_max);
+    const size_t nhist = per_block ? (size_t)c->nb_max : 1;   // histograms (and prefix-sum scratch rows) held at once
+    size_t need = sizeof(double) * nhist * (hoff[nspec] + cum_max);
     if (ensure(&c->d_hist, &c->hist_cap, need)) return 1;
-    CK(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * hoff[nspec], c->stream));
-    double* d_cum = c->d_hist + hoff[nspec];
+    CK(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * nhist * hoff[nspec], c->stream));
+    double* d_cum = c->d_hist + nhist * hoff[nspec];
     const int nw = c->nw;
     bool need_U = false;
     for (int i = 0; i < nspec; i++) need_U |= (specs[i].formula != WBGPU_IDENTITY);
     std::vector<EvGroup> groups = make_groups(specs, nspec);
+    auto finalize = [&](int nb, double* out) {   // nb histograms -> out[nb][total] (nb = 1: the weighted sum)
+        for (int i = 0; i < nspec; i++) {
+            const wbgpu_scan_spec& s = specs[i];
+            WbWindow w = make_window(s);
+            int ncomp = formula_ncomp(s.formula);
+            double scale = s.factor / (c->cell_volume * (double)c->nk_block);
+            dim3 grid((unsigned)ncomp, (unsigned)nb);
+            wb_scan_finalize_kernel<<<grid, 256, 0, c->stream>>>(c->d_hist + hoff[i], d_cum, ncomp, w.nEFx, s.nEF, s.fder, s.dEF,
+                                                             scale, out + ooffs[i], (long)hoff[nspec], (long)cum_max,
+                                                             (long)ooffs[nspec]);
+            c->launches++;
+        }
+    };
 
     for (int b0 = 0; b0 < nblocks; b0 += c->nb_max) {
         int nb = std::min(c->nb_max, nblocks - b0);
@@ -938,30 +954,37 @@ extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK
                 if (use_smem)
                     CK(cudaFuncSetAttribute(wb_scan_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
                 long nslots = nk * nw;
-                long nblk = std::min((nslots + 255) / 256, 148L * 2);
-                wb_scan_accumulate_kernel<<<(unsigned)nblk, 256, use_smem ? hbytes : 0, c->stream>>>(
-                    c->d_evlabel, c->d_evval + G.ev.off[s.formula], G.ev.NC, nslots, (int)(c->nk_block * nw), weight_dev + b0,
-                    ncomp, G.win, c->d_hist + hoff[i], use_smem);
+                if (per_block) {
+                    dim3 grid((unsigned)std::max(1L, std::min((c->nk_block * nw + 255) / 256, (long)(148 * 2 / std::max(nb, 1) + 1))),
+                              (unsigned)nb);
+                    wb_scan_accumulate_kernel<<<grid, 256, use_smem ? hbytes : 0, c->stream>>>(
+                        c->d_evlabel, c->d_evval + G.ev.off[s.formula], G.ev.NC, nslots, (int)(c->nk_block * nw), nullptr, ncomp,
+                        G.win, c->d_hist + hoff[i], use_smem, (long)hoff[nspec]);
+                } else {
+                    long nblk = std::min((nslots + 255) / 256, 148L * 2);
+                    wb_scan_accumulate_kernel<<<(unsigned)nblk, 256, use_smem ? hbytes : 0, c->stream>>>(
+                        c->d_evlabel, c->d_evval + G.ev.off[s.formula], G.ev.NC, nslots, (int)(c->nk_block * nw), weight_dev + b0,
+                        ncomp, G.win, c->d_hist + hoff[i], use_smem, 0L);
+                }
                 c->launches++;
             }
             stage_end(c);
             CK(cudaGetLastError());
         }
+        if (per_block) {
+            finalize(nb, out_dev + (size_t)b0 * ooffs[nspec]);
+            CK(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * nhist * hoff[nspec], c->stream));
+        }
     }
-    size_t ooff = 0;
-    for (int i = 0; i < nspec; i++) {
-        const wbgpu_scan_spec& s = specs[i];
-        WbWindow w = make_window(s);
-        int ncomp = formula_ncomp(s.formula);
-        double scale = s.factor / (c->cell_volume * (double)c->nk_block);
-        wb_scan_finalize_kernel<<<ncomp, 256, 0, c->stream>>>(c->d_hist + hoff[i], d_cum, ncomp, w.nEFx, s.nEF, s.fder,
-                                                                       s.dEF, scale, out_dev + ooff);
-        c->launches++;
-        ooff += (size_t)s.nEF * ncomp;
-    }
+    if (!per_block) finalize(1, out_dev);
     CK(cudaGetLastError());
     stage_collect(c);
     return 0;
+}
+
+extern "C" int wbgpu_static_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK_dev, const double* weight_dev,
+                                     const wbgpu_scan_spec* specs, int nspec, double* out_dev) {
+    return static_scan_impl(c, nblocks, dK_dev, weight_dev, specs, nspec, out_dev, false);
 }
 
 extern "C" int wbgpu_stage_times(const wbgpu_ctx* c, double* ms, int64_t* calls) {
@@ -1025,6 +1048,27 @@ extern "C" int wbgpu_static_scan(wbgpu_ctx* c, int nblocks, const double* dK, co
 }
 
 
+
+// per-K-block results (HOST pointers): out[nblocks][total], total = sum of wbgpu_spec_size over the specs
+extern "C" int wbgpu_static_scan_blocks(wbgpu_ctx* c, int nblocks, const double* dK, const wbgpu_scan_spec* specs, int nspec,
+                                        double* out) {
+    if (!c || !dK || !specs || !out) return set_err("wbgpu_static_scan_blocks: null pointer argument");
+    CK(cudaSetDevice(c->device));
+    size_t total = 0;
+    for (int i = 0; i < nspec; i++) {
+        int64_t sz = wbgpu_spec_size(&specs[i]);
+        if (sz < 0) return set_err("scan: unknown formula %d", specs[i].formula);
+        total += (size_t)sz;
+    }
+    const size_t nout = total * (size_t)std::max(nblocks, 0);
+    if (ensure(&c->d_dK, &c->dK_cap, sizeof(double) * 4 * (size_t)std::max(nblocks, 1))) return 1;
+    if (ensure(&c->d_out, &c->out_cap, sizeof(double) * std::max<size_t>(nout, 1))) return 1;
+    CK(cudaMemcpyAsync(c->d_dK, dK, sizeof(double) * 3 * nblocks, cudaMemcpyHostToDevice, c->stream));
+    if (static_scan_impl(c, nblocks, c->d_dK, nullptr, specs, nspec, c->d_out, true)) return 1;
+    CK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------ tetrahedron method
 extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* dK, const double* weight, const double* dK_cell,

@@ -77,6 +77,20 @@ class Engine:
             off += s.size
         return res
 
+    def scan_blocks(self, dK, specs):
+        """Per-K-block results: list (one per spec) of arrays `[nblocks, nEF, 3^rank]`."""
+        dK = as_f64(dK).reshape(-1, 3)
+        nb = dK.shape[0]
+        arr = (ScanSpec * len(specs))(*specs)
+        total = sum(s.size for s in specs)
+        out = np.zeros((nb, total))
+        check(self._L.wbgpu_static_scan_blocks(self._ctx, nb, dptr(dK), arr, len(specs), dptr(out)))
+        res, off = [], 0
+        for s in specs:
+            res.append(out[:, off:off + s.size].reshape((nb,) + s.shape).copy())
+            off += s.size
+        return res
+
     def scan_tetra(self, dK, weight, dK_cell, specs):
         """`scan()` with the tetrahedron method: `dK_cell` = Kpoint.dK_fullBZ = 1 / (NKdiv * NKFFT)."""
         dK = as_f64(dK).reshape(-1, 3)

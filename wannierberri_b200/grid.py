@@ -88,3 +88,50 @@ class Grid:
         dK = 1. / self.div
         shifts, factors = self.K_arrays()
         return [KpointBZ(K=s * self.FFT, dK=dK, NKFFT=self.FFT, factor=f) for s, f in zip(shifts, factors)]
+
+
+class KpointBZparallel:
+    """A K-point of the refinement loop with its cell of size dK (reference: grid/Kpoint.py:9-100, 104-184, without
+    the point-group star).  `K` is in units of 1/NKFFT of the reciprocal cell: `Kp_fullBZ = K / NKFFT` is the shift
+    of the FFT sub-grid."""
+
+    def __init__(self, K, dK, NKFFT, factor, refinement_level=0):
+        self.K = np.array(K, dtype=float)
+        self.dK = np.array(dK, dtype=float)
+        self.NKFFT = np.array(NKFFT)
+        self.factor = factor
+        self.refinement_level = refinement_level
+        self.result = None
+        self._max = None
+
+    @property
+    def Kp_fullBZ(self):
+        return self.K / self.NKFFT
+
+    @property
+    def dK_fullBZ(self):
+        return self.dK / self.NKFFT
+
+    @property
+    def was_evaluated_flag(self):
+        return self.result is not None
+
+    def set_result(self, res):
+        self.result = res
+        self._max = res.max
+
+    @property
+    def max(self):
+        return self._max * self.factor
+
+    def divide(self, ndiv):
+        """grid/Kpoint.py:146-176: ndiv[0] x ndiv[1] x ndiv[2] children tiling this point's cell; this point dies."""
+        ndiv = np.array(ndiv)
+        dK_adpt = self.dK / ndiv
+        adpt_shift = (-self.dK + dK_adpt) / 2.
+        newfac = self.factor / np.prod(ndiv)
+        children = [KpointBZparallel(self.K + adpt_shift + dK_adpt * np.array([x, y, z]), dK_adpt, self.NKFFT, newfac,
+                                     self.refinement_level + 1)
+                    for x in range(ndiv[0]) for y in range(ndiv[1]) for z in range(ndiv[2])]
+        self.factor = 0
+        return children

@@ -54,7 +54,10 @@ class EnergyResult:
 
     @property
     def max(self):
-        return np.array([np.abs(self.data).max(), np.linalg.norm(self.data)])
+        """[max |data|, norm, norm of the first difference along the energy axis] (energyresult.py:245-264):
+        the numbers by which adaptive refinement selects K-points."""
+        d = self.dataSmooth
+        return np.array([np.abs(d).max(), np.linalg.norm(d), np.linalg.norm(d[1:] - d[:-1])])
 
     def as_dict(self):
         """same keys as energyresult.py:224-239."""

@@ -45,10 +45,13 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
         device=None, write_files=False):
     """Integrate `calculators` over the k-grid.  Returns a `ResultDict` of `EnergyResult`.
 
-    Not implemented on the GPU path (raise, never fall back to a CPU loop): adaptive refinement,
-    restart files, symmetrisation of the result."""
+    Not implemented on the GPU path (raise, never fall back to a CPU loop): restart files, symmetrisation of the
+    result, adaptive refinement together with symmetry-reduced K-lists / tetrahedron / Kubo calculators."""
     if adpt_num_iter != 0:
-        raise NotImplementedError("adaptive refinement needs per-K-block results (SURVEY.md section 8(f), next-3)")
+        if use_irred_kpt:
+            raise NotImplementedError("adaptive refinement with symmetry-reduced K-lists is not implemented on the GPU path")
+        return _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac, fout_name, suffix, parallel,
+                             device, write_files, restart or allow_restart or dump_results, symmetrize, parameters_K)
     if restart or allow_restart or dump_results:
         raise NotImplementedError("restart / dump_results are not implemented on the GPU path")
     if symmetrize:
@@ -124,3 +127,99 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
     if write_files and rank == 0:
         res.savedata(prefix=fout_name, suffix=suffix, i_iter=0)
     return res
+
+
+def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac, fout_name, suffix, parallel, device,
+                  write_files, restart, symmetrize, parameters_K):
+    """The refinement loop of the reference (run_grid.py:303-387) on per-K-block results from the GPU
+    (`wbgpu_static_scan_blocks`): evaluate the new K-points, update the weighted sum, pick the `adpt_fac` points with
+    the largest contribution by every criterion of `ResultDict.max`, divide them `adpt_mesh`-fold, repeat."""
+    from .grid import KpointBZparallel
+    if restart:
+        raise NotImplementedError("restart / dump_results are not implemented on the GPU path")
+    if symmetrize:
+        raise NotImplementedError("symmetrize=True: apply system.pointgroup.symmetrize() of the reference to the result")
+    if parameters_K:
+        raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
+    system = as_system(system)
+    calcs = {}
+    for key, c in calculators.items():
+        if isinstance(c, _dyn.DynamicCalculator) or type(c).__name__ in _dyn._BY_NAME:
+            raise NotImplementedError("adaptive refinement of Kubo calculators is not implemented on the GPU path")
+        c = adapt_static(c)
+        if c.tetra:
+            raise NotImplementedError("adaptive refinement with tetra=True is not implemented on the GPU path")
+        calcs[key] = c
+    dist = _dist() if parallel else None
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    if device is None:
+        import torch
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+    NKFFT = np.array(grid.FFT, dtype=int)
+    shifts, factors = k_list_arrays(grid, False)
+    dK0 = 1. / np.array(grid.div, dtype=float)
+    K_list = [KpointBZparallel(s * NKFFT, dK0, NKFFT, f) for s, f in zip(shifts, factors)]
+    if adpt_num_iter < 0:  # run_grid.py:303-304
+        adpt_num_iter = -adpt_num_iter * np.prod(grid.div) / np.prod(adpt_mesh) / adpt_fac / 3
+    adpt_num_iter = int(round(adpt_num_iter))
+    adpt_mesh = np.array([adpt_mesh] * 3 if np.ndim(adpt_mesh) == 0 else adpt_mesh, dtype=int)
+    if np.max(adpt_mesh) <= 1:
+        adpt_num_iter = 0
+
+    specs, owner = [], []
+    for key, c in calcs.items():
+        for s in c.specs():
+            if getattr(system, "force_internal_terms_only", False):
+                s.external_terms = 0
+            specs.append(s)
+            owner.append(key)
+    engine = engine_for(system, device)
+    engine.plan(NKFFT, {int(s.formula) for s in specs} | {_lib.IDENTITY}, external_terms=any(s.external_terms for s in specs))
+
+    result_all = None
+    factors_old = None
+    for i_iter in range(adpt_num_iter + 1):
+        new = [i for i, K in enumerate(K_list) if not K.was_evaluated_flag]
+        # the new K-points are sharded over the ranks; every rank then holds all per-K-point results
+        lo, hi = shard_bounds(len(new), rank, world)
+        dK_new = np.array([K_list[i].Kp_fullBZ for i in new], dtype=float).reshape(-1, 3)
+        mine = engine.scan_blocks(dK_new[lo:hi], specs) if hi > lo else [np.zeros((0,) + s.shape) for s in specs]
+        if dist and world > 1:
+            import torch
+            dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            full = []
+            for a, s in zip(mine, specs):
+                buf = np.zeros((len(new),) + s.shape)
+                buf[lo:hi] = a
+                t = torch.from_numpy(buf).to(dev)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)   # disjoint slices: a gather written as a sum
+                full.append(t.cpu().numpy())
+            mine = full
+        result_sum_iter = None
+        for j, i in enumerate(new):
+            res = ResultDict({key: c.result([a[j] for a, o in zip(mine, owner) if o == key], system.cell_volume)
+                              for key, c in calcs.items()})
+            K_list[i].set_result(res)
+            contrib = res * K_list[i].factor
+            result_sum_iter = contrib if result_sum_iter is None else result_sum_iter + contrib
+        fac_now = np.array([K.factor for K in K_list])
+        if result_all is None:
+            result_all = result_sum_iter
+        else:  # run_grid.py:352-360: the points divided in the previous iteration lost their weight
+            diff = fac_now[:len(factors_old)] - factors_old
+            if result_sum_iter is not None:
+                result_all = result_all + result_sum_iter
+            for i, d in enumerate(diff):
+                if abs(d) > 1.e-8:
+                    result_all = result_all + K_list[i].result * d
+        factors_old = fac_now
+        if write_files and rank == 0:
+            result_all.savedata(prefix=fout_name, suffix=suffix, i_iter=i_iter)
+        if i_iter >= adpt_num_iter:
+            break
+        Kmax = np.array([K.max for K in K_list]).T
+        select_points = set().union(*(np.argsort(Km)[-adpt_fac:] for Km in Kmax))
+        for iK in select_points:
+            K_list += K_list[iK].divide(adpt_mesh)
+    return result_all
