@@ -20,8 +20,8 @@ class OracleEngine:
     """Test double with the interface of wannierberri_b200.Engine; shards are evaluated by the oracle."""
     FORMULA = {_lib.IDENTITY: orc.Identity, _lib.OMEGA: orc.Omega}
 
-    def __init__(self):
-        self.osys = orc.OracleSystem.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+    def __init__(self, osys=None):
+        self.osys = osys if osys is not None else orc.OracleSystem.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
 
     def plan(self, NKFFT, formulae, external_terms=True, max_kpoints_per_launch=0):
         self.NKFFT = np.array(NKFFT)
@@ -34,6 +34,20 @@ class OracleEngine:
                 Ef = np.linspace(s.Ef_first, s.Ef_last, s.nEF)
                 out[i] += w * orc.static_scan(data, self.FORMULA[s.formula], s.fder, Ef, degen_thresh=s.degen_thresh,
                                               degen_Kramers=bool(s.degen_Kramers), constant_factor=s.factor)
+        return out
+
+    def scan_blocks(self, dK, specs):
+        return [np.array([self.scan([d], [1.], [s])[0] for d in dK]).reshape((len(dK),) + s.shape) for s in specs]
+
+    def kubo_scan(self, dK, weight, spec, Efermi, omega):
+        kind = {_lib.KUBO_OPTCOND: "opt_conductivity", _lib.KUBO_JDOS: "jdos"}[int(spec.kind)]
+        out = 0
+        for d, w in zip(dK, weight):
+            data = orc.OracleDataK(self.osys, d, self.NKFFT)
+            out = out + w * orc.kubo_scan(data, kind, Efermi, omega, smr_fixed_width=spec.smr_fixed_width,
+                                          smr_type="Lorentzian" if spec.smr_type == 0 else "Gaussian",
+                                          degen_thresh=spec.degen_thresh, degen_Kramers=bool(spec.degen_Kramers),
+                                          external_terms=bool(spec.external_terms), constant_factor=spec.factor)
         return out
 
 
@@ -50,6 +64,25 @@ def main():
     res = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), calcs, parallel=True, device=0)
     for q in calcs:
         err = np.abs(res.results[q].data - g["upstream_golden_" + q]).max() / np.abs(g["upstream_golden_" + q]).max()
+        assert err < 1e-8, (q, err)
+    # Kubo scan sharded over the ranks (complex result through the float64 all-reduce)
+    gk = np.load(os.path.join(GOLDEN, "golden_fe_kubo.npz"))
+    oc = wb.calculators.dynamic.OpticalConductivity(Efermi=gk["ref_Efermi"], omega=gk["ref_omega"], smr_fixed_width=0.20,
+                                                    smr_type="Gaussian")
+    res = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), dict(oc=oc), parallel=True, device=0)
+    ref = gk["upstream_golden_opt_conductivity"]
+    assert np.abs(res.results["oc"].data - ref).max() / np.abs(ref).max() < 1e-8
+    # adaptive refinement: the new K-points of every iteration are sharded, all ranks take the same decisions
+    ga = np.load(os.path.join(GOLDEN, "golden_synth_adpt.npz"))
+    sysg = wb.synthetic_system(6, rmax=1, seed=4242)
+    eng2 = OracleEngine(orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
+                                         {k: sysg.get_R_mat(k) for k in ("Ham", "AA")}))
+    sys.modules["wannierberri_b200.run"].engine_for = lambda system, device=0: eng2
+    calcs = dict(ahc=st.AHC(Efermi=ga["Efermi"]), dos=st.DOS(Efermi=ga["Efermi"]))
+    res = wb.run(sysg, wb.Grid(sysg, NKdiv=[2, 2, 2], NKFFT=[3, 3, 3]), calcs, adpt_num_iter=1, adpt_fac=2, adpt_mesh=2,
+                 parallel=True, device=0)
+    for q in calcs:
+        err = np.abs(res.results[q].data - ga["iter1_" + q]).max() / np.abs(ga["iter1_" + q]).max()
         assert err < 1e-8, (q, err)
     dist.barrier()
     if rank == 0:
