@@ -8,7 +8,7 @@ fe = wb.System_R.from_npz("tests/golden/fe_system.npz")
 Ef = np.linspace(12.0, 22.0, 2000)
 for case, calcs in (("ahc_dos", dict(ahc=st.AHC(Efermi=Ef), dos=st.DOS(Efermi=Ef))), ("ahc_morb", dict(ahc=st.AHC(Efermi=Ef), morb=st.Morb(Efermi=Ef)))):
     specs = [s for c in calcs.values() for s in c.specs()]
-    for opts in (dict(rotate_trim=0), dict(rotate_trim=1)):
+    for opts in (dict(rot_r2=-1), dict(rot_r2=0), dict(rot_r2=1), dict(rot_r2=2), dict(rot_r2=3)):
         eng = wb.Engine(fe, device=0)
         for k, v in opts.items(): eng.set_option(k, v)
         eng.plan([20, 20, 20], [s.formula for s in specs], external_terms=True)

@@ -78,6 +78,7 @@ struct WbMmaPlan {
     int slot[6];     // >= 0: full rotation into Cs slots slot..slot+2 ; < 0: diagonal only, kind = -1 - slot
     int soff[6];     // staging slot of the item (offset in doubles from the shared-memory base); every item owns
                      // one, refilled for the NEXT k-point
+    int r1[6], r2[6]; // warp -> tile rotation of step 1 / step 2 of the item (balances the warps between barriers)
     int nstage;      // staging doubles in total
     int nslot;       // Cs matrices
 };
@@ -119,6 +120,7 @@ inline bool wb_mma_make_plan(const WbLayout& L, int mask, int external, WbMmaPla
         so += P->herm[i] ? 6 * WbMma<NW>::NTRI : WbMma<NW>::STAGE;
         so = (so + 1) / 2 * 2;
     }
+    for (int i = 0; i < n; i++) { P->r1[i] = P->herm[i] ? 1 : 0; P->r2[i] = P->herm[i] ? 3 : 2; }
     P->nstage = so - so0;
     P->nitem = n;
     P->nslot = slot;
@@ -264,7 +266,7 @@ wb_events_mma_kernel(const cplx* __restrict__ rec, WbLayout L, WbMmaPlan P, long
             // ---- step 1: Y = X U on stacked row tiles mt = w1, w1 + 4, ...  The warp -> tile map is rotated from
             // phase to phase so that the warp with one tile less is a different one each time (the four tensor
             // pipes of the SM, shared with the co-resident CTA, stay evenly loaded).
-            const int w1 = (warp + (herm ? 1 : 0)) & 3, w2 = (warp + (herm ? 3 : 2)) & 3;
+            const int w1 = (warp + P.r1[it]) & 3, w2 = (warp + P.r2[it]) & 3;
             auto step1 = [&](auto thi_c) {
                 constexpr int THI = decltype(thi_c)::value;   // column tiles of U that are multiplied
 #pragma unroll

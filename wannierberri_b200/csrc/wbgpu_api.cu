@@ -109,6 +109,7 @@ struct wbgpu_ctx {
     int rotate_method = 0;  // 0 = automatic, 1 = generic shared-memory DFMA kernel, 2 = DMMA kernel (Omega, nw <= 20),
                             // 3 = compile-time-NW DMMA kernel, 4 = batched DMMA GEMM to global memory + formula kernel
     int smem_optin = 0;
+    int rot_r2 = -1;        // experiment: override of the step-2 warp rotation of the fused rotation kernel
     int rotate_trim = 1;    // 1 = form only the needed columns of the rotated matrices when they are hermitian
     int dh_packed = 1;      // 1 = pack d_a H as a triangle when it is hermitian in R-space, 0 = never
     std::vector<int> h_iRvec;
@@ -243,6 +244,7 @@ extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "eig_method")) { c->eig_method = (int)value; return 0; }
     if (!strcmp(name, "rotate_method")) { c->rotate_method = (int)value; return 0; }
     if (!strcmp(name, "fourier_method")) { c->fourier_method = (int)value; return 0; }
+    if (!strcmp(name, "rot_r2")) { c->rot_r2 = (int)value; return 0; }
     if (!strcmp(name, "rotate_trim")) { c->rotate_trim = (int)value; return 0; }
     if (!strcmp(name, "dh_packed")) { c->dh_packed = (int)value; c->planned = false; return 0; }
     if (!strcmp(name, "timing")) {
@@ -732,6 +734,10 @@ static int launch_mma_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
 #define WB_MMA_CASE(NWC)                                                                            \
     case NWC:                                                                                       \
         if (!wb_mma_make_plan<NWC>(c->L, G.ev.mask, G.ev.external_terms, &P)) return -1;            \
+        /* with trimmed columns step 2 has 5 stacked tiles (warp w2 == 0 carries two): give that warp the single  \
+           step-1 tile of the NEXT item (w1 == 3), they run between the same pair of barriers */           \
+        if (c->L.dH_herm && c->rotate_trim) for (int i = 0; i < P.nitem; i++) P.r2[i] = 2;              \
+        for (int i = 0; i < P.nitem; i++) if (c->rot_r2 >= 0) P.r2[i] = c->rot_r2;                  \
         return (c->L.dH_herm && c->rotate_trim) ? launch_mma_t<NWC, true>(c, G, nk, P) : launch_mma_t<NWC, false>(c, G, nk, P);
     switch (c->nw) {
         WB_MMA_CASE(18)
