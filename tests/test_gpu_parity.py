@@ -398,6 +398,60 @@ def test_tetra_run_vs_reference(wb, fe):
     assert relerr(res.results["plain_ahc"].data, g4["upstream_golden_ahc"]) < RTOL
 
 
+@pytest.mark.parametrize("NKFFT,nEF", [([1, 1, 1], 5), ([5, 3, 7], 40), ([2, 9, 1], 1), ([3, 3, 3], 9001)])
+def test_odd_grid_shapes(wb, fe, fe_orc, orc, NKFFT, nEF):
+    """Edge cases of the grid / Fermi axes: a single k-point per K-block, unequal odd FFT grids (R-vectors alias onto
+    them, fourier/fft.py:177), one Fermi level (dEF = 0.001, static.py:55), a Fermi axis whose histogram does not
+    fit shared memory; and an empty K-block list."""
+    dK = np.array([0.013, 0.021, 0.007])
+    Ef = np.linspace(15., 19., nEF) if nEF > 1 else np.array([17.3])
+    st = wb.calculators.static
+    grid = wb.Grid(fe, NKdiv=[1, 1, 1], NKFFT=NKFFT)
+    data = wb.Data_K_R(fe, dK=dK, grid=grid)
+    odata = orc.OracleDataK(fe_orc, dK, NKFFT)
+    names = ("AHC", "DOS", "CumDOS") if nEF < 1000 else ("AHC", "DOS")
+    for name in names:
+        got = getattr(st, name)(Efermi=Ef)(data).data
+        ref = orc.CALCULATORS[name](odata, Ef)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-300), name
+    eng = wb.Engine(fe)
+    specs = st.AHC(Efermi=Ef).specs()
+    eng.plan(NKFFT, [s.formula for s in specs])
+    empty = eng.scan(np.zeros((0, 3)), np.zeros(0), specs)
+    assert empty[0].shape == specs[0].shape and not empty[0].any()
+
+
+def test_full_size_properties(wb, fe):
+    """BASELINE-size launches (K-blocks of 20^3 from the 400^3 grid, 2000 Fermi levels, 16 blocks = 128 000 k-points
+    per call) through size-independent properties: the band-counting sum rule, linearity in the K-block weights,
+    additivity over shards, and agreement of the fused nw = 18 rotation kernel with the size-generic path."""
+    st = wb.calculators.static
+    Ef = np.linspace(5.0, 50.0, 2000)   # brackets the whole band structure (9.3 .. 47 eV)
+    grid = wb.Grid(fe, NKdiv=[20, 20, 20], NKFFT=[20, 20, 20])
+    shifts, factors = grid.K_arrays()
+    sel = slice(1000, 1016)
+    specs = st.CumDOS(Efermi=Ef).specs() + st.AHC(Efermi=Ef).specs()
+    eng = wb.Engine(fe)
+    eng.plan([20, 20, 20], [s.formula for s in specs])
+    w = np.full(16, 1. / 16)
+    cum, ahc = eng.scan(shifts[sel], w, specs)
+    # every band is counted once per k-point: CumDOS * cell_volume = 18 above the top band, 0 below the bottom
+    assert abs(cum[-1] * fe.cell_volume - 18.) < 1e-9 and cum[0] == 0.
+    assert np.all(np.diff(cum) >= -1e-12)
+    # the Berry curvature summed over ALL bands vanishes identically at every k-point
+    assert np.abs(ahc[-1]).max() < 1e-9 * np.abs(ahc).max()
+    # linearity / additivity
+    cum2, ahc2 = eng.scan(shifts[sel], 3. * w, specs)
+    assert relerr(ahc2, 3. * ahc) < 1e-12 and relerr(cum2, 3. * cum) < 1e-12
+    parts = [eng.scan(shifts[1000 + 4 * i:1004 + 4 * i], w[:4], specs) for i in range(4)]
+    assert relerr(sum(p[1] for p in parts), ahc) < 1e-11
+    # fused kernel vs batched DMMA GEMM + formula kernel on the same 128 000 k-points
+    eng.set_option("rotate_method", 4)
+    ahc_g = eng.scan(shifts[sel], w, specs)[1]
+    assert relerr(ahc_g, ahc) < 1e-10
+
+
 def test_adaptive_refinement(wb, fe, orc):
     """run(adpt_num_iter > 0): per-K-block results from the GPU + the reference's refinement loop, against the
     reference's own run() on a model without symmetry (fixture of tests/golden/make_golden_adpt.py); per-K-block
