@@ -452,6 +452,36 @@ def test_full_size_properties(wb, fe):
     assert relerr(ahc_g, ahc) < 1e-10
 
 
+def test_run_symmetric_vs_upstream_golden(wb):
+    """The reference's default run mode (use_irred_kpt=True, symmetrize=True): symmetry-reduced K-list, results
+    symmetrised over the 16 operations of the magnetic point group of bcc Fe -- against the reference's own golden
+    files Fe_W90_sym-{ahc,dos,cumdos,Morb,spin,opt_conductivity}_iter-0000.npz (tests/test_run.py:432-459) and the
+    other quantities of the fixture (tests/golden/make_golden_sym.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_sym.npz"))
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"), pointgroup=["C4z", "C2x*TimeReversal", "Inversion"])
+    Ef = g["Efermi"]
+    st, dyn = wb.calculators.static, wb.calculators.dynamic
+    calcs = dict(ahc=st.AHC(Efermi=Ef), dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef), Morb=st.Morb(Efermi=Ef),
+                 spin=st.Spin(Efermi=Ef), berry_dipole_fsurf=st.BerryDipole_FermiSurf(Efermi=Ef),
+                 gme_orb_fsurf=st.GME_orb_FermiSurf(Efermi=Ef), gme_spin_fsurf=st.GME_spin_FermiSurf(Efermi=Ef),
+                 ahc_tetra=st.AHC(Efermi=Ef, tetra=True), dos_tetra=st.DOS(Efermi=Ef, tetra=True),
+                 opt_conductivity=dyn.OpticalConductivity(Efermi=g["opt_Efermi"], omega=g["opt_omega"],
+                                                          smr_fixed_width=0.20, smr_type="Gaussian"))
+    res = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), calcs, use_irred_kpt=True, symmetrize=True)
+    for q in ("ahc", "dos", "cumdos", "Morb", "spin", "opt_conductivity"):
+        assert relerr(res.results[q].data, g["upstream_golden_" + q]) < RTOL, q
+    for q in calcs:
+        assert res.results[q].data.shape == g[q].shape
+        if np.abs(g[q]).max() < 1e-10:   # forbidden by symmetry (inversion: no Berry dipole / gyrotropy): noise in both
+            assert np.abs(res.results[q].data).max() < 1e-10, q
+        else:
+            assert relerr(res.results[q].data, g[q]) < (1e-6 if q == "dos_tetra" else RTOL), q
+    # symmetrising a full-grid run leaves only what the magnetic point group allows: sigma_z for the AHC
+    full = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), dict(ahc=calcs["ahc"]), use_irred_kpt=False, symmetrize=True)
+    a = full.results["ahc"].data
+    assert np.abs(a[:, :2]).max() < 1e-12 * np.abs(a[:, 2]).max()
+
+
 def test_adaptive_refinement(wb, fe, orc):
     """run(adpt_num_iter > 0): per-K-block results from the GPU + the reference's refinement loop, against the
     reference's own run() on a model without symmetry (fixture of tests/golden/make_golden_adpt.py); per-K-block

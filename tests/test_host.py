@@ -125,3 +125,28 @@ def test_two_rank_gloo_run():
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
     assert "PARITY OK" in outs[0]
+
+
+FE_POINTGROUP = ["C4z", "C2x*TimeReversal", "Inversion"]   # tests/common_systems.py:186 of the reference
+
+
+def test_symmetry_reduced_k_list_bit_exact():
+    """Grid.get_K_list(use_symmetry=True) (grid/grid.py:149-189): the irreducible K-points and their absorbed weights
+    equal the reference's, in the reference's order; the group has 16 operations and averages tensors like the
+    reference (point_symmetry.py:104-119, 337-338)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_sym.npz"))
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"), pointgroup=FE_POINTGROUP)
+    assert fe.pointgroup.size == 16
+    shifts, factors = wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]).K_arrays(use_symmetry=True)
+    assert np.array_equal(shifts, g["K_list_Kp_fullBZ"])
+    assert np.array_equal(factors, g["K_list_factor"])
+    assert abs(factors.sum() - 1.) < 1e-15
+    # larger grid: weights still add up, fewer points
+    s2, f2 = wb.Grid(fe, NKdiv=[6, 6, 6], NKFFT=[2, 2, 2]).K_arrays(use_symmetry=True)
+    assert abs(f2.sum() - 1.) < 1e-13 and len(f2) < 6 ** 3 / 4
+    # symmetrisation: an axial vector along z (odd under TR, even under inversion) survives, x / y components vanish
+    from wannierberri_b200.result import EnergyResult
+    r = EnergyResult(np.arange(3.), np.tile(np.array([1., 2., 3.]), (3, 1)), transformTR="odd", transformInv="ident")
+    assert np.allclose(r.symmetrized(fe.pointgroup).data, np.tile(np.array([0., 0., 3.]), (3, 1)), atol=1e-14)
+    with pytest.raises(ValueError):
+        wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"), pointgroup=["C3z"])   # not a symmetry of the bcc cell

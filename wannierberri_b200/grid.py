@@ -1,6 +1,6 @@
 """k-grid: NK = NKdiv x NKFFT, the K-block list and the FFT sub-grid (bit-exact restatement of
-grid/grid.py:68-75,149-172,196-266 and grid/Kpoint.py:75-77 of the reference, without symmetry
-reduction -- symmetry-reduced K-lists built by the reference's own Grid are accepted by `run()`)."""
+grid/grid.py:68-75,149-172,196-266 and grid/Kpoint.py:75-77 of the reference; symmetry-reduced
+K-lists follow grid/grid.py:169-189 with the star of symmetry.py)."""
 import warnings
 
 import numpy as np
@@ -62,6 +62,7 @@ class Grid:
             warnings.warn(f" the requested k-grid {NK} was adjusted to {NKFFT * NKdiv}. ")
         self.div = NKdiv
         self.FFT = NKFFT
+        self.pointgroup = getattr(system, "pointgroup", None)
 
     @property
     def dense(self):
@@ -73,20 +74,38 @@ class Grid:
         ix, iy, iz = np.meshgrid(np.arange(self.FFT[0]), np.arange(self.FFT[1]), np.arange(self.FFT[2]), indexing="ij")
         return np.stack([ix.ravel() * dkx, iy.ravel() * dky, iz.ravel() * dkz], axis=1)
 
-    def K_arrays(self):
-        """(Kp_fullBZ[nK,3], factor[nK]) of the full K-list, x-major / z-fastest, same floating
-        point operations as the reference: K = [x,y,z] * (1./div); Kp_fullBZ = K / FFT."""
+    def K_arrays(self, use_symmetry=False):
+        """(Kp_fullBZ[nK,3], factor[nK]) of the K-list, x-major / z-fastest, same floating point operations as the
+        reference: K = [x,y,z] * (1./div); Kp_fullBZ = K / FFT.  With `use_symmetry` only one K-point of every star
+        of the point group is kept and it absorbs the weights of the others, in the reference's order
+        (grid/grid.py:169-189: the first point met in the z-outer / x-inner sweep survives)."""
         dK = 1. / self.div
         factor = 1. / np.prod(self.div)
         x, y, z = np.meshgrid(np.arange(self.div[0]), np.arange(self.div[1]), np.arange(self.div[2]), indexing="ij")
         K = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1) * dK[None, :]
-        return K / self.FFT[None, :], np.full(K.shape[0], factor)
+        factors = np.full(K.shape[0], factor)
+        if use_symmetry and self.pointgroup is not None:
+            from .symmetry import star
+            div = np.array(self.div)
+            alive = np.ones(tuple(div), dtype=bool)
+            fac = np.full(tuple(div), factor)
+            for iz in range(div[2]):
+                for iy in range(div[1]):
+                    for ix in range(div[0]):
+                        if not alive[ix, iy, iz]:
+                            continue
+                        st = np.array(np.round(star(self.pointgroup, np.array([ix, iy, iz]) * dK) * div), dtype=int) % div
+                        for k in map(tuple, st):
+                            if k != (ix, iy, iz) and alive[k]:
+                                fac[ix, iy, iz] += fac[k]
+                                alive[k] = False
+            keep = alive.ravel()
+            K, factors = K[keep], fac.ravel()[keep]
+        return K / self.FFT[None, :], factors
 
     def get_K_list(self, use_symmetry=False, k_batch=None):
-        if use_symmetry:
-            raise NotImplementedError("symmetry-reduced K-lists are built by the reference's Grid; pass that grid to run()")
         dK = 1. / self.div
-        shifts, factors = self.K_arrays()
+        shifts, factors = self.K_arrays(use_symmetry=use_symmetry)
         return [KpointBZ(K=s * self.FFT, dK=dK, NKFFT=self.FFT, factor=f) for s, f in zip(shifts, factors)]
 
 

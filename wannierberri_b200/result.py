@@ -48,6 +48,20 @@ class EnergyResult:
         return EnergyResult(self.Energies, self.data * other.reshape(shape), self.transformTR, self.transformInv,
                             self.rank, self.E_titles, self.comment, self.save_mode, self.smoothers)
 
+    def transform(self, sym):
+        """energyresult.py:266-278: the result seen after the point-group operation `sym`."""
+        return EnergyResult(self.Energies, sym.transform_tensor(self.data, self.rank, self.transformTR, self.transformInv),
+                            self.transformTR, self.transformInv, self.rank, self.E_titles, self.comment, self.save_mode,
+                            self.smoothers)
+
+    def symmetrized(self, pointgroup):
+        """PointGroup.symmetrize(result) (point_symmetry.py:337-338): mean over the group."""
+        from .symmetry import symmetrize_tensor
+        return EnergyResult(self.Energies,
+                            symmetrize_tensor(pointgroup, self.data, self.rank, self.transformTR, self.transformInv),
+                            self.transformTR, self.transformInv, self.rank, self.E_titles, self.comment, self.save_mode,
+                            self.smoothers)
+
     @property
     def dataSmooth(self):
         return self.data

@@ -31,8 +31,8 @@ def shard_bounds(n, rank, world):
 
 def k_list_arrays(grid, use_irred_kpt):
     """(Kp_fullBZ[nK,3], factor[nK]) from this package's Grid or from the reference's."""
-    if hasattr(grid, "K_arrays") and not use_irred_kpt:
-        return grid.K_arrays()
+    if hasattr(grid, "K_arrays"):
+        return grid.K_arrays(use_symmetry=use_irred_kpt)
     K_list = grid.get_K_list(use_symmetry=use_irred_kpt)
     return (np.array([K.Kp_fullBZ for K in K_list], dtype=float).reshape(-1, 3),
             np.array([K.factor for K in K_list], dtype=float))
@@ -54,11 +54,12 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
                              device, write_files, restart or allow_restart or dump_results, symmetrize, parameters_K)
     if restart or allow_restart or dump_results:
         raise NotImplementedError("restart / dump_results are not implemented on the GPU path")
-    if symmetrize:
-        raise NotImplementedError("symmetrize=True: apply system.pointgroup.symmetrize() of the reference to the result")
     if parameters_K:
         raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
     system = as_system(system)
+    pointgroup = getattr(system, "pointgroup", None)
+    if (symmetrize or use_irred_kpt) and pointgroup is None:
+        raise ValueError("use_irred_kpt / symmetrize need system.pointgroup (System_R.set_pointgroup)")
     calcs, dyn_calcs = {}, {}
     for key, c in calculators.items():
         dynamic = isinstance(c, _dyn.DynamicCalculator) or type(c).__name__ in _dyn._BY_NAME
@@ -123,6 +124,8 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
         results[key] = c.result(mine, system.cell_volume)
     for (key, c), a, raw in zip(dyn_calcs.items(), arrays[nstatic:], karrays):
         results[key] = c.result(a.view(raw.dtype).reshape(raw.shape))
+    if symmetrize:  # linear: applied once to the weighted sum instead of per K-point (run_grid.py:258-265)
+        results = {key: r.symmetrized(pointgroup) for key, r in results.items()}
     res = ResultDict(results)
     if write_files and rank == 0:
         res.savedata(prefix=fout_name, suffix=suffix, i_iter=0)

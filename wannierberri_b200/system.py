@@ -32,6 +32,7 @@ class System_R:
         # R + t_j - t_i   (rvectors.py:355-369)
         self.rvec = _Rvec(iRvec, cR[:, None, None, :] + (t[None, :, :] - t[:, None, :])[None])
         self._XX_R = {}
+        self.pointgroup = None
 
     # --- system_R.py:106-175
     def set_R_mat(self, key, value, reset=False):
@@ -49,6 +50,15 @@ class System_R:
         except KeyError:
             raise ValueError(f"The real-space matrix elements '{key}' are not set in the system")
 
+    def set_pointgroup(self, symmetry_gen=(), spacegroup=None):
+        """system.py:264-300 (generators only): symmetries of the system, used for symmetry-reduced K-lists and for
+        the symmetrisation of results.  Operations by name ("C4z", "C2x*TimeReversal", "Inversion", ...) or as
+        `wannierberri_b200.symmetry.PointSymmetry`."""
+        if spacegroup is not None:
+            raise NotImplementedError("space groups from irrep are not available on the GPU path; give the generators")
+        from .symmetry import PointGroup
+        self.pointgroup = PointGroup(symmetry_gen, real_lattice=self.real_lattice)
+
     def has_R_mat(self, key):
         return key in self._XX_R
 
@@ -62,10 +72,12 @@ class System_R:
         return 2 * np.abs(self.rvec.iRvec).max(axis=0) + 1
 
     @classmethod
-    def from_npz(cls, path):
+    def from_npz(cls, path, pointgroup=None):
         """Load the compact fixture format written by tests/golden/make_golden.py."""
         f = np.load(path)
         s = cls(f["real_lattice"], f["iRvec"], f["wannier_centers_cart"])
+        if pointgroup is not None:
+            s.set_pointgroup(pointgroup)
         for k in f.files:
             if k.startswith("XX_R_"):
                 s.set_R_mat(k[5:], f[k])
