@@ -482,6 +482,26 @@ def test_run_symmetric_vs_upstream_golden(wb):
     assert np.abs(a[:, :2]).max() < 1e-12 * np.abs(a[:, 2]).max()
 
 
+def test_adaptive_refinement_symmetric(wb):
+    """Refinement on the symmetry-reduced K-list (the reference's test_Fe_sym_refine, tests/test_run.py:557-578):
+    per-K-point results symmetrised before the selection, children of a divided K-point merged with their symmetry
+    equivalents (grid/Kpoint.py:146-216).  Iteration 1 against the reference's own golden files
+    Fe_W90_sym-*_iter-0001.npz, iterations 2 and 3 against the live reference run of make_golden_sym_adpt.py."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_sym_adpt.npz"))
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"), pointgroup=["C4z", "C2x*TimeReversal", "Inversion"])
+    Ef = g["Efermi"]
+    st = wb.calculators.static
+    for n_iter in (1, 2, 3):
+        calcs = dict(ahc=st.AHC(Efermi=Ef), dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef), Morb=st.Morb(Efermi=Ef),
+                     spin=st.Spin(Efermi=Ef))
+        res = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), calcs, use_irred_kpt=True, symmetrize=True,
+                     adpt_num_iter=n_iter)
+        for q in calcs:
+            assert relerr(res.results[q].data, g[f"iter{n_iter}_{q}"]) < RTOL, (n_iter, q)
+            if n_iter == 1:
+                assert relerr(res.results[q].data, g[f"upstream_golden_iter1_{q}"]) < RTOL, q
+
+
 def test_adaptive_refinement(wb, fe, orc):
     """run(adpt_num_iter > 0): per-K-block results from the GPU + the reference's refinement loop, against the
     reference's own run() on a model without symmetry (fixture of tests/golden/make_golden_adpt.py); per-K-block

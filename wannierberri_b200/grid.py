@@ -110,18 +110,20 @@ class Grid:
 
 
 class KpointBZparallel:
-    """A K-point of the refinement loop with its cell of size dK (reference: grid/Kpoint.py:9-100, 104-184, without
-    the point-group star).  `K` is in units of 1/NKFFT of the reciprocal cell: `Kp_fullBZ = K / NKFFT` is the shift
-    of the FFT sub-grid."""
+    """A K-point of the refinement loop with its cell of size dK (reference: grid/Kpoint.py:9-100, 104-184).
+    `K` is in units of 1/NKFFT of the reciprocal cell: `Kp_fullBZ = K / NKFFT` is the shift of the FFT sub-grid."""
 
-    def __init__(self, K, dK, NKFFT, factor, refinement_level=0):
+    def __init__(self, K, dK, NKFFT, factor, refinement_level=0, pointgroup=None):
         self.K = np.array(K, dtype=float)
         self.dK = np.array(dK, dtype=float)
         self.NKFFT = np.array(NKFFT)
         self.factor = factor
         self.refinement_level = refinement_level
+        self.pointgroup = pointgroup
         self.result = None
         self._max = None
+        self._star = None
+        self._distGamma = None
 
     @property
     def Kp_fullBZ(self):
@@ -143,14 +145,80 @@ class KpointBZparallel:
     def max(self):
         return self._max * self.factor
 
-    def divide(self, ndiv):
+    @property
+    def star(self):  # grid/Kpoint.py:115-120
+        if self._star is None:
+            if self.pointgroup is None:
+                self._star = np.array([self.K])
+            else:
+                from .symmetry import star
+                self._star = star(self.pointgroup, self.K)
+        return self._star
+
+    @property
+    def distGamma(self):  # grid/Kpoint.py:178-182
+        if self._distGamma is None:
+            sh = np.arange(-3, 4)
+            corners = np.array([[x, y, z] for x in sh for y in sh for z in sh])
+            self._distGamma = np.linalg.norm(((self.K % 1)[None, :] - corners).dot(self.pointgroup.recip_lattice), axis=1).min()
+        return self._distGamma
+
+    def equiv(self, other):  # grid/Kpoint.py:137-144
+        from .symmetry import SYMMETRY_PRECISION
+        if self.refinement_level != other.refinement_level:
+            return False
+        dif = self.star[:, None, :] - other.star[None, :, :]
+        return bool(np.linalg.norm((dif - np.round(dif)), axis=2).min() < SYMMETRY_PRECISION)
+
+    def absorb(self, other):  # grid/Kpoint.py:125-135
+        if other is None:
+            return
+        if other.was_evaluated_flag:
+            if self.was_evaluated_flag:
+                raise RuntimeError("combining two K-points with calculated result should not happen")
+            self.set_result(other.result)
+        self.factor += other.factor
+
+    def divide(self, ndiv, periodic=(True, True, True), use_symmetry=False):
         """grid/Kpoint.py:146-176: ndiv[0] x ndiv[1] x ndiv[2] children tiling this point's cell; this point dies."""
         ndiv = np.array(ndiv)
+        ndiv[np.logical_not(np.array(periodic, dtype=bool))] = 1
         dK_adpt = self.dK / ndiv
         adpt_shift = (-self.dK + dK_adpt) / 2.
         newfac = self.factor / np.prod(ndiv)
         children = [KpointBZparallel(self.K + adpt_shift + dK_adpt * np.array([x, y, z]), dK_adpt, self.NKFFT, newfac,
-                                     self.refinement_level + 1)
+                                     self.refinement_level + 1, self.pointgroup)
                     for x in range(ndiv[0]) for y in range(ndiv[1]) for z in range(ndiv[2])]
         self.factor = 0
+        if use_symmetry and self.pointgroup is not None:
+            exclude_equiv_points(children)
         return children
+
+
+def exclude_equiv_points(K_list, new_points=None):
+    """grid/Kpoint.py:185-216: among K-points at the same distance from Gamma, a later point that is symmetry-
+    equivalent to an earlier one is absorbed by it (only pairs involving a new point are examined)."""
+    n = len(K_list)
+    if new_points is None:
+        new_points = n
+    length = np.array([K.distGamma for K in K_list])
+    order = np.argsort(length)
+    length = length[order]
+    wall = [0] + list(np.where(length[1:] - length[:-1] > 1e-4)[0] + 1) + [len(K_list)]
+    exclude = []
+    for start, end in zip(wall[:-1], wall[1:]):
+        for l in range(start, end):
+            i = order[l]
+            if i not in exclude:
+                for m in range(start, end):
+                    j = order[m]
+                    if i >= j:
+                        continue
+                    if i < n - new_points and j < n - new_points:
+                        continue
+                    if j not in exclude:
+                        if K_list[i].equiv(K_list[j]):
+                            exclude.append(j)
+                            K_list[i].absorb(K_list[j])
+    for i in sorted(exclude)[-1::-1]:
+        del K_list[i]

@@ -48,10 +48,9 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
     Not implemented on the GPU path (raise, never fall back to a CPU loop): restart files, symmetrisation of the
     result, adaptive refinement together with symmetry-reduced K-lists / tetrahedron / Kubo calculators."""
     if adpt_num_iter != 0:
-        if use_irred_kpt:
-            raise NotImplementedError("adaptive refinement with symmetry-reduced K-lists is not implemented on the GPU path")
         return _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac, fout_name, suffix, parallel,
-                             device, write_files, restart or allow_restart or dump_results, symmetrize, parameters_K)
+                             device, write_files, restart or allow_restart or dump_results, symmetrize, use_irred_kpt,
+                             parameters_K)
     if restart or allow_restart or dump_results:
         raise NotImplementedError("restart / dump_results are not implemented on the GPU path")
     if parameters_K:
@@ -133,18 +132,20 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
 
 
 def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac, fout_name, suffix, parallel, device,
-                  write_files, restart, symmetrize, parameters_K):
+                  write_files, restart, symmetrize, use_irred_kpt, parameters_K):
     """The refinement loop of the reference (run_grid.py:303-387) on per-K-block results from the GPU
     (`wbgpu_static_scan_blocks`): evaluate the new K-points, update the weighted sum, pick the `adpt_fac` points with
     the largest contribution by every criterion of `ResultDict.max`, divide them `adpt_mesh`-fold, repeat."""
-    from .grid import KpointBZparallel
+    from .grid import KpointBZparallel, exclude_equiv_points
     if restart:
         raise NotImplementedError("restart / dump_results are not implemented on the GPU path")
-    if symmetrize:
-        raise NotImplementedError("symmetrize=True: apply system.pointgroup.symmetrize() of the reference to the result")
     if parameters_K:
         raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
     system = as_system(system)
+    pointgroup = getattr(system, "pointgroup", None)
+    if (symmetrize or use_irred_kpt) and pointgroup is None:
+        raise ValueError("use_irred_kpt / symmetrize need system.pointgroup (System_R.set_pointgroup)")
+    periodic = getattr(system, "periodic", (True, True, True))
     calcs = {}
     for key, c in calculators.items():
         if isinstance(c, _dyn.DynamicCalculator) or type(c).__name__ in _dyn._BY_NAME:
@@ -160,9 +161,10 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
 
     NKFFT = np.array(grid.FFT, dtype=int)
-    shifts, factors = k_list_arrays(grid, False)
+    shifts, factors = k_list_arrays(grid, use_irred_kpt)
     dK0 = 1. / np.array(grid.div, dtype=float)
-    K_list = [KpointBZparallel(s * NKFFT, dK0, NKFFT, f) for s, f in zip(shifts, factors)]
+    K_list = [KpointBZparallel(s * NKFFT, dK0, NKFFT, f, pointgroup=pointgroup if use_irred_kpt else None)
+              for s, f in zip(shifts, factors)]
     if adpt_num_iter < 0:  # run_grid.py:303-304
         adpt_num_iter = -adpt_num_iter * np.prod(grid.div) / np.prod(adpt_mesh) / adpt_fac / 3
     adpt_num_iter = int(round(adpt_num_iter))
@@ -201,8 +203,11 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
             mine = full
         result_sum_iter = None
         for j, i in enumerate(new):
-            res = ResultDict({key: c.result([a[j] for a, o in zip(mine, owner) if o == key], system.cell_volume)
-                              for key, c in calcs.items()})
+            res = {key: c.result([a[j] for a, o in zip(mine, owner) if o == key], system.cell_volume)
+                   for key, c in calcs.items()}
+            if symmetrize:   # per K-point here: K.max must see the symmetrised result (run_grid.py:258-265)
+                res = {key: r.symmetrized(pointgroup) for key, r in res.items()}
+            res = ResultDict(res)
             K_list[i].set_result(res)
             contrib = res * K_list[i].factor
             result_sum_iter = contrib if result_sum_iter is None else result_sum_iter + contrib
@@ -223,6 +228,9 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
             break
         Kmax = np.array([K.max for K in K_list]).T
         select_points = set().union(*(np.argsort(Km)[-adpt_fac:] for Km in Kmax))
+        l1 = len(K_list)
         for iK in select_points:
-            K_list += K_list[iK].divide(adpt_mesh)
+            K_list += K_list[iK].divide(adpt_mesh, periodic=periodic, use_symmetry=use_irred_kpt)
+        if use_irred_kpt:
+            exclude_equiv_points(K_list, new_points=len(K_list) - l1)
     return result_all
