@@ -51,7 +51,8 @@ enum {
     WBGPU_SPIN = 6,       /* Spin            covariant.py:331-335 rank 1 */
     WBGPU_KUBO = 7,       /* plan flag only: channels of the Kubo path (dH, and A with external terms),
                              Formula_OptCond calculators/dynamic.py:170-181 */
-    WBGPU_NFORMULA = 8
+    WBGPU_VEL_VEL = 8,    /* VelVel          covariant.py:817-820 rank 2 */
+    WBGPU_NFORMULA = 9
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */

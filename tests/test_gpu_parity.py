@@ -482,6 +482,20 @@ def test_run_symmetric_vs_upstream_golden(wb):
     assert np.abs(a[:, :2]).max() < 1e-12 * np.abs(a[:, 2]).max()
 
 
+def test_ohmic_fsurf_vs_upstream_golden(wb, fe):
+    """Ohmic_FermiSurf (formula VelVel) against the reference's own golden file
+    Fe_W90-conductivity_ohmic_fsurf_iter-0000.npz, with degenerate groups, and with the tetrahedron method."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_ohmic.npz"))
+    st = wb.calculators.static
+    calcs = dict(ohmic_fsurf=st.Ohmic_FermiSurf(Efermi=g["Efermi"]),
+                 ohmic_fsurf_thresh=st.Ohmic_FermiSurf(Efermi=g["Efermi"], degen_thresh=0.05),
+                 ohmic_fsurf_tetra=st.Ohmic_FermiSurf(Efermi=g["Efermi"], tetra=True))
+    res = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), calcs)
+    assert relerr(res.results["ohmic_fsurf"].data, g["upstream_golden_ohmic_fsurf"]) < RTOL
+    assert relerr(res.results["ohmic_fsurf_thresh"].data, g["ohmic_fsurf_thresh"]) < RTOL
+    assert relerr(res.results["ohmic_fsurf_tetra"].data, g["ohmic_fsurf_tetra"]) < 1e-6   # der = 1 tetrahedron weights
+
+
 def test_adaptive_refinement_symmetric(wb):
     """Refinement on the symmetry-reduced K-list (the reference's test_Fe_sym_refine, tests/test_run.py:557-578):
     per-K-point results symmetrised before the selection, children of a divided K-point merged with their symmetry

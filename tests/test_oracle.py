@@ -214,3 +214,13 @@ def test_adaptive_refinement_vs_reference():
     for n_iter in (0, 1, 3):
         for q in calcs:
             assert relerr(hist[n_iter][q], g[f"iter{n_iter}_{q}"]) < RTOL, (n_iter, q)
+
+
+def test_ohmic_fsurf_vs_upstream_golden(fe):
+    """Ohmic_FermiSurf (VelVel, calculators/static.py:393-403) on the reference's test grid against the reference's
+    own golden file Fe_W90-conductivity_ohmic_fsurf_iter-0000.npz."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_ohmic.npz"))
+    res = orc.run(fe, [2, 2, 2], [2, 2, 2], dict(a=("Ohmic_FermiSurf", g["Efermi"], {}),
+                                                  b=("Ohmic_FermiSurf", g["Efermi"], dict(degen_thresh=0.05))))
+    assert relerr(res["a"], g["upstream_golden_ohmic_fsurf"]) < RTOL
+    assert relerr(res["b"], g["ohmic_fsurf_thresh"]) < RTOL

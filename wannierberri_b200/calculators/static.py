@@ -15,7 +15,7 @@ from ..result import EnergyResult
 _TR_INV = {  # transformTR, transformInv of the formulae (covariant.py)
     _lib.IDENTITY: ("ident", "ident"), _lib.OMEGA: ("odd", "ident"), _lib.MORB_HPM: ("odd", "ident"),
     _lib.SPIN: ("odd", "ident"), _lib.VEL_OMEGA: ("ident", "odd"), _lib.VEL_HPLUS: ("ident", "odd"),
-    _lib.VEL_SPIN: ("ident", "odd"),
+    _lib.VEL_SPIN: ("ident", "odd"), _lib.VEL_VEL: ("ident", "ident"),
 }
 
 
@@ -217,8 +217,19 @@ class GME_spin_FermiSurf(StaticCalculator):
         super().__init__(constant_factor=constant_factor, **kwargs)
 
 
+class Ohmic_FermiSurf(StaticCalculator):
+    r"""Ohmic conductivity (:math:`S/m`), Fermi surface integral
+
+        | Output: :math:`\sigma_{\alpha\beta} = -e^2/\hbar \tau \int [dk] v_\alpha v_\beta f'`"""
+
+    def __init__(self, constant_factor=factors.factor_ohmic, **kwargs):
+        self.Formula = _lib.VEL_VEL
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
 _BY_NAME = {c.__name__: c for c in (DOS, CumDOS, Spin, AHC, Morb, BerryDipole_FermiSurf, GME_orb_FermiSurf,
-                                    GME_spin_FermiSurf)}
+                                    GME_spin_FermiSurf, Ohmic_FermiSurf)}
 
 
 def adapt(calc):

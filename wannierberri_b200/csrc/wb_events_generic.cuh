@@ -17,7 +17,7 @@
 
 struct WbEventLayout {
     int mask;          // bit f set: formula f requested
-    int off[8];        // offset of formula f inside the NC values of an event
+    int off[12];       // offset of formula f inside the NC values of an event
     int NC;            // values per event
     int internal_terms, external_terms;
 };
@@ -28,10 +28,10 @@ struct WbNeeds {
 };
 __host__ __device__ inline WbNeeds wb_needs(int mask, int external) {
     auto has = [&](int f) { return (mask >> f) & 1; };
-    bool omega = has(1), morb = has(2), vo = has(3), vh = has(4), vs = has(5), spin = has(6);
+    bool omega = has(1), morb = has(2), vo = has(3), vh = has(4), vs = has(5), spin = has(6), vv = has(8);
     WbNeeds n;
     n.D = omega || morb || vo || vh;
-    n.V = n.D || vs;
+    n.V = n.D || vs || vv;
     n.A = n.D && external;
     n.B = (morb || vh) && external;
     n.Oblk = (vo || vh) && external;
@@ -50,7 +50,7 @@ __host__ __device__ inline int wb_generic_nfull(const WbNeeds& n) {
 __host__ inline size_t wb_generic_smem_bytes(int nw, int mask, int external) {
     WbNeeds n = wb_needs(mask, external);
     size_t cplx_el = (size_t)(3 + wb_generic_nfull(n)) * nw * nw + 9 * (size_t)nw;  // U, X, Y, fulls, diag O/C/S
-    size_t dbl = 2 * (size_t)nw + 3 * (size_t)nw + 27 * (size_t)nw + 3 * (size_t)(nw + 1);  // Es, label, rows[3], prod[27], Tedge
+    size_t dbl = 2 * (size_t)nw + 3 * (size_t)nw + 36 * (size_t)nw + 3 * (size_t)(nw + 1);  // Es, label, rows[3], prod[27], Tedge
     return cplx_el * sizeof(cplx) + dbl * sizeof(double) + 2 * nw * sizeof(short) + 64;
 }
 
@@ -79,7 +79,7 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
     double *rows = R.rows, *prod = R.prod, *Tedge = R.Tedge;
     const short *g1 = R.g1, *g2 = R.g2;
     const bool f_omega = (ev.mask >> 1) & 1, f_morb = (ev.mask >> 2) & 1, f_vo = (ev.mask >> 3) & 1,
-               f_vh = (ev.mask >> 4) & 1, f_vs = (ev.mask >> 5) & 1, f_spin = (ev.mask >> 6) & 1;
+               f_vh = (ev.mask >> 4) & 1, f_vs = (ev.mask >> 5) & 1, f_spin = (ev.mask >> 6) & 1, f_vv = (ev.mask >> 8) & 1;
     const bool internal = ev.internal_terms, external = ev.external_terms;
     // diagonal accessors that work for both storage modes
     auto Odg = [&](int c, int n) { return need.Oblk ? Ob[c * n2 + n * nw + n] : Od[c * nw + n]; };
@@ -132,7 +132,7 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
     for (int x = threadIdx.x; x < 3 * nw; x += NT) {
         int c = x / nw, M = x % nw;
         double tr_omega = 0.;
-        double pv[3] = {0., 0., 0.}, ph[3] = {0., 0., 0.}, ps[3] = {0., 0., 0.};
+        double pv[3] = {0., 0., 0.}, ph[3] = {0., 0., 0.}, ps[3] = {0., 0., 0.}, pw[3] = {0., 0., 0.};
         if (g1[M] >= 0) {
             const int ga = g1[M], gb = g2[M];
             if (f_omega) {
@@ -164,12 +164,17 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
                 for (int Lb = ga; Lb < gb; Lb++)
                     for (int a = 0; a < 3; a++) ps[a] += cmul(Vb[a * n2 + Lb * nw + M], Sb[c * n2 + M * nw + Lb]).x;
             }
+            if (f_vv) {   // VelVel: sum_{L in group} V_LM,a V_ML,c
+                for (int Lb = ga; Lb < gb; Lb++)
+                    for (int a = 0; a < 3; a++) pw[a] += cmul(Vb[a * n2 + Lb * nw + M], Vb[c * n2 + M * nw + Lb]).x;
+            }
         }
         rows[c * nw + M] = tr_omega;
         for (int a = 0; a < 3; a++) {  // component (a, b = c) of the rank-2 products
-            prod[M * 27 + a * 3 + c] = pv[a];
-            prod[M * 27 + 9 + a * 3 + c] = ph[a];
-            prod[M * 27 + 18 + a * 3 + c] = ps[a];
+            prod[M * 36 + a * 3 + c] = pv[a];
+            prod[M * 36 + 9 + a * 3 + c] = ph[a];
+            prod[M * 36 + 18 + a * 3 + c] = ps[a];
+            prod[M * 36 + 27 + a * 3 + c] = pw[a];
         }
     }
     // ---- non-additive Morb_Hpm (static.py:109-117): T(x) = trace with inn = 0..x-1, out = x..nw-1,
@@ -240,17 +245,19 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
                     for (int n = x; n < b; n++) s += Sdg(c, n).x;
                     out[ev.off[6] + c] = s;
                 }
-            if (f_vo || f_vh || f_vs)
+            if (f_vo || f_vh || f_vs || f_vv)
                 for (int ab = 0; ab < 9; ab++) {
-                    double so = 0., sh = 0., ss = 0.;
+                    double so = 0., sh = 0., ss = 0., sv = 0.;
                     for (int n = x; n < b; n++) {
-                        so += prod[n * 27 + ab];
-                        sh += prod[n * 27 + 9 + ab];
-                        ss += prod[n * 27 + 18 + ab];
+                        so += prod[n * 36 + ab];
+                        sh += prod[n * 36 + 9 + ab];
+                        ss += prod[n * 36 + 18 + ab];
+                        sv += prod[n * 36 + 27 + ab];
                     }
                     if (f_vo) out[ev.off[3] + ab] = so;
                     if (f_vh) out[ev.off[4] + ab] = sh;
                     if (f_vs) out[ev.off[5] + ab] = ss;
+                    if (f_vv) out[ev.off[8] + ab] = sv;
                 }
         }
     }
@@ -280,8 +287,8 @@ wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, cons
     double* Es = (double*)p;
     double* label = Es + nw;
     double* rows = label + nw;         // [3][nw]   per-band Omega trace terms
-    double* prod = rows + 3 * nw;      // [nw][27]  per-band partial products: VelOmega 9 | VelHplus 9 | VelSpin 9
-    double* Tedge = prod + 27 * nw;    // [3][nw+1] cumulative non-additive traces
+    double* prod = rows + 3 * nw;      // [nw][36]  per-band partial products: VelOmega 9 | VelHplus 9 | VelSpin 9 | VelVel 9
+    double* Tedge = prod + 36 * nw;    // [3][nw+1] cumulative non-additive traces
     short* g1 = (short*)(Tedge + 3 * (nw + 1));
     short* g2 = g1 + nw;
 

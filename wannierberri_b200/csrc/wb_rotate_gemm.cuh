@@ -169,7 +169,7 @@ wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
     double* label = Es + nw;
     double* rows = label + nw;
     double* prod = rows + 3 * nw;
-    double* Tedge = prod + 27 * nw;
+    double* Tedge = prod + 36 * nw;
     short* g1 = (short*)(Tedge + 3 * (nw + 1));
     short* g2 = g1 + nw;
     for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
@@ -199,5 +199,5 @@ wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
 }
 
 __host__ inline size_t wb_xbar_events_smem_bytes(int nw) {
-    return sizeof(double) * ((size_t)2 * nw + 3 * nw + 27 * nw + 3 * (nw + 1)) + 2 * nw * sizeof(short) + 64;
+    return sizeof(double) * ((size_t)2 * nw + 3 * nw + 36 * nw + 3 * (nw + 1)) + 2 * nw * sizeof(short) + 64;
 }

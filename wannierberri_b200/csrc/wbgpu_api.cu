@@ -262,7 +262,7 @@ static int formula_rank(int f) {
     switch (f) {
         case WBGPU_IDENTITY: return 0;
         case WBGPU_OMEGA: case WBGPU_MORB_HPM: case WBGPU_SPIN: return 1;
-        case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: return 2;
+        case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: case WBGPU_VEL_VEL: return 2;
     }
     return -1;
 }
@@ -305,7 +305,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     const uint32_t m = formula_mask;
     auto has = [&](int f) { return (m >> f) & 1u; };
     bool need_dH = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
-                   has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO);
+                   has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO) || has(WBGPU_VEL_VEL);
     bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) || has(WBGPU_KUBO);
     bool need_A = berry && external_terms;
     bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS)) && external_terms;
@@ -408,8 +408,8 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     {
         int ncmax = 1;
         int sum = 0;
-        for (int f = 1; f < WBGPU_KUBO; f++)
-            if ((m >> f) & 1u) sum += formula_ncomp(f);
+        for (int f = 1; f < WBGPU_NFORMULA; f++)
+            if (f != WBGPU_KUBO && ((m >> f) & 1u)) sum += formula_ncomp(f);
         ncmax = std::max(ncmax, sum);
         c->ev_ncmax = ncmax;
         CK(cudaMalloc(&c->d_evval, sizeof(double) * nkl * nw * ncmax));
@@ -696,7 +696,7 @@ static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec)
             G.win = w;
             G.ev.mask = 0;
             G.ev.NC = 0;
-            for (int f = 0; f < 8; f++) G.ev.off[f] = 0;
+            for (int f = 0; f < 12; f++) G.ev.off[f] = 0;
             G.ev.internal_terms = s.internal_terms;
             G.ev.external_terms = s.external_terms;
             groups.push_back(G);
