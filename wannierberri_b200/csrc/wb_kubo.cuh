@@ -18,8 +18,12 @@
 //                              staged in shared memory in chunks, the frequency factors W of (entry, omega) are
 //                              computed once per chunk and shared by the 18 components;
 //   wb_kubo_finalize_kernel    running sum over Efermi, scale, transpose to the reference's [Ef][omega][3][3].
-// The reference's dense contraction costs n_omega * n_pair * n_Ef * 9 multiply-adds per k-point; this form
-// n_omega * n_pair * 9 * 2.
+// Optical conductivity: X_ij[ab] = -W1 M[ab] + W2 M[ba] couples a component only to its transpose, so the entries
+// carry M in the symmetric / antisymmetric basis (slot ab = M[ab] + M[ba], slot ba = M[ab] - M[ba] for a < b, the
+// diagonal as is) and the accumulator holds P = X[ab] + X[ba] = (W2 - W1) S and Q = X[ab] - X[ba] = -(W1 + W2) A:
+// ONE complex multiply per (entry, omega, component) instead of two; the finalize kernel changes the basis back.
+// The reference's dense contraction costs n_omega * n_pair * n_Ef * 9 complex multiply-adds per k-point; this form
+// n_omega * n_pair * 9 * 2 (two visits per pair).
 #pragma once
 #include "wb_common.cuh"
 #include "wb_groups.cuh"
@@ -146,22 +150,32 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
                 e[3] = (double)((nz1 ? 1 : 0) | (nz2 ? 2 : 0));
             } else {
                 const int a = ab / 3, b = ab - 3 * a;
-                cplx acc = cmake(0., 0.);
+                // M[ab] and M[ba] (slot ab stores their sum for a < b, their difference for a > b, M[aa] on the diagonal)
+                cplx acc = cmake(0., 0.), act = cmake(0., 0.);
                 for (int m = gs[i]; m < ge[i]; m++)
                     for (int n = gs[j]; n < ge[j]; n++) {
                         // A_mn,a = Abar_mn,a + i D_mn,a,  D_mn,a = -Vbar_mn,a / (E_m - E_n)
                         const double inv = wb_deinv(Es[m], Es[n]);
-                        const cplx Vmn = Vb[a * n2 + m * nw + n], Vnm = Vb[b * n2 + n * nw + m];
-                        cplx Amn = cmake(inv * Vmn.y, -inv * Vmn.x);     // i * (-inv V)
-                        cplx Anm = cmake(-inv * Vnm.y, inv * Vnm.x);     // i * (+inv V): 1/(E_n - E_m) = -inv
-                        if (P.external) {
-                            Amn = cadd(Amn, Ab[a * n2 + m * nw + n]);
-                            Anm = cadd(Anm, Ab[b * n2 + n * nw + m]);
+                        cplx Amn[2], Anm[2];
+#pragma unroll
+                        for (int x = 0; x < 2; x++) {
+                            const int d = x ? b : a;
+                            const cplx Vmn = Vb[d * n2 + m * nw + n], Vnm = Vb[d * n2 + n * nw + m];
+                            Amn[x] = cmake(inv * Vmn.y, -inv * Vmn.x);     // i * (-inv V)
+                            Anm[x] = cmake(-inv * Vnm.y, inv * Vnm.x);     // i * (+inv V): 1/(E_n - E_m) = -inv
+                            if (P.external) {
+                                Amn[x] = cadd(Amn[x], Ab[d * n2 + m * nw + n]);
+                                Anm[x] = cadd(Anm[x], Ab[d * n2 + n * nw + m]);
+                            }
                         }
-                        cfma(acc, Amn, Anm);
+                        cfma(acc, Amn[0], Anm[1]);   // A_mn,a A_nm,b -> M[ab]
+                        cfma(act, Amn[1], Anm[0]);   // A_mn,b A_nm,a -> M[ba]
                     }
-                e[2 + 2 * ab] = -sw * acc.y;   // i * acc
-                e[3 + 2 * ab] = sw * acc.x;
+                cplx v = acc;
+                if (a < b) v = cadd(acc, act);
+                else if (a > b) v = csub(act, acc);   // slot (a > b) holds M[ba'] - M[ab'] with (a', b') = (b, a): M[a'b'] - M[b'a']
+                e[2 + 2 * ab] = -sw * v.y;   // i * v
+                e[3 + 2 * ab] = sw * v.x;
             }
         }
     }
@@ -193,7 +207,8 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
     const int tid = threadIdx.x;
     const int iw = tid / NC, c = tid - iw * NC;
     const bool owner = iw < nwt;
-    const int ab = c >> 1, ri = c & 1, ba = (ab % 3) * 3 + ab / 3;
+    const int ab = c >> 1, ri = c & 1;
+    const int wsel = ((ab / 3) > (ab % 3)) ? 2 : 0;   // antisymmetric slot (a > b): Wn, else Wd
     double* const col = Dglob + ((size_t)(w0 + iw) * P.nEF) * NC + c;
     for (long ik = blockIdx.y; ik < nk; ik += gridDim.y) {
         const int cnt = count[ik];
@@ -213,8 +228,11 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
                 if (KIND == 0) {
                     const cplx c1 = wb_kubo_cfac(dl - om, P.eta, P.smr_type);
                     const cplx c2 = wb_kubo_cfac(-dl - om, P.eta, P.smr_type);
-                    o[0] = dl * c1.x; o[1] = dl * c1.y;      // pair (lo, hi): (E2 - E1) = +Delta, Fermi factor -1
-                    o[2] = -dl * c2.x; o[3] = -dl * c2.y;    // pair (hi, lo): Fermi factor +1
+                    // W1 = Delta cfac(Delta - omega): pair (lo, hi), Fermi factor -1;  W2 = -Delta cfac(-Delta - omega):
+                    // pair (hi, lo), Fermi factor +1.  Stored: Wd = W2 - W1 (symmetric slots), Wn = -(W1 + W2) (antisymmetric)
+                    const double w1x = dl * c1.x, w1y = dl * c1.y, w2x = -dl * c2.x, w2y = -dl * c2.y;
+                    o[0] = w2x - w1x; o[1] = w2y - w1y;
+                    o[2] = -(w1x + w2x); o[3] = -(w1y + w2y);
                 } else {
                     const int fl = (int)ent[p * WB_KUBO_ENT + 3];
                     o[0] = (fl & 1) ? wb_kubo_smear(dl - om, P.eta, P.smr_type) : 0.;    // (hi, lo): E1 - E2 = +Delta
@@ -234,9 +252,9 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
                     }
                     const double* W = Wb + (p * WT + iw) * 4;
                     if (KIND == 0) {
-                        const double Mr = e[2 + 2 * ab], Mi = e[3 + 2 * ab], Nr = e[2 + 2 * ba], Ni = e[3 + 2 * ba];
-                        if (ri == 0) Y += -(W[0] * Mr - W[1] * Mi) + (W[2] * Nr - W[3] * Ni);
-                        else Y += -(W[0] * Mi + W[1] * Mr) + (W[2] * Ni + W[3] * Nr);
+                        const double Mr = e[2 + 2 * ab], Mi = e[3 + 2 * ab], Wr = W[wsel], Wi = W[wsel + 1];
+                        if (ri == 0) Y += Wr * Mr - Wi * Mi;
+                        else Y += Wr * Mi + Wi * Mr;
                     } else {
                         Y += (W[0] - W[1]) * e[2];
                     }
@@ -247,16 +265,35 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
     }
 }
 
-// D holds differences along Efermi: out[iEf][iw][NC] = scale * sum_{f <= iEf} D[iw][f][NC]
+// D holds differences along Efermi: value[iw][iEf][c] = sum_{f <= iEf} D[iw][f][c].  JDOS (NC = 1): out = scale * value.
+// Optical conductivity (NC = 18): slots (ab, ba), a < b hold P = X[ab] + X[ba] and Q = X[ab] - X[ba]:
+// out[iEf][iw][ab] = scale (P + Q) / 2, out[..][ba] = scale (P - Q) / 2; the diagonal slots hold X[aa].
 __global__ void wb_kubo_finalize_kernel(const double* __restrict__ D, int nomega, int nEF, int NC, double scale,
                                         double* __restrict__ out) {
     const long total = (long)nomega * NC;
     for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
         const int c = (int)(x % NC), w = (int)(x / NC);
-        double run = 0.;
+        if (NC == 1) {
+            double run = 0.;
+            for (int f = 0; f < nEF; f++) {
+                run += D[((size_t)w * nEF + f) * NC + c];
+                out[((size_t)f * nomega + w) * NC + c] = scale * run;
+            }
+            continue;
+        }
+        const int ab = c >> 1, ri = c & 1, a = ab / 3, b = ab % 3;
+        if (a > b) continue;   // handled by the thread of the transposed slot
+        const int ct = 2 * (b * 3 + a) + ri;
+        double run = 0., runt = 0.;
         for (int f = 0; f < nEF; f++) {
             run += D[((size_t)w * nEF + f) * NC + c];
-            out[((size_t)f * nomega + w) * NC + c] = scale * run;
+            if (a == b) {
+                out[((size_t)f * nomega + w) * NC + c] = scale * run;
+            } else {
+                runt += D[((size_t)w * nEF + f) * NC + ct];
+                out[((size_t)f * nomega + w) * NC + c] = scale * 0.5 * (run + runt);
+                out[((size_t)f * nomega + w) * NC + ct] = scale * 0.5 * (run - runt);
+            }
         }
     }
 }
