@@ -50,7 +50,7 @@ __host__ __device__ inline int wb_generic_nfull(const WbNeeds& n) {
 __host__ inline size_t wb_generic_smem_bytes(int nw, int mask, int external) {
     WbNeeds n = wb_needs(mask, external);
     size_t cplx_el = (size_t)(3 + wb_generic_nfull(n)) * nw * nw + 9 * (size_t)nw;  // U, X, Y, fulls, diag O/C/S
-    size_t dbl = 2 * (size_t)nw + 3 * (size_t)nw + 36 * (size_t)nw + 3 * (size_t)(nw + 1);  // Es, label, rows[3], prod[27], Tedge
+    size_t dbl = 2 * (size_t)nw + 3 * (size_t)nw + 36 * (size_t)nw + 3 * (size_t)(nw + 1) + (size_t)nw * nw;  // Es, label, rows[3], prod[36], Tedge, inv
     return cplx_el * sizeof(cplx) + dbl * sizeof(double) + 2 * nw * sizeof(short) + 64;
 }
 
@@ -64,6 +64,7 @@ struct WbRotated {
     const double* label;
     double *rows, *prod, *Tedge;
     double* Mx;                                // [3][nw*nw] scratch of the non-additive Morb evaluation
+    double* inv;                               // [nw][nw] 1/(E_n - E_l) with the reference's cutoff (dEig_inv), filled here
     const short *g1, *g2;
 };
 
@@ -85,18 +86,28 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
     auto Odg = [&](int c, int n) { return need.Oblk ? Ob[c * n2 + n * nw + n] : Od[c * nw + n]; };
     auto Cdg = [&](int c, int n) { return need.Cblk ? Cb[c * n2 + n * nw + n] : Cd[c * nw + n]; };
     auto Sdg = [&](int c, int n) { return need.Sblk ? Sb[c * n2 + n * nw + n] : Sd[c * nw + n]; };
+    // dEig_inv once per k-point (data_K.py:290-298): the formulae below read every element many times
+    double* const inv = R.inv;
+    for (int x = threadIdx.x; x < n2; x += NT) inv[x] = wb_deinv(Es[x / nw], Es[x % nw]);
+    __syncthreads();
     auto Dm = [&](int a, int n, int l) {  // D_nl,a = -Vbar_nl,a / (E_n - E_l)
-        return cscale(-wb_deinv(Es[n], Es[l]), Vb[a * n2 + n * nw + l]);
+        return cscale(-inv[n * nw + l], Vb[a * n2 + n * nw + l]);
     };
 
     // ---- S-type sums for a pair (M, Lb) of one group [ga, gb), component c:
     //   S  = -i sum_l D_Ml,al D_lL,be + 1/2 O_ML - sum_l D_Ml,al A_lL,be + sum_l D_Ml,be A_lL,al - i sum_m A_Mm,al A_mL,be
     //   Sh = same with E_l, C, B, E_m  (Morb_H)
+    // Evaluated COOPERATIVELY by a group of LG = 8 adjacent lanes: the sum over the partner bands l is strided over
+    // the lanes, lane 0 adds the in-group and the diagonal terms, a butterfly over the group leaves the totals on
+    // every lane.  (A thread per (band, component) with serial O(nw) sums left most of the CTA idle.)
+    constexpr int LG = 8;
+    const int lgid = threadIdx.x % LG;
+    const unsigned gmask = 0xFFu << (8 * ((threadIdx.x & 31) / LG));
     auto S_pair = [&](int M, int Lb, int ga, int gb, int c, bool want_h, cplx& S, cplx& Sh) {
         const int al = WB_ALPHA(c), be = WB_BETA(c);
         S = cmake(0., 0.);
         Sh = cmake(0., 0.);
-        for (int l = 0; l < nw; l++) {
+        for (int l = lgid; l < nw; l += LG) {
             if (l >= ga && l < gb) continue;
             cplx DMa = Dm(al, M, l), DMb = Dm(be, M, l);
             if (internal) {
@@ -113,7 +124,7 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
                 }
             }
         }
-        if (external) {
+        if (external && lgid == 0) {
             for (int m = ga; m < gb; m++) {
                 cplx z = cmul(Ab[al * n2 + M * nw + m], Ab[be * n2 + m * nw + Lb]);  // -i z
                 S.x += z.y; S.y -= z.x;
@@ -126,10 +137,19 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
                 Sh.x += 0.5 * cc.x; Sh.y += 0.5 * cc.y;
             }
         }
+#pragma unroll
+        for (int o = 1; o < LG; o <<= 1) {
+            S.x += __shfl_xor_sync(gmask, S.x, o);
+            S.y += __shfl_xor_sync(gmask, S.y, o);
+            if (want_h) {   // uniform
+                Sh.x += __shfl_xor_sync(gmask, Sh.x, o);
+                Sh.y += __shfl_xor_sync(gmask, Sh.y, o);
+            }
+        }
     };
 
-    // ---- additive traces and products: one thread per (band M, component c)
-    for (int x = threadIdx.x; x < 3 * nw; x += NT) {
+    // ---- additive traces and products: one lane group per (band M, component c)
+    for (int x = threadIdx.x / LG; x < 3 * nw; x += NT / LG) {
         int c = x / nw, M = x % nw;
         double tr_omega = 0.;
         double pv[3] = {0., 0., 0.}, ph[3] = {0., 0., 0.}, ps[3] = {0., 0., 0.}, pw[3] = {0., 0., 0.};
@@ -169,12 +189,14 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
                     for (int a = 0; a < 3; a++) pw[a] += cmul(Vb[a * n2 + Lb * nw + M], Vb[c * n2 + M * nw + Lb]).x;
             }
         }
-        rows[c * nw + M] = tr_omega;
-        for (int a = 0; a < 3; a++) {  // component (a, b = c) of the rank-2 products
-            prod[M * 36 + a * 3 + c] = pv[a];
-            prod[M * 36 + 9 + a * 3 + c] = ph[a];
-            prod[M * 36 + 18 + a * 3 + c] = ps[a];
-            prod[M * 36 + 27 + a * 3 + c] = pw[a];
+        if (lgid == 0) {
+            rows[c * nw + M] = tr_omega;
+            for (int a = 0; a < 3; a++) {  // component (a, b = c) of the rank-2 products
+                prod[M * 36 + a * 3 + c] = pv[a];
+                prod[M * 36 + 9 + a * 3 + c] = ph[a];
+                prod[M * 36 + 18 + a * 3 + c] = ps[a];
+                prod[M * 36 + 27 + a * 3 + c] = pw[a];
+            }
         }
     }
     // ---- non-additive Morb_Hpm (static.py:109-117): T(x) = trace with inn = 0..x-1, out = x..nw-1,
@@ -289,7 +311,8 @@ wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, cons
     double* rows = label + nw;         // [3][nw]   per-band Omega trace terms
     double* prod = rows + 3 * nw;      // [nw][36]  per-band partial products: VelOmega 9 | VelHplus 9 | VelSpin 9 | VelVel 9
     double* Tedge = prod + 36 * nw;    // [3][nw+1] cumulative non-additive traces
-    short* g1 = (short*)(Tedge + 3 * (nw + 1));
+    double* invtab = Tedge + 3 * (nw + 1);   // [nw][nw]
+    short* g1 = (short*)(invtab + n2);
     short* g2 = g1 + nw;
 
     for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
@@ -339,6 +362,7 @@ wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, cons
         R.Vb = Vb; R.Ab = Ab; R.Bb = Bb; R.Ob = Ob; R.Cb = Cb; R.Sb = Sb; R.Od = Od; R.Cd = Cd; R.Sd = Sd;
         R.Es = Es; R.label = label; R.rows = rows; R.prod = prod; R.Tedge = Tedge;
         R.Mx = (double*)Xs;   // [3][n2] doubles = 1.5 n2 complex: Xs and half of Ys, both free now
+        R.inv = invtab;
         R.g1 = g1; R.g2 = g2;
         wb_formula_events<NT>(R, need, nw, ik, ev, ev_label, ev_val);
         __syncthreads();

@@ -151,7 +151,8 @@ wb_rotate_gemm_kernel(const cplx* __restrict__ rec, long recE, WbChanList ch, in
 }
 
 // Formula stage on rotated matrices held in global memory: one CTA per k-point.
-// xbar[k][nch][nw][nw]; the channel triples are ordered V | A | B | O | C | S (those present).
+// xbar[k][nch][nw][nw]; the channel triples are ordered V | A | B | O | C | S (those present) and are read in place
+// (L2): staging them in shared memory was measured and does not pay, the kernel is bound by its sums, not by latency.
 template <int NT>
 __global__ void __launch_bounds__(NT)
 wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall, WbWindow win,
@@ -159,18 +160,20 @@ wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
                       double* __restrict__ ev_val) {
     extern __shared__ __align__(16) double smem_x[];
     const int n2 = nw * nw;
+    double* const small = smem_x;
     WbNeeds need = wb_needs(ev.mask, ev.external_terms);
     // everything that is needed at all is rotated in full here
     need.Oblk = need.Oblk || need.Odiag;
     need.Cblk = need.Cblk || need.Cdiag;
     need.Sblk = need.Sblk || need.Sdiag;
     need.Odiag = need.Cdiag = need.Sdiag = false;
-    double* Es = smem_x;
+    double* Es = small;
     double* label = Es + nw;
     double* rows = label + nw;
     double* prod = rows + 3 * nw;
     double* Tedge = prod + 36 * nw;
-    short* g1 = (short*)(Tedge + 3 * (nw + 1));
+    double* invtab = Tedge + 3 * (nw + 1);   // [nw][nw]
+    short* g1 = (short*)(invtab + n2);
     short* g2 = g1 + nw;
     for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
         for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
@@ -181,17 +184,24 @@ wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
             if (threadIdx.x < 32) wb_band_groups_warp(Es, nw, win, g1, g2, label, threadIdx.x);
         } else if (threadIdx.x == 0) wb_band_groups(Es, nw, win, g1, g2, label);
         __syncthreads();
-        const cplx* p = xbar + (size_t)ik * nch * n2;
+        const cplx* gsrc = xbar + (size_t)ik * nch * n2;
+        int it = 0;
+        auto next = [&](bool present) {   // triple `it` of this k-point
+            const cplx* q = gsrc + (size_t)it * 3 * n2;
+            if (present) it++;
+            return q;
+        };
         WbRotated R;
-        R.Vb = p; if (need.V) p += 3 * n2;
-        R.Ab = p; if (need.A) p += 3 * n2;
-        R.Bb = p; if (need.B) p += 3 * n2;
-        R.Ob = p; if (need.Oblk) p += 3 * n2;
-        R.Cb = p; if (need.Cblk) p += 3 * n2;
-        R.Sb = p; if (need.Sblk) p += 3 * n2;
+        R.Vb = next(need.V);
+        R.Ab = next(need.A);
+        R.Bb = next(need.B);
+        R.Ob = next(need.Oblk);
+        R.Cb = next(need.Cblk);
+        R.Sb = next(need.Sblk);
         R.Od = R.Cd = R.Sd = nullptr;
         R.Es = Es; R.label = label; R.rows = rows; R.prod = prod; R.Tedge = Tedge;
         R.Mx = mx_scratch + (size_t)blockIdx.x * 3 * n2;
+        R.inv = invtab;
         R.g1 = g1; R.g2 = g2;
         wb_formula_events<NT>(R, need, nw, ik, ev, ev_label, ev_val);
         __syncthreads();
@@ -199,5 +209,6 @@ wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
 }
 
 __host__ inline size_t wb_xbar_events_smem_bytes(int nw) {
-    return sizeof(double) * ((size_t)2 * nw + 3 * nw + 36 * nw + 3 * (nw + 1)) + 2 * nw * sizeof(short) + 64;
+    return sizeof(double) * ((size_t)2 * nw + 3 * nw + 36 * nw + 3 * (nw + 1) + (size_t)nw * nw) +
+           2 * nw * sizeof(short) + 64;
 }
