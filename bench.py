@@ -320,7 +320,7 @@ def main():
                         "frac": BYTES_PER_K * kpts_rank / step_s / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
                         "note": "whole pipeline, algorithmic X(k) bytes (16*nw^2*10 per k-point) / sum of stage times"}
-        cpu = None if args.no_cpu_baseline else cpu_baseline_1core()
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline_1core()   # rank 0 at N = 1 only
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
