@@ -482,6 +482,20 @@ def test_run_symmetric_vs_upstream_golden(wb):
     assert np.abs(a[:, :2]).max() < 1e-12 * np.abs(a[:, 2]).max()
 
 
+@pytest.mark.parametrize("fder", [0, 1, 2, 3])
+def test_fder_stencils_vs_upstream_files(wb, fe, fder):
+    """StaticCalculator(Formula=Identity, fder=0..3): the finite-difference stencils of the scan (static.py:137-147)
+    against the reference's own files tests/reference/calculators/calculator-Fe-ident-fder=*.npz."""
+    from wannierberri_b200 import _lib
+    g = np.load(os.path.join(GOLDEN, "golden_fe_calc_fder.npz"))
+    grid = wb.Grid(fe, NKdiv=[1, 1, 1], NKFFT=g["NKFFT"])
+    data = wb.Data_K_R(fe, dK=g["dK"], grid=grid)
+    got = wb.calculators.static.StaticCalculator(Formula=_lib.IDENTITY, Efermi=g["Efermi"], tetra=False, fder=fder)(data).data
+    ref = g[f"upstream_ident_fder{fder}"]
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-300)
+
+
 def test_ohmic_fsurf_vs_upstream_golden(wb, fe):
     """Ohmic_FermiSurf (formula VelVel) against the reference's own golden file
     Fe_W90-conductivity_ohmic_fsurf_iter-0000.npz, with degenerate groups, and with the tetrahedron method."""

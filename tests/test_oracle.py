@@ -224,3 +224,14 @@ def test_ohmic_fsurf_vs_upstream_golden(fe):
                                                   b=("Ohmic_FermiSurf", g["Efermi"], dict(degen_thresh=0.05))))
     assert relerr(res["a"], g["upstream_golden_ohmic_fsurf"]) < RTOL
     assert relerr(res["b"], g["ohmic_fsurf_thresh"]) < RTOL
+
+
+@pytest.mark.parametrize("fder", [0, 1, 2, 3])
+def test_fder_stencils_vs_upstream_files(fe, fder):
+    """StaticCalculator(Formula=Identity, fder=0..3) (static.py:137-147) against the reference's own files
+    tests/reference/calculators/calculator-Fe-ident-fder=*.npz (tests/test_calc.py:71-77)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_calc_fder.npz"))
+    data = orc.OracleDataK(fe, g["dK"], g["NKFFT"])
+    got = orc.static_scan(data, orc.Identity, fder, g["Efermi"])
+    ref = g[f"upstream_ident_fder{fder}"]
+    assert np.abs(got - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-300)
