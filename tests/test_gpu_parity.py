@@ -496,6 +496,40 @@ def test_fder_stencils_vs_upstream_files(wb, fe, fder):
     assert np.abs(got - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-300)
 
 
+def test_random_system_vs_upstream_goldens(wb):
+    """The reference's `random` test system (6 WF, 20 R-vectors WITHOUT the R <-> -R symmetry -> the plan keeps d_aH as
+    full channels) through run(): static, tetrahedron and Kubo calculators against the reference's own golden files
+    random-*_iter-0000.npz (tests/test_run.py:653-669) and the live reference run of make_golden_random.py."""
+    g = np.load(os.path.join(GOLDEN, "golden_random.npz"))
+    rnd = wb.System_R.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    Ef = g["Efermi"]
+    st, dyn = wb.calculators.static, wb.calculators.dynamic
+    calcs = dict(ahc=st.AHC(Efermi=Ef), dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef), Morb=st.Morb(Efermi=Ef),
+                 spin=st.Spin(Efermi=Ef), conductivity_ohmic_fsurf=st.Ohmic_FermiSurf(Efermi=Ef),
+                 berry_dipole_fsurf=st.BerryDipole_FermiSurf(Efermi=Ef), gme_orb_fsurf=st.GME_orb_FermiSurf(Efermi=Ef),
+                 gme_spin_fsurf=st.GME_spin_FermiSurf(Efermi=Ef), ahc_tetra=st.AHC(Efermi=Ef, tetra=True),
+                 opt_conductivity=dyn.OpticalConductivity(Efermi=g["opt_Efermi"], omega=g["opt_omega"],
+                                                          smr_fixed_width=0.20, smr_type="Gaussian"),
+                 opt_conductivity_in=dyn.OpticalConductivity(Efermi=g["opt_in_Efermi"], omega=g["opt_omega"],
+                                                             smr_fixed_width=0.20, smr_type="Lorentzian"))
+    res = wb.run(rnd, wb.Grid(rnd, NK=[6, 6, 6], NKFFT=[3, 3, 3]), calcs)
+    for q in calcs:
+        assert res.results[q].data.shape == g[q].shape, q
+        assert np.abs(res.results[q].data - g[q]).max() <= RTOL * max(np.abs(g[q]).max(), 1e-300), q
+        if "upstream_golden_" + q in g.files:
+            ref = g["upstream_golden_" + q]
+            assert np.abs(res.results[q].data - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-300), q
+    # every rotation / eigensolver variant on this system
+    for method in (1, 4):
+        eng = wb.Engine(rnd)
+        eng.set_option("rotate_method", method)
+        specs = calcs["ahc"].specs() + calcs["Morb"].specs()
+        eng.plan([3, 3, 3], [s.formula for s in specs])
+        shifts, factors = wb.Grid(rnd, NK=[6, 6, 6], NKFFT=[3, 3, 3]).K_arrays()
+        a = eng.scan(shifts, factors, specs)[0]
+        assert relerr(a, g["ahc"]) < RTOL, method
+
+
 def test_ohmic_fsurf_vs_upstream_golden(wb, fe):
     """Ohmic_FermiSurf (formula VelVel) against the reference's own golden file
     Fe_W90-conductivity_ohmic_fsurf_iter-0000.npz, with degenerate groups, and with the tetrahedron method."""

@@ -235,3 +235,27 @@ def test_fder_stencils_vs_upstream_files(fe, fder):
     got = orc.static_scan(data, orc.Identity, fder, g["Efermi"])
     ref = g[f"upstream_ident_fder{fder}"]
     assert np.abs(got - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-300)
+
+
+RANDOM_CASES = dict(
+    ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}), spin=("Spin", {}),
+    conductivity_ohmic_fsurf=("Ohmic_FermiSurf", {}), berry_dipole_fsurf=("BerryDipole_FermiSurf", {}),
+    gme_orb_fsurf=("GME_orb_FermiSurf", {}), gme_spin_fsurf=("GME_spin_FermiSurf", {}),
+)
+
+
+def test_random_system_vs_upstream_goldens():
+    """The reference's `random` test system (6 WF, 20 R-vectors without the R <-> -R symmetry: H(k) is hermitised by the
+    transform, d_aH is NOT hermitian) against the reference's own golden files random-*_iter-0000.npz
+    (tests/test_run.py:653-669) and a live reference run (tests/golden/make_golden_random.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_random.npz"))
+    rnd = orc.OracleSystem.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    calcs = {k: (name, g["Efermi"], kw) for k, (name, kw) in RANDOM_CASES.items()}
+    calcs["opt_conductivity"] = ("OpticalConductivity", g["opt_Efermi"], dict(omega=g["opt_omega"], smr_fixed_width=0.20, smr_type="Gaussian"))
+    calcs["opt_conductivity_in"] = ("OpticalConductivity", g["opt_in_Efermi"], dict(omega=g["opt_omega"], smr_fixed_width=0.20))
+    res = orc.run(rnd, [2, 2, 2], [3, 3, 3], calcs)
+    for q in calcs:
+        scale = max(np.abs(g[q]).max(), 1e-300)
+        assert np.abs(res[q] - g[q]).max() <= RTOL * scale, q
+        if "upstream_golden_" + q in g.files:
+            assert np.abs(res[q] - g["upstream_golden_" + q]).max() <= RTOL * max(np.abs(g["upstream_golden_" + q]).max(), 1e-300), q
