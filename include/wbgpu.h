@@ -52,7 +52,9 @@ enum {
     WBGPU_KUBO = 7,       /* plan flag only: channels of the Kubo path (dH, and A with external terms),
                              Formula_OptCond calculators/dynamic.py:170-181 */
     WBGPU_VEL_VEL = 8,    /* VelVel          covariant.py:817-820 rank 2 */
-    WBGPU_NFORMULA = 9
+    WBGPU_INV_MASS = 9,   /* InvMass         elementary.py:28-34 (generalised derivative of the velocity, needs
+                             the second comma-derivative of H) rank 2 */
+    WBGPU_NFORMULA = 10
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */

@@ -37,6 +37,8 @@ int main() {
     for (int a = 0; a < 3; a++) L.off_A[a] = take(true);
     for (int a = 0; a < 3; a++) L.off_O[a] = take(true);
     for (int a = 0; a < 3; a++) L.off_B[a] = L.off_C[a] = L.off_S[a] = -1;
+    for (int a = 0; a < 6; a++) L.off_W[a] = -1;
+    L.dH_herm = 0;
     L.E = off;
     WbMmaPlan P; wb_mma_make_plan<NW>(L, 2, 1, &P);
     std::vector<double> hx((size_t)4096 * L.E * 2);

@@ -530,6 +530,30 @@ def test_random_system_vs_upstream_goldens(wb):
         assert relerr(a, g["ahc"]) < RTOL, method
 
 
+@pytest.mark.parametrize("tag", ["fe", "random"])
+@pytest.mark.parametrize("rotate_method", [0, 1])
+def test_ohmic_fermi_sea_vs_upstream_golden(wb, fe, tag, rotate_method):
+    """Ohmic_FermiSea (formula InvMass: second comma-derivative channels of H, rotated diagonals, generalised
+    derivative) against the reference's own golden files {Fe_W90,random}-conductivity_ohmic_iter-0000.npz, with
+    degenerate groups and with the tetrahedron method; hermitian-packed (Fe) and full (random) derivative channels."""
+    g = np.load(os.path.join(GOLDEN, "golden_ohmic_sea.npz"))
+    system = fe if tag == "fe" else wb.System_R.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    NK, NKFFT = ([4, 4, 4], [2, 2, 2]) if tag == "fe" else ([6, 6, 6], [3, 3, 3])
+    Ef = g[f"{tag}_Efermi"]
+    st = wb.calculators.static
+    calcs = dict(ohmic=st.Ohmic_FermiSea(Efermi=Ef), ohmic_thresh=st.Ohmic_FermiSea(Efermi=Ef, degen_thresh=0.05),
+                 ohmic_tetra=st.Ohmic_FermiSea(Efermi=Ef, tetra=True), ahc=st.AHC(Efermi=Ef))
+    from wannierberri_b200.data_K import engine_for
+    engine_for(system, 0).set_option("rotate_method", rotate_method)
+    try:
+        res = wb.run(system, wb.Grid(system, NK=NK, NKFFT=NKFFT), calcs, device=0)
+    finally:
+        engine_for(system, 0).set_option("rotate_method", 0)
+    assert relerr(res.results["ohmic"].data, g[f"{tag}_upstream_golden_ohmic"]) < RTOL
+    for q in ("ohmic", "ohmic_thresh", "ohmic_tetra"):
+        assert relerr(res.results[q].data, g[f"{tag}_{q}"]) < RTOL, q
+
+
 def test_ohmic_fsurf_vs_upstream_golden(wb, fe):
     """Ohmic_FermiSurf (formula VelVel) against the reference's own golden file
     Fe_W90-conductivity_ohmic_fsurf_iter-0000.npz, with degenerate groups, and with the tetrahedron method."""

@@ -259,3 +259,15 @@ def test_random_system_vs_upstream_goldens():
         assert np.abs(res[q] - g[q]).max() <= RTOL * scale, q
         if "upstream_golden_" + q in g.files:
             assert np.abs(res[q] - g["upstream_golden_" + q]).max() <= RTOL * max(np.abs(g["upstream_golden_" + q]).max(), 1e-300), q
+
+
+@pytest.mark.parametrize("tag,div,fft", [("fe", [2, 2, 2], [2, 2, 2]), ("random", [2, 2, 2], [3, 3, 3])])
+def test_ohmic_fermi_sea_vs_upstream_golden(tag, div, fft):
+    """Ohmic_FermiSea (InvMass: Xbar('Ham', 2) + generalised derivative, elementary.py:28-34, formula.py:95-112)
+    against the reference's own golden files {Fe_W90,random}-conductivity_ohmic_iter-0000.npz."""
+    g = np.load(os.path.join(GOLDEN, "golden_ohmic_sea.npz"))
+    system = orc.OracleSystem.from_npz(os.path.join(GOLDEN, "fe_system.npz" if tag == "fe" else "random_system.npz"))
+    Ef = g[f"{tag}_Efermi"]
+    res = orc.run(system, div, fft, dict(a=("Ohmic_FermiSea", Ef, {}), b=("Ohmic_FermiSea", Ef, dict(degen_thresh=0.05))))
+    assert relerr(res["a"], g[f"{tag}_upstream_golden_ohmic"]) < RTOL
+    assert relerr(res["b"], g[f"{tag}_ohmic_thresh"]) < RTOL

@@ -9,9 +9,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwbgpu.so")
 
 # enums of include/wbgpu.h
-IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN, KUBO, VEL_VEL = range(9)
+IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN, KUBO, VEL_VEL, INV_MASS = range(10)
 KUBO_OPTCOND, KUBO_JDOS = 0, 1
-FORMULA_RANK = {IDENTITY: 0, OMEGA: 1, MORB_HPM: 1, SPIN: 1, VEL_OMEGA: 2, VEL_HPLUS: 2, VEL_SPIN: 2, VEL_VEL: 2}
+FORMULA_RANK = {IDENTITY: 0, OMEGA: 1, MORB_HPM: 1, SPIN: 1, VEL_OMEGA: 2, VEL_HPLUS: 2, VEL_SPIN: 2, VEL_VEL: 2,
+                INV_MASS: 2}
 KEYS = {"Ham": 0, "AA": 1, "BB": 2, "CC": 3, "SS": 4}
 CHANNELS = {"Ham": 0, "dHam": 1, "AA": 2, "rotAA": 3, "BB": 4, "CC": 5, "SS": 6}
 

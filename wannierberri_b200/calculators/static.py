@@ -16,6 +16,7 @@ _TR_INV = {  # transformTR, transformInv of the formulae (covariant.py)
     _lib.IDENTITY: ("ident", "ident"), _lib.OMEGA: ("odd", "ident"), _lib.MORB_HPM: ("odd", "ident"),
     _lib.SPIN: ("odd", "ident"), _lib.VEL_OMEGA: ("ident", "odd"), _lib.VEL_HPLUS: ("ident", "odd"),
     _lib.VEL_SPIN: ("ident", "odd"), _lib.VEL_VEL: ("ident", "ident"),
+    _lib.INV_MASS: ("ident", "ident"),
 }
 
 
@@ -228,8 +229,19 @@ class Ohmic_FermiSurf(StaticCalculator):
         super().__init__(constant_factor=constant_factor, **kwargs)
 
 
+class Ohmic_FermiSea(StaticCalculator):
+    r"""Ohmic conductivity (:math:`S/m`), Fermi sea integral
+
+        | Output: :math:`\sigma_{\alpha\beta} = e^2/\hbar \tau \int [dk] \partial_\beta v_\alpha f`"""
+
+    def __init__(self, constant_factor=factors.factor_ohmic, **kwargs):
+        self.Formula = _lib.INV_MASS
+        self.fder = 0
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
 _BY_NAME = {c.__name__: c for c in (DOS, CumDOS, Spin, AHC, Morb, BerryDipole_FermiSurf, GME_orb_FermiSurf,
-                                    GME_spin_FermiSurf, Ohmic_FermiSurf)}
+                                    GME_spin_FermiSurf, Ohmic_FermiSurf, Ohmic_FermiSea)}
 
 
 def adapt(calc):

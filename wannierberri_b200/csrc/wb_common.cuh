@@ -57,7 +57,14 @@ struct WbLayout {
     int off_B[3];    // full
     int off_C[3];    // full
     int off_S[3];    // hermitian
+    int off_W[6];    // d_b d_d H, (b, d) = xx xy xz yy yz zz; packed like d_a H (triangle iff dH_herm)
 };
+
+// index of the symmetric pair (b, d) in off_W
+__host__ __device__ __forceinline__ int wb_sym6(int b, int d) {
+    const int lo = b < d ? b : d, hi = b < d ? d : b;
+    return lo * 3 - (lo * (lo - 1)) / 2 + (hi - lo);
+}
 
 // load element (i,j) of a channel of a record
 __device__ __forceinline__ cplx load_herm(const cplx* __restrict__ rec, int off, int i, int j, int nw) {

@@ -24,14 +24,16 @@ struct WbEventLayout {
 
 // which rotated matrices a formula mask needs
 struct WbNeeds {
-    bool V, A, B, Odiag, Cdiag, Sdiag, Oblk, Cblk, Sblk, D;
+    bool V, A, B, Odiag, Cdiag, Sdiag, Oblk, Cblk, Sblk, D, Wdiag, Wblk;
 };
 __host__ __device__ inline WbNeeds wb_needs(int mask, int external) {
     auto has = [&](int f) { return (mask >> f) & 1; };
-    bool omega = has(1), morb = has(2), vo = has(3), vh = has(4), vs = has(5), spin = has(6), vv = has(8);
+    bool omega = has(1), morb = has(2), vo = has(3), vh = has(4), vs = has(5), spin = has(6), vv = has(8), im = has(9);
     WbNeeds n;
     n.D = omega || morb || vo || vh;
-    n.V = n.D || vs || vv;
+    n.V = n.D || vs || vv || im;
+    n.Wdiag = im;
+    n.Wblk = false;
     n.A = n.D && external;
     n.B = (morb || vh) && external;
     n.Oblk = (vo || vh) && external;
@@ -49,8 +51,8 @@ __host__ __device__ inline int wb_generic_nfull(const WbNeeds& n) {
 }
 __host__ inline size_t wb_generic_smem_bytes(int nw, int mask, int external) {
     WbNeeds n = wb_needs(mask, external);
-    size_t cplx_el = (size_t)(3 + wb_generic_nfull(n)) * nw * nw + 9 * (size_t)nw;  // U, X, Y, fulls, diag O/C/S
-    size_t dbl = 2 * (size_t)nw + 3 * (size_t)nw + 36 * (size_t)nw + 3 * (size_t)(nw + 1) + (size_t)nw * nw;  // Es, label, rows[3], prod[36], Tedge, inv
+    size_t cplx_el = (size_t)(3 + wb_generic_nfull(n)) * nw * nw + 15 * (size_t)nw;  // U, X, Y, fulls, diag O/C/S/W
+    size_t dbl = 2 * (size_t)nw + 3 * (size_t)nw + 45 * (size_t)nw + 3 * (size_t)(nw + 1) + (size_t)nw * nw;  // Es, label, rows[3], prod[36], Tedge, inv
     return cplx_el * sizeof(cplx) + dbl * sizeof(double) + 2 * nw * sizeof(short) + 64;
 }
 
@@ -60,6 +62,7 @@ __host__ inline size_t wb_generic_smem_bytes(int nw, int mask, int external) {
 struct WbRotated {
     const cplx *Vb, *Ab, *Bb, *Ob, *Cb, *Sb;   // full blocks
     const cplx *Od, *Cd, *Sd;                  // diagonals (used when the corresponding block is absent)
+    const cplx *Wb, *Wd;                       // second derivative of H: [6][nw*nw] blocks or [6][nw] diagonals
     const double* Es;
     const double* label;
     double *rows, *prod, *Tedge;
@@ -80,12 +83,14 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
     double *rows = R.rows, *prod = R.prod, *Tedge = R.Tedge;
     const short *g1 = R.g1, *g2 = R.g2;
     const bool f_omega = (ev.mask >> 1) & 1, f_morb = (ev.mask >> 2) & 1, f_vo = (ev.mask >> 3) & 1,
-               f_vh = (ev.mask >> 4) & 1, f_vs = (ev.mask >> 5) & 1, f_spin = (ev.mask >> 6) & 1, f_vv = (ev.mask >> 8) & 1;
+               f_vh = (ev.mask >> 4) & 1, f_vs = (ev.mask >> 5) & 1, f_spin = (ev.mask >> 6) & 1, f_vv = (ev.mask >> 8) & 1,
+               f_im = (ev.mask >> 9) & 1;
     const bool internal = ev.internal_terms, external = ev.external_terms;
     // diagonal accessors that work for both storage modes
     auto Odg = [&](int c, int n) { return need.Oblk ? Ob[c * n2 + n * nw + n] : Od[c * nw + n]; };
     auto Cdg = [&](int c, int n) { return need.Cblk ? Cb[c * n2 + n * nw + n] : Cd[c * nw + n]; };
     auto Sdg = [&](int c, int n) { return need.Sblk ? Sb[c * n2 + n * nw + n] : Sd[c * nw + n]; };
+    auto Wdg = [&](int c6, int n) { return need.Wblk ? R.Wb[c6 * n2 + n * nw + n] : R.Wd[c6 * nw + n]; };
     // dEig_inv once per k-point (data_K.py:290-298): the formulae below read every element many times
     double* const inv = R.inv;
     for (int x = threadIdx.x; x < n2; x += NT) inv[x] = wb_deinv(Es[x / nw], Es[x % nw]);
@@ -152,7 +157,7 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
     for (int x = threadIdx.x / LG; x < 3 * nw; x += NT / LG) {
         int c = x / nw, M = x % nw;
         double tr_omega = 0.;
-        double pv[3] = {0., 0., 0.}, ph[3] = {0., 0., 0.}, ps[3] = {0., 0., 0.}, pw[3] = {0., 0., 0.};
+        double pv[3] = {0., 0., 0.}, ph[3] = {0., 0., 0.}, ps[3] = {0., 0., 0.}, pw[3] = {0., 0., 0.}, pm[3] = {0., 0., 0.};
         if (g1[M] >= 0) {
             const int ga = g1[M], gb = g2[M];
             if (f_omega) {
@@ -184,6 +189,22 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
                 for (int Lb = ga; Lb < gb; Lb++)
                     for (int a = 0; a < 3; a++) ps[a] += cmul(Vb[a * n2 + Lb * nw + M], Sb[c * n2 + M * nw + Lb]).x;
             }
+            if (f_im) {
+                // InvMass (elementary.py:28-34, formula.py:108-112), trace over the group, b = c:
+                //   W_MM,bd + sum_{l notin group} ( -D_Ml,d V_lM,b + V_Ml,b D_lM,d ) = W_MM,bd + sum_l (V_Ml,d V_lM,b + V_Ml,b V_lM,d) / (E_M - E_l)
+                for (int l = lgid; l < nw; l += LG) {
+                    if (l >= ga && l < gb) continue;
+                    const double iv = inv[M * nw + l];
+                    const cplx VMlb = Vb[c * n2 + M * nw + l], VlMb = Vb[c * n2 + l * nw + M];
+                    for (int d = 0; d < 3; d++)
+                        pm[d] += iv * (cmul(Vb[d * n2 + M * nw + l], VlMb).x + cmul(VMlb, Vb[d * n2 + l * nw + M]).x);
+                }
+                for (int d = 0; d < 3; d++) {
+#pragma unroll
+                    for (int o = 1; o < LG; o <<= 1) pm[d] += __shfl_xor_sync(gmask, pm[d], o);
+                    pm[d] += Wdg(wb_sym6(c, d), M).x;
+                }
+            }
             if (f_vv) {   // VelVel: sum_{L in group} V_LM,a V_ML,c
                 for (int Lb = ga; Lb < gb; Lb++)
                     for (int a = 0; a < 3; a++) pw[a] += cmul(Vb[a * n2 + Lb * nw + M], Vb[c * n2 + M * nw + Lb]).x;
@@ -192,10 +213,11 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
         if (lgid == 0) {
             rows[c * nw + M] = tr_omega;
             for (int a = 0; a < 3; a++) {  // component (a, b = c) of the rank-2 products
-                prod[M * 36 + a * 3 + c] = pv[a];
-                prod[M * 36 + 9 + a * 3 + c] = ph[a];
-                prod[M * 36 + 18 + a * 3 + c] = ps[a];
-                prod[M * 36 + 27 + a * 3 + c] = pw[a];
+                prod[M * 45 + a * 3 + c] = pv[a];
+                prod[M * 45 + 9 + a * 3 + c] = ph[a];
+                prod[M * 45 + 18 + a * 3 + c] = ps[a];
+                prod[M * 45 + 27 + a * 3 + c] = pw[a];
+                prod[M * 45 + 36 + c * 3 + a] = pm[a];   // InvMass [b = c][d = a]
             }
         }
     }
@@ -267,15 +289,17 @@ __device__ __forceinline__ void wb_formula_events(const WbRotated& R, const WbNe
                     for (int n = x; n < b; n++) s += Sdg(c, n).x;
                     out[ev.off[6] + c] = s;
                 }
-            if (f_vo || f_vh || f_vs || f_vv)
+            if (f_vo || f_vh || f_vs || f_vv || f_im)
                 for (int ab = 0; ab < 9; ab++) {
-                    double so = 0., sh = 0., ss = 0., sv = 0.;
+                    double so = 0., sh = 0., ss = 0., sv = 0., sm = 0.;
                     for (int n = x; n < b; n++) {
-                        so += prod[n * 36 + ab];
-                        sh += prod[n * 36 + 9 + ab];
-                        ss += prod[n * 36 + 18 + ab];
-                        sv += prod[n * 36 + 27 + ab];
+                        so += prod[n * 45 + ab];
+                        sh += prod[n * 45 + 9 + ab];
+                        ss += prod[n * 45 + 18 + ab];
+                        sv += prod[n * 45 + 27 + ab];
+                        sm += prod[n * 45 + 36 + ab];
                     }
+                    if (f_im) out[ev.off[9] + ab] = sm;
                     if (f_vo) out[ev.off[3] + ab] = so;
                     if (f_vh) out[ev.off[4] + ab] = sh;
                     if (f_vs) out[ev.off[5] + ab] = ss;
@@ -306,11 +330,12 @@ wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, cons
     cplx* Od = p; p += 3 * nw;
     cplx* Cd = p; p += 3 * nw;
     cplx* Sd = p; p += 3 * nw;
+    cplx* Wd = p; p += 6 * nw;
     double* Es = (double*)p;
     double* label = Es + nw;
     double* rows = label + nw;         // [3][nw]   per-band Omega trace terms
-    double* prod = rows + 3 * nw;      // [nw][36]  per-band partial products: VelOmega 9 | VelHplus 9 | VelSpin 9 | VelVel 9
-    double* Tedge = prod + 36 * nw;    // [3][nw+1] cumulative non-additive traces
+    double* prod = rows + 3 * nw;      // [nw][45]  per-band partial products: VelOmega 9 | VelHplus 9 | VelSpin 9 | VelVel 9 | InvMass 9
+    double* Tedge = prod + 45 * nw;    // [3][nw+1] cumulative non-additive traces
     double* invtab = Tedge + 3 * (nw + 1);   // [nw][nw]
     short* g1 = (short*)(invtab + n2);
     short* g2 = g1 + nw;
@@ -330,8 +355,8 @@ wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, cons
                 wb_rotate_smem<NT>(Us, Xs, Ys, dst + a * n2, nw);
             }
         };
-        auto rotate_diag = [&](const int* offs, bool herm, cplx* dst) {
-            for (int c = 0; c < 3; c++) {
+        auto rotate_diag = [&](const int* offs, bool herm, cplx* dst, int ncomp = 3) {
+            for (int c = 0; c < ncomp; c++) {
                 wb_load_channel<NT>(r, offs[c], herm, Xs, nw);
                 for (int x = threadIdx.x; x < n2; x += NT) {
                     int i = x / nw, l = x % nw;
@@ -357,9 +382,11 @@ wb_events_generic_kernel(const cplx* __restrict__ rec, WbLayout L, long nk, cons
         if (need.Odiag) rotate_diag(L.off_O, true, Od);
         if (need.Cdiag) rotate_diag(L.off_C, false, Cd);
         if (need.Sdiag) rotate_diag(L.off_S, true, Sd);
+        if (need.Wdiag) rotate_diag(L.off_W, L.dH_herm, Wd, 6);
         __syncthreads();
         WbRotated R;
         R.Vb = Vb; R.Ab = Ab; R.Bb = Bb; R.Ob = Ob; R.Cb = Cb; R.Sb = Sb; R.Od = Od; R.Cd = Cd; R.Sd = Sd;
+        R.Wb = nullptr; R.Wd = Wd;
         R.Es = Es; R.label = label; R.rows = rows; R.prod = prod; R.Tedge = Tedge;
         R.Mx = (double*)Xs;   // [3][n2] doubles = 1.5 n2 complex: Xs and half of Ys, both free now
         R.inv = invtab;

@@ -68,6 +68,15 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
                 else atomic_cadd(&table[cellR * E + L.off_dH[a] + i * nw + j], d);
             }
         }
+        if (L.off_W[0] >= 0) {   // second comma-derivative: i T_d (i T_b H) = -T_b T_d H   (rvectors.py:487-494, twice)
+            for (int b = 0; b < 3; b++)
+                for (int d = b; d < 3; d++) {
+                    const cplx w = cmake(-(T[d] * (T[b] * h.x)), -(T[d] * (T[b] * h.y)));
+                    const int off = L.off_W[wb_sym6(b, d)];
+                    if (L.dH_herm) add_herm(table, cellR, cellmR, E, off, i, j, nw, w);
+                    else atomic_cadd(&table[cellR * E + off + i * nw + j], w);
+                }
+        }
     }
     if (in.AA && L.off_A[0] >= 0) {
         cplx A[3];

@@ -17,8 +17,8 @@
 
 struct WbChanList {
     int n;
-    int off[18];    // record offset (complex elements) of the matrix
-    int herm[18];   // upper-triangle packed
+    int off[24];    // record offset (complex elements) of the matrix
+    int herm[24];   // upper-triangle packed
 };
 
 __device__ __forceinline__ void wb_dmma_acc(double& d0, double& d1, double a, double b) {
@@ -167,11 +167,13 @@ wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
     need.Cblk = need.Cblk || need.Cdiag;
     need.Sblk = need.Sblk || need.Sdiag;
     need.Odiag = need.Cdiag = need.Sdiag = false;
+    need.Wblk = need.Wdiag;
+    need.Wdiag = false;
     double* Es = small;
     double* label = Es + nw;
     double* rows = label + nw;
     double* prod = rows + 3 * nw;
-    double* Tedge = prod + 36 * nw;
+    double* Tedge = prod + 45 * nw;
     double* invtab = Tedge + 3 * (nw + 1);   // [nw][nw]
     short* g1 = (short*)(invtab + n2);
     short* g2 = g1 + nw;
@@ -198,6 +200,8 @@ wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
         R.Ob = next(need.Oblk);
         R.Cb = next(need.Cblk);
         R.Sb = next(need.Sblk);
+        R.Wb = gsrc + (size_t)it * 3 * n2;   // six matrices after the triples
+        R.Wd = nullptr;
         R.Od = R.Cd = R.Sd = nullptr;
         R.Es = Es; R.label = label; R.rows = rows; R.prod = prod; R.Tedge = Tedge;
         R.Mx = mx_scratch + (size_t)blockIdx.x * 3 * n2;
@@ -209,6 +213,6 @@ wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
 }
 
 __host__ inline size_t wb_xbar_events_smem_bytes(int nw) {
-    return sizeof(double) * ((size_t)2 * nw + 3 * nw + 36 * nw + 3 * (nw + 1) + (size_t)nw * nw) +
+    return sizeof(double) * ((size_t)2 * nw + 3 * nw + 45 * nw + 3 * (nw + 1) + (size_t)nw * nw) +
            2 * nw * sizeof(short) + 64;
 }

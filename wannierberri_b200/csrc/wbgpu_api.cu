@@ -262,7 +262,7 @@ static int formula_rank(int f) {
     switch (f) {
         case WBGPU_IDENTITY: return 0;
         case WBGPU_OMEGA: case WBGPU_MORB_HPM: case WBGPU_SPIN: return 1;
-        case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: case WBGPU_VEL_VEL: return 2;
+        case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: case WBGPU_VEL_VEL: case WBGPU_INV_MASS: return 2;
     }
     return -1;
 }
@@ -305,7 +305,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     const uint32_t m = formula_mask;
     auto has = [&](int f) { return (m >> f) & 1u; };
     bool need_dH = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
-                   has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO) || has(WBGPU_VEL_VEL);
+                   has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO) || has(WBGPU_VEL_VEL) || has(WBGPU_INV_MASS);
     bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) || has(WBGPU_KUBO);
     bool need_A = berry && external_terms;
     bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS)) && external_terms;
@@ -356,6 +356,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     for (int a = 0; a < 3; a++) L.off_B[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_C[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_S[a] = need_S ? take(true) : -1;
+    for (int a = 0; a < 6; a++) L.off_W[a] = has(WBGPU_INV_MASS) ? take(dH_herm) : -1;
     L.E = off;
     c->L = L;
     c->mask = m;
@@ -793,6 +794,8 @@ static int run_events_xbar(wbgpu_ctx* c, const EvGroup& G, long nk) {
     if (need.Oblk || need.Odiag) add3(L.off_O, true);
     if (need.Cblk || need.Cdiag) add3(L.off_C, false);
     if (need.Sblk || need.Sdiag) add3(L.off_S, true);
+    if (need.Wdiag)
+        for (int a = 0; a < 6; a++) { ch.off[ch.n] = L.off_W[a]; ch.herm[ch.n] = L.dH_herm; ch.n++; }
     const long chunk = xbar_chunk(c, ch.n, nk);
     if (ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * nw * nw)) return 1;
     constexpr int NT = 128;
@@ -834,7 +837,7 @@ static int run_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
     const WbLayout& L = c->L;
     if ((need.V && L.off_dH[0] < 0) || (need.A && L.off_A[0] < 0) || (need.B && L.off_B[0] < 0) ||
         ((need.Oblk || need.Odiag) && L.off_O[0] < 0) || ((need.Cblk || need.Cdiag) && L.off_C[0] < 0) ||
-        ((need.Sblk || need.Sdiag) && L.off_S[0] < 0))
+        ((need.Sblk || need.Sdiag) && L.off_S[0] < 0) || (need.Wdiag && L.off_W[0] < 0))
         return set_err("scan: the plan does not hold the channels that formula mask 0x%x needs", G.ev.mask);
     if (G.win.Ebmin) return run_events_xbar(c, G, nk);   // tetrahedron band groups: size-generic path
     // compile-time-NW tensor-core kernel (Omega and/or Morb_Hpm)
@@ -1101,6 +1104,7 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
     WbLayout LH;
     LH.nw = nw; LH.ntri = nw * (nw + 1) / 2; LH.E = LH.ntri; LH.off_H = 0; LH.dH_herm = 0;
     for (int a = 0; a < 3; a++) LH.off_dH[a] = LH.off_A[a] = LH.off_O[a] = LH.off_B[a] = LH.off_C[a] = LH.off_S[a] = -1;
+    for (int a = 0; a < 6; a++) LH.off_W[a] = -1;
     const size_t ncell = (size_t)c->nbox.x * c->nbox.y * c->nbox.z;
     if (!c->d_tableH) {
         CK(cudaMalloc(&c->d_tableH, sizeof(cplx) * ncell * LH.E));
