@@ -23,9 +23,15 @@ def main():
     Ef = np.linspace(17, 18, 11)
     st = calc.static
     out = dict(Efermi=Ef, NK=np.array([4, 4, 4]), NKFFT=np.array([2, 2, 2]))
-    for n_iter in (1, 2, 3):
+    for n_iter, full_set in ((1, False), (2, False), (3, False), (1, True), (2, True), (3, True)):
         calcs = dict(ahc=st.AHC(Efermi=Ef), dos=st.DOS(Efermi=Ef), cumdos=st.CumDOS(Efermi=Ef), Morb=st.Morb(Efermi=Ef),
                      spin=st.Spin(Efermi=Ef))
+        if full_set:   # the calculator set of the reference's own test (tests/test_run.py:119-129, 557-578)
+            test_kw = dict(kwargs_formula=dict(FF_rotAA=True, CCab_antisym=True))
+            calcs = dict(ahc=st.AHC(Efermi=Ef), ahc_test=st.AHC_test(Efermi=Ef, **test_kw),
+                         conductivity_ohmic=st.Ohmic_FermiSea(Efermi=Ef), conductivity_ohmic_fsurf=st.Ohmic_FermiSurf(Efermi=Ef),
+                         Morb=st.Morb(Efermi=Ef), Morb_test=st.Morb_test(Efermi=Ef, **test_kw), dos=st.DOS(Efermi=Ef),
+                         cumdos=st.CumDOS(Efermi=Ef), spin=st.Spin(Efermi=Ef))
         cwd = os.getcwd()
         with tempfile.TemporaryDirectory() as tmp:
             os.chdir(tmp)
@@ -37,9 +43,11 @@ def main():
             finally:
                 os.chdir(cwd)
         for q in calcs:
+            if q.endswith("_test"):
+                continue
             got = res.results[q].data
-            out[f"iter{n_iter}_{q}"] = got
-            if n_iter == 1:
+            out[f"{'full_' if full_set else ''}iter{n_iter}_{q}"] = got
+            if n_iter == 1 or full_set:
                 ref = np.load(os.path.join(REF, "tests/reference/integrate_files", f"Fe_W90_sym-{q}_iter-{n_iter:04d}.npz"))["data"]
                 err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)
                 print(f"Fe_W90_sym-{q}_iter-{n_iter:04d}: live reference run vs reference golden file: rel err {err:.2e}")
