@@ -554,6 +554,36 @@ def test_ohmic_fermi_sea_vs_upstream_golden(wb, fe, tag, rotate_method):
         assert relerr(res.results[q].data, g[f"{tag}_{q}"]) < RTOL, q
 
 
+def test_te_qe_tetra_symmetric_vs_upstream_goldens(wb):
+    """The reference's Te test (tests/test_run.py:1101-1119; BASELINE config 3 family): 24-WF spinor system, tetrahedron
+    method, symmetry-reduced K-list (point group C3z, C2x, TimeReversal) + symmetrisation, NK = [3,3,4] with
+    NKFFT = [1,1,4] -- against the reference's own golden files Te_QE-{dos,cumdos,GME_orb_FermiSurf}_iter-0000.npz and
+    the other quantities of the live reference run (tests/golden/make_golden_te_qe.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_te_qe.npz"))
+    te = wb.System_R.from_npz(os.path.join(GOLDEN, "te_system.npz"), pointgroup=["C3z", "C2x", "TimeReversal"])
+    grid = wb.Grid(te, NK=[3, 3, 4], NKFFT=[1, 1, 4])
+    shifts, factors = grid.K_arrays(use_symmetry=True)
+    assert np.array_equal(shifts, g["K_list_Kp_fullBZ"]) and np.array_equal(factors, g["K_list_factor"])
+    Ef = g["Efermi"]
+    st = wb.calculators.static
+    calcs = dict(dos=st.DOS(Efermi=Ef, tetra=True), cumdos=st.CumDOS(Efermi=Ef, tetra=True),
+                 GME_orb_FermiSurf=st.GME_orb_FermiSurf(Efermi=Ef, tetra=True),
+                 GME_spin_FermiSurf=st.GME_spin_FermiSurf(Efermi=Ef, tetra=True),
+                 berry_dipole_fsurf=st.BerryDipole_FermiSurf(Efermi=Ef, tetra=True), ahc=st.AHC(Efermi=Ef, tetra=True))
+    res = wb.run(te, grid, calcs, use_irred_kpt=True, symmetrize=True)
+    der1 = ("dos", "GME_orb_FermiSurf", "GME_spin_FermiSurf", "berry_dipole_fsurf")   # der = 1 tetrahedron weights: 1e-6
+    for q in calcs:
+        tol = 1e-6 if q in der1 else RTOL
+        scale = np.abs(g[q]).max()
+        if q == "ahc":   # forbidden by time reversal: rounding noise (~1e-9 S/m) in the reference and here
+            assert scale < 1e-6 and np.abs(res.results[q].data).max() < 1e-6, q
+            continue
+        assert np.abs(res.results[q].data - g[q]).max() <= tol * scale, q
+        if "upstream_golden_" + q in g.files:
+            ref = g["upstream_golden_" + q]
+            assert np.abs(res.results[q].data - ref).max() <= tol * np.abs(ref).max(), q
+
+
 def test_ohmic_fsurf_vs_upstream_golden(wb, fe):
     """Ohmic_FermiSurf (formula VelVel) against the reference's own golden file
     Fe_W90-conductivity_ohmic_fsurf_iter-0000.npz, with degenerate groups, and with the tetrahedron method."""
