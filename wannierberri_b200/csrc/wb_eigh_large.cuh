@@ -240,9 +240,29 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
                     if (tid < len2) rs[((s + 1) & 1) * 128 + tid] = myrot[r0 + len + tid];
                 }
                 if (tid < n) {
+                    // rotation i touches columns i, i+1 of this thread's row; the loads of a batch of four columns
+                    // are issued before the stores of the batch (distinct addresses, but the compiler cannot know)
                     const double2* q = rs + (s & 1) * 128;
                     double carry = Zs[m * n + tid];
-                    for (int i = m - 1; i >= l; i--) {
+                    int i = m - 1;
+                    for (; i - 3 >= l; i -= 4) {
+                        const double z0 = Zs[i * n + tid], z1 = Zs[(i - 1) * n + tid], z2 = Zs[(i - 2) * n + tid],
+                                     z3 = Zs[(i - 3) * n + tid];
+                        const double2 c0 = q[m - 1 - i], c1 = q[m - i], c2 = q[m + 1 - i], c3 = q[m + 2 - i];
+                        const double o0 = c0.y * z0 + c0.x * carry;
+                        carry = c0.x * z0 - c0.y * carry;
+                        const double o1 = c1.y * z1 + c1.x * carry;
+                        carry = c1.x * z1 - c1.y * carry;
+                        const double o2 = c2.y * z2 + c2.x * carry;
+                        carry = c2.x * z2 - c2.y * carry;
+                        const double o3 = c3.y * z3 + c3.x * carry;
+                        carry = c3.x * z3 - c3.y * carry;
+                        Zs[(i + 1) * n + tid] = o0;
+                        Zs[i * n + tid] = o1;
+                        Zs[(i - 1) * n + tid] = o2;
+                        Zs[(i - 2) * n + tid] = o3;
+                    }
+                    for (; i >= l; i--) {
                         const double2 cs = q[m - 1 - i];
                         const double zi = Zs[i * n + tid];
                         Zs[(i + 1) * n + tid] = cs.y * zi + cs.x * carry;
