@@ -271,3 +271,22 @@ def test_ohmic_fermi_sea_vs_upstream_golden(tag, div, fft):
     res = orc.run(system, div, fft, dict(a=("Ohmic_FermiSea", Ef, {}), b=("Ohmic_FermiSea", Ef, dict(degen_thresh=0.05))))
     assert relerr(res["a"], g[f"{tag}_upstream_golden_ohmic"]) < RTOL
     assert relerr(res["b"], g[f"{tag}_ohmic_thresh"]) < RTOL
+
+
+SHC_CASES = dict(ref_qiao=("qiao", "ref", {}), ref_ryoo=("ryoo", "ref", {}), in_qiao=("qiao", "in", {}), in_ryoo=("ryoo", "in", {}),
+                 in_simple=("simple", "in", {}), in_ryoo_thresh=("ryoo", "in", dict(degen_thresh=0.3)))
+
+
+@pytest.mark.parametrize("case", sorted(SHC_CASES))
+def test_shc_random_system(case):
+    """Kubo spin Hall conductivity (calculators/dynamic.py:204-237, formula/covariant.py:689-756) on the reference's
+    `random` system: the three spin-current types against the live reference run of make_golden_shc.py and, for
+    qiao / ryoo, the reference's own golden files random-opt_SHC{qiao,ryoo}_iter-0000.npz."""
+    g = np.load(os.path.join(GOLDEN, "golden_random_shc.npz"))
+    rnd = orc.OracleSystem.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    t, ax, extra = SHC_CASES[case]
+    kw = dict(omega=g["omega"], smr_fixed_width=0.20, smr_type="Gaussian" if ax == "ref" else "Lorentzian", SHC_type=t, **extra)
+    res = orc.run(rnd, [2, 2, 2], [3, 3, 3], dict(a=("SHC", g[ax + "_Efermi"], kw)))
+    assert relerr(res["a"], g[case]) < RTOL
+    if ax == "ref":
+        assert relerr(res["a"], g["upstream_golden_" + t]) < RTOL
