@@ -54,11 +54,16 @@ enum {
     WBGPU_VEL_VEL = 8,    /* VelVel          covariant.py:817-820 rank 2 */
     WBGPU_INV_MASS = 9,   /* InvMass         elementary.py:28-34 (generalised derivative of the velocity, needs
                              the second comma-derivative of H) rank 2 */
-    WBGPU_NFORMULA = 10
+    WBGPU_SHC_RYOO = 10,  /* plan flags only: channels of dynamic.SHC with the spin current of Ryoo et al. (SA, SHA), */
+    WBGPU_SHC_QIAO = 11,  /*   of Qiao et al. (SH, SR, SHR),                                                          */
+    WBGPU_SHC_SIMPLE = 12,/*   and {S, v}/2 (SS only); all need dH, SS and (external terms) AA                        */
+    WBGPU_NFORMULA = 13
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */
-enum { WBGPU_HAM = 0, WBGPU_AA = 1, WBGPU_BB = 2, WBGPU_CC = 3, WBGPU_SS = 4, WBGPU_NKEYS = 5 };
+enum { WBGPU_HAM = 0, WBGPU_AA = 1, WBGPU_BB = 2, WBGPU_CC = 3, WBGPU_SS = 4,
+       /* spin-current matrices of the Kubo spin Hall conductivity (formula/covariant.py:729-756) */
+       WBGPU_SA = 5, WBGPU_SHA = 6, WBGPU_SR = 7, WBGPU_SH = 8, WBGPU_SHR = 9, WBGPU_NKEYS = 10 };
 
 /* Wannier-gauge k-space channels that wbgpu_xk can return (parity probe) */
 enum {
@@ -99,7 +104,8 @@ int wbgpu_create(wbgpu_ctx** ctx, int device, int nw, int nR, const int32_t* iRv
                  const double* cRvec_shifted, double cell_volume, void* stream);
 int wbgpu_destroy(wbgpu_ctx* ctx);
 
-/* Copy one R-space matrix to the device: X_R[nR][nw][nw][ncart] complex128, ncart = 1 (Ham) or 3. */
+/* Copy one R-space matrix to the device: X_R[nR][nw][nw][ncart] complex128, ncart = 1 (Ham), 3 (AA, BB, CC, SS, SH)
+ * or 9 (SA, SHA, SR, SHR: [3 velocity][3 spin]). */
 int wbgpu_set_R_matrix(wbgpu_ctx* ctx, int key, const double* X_R, int ncart);
 
 /* Fix the FFT sub-grid NKFFT[3] and the set of formulae that will be evaluated
@@ -135,14 +141,17 @@ int wbgpu_static_scan_tetra(wbgpu_ctx* ctx, int nblocks, const double* dK, const
                             const wbgpu_scan_spec* specs, int nspec, double* out);
 
 /* One (Efermi x omega) scan = one DynamicCalculator.__call__ (calculators/dynamic.py:26-114) at kBT = 0. */
-enum { WBGPU_KUBO_OPTCOND = 0,  /* OpticalConductivity dynamic.py:184-196: complex128 data[nEF][nomega][3][3] */
-       WBGPU_KUBO_JDOS = 1 };   /* JDOS                dynamic.py:146-162: float64    data[nEF][nomega]       */
+enum { WBGPU_KUBO_OPTCOND = 0,  /* OpticalConductivity dynamic.py:184-196: complex128 data[nEF][nomega][3][3]    */
+       WBGPU_KUBO_JDOS = 1,     /* JDOS                dynamic.py:146-162: float64    data[nEF][nomega]          */
+       WBGPU_KUBO_SHC = 2 };    /* SHC                 dynamic.py:204-237: complex128 data[nEF][nomega][3][3][3] */
 typedef struct wbgpu_kubo_spec {
     int32_t kind;            /* WBGPU_KUBO_*                                   */
     int32_t nEF, nomega;
     int32_t smr_type;        /* 0 = Lorentzian, 1 = Gaussian (dynamic.py:49-54) */
     int32_t degen_Kramers;
     int32_t external_terms;  /* kwargs_formula (formula.py:11-29)               */
+    int32_t shc_type;        /* SHC only: WBGPU_SHC_RYOO / _QIAO / _SIMPLE      */
+    int32_t reserved;
     double smr_fixed_width;
     double degen_thresh;
     double factor;           /* constant_factor                                */

@@ -40,14 +40,16 @@ class OracleEngine:
         return [np.array([self.scan([d], [1.], [s])[0] for d in dK]).reshape((len(dK),) + s.shape) for s in specs]
 
     def kubo_scan(self, dK, weight, spec, Efermi, omega):
-        kind = {_lib.KUBO_OPTCOND: "opt_conductivity", _lib.KUBO_JDOS: "jdos"}[int(spec.kind)]
+        kind = {_lib.KUBO_OPTCOND: "opt_conductivity", _lib.KUBO_JDOS: "jdos", _lib.KUBO_SHC: "shc"}[int(spec.kind)]
+        shc_type = {v: k for k, v in _lib.SHC_TYPES.items()}.get(int(spec.shc_type), "ryoo")
         out = 0
         for d, w in zip(dK, weight):
             data = orc.OracleDataK(self.osys, d, self.NKFFT)
             out = out + w * orc.kubo_scan(data, kind, Efermi, omega, smr_fixed_width=spec.smr_fixed_width,
                                           smr_type="Lorentzian" if spec.smr_type == 0 else "Gaussian",
                                           degen_thresh=spec.degen_thresh, degen_Kramers=bool(spec.degen_Kramers),
-                                          external_terms=bool(spec.external_terms), constant_factor=spec.factor)
+                                          external_terms=bool(spec.external_terms), constant_factor=spec.factor,
+                                          SHC_type=shc_type)
         return out
 
 
@@ -72,6 +74,16 @@ def main():
     res = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), dict(oc=oc), parallel=True, device=0)
     ref = gk["upstream_golden_opt_conductivity"]
     assert np.abs(res.results["oc"].data - ref).max() / np.abs(ref).max() < 1e-8
+    # spin Hall conductivity on the reference's `random` system (rank-3 complex result), K-blocks sharded over the ranks
+    gs = np.load(os.path.join(GOLDEN, "golden_random_shc.npz"))
+    rnd = wb.System_R.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    eng3 = OracleEngine(orc.OracleSystem.from_npz(os.path.join(GOLDEN, "random_system.npz")))
+    sys.modules["wannierberri_b200.run"].engine_for = lambda system, device=0: eng3
+    shc = wb.calculators.dynamic.SHC(Efermi=gs["ref_Efermi"], omega=gs["omega"], smr_fixed_width=0.20, smr_type="Gaussian",
+                                     SHC_type="qiao")
+    res = wb.run(rnd, wb.Grid(rnd, NK=gs["NK"], NKFFT=gs["NKFFT"]), dict(shc=shc), parallel=True, device=0)
+    ref = gs["upstream_golden_qiao"]
+    assert np.abs(res.results["shc"].data - ref).max() / np.abs(ref).max() < 1e-8
     # adaptive refinement: the new K-points of every iteration are sharded, all ranks take the same decisions
     ga = np.load(os.path.join(GOLDEN, "golden_synth_adpt.npz"))
     sysg = wb.synthetic_system(6, rmax=1, seed=4242)

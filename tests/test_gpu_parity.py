@@ -359,6 +359,69 @@ def test_kubo_synthetic(wb, orc, nw, nEF, nom):
     assert relerr(got, orc.JDOS(odata, Ef, omega=om, **kw)) < RTOL
 
 
+# ---------------------------------------------------------------------------------------- Kubo spin Hall conductivity
+SHC_CASES = dict(ref_qiao=("qiao", "ref", {}), ref_ryoo=("ryoo", "ref", {}), in_qiao=("qiao", "in", {}), in_ryoo=("ryoo", "in", {}),
+                 in_simple=("simple", "in", {}), in_ryoo_thresh=("ryoo", "in", dict(degen_thresh=0.3)))
+
+
+def test_shc_random_system_vs_upstream_goldens(wb):
+    """dynamic.SHC (Kubo spin Hall conductivity, spin currents of Ryoo / Qiao / {S, v}/2) on the reference's `random`
+    system through run(), all six scans in one call: against the live reference run of make_golden_shc.py and the
+    reference's own golden files random-opt_SHC{qiao,ryoo}_iter-0000.npz (tests/test_run.py:653-669)."""
+    g = np.load(os.path.join(GOLDEN, "golden_random_shc.npz"))
+    rnd = wb.System_R.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    calcs = {}
+    for case, (t, ax, extra) in SHC_CASES.items():
+        calcs[case] = wb.calculators.dynamic.SHC(Efermi=g[ax + "_Efermi"], omega=g["omega"], smr_fixed_width=0.20,
+                                                 smr_type="Gaussian" if ax == "ref" else "Lorentzian", SHC_type=t, **extra)
+    calcs["abc"] = wb.calculators.dynamic.SHC(Efermi=g["in_Efermi"], omega=g["omega"], smr_fixed_width=0.20, SHC_type="ryoo",
+                                              shc_abc=(1, 2, 3))
+    res = wb.run(rnd, wb.Grid(rnd, NK=g["NK"], NKFFT=g["NKFFT"]), calcs)
+    for case, (t, ax, extra) in SHC_CASES.items():
+        got = res.results[case].data
+        assert got.shape == g[case].shape, case
+        assert relerr(got, g[case]) < RTOL, case
+        if ax == "ref":
+            assert relerr(got, g["upstream_golden_" + t]) < RTOL, case
+    assert res.results["abc"].data.shape == g["in_ryoo"].shape[:2]
+    assert relerr(res.results["abc"].data, g["in_ryoo"][:, :, 0, 1, 2]) < RTOL
+
+
+@pytest.mark.parametrize("nw,nEF,nom,external", [(14, 40, 45, True), (33, 7, 5, False)])
+def test_shc_synthetic(wb, orc, nw, nEF, nom, external):
+    """SHC on a synthetic model with the R <-> -R symmetry (hermitian-packed d_aH, SS channels), random spin-current
+    matrices, more bands than a warp and more frequencies than one omega tile, one K-block, against the oracle."""
+    sysg = wb.synthetic_system(nw, rmax=1, seed=900 + nw, matrices=("Ham", "AA", "SS"))
+    rng = np.random.default_rng(5 + nw)
+    nR = sysg.rvec.nRvec
+    for key, tail in (("SA", (3, 3)), ("SHA", (3, 3)), ("SR", (3, 3)), ("SH", (3,)), ("SHR", (3, 3))):
+        shape = (nR, nw, nw) + tail
+        sysg.set_R_mat(key, 0.1 * (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)))
+    syso = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
+                            {k: sysg.get_R_mat(k) for k in ("Ham", "AA", "SS", "SA", "SHA", "SR", "SH", "SHR")})
+    NKFFT, dK = [2, 2, 2], [0.05, 0.11, 0.02]
+    Ef, om = np.linspace(-1., 1., nEF), np.linspace(0., 5., nom)
+    grid = wb.Grid(sysg, NKdiv=[1, 1, 1], NKFFT=NKFFT)
+    data = wb.Data_K_R(sysg, dK=dK, grid=grid)
+    odata = orc.OracleDataK(syso, dK, NKFFT)
+    for t in ("ryoo", "qiao", "simple"):
+        kw = dict(smr_fixed_width=0.1, smr_type="Lorentzian")
+        got = wb.calculators.dynamic.SHC(Efermi=Ef, omega=om, SHC_type=t, kwargs_formula=dict(external_terms=external),
+                                         **kw)(data).data
+        ref = orc.SHC(odata, Ef, omega=om, SHC_type=t, external_terms=external, **kw)
+        assert got.shape == ref.shape == (nEF, nom, 3, 3, 3)
+        assert relerr(got, ref) < RTOL, t
+
+
+def test_shc_errors(wb, fe):
+    """unknown spin-current type (formula/covariant.py:696-697) and missing R-matrices (system_R.py:106-111)"""
+    with pytest.raises(ValueError):
+        wb.calculators.dynamic.SHC(Efermi=[0.], omega=[0.], SHC_type="other")
+    grid = wb.Grid(fe, NKdiv=[1, 1, 1], NKFFT=[2, 2, 2])
+    with pytest.raises(ValueError):   # the Fe fixture carries no SA / SHA
+        wb.calculators.dynamic.SHC(Efermi=[17.], omega=[0., 1.])(wb.Data_K_R(fe, dK=[0, 0, 0], grid=grid))
+
+
 # ---------------------------------------------------------------------------------------- tetrahedron method
 TETRA_CASES = dict(
     ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}), spin=("Spin", {}),

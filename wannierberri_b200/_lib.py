@@ -9,11 +9,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwbgpu.so")
 
 # enums of include/wbgpu.h
-IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN, KUBO, VEL_VEL, INV_MASS = range(10)
-KUBO_OPTCOND, KUBO_JDOS = 0, 1
+(IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN, KUBO, VEL_VEL, INV_MASS, SHC_RYOO, SHC_QIAO,
+ SHC_SIMPLE) = range(13)
+SHC_TYPES = {"ryoo": SHC_RYOO, "qiao": SHC_QIAO, "simple": SHC_SIMPLE}
+KUBO_OPTCOND, KUBO_JDOS, KUBO_SHC = 0, 1, 2
 FORMULA_RANK = {IDENTITY: 0, OMEGA: 1, MORB_HPM: 1, SPIN: 1, VEL_OMEGA: 2, VEL_HPLUS: 2, VEL_SPIN: 2, VEL_VEL: 2,
                 INV_MASS: 2}
-KEYS = {"Ham": 0, "AA": 1, "BB": 2, "CC": 3, "SS": 4}
+KEYS = {"Ham": 0, "AA": 1, "BB": 2, "CC": 3, "SS": 4, "SA": 5, "SHA": 6, "SR": 7, "SH": 8, "SHR": 9}
+KEY_NCART = {"Ham": 1, "SA": 9, "SHA": 9, "SR": 9, "SHR": 9}   # default 3
 CHANNELS = {"Ham": 0, "dHam": 1, "AA": 2, "rotAA": 3, "BB": 4, "CC": 5, "SS": 6}
 
 
@@ -34,12 +37,18 @@ class ScanSpec(C.Structure):
 
 class KuboSpec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nEF", C.c_int32), ("nomega", C.c_int32), ("smr_type", C.c_int32),
-                ("degen_Kramers", C.c_int32), ("external_terms", C.c_int32),
+                ("degen_Kramers", C.c_int32), ("external_terms", C.c_int32), ("shc_type", C.c_int32),
+                ("reserved", C.c_int32),
                 ("smr_fixed_width", C.c_double), ("degen_thresh", C.c_double), ("factor", C.c_double)]
 
     @property
     def shape(self):
-        return (int(self.nEF), int(self.nomega)) + ((3, 3) if int(self.kind) == KUBO_OPTCOND else ())
+        return (int(self.nEF), int(self.nomega)) + {KUBO_OPTCOND: (3, 3), KUBO_SHC: (3, 3, 3)}.get(int(self.kind), ())
+
+    @property
+    def formula_flag(self):
+        """the plan flag (wbgpu_plan formula_mask bit) this scan needs"""
+        return int(self.shc_type) if int(self.kind) == KUBO_SHC else KUBO
 
 
 _lib = None

@@ -16,6 +16,8 @@ class DynamicCalculator(Calculator):
 
     kind = None
     dtype = complex
+    extra_kwargs_formula = ()
+    shc_type = 0
 
     def __init__(self, Efermi=None, omega=None, kBT=0, smr_fixed_width=0.1, smr_type='Lorentzian',
                  kwargs_formula=None, dtype=None, **kwargs):
@@ -33,7 +35,7 @@ class DynamicCalculator(Calculator):
         self.smr_fixed_width = smr_fixed_width
         self.smr_type = smr_type
         self.kwargs_formula = copy(kwargs_formula) if kwargs_formula is not None else {}
-        unknown = set(self.kwargs_formula) - {"external_terms"}
+        unknown = set(self.kwargs_formula) - {"external_terms"} - set(self.extra_kwargs_formula)
         if unknown:
             raise NotImplementedError(f"kwargs_formula {sorted(unknown)} are not implemented on the GPU path")
         self.constant_factor = 1.
@@ -46,8 +48,8 @@ class DynamicCalculator(Calculator):
         return KuboSpec(kind=self.kind, nEF=len(self.Efermi), nomega=len(self.omega),
                         smr_type=0 if self.smr_type == "Lorentzian" else 1,
                         degen_Kramers=int(bool(self.degen_Kramers)), external_terms=int(self.external_terms),
-                        smr_fixed_width=float(self.smr_fixed_width), degen_thresh=float(self.degen_thresh),
-                        factor=float(self.constant_factor))
+                        shc_type=int(self.shc_type), smr_fixed_width=float(self.smr_fixed_width),
+                        degen_thresh=float(self.degen_thresh), factor=float(self.constant_factor))
 
     def result(self, data):
         return EnergyResult([self.Efermi, self.omega], data, transformTR=self.transformTR,
@@ -80,7 +82,35 @@ class OpticalConductivity(DynamicCalculator):
         self.constant_factor = factors.factor_opt
 
 
-_BY_NAME = {c.__name__: c for c in (JDOS, OpticalConductivity)}
+class SHC(DynamicCalculator):
+    r"""Spin Hall conductivity :math:`\sigma^{s}_{ab}(\omega)` (Kubo; dynamic.py:224-237), data `[Efermi, omega, a, b, s]`
+    with the spin current of Ryoo et al. (`SHC_type="ryoo"`, needs SA, SHA), of Qiao et al. (`"qiao"`: SR, SH, SHR)
+    or `{S, v}/2` (`"simple"`).  `shc_abc=(a, b, c)` (1-based) keeps one component."""
+    kind = _lib.KUBO_SHC
+    transformTR, transformInv = "ident", "ident"
+    extra_kwargs_formula = ("SHC_type", "shc_abc")
+
+    def __init__(self, SHC_type="ryoo", shc_abc=None, **kwargs):
+        super().__init__(**kwargs)
+        SHC_type = self.kwargs_formula.get("SHC_type", SHC_type)
+        shc_abc = self.kwargs_formula.get("shc_abc", shc_abc)
+        if SHC_type not in _lib.SHC_TYPES:
+            raise ValueError(f"spin_current_type {SHC_type} not recognized")  # formula/covariant.py:696-697
+        if shc_abc is not None:
+            assert len(shc_abc) == 3
+        self.kwargs_formula.update(dict(SHC_type=SHC_type, shc_abc=shc_abc))
+        self.SHC_type, self.shc_abc = SHC_type, shc_abc
+        self.shc_type = _lib.SHC_TYPES[SHC_type]
+        self.constant_factor = factors.factor_shc
+
+    def result(self, data):
+        if self.shc_abc is not None and data.ndim == 5:   # Formula_SHC, dynamic.py:212-216
+            a, b, c = (x - 1 for x in self.shc_abc)
+            data = np.ascontiguousarray(data[:, :, a, b, c])
+        return super().result(data)
+
+
+_BY_NAME = {c.__name__: c for c in (JDOS, OpticalConductivity, SHC)}
 
 
 def adapt(calc):

@@ -27,6 +27,7 @@ struct WbRInputs {
     const cplx* BB;
     const cplx* CC;
     const cplx* SS;
+    const cplx *SA, *SHA, *SR, *SH, *SHR;   // [nR][nw][nw][3][3] ([3] for SH)
     const double* T;   // [nR][nw][nw][3]  cRvec_shifted
     const int* iRvec;  // [nR][3]
 };
@@ -98,6 +99,17 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
         for (int a = 0; a < 3; a++) atomic_cadd(&table[cellR * E + L.off_C[a] + i * nw + j], in.CC[idx * 3 + a]);
     if (in.SS && L.off_S[0] >= 0)
         for (int a = 0; a < 3; a++) add_herm(table, cellR, cellmR, E, L.off_S[a], i, j, nw, in.SS[idx * 3 + a]);
+    // spin-current matrices: not hermitised (data_K_R.py:84-87)
+    if (in.SA && L.off_SA[0] >= 0)
+        for (int a = 0; a < 9; a++) atomic_cadd(&table[cellR * E + L.off_SA[a] + i * nw + j], in.SA[idx * 9 + a]);
+    if (in.SHA && L.off_SHA[0] >= 0)
+        for (int a = 0; a < 9; a++) atomic_cadd(&table[cellR * E + L.off_SHA[a] + i * nw + j], in.SHA[idx * 9 + a]);
+    if (in.SR && L.off_SR[0] >= 0)
+        for (int a = 0; a < 9; a++) atomic_cadd(&table[cellR * E + L.off_SR[a] + i * nw + j], in.SR[idx * 9 + a]);
+    if (in.SH && L.off_SH[0] >= 0)
+        for (int a = 0; a < 3; a++) atomic_cadd(&table[cellR * E + L.off_SH[a] + i * nw + j], in.SH[idx * 3 + a]);
+    if (in.SHR && L.off_SHR[0] >= 0)
+        for (int a = 0; a < 9; a++) atomic_cadd(&table[cellR * E + L.off_SHR[a] + i * nw + j], in.SHR[idx * 9 + a]);
 }
 
 // Is  d_a H_R = i (R + t_j - t_i)_a H_R  hermitian, i.e. dH(R; i, j) == conj(dH(-R; j, i))?  The reference does not

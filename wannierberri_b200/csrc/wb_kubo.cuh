@@ -30,11 +30,22 @@
 #include "wb_rotate_formula.cuh"
 
 constexpr int WB_KUBO_ENT = 20;    // doubles per entry: Delta | owner bin | M[9] complex (signed, weighted)
+constexpr int WB_SHC_ENT = 56;     // spin Hall: Delta | owner bin | M_(lo,hi)[27] | M_(hi,lo)[27] real
 constexpr int WB_KUBO_CHUNK = 32;  // entries staged per step of the accumulation kernel
 constexpr int WB_KUBO_WT = 32;     // omega values per CTA of the accumulation kernel
 
+__host__ __device__ constexpr int wb_kubo_ent(int kind) { return kind == 2 ? WB_SHC_ENT : WB_KUBO_ENT; }
+
+// spin Hall conductivity: which rotated matrices (in units of nw x nw matrices of the rotated record) feed the
+// spin-velocity matrix of formula/covariant.py:689-756
+struct WbShcChans {
+    int type;        // WBGPU_SHC_RYOO / _QIAO / _SIMPLE
+    int iV, iA, iS;  // d_a H [3], A [3] (-1 without external terms), SS [3]
+    int iX1, iX2, iX3;   // ryoo: SA [9], SHA [9], -;  qiao: SR [9], SH [3], SHR [9]
+};
+
 struct WbKuboParams {
-    int kind;        // 0 = optical conductivity, 1 = JDOS
+    int kind;        // 0 = optical conductivity, 1 = JDOS, 2 = spin Hall conductivity
     int smr_type;    // 0 = Lorentzian, 1 = Gaussian
     int external;    // external terms (Abar) in A_H
     int nEF, nomega;
@@ -63,7 +74,8 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
 wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, long kofs, const double* __restrict__ Eall,
                        WbWindow win, WbKuboParams P, const double* __restrict__ Ef, const double* __restrict__ weight,
-                       long nk_block, double* __restrict__ entries, int* __restrict__ count, int cap) {
+                       long nk_block, double* __restrict__ entries, int* __restrict__ count, int cap,
+                       const cplx* __restrict__ Jspin) {
     extern __shared__ __align__(16) double smem_k[];
     double* Es = smem_k;
     double* label = Es + nw;
@@ -78,6 +90,7 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
     plist = (ushort2*)(((uintptr_t)plist + 3) & ~(uintptr_t)3);
     const int n2 = nw * nw;
     const int lane = threadIdx.x & 31;
+    const int ENT = wb_kubo_ent(P.kind);
     for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
         __syncthreads();
         for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
@@ -127,16 +140,17 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
         const int nvalid = misc[1];
         if (threadIdx.x == 0) count[ik] = nvalid;
         const double wgt = weight[(kofs + ik) / nk_block];
-        double* ent = entries + (size_t)ik * cap * WB_KUBO_ENT;
+        double* ent = entries + (size_t)ik * cap * ENT;
         const cplx* Vb = xbar + (size_t)ik * nch * n2;
         const cplx* Ab = Vb + 3 * n2;
-        const int per = (P.kind == 0) ? 9 : 1;
+        const cplx* Jb = Jspin + (size_t)ik * 9 * n2;
+        const int per = (P.kind == 0) ? 9 : (P.kind == 2) ? 27 : 1;
         for (int x = threadIdx.x; x < nvalid * per; x += NT) {
             const int slot = x / per, ab = x - slot * per;
             const ushort2 pr = plist[slot];
             const int i = min(pr.x, pr.y), j = max(pr.x, pr.y);   // lo, hi group
             const double sw = (pr.y > pr.x) ? wgt : -wgt;         // +X at the bin of the lower group, -X at the upper
-            double* e = ent + (size_t)slot * WB_KUBO_ENT;
+            double* e = ent + (size_t)slot * ENT;
             if (ab == 0) {
                 e[0] = gE[j] - gE[i];
                 e[1] = (double)gidx[pr.x];
@@ -148,6 +162,29 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
                 const bool nz2 = (lo < P.EFmax) && (hi > P.EFmin) && (P.wlo < dm) && (dm < P.whi);
                 e[2] = sw * (double)((ge[i] - gs[i]) * (ge[j] - gs[j]));
                 e[3] = (double)((nz1 ? 1 : 0) | (nz2 ? 2 : 0));
+            } else if (P.kind == 2) {
+                // Formula_SHC (dynamic.py:204-221): M_(1,2)[a, b, s] = sum_{m in 1, n in 2} Im( J_mn^{a s} B_nm^b ),
+                // J = spin-velocity matrix, B = -i A_H
+                const int a = ab / 9, b = (ab / 3) % 3, sp = ab % 3;
+                const cplx* J = Jb + (size_t)(3 * a + sp) * n2;
+                double mlh = 0., mhl = 0.;
+                for (int m = gs[i]; m < ge[i]; m++)
+                    for (int n = gs[j]; n < ge[j]; n++) {
+                        const double inv = wb_deinv(Es[m], Es[n]);
+                        const cplx Vmn = Vb[b * n2 + m * nw + n], Vnm = Vb[b * n2 + n * nw + m];
+                        cplx Amn = cmake(inv * Vmn.y, -inv * Vmn.x);     // i D_mn,  D_mn = -V_mn / (E_m - E_n)
+                        cplx Anm = cmake(-inv * Vnm.y, inv * Vnm.x);
+                        if (P.external) {
+                            Amn = cadd(Amn, Ab[b * n2 + m * nw + n]);
+                            Anm = cadd(Anm, Ab[b * n2 + n * nw + m]);
+                        }
+                        const cplx Jmn = J[m * nw + n], Jnm = J[n * nw + m];
+                        // Im(J * (-i A)) = -Re(J A)
+                        mlh -= Jmn.x * Anm.x - Jmn.y * Anm.y;
+                        mhl -= Jnm.x * Amn.x - Jnm.y * Amn.y;
+                    }
+                e[2 + ab] = sw * mlh;
+                e[29 + ab] = sw * mhl;
             } else {
                 const int a = ab / 3, b = ab - 3 * a;
                 // M[ab] and M[ba] (slot ab stores their sum for a < b, their difference for a > b, M[aa] on the diagonal)
@@ -181,6 +218,85 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
     }
 }
 
+// Spin-velocity matrix  J[k][3 a + s][m][n] = ( <m| v^a S^s |n> + h.c. ) / 2  in the Hamiltonian gauge
+// (SpinVelocity, formula/covariant.py:689-756), from the rotated matrices of one k-point:
+//   simple  J_mn = sum_l S_ml^s ( V_ln^a + i A_ln^a (E_l - E_n) )                                  (:700-707)
+//   ryoo    J_mn = -i ( E_n SA_mn^{as} - SHA_mn^{as} ) + sum_l S_ml^s V_ln^a                        (:741-756)
+//   qiao    J_mn = Re(V_nn^a) S_mn^s + E_n ( -i SR_mn^{as} + sum_l S_ml^s D_ln^a )
+//                  - ( -i SHR_mn^{as} + sum_l SH_ml^s D_ln^a ),   D_ln = -V_ln / (E_l - E_n)        (:709-739)
+// CTA per k-point; thread = (component, m <= n): the raw elements (m, n) and (n, m), then the hermitian part.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_shc_spinvel_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall, WbShcChans C,
+                      int external, cplx* __restrict__ Jout) {
+    extern __shared__ __align__(16) double smem_sv[];
+    double* Es = smem_sv;
+    const int n2 = nw * nw, ntri = nw * (nw + 1) / 2;
+    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        __syncthreads();
+        for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
+        __syncthreads();
+        const cplx* X = xbar + (size_t)ik * nch * n2;
+        cplx* Jk = Jout + (size_t)ik * 9 * n2;
+        for (int x = threadIdx.x; x < 9 * ntri; x += NT) {
+            const int comp = x / ntri;
+            int t = x - comp * ntri, m = 0;
+            while (t >= nw - m) { t -= nw - m; m++; }
+            const int n = m + t;
+            const int a = comp / 3, sp = comp - 3 * a;
+            const cplx* V = X + (size_t)(C.iV + a) * n2;
+            const cplx* S = X + (size_t)(C.iS + sp) * n2;
+            cplx raw[2];
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const int r = side ? n : m, q = side ? m : n;   // element (r, q)
+                const double Eq = Es[q];
+                cplx acc = cmake(0., 0.);
+                if (C.type == WBGPU_SHC_QIAO) {
+                    const cplx* SH = X + (size_t)(C.iX2 + sp) * n2;
+                    cplx k1 = cmake(0., 0.), l1 = cmake(0., 0.);
+                    for (int l = 0; l < nw; l++) {
+                        const double f = -wb_deinv(Es[l], Eq);
+                        const cplx v = V[l * nw + q];
+                        const cplx D = cmake(f * v.x, f * v.y);
+                        cfma(k1, S[r * nw + l], D);
+                        cfma(l1, SH[r * nw + l], D);
+                    }
+                    const cplx sr = X[(size_t)(C.iX1 + comp) * n2 + r * nw + q];
+                    const cplx shr = X[(size_t)(C.iX3 + comp) * n2 + r * nw + q];
+                    // -i z = (z.y, -z.x)
+                    const cplx K = cmake(sr.y + k1.x, -sr.x + k1.y), Lq = cmake(shr.y + l1.x, -shr.x + l1.y);
+                    const double dE = V[q * nw + q].x;
+                    const cplx s = S[r * nw + q];
+                    acc = cmake(dE * s.x + Eq * K.x - Lq.x, dE * s.y + Eq * K.y - Lq.y);
+                } else {
+                    const bool ext = C.type == WBGPU_SHC_SIMPLE && external;
+                    const cplx* A = X + (size_t)(C.iA + a) * n2;
+                    for (int l = 0; l < nw; l++) {
+                        cplx v = V[l * nw + q];
+                        if (ext) {   // + i A_lq (E_l - E_q)
+                            const cplx al = A[l * nw + q];
+                            const double d = Es[l] - Eq;
+                            v = cmake(v.x - d * al.y, v.y + d * al.x);
+                        }
+                        cfma(acc, S[r * nw + l], v);
+                    }
+                    if (C.type == WBGPU_SHC_RYOO) {
+                        const cplx sa = X[(size_t)(C.iX1 + comp) * n2 + r * nw + q];
+                        const cplx sha = X[(size_t)(C.iX2 + comp) * n2 + r * nw + q];
+                        const cplx z = cmake(Eq * sa.x - sha.x, Eq * sa.y - sha.y);
+                        acc = cmake(acc.x + z.y, acc.y - z.x);
+                    }
+                }
+                raw[side] = acc;
+            }
+            const cplx h = cmake(0.5 * (raw[0].x + raw[1].x), 0.5 * (raw[0].y - raw[1].y));
+            Jk[(size_t)comp * n2 + m * nw + n] = h;
+            Jk[(size_t)comp * n2 + n * nw + m] = cmake(h.x, -h.y);
+        }
+    }
+}
+
 // factor_omega of OpticalConductivity (dynamic.py:191-196) without the (E2 - E1) prefactor: 1/(d - i eta), the
 // imaginary part replaced by pi * Gaussian(d) for smr_type != Lorentzian
 __device__ __forceinline__ cplx wb_kubo_cfac(double d, double eta, int smr_type) {
@@ -196,34 +312,39 @@ __device__ __forceinline__ double wb_kubo_smear(double x, double eta, int smr_ty
     return 0.;
 }
 
+// threads per omega value of the accumulation kernel: optical conductivity (component, re | im) = 18, JDOS 1,
+// spin Hall 27 components (each thread carries the real and the imaginary part)
+__host__ __device__ constexpr int wb_kubo_tpw(int kind) { return kind == 0 ? 18 : kind == 2 ? 27 : 1; }
+__host__ __device__ constexpr int wb_kubo_nc(int kind) { return kind == 0 ? 18 : kind == 2 ? 54 : 1; }
+
 template <int KIND>
-__global__ void __launch_bounds__((KIND == 0 ? 18 : 1) * WB_KUBO_WT)
+__global__ void __launch_bounds__(wb_kubo_tpw(KIND) * WB_KUBO_WT)
 wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restrict__ count, int cap, long nk,
                           WbKuboParams P, const double* __restrict__ omega, double* __restrict__ Dglob) {
-    constexpr int NC = KIND == 0 ? 18 : 1, WT = WB_KUBO_WT, NT = NC * WT;
-    __shared__ __align__(16) double ent[WB_KUBO_CHUNK * WB_KUBO_ENT];
+    constexpr int TPW = wb_kubo_tpw(KIND), NC = wb_kubo_nc(KIND), WT = WB_KUBO_WT, NT = TPW * WT, ENT = wb_kubo_ent(KIND);
+    __shared__ __align__(16) double ent[WB_KUBO_CHUNK * ENT];
     __shared__ __align__(16) double Wb[WB_KUBO_CHUNK * WT * 4];
     const int w0 = blockIdx.x * WT, nwt = min(WT, P.nomega - w0);
     const int tid = threadIdx.x;
-    const int iw = tid / NC, c = tid - iw * NC;
+    const int iw = tid / TPW, c = tid - iw * TPW;
     const bool owner = iw < nwt;
     const int ab = c >> 1, ri = c & 1;
     const int wsel = ((ab / 3) > (ab % 3)) ? 2 : 0;   // antisymmetric slot (a > b): Wn, else Wd
-    double* const col = Dglob + ((size_t)(w0 + iw) * P.nEF) * NC + c;
+    double* const col = Dglob + ((size_t)(w0 + iw) * P.nEF) * NC + (KIND == 2 ? 2 * c : c);
     for (long ik = blockIdx.y; ik < nk; ik += gridDim.y) {
         const int cnt = count[ik];
-        const double* src = entries + (size_t)ik * cap * WB_KUBO_ENT;
-        double Y = 0.;
+        const double* src = entries + (size_t)ik * cap * ENT;
+        double Y = 0., Y2 = 0.;
         int curbin = -1;
         for (int p0 = 0; p0 < cnt; p0 += WB_KUBO_CHUNK) {
             const int np = min(WB_KUBO_CHUNK, cnt - p0);
             __syncthreads();
-            for (int x = tid; x < np * WB_KUBO_ENT; x += NT) ent[x] = src[(size_t)p0 * WB_KUBO_ENT + x];
+            for (int x = tid; x < np * ENT; x += NT) ent[x] = src[(size_t)p0 * ENT + x];
             __syncthreads();
             // ---- phase A: frequency factors of (entry, omega), shared by the components
             for (int x = tid; x < np * nwt; x += NT) {
                 const int p = x / nwt, w = x - p * nwt;
-                const double dl = ent[p * WB_KUBO_ENT], om = omega[w0 + w];
+                const double dl = ent[p * ENT], om = omega[w0 + w];
                 double* o = Wb + (p * WT + w) * 4;
                 if (KIND == 0) {
                     const cplx c1 = wb_kubo_cfac(dl - om, P.eta, P.smr_type);
@@ -233,8 +354,15 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
                     const double w1x = dl * c1.x, w1y = dl * c1.y, w2x = -dl * c2.x, w2y = -dl * c2.y;
                     o[0] = w2x - w1x; o[1] = w2y - w1y;
                     o[2] = -(w1x + w2x); o[3] = -(w1y + w2y);
+                } else if (KIND == 2) {
+                    // SHC.factor_omega (dynamic.py:232-237): cfac(E1 - E2 - omega) / 2; pair (lo, hi) with the Fermi
+                    // factor -1, pair (hi, lo) with +1
+                    const cplx c1 = wb_kubo_cfac(-dl - om, P.eta, P.smr_type);
+                    const cplx c2 = wb_kubo_cfac(dl - om, P.eta, P.smr_type);
+                    o[0] = -0.5 * c1.x; o[1] = -0.5 * c1.y;
+                    o[2] = 0.5 * c2.x; o[3] = 0.5 * c2.y;
                 } else {
-                    const int fl = (int)ent[p * WB_KUBO_ENT + 3];
+                    const int fl = (int)ent[p * ENT + 3];
                     o[0] = (fl & 1) ? wb_kubo_smear(dl - om, P.eta, P.smr_type) : 0.;    // (hi, lo): E1 - E2 = +Delta
                     o[1] = (fl & 2) ? wb_kubo_smear(-dl - om, P.eta, P.smr_type) : 0.;   // (lo, hi)
                 }
@@ -243,18 +371,24 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
             // ---- phase B: thread = (omega, component): register accumulation per owner bin
             if (owner) {
                 for (int p = 0; p < np; p++) {
-                    const double* e = ent + p * WB_KUBO_ENT;
+                    const double* e = ent + p * ENT;
                     const int bin = (int)e[1];
                     if (bin != curbin) {   // uniform
                         if (curbin >= 0 && Y != 0.) atomicAdd(col + (size_t)curbin * NC, Y);
+                        if (KIND == 2 && curbin >= 0 && Y2 != 0.) atomicAdd(col + (size_t)curbin * NC + 1, Y2);
                         curbin = bin;
                         Y = 0.;
+                        Y2 = 0.;
                     }
                     const double* W = Wb + (p * WT + iw) * 4;
                     if (KIND == 0) {
                         const double Mr = e[2 + 2 * ab], Mi = e[3 + 2 * ab], Wr = W[wsel], Wi = W[wsel + 1];
                         if (ri == 0) Y += Wr * Mr - Wi * Mi;
                         else Y += Wr * Mi + Wi * Mr;
+                    } else if (KIND == 2) {
+                        const double m1 = e[2 + c], m2 = e[29 + c];
+                        Y += W[0] * m1 + W[2] * m2;
+                        Y2 += W[1] * m1 + W[3] * m2;
                     } else {
                         Y += (W[0] - W[1]) * e[2];
                     }
@@ -262,10 +396,12 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
             }
         }
         if (owner && curbin >= 0 && Y != 0.) atomicAdd(col + (size_t)curbin * NC, Y);
+        if (KIND == 2 && owner && curbin >= 0 && Y2 != 0.) atomicAdd(col + (size_t)curbin * NC + 1, Y2);
     }
 }
 
-// D holds differences along Efermi: value[iw][iEf][c] = sum_{f <= iEf} D[iw][f][c].  JDOS (NC = 1): out = scale * value.
+// D holds differences along Efermi: value[iw][iEf][c] = sum_{f <= iEf} D[iw][f][c].  JDOS (NC = 1) and spin Hall
+// (NC = 54 = [a][b][s][re | im]): out = scale * value.
 // Optical conductivity (NC = 18): slots (ab, ba), a < b hold P = X[ab] + X[ba] and Q = X[ab] - X[ba]:
 // out[iEf][iw][ab] = scale (P + Q) / 2, out[..][ba] = scale (P - Q) / 2; the diagonal slots hold X[aa].
 __global__ void wb_kubo_finalize_kernel(const double* __restrict__ D, int nomega, int nEF, int NC, double scale,
@@ -273,7 +409,7 @@ __global__ void wb_kubo_finalize_kernel(const double* __restrict__ D, int nomega
     const long total = (long)nomega * NC;
     for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
         const int c = (int)(x % NC), w = (int)(x / NC);
-        if (NC == 1) {
+        if (NC != 18) {   // JDOS, spin Hall: plain running sum
             double run = 0.;
             for (int f = 0; f < nEF; f++) {
                 run += D[((size_t)w * nEF + f) * NC + c];

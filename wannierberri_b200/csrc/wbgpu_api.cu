@@ -58,7 +58,7 @@ struct wbgpu_ctx {
     double cell_volume = 0;
     int* d_iRvec = nullptr;
     double* d_T = nullptr;
-    cplx* d_XR[WBGPU_NKEYS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cplx* d_XR[WBGPU_NKEYS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int3 rmin{0, 0, 0}, nbox{1, 1, 1};
     // plan
     bool planned = false;
@@ -88,6 +88,8 @@ struct wbgpu_ctx {
     size_t kent_cap = 0;
     double* d_kacc = nullptr;
     size_t kacc_cap = 0;
+    double* d_shcJ = nullptr;   // spin-velocity matrices of a sub-batch [k][9][nw][nw] complex
+    size_t shcJ_cap = 0;
     // tetrahedron method: H-only R-space table, corner energies [8][nkl][nw], per-band min / max over the cell
     cplx* d_tableH = nullptr;
     double* d_Ec = nullptr;
@@ -220,7 +222,7 @@ extern "C" int wbgpu_destroy(wbgpu_ctx* c) {
     free_plan(c);
     cudaFree(c->d_iRvec); cudaFree(c->d_T); cudaFree(c->d_sweeps);
     for (int k = 0; k < WBGPU_NKEYS; k++) cudaFree(c->d_XR[k]);
-    cudaFree(c->d_xbar); cudaFree(c->d_mx); cudaFree(c->d_kent); cudaFree(c->d_kacc); cudaFree(c->d_Ec);
+    cudaFree(c->d_xbar); cudaFree(c->d_mx); cudaFree(c->d_kent); cudaFree(c->d_kacc); cudaFree(c->d_shcJ); cudaFree(c->d_Ec);
     cudaFree(c->d_hist); cudaFree(c->d_cum); cudaFree(c->d_dK); cudaFree(c->d_weight); cudaFree(c->d_out);
     delete c;
     return 0;
@@ -229,7 +231,7 @@ extern "C" int wbgpu_destroy(wbgpu_ctx* c) {
 extern "C" int wbgpu_set_R_matrix(wbgpu_ctx* c, int key, const double* X_R, int ncart) {
     if (!c || !X_R) return set_err("wbgpu_set_R_matrix: null pointer argument");
     if (key < 0 || key >= WBGPU_NKEYS) return set_err("wbgpu_set_R_matrix: unknown key %d", key);
-    int want = (key == WBGPU_HAM) ? 1 : 3;
+    int want = (key == WBGPU_HAM) ? 1 : (key == WBGPU_SA || key == WBGPU_SHA || key == WBGPU_SR || key == WBGPU_SHR) ? 9 : 3;
     if (ncart != want) return set_err("wbgpu_set_R_matrix: key %d needs ncart=%d, got %d", key, want, ncart);
     CK(cudaSetDevice(c->device));
     size_t bytes = sizeof(cplx) * (size_t)c->nR * c->nw * c->nw * ncart;
@@ -305,11 +307,17 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     const uint32_t m = formula_mask;
     auto has = [&](int f) { return (m >> f) & 1u; };
     bool need_dH = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
-                   has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO) || has(WBGPU_VEL_VEL) || has(WBGPU_INV_MASS);
+                   has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO) || has(WBGPU_VEL_VEL) || has(WBGPU_INV_MASS) || has(WBGPU_SHC_RYOO) ||
+                   has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE);
+    const bool shc = has(WBGPU_SHC_RYOO) || has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE);
     bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) || has(WBGPU_KUBO);
-    bool need_A = berry && external_terms;
+    bool need_A = (berry || shc) && external_terms;
     bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS)) && external_terms;
-    bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN);
+    bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN) || shc;
+    if (has(WBGPU_SHC_RYOO) && (!c->d_XR[WBGPU_SA] || !c->d_XR[WBGPU_SHA]))
+        return set_err("wbgpu_plan: R-matrices 'SA','SHA' are not set (SHC_type='ryoo')");
+    if (has(WBGPU_SHC_QIAO) && (!c->d_XR[WBGPU_SR] || !c->d_XR[WBGPU_SH] || !c->d_XR[WBGPU_SHR]))
+        return set_err("wbgpu_plan: R-matrices 'SR','SH','SHR' are not set (SHC_type='qiao')");
     if (need_A && !c->d_XR[WBGPU_AA]) return set_err("wbgpu_plan: R-matrix 'AA' is not set (needed for external terms)");
     if (need_BC && (!c->d_XR[WBGPU_BB] || !c->d_XR[WBGPU_CC])) return set_err("wbgpu_plan: R-matrices 'BB','CC' are not set");
     if (need_S && !c->d_XR[WBGPU_SS]) return set_err("wbgpu_plan: R-matrix 'SS' is not set");
@@ -357,6 +365,11 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     for (int a = 0; a < 3; a++) L.off_C[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_S[a] = need_S ? take(true) : -1;
     for (int a = 0; a < 6; a++) L.off_W[a] = has(WBGPU_INV_MASS) ? take(dH_herm) : -1;
+    for (int a = 0; a < 9; a++) L.off_SA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
+    for (int a = 0; a < 9; a++) L.off_SHA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
+    for (int a = 0; a < 9; a++) L.off_SR[a] = has(WBGPU_SHC_QIAO) ? take(false) : -1;
+    for (int a = 0; a < 3; a++) L.off_SH[a] = has(WBGPU_SHC_QIAO) ? take(false) : -1;
+    for (int a = 0; a < 9; a++) L.off_SHR[a] = has(WBGPU_SHC_QIAO) ? take(false) : -1;
     L.E = off;
     c->L = L;
     c->mask = m;
@@ -374,6 +387,11 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     in.BB = need_BC ? c->d_XR[WBGPU_BB] : nullptr;
     in.CC = need_BC ? c->d_XR[WBGPU_CC] : nullptr;
     in.SS = need_S ? c->d_XR[WBGPU_SS] : nullptr;
+    in.SA = has(WBGPU_SHC_RYOO) ? c->d_XR[WBGPU_SA] : nullptr;
+    in.SHA = has(WBGPU_SHC_RYOO) ? c->d_XR[WBGPU_SHA] : nullptr;
+    in.SR = has(WBGPU_SHC_QIAO) ? c->d_XR[WBGPU_SR] : nullptr;
+    in.SH = has(WBGPU_SHC_QIAO) ? c->d_XR[WBGPU_SH] : nullptr;
+    in.SHR = has(WBGPU_SHC_QIAO) ? c->d_XR[WBGPU_SHR] : nullptr;
     in.T = c->d_T;
     in.iRvec = c->d_iRvec;
     long total = (long)c->nR * nw * nw;
@@ -410,7 +428,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
         int ncmax = 1;
         int sum = 0;
         for (int f = 1; f < WBGPU_NFORMULA; f++)
-            if (f != WBGPU_KUBO && ((m >> f) & 1u)) sum += formula_ncomp(f);
+            if (formula_rank(f) >= 0 && ((m >> f) & 1u)) sum += formula_ncomp(f);
         ncmax = std::max(ncmax, sum);
         c->ev_ncmax = ncmax;
         CK(cudaMalloc(&c->d_evval, sizeof(double) * nkl * nw * ncmax));
@@ -1105,6 +1123,8 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
     LH.nw = nw; LH.ntri = nw * (nw + 1) / 2; LH.E = LH.ntri; LH.off_H = 0; LH.dH_herm = 0;
     for (int a = 0; a < 3; a++) LH.off_dH[a] = LH.off_A[a] = LH.off_O[a] = LH.off_B[a] = LH.off_C[a] = LH.off_S[a] = -1;
     for (int a = 0; a < 6; a++) LH.off_W[a] = -1;
+    for (int a = 0; a < 9; a++) LH.off_SA[a] = LH.off_SHA[a] = LH.off_SR[a] = LH.off_SHR[a] = -1;
+    for (int a = 0; a < 3; a++) LH.off_SH[a] = -1;
     const size_t ncell = (size_t)c->nbox.x * c->nbox.y * c->nbox.z;
     if (!c->d_tableH) {
         CK(cudaMalloc(&c->d_tableH, sizeof(cplx) * ncell * LH.E));
@@ -1112,6 +1132,7 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
         WbRInputs in;
         in.Ham = c->d_XR[WBGPU_HAM];
         in.AA = in.BB = in.CC = in.SS = nullptr;
+        in.SA = in.SHA = in.SR = in.SH = in.SHR = nullptr;
         in.T = c->d_T;
         in.iRvec = c->d_iRvec;
         long total = (long)c->nR * nw * nw;
@@ -1229,6 +1250,7 @@ extern "C" int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* s) {
     if (!s || s->nEF < 1 || s->nomega < 1) return -1;
     if (s->kind == WBGPU_KUBO_OPTCOND) return (int64_t)s->nEF * s->nomega * 18;
     if (s->kind == WBGPU_KUBO_JDOS) return (int64_t)s->nEF * s->nomega;
+    if (s->kind == WBGPU_KUBO_SHC) return (int64_t)s->nEF * s->nomega * 54;
     return -1;
 }
 
@@ -1240,14 +1262,22 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     if (nout < 0) return set_err("wbgpu_kubo_scan: bad spec (kind=%d nEF=%d nomega=%d)", spec->kind, spec->nEF, spec->nomega);
     if (spec->smr_type != 0 && spec->smr_type != 1) return set_err("wbgpu_kubo_scan: Invalid smearing type %d", spec->smr_type);
     if (!(spec->smr_fixed_width > 0)) return set_err("wbgpu_kubo_scan: smr_fixed_width must be positive");
-    const bool optcond = spec->kind == WBGPU_KUBO_OPTCOND;
+    const bool optcond = spec->kind == WBGPU_KUBO_OPTCOND, shc = spec->kind == WBGPU_KUBO_SHC;
+    const bool rotated = optcond || shc;   // needs eigenvectors and rotated matrices
     const WbLayout& L = c->L;
+    if (shc) {
+        const int t = spec->shc_type;
+        if (t != WBGPU_SHC_RYOO && t != WBGPU_SHC_QIAO && t != WBGPU_SHC_SIMPLE)
+            return set_err("wbgpu_kubo_scan: spin_current_type %d not recognized", t);   // covariant.py:696-697
+        if (!((c->mask >> t) & 1u) || L.off_dH[0] < 0 || L.off_S[0] < 0 || (spec->external_terms && L.off_A[0] < 0))
+            return set_err("wbgpu_kubo_scan: the plan does not hold the channels of this spin Hall scan (declare WBGPU_SHC_*)");
+    }
     if (optcond && (!((c->mask >> WBGPU_KUBO) & 1u) || L.off_dH[0] < 0 || (spec->external_terms && L.off_A[0] < 0)))
         return set_err("wbgpu_kubo_scan: the plan does not hold the channels of the Kubo path (declare WBGPU_KUBO)");
     for (int i = 1; i < spec->nEF; i++)
         if (!(Efermi[i] > Efermi[i - 1])) return set_err("wbgpu_kubo_scan: Efermi must be strictly ascending");
     CK(cudaSetDevice(c->device));
-    const int nw = c->nw, nEF = spec->nEF, nom = spec->nomega, NC = optcond ? 18 : 1;
+    const int nw = c->nw, nEF = spec->nEF, nom = spec->nomega, NC = wb_kubo_nc(spec->kind), ENT = wb_kubo_ent(spec->kind);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
 
@@ -1279,14 +1309,25 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     CK(cudaMemsetAsync(c->d_kacc, 0, sizeof(double) * nacc, c->stream));
 
     const int nwtile = (nom + WB_KUBO_WT - 1) / WB_KUBO_WT;
-    const int nthreads = NC * WB_KUBO_WT;
+    const int nthreads = wb_kubo_tpw(spec->kind) * WB_KUBO_WT;
 
     WbChanList ch;
     ch.n = 0;
-    if (optcond) {
-        for (int a = 0; a < 3; a++) { ch.off[ch.n] = L.off_dH[a]; ch.herm[ch.n] = L.dH_herm; ch.n++; }
-        if (spec->external_terms)
-            for (int a = 0; a < 3; a++) { ch.off[ch.n] = L.off_A[a]; ch.herm[ch.n] = 1; ch.n++; }
+    WbShcChans sc;
+    sc.type = spec->shc_type; sc.iV = 0; sc.iA = sc.iS = sc.iX1 = sc.iX2 = sc.iX3 = -1;
+    auto addn = [&](const int* offs, int n, int herm) {
+        const int first = ch.n;
+        for (int a = 0; a < n; a++) { ch.off[ch.n] = offs[a]; ch.herm[ch.n] = herm; ch.n++; }
+        return first;
+    };
+    if (rotated) {
+        addn(L.off_dH, 3, L.dH_herm);
+        if (spec->external_terms) sc.iA = addn(L.off_A, 3, 1);
+    }
+    if (shc) {
+        sc.iS = addn(L.off_S, 3, 1);
+        if (sc.type == WBGPU_SHC_RYOO) { sc.iX1 = addn(L.off_SA, 9, 0); sc.iX2 = addn(L.off_SHA, 9, 0); }
+        if (sc.type == WBGPU_SHC_QIAO) { sc.iX1 = addn(L.off_SR, 9, 0); sc.iX2 = addn(L.off_SH, 3, 0); sc.iX3 = addn(L.off_SHR, 9, 0); }
     }
     const int cap = std::max(1, nw * (nw - 1));
     const size_t smem_ent = wb_kubo_entries_smem_bytes(nw);
@@ -1300,27 +1341,36 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
         if (run_fourier(c, c->d_dK + 3 * (size_t)b0, nb)) return 1;
         stage_end(c);
         stage_begin(c, WBGPU_STAGE_EIGH);
-        if (run_eigh(c, nk, optcond)) return 1;
+        if (run_eigh(c, nk, rotated)) return 1;
         stage_end(c);
-        long chunk = std::min(nk, std::max(1L, (long)(3.0e9 / (8.0 * WB_KUBO_ENT * cap))));
-        if (optcond) chunk = std::min(chunk, xbar_chunk(c, ch.n, nk));
-        if (optcond && ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * nw * nw)) return 1;
-        if (ensure(&c->d_kent, &c->kent_cap, sizeof(double) * (size_t)chunk * cap * WB_KUBO_ENT + sizeof(int) * (size_t)chunk + 16)) return 1;
-        int* d_count = (int*)(c->d_kent + (size_t)chunk * cap * WB_KUBO_ENT);
+        long chunk = std::min(nk, std::max(1L, (long)(3.0e9 / (8.0 * ENT * cap))));
+        if (rotated) chunk = std::min(chunk, xbar_chunk(c, ch.n, nk));
+        if (rotated && ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * nw * nw)) return 1;
+        if (shc && ensure(&c->d_shcJ, &c->shcJ_cap, sizeof(cplx) * (size_t)chunk * 9 * nw * nw)) return 1;
+        if (ensure(&c->d_kent, &c->kent_cap, sizeof(double) * (size_t)chunk * cap * ENT + sizeof(int) * (size_t)chunk + 16)) return 1;
+        int* d_count = (int*)(c->d_kent + (size_t)chunk * cap * ENT);
         for (long k0 = 0; k0 < nk; k0 += chunk) {
             const long n = std::min(chunk, nk - k0);
-            if (optcond) {
+            if (rotated) {
                 stage_begin(c, WBGPU_STAGE_ROTATE);
                 if (rotate_gemm(c, ch, k0, n)) return 1;
+                if (shc) {
+                    wb_shc_spinvel_kernel<256><<<(unsigned)std::min(n, (long)sms * 8), 256, sizeof(double) * nw, c->stream>>>(
+                        (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, sc, spec->external_terms, (cplx*)c->d_shcJ);
+                    c->launches++;
+                }
                 stage_end(c);
             }
             stage_begin(c, WBGPU_STAGE_SCAN);
             wb_kubo_entries_kernel<128><<<(unsigned)std::min(n, (long)sms * 8), 128, smem_ent, c->stream>>>(
-                (const cplx*)c->d_xbar, ch.n, nw, n, k0, c->d_E + k0 * nw, win, P, d_Ef, d_w + b0, c->nk_block, c->d_kent, d_count, cap);
+                (const cplx*)c->d_xbar, ch.n, nw, n, k0, c->d_E + k0 * nw, win, P, d_Ef, d_w + b0, c->nk_block, c->d_kent, d_count, cap,
+                (const cplx*)c->d_shcJ);
             const int nsplit = (int)std::max(1L, std::min(n, (long)((6 * sms + nwtile - 1) / nwtile)));
             dim3 grid((unsigned)nwtile, (unsigned)nsplit);
             if (optcond)
                 wb_kubo_accumulate_kernel<0><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
+            else if (shc)
+                wb_kubo_accumulate_kernel<2><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
             else
                 wb_kubo_accumulate_kernel<1><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
             c->launches += 2;

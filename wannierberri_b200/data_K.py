@@ -52,7 +52,7 @@ class Data_K_R:
         from . import _lib
         if self.force_internal_terms_only:
             spec.external_terms = 0
-        self._plan([_lib.KUBO], bool(spec.external_terms))
+        self._plan([spec.formula_flag], bool(spec.external_terms))
         return self.engine.kubo_scan(self.dK[None, :], np.ones(1), spec, Efermi, omega)
 
     @property

@@ -32,8 +32,8 @@ class Engine:
         for key, idx in _lib.KEYS.items():
             if system.has_R_mat(key):
                 X = np.ascontiguousarray(system.get_R_mat(key), dtype=np.complex128)
-                ncart = 1 if key == "Ham" else 3
-                want = (self.nR, self.nw, self.nw) + ((3,) if ncart == 3 else ())
+                ncart = _lib.KEY_NCART.get(key, 3)
+                want = (self.nR, self.nw, self.nw) + {1: (), 3: (3,), 9: (3, 3)}[ncart]
                 if X.shape != want:
                     raise ValueError(f"R-matrix {key} has shape {X.shape}, expected {want}")
                 check(L.wbgpu_set_R_matrix(self._ctx, idx, dptr(X.view(np.float64)), ncart))
@@ -116,8 +116,8 @@ class Engine:
                                             C.c_void_p(out_dev.data_ptr())))
 
     def kubo_scan(self, dK, weight, spec, Efermi, omega):
-        """One (Efermi x omega) scan over a list of K-blocks: `[nEF, nomega, 3, 3]` complex (optical conductivity)
-        or `[nEF, nomega]` float (JDOS)."""
+        """One (Efermi x omega) scan over a list of K-blocks: `[nEF, nomega, 3, 3]` complex (optical conductivity),
+        `[nEF, nomega, 3, 3, 3]` complex (spin Hall conductivity) or `[nEF, nomega]` float (JDOS)."""
         dK = as_f64(dK).reshape(-1, 3)
         weight = as_f64(weight).reshape(-1)
         Efermi, omega = as_f64(Efermi), as_f64(omega)
@@ -125,7 +125,7 @@ class Engine:
         out = np.zeros(int(self._L.wbgpu_kubo_size(C.byref(spec))))
         check(self._L.wbgpu_kubo_scan(self._ctx, dK.shape[0], dptr(dK), dptr(weight), C.byref(spec), dptr(Efermi),
                                       dptr(omega), dptr(out)))
-        if int(spec.kind) == _lib.KUBO_OPTCOND:
+        if int(spec.kind) in (_lib.KUBO_OPTCOND, _lib.KUBO_SHC):
             return out.view(np.complex128).reshape(spec.shape)
         return out.reshape(spec.shape)
 

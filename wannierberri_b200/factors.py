@@ -10,5 +10,6 @@ factor_gme_orb = factor_morb_evA2_to_muB * bohr_magneton / angstrom ** 2
 factor_gme_spin = -bohr_magneton / angstrom ** 2
 factor_ahc = -(elementary_charge ** 2 / hbar / angstrom)
 factor_opt = -factor_ahc
+factor_shc = -factor_ahc
 TAU_UNIT = 1E-15
 factor_ohmic = (elementary_charge ** 2 / hbar / angstrom * TAU_UNIT * elementary_charge / hbar)

@@ -91,7 +91,7 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
             ks.external_terms = 0
         kspecs[key] = ks
     external = any(s.external_terms for s in specs + tspecs) or any(ks.external_terms for ks in kspecs.values())
-    formulae = {int(s.formula) for s in specs + tspecs} | ({_lib.KUBO} if kspecs else set()) | {_lib.IDENTITY}
+    formulae = {int(s.formula) for s in specs + tspecs} | {ks.formula_flag for ks in kspecs.values()} | {_lib.IDENTITY}
     engine = engine_for(system, device)
     engine.plan(np.array(grid.FFT, dtype=int), formulae, external_terms=external)
     arrays = engine.scan(shifts[lo:hi], factors[lo:hi], specs) if specs else []
