@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Golden fixture of the next-row-4 Fermi-sea formulae -- BerryDipole_FermiSea / NLAHC_FermiSea (formula DerOmega,
+formula/covariant.py:212-259) and the static spin Hall conductivity static.SHC (formula SpinOmega, :759-789) -- from the
+UNMODIFIED upstream reference:
+  * the reference's `random` system (no symmetry, all R-matrices), NK = 6, NKFFT = 3;
+  * the reference's Te test (tests/test_run.py:1101-1119; tetrahedron method, symmetry-reduced K-list), asserting that
+    the live run reproduces the reference's own golden files Te_QE-{BerryDipole_FermiSea,berry_dipole}_iter-0000.npz.
+
+    cd /tmp && PYTHONPATH=/root/reference:/root/repo/oracle/stubs python /root/repo/tests/golden/make_golden_fsea.py
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from make_golden import REF, OUT, run_ref, build_te, System_R, wberri, calc  # noqa: E402
+
+
+def main():
+    st = calc.static
+    rnd = System_R.from_npz(path=os.path.join(REF, "tests", "data", "random"), legacy=True)
+    Ef = np.linspace(-2, 2, 9)
+    calcs = dict(bd_sea=st.BerryDipole_FermiSea(Efermi=Ef),
+                 bd_sea_int=st.BerryDipole_FermiSea(Efermi=Ef, kwargs_formula=dict(external_terms=False)),
+                 bd_sea_thresh=st.BerryDipole_FermiSea(Efermi=Ef, degen_thresh=0.3),
+                 bd_sea_tetra=st.BerryDipole_FermiSea(Efermi=Ef, tetra=True),
+                 nlahc_sea=st.NLAHC_FermiSea(Efermi=Ef),
+                 shc_ryoo=st.SHC(Efermi=Ef, kwargs_formula=dict(spin_current_type="ryoo")),
+                 shc_qiao=st.SHC(Efermi=Ef, kwargs_formula=dict(spin_current_type="qiao")),
+                 shc_simple=st.SHC(Efermi=Ef, kwargs_formula=dict(spin_current_type="simple")),
+                 shc_simple_int=st.SHC(Efermi=Ef, kwargs_formula=dict(spin_current_type="simple", external_terms=False)),
+                 shc_ryoo_thresh=st.SHC(Efermi=Ef, degen_thresh=0.3, kwargs_formula=dict(spin_current_type="ryoo")),
+                 shc_qiao_tetra=st.SHC(Efermi=Ef, tetra=True, kwargs_formula=dict(spin_current_type="qiao")))
+    grid, res = run_ref(rnd, [6, 6, 6], [3, 3, 3], calcs)
+    out = dict(rnd_Efermi=Ef, rnd_NK=np.array([6, 6, 6]), rnd_NKFFT=np.array([3, 3, 3]))
+    for q in calcs:
+        out["rnd_" + q] = res.results[q].data
+
+    te = build_te()   # pointgroup C3z, C2x, TimeReversal (tests/common_systems.py:1022-1027)
+    Ef = np.linspace(4, 8, 11)
+    calcs = dict(BerryDipole_FermiSea=st.BerryDipole_FermiSea(Efermi=Ef, tetra=True),
+                 berry_dipole=st.NLAHC_FermiSea(Efermi=Ef, tetra=True),
+                 BerryDipole_FermiSea_notetra=st.BerryDipole_FermiSea(Efermi=Ef))
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            grid = wberri.Grid(te, NK=[3, 3, 4], NKFFT=[1, 1, 4])
+            res = wberri.run(te, grid=grid, calculators=calcs, parallel=False, use_irred_kpt=True, symmetrize=True,
+                             fout_name="g", print_progress_step_time=1e9, print_progress_step_percent=1000)
+        finally:
+            os.chdir(cwd)
+    out.update(te_Efermi=Ef, te_NK=np.array([3, 3, 4]), te_NKFFT=np.array([1, 1, 4]))
+    for q in ("BerryDipole_FermiSea", "berry_dipole"):
+        ref = np.load(os.path.join(REF, "tests/reference/integrate_files", f"Te_QE-{q}_iter-0000.npz"))["data"]
+        got = res.results[q].data
+        err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)
+        print(f"Te_QE-{q}: live reference run vs reference golden file: rel err {err:.2e}")
+        assert err < 1e-7, q
+        out["te_upstream_golden_" + q] = ref
+    for q in calcs:
+        out["te_" + q] = res.results[q].data
+    np.savez_compressed(os.path.join(OUT, "golden_fsea.npz"), **out)
+    print("written", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -290,3 +290,28 @@ def test_shc_random_system(case):
     assert relerr(res["a"], g[case]) < RTOL
     if ax == "ref":
         assert relerr(res["a"], g["upstream_golden_" + t]) < RTOL
+
+
+FSEA_CASES = dict(
+    bd_sea=("BerryDipole_FermiSea", {}), bd_sea_int=("BerryDipole_FermiSea", dict(kwargs_formula=dict(external_terms=False))),
+    bd_sea_thresh=("BerryDipole_FermiSea", dict(degen_thresh=0.3)), bd_sea_tetra=("BerryDipole_FermiSea", dict(tetra=True)),
+    nlahc_sea=("NLAHC_FermiSea", {}),
+    shc_ryoo=("SHC_static", dict(kwargs_formula=dict(spin_current_type="ryoo"))),
+    shc_qiao=("SHC_static", dict(kwargs_formula=dict(spin_current_type="qiao"))),
+    shc_simple=("SHC_static", dict(kwargs_formula=dict(spin_current_type="simple"))),
+    shc_simple_int=("SHC_static", dict(kwargs_formula=dict(spin_current_type="simple", external_terms=False))),
+    shc_ryoo_thresh=("SHC_static", dict(degen_thresh=0.3, kwargs_formula=dict(spin_current_type="ryoo"))),
+    shc_qiao_tetra=("SHC_static", dict(tetra=True, kwargs_formula=dict(spin_current_type="qiao"))),
+)
+
+
+def test_fermi_sea_formulae_random_system():
+    """DerOmega (BerryDipole_FermiSea / NLAHC_FermiSea; formula/covariant.py:212-259) and SpinOmega (static.SHC; :759-789)
+    on the reference's `random` system against the live reference run of make_golden_fsea.py (which also reproduces the
+    upstream Te_QE-{BerryDipole_FermiSea,berry_dipole} golden files, checked on the GPU path with symmetry + tetra)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fsea.npz"))
+    rnd = orc.OracleSystem.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    res = orc.run(rnd, [2, 2, 2], [3, 3, 3], {k: (name, g["rnd_Efermi"], kw) for k, (name, kw) in FSEA_CASES.items()})
+    for k in FSEA_CASES:
+        assert res[k].shape == g["rnd_" + k].shape, k
+        assert relerr(res[k], g["rnd_" + k]) < RTOL, k

@@ -13,3 +13,4 @@ factor_opt = -factor_ahc
 factor_shc = -factor_ahc
 TAU_UNIT = 1E-15
 factor_ohmic = (elementary_charge ** 2 / hbar / angstrom * TAU_UNIT * elementary_charge / hbar)
+factor_nlahc = elementary_charge ** 3 / hbar ** 2 * TAU_UNIT
