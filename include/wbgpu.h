@@ -54,10 +54,15 @@ enum {
     WBGPU_VEL_VEL = 8,    /* VelVel          covariant.py:817-820 rank 2 */
     WBGPU_INV_MASS = 9,   /* InvMass         elementary.py:28-34 (generalised derivative of the velocity, needs
                              the second comma-derivative of H) rank 2 */
-    WBGPU_SHC_RYOO = 10,  /* plan flags only: channels of dynamic.SHC with the spin current of Ryoo et al. (SA, SHA), */
-    WBGPU_SHC_QIAO = 11,  /*   of Qiao et al. (SH, SR, SHR),                                                          */
-    WBGPU_SHC_SIMPLE = 12,/*   and {S, v}/2 (SS only); all need dH, SS and (external terms) AA                        */
-    WBGPU_NFORMULA = 13
+    /* Spin Hall conductivity with the spin current of Ryoo et al. (R-matrices SA, SHA), of Qiao et al. (SR, SH, SHR) or
+       {S, v}/2 (SS only).  As a plan flag: the channels of the Kubo scan dynamic.SHC (WBGPU_KUBO_SHC).  As the formula of
+       a static scan: SpinOmega (spin Berry curvature, covariant.py:759-789; static.SHC), rank 3 [a][b][s]. */
+    WBGPU_SHC_RYOO = 10,
+    WBGPU_SHC_QIAO = 11,
+    WBGPU_SHC_SIMPLE = 12,
+    WBGPU_DER_OMEGA = 13, /* DerOmega        covariant.py:212-259 (generalised derivative of the Berry curvature:
+                             BerryDipole_FermiSea, NLAHC_FermiSea), rank 2 [c][d]; needs d_b d_d H, d_d A_b, d_d rotA_c */
+    WBGPU_NFORMULA = 14
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */

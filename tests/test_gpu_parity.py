@@ -647,6 +647,77 @@ def test_te_qe_tetra_symmetric_vs_upstream_goldens(wb):
             assert np.abs(res.results[q].data - ref).max() <= tol * np.abs(ref).max(), q
 
 
+# ---------------------------------------------------------------------------------------- Fermi-sea formulae of next-row 4
+FSEA_CASES = dict(
+    bd_sea=("BerryDipole_FermiSea", {}), bd_sea_int=("BerryDipole_FermiSea", dict(kwargs_formula=dict(external_terms=False))),
+    bd_sea_thresh=("BerryDipole_FermiSea", dict(degen_thresh=0.3)), bd_sea_tetra=("BerryDipole_FermiSea", dict(tetra=True)),
+    nlahc_sea=("NLAHC_FermiSea", {}),
+    shc_ryoo=("SHC", dict(kwargs_formula=dict(spin_current_type="ryoo"))),
+    shc_qiao=("SHC", dict(kwargs_formula=dict(spin_current_type="qiao"))),
+    shc_simple=("SHC", dict(kwargs_formula=dict(spin_current_type="simple"))),
+    shc_simple_int=("SHC", dict(kwargs_formula=dict(spin_current_type="simple", external_terms=False))),
+    shc_ryoo_thresh=("SHC", dict(degen_thresh=0.3, kwargs_formula=dict(spin_current_type="ryoo"))),
+    shc_qiao_tetra=("SHC", dict(tetra=True, kwargs_formula=dict(spin_current_type="qiao"))),
+)
+
+
+def test_fermi_sea_formulae_random_system(wb):
+    """DerOmega (BerryDipole_FermiSea, NLAHC_FermiSea; formula/covariant.py:212-259) and SpinOmega (static.SHC; :759-789)
+    on the reference's `random` system (full d_aH channels, degenerate groups, tetrahedron method) through run(), all
+    scans in one call, against the live reference run of tests/golden/make_golden_fsea.py."""
+    g = np.load(os.path.join(GOLDEN, "golden_fsea.npz"))
+    rnd = wb.System_R.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    st = wb.calculators.static
+    calcs = {k: getattr(st, name)(Efermi=g["rnd_Efermi"], **kw) for k, (name, kw) in FSEA_CASES.items()}
+    res = wb.run(rnd, wb.Grid(rnd, NK=g["rnd_NK"], NKFFT=g["rnd_NKFFT"]), calcs)
+    for k in FSEA_CASES:
+        assert res.results[k].data.shape == g["rnd_" + k].shape, k
+        assert relerr(res.results[k].data, g["rnd_" + k]) < RTOL, k
+
+
+def test_te_qe_berry_dipole_fermi_sea_vs_upstream_goldens(wb):
+    """The reference's Te test (tests/test_run.py:1101-1119): BerryDipole_FermiSea and NLAHC_FermiSea with the tetrahedron
+    method on the symmetry-reduced K-list, against the reference's own golden files
+    Te_QE-{BerryDipole_FermiSea,berry_dipole}_iter-0000.npz; and without tetrahedra against the live reference run."""
+    g = np.load(os.path.join(GOLDEN, "golden_fsea.npz"))
+    te = wb.System_R.from_npz(os.path.join(GOLDEN, "te_system.npz"), pointgroup=["C3z", "C2x", "TimeReversal"])
+    Ef = g["te_Efermi"]
+    st = wb.calculators.static
+    calcs = dict(BerryDipole_FermiSea=st.BerryDipole_FermiSea(Efermi=Ef, tetra=True),
+                 berry_dipole=st.NLAHC_FermiSea(Efermi=Ef, tetra=True),
+                 BerryDipole_FermiSea_notetra=st.BerryDipole_FermiSea(Efermi=Ef))
+    res = wb.run(te, wb.Grid(te, NK=g["te_NK"], NKFFT=g["te_NKFFT"]), calcs, use_irred_kpt=True, symmetrize=True)
+    for q in calcs:
+        assert relerr(res.results[q].data, g["te_" + q]) < RTOL, q
+        if "te_upstream_golden_" + q in g.files:
+            assert relerr(res.results[q].data, g["te_upstream_golden_" + q]) < RTOL, q
+
+
+@pytest.mark.parametrize("nw,pairs", [(12, True), (35, False)])
+def test_fermi_sea_formulae_synthetic(wb, orc, nw, pairs):
+    """DerOmega and SpinOmega on synthetic models with the R <-> -R symmetry (hermitian-packed derivative channels):
+    exactly degenerate pairs (groups of two bands, D = 0 inside a group) and more bands than a warp, against the oracle."""
+    sysg = wb.synthetic_system(nw, rmax=1, seed=300 + nw, matrices=("Ham", "AA", "SS"), degenerate_pairs=pairs)
+    rng = np.random.default_rng(11 + nw)
+    nR = sysg.rvec.nRvec
+    for key, tail in (("SA", (3, 3)), ("SHA", (3, 3))):
+        shape = (nR, nw, nw) + tail
+        sysg.set_R_mat(key, 0.1 * (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)))
+    syso = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
+                            {k: sysg.get_R_mat(k) for k in ("Ham", "AA", "SS", "SA", "SHA")})
+    NKFFT, dK = [2, 2, 2], [0.05, 0.11, 0.02]
+    Ef = np.linspace(-1., 1., 21)
+    data = wb.Data_K_R(sysg, dK=dK, grid=wb.Grid(sysg, NKdiv=[1, 1, 1], NKFFT=NKFFT))
+    odata = orc.OracleDataK(syso, dK, NKFFT)
+    st = wb.calculators.static
+    got = st.BerryDipole_FermiSea(Efermi=Ef)(data).data
+    assert relerr(got, orc.BerryDipole_FermiSea(odata, Ef)) < RTOL
+    got = st.BerryDipole_FermiSea(Efermi=Ef, kwargs_formula=dict(external_terms=False))(data).data
+    assert relerr(got, orc.BerryDipole_FermiSea(odata, Ef, kwargs_formula=dict(external_terms=False))) < RTOL
+    got = st.SHC(Efermi=Ef, kwargs_formula=dict(spin_current_type="ryoo"))(data).data
+    assert relerr(got, orc.SHC_static(odata, Ef, kwargs_formula=dict(spin_current_type="ryoo"))) < RTOL
+
+
 def test_ohmic_fsurf_vs_upstream_golden(wb, fe):
     """Ohmic_FermiSurf (formula VelVel) against the reference's own golden file
     Fe_W90-conductivity_ohmic_fsurf_iter-0000.npz, with degenerate groups, and with the tetrahedron method."""

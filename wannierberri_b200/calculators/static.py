@@ -16,7 +16,8 @@ _TR_INV = {  # transformTR, transformInv of the formulae (covariant.py)
     _lib.IDENTITY: ("ident", "ident"), _lib.OMEGA: ("odd", "ident"), _lib.MORB_HPM: ("odd", "ident"),
     _lib.SPIN: ("odd", "ident"), _lib.VEL_OMEGA: ("ident", "odd"), _lib.VEL_HPLUS: ("ident", "odd"),
     _lib.VEL_SPIN: ("ident", "odd"), _lib.VEL_VEL: ("ident", "ident"),
-    _lib.INV_MASS: ("ident", "ident"),
+    _lib.INV_MASS: ("ident", "ident"), _lib.DER_OMEGA: ("ident", "odd"),
+    _lib.SHC_RYOO: ("ident", "ident"), _lib.SHC_QIAO: ("ident", "ident"), _lib.SHC_SIMPLE: ("ident", "ident"),
 }
 
 
@@ -37,6 +38,8 @@ class Calculator:
 
 class StaticCalculator(Calculator):
 
+    extra_kwargs_formula = ()
+
     def __init__(self, Efermi, tetra=False, smoother=None, constant_factor=1., use_factor=True, kwargs_formula=None,
                  Emin=-np.inf, Emax=np.inf, hole_like=False, k_resolved=False, Formula=None, fder=None,
                  select_bands=None, **kwargs):
@@ -55,7 +58,7 @@ class StaticCalculator(Calculator):
         if Emin != -np.inf or Emax != np.inf:
             raise NotImplementedError("Emin/Emax band selection is not implemented on the GPU path")
         self.kwargs_formula = copy(kwargs_formula) if kwargs_formula is not None else {}
-        unknown = set(self.kwargs_formula) - {"internal_terms", "external_terms"}
+        unknown = set(self.kwargs_formula) - {"internal_terms", "external_terms"} - set(self.extra_kwargs_formula)
         if unknown:
             raise NotImplementedError(f"kwargs_formula {sorted(unknown)} are not implemented on the GPU path")
         self.use_factor = use_factor
@@ -240,8 +243,48 @@ class Ohmic_FermiSea(StaticCalculator):
         super().__init__(constant_factor=constant_factor, **kwargs)
 
 
+class BerryDipole_FermiSea(StaticCalculator):
+    r"""Berry curvature dipole (dimensionless)
+
+        | With Fermi sea integral. Eq(29) in `Ref <https://www.nature.com/articles/s41524-021-00498-5>`__
+        | Output: :math:`D_{\beta\delta} = \int [dk] \partial_\beta \Omega_\delta f`"""
+
+    def __init__(self, **kwargs):
+        self.Formula = _lib.DER_OMEGA
+        self.fder = 0
+        super().__init__(**kwargs)
+
+    def combine(self, arrays, cell_volume):  # static.py:483-487: axes swapped to (beta, delta)
+        return np.ascontiguousarray(arrays[0].swapaxes(1, 2))
+
+
+class NLAHC_FermiSea(BerryDipole_FermiSea):
+    r"""Nonlinear anomalous Hall conductivity  (:math:`S^2/A`)
+
+        | With Fermi sea integral. Eq(29) in `Ref <https://www.nature.com/articles/s41524-021-00498-5>`__
+        | Output: :math:`D_{\beta\delta} = e^3/\hbar^2 \tau \int [dk] \partial_\beta \Omega_\delta f`"""
+
+    def __init__(self, constant_factor=factors.factor_nlahc, **kwargs):
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+class SHC(StaticCalculator):
+    r"""Spin Hall conductivity with dc (:math:`S/m`), Fermi sea integral of the spin Berry curvature (static.py:647-660);
+    `kwargs_formula={'spin_current_type': 'ryoo' | 'qiao' | 'simple'}`.  Output `[Efermi, a, b, s]`."""
+    extra_kwargs_formula = ("spin_current_type",)
+
+    def __init__(self, constant_factor=-factors.factor_ahc / 2, **kwargs):
+        t = (kwargs.get("kwargs_formula") or {}).get("spin_current_type", "ryoo")
+        if t not in _lib.SHC_TYPES:
+            raise ValueError(f"spin_current_type {t} not recognized")  # formula/covariant.py:696-697
+        self.Formula = _lib.SHC_TYPES[t]
+        self.fder = 0
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
 _BY_NAME = {c.__name__: c for c in (DOS, CumDOS, Spin, AHC, Morb, BerryDipole_FermiSurf, GME_orb_FermiSurf,
-                                    GME_spin_FermiSurf, Ohmic_FermiSurf, Ohmic_FermiSea)}
+                                    GME_spin_FermiSurf, Ohmic_FermiSurf, Ohmic_FermiSea, BerryDipole_FermiSea,
+                                    NLAHC_FermiSea, SHC)}
 
 
 def adapt(calc):
@@ -256,9 +299,10 @@ def adapt(calc):
               kwargs_formula=calc.kwargs_formula, hole_like=False, k_resolved=calc.k_resolved,
               select_bands=calc.select_bands, degen_thresh=calc.degen_thresh, degen_Kramers=calc.degen_Kramers,
               save_mode=calc.save_mode)
-    if name not in ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf"):
+    fixed = ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf", "BerryDipole_FermiSea")   # no constant_factor argument
+    if name not in fixed:
         kw["constant_factor"] = calc.constant_factor  # hole_like sign already folded in by the reference
     new = _BY_NAME[name](**kw)
-    if name in ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf"):
+    if name in fixed:
         new.constant_factor = calc.constant_factor
     return new

@@ -60,6 +60,8 @@ struct WbLayout {
     int off_W[6];    // d_b d_d H, (b, d) = xx xy xz yy yz zz; packed like d_a H (triangle iff dH_herm)
     // spin-current matrices (full): [3 velocity][3 spin] -> index 3 a + s; SH: [3 spin]
     int off_SA[9], off_SHA[9], off_SR[9], off_SH[3], off_SHR[9];
+    // comma-derivatives d_d A_b and d_d rotA_c (index 3 b + d), hermitian like A and rotA (data_K_R.py:84-87)
+    int off_dA[9], off_dO[9];
 };
 
 // index of the symmetric pair (b, d) in off_W

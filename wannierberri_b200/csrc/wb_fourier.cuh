@@ -92,6 +92,17 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
                 add_herm(table, cellR, cellmR, E, L.off_O[c], i, j, nw, cmake(-d.y, d.x));
             }
         }
+        if (L.off_dA[0] >= 0) {   // i T_d A_b and i T_d rotA_c (rvectors.py:487-494)
+            for (int b = 0; b < 3; b++) {
+                const int al = WB_ALPHA(b), be = WB_BETA(b);
+                const cplx r0 = cmake(T[al] * A[be].x - T[be] * A[al].x, T[al] * A[be].y - T[be] * A[al].y);
+                const cplx rot = cmake(-r0.y, r0.x);
+                for (int d = 0; d < 3; d++) {
+                    add_herm(table, cellR, cellmR, E, L.off_dA[3 * b + d], i, j, nw, cmake(-T[d] * A[b].y, T[d] * A[b].x));
+                    add_herm(table, cellR, cellmR, E, L.off_dO[3 * b + d], i, j, nw, cmake(-T[d] * rot.y, T[d] * rot.x));
+                }
+            }
+        }
     }
     if (in.BB && L.off_B[0] >= 0)
         for (int a = 0; a < 3; a++) atomic_cadd(&table[cellR * E + L.off_B[a] + i * nw + j], in.BB[idx * 3 + a]);

@@ -1,0 +1,244 @@
+// Fermi-sea formulae of next-row 4 on the rotated matrices of wb_rotate_gemm.cuh:
+//   wb_spinomega_events_kernel   SpinOmega (spin Berry curvature, static.SHC; formula/covariant.py:759-789), rank 3
+//   wb_deromega_events_kernel    DerOmega  (generalised derivative of the Berry curvature, BerryDipole_FermiSea /
+//                                NLAHC_FermiSea; formula/covariant.py:212-259 with DerDcov, formula/elementary.py:56-72,
+//                                and Matrix_GenDer_ln, formula/formula.py:95-118), rank 2
+// One CTA per k-point; band groups and the "event" output (one slot per band that starts a group, values of the trace
+// over the group) are those of wb_events_generic.cuh, so the Fermi scan / tetrahedron stages are shared.  Each of the
+// two formulae is evaluated in an event pass of its own (WbEventLayout with a single formula at offset 0).
+#pragma once
+#include "wb_common.cuh"
+#include "wb_groups.cuh"
+#include "wb_rotate_formula.cuh"
+
+// positions (in units of nw x nw matrices of the rotated record of one k-point) of the matrices DerOmega needs
+struct WbDerOmegaChans {
+    int iV, iA, iO, iW, idA, idO;   // d_a H [3] | A [3] | rotA [3] | d_b d_d H [6, wb_sym6] | d_d A_b [9, 3 b + d] | d_d rotA_c [9]
+};
+
+__host__ inline size_t wb_fsea_smem_bytes(int nw, int ncomp) {
+    return sizeof(double) * (2 * (size_t)nw + (size_t)nw * nw + (size_t)nw * ncomp) + 2 * nw * sizeof(short) + 64;
+}
+
+template <int NT>
+__device__ __forceinline__ void wb_fsea_groups(const double* __restrict__ Eall, long ik, int nw, const WbWindow& win,
+                                               double* Es, double* label, double* inv, short* g1, short* g2) {
+    for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
+    __syncthreads();
+    if (win.Ebmin) {
+        if (threadIdx.x == 0) wb_band_groups_tetra(Es, win.Ebmin + ik * nw, win.Ebmax + ik * nw, nw, win, g1, g2, label);
+    } else if (nw <= 32) {
+        if (threadIdx.x < 32) wb_band_groups_warp(Es, nw, win, g1, g2, label, threadIdx.x);
+    } else if (threadIdx.x == 0) wb_band_groups(Es, nw, win, g1, g2, label);
+    for (int x = threadIdx.x; x < nw * nw; x += NT) inv[x] = wb_deinv(Es[x / nw], Es[x % nw]);   // dEig_inv (data_K.py:290-298)
+    __syncthreads();
+}
+
+// trace_G[a][b][s] = sum_{m in G} sum_{l notin G} -2 Im( J_ml^{as} / (E_m - E_l) * (D_lm^b - i A_lm^b) )
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_spinomega_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall,
+                           WbWindow win, int iV, int iA, const cplx* __restrict__ Jspin, double* __restrict__ ev_label,
+                           double* __restrict__ ev_val) {
+    extern __shared__ __align__(16) double smem_f[];
+    const int n2 = nw * nw;
+    double* Es = smem_f;
+    double* label = Es + nw;
+    double* inv = label + nw;
+    double* vals = inv + n2;           // [nw][27]
+    short* g1 = (short*)(vals + 27 * nw);
+    short* g2 = g1 + nw;
+    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        __syncthreads();
+        wb_fsea_groups<NT>(Eall, ik, nw, win, Es, label, inv, g1, g2);
+        const cplx* X = xbar + (size_t)ik * nch * n2;
+        const cplx* J = Jspin + (size_t)ik * 9 * n2;
+        for (int x = threadIdx.x; x < nw * 27; x += NT) {
+            const int m = x / 27, comp = x - 27 * m;
+            const int a = comp / 9, b = (comp / 3) % 3, s = comp % 3;
+            double acc = 0.;
+            if (g1[m] >= 0) {
+                const int ga = g1[m], gb = g2[m];
+                const cplx* Jm = J + (size_t)(3 * a + s) * n2 + m * nw;
+                const cplx* Vb = X + (size_t)(iV + b) * n2;
+                for (int l = 0; l < nw; l++) {
+                    if (l >= ga && l < gb) continue;
+                    const double iml = inv[m * nw + l];
+                    const cplx v = Vb[l * nw + m];
+                    cplx vd = cmake(iml * v.x, iml * v.y);      // D_lm = -V_lm / (E_l - E_m) = V_lm / (E_m - E_l)
+                    if (iA >= 0) {                               // - i A_lm
+                        const cplx al = X[(size_t)(iA + b) * n2 + l * nw + m];
+                        vd = cmake(vd.x + al.y, vd.y - al.x);
+                    }
+                    const cplx j = Jm[l];
+                    acc += iml * (j.x * vd.y + j.y * vd.x);
+                }
+            }
+            vals[x] = -2. * acc;
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x < nw; x += NT) ev_label[ik * nw + x] = label[x];
+        for (int x = threadIdx.x; x < nw * 27; x += NT) {
+            const int n0 = x / 27, comp = x - 27 * n0;
+            if (label[n0] != CUDART_INF) {
+                double s = 0.;
+                for (int n = n0; n < g2[n0]; n++) s += vals[n * 27 + comp];
+                ev_val[((size_t)ik * nw + n0) * 27 + comp] = s;
+            }
+        }
+    }
+}
+
+__host__ __device__ inline size_t wb_deromega_scratch_elems(int nw) { return (size_t)36 * nw * nw; }   // complex elements per CTA
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_deromega_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall,
+                          WbWindow win, WbDerOmegaChans C, int internal, int external, cplx* __restrict__ scratch,
+                          double* __restrict__ ev_label, double* __restrict__ ev_val) {
+    extern __shared__ __align__(16) double smem_f[];
+    const int n2 = nw * nw;
+    double* Es = smem_f;
+    double* label = Es + nw;
+    double* inv = label + nw;
+    double* vals = inv + n2;           // [nw][9]: rows of the current group (indexed by band)
+    short* g1 = (short*)(vals + 9 * nw);
+    short* g2 = g1 + nw;
+    cplx* const T1 = scratch + (size_t)blockIdx.x * wb_deromega_scratch_elems(nw);   // dD_ln [l][n - ga][b][d]
+    cplx* const T2 = T1 + (size_t)9 * n2;                                            // dD_ml [m - ga][l][a][d]
+    cplx* const T3 = T2 + (size_t)9 * n2;                                            // dA_ln [l][n - ga][b][d]
+    cplx* const T4 = T3 + (size_t)9 * n2;                                            // dA_pn [p - ga][n - ga][b][d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = NT / 32;
+    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        __syncthreads();
+        wb_fsea_groups<NT>(Eall, ik, nw, win, Es, label, inv, g1, g2);
+        const cplx* X = xbar + (size_t)ik * nch * n2;
+        const cplx* V = X + (size_t)C.iV * n2;
+        const cplx* A = X + (size_t)C.iA * n2;
+        const cplx* O = X + (size_t)C.iO * n2;
+        const cplx* W = X + (size_t)C.iW * n2;
+        const cplx* dAc = X + (size_t)C.idA * n2;
+        const cplx* dOc = X + (size_t)C.idO * n2;
+        auto Dm = [&](int a, int p, int q) {   // D_pq,a = -V_pq,a / (E_p - E_q)
+            return cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]);
+        };
+        for (int x = threadIdx.x; x < nw; x += NT) ev_label[ik * nw + x] = label[x];
+        for (int ga = 0; ga < nw; ga++) {
+            if (label[ga] == CUDART_INF) continue;   // uniform: no group starts here
+            const int gb = g2[ga], g = gb - ga;
+            auto in_G = [&](int q) { return q >= ga && q < gb; };
+            // ---- DerDcov: dD_rc^{bd} = -1/(E_r - E_c) ( W_rc^{bd} + sum_{p in rows} (V_rp^b D_pc^d + V_rp^d D_pc^b)
+            //                                              - sum_{q in cols} (D_rq^b V_qc^d + D_rq^d V_qc^b) )
+            //      T1: rows = out, cols = G;  T2: rows = G, cols = out (needed by the external terms only)
+            const int nT12 = external ? 2 : 1;
+            for (int x = threadIdx.x; x < nT12 * nw * g * 9; x += NT) {
+                const int which = x / (nw * g * 9);
+                int y = x - which * (nw * g * 9);
+                const int bd = y % 9; y /= 9;
+                const int b = bd / 3, d = bd - 3 * b;
+                int r, cidx;
+                if (which == 0) { cidx = ga + y % g; r = y / g; }    // r = l (any band), c in G
+                else { cidx = y % nw; r = ga + y / nw; }             // r = m in G, c = l
+                const bool rG = in_G(r), cG = in_G(cidx);
+                cplx res = cmake(0., 0.);
+                if (rG != cG) {
+                    cplx sum = W[(size_t)wb_sym6(b, d) * n2 + r * nw + cidx];
+                    for (int p = 0; p < nw; p++) {
+                        if (in_G(p) == rG) {      // p in the row set
+                            cfma(sum, V[(size_t)b * n2 + r * nw + p], Dm(d, p, cidx));
+                            cfma(sum, V[(size_t)d * n2 + r * nw + p], Dm(b, p, cidx));
+                        } else {                  // p in the column set
+                            const cplx z1 = cmul(Dm(b, r, p), V[(size_t)d * n2 + p * nw + cidx]);
+                            const cplx z2 = cmul(Dm(d, r, p), V[(size_t)b * n2 + p * nw + cidx]);
+                            sum = cmake(sum.x - z1.x - z2.x, sum.y - z1.y - z2.y);
+                        }
+                    }
+                    res = cscale(-inv[r * nw + cidx], sum);
+                }
+                if (which == 0) T1[((size_t)r * g + (cidx - ga)) * 9 + bd] = res;
+                else T2[((size_t)(r - ga) * nw + cidx) * 9 + bd] = res;
+            }
+            // ---- Matrix_GenDer_ln of A:  T3 = dA.ln (l in out, n in G),  T4 = dA.nn (p, n in G)
+            if (external) {
+                for (int x = threadIdx.x; x < nw * g * 9; x += NT) {
+                    int y = x;
+                    const int bd = y % 9; y /= 9;
+                    const int b = bd / 3, d = bd - 3 * b;
+                    const int n = ga + y % g, l = y / g;
+                    cplx sum = dAc[(size_t)bd * n2 + l * nw + n];
+                    if (!in_G(l)) {
+                        // dA_ln = A,d_ln - sum_{m' in G} D_lm'^d A_m'n^b + sum_{p in out} A_lp^b D_pn^d
+                        for (int p = 0; p < nw; p++) {
+                            if (in_G(p)) {
+                                const cplx z = cmul(Dm(d, l, p), A[(size_t)b * n2 + p * nw + n]);
+                                sum = cmake(sum.x - z.x, sum.y - z.y);
+                            } else cfma(sum, A[(size_t)b * n2 + l * nw + p], Dm(d, p, n));
+                        }
+                        T3[((size_t)l * g + (n - ga)) * 9 + bd] = sum;
+                    } else {
+                        // dA_pn (p = l in G) = A,d_pn - sum_{q in out} D_pq^d A_qn^b + sum_{q in out} A_pq^b D_qn^d
+                        for (int q = 0; q < nw; q++) {
+                            if (in_G(q)) continue;
+                            const cplx z = cmul(Dm(d, l, q), A[(size_t)b * n2 + q * nw + n]);
+                            sum = cmake(sum.x - z.x, sum.y - z.y);
+                            cfma(sum, A[(size_t)b * n2 + l * nw + q], Dm(d, q, n));
+                        }
+                        T4[((size_t)(l - ga) * g + (n - ga)) * 9 + bd] = sum;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- trace: one warp per (m in G, c, d), lanes over the partner bands
+            for (int item = warp; item < g * 9; item += nwarp) {
+                const int m = ga + item / 9, cd = item % 9, c = cd / 3, d = cd - 3 * c;
+                cplx S = cmake(0., 0.);
+                for (int l = lane; l < nw; l += 32) {
+                    const bool lG = in_G(l);
+                    if (external && !lG) {   // 1/2 of the generalised derivative of rotA, off-diagonal part
+                        cplx z = cmul(O[(size_t)c * n2 + m * nw + l], Dm(d, l, m));
+                        const cplx z2 = cmul(Dm(d, m, l), O[(size_t)c * n2 + l * nw + m]);
+                        S.x += 0.5 * (z.x - z2.x);
+                        S.y += 0.5 * (z.y - z2.y);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        const int a = t ? WB_BETA(c) : WB_ALPHA(c), b = t ? WB_ALPHA(c) : WB_BETA(c);
+                        const double sg = t ? -1. : 1.;
+                        if (!lG) {
+                            const cplx Dml = Dm(a, m, l);
+                            if (internal) {   // -i s D_ml^a dD_lm^{bd}
+                                const cplx z = cmul(Dml, T1[((size_t)l * g + (m - ga)) * 9 + 3 * b + d]);
+                                S.x += sg * z.y;
+                                S.y -= sg * z.x;
+                            }
+                            if (external) {   // -s D_ml^a dA_lm^{b:d} - s dD_ml^{ad} A_lm^b
+                                const cplx z = cmul(Dml, T3[((size_t)l * g + (m - ga)) * 9 + 3 * b + d]);
+                                const cplx z2 = cmul(T2[((size_t)(m - ga) * nw + l) * 9 + 3 * a + d], A[(size_t)b * n2 + l * nw + m]);
+                                S.x -= sg * (z.x + z2.x);
+                                S.y -= sg * (z.y + z2.y);
+                            }
+                        } else if (external) {   // -i s A_mp^a dA_pm^{b:d},  p = l in G
+                            const cplx z = cmul(A[(size_t)a * n2 + m * nw + l], T4[((size_t)(l - ga) * g + (m - ga)) * 9 + 3 * b + d]);
+                            S.x += sg * z.y;
+                            S.y -= sg * z.x;
+                        }
+                    }
+                }
+                double re = S.x;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) re += __shfl_xor_sync(0xffffffffu, re, o);
+                if (lane == 0) {
+                    if (external) re += 0.5 * dOc[(size_t)cd * n2 + m * nw + m].x;
+                    vals[m * 9 + cd] = 2. * re;   // summ + summ^dagger, real part of the trace
+                }
+            }
+            __syncthreads();
+            for (int cd = threadIdx.x; cd < 9; cd += NT) {
+                double s = 0.;
+                for (int n = ga; n < gb; n++) s += vals[n * 9 + cd];
+                ev_val[((size_t)ik * nw + ga) * 9 + cd] = s;
+            }
+            __syncthreads();
+        }
+    }
+}

@@ -28,6 +28,7 @@
 #include "wb_rotate_gemm.cuh"
 #include "wb_scan.cuh"
 #include "wb_kubo.cuh"
+#include "wb_fsea.cuh"
 #include "wb_tetra.cuh"
 #include "wb_probe.cuh"
 
@@ -264,14 +265,18 @@ static int formula_rank(int f) {
     switch (f) {
         case WBGPU_IDENTITY: return 0;
         case WBGPU_OMEGA: case WBGPU_MORB_HPM: case WBGPU_SPIN: return 1;
-        case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: case WBGPU_VEL_VEL: case WBGPU_INV_MASS: return 2;
+        case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: case WBGPU_VEL_VEL: case WBGPU_INV_MASS:
+        case WBGPU_DER_OMEGA: return 2;
+        case WBGPU_SHC_RYOO: case WBGPU_SHC_QIAO: case WBGPU_SHC_SIMPLE: return 3;   // SpinOmega
     }
     return -1;
 }
 static int formula_ncomp(int f) {
     int r = formula_rank(f);
-    return r == 0 ? 1 : r == 1 ? 3 : 9;
+    return r == 0 ? 1 : r == 1 ? 3 : r == 2 ? 9 : 27;
 }
+// formulae evaluated by a kernel of their own (wb_fsea.cuh): one event pass per spec
+static bool formula_solo(int f) { return f == WBGPU_SHC_RYOO || f == WBGPU_SHC_QIAO || f == WBGPU_SHC_SIMPLE || f == WBGPU_DER_OMEGA; }
 static int fder_extra(int fder) { return fder == 0 ? 0 : (fder <= 2 ? 1 : 2); }
 
 extern "C" int64_t wbgpu_spec_size(const wbgpu_scan_spec* s) {
@@ -308,10 +313,10 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     auto has = [&](int f) { return (m >> f) & 1u; };
     bool need_dH = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
                    has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO) || has(WBGPU_VEL_VEL) || has(WBGPU_INV_MASS) || has(WBGPU_SHC_RYOO) ||
-                   has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE);
+                   has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE) || has(WBGPU_DER_OMEGA);
     const bool shc = has(WBGPU_SHC_RYOO) || has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE);
     bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) || has(WBGPU_KUBO);
-    bool need_A = (berry || shc) && external_terms;
+    bool need_A = (berry || shc || has(WBGPU_DER_OMEGA)) && external_terms;
     bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS)) && external_terms;
     bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN) || shc;
     if (has(WBGPU_SHC_RYOO) && (!c->d_XR[WBGPU_SA] || !c->d_XR[WBGPU_SHA]))
@@ -359,12 +364,15 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     L.off_H = take(true);
     for (int a = 0; a < 3; a++) L.off_dH[a] = need_dH ? take(dH_herm) : -1;
     for (int a = 0; a < 3; a++) L.off_A[a] = need_A ? take(true) : -1;
-    bool need_O = need_A && (has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS));
+    bool need_O = need_A && (has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
+                             has(WBGPU_DER_OMEGA));
     for (int a = 0; a < 3; a++) L.off_O[a] = need_O ? take(true) : -1;
     for (int a = 0; a < 3; a++) L.off_B[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_C[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_S[a] = need_S ? take(true) : -1;
-    for (int a = 0; a < 6; a++) L.off_W[a] = has(WBGPU_INV_MASS) ? take(dH_herm) : -1;
+    for (int a = 0; a < 6; a++) L.off_W[a] = (has(WBGPU_INV_MASS) || has(WBGPU_DER_OMEGA)) ? take(dH_herm) : -1;
+    for (int a = 0; a < 9; a++) L.off_dA[a] = (has(WBGPU_DER_OMEGA) && need_A) ? take(true) : -1;
+    for (int a = 0; a < 9; a++) L.off_dO[a] = (has(WBGPU_DER_OMEGA) && need_A) ? take(true) : -1;
     for (int a = 0; a < 9; a++) L.off_SA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_SHA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_SR[a] = has(WBGPU_SHC_QIAO) ? take(false) : -1;
@@ -688,6 +696,7 @@ struct EvGroup {
     WbWindow win;
     WbEventLayout ev;
     std::vector<int> specs;
+    bool solo = false;   // a formula with an event kernel of its own
 };
 
 static bool same_window(const WbWindow& a, const WbWindow& b) {
@@ -702,10 +711,10 @@ static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec)
         WbWindow w = make_window(s);
         bool ident = (s.formula == WBGPU_IDENTITY);
         int found = -1;
-        for (size_t g = 0; g < groups.size(); g++) {
+        for (size_t g = 0; g < groups.size() && !formula_solo(s.formula); g++) {
             EvGroup& G = groups[g];
             bool g_ident = (G.ev.mask == 1);
-            if (g_ident != ident || !same_window(G.win, w)) continue;
+            if (G.solo || g_ident != ident || !same_window(G.win, w)) continue;
             if (!ident && (G.ev.internal_terms != s.internal_terms || G.ev.external_terms != s.external_terms)) continue;
             found = (int)g;
             break;
@@ -715,7 +724,8 @@ static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec)
             G.win = w;
             G.ev.mask = 0;
             G.ev.NC = 0;
-            for (int f = 0; f < 12; f++) G.ev.off[f] = 0;
+            for (int f = 0; f < 16; f++) G.ev.off[f] = 0;
+            G.solo = formula_solo(s.formula);
             G.ev.internal_terms = s.internal_terms;
             G.ev.external_terms = s.external_terms;
             groups.push_back(G);
@@ -836,6 +846,90 @@ static int run_events_xbar(wbgpu_ctx* c, const EvGroup& G, long nk) {
     return 0;
 }
 
+// SpinOmega / DerOmega: batched DMMA rotation to global memory, then the formula's own event kernel (wb_fsea.cuh)
+static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
+    const int nw = c->nw, n2 = nw * nw;
+    const WbLayout& L = c->L;
+    int formula = -1;
+    for (int f = 0; f < WBGPU_NFORMULA; f++)
+        if ((G.ev.mask >> f) & 1) formula = f;
+    const bool ext = G.ev.external_terms;
+    WbChanList ch;
+    ch.n = 0;
+    auto addn = [&](const int* offs, int n, int herm) {
+        const int first = ch.n;
+        for (int a = 0; a < n; a++) { ch.off[ch.n] = offs[a]; ch.herm[ch.n] = herm; ch.n++; }
+        return first;
+    };
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    constexpr int NT = 256;
+    if (formula == WBGPU_DER_OMEGA) {
+        if (L.off_dH[0] < 0 || L.off_W[0] < 0 || (ext && (L.off_A[0] < 0 || L.off_O[0] < 0 || L.off_dA[0] < 0)))
+            return set_err("scan: the plan does not hold the channels of DerOmega");
+        WbDerOmegaChans C;
+        C.iV = addn(L.off_dH, 3, L.dH_herm);
+        C.iW = addn(L.off_W, 6, L.dH_herm);
+        C.iA = C.iO = C.idA = C.idO = 0;
+        if (ext) {
+            C.iA = addn(L.off_A, 3, 1);
+            C.iO = addn(L.off_O, 3, 1);
+            C.idA = addn(L.off_dA, 9, 1);
+            C.idO = addn(L.off_dO, 9, 1);
+        }
+        const long chunk = xbar_chunk(c, ch.n, nk);
+        if (ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * n2)) return 1;
+        const size_t per_cta = sizeof(cplx) * wb_deromega_scratch_elems(nw);
+        const long nblk_max = std::max(32L, std::min((long)sms * 4, (long)(1.5e9 / (double)per_cta)));
+        if (ensure(&c->d_mx, &c->mx_cap, per_cta * (size_t)nblk_max)) return 1;
+        const size_t smem = wb_fsea_smem_bytes(nw, 9);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(wb_deromega_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (long k0 = 0; k0 < nk; k0 += chunk) {
+            const long n = std::min(chunk, nk - k0);
+            if (rotate_gemm(c, ch, k0, n)) return 1;
+            WbWindow wloc = G.win;
+            if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
+            wb_deromega_events_kernel<NT><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, C, G.ev.internal_terms, ext ? 1 : 0, (cplx*)c->d_mx,
+                c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * 9);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
+        return 0;
+    }
+    // SpinOmega
+    if (L.off_dH[0] < 0 || L.off_S[0] < 0 || (ext && L.off_A[0] < 0))
+        return set_err("scan: the plan does not hold the channels of SpinOmega");
+    WbShcChans sc;
+    sc.type = formula; sc.iA = sc.iX1 = sc.iX2 = sc.iX3 = -1;
+    sc.iV = addn(L.off_dH, 3, L.dH_herm);
+    if (ext) sc.iA = addn(L.off_A, 3, 1);
+    sc.iS = addn(L.off_S, 3, 1);
+    if (formula == WBGPU_SHC_RYOO) { sc.iX1 = addn(L.off_SA, 9, 0); sc.iX2 = addn(L.off_SHA, 9, 0); }
+    if (formula == WBGPU_SHC_QIAO) { sc.iX1 = addn(L.off_SR, 9, 0); sc.iX2 = addn(L.off_SH, 3, 0); sc.iX3 = addn(L.off_SHR, 9, 0); }
+    const long chunk = xbar_chunk(c, ch.n, nk);
+    if (ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * n2)) return 1;
+    if (ensure(&c->d_shcJ, &c->shcJ_cap, sizeof(cplx) * (size_t)chunk * 9 * n2)) return 1;
+    const size_t smem = wb_fsea_smem_bytes(nw, 27);
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(wb_spinomega_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (long k0 = 0; k0 < nk; k0 += chunk) {
+        const long n = std::min(chunk, nk - k0);
+        if (rotate_gemm(c, ch, k0, n)) return 1;
+        wb_shc_spinvel_kernel<256><<<(unsigned)std::min(n, (long)sms * 8), 256, sizeof(double) * nw, c->stream>>>(
+            (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, sc, ext ? 1 : 0, (cplx*)c->d_shcJ);
+        WbWindow wloc = G.win;
+        if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
+        wb_spinomega_events_kernel<NT><<<(unsigned)std::min(n, (long)sms * 8), NT, smem, c->stream>>>(
+            (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, sc.iV, sc.iA, (const cplx*)c->d_shcJ, c->d_evlabel + k0 * nw,
+            c->d_evval + (size_t)k0 * nw * 27);
+        c->launches += 2;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
 static int run_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
     const int nw = c->nw;
     const WbWindow& win = G.win;
@@ -851,6 +945,7 @@ static int run_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
         CK(cudaGetLastError());
         return 0;
     }
+    if (G.solo) return run_events_solo(c, G, nk);
     WbNeeds need = wb_needs(G.ev.mask, G.ev.external_terms);
     const WbLayout& L = c->L;
     if ((need.V && L.off_dH[0] < 0) || (need.A && L.off_A[0] < 0) || (need.B && L.off_B[0] < 0) ||
@@ -1123,7 +1218,7 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
     LH.nw = nw; LH.ntri = nw * (nw + 1) / 2; LH.E = LH.ntri; LH.off_H = 0; LH.dH_herm = 0;
     for (int a = 0; a < 3; a++) LH.off_dH[a] = LH.off_A[a] = LH.off_O[a] = LH.off_B[a] = LH.off_C[a] = LH.off_S[a] = -1;
     for (int a = 0; a < 6; a++) LH.off_W[a] = -1;
-    for (int a = 0; a < 9; a++) LH.off_SA[a] = LH.off_SHA[a] = LH.off_SR[a] = LH.off_SHR[a] = -1;
+    for (int a = 0; a < 9; a++) LH.off_SA[a] = LH.off_SHA[a] = LH.off_SR[a] = LH.off_SHR[a] = LH.off_dA[a] = LH.off_dO[a] = -1;
     for (int a = 0; a < 3; a++) LH.off_SH[a] = -1;
     const size_t ncell = (size_t)c->nbox.x * c->nbox.y * c->nbox.z;
     if (!c->d_tableH) {

@@ -61,7 +61,9 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
         raise ValueError("use_irred_kpt / symmetrize need system.pointgroup (System_R.set_pointgroup)")
     calcs, dyn_calcs = {}, {}
     for key, c in calculators.items():
-        dynamic = isinstance(c, _dyn.DynamicCalculator) or type(c).__name__ in _dyn._BY_NAME
+        # static.SHC and dynamic.SHC share their class name: a Kubo calculator is the one that carries a frequency axis
+        dynamic = isinstance(c, _dyn.DynamicCalculator) or (type(c).__name__ in _dyn._BY_NAME and hasattr(c, "omega")
+                                                             and not hasattr(c, "fder"))
         c = _dyn.adapt(c) if dynamic else adapt_static(c)
         if not c.allow_grid:
             raise ValueError(f"Calculator {key} is not compatible with a grid")
