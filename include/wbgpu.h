@@ -62,7 +62,15 @@ enum {
     WBGPU_SHC_SIMPLE = 12,
     WBGPU_DER_OMEGA = 13, /* DerOmega        covariant.py:212-259 (generalised derivative of the Berry curvature:
                              BerryDipole_FermiSea, NLAHC_FermiSea), rank 2 [c][d]; needs d_b d_d H, d_d A_b, d_d rotA_c */
-    WBGPU_NFORMULA = 14
+    WBGPU_DER_SPIN = 14,  /* DerSpin         covariant.py:338-342 (generalised derivative of the spin: GME_spin_FermiSea) rank 2 [s][d] */
+    /* FormulaProduct (formula/formula.py:121-149) of Velocity, InvMass, Omega, Spin nn-blocks (covariant.py:823-858) */
+    WBGPU_VEL_VEL_VEL = 15,   /* VelVelVel  rank 3 (NLDrude_Fermider2)      */
+    WBGPU_MASS_VEL = 16,      /* MassVel    rank 3 (NLDrude_FermiSurf)      */
+    WBGPU_MASS_MASS = 17,     /* MassMass   rank 4 (Hall_classic_FermiSea)  */
+    WBGPU_VEL_MASS_VEL = 18,  /* VelMassVel rank 4 (Hall_classic_FermiSurf) */
+    WBGPU_OMEGA_S = 19,       /* OmegaS     rank 2 (AHC_Zeeman_spin)        */
+    WBGPU_OMEGA_OMEGA = 20,   /* OmegaOmega rank 2                          */
+    WBGPU_NFORMULA = 21
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */

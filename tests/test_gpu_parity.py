@@ -658,6 +658,14 @@ FSEA_CASES = dict(
     shc_simple_int=("SHC", dict(kwargs_formula=dict(spin_current_type="simple", external_terms=False))),
     shc_ryoo_thresh=("SHC", dict(degen_thresh=0.3, kwargs_formula=dict(spin_current_type="ryoo"))),
     shc_qiao_tetra=("SHC", dict(tetra=True, kwargs_formula=dict(spin_current_type="qiao"))),
+    gme_spin_sea=("GME_spin_FermiSea", {}), gme_spin_sea_tetra=("GME_spin_FermiSea", dict(tetra=True)),
+    nldrude_fsurf=("NLDrude_FermiSurf", {}), nldrude_fder2=("NLDrude_Fermider2", {}),
+    nldrude_fsurf_thresh=("NLDrude_FermiSurf", dict(degen_thresh=0.3)),
+    hall_fsurf=("Hall_classic_FermiSurf", {}), hall_sea=("Hall_classic_FermiSea", {}),
+    hall_fsurf_thresh=("Hall_classic_FermiSurf", dict(degen_thresh=0.3)), hall_sea_tetra=("Hall_classic_FermiSea", dict(tetra=True)),
+    ahc_zeeman_spin=("AHC_Zeeman_spin", {}), ahc_zeeman_spin_thresh=("AHC_Zeeman_spin", dict(degen_thresh=0.3)),
+    ahc_zeeman_spin_int=("AHC_Zeeman_spin", dict(kwargs_formula=dict(external_terms=False))),
+    omegaomega=("OmegaOmega", {}), nlahc_fsurf=("NLAHC_FermiSurf", {}),
 )
 
 
@@ -678,19 +686,22 @@ def test_fermi_sea_formulae_random_system(wb):
 def test_te_qe_berry_dipole_fermi_sea_vs_upstream_goldens(wb):
     """The reference's Te test (tests/test_run.py:1101-1119): BerryDipole_FermiSea and NLAHC_FermiSea with the tetrahedron
     method on the symmetry-reduced K-list, against the reference's own golden files
-    Te_QE-{BerryDipole_FermiSea,berry_dipole}_iter-0000.npz; and without tetrahedra against the live reference run."""
+    Te_QE-{BerryDipole_FermiSea,berry_dipole,AHC_Zeeman_spin}_iter-0000.npz; and without tetrahedra against the live
+    reference run.  (AHC_Zeeman_spin: der = 1 tetrahedron weights, 1e-6 as in test_te_qe_tetra_symmetric_vs_upstream_goldens.)"""
     g = np.load(os.path.join(GOLDEN, "golden_fsea.npz"))
     te = wb.System_R.from_npz(os.path.join(GOLDEN, "te_system.npz"), pointgroup=["C3z", "C2x", "TimeReversal"])
     Ef = g["te_Efermi"]
     st = wb.calculators.static
     calcs = dict(BerryDipole_FermiSea=st.BerryDipole_FermiSea(Efermi=Ef, tetra=True),
                  berry_dipole=st.NLAHC_FermiSea(Efermi=Ef, tetra=True),
-                 BerryDipole_FermiSea_notetra=st.BerryDipole_FermiSea(Efermi=Ef))
+                 BerryDipole_FermiSea_notetra=st.BerryDipole_FermiSea(Efermi=Ef),
+                 AHC_Zeeman_spin=st.AHC_Zeeman_spin(Efermi=Ef, tetra=True))
     res = wb.run(te, wb.Grid(te, NK=g["te_NK"], NKFFT=g["te_NKFFT"]), calcs, use_irred_kpt=True, symmetrize=True)
     for q in calcs:
-        assert relerr(res.results[q].data, g["te_" + q]) < RTOL, q
+        tol = 1e-6 if q == "AHC_Zeeman_spin" else RTOL
+        assert relerr(res.results[q].data, g["te_" + q]) < tol, q
         if "te_upstream_golden_" + q in g.files:
-            assert relerr(res.results[q].data, g["te_upstream_golden_" + q]) < RTOL, q
+            assert relerr(res.results[q].data, g["te_upstream_golden_" + q]) < tol, q
 
 
 @pytest.mark.parametrize("nw,pairs", [(12, True), (35, False)])

@@ -302,6 +302,14 @@ FSEA_CASES = dict(
     shc_simple_int=("SHC_static", dict(kwargs_formula=dict(spin_current_type="simple", external_terms=False))),
     shc_ryoo_thresh=("SHC_static", dict(degen_thresh=0.3, kwargs_formula=dict(spin_current_type="ryoo"))),
     shc_qiao_tetra=("SHC_static", dict(tetra=True, kwargs_formula=dict(spin_current_type="qiao"))),
+    gme_spin_sea=("GME_spin_FermiSea", {}), gme_spin_sea_tetra=("GME_spin_FermiSea", dict(tetra=True)),
+    nldrude_fsurf=("NLDrude_FermiSurf", {}), nldrude_fder2=("NLDrude_Fermider2", {}),
+    nldrude_fsurf_thresh=("NLDrude_FermiSurf", dict(degen_thresh=0.3)),
+    hall_fsurf=("Hall_classic_FermiSurf", {}), hall_sea=("Hall_classic_FermiSea", {}),
+    hall_fsurf_thresh=("Hall_classic_FermiSurf", dict(degen_thresh=0.3)), hall_sea_tetra=("Hall_classic_FermiSea", dict(tetra=True)),
+    ahc_zeeman_spin=("AHC_Zeeman_spin", {}), ahc_zeeman_spin_thresh=("AHC_Zeeman_spin", dict(degen_thresh=0.3)),
+    ahc_zeeman_spin_int=("AHC_Zeeman_spin", dict(kwargs_formula=dict(external_terms=False))),
+    omegaomega=("OmegaOmega", {}), nlahc_fsurf=("NLAHC_FermiSurf", {}),
 )
 
 

@@ -18,7 +18,12 @@ _TR_INV = {  # transformTR, transformInv of the formulae (covariant.py)
     _lib.VEL_SPIN: ("ident", "odd"), _lib.VEL_VEL: ("ident", "ident"),
     _lib.INV_MASS: ("ident", "ident"), _lib.DER_OMEGA: ("ident", "odd"),
     _lib.SHC_RYOO: ("ident", "ident"), _lib.SHC_QIAO: ("ident", "ident"), _lib.SHC_SIMPLE: ("ident", "ident"),
+    # products: TransformProduct of the factors (V: odd, odd; InvMass: ident, ident; Omega, Spin: odd, ident)
+    _lib.DER_SPIN: ("ident", "odd"), _lib.VEL_VEL_VEL: ("odd", "odd"), _lib.MASS_VEL: ("odd", "odd"),
+    _lib.MASS_MASS: ("ident", "ident"), _lib.VEL_MASS_VEL: ("ident", "ident"), _lib.OMEGA_S: ("ident", "ident"),
+    _lib.OMEGA_OMEGA: ("ident", "ident"),
 }
+_ALPHA, _BETA = np.array([1, 2, 0]), np.array([2, 0, 1])   # utility.py:45-46
 
 
 class Calculator:
@@ -282,9 +287,97 @@ class SHC(StaticCalculator):
         super().__init__(constant_factor=constant_factor, **kwargs)
 
 
+class NLAHC_FermiSurf(BerryDipole_FermiSurf):
+    r"""Nonlinear anomalous Hall conductivity (:math:`S^2/A`), Fermi surface integral (static.py:461-469)"""
+
+    def __init__(self, constant_factor=factors.factor_nlahc, **kwargs):
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+class GME_spin_FermiSea(StaticCalculator):
+    r"""Gyrotropic tensor spin part (:math:`A`), Fermi sea integral (static.py:322-337)
+
+        | Output: :math:`K^{spin}_{\alpha :\mu} = -\int [dk] \partial_\alpha s_\mu f`"""
+
+    def __init__(self, constant_factor=factors.factor_gme_spin, **kwargs):
+        self.Formula = _lib.DER_SPIN
+        self.fder = 0
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+    def combine(self, arrays, cell_volume):
+        return np.ascontiguousarray(arrays[0].swapaxes(1, 2))
+
+
+def _hall_classic_post(d):   # static.py:419-423
+    d = d[:, :, :, _BETA, _ALPHA] - d[:, :, :, _ALPHA, _BETA]
+    return np.ascontiguousarray(0.5 * (d[:, _ALPHA, _BETA, :] - d[:, _BETA, _ALPHA, :]))
+
+
+class Hall_classic_FermiSurf(StaticCalculator):
+    r"""Classic Hall conductivity (:math:`S/m/T`), Fermi surface integral (static.py:407-424)"""
+
+    def __init__(self, constant_factor=factors.factor_hall_classic, **kwargs):
+        self.Formula = _lib.VEL_MASS_VEL
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+    def combine(self, arrays, cell_volume):
+        return _hall_classic_post(arrays[0])
+
+
+class Hall_classic_FermiSea(StaticCalculator):
+    r"""Classic Hall conductivity (:math:`S/m/T`), Fermi sea integral (static.py:427-445)"""
+
+    def __init__(self, constant_factor=factors.factor_hall_classic, **kwargs):
+        self.Formula = _lib.MASS_MASS
+        self.fder = 0
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+    def combine(self, arrays, cell_volume):
+        return _hall_classic_post(arrays[0].transpose(0, 4, 1, 2, 3))
+
+
+class NLDrude_FermiSurf(StaticCalculator):
+    r"""Drude conductivity (:math:`S^2/A`), Fermi surface integral (static.py:532-542)"""
+
+    def __init__(self, constant_factor=factors.factor_nldrude, **kwargs):
+        self.Formula = _lib.MASS_VEL
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+class NLDrude_Fermider2(StaticCalculator):
+    r"""Drude conductivity (:math:`S^2/A`), second derivative of the distribution function (static.py:545-555)"""
+
+    def __init__(self, constant_factor=factors.factor_nldrude / 2, **kwargs):
+        self.Formula = _lib.VEL_VEL_VEL
+        self.fder = 2
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+class AHC_Zeeman_spin(StaticCalculator):
+    r"""AHC conductivity Zeeman correction term spin part (:math:`S/m/T`), Fermi surface integral (static.py:605-615)"""
+
+    def __init__(self, constant_factor=factors.fac_spin_Z * factors.factor_ahc, **kwargs):
+        self.Formula = _lib.OMEGA_S
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+class OmegaOmega(StaticCalculator):
+    r"""static.py:618-623"""
+
+    def __init__(self, **kwargs):
+        self.Formula = _lib.OMEGA_OMEGA
+        self.fder = 1
+        super().__init__(**kwargs)
+
+
 _BY_NAME = {c.__name__: c for c in (DOS, CumDOS, Spin, AHC, Morb, BerryDipole_FermiSurf, GME_orb_FermiSurf,
                                     GME_spin_FermiSurf, Ohmic_FermiSurf, Ohmic_FermiSea, BerryDipole_FermiSea,
-                                    NLAHC_FermiSea, SHC)}
+                                    NLAHC_FermiSea, SHC, NLAHC_FermiSurf, GME_spin_FermiSea, Hall_classic_FermiSurf,
+                                    Hall_classic_FermiSea, NLDrude_FermiSurf, NLDrude_Fermider2, AHC_Zeeman_spin,
+                                    OmegaOmega)}
 
 
 def adapt(calc):
@@ -299,7 +392,7 @@ def adapt(calc):
               kwargs_formula=calc.kwargs_formula, hole_like=False, k_resolved=calc.k_resolved,
               select_bands=calc.select_bands, degen_thresh=calc.degen_thresh, degen_Kramers=calc.degen_Kramers,
               save_mode=calc.save_mode)
-    fixed = ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf", "BerryDipole_FermiSea")   # no constant_factor argument
+    fixed = ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf", "BerryDipole_FermiSea", "OmegaOmega")   # no constant_factor argument
     if name not in fixed:
         kw["constant_factor"] = calc.constant_factor  # hole_like sign already folded in by the reference
     new = _BY_NAME[name](**kw)

@@ -62,6 +62,7 @@ struct WbLayout {
     int off_SA[9], off_SHA[9], off_SR[9], off_SH[3], off_SHR[9];
     // comma-derivatives d_d A_b and d_d rotA_c (index 3 b + d), hermitian like A and rotA (data_K_R.py:84-87)
     int off_dA[9], off_dO[9];
+    int off_dS[9];   // d_d S_s, hermitian
 };
 
 // index of the symmetric pair (b, d) in off_W

@@ -110,6 +110,11 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
         for (int a = 0; a < 3; a++) atomic_cadd(&table[cellR * E + L.off_C[a] + i * nw + j], in.CC[idx * 3 + a]);
     if (in.SS && L.off_S[0] >= 0)
         for (int a = 0; a < 3; a++) add_herm(table, cellR, cellmR, E, L.off_S[a], i, j, nw, in.SS[idx * 3 + a]);
+    if (in.SS && L.off_dS[0] >= 0)
+        for (int a = 0; a < 3; a++) {
+            const cplx sv = in.SS[idx * 3 + a];
+            for (int d = 0; d < 3; d++) add_herm(table, cellR, cellmR, E, L.off_dS[3 * a + d], i, j, nw, cmake(-T[d] * sv.y, T[d] * sv.x));
+        }
     // spin-current matrices: not hermitised (data_K_R.py:84-87)
     if (in.SA && L.off_SA[0] >= 0)
         for (int a = 0; a < 9; a++) atomic_cadd(&table[cellR * E + L.off_SA[a] + i * nw + j], in.SA[idx * 9 + a]);

@@ -242,3 +242,147 @@ wb_deromega_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long n
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// FormulaProduct (formula/formula.py:121-149) of up to three factors whose nn blocks are formed per band group:
+//   kind 1  V    covariant('Ham', commader = 1)                     rank 1
+//   kind 2  M    InvMass = generalised derivative of V               rank 2  (elementary.py:28-34, formula.py:95-112)
+//   kind 3  Om   Omega                                              rank 1  (covariant.py:161-203)
+//   kind 4  S    Spin                                               rank 1  (covariant.py:331-335)
+//   kind 5  dS   DerSpin = generalised derivative of S               rank 2  (covariant.py:338-342)
+// trace over the group of F1 F2 (F3), cartesian indices appended in order.  Covers VelVelVel, MassVel, MassMass,
+// VelMassVel, OmegaS, OmegaOmega (covariant.py:823-858) and the single-factor DerSpin.
+struct WbProductSpec {
+    int nf;
+    int kind[3];
+    int iV, iW, iA, iO, iS, idS;   // matrix positions in the rotated record: d_a H [3] | d_b d_d H [6] | A [3] | rotA [3] | S [3] | d_d S_s [9]
+};
+__host__ __device__ inline int wb_product_kind_ncomp(int kind) { return (kind == 2 || kind == 5) ? 9 : 3; }
+__host__ __device__ inline size_t wb_product_scratch_elems(int nw) { return (size_t)56 * nw * nw; }
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_product_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall,
+                         WbWindow win, WbProductSpec P, int internal, int external, cplx* __restrict__ scratch,
+                         double* __restrict__ ev_label, double* __restrict__ ev_val) {
+    extern __shared__ __align__(16) double smem_f[];
+    const int n2 = nw * nw;
+    double* Es = smem_f;
+    double* label = Es + nw;
+    double* inv = label + nw;
+    short* g1 = (short*)(inv + n2);
+    short* g2 = g1 + nw;
+    cplx* const F0 = scratch + (size_t)blockIdx.x * wb_product_scratch_elems(nw);
+    int nc[3] = {1, 1, 1};
+    for (int f = 0; f < P.nf; f++) nc[f] = wb_product_kind_ncomp(P.kind[f]);
+    const int NC = nc[0] * nc[1] * nc[2];
+    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        __syncthreads();
+        wb_fsea_groups<NT>(Eall, ik, nw, win, Es, label, inv, g1, g2);
+        const cplx* X = xbar + (size_t)ik * nch * n2;
+        const cplx* V = X + (size_t)P.iV * n2;
+        const cplx* A = X + (size_t)P.iA * n2;
+        auto Dm = [&](int a, int p, int q) { return cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]); };
+        for (int x = threadIdx.x; x < nw; x += NT) ev_label[ik * nw + x] = label[x];
+        for (int ga = 0; ga < nw; ga++) {
+            if (label[ga] == CUDART_INF) continue;   // uniform
+            const int gb = g2[ga], g = gb - ga, gg = g * g;
+            auto in_G = [&](int q) { return q >= ga && q < gb; };
+            cplx* Fb[3];
+            Fb[0] = F0;
+            Fb[1] = Fb[0] + (size_t)gg * nc[0];
+            Fb[2] = Fb[1] + (size_t)gg * nc[1];
+            cplx* const Pm = Fb[2] + (size_t)gg * nc[2];   // F1 F2 of a three-factor product: [g][g][nc0 nc1]
+            // ---- factor blocks F_f[m - ga][n - ga][comp]
+            const int tot = gg * (nc[0] + (P.nf > 1 ? nc[1] : 0) + (P.nf > 2 ? nc[2] : 0));
+            for (int x = threadIdx.x; x < tot; x += NT) {
+                int f = 0, y = x;
+                while (y >= gg * nc[f]) { y -= gg * nc[f]; f++; }
+                const int comp = y % nc[f];
+                const int mn = y / nc[f], m = ga + mn / g, n = ga + mn % g;
+                const int kind = P.kind[f];
+                cplx val;
+                if (kind == 1) val = V[(size_t)comp * n2 + m * nw + n];
+                else if (kind == 4) val = X[(size_t)(P.iS + comp) * n2 + m * nw + n];
+                else if (kind == 2 || kind == 5) {
+                    // X^{b:d}_mn = X,d_mn - sum_{l notin G} D_ml^d X_ln^b + sum_l X_ml^b D_ln^d
+                    const int b = comp / 3, d = comp - 3 * b;
+                    const cplx* Xb = (kind == 2) ? V + (size_t)b * n2 : X + (size_t)(P.iS + b) * n2;
+                    val = (kind == 2) ? X[(size_t)(P.iW + wb_sym6(b, d)) * n2 + m * nw + n] : X[(size_t)(P.idS + comp) * n2 + m * nw + n];
+                    for (int l = 0; l < nw; l++) {
+                        if (in_G(l)) continue;
+                        const cplx z = cmul(Dm(d, m, l), Xb[l * nw + n]);
+                        val = cmake(val.x - z.x, val.y - z.y);
+                        cfma(val, Xb[m * nw + l], Dm(d, l, n));
+                    }
+                } else {
+                    // Omega_c[m, n] = S(m, n) + conj(S(n, m)),
+                    // S(M, L) = -i sum_l D_Ml^al D_lL^be + 1/2 O_ML - sum_l D_Ml^al A_lL^be + sum_l D_Ml^be A_lL^al - i sum_{m' in G} A_Mm'^al A_m'L^be
+                    const int al = WB_ALPHA(comp), be = WB_BETA(comp);
+                    val = cmake(0., 0.);
+#pragma unroll
+                    for (int side = 0; side < 2; side++) {
+                        const int M = side ? n : m, Lb = side ? m : n;
+                        cplx S = cmake(0., 0.);
+                        for (int l = 0; l < nw; l++) {
+                            if (in_G(l)) {
+                                if (external) {
+                                    const cplx z = cmul(A[(size_t)al * n2 + M * nw + l], A[(size_t)be * n2 + l * nw + Lb]);
+                                    S.x += z.y; S.y -= z.x;
+                                }
+                                continue;
+                            }
+                            const cplx DMa = Dm(al, M, l), DMb = Dm(be, M, l);
+                            if (internal) {
+                                const cplx z = cmul(DMa, Dm(be, l, Lb));
+                                S.x += z.y; S.y -= z.x;
+                            }
+                            if (external) {
+                                const cplx z = csub(cmul(DMb, A[(size_t)al * n2 + l * nw + Lb]), cmul(DMa, A[(size_t)be * n2 + l * nw + Lb]));
+                                S = cadd(S, z);
+                            }
+                        }
+                        if (external) {
+                            const cplx o = X[(size_t)(P.iO + comp) * n2 + M * nw + Lb];
+                            S.x += 0.5 * o.x; S.y += 0.5 * o.y;
+                        }
+                        val = side ? cmake(val.x + S.x, val.y - S.y) : S;
+                    }
+                }
+                Fb[f][y] = val;
+            }
+            __syncthreads();
+            if (P.nf == 3) {
+                const int n01 = nc[0] * nc[1];
+                for (int x = threadIdx.x; x < gg * n01; x += NT) {
+                    const int c01 = x % n01, mp = x / n01, m = mp / g, p = mp % g;
+                    const int c0 = c01 / nc[1], c1 = c01 - c0 * nc[1];
+                    cplx acc = cmake(0., 0.);
+                    for (int n = 0; n < g; n++) cfma(acc, Fb[0][(size_t)(m * g + n) * nc[0] + c0], Fb[1][(size_t)(n * g + p) * nc[1] + c1]);
+                    Pm[x] = acc;
+                }
+                __syncthreads();
+            }
+            // ---- trace
+            for (int comp = threadIdx.x; comp < NC; comp += NT) {
+                double tr = 0.;
+                if (P.nf == 1) {
+                    for (int m = 0; m < g; m++) tr += Fb[0][(size_t)(m * g + m) * nc[0] + comp].x;
+                } else {
+                    const int nlast = (P.nf == 2) ? nc[1] : nc[2];
+                    const int cl = comp % nlast, cf = comp / nlast;
+                    const cplx* L = (P.nf == 2) ? Fb[0] : Pm;
+                    const cplx* Rr = (P.nf == 2) ? Fb[1] : Fb[2];
+                    const int nfirst = NC / nlast;
+                    for (int m = 0; m < g; m++)
+                        for (int n = 0; n < g; n++) {
+                            const cplx a = L[(size_t)(m * g + n) * nfirst + cf], b = Rr[(size_t)(n * g + m) * nlast + cl];
+                            tr += a.x * b.x - a.y * b.y;
+                        }
+                }
+                ev_val[((size_t)ik * nw + ga) * NC + comp] = tr;
+            }
+            __syncthreads();
+        }
+    }
+}

@@ -266,17 +266,43 @@ static int formula_rank(int f) {
         case WBGPU_IDENTITY: return 0;
         case WBGPU_OMEGA: case WBGPU_MORB_HPM: case WBGPU_SPIN: return 1;
         case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: case WBGPU_VEL_VEL: case WBGPU_INV_MASS:
-        case WBGPU_DER_OMEGA: return 2;
-        case WBGPU_SHC_RYOO: case WBGPU_SHC_QIAO: case WBGPU_SHC_SIMPLE: return 3;   // SpinOmega
+        case WBGPU_DER_OMEGA: case WBGPU_DER_SPIN: case WBGPU_OMEGA_S: case WBGPU_OMEGA_OMEGA: return 2;
+        case WBGPU_SHC_RYOO: case WBGPU_SHC_QIAO: case WBGPU_SHC_SIMPLE:   // SpinOmega
+        case WBGPU_VEL_VEL_VEL: case WBGPU_MASS_VEL: return 3;
+        case WBGPU_MASS_MASS: case WBGPU_VEL_MASS_VEL: return 4;
     }
     return -1;
 }
 static int formula_ncomp(int f) {
-    int r = formula_rank(f);
-    return r == 0 ? 1 : r == 1 ? 3 : r == 2 ? 9 : 27;
+    int r = formula_rank(f), n = 1;
+    for (int i = 0; i < r; i++) n *= 3;
+    return n;
 }
 // formulae evaluated by a kernel of their own (wb_fsea.cuh): one event pass per spec
-static bool formula_solo(int f) { return f == WBGPU_SHC_RYOO || f == WBGPU_SHC_QIAO || f == WBGPU_SHC_SIMPLE || f == WBGPU_DER_OMEGA; }
+static bool formula_solo(int f) { return f >= WBGPU_SHC_RYOO && f < WBGPU_NFORMULA; }
+// factor kinds of the FormulaProduct formulae (wb_fsea.cuh: 1 V, 2 InvMass, 3 Omega, 4 Spin, 5 DerSpin)
+static bool formula_product(int f, WbProductSpec* P) {
+    int k[3] = {0, 0, 0}, n = 0;
+    switch (f) {
+        case WBGPU_DER_SPIN: n = 1; k[0] = 5; break;
+        case WBGPU_VEL_VEL_VEL: n = 3; k[0] = k[1] = k[2] = 1; break;
+        case WBGPU_MASS_VEL: n = 2; k[0] = 2; k[1] = 1; break;
+        case WBGPU_MASS_MASS: n = 2; k[0] = k[1] = 2; break;
+        case WBGPU_VEL_MASS_VEL: n = 3; k[0] = 1; k[1] = 2; k[2] = 1; break;
+        case WBGPU_OMEGA_S: n = 2; k[0] = 3; k[1] = 4; break;
+        case WBGPU_OMEGA_OMEGA: n = 2; k[0] = k[1] = 3; break;
+        default: return false;
+    }
+    if (P) { P->nf = n; for (int i = 0; i < 3; i++) P->kind[i] = k[i]; }
+    return true;
+}
+static bool product_has(int f, int kind) {
+    WbProductSpec P;
+    if (!formula_product(f, &P)) return false;
+    for (int i = 0; i < P.nf; i++)
+        if (P.kind[i] == kind) return true;
+    return false;
+}
 static int fder_extra(int fder) { return fder == 0 ? 0 : (fder <= 2 ? 1 : 2); }
 
 extern "C" int64_t wbgpu_spec_size(const wbgpu_scan_spec* s) {
@@ -315,10 +341,19 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
                    has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO) || has(WBGPU_VEL_VEL) || has(WBGPU_INV_MASS) || has(WBGPU_SHC_RYOO) ||
                    has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE) || has(WBGPU_DER_OMEGA);
     const bool shc = has(WBGPU_SHC_RYOO) || has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE);
+    bool prod_any = false, prod_mass = false, prod_omega = false, prod_spin = false;
+    for (int f = WBGPU_DER_SPIN; f < WBGPU_NFORMULA; f++)
+        if (has(f)) {
+            prod_any = true;
+            prod_mass |= product_has(f, 2);
+            prod_omega |= product_has(f, 3);
+            prod_spin |= product_has(f, 4) || product_has(f, 5);
+        }
+    need_dH = need_dH || prod_any;
     bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) || has(WBGPU_KUBO);
-    bool need_A = (berry || shc || has(WBGPU_DER_OMEGA)) && external_terms;
+    bool need_A = (berry || shc || has(WBGPU_DER_OMEGA) || prod_omega) && external_terms;
     bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS)) && external_terms;
-    bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN) || shc;
+    bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN) || shc || prod_spin;
     if (has(WBGPU_SHC_RYOO) && (!c->d_XR[WBGPU_SA] || !c->d_XR[WBGPU_SHA]))
         return set_err("wbgpu_plan: R-matrices 'SA','SHA' are not set (SHC_type='ryoo')");
     if (has(WBGPU_SHC_QIAO) && (!c->d_XR[WBGPU_SR] || !c->d_XR[WBGPU_SH] || !c->d_XR[WBGPU_SHR]))
@@ -365,12 +400,13 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     for (int a = 0; a < 3; a++) L.off_dH[a] = need_dH ? take(dH_herm) : -1;
     for (int a = 0; a < 3; a++) L.off_A[a] = need_A ? take(true) : -1;
     bool need_O = need_A && (has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
-                             has(WBGPU_DER_OMEGA));
+                             has(WBGPU_DER_OMEGA) || prod_omega);
     for (int a = 0; a < 3; a++) L.off_O[a] = need_O ? take(true) : -1;
     for (int a = 0; a < 3; a++) L.off_B[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_C[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_S[a] = need_S ? take(true) : -1;
-    for (int a = 0; a < 6; a++) L.off_W[a] = (has(WBGPU_INV_MASS) || has(WBGPU_DER_OMEGA)) ? take(dH_herm) : -1;
+    for (int a = 0; a < 6; a++) L.off_W[a] = (has(WBGPU_INV_MASS) || has(WBGPU_DER_OMEGA) || prod_mass) ? take(dH_herm) : -1;
+    for (int a = 0; a < 9; a++) L.off_dS[a] = has(WBGPU_DER_SPIN) ? take(true) : -1;
     for (int a = 0; a < 9; a++) L.off_dA[a] = (has(WBGPU_DER_OMEGA) && need_A) ? take(true) : -1;
     for (int a = 0; a < 9; a++) L.off_dO[a] = (has(WBGPU_DER_OMEGA) && need_A) ? take(true) : -1;
     for (int a = 0; a < 9; a++) L.off_SA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
@@ -414,7 +450,9 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     if (nw <= 32) per_k += 16.0 * (2 * nw * nw + 32) + 4.0 * (6 * nw + 12) + 32.0 * nw + 16;  // QL rotation stream etc.
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    long kmax = (long)(0.45 * (double)free_b / per_k);
+    // at most 45 % of the free memory and 48 GB: the sub-batched buffers of the scan calls (rotated matrices, Kubo
+    // entries, eigensolver work space, formula scratch: <= 3 .. 6 GB each) and other contexts need the rest
+    long kmax = (long)(std::min(0.45 * (double)free_b, 48.0e9) / per_k);
     long want = max_kpoints_per_launch > 0 ? (long)max_kpoints_per_launch : 262144;
     kmax = std::min(kmax, want);
     long nb = std::max(1L, kmax / c->nk_block);
@@ -724,7 +762,7 @@ static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec)
             G.win = w;
             G.ev.mask = 0;
             G.ev.NC = 0;
-            for (int f = 0; f < 16; f++) G.ev.off[f] = 0;
+            for (int f = 0; f < 24; f++) G.ev.off[f] = 0;
             G.solo = formula_solo(s.formula);
             G.ev.internal_terms = s.internal_terms;
             G.ev.external_terms = s.external_terms;
@@ -893,6 +931,40 @@ static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
             wb_deromega_events_kernel<NT><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
                 (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, C, G.ev.internal_terms, ext ? 1 : 0, (cplx*)c->d_mx,
                 c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * 9);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
+        return 0;
+    }
+    WbProductSpec P;
+    if (formula_product(formula, &P)) {
+        const bool hasM = product_has(formula, 2), hasO = product_has(formula, 3), hasS = product_has(formula, 4) || product_has(formula, 5);
+        if (L.off_dH[0] < 0 || (hasM && L.off_W[0] < 0) || (hasO && ext && (L.off_A[0] < 0 || L.off_O[0] < 0)) ||
+            (hasS && L.off_S[0] < 0) || (formula == WBGPU_DER_SPIN && L.off_dS[0] < 0))
+            return set_err("scan: the plan does not hold the channels of formula %d", formula);
+        P.iW = P.iA = P.iO = P.iS = P.idS = 0;
+        P.iV = addn(L.off_dH, 3, L.dH_herm);
+        if (hasM) P.iW = addn(L.off_W, 6, L.dH_herm);
+        if (hasO && ext) { P.iA = addn(L.off_A, 3, 1); P.iO = addn(L.off_O, 3, 1); }
+        if (hasS) P.iS = addn(L.off_S, 3, 1);
+        if (formula == WBGPU_DER_SPIN) P.idS = addn(L.off_dS, 9, 1);
+        const int NC = formula_ncomp(formula);
+        const long chunk = xbar_chunk(c, ch.n, nk);
+        if (ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * n2)) return 1;
+        const size_t per_cta = sizeof(cplx) * wb_product_scratch_elems(nw);
+        const long nblk_max = std::max(32L, std::min((long)sms * 4, (long)(1.5e9 / (double)per_cta)));
+        if (ensure(&c->d_mx, &c->mx_cap, per_cta * (size_t)nblk_max)) return 1;
+        const size_t smem = wb_fsea_smem_bytes(nw, 0);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(wb_product_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (long k0 = 0; k0 < nk; k0 += chunk) {
+            const long n = std::min(chunk, nk - k0);
+            if (rotate_gemm(c, ch, k0, n)) return 1;
+            WbWindow wloc = G.win;
+            if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
+            wb_product_events_kernel<NT><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, P, G.ev.internal_terms, ext ? 1 : 0, (cplx*)c->d_mx,
+                c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * NC);
             c->launches++;
             CK(cudaGetLastError());
         }
@@ -1218,7 +1290,7 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
     LH.nw = nw; LH.ntri = nw * (nw + 1) / 2; LH.E = LH.ntri; LH.off_H = 0; LH.dH_herm = 0;
     for (int a = 0; a < 3; a++) LH.off_dH[a] = LH.off_A[a] = LH.off_O[a] = LH.off_B[a] = LH.off_C[a] = LH.off_S[a] = -1;
     for (int a = 0; a < 6; a++) LH.off_W[a] = -1;
-    for (int a = 0; a < 9; a++) LH.off_SA[a] = LH.off_SHA[a] = LH.off_SR[a] = LH.off_SHR[a] = LH.off_dA[a] = LH.off_dO[a] = -1;
+    for (int a = 0; a < 9; a++) LH.off_SA[a] = LH.off_SHA[a] = LH.off_SR[a] = LH.off_SHR[a] = LH.off_dA[a] = LH.off_dO[a] = LH.off_dS[a] = -1;
     for (int a = 0; a < 3; a++) LH.off_SH[a] = -1;
     const size_t ncell = (size_t)c->nbox.x * c->nbox.y * c->nbox.z;
     if (!c->d_tableH) {
@@ -1329,7 +1401,7 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
         const wbgpu_scan_spec& s = specs[i];
         const int ncomp = formula_ncomp(s.formula);
         const double scale = s.factor / (c->cell_volume * (double)c->nk_block);
-        wb_tetra_finalize_kernel<<<1, 32, 0, c->stream>>>(c->d_hist + hoff[i], s.nEF, ncomp, scale, c->d_out + ooff);
+        wb_tetra_finalize_kernel<<<(unsigned)((ncomp + 31) / 32), 32, 0, c->stream>>>(c->d_hist + hoff[i], s.nEF, ncomp, scale, c->d_out + ooff);
         c->launches++;
         ooff += (size_t)s.nEF * ncomp;
     }

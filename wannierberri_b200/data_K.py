@@ -6,13 +6,20 @@ import numpy as np
 from .engine import Engine
 
 _ENGINES = {}
+_MAX_ENGINES = 3   # every engine owns device work space (wbgpu_plan: up to 48 GB): the least recently used one is closed
 
 
 def engine_for(system, device=0):
     key = (id(system), device)
-    if key not in _ENGINES:
-        _ENGINES[key] = Engine(system, device=device)
-    return _ENGINES[key]
+    eng = _ENGINES.pop(key, None)
+    if eng is None or eng.system is not system:
+        if eng is not None:
+            eng.close()
+        while len(_ENGINES) >= _MAX_ENGINES:
+            _ENGINES.pop(next(iter(_ENGINES))).close()
+        eng = Engine(system, device=device)
+    _ENGINES[key] = eng   # most recently used last
+    return eng
 
 
 class Data_K_R:

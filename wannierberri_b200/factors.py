@@ -14,3 +14,6 @@ factor_shc = -factor_ahc
 TAU_UNIT = 1E-15
 factor_ohmic = (elementary_charge ** 2 / hbar / angstrom * TAU_UNIT * elementary_charge / hbar)
 factor_nlahc = elementary_charge ** 3 / hbar ** 2 * TAU_UNIT
+fac_spin_Z = hbar / (2 * electron_mass)
+factor_hall_classic = -(elementary_charge ** 3 / hbar ** 2 * angstrom * TAU_UNIT ** 2 * elementary_charge ** 2 / hbar ** 2)
+factor_nldrude = -(elementary_charge ** 3 / hbar ** 2 * TAU_UNIT ** 2 * elementary_charge / hbar)
