@@ -323,3 +323,25 @@ def test_fermi_sea_formulae_random_system():
     for k in FSEA_CASES:
         assert res[k].shape == g["rnd_" + k].shape, k
         assert relerr(res[k], g["rnd_" + k]) < RTOL, k
+
+
+SHIFT_CASES = dict(
+    shift=("ShiftCurrent", dict(sc_eta=0.1, smr_type="Lorentzian")), shift_gauss=("ShiftCurrent", dict(sc_eta=0.04, smr_type="Gaussian")),
+    shift_int=("ShiftCurrent", dict(sc_eta=0.1, smr_type="Lorentzian", external_terms=False)),
+    shift_thresh=("ShiftCurrent", dict(sc_eta=0.1, smr_type="Lorentzian", degen_thresh=0.3)),
+    injection=("InjectionCurrent", dict(smr_type="Lorentzian")), injection_gauss=("InjectionCurrent", dict(smr_type="Gaussian")),
+    injection_int=("InjectionCurrent", dict(smr_type="Lorentzian", external_terms=False)),
+    injection_thresh=("InjectionCurrent", dict(smr_type="Lorentzian", degen_thresh=0.3)),
+)
+
+
+def test_shift_and_injection_current_random_system():
+    """Kubo shift current and injection current (calculators/dynamic.py:244-365) on the reference's `random` system against
+    the live reference run of tests/golden/make_golden_shift.py."""
+    g = np.load(os.path.join(GOLDEN, "golden_random_shift.npz"))
+    rnd = orc.OracleSystem.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    calcs = {k: (name, g["Efermi"], dict(omega=g["omega"], smr_fixed_width=0.20, **kw)) for k, (name, kw) in SHIFT_CASES.items()}
+    res = orc.run(rnd, [2, 2, 2], [3, 3, 3], calcs)
+    for k in SHIFT_CASES:
+        assert res[k].shape == g[k].shape and res[k].dtype == g[k].dtype, k
+        assert relerr(res[k], g[k]) < RTOL, k
