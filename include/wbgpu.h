@@ -70,7 +70,8 @@ enum {
     WBGPU_VEL_MASS_VEL = 18,  /* VelMassVel rank 4 (Hall_classic_FermiSurf) */
     WBGPU_OMEGA_S = 19,       /* OmegaS     rank 2 (AHC_Zeeman_spin)        */
     WBGPU_OMEGA_OMEGA = 20,   /* OmegaOmega rank 2                          */
-    WBGPU_NFORMULA = 21
+    WBGPU_SHIFT_CURRENT = 21, /* plan flag only: channels of the Kubo shift current (d_a H, d_b d_d H, A, d_d A_b) */
+    WBGPU_NFORMULA = 22
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */
@@ -156,7 +157,9 @@ int wbgpu_static_scan_tetra(wbgpu_ctx* ctx, int nblocks, const double* dK, const
 /* One (Efermi x omega) scan = one DynamicCalculator.__call__ (calculators/dynamic.py:26-114) at kBT = 0. */
 enum { WBGPU_KUBO_OPTCOND = 0,  /* OpticalConductivity dynamic.py:184-196: complex128 data[nEF][nomega][3][3]    */
        WBGPU_KUBO_JDOS = 1,     /* JDOS                dynamic.py:146-162: float64    data[nEF][nomega]          */
-       WBGPU_KUBO_SHC = 2 };    /* SHC                 dynamic.py:204-237: complex128 data[nEF][nomega][3][3][3] */
+       WBGPU_KUBO_SHC = 2,      /* SHC                 dynamic.py:204-237: complex128 data[nEF][nomega][3][3][3] */
+       WBGPU_KUBO_SHIFT = 3,    /* ShiftCurrent        dynamic.py:244-322: float64    data[nEF][nomega][3][3][3] (spec.sc_eta) */
+       WBGPU_KUBO_INJECTION = 4 /* InjectionCurrent    dynamic.py:330-365: complex128 data[nEF][nomega][3][3][3] */ };
 typedef struct wbgpu_kubo_spec {
     int32_t kind;            /* WBGPU_KUBO_*                                   */
     int32_t nEF, nomega;
@@ -168,6 +171,7 @@ typedef struct wbgpu_kubo_spec {
     double smr_fixed_width;
     double degen_thresh;
     double factor;           /* constant_factor                                */
+    double sc_eta;           /* ShiftCurrent only: broadening of the energy denominators of the generalised derivative */
 } wbgpu_kubo_spec;
 /* number of float64 values the scan writes (complex counted as 2) */
 int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* spec);

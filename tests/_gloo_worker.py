@@ -40,7 +40,8 @@ class OracleEngine:
         return [np.array([self.scan([d], [1.], [s])[0] for d in dK]).reshape((len(dK),) + s.shape) for s in specs]
 
     def kubo_scan(self, dK, weight, spec, Efermi, omega):
-        kind = {_lib.KUBO_OPTCOND: "opt_conductivity", _lib.KUBO_JDOS: "jdos", _lib.KUBO_SHC: "shc"}[int(spec.kind)]
+        kind = {_lib.KUBO_OPTCOND: "opt_conductivity", _lib.KUBO_JDOS: "jdos", _lib.KUBO_SHC: "shc", _lib.KUBO_SHIFT: "shift_current",
+                _lib.KUBO_INJECTION: "injection_current"}[int(spec.kind)]
         shc_type = {v: k for k, v in _lib.SHC_TYPES.items()}.get(int(spec.shc_type), "ryoo")
         out = 0
         for d, w in zip(dK, weight):
@@ -49,7 +50,7 @@ class OracleEngine:
                                           smr_type="Lorentzian" if spec.smr_type == 0 else "Gaussian",
                                           degen_thresh=spec.degen_thresh, degen_Kramers=bool(spec.degen_Kramers),
                                           external_terms=bool(spec.external_terms), constant_factor=spec.factor,
-                                          SHC_type=shc_type)
+                                          SHC_type=shc_type, sc_eta=spec.sc_eta)
         return out
 
 

@@ -422,6 +422,50 @@ def test_shc_errors(wb, fe):
         wb.calculators.dynamic.SHC(Efermi=[17.], omega=[0., 1.])(wb.Data_K_R(fe, dK=[0, 0, 0], grid=grid))
 
 
+# ---------------------------------------------------------------------------------------- Kubo shift / injection current
+SHIFT_CASES = dict(
+    shift=("ShiftCurrent", dict(sc_eta=0.1, smr_type="Lorentzian")), shift_gauss=("ShiftCurrent", dict(sc_eta=0.04, smr_type="Gaussian")),
+    shift_int=("ShiftCurrent", dict(sc_eta=0.1, smr_type="Lorentzian", kwargs_formula=dict(external_terms=False))),
+    shift_thresh=("ShiftCurrent", dict(sc_eta=0.1, smr_type="Lorentzian", degen_thresh=0.3)),
+    injection=("InjectionCurrent", dict(smr_type="Lorentzian")), injection_gauss=("InjectionCurrent", dict(smr_type="Gaussian")),
+    injection_int=("InjectionCurrent", dict(smr_type="Lorentzian", kwargs_formula=dict(external_terms=False))),
+    injection_thresh=("InjectionCurrent", dict(smr_type="Lorentzian", degen_thresh=0.3)),
+)
+
+
+def test_shift_and_injection_current_random_system(wb):
+    """Kubo shift current and injection current (calculators/dynamic.py:244-365) on the reference's `random` system through
+    run(), against the live reference run of tests/golden/make_golden_shift.py."""
+    g = np.load(os.path.join(GOLDEN, "golden_random_shift.npz"))
+    rnd = wb.System_R.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    dyn = wb.calculators.dynamic
+    calcs = {k: getattr(dyn, name)(Efermi=g["Efermi"], omega=g["omega"], smr_fixed_width=0.20, **kw)
+             for k, (name, kw) in SHIFT_CASES.items()}
+    res = wb.run(rnd, wb.Grid(rnd, NK=g["NK"], NKFFT=g["NKFFT"]), calcs)
+    for k in SHIFT_CASES:
+        got = res.results[k].data
+        assert got.shape == g[k].shape and got.dtype == g[k].dtype, k
+        assert relerr(got, g[k]) < RTOL, k
+
+
+@pytest.mark.parametrize("nw,nom", [(14, 45), (33, 5)])
+def test_shift_and_injection_current_synthetic(wb, orc, nw, nom):
+    """the same on a synthetic model with the R <-> -R symmetry (hermitian-packed channels), more bands than a warp and
+    more frequencies than one omega tile, one K-block, against the oracle."""
+    sysg = wb.synthetic_system(nw, rmax=1, seed=500 + nw)
+    syso = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
+                            {k: sysg.get_R_mat(k) for k in ("Ham", "AA")})
+    NKFFT, dK = [2, 2, 2], [0.05, 0.11, 0.02]
+    Ef, om = np.linspace(-1., 1., 12), np.linspace(0., 5., nom)
+    data = wb.Data_K_R(sysg, dK=dK, grid=wb.Grid(sysg, NKdiv=[1, 1, 1], NKFFT=NKFFT))
+    odata = orc.OracleDataK(syso, dK, NKFFT)
+    kw = dict(smr_fixed_width=0.1, smr_type="Lorentzian")
+    got = wb.calculators.dynamic.ShiftCurrent(Efermi=Ef, omega=om, sc_eta=0.05, **kw)(data).data
+    assert relerr(got, orc.ShiftCurrent(odata, Ef, omega=om, sc_eta=0.05, **kw)) < RTOL
+    got = wb.calculators.dynamic.InjectionCurrent(Efermi=Ef, omega=om, **kw)(data).data
+    assert relerr(got, orc.InjectionCurrent(odata, Ef, omega=om, **kw)) < RTOL
+
+
 # ---------------------------------------------------------------------------------------- tetrahedron method
 TETRA_CASES = dict(
     ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}), spin=("Spin", {}),

@@ -10,9 +10,9 @@ LIB_PATH = os.path.join(_HERE, "libwbgpu.so")
 
 # enums of include/wbgpu.h
 (IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN, KUBO, VEL_VEL, INV_MASS, SHC_RYOO, SHC_QIAO,
- SHC_SIMPLE, DER_OMEGA, DER_SPIN, VEL_VEL_VEL, MASS_VEL, MASS_MASS, VEL_MASS_VEL, OMEGA_S, OMEGA_OMEGA) = range(21)
+ SHC_SIMPLE, DER_OMEGA, DER_SPIN, VEL_VEL_VEL, MASS_VEL, MASS_MASS, VEL_MASS_VEL, OMEGA_S, OMEGA_OMEGA, SHIFT_CURRENT) = range(22)
 SHC_TYPES = {"ryoo": SHC_RYOO, "qiao": SHC_QIAO, "simple": SHC_SIMPLE}
-KUBO_OPTCOND, KUBO_JDOS, KUBO_SHC = 0, 1, 2
+KUBO_OPTCOND, KUBO_JDOS, KUBO_SHC, KUBO_SHIFT, KUBO_INJECTION = 0, 1, 2, 3, 4
 FORMULA_RANK = {IDENTITY: 0, OMEGA: 1, MORB_HPM: 1, SPIN: 1, VEL_OMEGA: 2, VEL_HPLUS: 2, VEL_SPIN: 2, VEL_VEL: 2,
                 INV_MASS: 2, DER_OMEGA: 2, SHC_RYOO: 3, SHC_QIAO: 3, SHC_SIMPLE: 3, DER_SPIN: 2, VEL_VEL_VEL: 3, MASS_VEL: 3,
                 MASS_MASS: 4, VEL_MASS_VEL: 4, OMEGA_S: 2, OMEGA_OMEGA: 2}
@@ -40,16 +40,22 @@ class KuboSpec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nEF", C.c_int32), ("nomega", C.c_int32), ("smr_type", C.c_int32),
                 ("degen_Kramers", C.c_int32), ("external_terms", C.c_int32), ("shc_type", C.c_int32),
                 ("reserved", C.c_int32),
-                ("smr_fixed_width", C.c_double), ("degen_thresh", C.c_double), ("factor", C.c_double)]
+                ("smr_fixed_width", C.c_double), ("degen_thresh", C.c_double), ("factor", C.c_double),
+                ("sc_eta", C.c_double)]
 
     @property
     def shape(self):
-        return (int(self.nEF), int(self.nomega)) + {KUBO_OPTCOND: (3, 3), KUBO_SHC: (3, 3, 3)}.get(int(self.kind), ())
+        return (int(self.nEF), int(self.nomega)) + {KUBO_OPTCOND: (3, 3), KUBO_SHC: (3, 3, 3), KUBO_SHIFT: (3, 3, 3),
+                                                     KUBO_INJECTION: (3, 3, 3)}.get(int(self.kind), ())
+
+    @property
+    def is_complex(self):
+        return int(self.kind) in (KUBO_OPTCOND, KUBO_SHC, KUBO_INJECTION)
 
     @property
     def formula_flag(self):
         """the plan flag (wbgpu_plan formula_mask bit) this scan needs"""
-        return int(self.shc_type) if int(self.kind) == KUBO_SHC else KUBO
+        return {KUBO_SHC: int(self.shc_type), KUBO_SHIFT: SHIFT_CURRENT}.get(int(self.kind), KUBO)
 
 
 _lib = None

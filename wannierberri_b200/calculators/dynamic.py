@@ -18,6 +18,7 @@ class DynamicCalculator(Calculator):
     dtype = complex
     extra_kwargs_formula = ()
     shc_type = 0
+    sc_eta = 0.
 
     def __init__(self, Efermi=None, omega=None, kBT=0, smr_fixed_width=0.1, smr_type='Lorentzian',
                  kwargs_formula=None, dtype=None, **kwargs):
@@ -49,7 +50,8 @@ class DynamicCalculator(Calculator):
                         smr_type=0 if self.smr_type == "Lorentzian" else 1,
                         degen_Kramers=int(bool(self.degen_Kramers)), external_terms=int(self.external_terms),
                         shc_type=int(self.shc_type), smr_fixed_width=float(self.smr_fixed_width),
-                        degen_thresh=float(self.degen_thresh), factor=float(self.constant_factor))
+                        degen_thresh=float(self.degen_thresh), factor=float(self.constant_factor),
+                        sc_eta=float(self.sc_eta))
 
     def result(self, data):
         return EnergyResult([self.Efermi, self.omega], data, transformTR=self.transformTR,
@@ -110,7 +112,32 @@ class SHC(DynamicCalculator):
         return super().result(data)
 
 
-_BY_NAME = {c.__name__: c for c in (JDOS, OpticalConductivity, SHC)}
+class ShiftCurrent(DynamicCalculator):
+    r"""Shift current :math:`\sigma^{abc}(\omega)` (dynamic.py:244-322), data `[Efermi, omega, a, b, c]` real; `sc_eta`
+    broadens the energy denominators of the generalised derivative of the Berry connection."""
+    kind = _lib.KUBO_SHIFT
+    dtype = float
+    transformTR, transformInv = "ident", "odd"
+    extra_kwargs_formula = ("sc_eta",)
+
+    def __init__(self, sc_eta, **kwargs):
+        super().__init__(**kwargs)
+        self.sc_eta = float(self.kwargs_formula.get("sc_eta", sc_eta))
+        self.kwargs_formula.update(dict(sc_eta=self.sc_eta))
+        self.constant_factor = factors.factor_shift_current
+
+
+class InjectionCurrent(DynamicCalculator):
+    r"""Injection current (dynamic.py:330-365; Eq. (10) of Lihm and Park, PRB 105, 045201), data `[Efermi, omega, a, b, c]`"""
+    kind = _lib.KUBO_INJECTION
+    transformTR, transformInv = "odd_trans_021", "odd"
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.constant_factor = factors.factor_injection_current
+
+
+_BY_NAME = {c.__name__: c for c in (JDOS, OpticalConductivity, SHC, ShiftCurrent, InjectionCurrent)}
 
 
 def adapt(calc):
@@ -120,7 +147,8 @@ def adapt(calc):
     name = type(calc).__name__
     if name not in _BY_NAME:
         raise ValueError(f"calculator {name} is not available on the GPU path")
-    new = _BY_NAME[name](Efermi=np.array(calc.Efermi), omega=np.array(calc.omega), kBT=calc.kBT,
+    extra = dict(sc_eta=calc.kwargs_formula["sc_eta"]) if name == "ShiftCurrent" else {}
+    new = _BY_NAME[name](Efermi=np.array(calc.Efermi), omega=np.array(calc.omega), kBT=calc.kBT, **extra,
                          smr_fixed_width=calc.smr_fixed_width, smr_type=calc.smr_type,
                          kwargs_formula=calc.kwargs_formula, degen_thresh=calc.degen_thresh,
                          degen_Kramers=calc.degen_Kramers, save_mode=calc.save_mode)

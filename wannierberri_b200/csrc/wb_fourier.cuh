@@ -99,7 +99,8 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
                 const cplx rot = cmake(-r0.y, r0.x);
                 for (int d = 0; d < 3; d++) {
                     add_herm(table, cellR, cellmR, E, L.off_dA[3 * b + d], i, j, nw, cmake(-T[d] * A[b].y, T[d] * A[b].x));
-                    add_herm(table, cellR, cellmR, E, L.off_dO[3 * b + d], i, j, nw, cmake(-T[d] * rot.y, T[d] * rot.x));
+                    if (L.off_dO[0] >= 0)
+                        add_herm(table, cellR, cellmR, E, L.off_dO[3 * b + d], i, j, nw, cmake(-T[d] * rot.y, T[d] * rot.x));
                 }
             }
         }

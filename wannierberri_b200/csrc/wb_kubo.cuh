@@ -34,7 +34,10 @@ constexpr int WB_SHC_ENT = 56;     // spin Hall: Delta | owner bin | M_(lo,hi)[2
 constexpr int WB_KUBO_CHUNK = 32;  // entries staged per step of the accumulation kernel
 constexpr int WB_KUBO_WT = 32;     // omega values per CTA of the accumulation kernel
 
-__host__ __device__ constexpr int wb_kubo_ent(int kind) { return kind == 2 ? WB_SHC_ENT : WB_KUBO_ENT; }
+// kinds (WbKuboParams::kind = WBGPU_KUBO_*): 0 optical conductivity, 1 JDOS, 2 spin Hall, 3 shift current, 4 injection
+// current; the rank-3 kinds (>= 2) share the entry size and the thread layout of the accumulation kernel, whose template
+// argument is 0, 1, 2 (real matrix elements: spin Hall, shift current) or 3 (complex matrix elements: injection current)
+__host__ __device__ constexpr int wb_kubo_ent(int kind) { return kind >= 2 ? WB_SHC_ENT : WB_KUBO_ENT; }
 
 // spin Hall conductivity: which rotated matrices (in units of nw x nw matrices of the rotated record) feed the
 // spin-velocity matrix of formula/covariant.py:689-756
@@ -45,7 +48,8 @@ struct WbShcChans {
 };
 
 struct WbKuboParams {
-    int kind;        // 0 = optical conductivity, 1 = JDOS, 2 = spin Hall conductivity
+    int kind;        // 0 = optical conductivity, 1 = JDOS, 2 = spin Hall conductivity, 3 = shift current, 4 = injection current
+    double sc_eta;   // shift current: broadening of the denominators of the generalised derivative
     int smr_type;    // 0 = Lorentzian, 1 = Gaussian
     int external;    // external terms (Abar) in A_H
     int nEF, nomega;
@@ -144,7 +148,7 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
         const cplx* Vb = xbar + (size_t)ik * nch * n2;
         const cplx* Ab = Vb + 3 * n2;
         const cplx* Jb = Jspin + (size_t)ik * 9 * n2;
-        const int per = (P.kind == 0) ? 9 : (P.kind == 2) ? 27 : 1;
+        const int per = (P.kind == 0) ? 9 : (P.kind >= 2) ? 27 : 1;
         for (int x = threadIdx.x; x < nvalid * per; x += NT) {
             const int slot = x / per, ab = x - slot * per;
             const ushort2 pr = plist[slot];
@@ -185,6 +189,51 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
                     }
                 e[2 + ab] = sw * mlh;
                 e[29 + ab] = sw * mhl;
+            } else if (P.kind == 3) {
+                // ShiftCurrentFormula (dynamic.py:298-303): Imn[n, m, a, b, c] = -Im( Agen_nm^{c a} A_mn^b ) + (b <-> c); the
+                // frequency factor is even in the pair, the Fermi factor odd: entry = M_(hi,lo) - M_(lo,hi)
+                const int a = ab / 9, b = (ab / 3) % 3, cc = ab % 3;
+                double acc = 0.;
+                for (int m = gs[i]; m < ge[i]; m++)
+                    for (int n = gs[j]; n < ge[j]; n++) {
+                        const double inv = wb_deinv(Es[m], Es[n]);
+#pragma unroll
+                        for (int t = 0; t < 2; t++) {
+                            const int bb = t ? cc : b, c2 = t ? b : cc;   // term (b, c) and its (b <-> c) partner
+                            const cplx Vmn = Vb[bb * n2 + m * nw + n], Vnm = Vb[bb * n2 + n * nw + m];
+                            cplx Amn = cmake(inv * Vmn.y, -inv * Vmn.x), Anm = cmake(-inv * Vnm.y, inv * Vnm.x);
+                            if (P.external) {
+                                Amn = cadd(Amn, Ab[bb * n2 + m * nw + n]);
+                                Anm = cadd(Anm, Ab[bb * n2 + n * nw + m]);
+                            }
+                            const cplx Gmn = Jb[(size_t)(3 * c2 + a) * n2 + m * nw + n], Gnm = Jb[(size_t)(3 * c2 + a) * n2 + n * nw + m];
+                            // (lo, hi): n' = m, m' = n: -Im(G_mn A_nm);  (hi, lo): -Im(G_nm A_mn)
+                            acc += (Gmn.x * Anm.y + Gmn.y * Anm.x) - (Gnm.x * Amn.y + Gnm.y * Amn.x);
+                        }
+                    }
+                e[2 + ab] = sw * acc;
+                e[29 + ab] = 0.;
+            } else if (P.kind == 4) {
+                // InjectionCurrentFormula (dynamic.py:336-343): Imn[m, n, a, b, c] = (v_m - v_n)^a A_mn^b A_nm^c, pair (lo, hi);
+                // the reversed pair is -Imn[m, n, a, c, b]
+                const int a = ab / 9, b = (ab / 3) % 3, cc = ab % 3;
+                cplx acc = cmake(0., 0.);
+                for (int m = gs[i]; m < ge[i]; m++)
+                    for (int n = gs[j]; n < ge[j]; n++) {
+                        const double inv = wb_deinv(Es[m], Es[n]);
+                        const cplx Vmn = Vb[b * n2 + m * nw + n], Vnm = Vb[cc * n2 + n * nw + m];
+                        cplx Amn = cmake(inv * Vmn.y, -inv * Vmn.x), Anm = cmake(-inv * Vnm.y, inv * Vnm.x);
+                        if (P.external) {
+                            Amn = cadd(Amn, Ab[b * n2 + m * nw + n]);
+                            Anm = cadd(Anm, Ab[cc * n2 + n * nw + m]);
+                        }
+                        const double dv = Vb[a * n2 + m * nw + m].x - Vb[a * n2 + n * nw + n].x;
+                        const cplx z = cmul(Amn, Anm);
+                        acc.x += dv * z.x;
+                        acc.y += dv * z.y;
+                    }
+                e[2 + 2 * ab] = sw * acc.x;
+                e[3 + 2 * ab] = sw * acc.y;
             } else {
                 const int a = ab / 3, b = ab - 3 * a;
                 // M[ab] and M[ba] (slot ab stores their sum for a < b, their difference for a > b, M[aa] on the diagonal)
@@ -297,6 +346,74 @@ wb_shc_spinvel_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
     }
 }
 
+// Generalised derivative of the Berry connection of the shift current (ShiftCurrentFormula, dynamic.py:247-296):
+//   Agen[k][3 c + a][n][m] = i ( W_nm^{ca} + sum_HD + DV_bit ) / (E_m - E_n)  [ + A,a_nm^c + AD_bit - i AA_bit + sum_AD ]
+// with P_lm^a = -V_lm^a (E_l - E_m) / ((E_l - E_m)^2 + sc_eta^2),
+//   sum_XD = sum_l ( X_nl^c P_lm^a - P_nl^a X_lm^c ) - X_nn^c P_nm^a + P_nm^a X_mm^c        (X = V, A)
+//   XD_bit = D_nm^c (X_nn^a - X_mm^a) + D_nm^a (X_nn^c - X_mm^c)                            (X = V, A)
+//   AA_bit = (A_nn^a - A_mm^a) A_nm^c
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_shift_agen_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall, int iW, int iA,
+                     int idA, double sc_eta, cplx* __restrict__ Gout) {
+    extern __shared__ __align__(16) double smem_sv[];
+    double* Es = smem_sv;
+    const int n2 = nw * nw;
+    const double eta2 = sc_eta * sc_eta;
+    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        __syncthreads();
+        for (int x = threadIdx.x; x < nw; x += NT) Es[x] = Eall[ik * nw + x];
+        __syncthreads();
+        const cplx* X = xbar + (size_t)ik * nch * n2;
+        const cplx* V = X;   // d_a H is the first triple of the record
+        cplx* Gk = Gout + (size_t)ik * 9 * n2;
+        auto Pv = [&](int a, int l, int q) {
+            const double d = Es[l] - Es[q];
+            return cscale(-d / (d * d + eta2), V[(size_t)a * n2 + l * nw + q]);
+        };
+        for (int x = threadIdx.x; x < 9 * n2; x += NT) {
+            const int ca = x / n2, nm = x - ca * n2, n = nm / nw, m = nm - n * nw;
+            const int c = ca / 3, a = ca - 3 * c;
+            const cplx Pnm = Pv(a, n, m);
+            const double inm = wb_deinv(Es[n], Es[m]);
+            const cplx Dc = cscale(-inm, V[(size_t)c * n2 + nm]), Da = cscale(-inm, V[(size_t)a * n2 + nm]);
+            cplx sumV = cmake(0., 0.), sumA = cmake(0., 0.);
+            for (int l = 0; l < nw; l++) {
+                const cplx Plm = Pv(a, l, m), Pnl = Pv(a, n, l);
+                cfma(sumV, V[(size_t)c * n2 + n * nw + l], Plm);
+                const cplx z = cmul(Pnl, V[(size_t)c * n2 + l * nw + m]);
+                sumV = cmake(sumV.x - z.x, sumV.y - z.y);
+                if (iA >= 0) {
+                    const cplx* Ac = X + (size_t)(iA + c) * n2;
+                    cfma(sumA, Ac[n * nw + l], Plm);
+                    const cplx z2 = cmul(Pnl, Ac[l * nw + m]);
+                    sumA = cmake(sumA.x - z2.x, sumA.y - z2.y);
+                }
+            }
+            const cplx Vnn_c = V[(size_t)c * n2 + n * nw + n], Vmm_c = V[(size_t)c * n2 + m * nw + m];
+            const cplx Vnn_a = V[(size_t)a * n2 + n * nw + n], Vmm_a = V[(size_t)a * n2 + m * nw + m];
+            cplx t = X[(size_t)(iW + wb_sym6(c, a)) * n2 + nm];
+            t = cadd(t, sumV);
+            t = cadd(t, cmul(Pnm, csub(Vmm_c, Vnn_c)));
+            t = cadd(t, cmul(Dc, csub(Vnn_a, Vmm_a)));
+            t = cadd(t, cmul(Da, csub(Vnn_c, Vmm_c)));
+            const double imn = wb_deinv(Es[m], Es[n]);
+            cplx g = cmake(-imn * t.y, imn * t.x);   // i t / (E_m - E_n)
+            if (iA >= 0) {
+                const cplx* Ac = X + (size_t)(iA + c) * n2;
+                const cplx* Aa = X + (size_t)(iA + a) * n2;
+                const cplx dAc = csub(Ac[n * nw + n], Ac[m * nw + m]), dAa = csub(Aa[n * nw + n], Aa[m * nw + m]);
+                g = cadd(g, X[(size_t)(idA + 3 * c + a) * n2 + nm]);
+                g = cadd(g, cadd(cmul(Dc, dAa), cmul(Da, dAc)));            // AD_bit
+                const cplx aa = cmul(dAa, Ac[nm]);                            // AA_bit
+                g = cmake(g.x + aa.y, g.y - aa.x);                            // - i AA_bit
+                g = cadd(g, cadd(sumA, cmul(Pnm, cmake(-dAc.x, -dAc.y))));   // sum_AD: - A_nn^c P_nm^a + P_nm^a A_mm^c
+            }
+            Gk[x] = g;
+        }
+    }
+}
+
 // factor_omega of OpticalConductivity (dynamic.py:191-196) without the (E2 - E1) prefactor: 1/(d - i eta), the
 // imaginary part replaced by pi * Gaussian(d) for smr_type != Lorentzian
 __device__ __forceinline__ cplx wb_kubo_cfac(double d, double eta, int smr_type) {
@@ -314,8 +431,8 @@ __device__ __forceinline__ double wb_kubo_smear(double x, double eta, int smr_ty
 
 // threads per omega value of the accumulation kernel: optical conductivity (component, re | im) = 18, JDOS 1,
 // spin Hall 27 components (each thread carries the real and the imaginary part)
-__host__ __device__ constexpr int wb_kubo_tpw(int kind) { return kind == 0 ? 18 : kind == 2 ? 27 : 1; }
-__host__ __device__ constexpr int wb_kubo_nc(int kind) { return kind == 0 ? 18 : kind == 2 ? 54 : 1; }
+__host__ __device__ constexpr int wb_kubo_tpw(int kind) { return kind == 0 ? 18 : kind >= 2 ? 27 : 1; }
+__host__ __device__ constexpr int wb_kubo_nc(int kind) { return kind == 0 ? 18 : kind >= 2 ? 54 : 1; }
 
 template <int KIND>
 __global__ void __launch_bounds__(wb_kubo_tpw(KIND) * WB_KUBO_WT)
@@ -330,7 +447,8 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
     const bool owner = iw < nwt;
     const int ab = c >> 1, ri = c & 1;
     const int wsel = ((ab / 3) > (ab % 3)) ? 2 : 0;   // antisymmetric slot (a > b): Wn, else Wd
-    double* const col = Dglob + ((size_t)(w0 + iw) * P.nEF) * NC + (KIND == 2 ? 2 * c : c);
+    double* const col = Dglob + ((size_t)(w0 + iw) * P.nEF) * NC + (KIND >= 2 ? 2 * c : c);
+    const int ct = (c / 9) * 9 + (c % 3) * 3 + (c / 3) % 3;   // KIND 3: component (a, c, b) of (a, b, c)
     for (long ik = blockIdx.y; ik < nk; ik += gridDim.y) {
         const int cnt = count[ik];
         const double* src = entries + (size_t)ik * cap * ENT;
@@ -354,6 +472,10 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
                     const double w1x = dl * c1.x, w1y = dl * c1.y, w2x = -dl * c2.x, w2y = -dl * c2.y;
                     o[0] = w2x - w1x; o[1] = w2y - w1y;
                     o[2] = -(w1x + w2x); o[3] = -(w1y + w2y);
+                } else if (KIND == 2 && P.kind == 3) {
+                    // ShiftCurrent.factor_omega (dynamic.py:319-322), the same for both orders of the pair
+                    o[0] = wb_kubo_smear(-dl - om, P.eta, P.smr_type) + wb_kubo_smear(dl - om, P.eta, P.smr_type);
+                    o[1] = o[2] = o[3] = 0.;
                 } else if (KIND == 2) {
                     // SHC.factor_omega (dynamic.py:232-237): cfac(E1 - E2 - omega) / 2; pair (lo, hi) with the Fermi
                     // factor -1, pair (hi, lo) with +1
@@ -361,6 +483,11 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
                     const cplx c2 = wb_kubo_cfac(dl - om, P.eta, P.smr_type);
                     o[0] = -0.5 * c1.x; o[1] = -0.5 * c1.y;
                     o[2] = 0.5 * c2.x; o[3] = 0.5 * c2.y;
+                } else if (KIND == 3) {
+                    // InjectionCurrent.factor_omega (dynamic.py:363-365): smear(E1 - E2 - omega); pair (lo, hi) with the Fermi
+                    // factor -1 on M[abc], pair (hi, lo) with +1 on -M[acb]
+                    o[0] = -wb_kubo_smear(-dl - om, P.eta, P.smr_type);
+                    o[1] = -wb_kubo_smear(dl - om, P.eta, P.smr_type);
                 } else {
                     const int fl = (int)ent[p * ENT + 3];
                     o[0] = (fl & 1) ? wb_kubo_smear(dl - om, P.eta, P.smr_type) : 0.;    // (hi, lo): E1 - E2 = +Delta
@@ -375,7 +502,7 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
                     const int bin = (int)e[1];
                     if (bin != curbin) {   // uniform
                         if (curbin >= 0 && Y != 0.) atomicAdd(col + (size_t)curbin * NC, Y);
-                        if (KIND == 2 && curbin >= 0 && Y2 != 0.) atomicAdd(col + (size_t)curbin * NC + 1, Y2);
+                        if (KIND >= 2 && curbin >= 0 && Y2 != 0.) atomicAdd(col + (size_t)curbin * NC + 1, Y2);
                         curbin = bin;
                         Y = 0.;
                         Y2 = 0.;
@@ -389,6 +516,9 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
                         const double m1 = e[2 + c], m2 = e[29 + c];
                         Y += W[0] * m1 + W[2] * m2;
                         Y2 += W[1] * m1 + W[3] * m2;
+                    } else if (KIND == 3) {
+                        Y += W[0] * e[2 + 2 * c] + W[1] * e[2 + 2 * ct];
+                        Y2 += W[0] * e[3 + 2 * c] + W[1] * e[3 + 2 * ct];
                     } else {
                         Y += (W[0] - W[1]) * e[2];
                     }
@@ -396,7 +526,7 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
             }
         }
         if (owner && curbin >= 0 && Y != 0.) atomicAdd(col + (size_t)curbin * NC, Y);
-        if (KIND == 2 && owner && curbin >= 0 && Y2 != 0.) atomicAdd(col + (size_t)curbin * NC + 1, Y2);
+        if (KIND >= 2 && owner && curbin >= 0 && Y2 != 0.) atomicAdd(col + (size_t)curbin * NC + 1, Y2);
     }
 }
 
@@ -405,15 +535,17 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
 // Optical conductivity (NC = 18): slots (ab, ba), a < b hold P = X[ab] + X[ba] and Q = X[ab] - X[ba]:
 // out[iEf][iw][ab] = scale (P + Q) / 2, out[..][ba] = scale (P - Q) / 2; the diagonal slots hold X[aa].
 __global__ void wb_kubo_finalize_kernel(const double* __restrict__ D, int nomega, int nEF, int NC, double scale,
-                                        double* __restrict__ out) {
+                                        double* __restrict__ out, int real_only) {
     const long total = (long)nomega * NC;
     for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
         const int c = (int)(x % NC), w = (int)(x / NC);
-        if (NC != 18) {   // JDOS, spin Hall: plain running sum
+        if (NC != 18) {   // JDOS, rank-3 kinds: plain running sum (shift current: the real parts only)
+            if (real_only && (c & 1)) continue;
             double run = 0.;
             for (int f = 0; f < nEF; f++) {
                 run += D[((size_t)w * nEF + f) * NC + c];
-                out[((size_t)f * nomega + w) * NC + c] = scale * run;
+                if (real_only) out[((size_t)f * nomega + w) * (NC / 2) + (c >> 1)] = scale * run;
+                else out[((size_t)f * nomega + w) * NC + c] = scale * run;
             }
             continue;
         }

@@ -339,7 +339,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     auto has = [&](int f) { return (m >> f) & 1u; };
     bool need_dH = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
                    has(WBGPU_VEL_SPIN) || has(WBGPU_KUBO) || has(WBGPU_VEL_VEL) || has(WBGPU_INV_MASS) || has(WBGPU_SHC_RYOO) ||
-                   has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE) || has(WBGPU_DER_OMEGA);
+                   has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE) || has(WBGPU_DER_OMEGA) || has(WBGPU_SHIFT_CURRENT);
     const bool shc = has(WBGPU_SHC_RYOO) || has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE);
     bool prod_any = false, prod_mass = false, prod_omega = false, prod_spin = false;
     for (int f = WBGPU_DER_SPIN; f < WBGPU_NFORMULA; f++)
@@ -351,7 +351,7 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
         }
     need_dH = need_dH || prod_any;
     bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) || has(WBGPU_KUBO);
-    bool need_A = (berry || shc || has(WBGPU_DER_OMEGA) || prod_omega) && external_terms;
+    bool need_A = (berry || shc || has(WBGPU_DER_OMEGA) || prod_omega || has(WBGPU_SHIFT_CURRENT)) && external_terms;
     bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS)) && external_terms;
     bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN) || shc || prod_spin;
     if (has(WBGPU_SHC_RYOO) && (!c->d_XR[WBGPU_SA] || !c->d_XR[WBGPU_SHA]))
@@ -405,9 +405,10 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     for (int a = 0; a < 3; a++) L.off_B[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_C[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_S[a] = need_S ? take(true) : -1;
-    for (int a = 0; a < 6; a++) L.off_W[a] = (has(WBGPU_INV_MASS) || has(WBGPU_DER_OMEGA) || prod_mass) ? take(dH_herm) : -1;
+    for (int a = 0; a < 6; a++)
+        L.off_W[a] = (has(WBGPU_INV_MASS) || has(WBGPU_DER_OMEGA) || prod_mass || has(WBGPU_SHIFT_CURRENT)) ? take(dH_herm) : -1;
     for (int a = 0; a < 9; a++) L.off_dS[a] = has(WBGPU_DER_SPIN) ? take(true) : -1;
-    for (int a = 0; a < 9; a++) L.off_dA[a] = (has(WBGPU_DER_OMEGA) && need_A) ? take(true) : -1;
+    for (int a = 0; a < 9; a++) L.off_dA[a] = ((has(WBGPU_DER_OMEGA) || has(WBGPU_SHIFT_CURRENT)) && need_A) ? take(true) : -1;
     for (int a = 0; a < 9; a++) L.off_dO[a] = (has(WBGPU_DER_OMEGA) && need_A) ? take(true) : -1;
     for (int a = 0; a < 9; a++) L.off_SA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_SHA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
@@ -1417,7 +1418,8 @@ extern "C" int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* s) {
     if (!s || s->nEF < 1 || s->nomega < 1) return -1;
     if (s->kind == WBGPU_KUBO_OPTCOND) return (int64_t)s->nEF * s->nomega * 18;
     if (s->kind == WBGPU_KUBO_JDOS) return (int64_t)s->nEF * s->nomega;
-    if (s->kind == WBGPU_KUBO_SHC) return (int64_t)s->nEF * s->nomega * 54;
+    if (s->kind == WBGPU_KUBO_SHC || s->kind == WBGPU_KUBO_INJECTION) return (int64_t)s->nEF * s->nomega * 54;
+    if (s->kind == WBGPU_KUBO_SHIFT) return (int64_t)s->nEF * s->nomega * 27;
     return -1;
 }
 
@@ -1430,7 +1432,8 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     if (spec->smr_type != 0 && spec->smr_type != 1) return set_err("wbgpu_kubo_scan: Invalid smearing type %d", spec->smr_type);
     if (!(spec->smr_fixed_width > 0)) return set_err("wbgpu_kubo_scan: smr_fixed_width must be positive");
     const bool optcond = spec->kind == WBGPU_KUBO_OPTCOND, shc = spec->kind == WBGPU_KUBO_SHC;
-    const bool rotated = optcond || shc;   // needs eigenvectors and rotated matrices
+    const bool shift = spec->kind == WBGPU_KUBO_SHIFT, inject = spec->kind == WBGPU_KUBO_INJECTION;
+    const bool rotated = optcond || shc || shift || inject;   // needs eigenvectors and rotated matrices
     const WbLayout& L = c->L;
     if (shc) {
         const int t = spec->shc_type;
@@ -1439,7 +1442,11 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
         if (!((c->mask >> t) & 1u) || L.off_dH[0] < 0 || L.off_S[0] < 0 || (spec->external_terms && L.off_A[0] < 0))
             return set_err("wbgpu_kubo_scan: the plan does not hold the channels of this spin Hall scan (declare WBGPU_SHC_*)");
     }
-    if (optcond && (!((c->mask >> WBGPU_KUBO) & 1u) || L.off_dH[0] < 0 || (spec->external_terms && L.off_A[0] < 0)))
+    if (shift && (!((c->mask >> WBGPU_SHIFT_CURRENT) & 1u) || L.off_dH[0] < 0 || L.off_W[0] < 0 ||
+                  (spec->external_terms && (L.off_A[0] < 0 || L.off_dA[0] < 0))))
+        return set_err("wbgpu_kubo_scan: the plan does not hold the channels of the shift current (declare WBGPU_SHIFT_CURRENT)");
+    if (shift && !(spec->sc_eta > 0)) return set_err("wbgpu_kubo_scan: sc_eta must be positive");
+    if ((optcond || inject) && (!((c->mask >> WBGPU_KUBO) & 1u) || L.off_dH[0] < 0 || (spec->external_terms && L.off_A[0] < 0)))
         return set_err("wbgpu_kubo_scan: the plan does not hold the channels of the Kubo path (declare WBGPU_KUBO)");
     for (int i = 1; i < spec->nEF; i++)
         if (!(Efermi[i] > Efermi[i - 1])) return set_err("wbgpu_kubo_scan: Efermi must be strictly ascending");
@@ -1451,6 +1458,7 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     WbKuboParams P;
     P.kind = spec->kind; P.smr_type = spec->smr_type; P.external = spec->external_terms; P.nEF = nEF; P.nomega = nom;
     P.eta = spec->smr_fixed_width;
+    P.sc_eta = spec->sc_eta;
     P.EFmin = Efermi[0]; P.EFmax = Efermi[nEF - 1];
     double wmin = omega[0], wmax = omega[0];
     for (int i = 1; i < nom; i++) { wmin = std::min(wmin, omega[i]); wmax = std::max(wmax, omega[i]); }
@@ -1496,6 +1504,12 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
         if (sc.type == WBGPU_SHC_RYOO) { sc.iX1 = addn(L.off_SA, 9, 0); sc.iX2 = addn(L.off_SHA, 9, 0); }
         if (sc.type == WBGPU_SHC_QIAO) { sc.iX1 = addn(L.off_SR, 9, 0); sc.iX2 = addn(L.off_SH, 3, 0); sc.iX3 = addn(L.off_SHR, 9, 0); }
     }
+    int iW = 0, idA = 0;
+    if (shift) {
+        iW = addn(L.off_W, 6, L.dH_herm);
+        if (spec->external_terms) idA = addn(L.off_dA, 9, 1);
+    }
+    const bool needJ = shc || shift;   // a [9][nw][nw] matrix per k-point in d_shcJ
     const int cap = std::max(1, nw * (nw - 1));
     const size_t smem_ent = wb_kubo_entries_smem_bytes(nw);
     if (smem_ent > 48 * 1024)
@@ -1513,7 +1527,7 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
         long chunk = std::min(nk, std::max(1L, (long)(3.0e9 / (8.0 * ENT * cap))));
         if (rotated) chunk = std::min(chunk, xbar_chunk(c, ch.n, nk));
         if (rotated && ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * nw * nw)) return 1;
-        if (shc && ensure(&c->d_shcJ, &c->shcJ_cap, sizeof(cplx) * (size_t)chunk * 9 * nw * nw)) return 1;
+        if (needJ && ensure(&c->d_shcJ, &c->shcJ_cap, sizeof(cplx) * (size_t)chunk * 9 * nw * nw)) return 1;
         if (ensure(&c->d_kent, &c->kent_cap, sizeof(double) * (size_t)chunk * cap * ENT + sizeof(int) * (size_t)chunk + 16)) return 1;
         int* d_count = (int*)(c->d_kent + (size_t)chunk * cap * ENT);
         for (long k0 = 0; k0 < nk; k0 += chunk) {
@@ -1526,6 +1540,11 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
                         (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, sc, spec->external_terms, (cplx*)c->d_shcJ);
                     c->launches++;
                 }
+                if (shift) {
+                    wb_shift_agen_kernel<256><<<(unsigned)std::min(n, (long)sms * 8), 256, sizeof(double) * nw, c->stream>>>(
+                        (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, iW, sc.iA, idA, spec->sc_eta, (cplx*)c->d_shcJ);
+                    c->launches++;
+                }
                 stage_end(c);
             }
             stage_begin(c, WBGPU_STAGE_SCAN);
@@ -1536,8 +1555,10 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
             dim3 grid((unsigned)nwtile, (unsigned)nsplit);
             if (optcond)
                 wb_kubo_accumulate_kernel<0><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
-            else if (shc)
+            else if (shc || shift)
                 wb_kubo_accumulate_kernel<2><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
+            else if (inject)
+                wb_kubo_accumulate_kernel<3><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
             else
                 wb_kubo_accumulate_kernel<1><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
             c->launches += 2;
@@ -1547,10 +1568,10 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     }
     const double scale = spec->factor / (c->cell_volume * (double)c->nk_block);
     wb_kubo_finalize_kernel<<<(unsigned)(((size_t)nom * NC + 127) / 128), 128, 0, c->stream>>>(c->d_kacc, nom, nEF, NC, scale,
-                                                                                                    c->d_kacc + nacc);
+                                                                                                    c->d_kacc + nacc, shift ? 1 : 0);
     c->launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, c->d_kacc + nacc, sizeof(double) * nacc, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out, c->d_kacc + nacc, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     stage_collect(c);
     return 0;

@@ -125,7 +125,7 @@ class Engine:
         out = np.zeros(int(self._L.wbgpu_kubo_size(C.byref(spec))))
         check(self._L.wbgpu_kubo_scan(self._ctx, dK.shape[0], dptr(dK), dptr(weight), C.byref(spec), dptr(Efermi),
                                       dptr(omega), dptr(out)))
-        if int(spec.kind) in (_lib.KUBO_OPTCOND, _lib.KUBO_SHC):
+        if spec.is_complex:
             return out.view(np.complex128).reshape(spec.shape)
         return out.reshape(spec.shape)
 

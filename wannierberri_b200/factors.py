@@ -17,3 +17,6 @@ factor_nlahc = elementary_charge ** 3 / hbar ** 2 * TAU_UNIT
 fac_spin_Z = hbar / (2 * electron_mass)
 factor_hall_classic = -(elementary_charge ** 3 / hbar ** 2 * angstrom * TAU_UNIT ** 2 * elementary_charge ** 2 / hbar ** 2)
 factor_nldrude = -(elementary_charge ** 3 / hbar ** 2 * TAU_UNIT ** 2 * elementary_charge / hbar)
+from math import pi  # noqa: E402
+factor_shift_current = hbar / elementary_charge * pi * elementary_charge ** 3 / (4 * hbar ** 2)
+factor_injection_current = -pi * elementary_charge ** 3 / (hbar ** 2) * TAU_UNIT

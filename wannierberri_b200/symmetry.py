@@ -50,6 +50,8 @@ def apply_transform(name, res):
         return -res
     if name == "trans":
         return np.swapaxes(res, -1, -2)
+    if name == "odd_trans_021":   # Transform(factor=-1, transpose_axes=(0, 2, 1)) of a rank-3 tensor
+        return -np.swapaxes(res, -1, -2)
     raise ValueError(f"unknown transform {name!r}")
 
 
