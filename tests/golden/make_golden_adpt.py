@@ -35,6 +35,18 @@ def main():
             out[f"iter{n_iter}_{q}"] = res.results[q].data
     np.savez_compressed(os.path.join(OUT, "golden_synth_adpt.npz"), **out)
     print("written", os.path.join(OUT, "golden_synth_adpt.npz"))
+    # refinement driven by tetrahedron-method and Kubo calculators (per-K-point cells shrink with the refinement)
+    from wannierberri.calculators import dynamic as dyn
+    Ef2 = np.linspace(-3., 3., 13)
+    calcs = dict(ahc_tetra=calc.static.AHC(Efermi=Ef2, tetra=True), dos_tetra=calc.static.DOS(Efermi=Ef2, tetra=True),
+                 cumdos=calc.static.CumDOS(Efermi=Ef2),
+                 optcond=dyn.OpticalConductivity(Efermi=Ef2[::4], omega=np.linspace(0., 4., 9), smr_fixed_width=0.2))
+    out = dict(Efermi=Ef2, omega=np.linspace(0., 4., 9))
+    for n_iter in (0, 2):
+        grid, res = run_ref(system, [6, 6, 6], [3, 3, 3], calcs, adpt_num_iter=n_iter, adpt_fac=2, adpt_mesh=2)
+        for q in calcs:
+            out[f"iter{n_iter}_{q}"] = res.results[q].data
+    np.savez_compressed(os.path.join(OUT, "golden_synth_adpt_tetra_kubo.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -839,6 +839,24 @@ def test_adaptive_refinement(wb, fe, orc):
         assert relerr(np.tensordot(factors, b, axes=(0, 0)), w) < 1e-12
 
 
+def test_adaptive_refinement_tetra_and_kubo(wb):
+    """run(adpt_num_iter = 2) driven by tetrahedron-method and Kubo calculators (evaluated one K-point per call, the
+    tetrahedron cell of a refined K-point is its own dK / NKFFT, grid/Kpoint.py:107-109) next to a plain static one,
+    against the reference's own run() (fixture of tests/golden/make_golden_adpt.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_synth_adpt_tetra_kubo.npz"))
+    sysg = wb.synthetic_system(6, rmax=1, seed=4242)
+    st, dyn = wb.calculators.static, wb.calculators.dynamic
+    Ef = g["Efermi"]
+    for n_iter in (0, 2):
+        calcs = dict(ahc_tetra=st.AHC(Efermi=Ef, tetra=True), dos_tetra=st.DOS(Efermi=Ef, tetra=True), cumdos=st.CumDOS(Efermi=Ef),
+                     optcond=dyn.OpticalConductivity(Efermi=Ef[::4], omega=g["omega"], smr_fixed_width=0.2))
+        grid = wb.Grid(sysg, NKdiv=[2, 2, 2], NKFFT=[3, 3, 3])
+        res = wb.run(sysg, grid, calcs, adpt_num_iter=n_iter, adpt_fac=2, adpt_mesh=2) if n_iter else wb.run(sysg, grid, calcs)
+        for q in calcs:
+            tol = 1e-6 if q == "dos_tetra" else RTOL   # der = 1 tetrahedron weights (see TETRA_CASES)
+            assert relerr(res.results[q].data, g[f"iter{n_iter}_{q}"]) < tol, (n_iter, q)
+
+
 def test_run_fe_vs_upstream_golden(wb, fe):
     """run() on the reference's own test grid against the data of the reference's golden files
     tests/reference/integrate_files/Fe_W90-{ahc,dos,cumdos}_iter-0000.npz."""

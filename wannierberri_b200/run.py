@@ -148,14 +148,14 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
     if (symmetrize or use_irred_kpt) and pointgroup is None:
         raise ValueError("use_irred_kpt / symmetrize need system.pointgroup (System_R.set_pointgroup)")
     periodic = getattr(system, "periodic", (True, True, True))
-    calcs = {}
+    calcs, slow_calcs = {}, {}   # slow: tetrahedron / Kubo calculators, evaluated one K-point per call
     for key, c in calculators.items():
-        if isinstance(c, _dyn.DynamicCalculator) or type(c).__name__ in _dyn._BY_NAME:
-            raise NotImplementedError("adaptive refinement of Kubo calculators is not implemented on the GPU path")
+        if isinstance(c, _dyn.DynamicCalculator) or (type(c).__name__ in _dyn._BY_NAME and hasattr(c, "omega")
+                                                       and not hasattr(c, "fder")):
+            slow_calcs[key] = _dyn.adapt(c)
+            continue
         c = adapt_static(c)
-        if c.tetra:
-            raise NotImplementedError("adaptive refinement with tetra=True is not implemented on the GPU path")
-        calcs[key] = c
+        (slow_calcs if c.tetra else calcs)[key] = c
     dist = _dist() if parallel else None
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     if device is None:
@@ -181,8 +181,28 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
                 s.external_terms = 0
             specs.append(s)
             owner.append(key)
+    internal_only = getattr(system, "force_internal_terms_only", False)
+    slow_specs = {}
+    for key, c in slow_calcs.items():
+        sp = [c.spec()] if isinstance(c, _dyn.DynamicCalculator) else c.specs()
+        for s in sp:
+            if internal_only:
+                s.external_terms = 0
+        slow_specs[key] = sp
+    flags = {int(s.formula) for s in specs} | {_lib.IDENTITY}
+    for key, c in slow_calcs.items():
+        flags |= {s.formula_flag if isinstance(c, _dyn.DynamicCalculator) else int(s.formula) for s in slow_specs[key]}
+    external = any(s.external_terms for s in specs) or any(s.external_terms for sp in slow_specs.values() for s in sp)
     engine = engine_for(system, device)
-    engine.plan(NKFFT, {int(s.formula) for s in specs} | {_lib.IDENTITY}, external_terms=any(s.external_terms for s in specs))
+    engine.plan(NKFFT, flags, external_terms=external)
+
+    def eval_slow(key, K):
+        """one K-point through the tetrahedron / Kubo scans (per-K-point cell K.dK_fullBZ, grid/Kpoint.py:107-109)"""
+        c, sp = slow_calcs[key], slow_specs[key]
+        dK = np.array(K.Kp_fullBZ, dtype=float)[None, :]
+        if isinstance(c, _dyn.DynamicCalculator):
+            return [np.ascontiguousarray(engine.kubo_scan(dK, np.ones(1), sp[0], c.Efermi, c.omega))]
+        return engine.scan_tetra(dK, np.ones(1), np.array(K.dK_fullBZ, dtype=float), sp)
 
     result_all = None
     factors_old = None
@@ -191,7 +211,28 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
         # the new K-points are sharded over the ranks; every rank then holds all per-K-point results
         lo, hi = shard_bounds(len(new), rank, world)
         dK_new = np.array([K_list[i].Kp_fullBZ for i in new], dtype=float).reshape(-1, 3)
-        mine = engine.scan_blocks(dK_new[lo:hi], specs) if hi > lo else [np.zeros((0,) + s.shape) for s in specs]
+        mine = engine.scan_blocks(dK_new[lo:hi], specs) if (hi > lo and specs) else [np.zeros((0,) + s.shape) for s in specs]
+        slow = {}   # key -> list over the new K-points of this rank's shard of [array per spec]
+        for key in slow_calcs:
+            slow[key] = [eval_slow(key, K_list[i]) for i in new[lo:hi]]
+        if dist and world > 1 and slow_calcs:
+            import torch
+            dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            for key, c in slow_calcs.items():
+                shapes = [s.shape for s in slow_specs[key]]
+                cplx = isinstance(c, _dyn.DynamicCalculator) and slow_specs[key][0].is_complex
+                gathered = []
+                for isp, shp in enumerate(shapes):
+                    buf = np.zeros((len(new),) + shp, dtype=complex if cplx else float)
+                    for j in range(hi - lo):
+                        buf[lo + j] = slow[key][j][isp]
+                    t = torch.from_numpy(np.ascontiguousarray(buf).view(np.float64)).to(dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                    gathered.append(t.cpu().numpy().view(buf.dtype).reshape(buf.shape))
+                slow[key] = [[gathered[isp][j] for isp in range(len(shapes))] for j in range(len(new))]
+            slow_lo = 0
+        else:
+            slow_lo = lo
         if dist and world > 1:
             import torch
             dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
@@ -207,6 +248,9 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
         for j, i in enumerate(new):
             res = {key: c.result([a[j] for a, o in zip(mine, owner) if o == key], system.cell_volume)
                    for key, c in calcs.items()}
+            for key, c in slow_calcs.items():
+                arrs = slow[key][j - slow_lo]
+                res[key] = c.result(arrs[0]) if isinstance(c, _dyn.DynamicCalculator) else c.result(arrs, system.cell_volume)
             if symmetrize:   # per K-point here: K.max must see the symmetrised result (run_grid.py:258-265)
                 res = {key: r.symmetrized(pointgroup) for key, r in res.items()}
             res = ResultDict(res)
