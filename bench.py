@@ -60,7 +60,33 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.samples, self.proc = index, [], None
 
+    # NVML bit masks of nvmlClocksEventReasons (nvml.h): the reasons the timing rules reject or note
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            mask = int(get_reasons(h))
+            flags = ["Active" if mask & bit else "Not Active" for bit in (0x8, 0x40, 0x20, 0x4)]
+            self.samples.append(",".join([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(smax)] + flags))
+            time.sleep(0.005)
+
     def start(self):
+        # the timed region is ~0.1 s: NVML is polled every 5 ms from a thread (the same counters nvidia-smi prints);
+        # `nvidia-smi -lms` (one sample per 100 ms after its start-up) is the fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.stop_flag = threading.Event()
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            self.proc = "nvml"
+            return
+        except Exception:
+            self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -77,7 +103,10 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.proc == "nvml":
+            self.stop_flag.set()
+        else:
+            self.proc.terminate()
         self.t.join(timeout=2)
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -92,7 +121,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.proc == "nvml" else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
