@@ -154,7 +154,7 @@ int64_t wbgpu_spec_size(const wbgpu_scan_spec* spec);
 int wbgpu_static_scan_tetra(wbgpu_ctx* ctx, int nblocks, const double* dK, const double* weight, const double* dK_cell,
                             const wbgpu_scan_spec* specs, int nspec, double* out);
 
-/* One (Efermi x omega) scan = one DynamicCalculator.__call__ (calculators/dynamic.py:26-114) at kBT = 0. */
+/* One (Efermi x omega) scan = one DynamicCalculator.__call__ (calculators/dynamic.py:26-114). */
 enum { WBGPU_KUBO_OPTCOND = 0,  /* OpticalConductivity dynamic.py:184-196: complex128 data[nEF][nomega][3][3]    */
        WBGPU_KUBO_JDOS = 1,     /* JDOS                dynamic.py:146-162: float64    data[nEF][nomega]          */
        WBGPU_KUBO_SHC = 2,      /* SHC                 dynamic.py:204-237: complex128 data[nEF][nomega][3][3][3] */
@@ -172,6 +172,7 @@ typedef struct wbgpu_kubo_spec {
     double degen_thresh;
     double factor;           /* constant_factor                                */
     double sc_eta;           /* ShiftCurrent only: broadening of the energy denominators of the generalised derivative */
+    double kBT;              /* temperature of the Fermi-Dirac factor (utility.py:172-182); 0 = step function        */
 } wbgpu_kubo_spec;
 /* number of float64 values the scan writes (complex counted as 2) */
 int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* spec);

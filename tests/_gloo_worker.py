@@ -46,7 +46,7 @@ class OracleEngine:
         out = 0
         for d, w in zip(dK, weight):
             data = orc.OracleDataK(self.osys, d, self.NKFFT)
-            out = out + w * orc.kubo_scan(data, kind, Efermi, omega, smr_fixed_width=spec.smr_fixed_width,
+            out = out + w * orc.kubo_scan(data, kind, Efermi, omega, kBT=spec.kBT, smr_fixed_width=spec.smr_fixed_width,
                                           smr_type="Lorentzian" if spec.smr_type == 0 else "Gaussian",
                                           degen_thresh=spec.degen_thresh, degen_Kramers=bool(spec.degen_Kramers),
                                           external_terms=bool(spec.external_terms), constant_factor=spec.factor,

@@ -466,6 +466,44 @@ def test_shift_and_injection_current_synthetic(wb, orc, nw, nom):
     assert relerr(got, orc.InjectionCurrent(odata, Ef, omega=om, **kw)) < RTOL
 
 
+KBT_CASES = dict(
+    optcond=("OpticalConductivity", dict(kBT=0.05)), optcond_hot=("OpticalConductivity", dict(kBT=0.5, smr_type="Gaussian")),
+    jdos=("JDOS", dict(kBT=0.05)), shc_ryoo=("SHC", dict(SHC_type="ryoo", kBT=0.03)),
+    shift=("ShiftCurrent", dict(sc_eta=0.1, kBT=0.05)), injection=("InjectionCurrent", dict(kBT=0.01)),
+    optcond_thresh=("OpticalConductivity", dict(kBT=0.05, degen_thresh=0.3)),
+)
+
+
+def test_kubo_finite_temperature_random_system(wb):
+    """Kubo calculators at kBT > 0 (the owner value of a band group is spread over the Fermi levels within +- 30 kBT of its
+    energy with the Fermi-Dirac differences) through run(), against the live reference run of make_golden_kbt.py."""
+    g = np.load(os.path.join(GOLDEN, "golden_random_kbt.npz"))
+    rnd = wb.System_R.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    dyn = wb.calculators.dynamic
+    calcs = {k: getattr(dyn, name)(Efermi=g["Efermi"], omega=g["omega"], smr_fixed_width=0.20, **kw)
+             for k, (name, kw) in KBT_CASES.items()}
+    res = wb.run(rnd, wb.Grid(rnd, NK=g["NK"], NKFFT=g["NKFFT"]), calcs)
+    for k in KBT_CASES:
+        assert res.results[k].data.shape == g[k].shape, k
+        assert relerr(res.results[k].data, g[k]) < RTOL, k
+
+
+def test_kubo_finite_temperature_synthetic(wb, orc):
+    """32-WF model, non-uniform Fermi axis, kBT comparable to the level spacing, against the oracle"""
+    sysg = wb.synthetic_system(32, rmax=1, seed=732)
+    syso = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
+                            {k: sysg.get_R_mat(k) for k in ("Ham", "AA")})
+    NKFFT, dK = [2, 2, 2], [0.05, 0.11, 0.02]
+    Ef, om = np.sort(np.concatenate([np.linspace(-1., 1., 30), [-0.333, 0.017, 0.018]])), np.linspace(0., 5., 40)
+    data = wb.Data_K_R(sysg, dK=dK, grid=wb.Grid(sysg, NKdiv=[1, 1, 1], NKFFT=NKFFT))
+    odata = orc.OracleDataK(syso, dK, NKFFT)
+    kw = dict(smr_fixed_width=0.1, smr_type="Lorentzian", kBT=0.02)
+    got = wb.calculators.dynamic.OpticalConductivity(Efermi=Ef, omega=om, **kw)(data).data
+    assert relerr(got, orc.OpticalConductivity(odata, Ef, omega=om, **kw)) < RTOL
+    got = wb.calculators.dynamic.JDOS(Efermi=Ef, omega=om, **kw)(data).data
+    assert relerr(got, orc.JDOS(odata, Ef, omega=om, **kw)) < RTOL
+
+
 # ---------------------------------------------------------------------------------------- tetrahedron method
 TETRA_CASES = dict(
     ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}), spin=("Spin", {}),

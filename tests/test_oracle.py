@@ -345,3 +345,23 @@ def test_shift_and_injection_current_random_system():
     for k in SHIFT_CASES:
         assert res[k].shape == g[k].shape and res[k].dtype == g[k].dtype, k
         assert relerr(res[k], g[k]) < RTOL, k
+
+
+KBT_CASES = dict(
+    optcond=("OpticalConductivity", dict(kBT=0.05)), optcond_hot=("OpticalConductivity", dict(kBT=0.5, smr_type="Gaussian")),
+    jdos=("JDOS", dict(kBT=0.05)), shc_ryoo=("SHC", dict(SHC_type="ryoo", kBT=0.03)),
+    shift=("ShiftCurrent", dict(sc_eta=0.1, kBT=0.05)), injection=("InjectionCurrent", dict(kBT=0.01)),
+    optcond_thresh=("OpticalConductivity", dict(kBT=0.05, degen_thresh=0.3)),
+)
+
+
+def test_kubo_finite_temperature_random_system():
+    """Kubo calculators with the Fermi-Dirac factor at kBT > 0 (utility.py:172-182, dynamic.py:44-45,61-69) on the reference's
+    `random` system against the live reference run of tests/golden/make_golden_kbt.py."""
+    g = np.load(os.path.join(GOLDEN, "golden_random_kbt.npz"))
+    rnd = orc.OracleSystem.from_npz(os.path.join(GOLDEN, "random_system.npz"))
+    calcs = {k: (name, g["Efermi"], dict(omega=g["omega"], smr_fixed_width=0.20, **kw)) for k, (name, kw) in KBT_CASES.items()}
+    res = orc.run(rnd, [2, 2, 2], [3, 3, 3], calcs)
+    for k in KBT_CASES:
+        assert res[k].shape == g[k].shape, k
+        assert relerr(res[k], g[k]) < RTOL, k

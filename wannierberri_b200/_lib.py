@@ -41,7 +41,7 @@ class KuboSpec(C.Structure):
                 ("degen_Kramers", C.c_int32), ("external_terms", C.c_int32), ("shc_type", C.c_int32),
                 ("reserved", C.c_int32),
                 ("smr_fixed_width", C.c_double), ("degen_thresh", C.c_double), ("factor", C.c_double),
-                ("sc_eta", C.c_double)]
+                ("sc_eta", C.c_double), ("kBT", C.c_double)]
 
     @property
     def shape(self):

@@ -25,9 +25,8 @@ class DynamicCalculator(Calculator):
         super().__init__(**kwargs)
         self.Efermi = np.array(Efermi, dtype=float).reshape(-1)
         self.omega = np.array(omega, dtype=float).reshape(-1)
-        if kBT != 0:
-            raise NotImplementedError("kBT > 0 is not implemented on the GPU path (the Fermi factor is no longer an "
-                                      "interval of the Efermi axis)")
+        if kBT < 0:
+            raise ValueError("kBT must not be negative")
         if smr_type not in ("Lorentzian", "Gaussian"):
             raise ValueError(f"Invalid smearing type {smr_type}")  # dynamic.py:54
         if len(self.Efermi) > 1 and not np.all(np.diff(self.Efermi) > 0):
@@ -51,7 +50,7 @@ class DynamicCalculator(Calculator):
                         degen_Kramers=int(bool(self.degen_Kramers)), external_terms=int(self.external_terms),
                         shc_type=int(self.shc_type), smr_fixed_width=float(self.smr_fixed_width),
                         degen_thresh=float(self.degen_thresh), factor=float(self.constant_factor),
-                        sc_eta=float(self.sc_eta))
+                        sc_eta=float(self.sc_eta), kBT=float(self.kBT))
 
     def result(self, data):
         return EnergyResult([self.Efermi, self.omega], data, transformTR=self.transformTR,

@@ -50,6 +50,8 @@ struct WbShcChans {
 struct WbKuboParams {
     int kind;        // 0 = optical conductivity, 1 = JDOS, 2 = spin Hall conductivity, 3 = shift current, 4 = injection current
     double sc_eta;   // shift current: broadening of the denominators of the generalised derivative
+    double kBT;      // 0: the Fermi factor of a group is a step at its owner bin; > 0: Fermi-Dirac (utility.py:172-182), the
+                     // owner's value is spread over the bins within +- 30 kBT of its energy (entries then carry the energy)
     int smr_type;    // 0 = Lorentzian, 1 = Gaussian
     int external;    // external terms (Abar) in A_H
     int nEF, nomega;
@@ -116,12 +118,18 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
             int slot = 0;
             for (int t = 0; t < ng; t++) {
                 const int st = gidx[t];
-                if (st >= P.nEF) break;   // s is monotone in the group index
+                if (P.kBT > 0.) {
+                    if (gE[t] - 30. * P.kBT > P.EFmax) break;   // f = 0 on the whole Fermi axis, and for every later group
+                } else if (st >= P.nEF) break;   // s is monotone in the group index
                 for (int u0 = 0; u0 < ng; u0 += 32) {
                     const int u = u0 + lane;
                     bool valid = false;
                     if (u < ng && u != t) {
                         valid = (u > t) ? (st < gidx[u]) : (gidx[u] < st);
+                        if (P.kBT > 0.) {   // DynamicCalculator.nonzero (dynamic.py:65-69)
+                            const double e1max = P.EFmin - 30. * P.kBT, e0min = P.EFmax + 30. * P.kBT;
+                            valid = !((gE[t] < e1max && gE[u] < e1max) || (gE[t] > e0min && gE[u] > e0min));
+                        }
                         if (valid && P.kind == 1) {
                             const double lo = gE[min(t, u)], hi = gE[max(t, u)];
                             const double d = hi - lo, dm = lo - hi;
@@ -157,7 +165,7 @@ wb_kubo_entries_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
             double* e = ent + (size_t)slot * ENT;
             if (ab == 0) {
                 e[0] = gE[j] - gE[i];
-                e[1] = (double)gidx[pr.x];
+                e[1] = (P.kBT > 0.) ? gE[pr.x] : (double)gidx[pr.x];
             }
             if (P.kind == 1) {
                 const double lo = gE[i], hi = gE[j];
@@ -437,7 +445,8 @@ __host__ __device__ constexpr int wb_kubo_nc(int kind) { return kind == 0 ? 18 :
 template <int KIND>
 __global__ void __launch_bounds__(wb_kubo_tpw(KIND) * WB_KUBO_WT)
 wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restrict__ count, int cap, long nk,
-                          WbKuboParams P, const double* __restrict__ omega, double* __restrict__ Dglob) {
+                          WbKuboParams P, const double* __restrict__ omega, const double* __restrict__ Ef,
+                          double* __restrict__ Dglob) {
     constexpr int TPW = wb_kubo_tpw(KIND), NC = wb_kubo_nc(KIND), WT = WB_KUBO_WT, NT = TPW * WT, ENT = wb_kubo_ent(KIND);
     __shared__ __align__(16) double ent[WB_KUBO_CHUNK * ENT];
     __shared__ __align__(16) double Wb[WB_KUBO_CHUNK * WT * 4];
@@ -453,7 +462,29 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
         const int cnt = count[ik];
         const double* src = entries + (size_t)ik * cap * ENT;
         double Y = 0., Y2 = 0.;
-        int curbin = -1;
+        double curown = -CUDART_INF;   // owner of the values being accumulated: its bin (kBT = 0) or its energy
+        bool have = false;
+        // add the owner's value (Y, Y2) times its Fermi factor to the difference array
+        auto flush = [&]() {
+            if (!have || (Y == 0. && Y2 == 0.)) return;
+            if (P.kBT == 0.) {
+                const size_t o = (size_t)(int)curown * NC;
+                if (Y != 0.) atomicAdd(col + o, Y);
+                if (KIND >= 2 && Y2 != 0.) atomicAdd(col + o + 1, Y2);
+                return;
+            }
+            const double E = curown, top = E + 30. * P.kBT;
+            double prev = 0.;
+            for (int i = wb_lower_bound(Ef, P.nEF, E - 30. * P.kBT); i < P.nEF; i++) {
+                const double mu = Ef[i];
+                const double f = (mu > top) ? 1. : 1. / (exp((E - mu) / P.kBT) + 1.);
+                const double d = f - prev;
+                prev = f;
+                atomicAdd(col + (size_t)i * NC, Y * d);
+                if (KIND >= 2) atomicAdd(col + (size_t)i * NC + 1, Y2 * d);
+                if (mu > top) break;
+            }
+        };
         for (int p0 = 0; p0 < cnt; p0 += WB_KUBO_CHUNK) {
             const int np = min(WB_KUBO_CHUNK, cnt - p0);
             __syncthreads();
@@ -499,11 +530,11 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
             if (owner) {
                 for (int p = 0; p < np; p++) {
                     const double* e = ent + p * ENT;
-                    const int bin = (int)e[1];
-                    if (bin != curbin) {   // uniform
-                        if (curbin >= 0 && Y != 0.) atomicAdd(col + (size_t)curbin * NC, Y);
-                        if (KIND >= 2 && curbin >= 0 && Y2 != 0.) atomicAdd(col + (size_t)curbin * NC + 1, Y2);
-                        curbin = bin;
+                    const double own = e[1];
+                    if (!have || own != curown) {   // uniform
+                        flush();
+                        curown = own;
+                        have = true;
                         Y = 0.;
                         Y2 = 0.;
                     }
@@ -525,8 +556,7 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
                 }
             }
         }
-        if (owner && curbin >= 0 && Y != 0.) atomicAdd(col + (size_t)curbin * NC, Y);
-        if (KIND >= 2 && owner && curbin >= 0 && Y2 != 0.) atomicAdd(col + (size_t)curbin * NC + 1, Y2);
+        if (owner) flush();
     }
 }
 

@@ -1431,6 +1431,7 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     if (nout < 0) return set_err("wbgpu_kubo_scan: bad spec (kind=%d nEF=%d nomega=%d)", spec->kind, spec->nEF, spec->nomega);
     if (spec->smr_type != 0 && spec->smr_type != 1) return set_err("wbgpu_kubo_scan: Invalid smearing type %d", spec->smr_type);
     if (!(spec->smr_fixed_width > 0)) return set_err("wbgpu_kubo_scan: smr_fixed_width must be positive");
+    if (!(spec->kBT >= 0)) return set_err("wbgpu_kubo_scan: kBT must not be negative");
     const bool optcond = spec->kind == WBGPU_KUBO_OPTCOND, shc = spec->kind == WBGPU_KUBO_SHC;
     const bool shift = spec->kind == WBGPU_KUBO_SHIFT, inject = spec->kind == WBGPU_KUBO_INJECTION;
     const bool rotated = optcond || shc || shift || inject;   // needs eigenvectors and rotated matrices
@@ -1459,6 +1460,7 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     P.kind = spec->kind; P.smr_type = spec->smr_type; P.external = spec->external_terms; P.nEF = nEF; P.nomega = nom;
     P.eta = spec->smr_fixed_width;
     P.sc_eta = spec->sc_eta;
+    P.kBT = spec->kBT;
     P.EFmin = Efermi[0]; P.EFmax = Efermi[nEF - 1];
     double wmin = omega[0], wmax = omega[0];
     for (int i = 1; i < nom; i++) { wmin = std::min(wmin, omega[i]); wmax = std::max(wmax, omega[i]); }
@@ -1554,13 +1556,13 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
             const int nsplit = (int)std::max(1L, std::min(n, (long)((6 * sms + nwtile - 1) / nwtile)));
             dim3 grid((unsigned)nwtile, (unsigned)nsplit);
             if (optcond)
-                wb_kubo_accumulate_kernel<0><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
+                wb_kubo_accumulate_kernel<0><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
             else if (shc || shift)
-                wb_kubo_accumulate_kernel<2><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
+                wb_kubo_accumulate_kernel<2><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
             else if (inject)
-                wb_kubo_accumulate_kernel<3><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
+                wb_kubo_accumulate_kernel<3><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
             else
-                wb_kubo_accumulate_kernel<1><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, c->d_kacc);
+                wb_kubo_accumulate_kernel<1><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
             c->launches += 2;
             stage_end(c);
             CK(cudaGetLastError());
