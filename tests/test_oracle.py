@@ -310,6 +310,8 @@ FSEA_CASES = dict(
     ahc_zeeman_spin=("AHC_Zeeman_spin", {}), ahc_zeeman_spin_thresh=("AHC_Zeeman_spin", dict(degen_thresh=0.3)),
     ahc_zeeman_spin_int=("AHC_Zeeman_spin", dict(kwargs_formula=dict(external_terms=False))),
     omegaomega=("OmegaOmega", {}), nlahc_fsurf=("NLAHC_FermiSurf", {}),
+    nldrude_sea=("NLDrude_FermiSea", {}), nldrude_sea_thresh=("NLDrude_FermiSea", dict(degen_thresh=0.3)),
+    nldrude_sea_tetra=("NLDrude_FermiSea", dict(tetra=True)),
 )
 
 
