@@ -71,7 +71,9 @@ enum {
     WBGPU_OMEGA_S = 19,       /* OmegaS     rank 2 (AHC_Zeeman_spin)        */
     WBGPU_OMEGA_OMEGA = 20,   /* OmegaOmega rank 2                          */
     WBGPU_SHIFT_CURRENT = 21, /* plan flag only: channels of the Kubo shift current (d_a H, d_b d_d H, A, d_d A_b) */
-    WBGPU_NFORMULA = 22
+    WBGPU_DER3E = 22,         /* Der3E  covariant.py:126-151 (third derivative of the band energy: NLDrude_FermiSea) rank 3;
+                                 needs d_b d_d H and d_b d_c d_d H */
+    WBGPU_NFORMULA = 23
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */

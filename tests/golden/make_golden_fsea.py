@@ -80,9 +80,10 @@ def main():
         print(f"Te_QE-{q}: live reference run vs reference golden file: rel err {err:.2e}")
         if err < 1e-7:
             out["te_upstream_golden_" + q] = ref
-        else:   # reported, not asserted: the fixture then pins the live run of the checked-out reference only
+        else:   # the NLDrude quantities are odd under time reversal and vanish on Te: both files hold ~1e-17 of noise
             assert q not in ("BerryDipole_FermiSea", "berry_dipole"), q
-            print(f"   (upstream golden file of {q} is not reproduced by the checked-out reference itself: not stored)")
+            assert np.abs(ref).max() < 1e-14 and np.abs(got).max() < 1e-14, q
+            print(f"   ({q} vanishes by symmetry, max |value| {np.abs(got).max():.1e}: upstream file not stored)")
     for q in calcs:
         out["te_" + q] = res.results[q].data
     np.savez_compressed(os.path.join(OUT, "golden_fsea.npz"), **out)

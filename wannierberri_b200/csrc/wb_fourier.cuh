@@ -79,6 +79,18 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
                 }
         }
     }
+    if (in.Ham && L.off_W3[0] >= 0) {   // third comma-derivative: -i T_b T_c T_d H
+        const cplx h = in.Ham[idx];
+        int t = 0;
+        for (int b = 0; b < 3; b++)
+            for (int cc = b; cc < 3; cc++)
+                for (int d = cc; d < 3; d++, t++) {
+                    const double f = T[b] * T[cc] * T[d];
+                    const cplx w = cmake(f * h.y, -f * h.x);
+                    if (L.dH_herm) add_herm(table, cellR, cellmR, E, L.off_W3[t], i, j, nw, w);
+                    else atomic_cadd(&table[cellR * E + L.off_W3[t] + i * nw + j], w);
+                }
+    }
     if (in.AA && L.off_A[0] >= 0) {
         cplx A[3];
         for (int a = 0; a < 3; a++) {

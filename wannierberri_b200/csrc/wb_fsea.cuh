@@ -386,3 +386,118 @@ wb_product_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Der3E (formula/covariant.py:126-151): third derivative of the band energy, trace over a band group G of
+//   W3_mn^{abc} - D_ml^c W_ln^{ab} + W_ml^{ab} D_ln^c        (DerWln.nn, elementary.py:36-43)
+//   + dV_ml^{a:c} D_ln^b + V_ml^a dD_ln^{bc} - dD_ml^{bc} V_ln^a - D_ml^b dV_ln^{a:c}
+// with the generalised derivatives of V (InvMass, elementary.py:28-34) and of D (DerDcov, :56-72) between G and its
+// complement.  Channels: d_a H [3] | d_b d_d H [6, wb_sym6] | d_b d_c d_d H [10, wb_sym10].
+__host__ __device__ __forceinline__ int wb_sym10(int a, int b, int c) {
+    // index of the sorted triple among xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
+    int lo = min(a, min(b, c)), hi = max(a, max(b, c)), mid = a + b + c - lo - hi;
+    const int base[3] = {0, 6, 9};
+    return base[lo] + ((lo == 0) ? (mid == 0 ? hi : (mid == 1 ? 2 + hi : 5)) : (lo == 1) ? (mid == 1 ? hi - 1 : 2) : 0);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_der3e_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall, WbWindow win,
+                       int iV, int iW, int iW3, cplx* __restrict__ scratch, double* __restrict__ ev_label,
+                       double* __restrict__ ev_val) {
+    extern __shared__ __align__(16) double smem_f[];
+    const int n2 = nw * nw;
+    double* Es = smem_f;
+    double* label = Es + nw;
+    double* inv = label + nw;
+    double* vals = inv + n2;           // [nw][27]
+    short* g1 = (short*)(vals + 27 * nw);
+    short* g2 = g1 + nw;
+    cplx* const T1 = scratch + (size_t)blockIdx.x * wb_deromega_scratch_elems(nw);   // dD_ln [l][n - ga][b][c]
+    cplx* const T2 = T1 + (size_t)9 * n2;                                            // dD_ml [m - ga][l][b][c]
+    cplx* const T5 = T2 + (size_t)9 * n2;                                            // dV_ml [m - ga][l][a][c]
+    cplx* const T6 = T5 + (size_t)9 * n2;                                            // dV_ln [l][n - ga][a][c]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = NT / 32;
+    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        __syncthreads();
+        wb_fsea_groups<NT>(Eall, ik, nw, win, Es, label, inv, g1, g2);
+        const cplx* X = xbar + (size_t)ik * nch * n2;
+        const cplx* V = X + (size_t)iV * n2;
+        const cplx* W = X + (size_t)iW * n2;
+        const cplx* W3 = X + (size_t)iW3 * n2;
+        auto Dm = [&](int a, int p, int q) { return cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]); };
+        for (int x = threadIdx.x; x < nw; x += NT) ev_label[ik * nw + x] = label[x];
+        for (int ga = 0; ga < nw; ga++) {
+            if (label[ga] == CUDART_INF) continue;   // uniform
+            const int gb = g2[ga], g = gb - ga;
+            auto in_G = [&](int q) { return q >= ga && q < gb; };
+            // which: 0 dD rows out cols G (T1) | 1 dD rows G cols out (T2) | 2 dV rows G cols out (T5) | 3 dV rows out cols G (T6)
+            for (int x = threadIdx.x; x < 4 * nw * g * 9; x += NT) {
+                const int which = x / (nw * g * 9);
+                int y = x - which * (nw * g * 9);
+                const int bd = y % 9; y /= 9;
+                const int b = bd / 3, d = bd - 3 * b;
+                const bool rows_out = (which == 0 || which == 3);
+                int r, cidx;
+                if (rows_out) { cidx = ga + y % g; r = y / g; }
+                else { cidx = y % nw; r = ga + y / nw; }
+                const bool rG = in_G(r), cG = in_G(cidx);
+                cplx res = cmake(0., 0.);
+                if (rG != cG) {
+                    cplx sum = W[(size_t)wb_sym6(b, d) * n2 + r * nw + cidx];
+                    if (which < 2) {   // DerDcov
+                        for (int p = 0; p < nw; p++) {
+                            if (in_G(p) == rG) {
+                                cfma(sum, V[(size_t)b * n2 + r * nw + p], Dm(d, p, cidx));
+                                cfma(sum, V[(size_t)d * n2 + r * nw + p], Dm(b, p, cidx));
+                            } else {
+                                const cplx z1 = cmul(Dm(b, r, p), V[(size_t)d * n2 + p * nw + cidx]);
+                                const cplx z2 = cmul(Dm(d, r, p), V[(size_t)b * n2 + p * nw + cidx]);
+                                sum = cmake(sum.x - z1.x - z2.x, sum.y - z1.y - z2.y);
+                            }
+                        }
+                        res = cscale(-inv[r * nw + cidx], sum);
+                    } else {           // InvMass: V^{b:d}_rc = W_rc^{bd} - sum_{q in cols} D_rq^d V_qc^b + sum_{p in rows} V_rp^b D_pc^d
+                        for (int p = 0; p < nw; p++) {
+                            if (in_G(p) == rG) cfma(sum, V[(size_t)b * n2 + r * nw + p], Dm(d, p, cidx));
+                            else {
+                                const cplx z = cmul(Dm(d, r, p), V[(size_t)b * n2 + p * nw + cidx]);
+                                sum = cmake(sum.x - z.x, sum.y - z.y);
+                            }
+                        }
+                        res = sum;
+                    }
+                }
+                cplx* T = (which == 0) ? T1 : (which == 1) ? T2 : (which == 2) ? T5 : T6;
+                if (rows_out) T[((size_t)r * g + (cidx - ga)) * 9 + bd] = res;
+                else T[((size_t)(r - ga) * nw + cidx) * 9 + bd] = res;
+            }
+            __syncthreads();
+            // ---- trace: one warp per (m in G, a, b, c), lanes over the partner bands
+            for (int item = warp; item < g * 27; item += nwarp) {
+                const int m = ga + item / 27, abc = item % 27, a = abc / 9, b = (abc / 3) % 3, c = abc % 3;
+                double re = 0.;
+                for (int l = lane; l < nw; l += 32) {
+                    if (in_G(l)) continue;
+                    const cplx Dml_c = Dm(c, m, l), Dlm_c = Dm(c, l, m), Dlm_b = Dm(b, l, m), Dml_b = Dm(b, m, l);
+                    const int ab6 = wb_sym6(a, b);
+                    re += cmul(W[(size_t)ab6 * n2 + m * nw + l], Dlm_c).x - cmul(Dml_c, W[(size_t)ab6 * n2 + l * nw + m]).x;
+                    re += cmul(T5[((size_t)(m - ga) * nw + l) * 9 + 3 * a + c], Dlm_b).x;
+                    re += cmul(V[(size_t)a * n2 + m * nw + l], T1[((size_t)l * g + (m - ga)) * 9 + 3 * b + c]).x;
+                    re -= cmul(T2[((size_t)(m - ga) * nw + l) * 9 + 3 * b + c], V[(size_t)a * n2 + l * nw + m]).x;
+                    re -= cmul(Dml_b, T6[((size_t)l * g + (m - ga)) * 9 + 3 * a + c]).x;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) re += __shfl_xor_sync(0xffffffffu, re, o);
+                if (lane == 0) vals[m * 27 + abc] = re + W3[(size_t)wb_sym10(a, b, c) * n2 + m * nw + m].x;
+            }
+            __syncthreads();
+            for (int abc = threadIdx.x; abc < 27; abc += NT) {
+                double s = 0.;
+                for (int n = ga; n < gb; n++) s += vals[n * 27 + abc];
+                ev_val[((size_t)ik * nw + ga) * 27 + abc] = s;
+            }
+            __syncthreads();
+        }
+    }
+}
