@@ -47,7 +47,10 @@ def main():
                  ahc_zeeman_spin_int=st.AHC_Zeeman_spin(Efermi=Ef, kwargs_formula=dict(external_terms=False)),
                  omegaomega=st.OmegaOmega(Efermi=Ef), nlahc_fsurf=st.NLAHC_FermiSurf(Efermi=Ef),
                  nldrude_sea=st.NLDrude_FermiSea(Efermi=Ef), nldrude_sea_thresh=st.NLDrude_FermiSea(Efermi=Ef, degen_thresh=0.3),
-                 nldrude_sea_tetra=st.NLDrude_FermiSea(Efermi=Ef, tetra=True))
+                 nldrude_sea_tetra=st.NLDrude_FermiSea(Efermi=Ef, tetra=True),
+                 gme_orb_sea=st.GME_orb_FermiSea(Efermi=Ef), gme_orb_sea_thresh=st.GME_orb_FermiSea(Efermi=Ef, degen_thresh=0.3),
+                 gme_orb_sea_int=st.GME_orb_FermiSea(Efermi=Ef, kwargs_formula=dict(external_terms=False)),
+                 gme_orb_sea_tetra=st.GME_orb_FermiSea(Efermi=Ef, tetra=True))
     grid, res = run_ref(rnd, [6, 6, 6], [3, 3, 3], calcs)
     out = dict(rnd_Efermi=Ef, rnd_NK=np.array([6, 6, 6]), rnd_NKFFT=np.array([3, 3, 3]))
     for q in calcs:
@@ -61,7 +64,8 @@ def main():
                  NLDrude_FermiSurf=st.NLDrude_FermiSurf(Efermi=Ef, tetra=True),
                  NLDrude_Fermider2=st.NLDrude_Fermider2(Efermi=Ef, tetra=True),
                  AHC_Zeeman_spin=st.AHC_Zeeman_spin(Efermi=Ef, tetra=True),
-                 NLDrude_FermiSea=st.NLDrude_FermiSea(Efermi=Ef, tetra=True))
+                 NLDrude_FermiSea=st.NLDrude_FermiSea(Efermi=Ef, tetra=True),
+                 GME_orb_FermiSea=st.GME_orb_FermiSea(Efermi=Ef, tetra=True))
     cwd = os.getcwd()
     with tempfile.TemporaryDirectory() as tmp:
         os.chdir(tmp)
@@ -73,7 +77,7 @@ def main():
             os.chdir(cwd)
     out.update(te_Efermi=Ef, te_NK=np.array([3, 3, 4]), te_NKFFT=np.array([1, 1, 4]))
     for q in ("BerryDipole_FermiSea", "berry_dipole", "NLDrude_FermiSurf", "NLDrude_Fermider2", "AHC_Zeeman_spin",
-              "NLDrude_FermiSea"):
+              "NLDrude_FermiSea", "GME_orb_FermiSea"):
         ref = np.load(os.path.join(REF, "tests/reference/integrate_files", f"Te_QE-{q}_iter-0000.npz"))["data"]
         got = res.results[q].data
         err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)

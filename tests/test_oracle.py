@@ -312,6 +312,9 @@ FSEA_CASES = dict(
     omegaomega=("OmegaOmega", {}), nlahc_fsurf=("NLAHC_FermiSurf", {}),
     nldrude_sea=("NLDrude_FermiSea", {}), nldrude_sea_thresh=("NLDrude_FermiSea", dict(degen_thresh=0.3)),
     nldrude_sea_tetra=("NLDrude_FermiSea", dict(tetra=True)),
+    gme_orb_sea=("GME_orb_FermiSea", {}), gme_orb_sea_thresh=("GME_orb_FermiSea", dict(degen_thresh=0.3)),
+    gme_orb_sea_int=("GME_orb_FermiSea", dict(kwargs_formula=dict(external_terms=False))),
+    gme_orb_sea_tetra=("GME_orb_FermiSea", dict(tetra=True)),
 )
 
 
