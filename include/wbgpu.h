@@ -73,7 +73,10 @@ enum {
     WBGPU_SHIFT_CURRENT = 21, /* plan flag only: channels of the Kubo shift current (d_a H, d_b d_d H, A, d_d A_b) */
     WBGPU_DER3E = 22,         /* Der3E  covariant.py:126-151 (third derivative of the band energy: NLDrude_FermiSea) rank 3;
                                  needs d_b d_d H and d_b d_c d_d H */
-    WBGPU_NFORMULA = 23
+    WBGPU_DER_MORB = 23,      /* DerMorb (sign = +1)  covariant.py:463-547 (generalised derivative of the orbital moment:
+                                 GME_orb_FermiSea), rank 2 [c][d], not additive; needs the channels of DerOmega plus BB, CC and
+                                 their comma-derivatives */
+    WBGPU_NFORMULA = 24
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */

@@ -750,6 +750,9 @@ FSEA_CASES = dict(
     omegaomega=("OmegaOmega", {}), nlahc_fsurf=("NLAHC_FermiSurf", {}),
     nldrude_sea=("NLDrude_FermiSea", {}), nldrude_sea_thresh=("NLDrude_FermiSea", dict(degen_thresh=0.3)),
     nldrude_sea_tetra=("NLDrude_FermiSea", dict(tetra=True)),
+    gme_orb_sea=("GME_orb_FermiSea", {}), gme_orb_sea_thresh=("GME_orb_FermiSea", dict(degen_thresh=0.3)),
+    gme_orb_sea_int=("GME_orb_FermiSea", dict(kwargs_formula=dict(external_terms=False))),
+    gme_orb_sea_tetra=("GME_orb_FermiSea", dict(tetra=True)),
 )
 
 
@@ -780,7 +783,8 @@ def test_te_qe_berry_dipole_fermi_sea_vs_upstream_goldens(wb):
                  berry_dipole=st.NLAHC_FermiSea(Efermi=Ef, tetra=True),
                  BerryDipole_FermiSea_notetra=st.BerryDipole_FermiSea(Efermi=Ef),
                  AHC_Zeeman_spin=st.AHC_Zeeman_spin(Efermi=Ef, tetra=True),
-                 NLDrude_FermiSea=st.NLDrude_FermiSea(Efermi=Ef, tetra=True))
+                 NLDrude_FermiSea=st.NLDrude_FermiSea(Efermi=Ef, tetra=True),
+                 GME_orb_FermiSea=st.GME_orb_FermiSea(Efermi=Ef, tetra=True))
     res = wb.run(te, wb.Grid(te, NK=g["te_NK"], NKFFT=g["te_NKFFT"]), calcs, use_irred_kpt=True, symmetrize=True)
     for q in calcs:
         tol = 1e-6 if q == "AHC_Zeeman_spin" else RTOL
@@ -796,14 +800,14 @@ def test_te_qe_berry_dipole_fermi_sea_vs_upstream_goldens(wb):
 def test_fermi_sea_formulae_synthetic(wb, orc, nw, pairs):
     """DerOmega and SpinOmega on synthetic models with the R <-> -R symmetry (hermitian-packed derivative channels):
     exactly degenerate pairs (groups of two bands, D = 0 inside a group) and more bands than a warp, against the oracle."""
-    sysg = wb.synthetic_system(nw, rmax=1, seed=300 + nw, matrices=("Ham", "AA", "SS"), degenerate_pairs=pairs)
+    sysg = wb.synthetic_system(nw, rmax=1, seed=300 + nw, matrices=("Ham", "AA", "SS", "BB", "CC"), degenerate_pairs=pairs)
     rng = np.random.default_rng(11 + nw)
     nR = sysg.rvec.nRvec
     for key, tail in (("SA", (3, 3)), ("SHA", (3, 3))):
         shape = (nR, nw, nw) + tail
         sysg.set_R_mat(key, 0.1 * (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)))
     syso = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart,
-                            {k: sysg.get_R_mat(k) for k in ("Ham", "AA", "SS", "SA", "SHA")})
+                            {k: sysg.get_R_mat(k) for k in ("Ham", "AA", "SS", "SA", "SHA", "BB", "CC")})
     NKFFT, dK = [2, 2, 2], [0.05, 0.11, 0.02]
     Ef = np.linspace(-1., 1., 21)
     data = wb.Data_K_R(sysg, dK=dK, grid=wb.Grid(sysg, NKdiv=[1, 1, 1], NKFFT=NKFFT))
@@ -817,6 +821,8 @@ def test_fermi_sea_formulae_synthetic(wb, orc, nw, pairs):
     assert relerr(got, orc.SHC_static(odata, Ef, kwargs_formula=dict(spin_current_type="ryoo"))) < RTOL
     got = st.NLDrude_FermiSea(Efermi=Ef)(data).data
     assert relerr(got, orc.NLDrude_FermiSea(odata, Ef)) < RTOL
+    got = st.GME_orb_FermiSea(Efermi=Ef)(data).data
+    assert relerr(got, orc.GME_orb_FermiSea(odata, Ef)) < RTOL
     got = st.Hall_classic_FermiSea(Efermi=Ef)(data).data
     assert relerr(got, orc.Hall_classic_FermiSea(odata, Ef)) < RTOL
     got = st.AHC_Zeeman_spin(Efermi=Ef)(data).data

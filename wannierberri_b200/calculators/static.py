@@ -21,7 +21,7 @@ _TR_INV = {  # transformTR, transformInv of the formulae (covariant.py)
     # products: TransformProduct of the factors (V: odd, odd; InvMass: ident, ident; Omega, Spin: odd, ident)
     _lib.DER_SPIN: ("ident", "odd"), _lib.VEL_VEL_VEL: ("odd", "odd"), _lib.MASS_VEL: ("odd", "odd"),
     _lib.MASS_MASS: ("ident", "ident"), _lib.VEL_MASS_VEL: ("ident", "ident"), _lib.OMEGA_S: ("ident", "ident"),
-    _lib.OMEGA_OMEGA: ("ident", "ident"), _lib.DER3E: ("odd", "odd"),
+    _lib.OMEGA_OMEGA: ("ident", "ident"), _lib.DER3E: ("odd", "odd"), _lib.DER_MORB: ("ident", "odd"),
 }
 _ALPHA, _BETA = np.array([1, 2, 0]), np.array([2, 0, 1])   # utility.py:45-46
 
@@ -346,6 +346,24 @@ class NLDrude_FermiSurf(StaticCalculator):
         super().__init__(constant_factor=constant_factor, **kwargs)
 
 
+class GME_orb_FermiSea(StaticCalculator):
+    r"""Gyrotropic tensor orbital part (:math:`A`), Fermi sea integral (static.py:284-300)
+
+        | Output: :math:`K^{orb}_{\alpha :\mu} = -\int [dk] \partial_\alpha m_\mu f`, :math:`m = H + G - 2E_f \cdot \Omega`"""
+
+    def __init__(self, constant_factor=factors.factor_gme_orb, **kwargs):
+        self.Formula = _lib.DER_MORB
+        self.fder = 0
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+    def specs(self):   # DerMorb and BerryDipole_FermiSea(constant_factor = same)
+        return [self._spec(), self._spec(formula=_lib.DER_OMEGA)]
+
+    def combine(self, arrays, cell_volume):
+        Hplus, Om = arrays
+        return np.ascontiguousarray((Hplus - 2 * Om * self.Efermi[:, None, None]).swapaxes(1, 2))
+
+
 class NLDrude_FermiSea(StaticCalculator):
     r"""Drude conductivity (:math:`S^2/A`), Fermi sea integral of the third derivative of the band energy (static.py:519-529)"""
 
@@ -385,7 +403,7 @@ class OmegaOmega(StaticCalculator):
 _BY_NAME = {c.__name__: c for c in (DOS, CumDOS, Spin, AHC, Morb, BerryDipole_FermiSurf, GME_orb_FermiSurf,
                                     GME_spin_FermiSurf, Ohmic_FermiSurf, Ohmic_FermiSea, BerryDipole_FermiSea,
                                     NLAHC_FermiSea, SHC, NLAHC_FermiSurf, GME_spin_FermiSea, Hall_classic_FermiSurf,
-                                    Hall_classic_FermiSea, NLDrude_FermiSurf, NLDrude_Fermider2, NLDrude_FermiSea, AHC_Zeeman_spin,
+                                    Hall_classic_FermiSea, NLDrude_FermiSurf, NLDrude_Fermider2, NLDrude_FermiSea, GME_orb_FermiSea, AHC_Zeeman_spin,
                                     OmegaOmega)}
 
 

@@ -63,6 +63,7 @@ struct WbLayout {
     // comma-derivatives d_d A_b and d_d rotA_c (index 3 b + d), hermitian like A and rotA (data_K_R.py:84-87)
     int off_dA[9], off_dO[9];
     int off_dS[9];   // d_d S_s, hermitian
+    int off_dB[9], off_dC[9];   // d_d B_b, d_d C_c (full)
     int off_W3[10];  // d_b d_c d_d H, sorted triples xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz; packed like d_a H
 };
 

@@ -121,6 +121,14 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
         for (int a = 0; a < 3; a++) atomic_cadd(&table[cellR * E + L.off_B[a] + i * nw + j], in.BB[idx * 3 + a]);
     if (in.CC && L.off_C[0] >= 0)
         for (int a = 0; a < 3; a++) atomic_cadd(&table[cellR * E + L.off_C[a] + i * nw + j], in.CC[idx * 3 + a]);
+    if (in.BB && in.CC && L.off_dB[0] >= 0)   // i T_d B_b, i T_d C_c
+        for (int a = 0; a < 3; a++) {
+            const cplx bv = in.BB[idx * 3 + a], cv = in.CC[idx * 3 + a];
+            for (int d = 0; d < 3; d++) {
+                atomic_cadd(&table[cellR * E + L.off_dB[3 * a + d] + i * nw + j], cmake(-T[d] * bv.y, T[d] * bv.x));
+                atomic_cadd(&table[cellR * E + L.off_dC[3 * a + d] + i * nw + j], cmake(-T[d] * cv.y, T[d] * cv.x));
+            }
+        }
     if (in.SS && L.off_S[0] >= 0)
         for (int a = 0; a < 3; a++) add_herm(table, cellR, cellmR, E, L.off_S[a], i, j, nw, in.SS[idx * 3 + a]);
     if (in.SS && L.off_dS[0] >= 0)

@@ -501,3 +501,248 @@ wb_der3e_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// DerMorb (formula/covariant.py:463-547; GME_orb_FermiSea): DerMorb_H plus Eav * DerOmega + (Omega V + V Omega) / 2.
+// Not additive (static.py:109-117): T(x) = trace with inn = [0, x), out = [x, nw) at every edge x of a band group, value
+// of the group [a, b) = T(b) - T(a).  Per edge the generalised derivatives between inn and out are formed as in
+// wb_deromega_events_kernel (dD, dA) plus dB.ln, the two V-weighted double sums and the Omega block of inn.
+struct WbDerMorbChans {
+    int iV, iW, iA, iO, idA, idO, iB, idB, iC, idC;   // [3] [6] [3] [3] [9] [9] [3] [9] [3] [9]
+};
+__host__ __device__ inline size_t wb_dermorb_scratch_elems(int nw) { return (size_t)66 * nw * nw; }
+__host__ inline size_t wb_dermorb_smem_bytes(int nw) {
+    return sizeof(double) * (2 * (size_t)nw + (size_t)nw * nw + 9 * (size_t)nw + 9 * ((size_t)nw + 1)) + 2 * nw * sizeof(short) +
+           (nw + 1) * sizeof(int) + 64;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+wb_dermorb_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall,
+                         WbWindow win, WbDerMorbChans C, int internal, int external, cplx* __restrict__ scratch,
+                         double* __restrict__ ev_label, double* __restrict__ ev_val) {
+    extern __shared__ __align__(16) double smem_f[];
+    const int n2 = nw * nw;
+    double* Es = smem_f;
+    double* label = Es + nw;
+    double* inv = label + nw;
+    double* vals = inv + n2;                 // [nw][9]
+    double* Tedge = vals + 9 * nw;           // [nw + 1][9]
+    short* g1 = (short*)(Tedge + 9 * (nw + 1));
+    short* g2 = g1 + nw;
+    int* edge = (int*)(g2 + nw + (nw & 1) * 1);
+    edge = (int*)(((uintptr_t)edge + 3) & ~(uintptr_t)3);
+    cplx* const T1 = scratch + (size_t)blockIdx.x * wb_dermorb_scratch_elems(nw);   // dD_ln [l][n][b][d]
+    cplx* const T2 = T1 + (size_t)9 * n2;    // dD_ml [m][l][a][d]
+    cplx* const T3 = T2 + (size_t)9 * n2;    // dA_ln [l][n][b][d]
+    cplx* const T4 = T3 + (size_t)9 * n2;    // dA_pn [p][n][b][d]
+    cplx* const T7 = T4 + (size_t)9 * n2;    // dB_ln [l][n][b][d]
+    cplx* const T8 = T7 + (size_t)9 * n2;    // sum_{l in out} V_pl^d D_lm^beta(c)  [p][m][d][c]   (p in out)
+    cplx* const T9 = T8 + (size_t)9 * n2;    // sum_{l in inn} V_pl^d A_lm^beta(c)  [p][m][d][c]   (p in inn)
+    cplx* const T10 = T9 + (size_t)9 * n2;   // Omega_ml^c [m][l][c]   (m, l in inn)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = NT / 32;
+    for (long ik = blockIdx.x; ik < nk; ik += gridDim.x) {
+        __syncthreads();
+        wb_fsea_groups<NT>(Eall, ik, nw, win, Es, label, inv, g1, g2);
+        for (int x = threadIdx.x; x <= nw; x += NT) edge[x] = 0;
+        for (int x = threadIdx.x; x < 9 * (nw + 1); x += NT) Tedge[x] = 0.;
+        __syncthreads();
+        for (int x = threadIdx.x; x < nw; x += NT)
+            if (label[x] != CUDART_INF) { edge[x] = 1; edge[g2[x]] = 1; }
+        __syncthreads();
+        const cplx* X = xbar + (size_t)ik * nch * n2;
+        const cplx* V = X + (size_t)C.iV * n2;
+        const cplx* W = X + (size_t)C.iW * n2;
+        const cplx* A = X + (size_t)C.iA * n2;
+        const cplx* O = X + (size_t)C.iO * n2;
+        const cplx* dAc = X + (size_t)C.idA * n2;
+        const cplx* dOc = X + (size_t)C.idO * n2;
+        const cplx* B = X + (size_t)C.iB * n2;
+        const cplx* dBc = X + (size_t)C.idB * n2;
+        const cplx* Cm = X + (size_t)C.iC * n2;
+        const cplx* dCc = X + (size_t)C.idC * n2;
+        auto Dm = [&](int a, int p, int q) { return cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]); };
+        for (int x = threadIdx.x; x < nw; x += NT) ev_label[ik * nw + x] = label[x];
+        for (int xe = 1; xe <= nw; xe++) {
+            if (!edge[xe]) continue;   // uniform
+            const int g = xe;          // inn = [0, g), out = [g, nw)
+            auto in_G = [&](int q) { return q < g; };
+            // ---- T1 / T2: DerDcov between out and inn (as in wb_deromega_events_kernel)
+            for (int x = threadIdx.x; x < 2 * nw * g * 9; x += NT) {
+                const int which = x / (nw * g * 9);
+                int y = x - which * (nw * g * 9);
+                const int bd = y % 9; y /= 9;
+                const int b = bd / 3, d = bd - 3 * b;
+                int r, cidx;
+                if (which == 0) { cidx = y % g; r = y / g; }
+                else { cidx = y % nw; r = y / nw; }
+                const bool rG = in_G(r), cG = in_G(cidx);
+                cplx res = cmake(0., 0.);
+                if (rG != cG) {
+                    cplx sum = W[(size_t)wb_sym6(b, d) * n2 + r * nw + cidx];
+                    for (int p = 0; p < nw; p++) {
+                        if (in_G(p) == rG) {
+                            cfma(sum, V[(size_t)b * n2 + r * nw + p], Dm(d, p, cidx));
+                            cfma(sum, V[(size_t)d * n2 + r * nw + p], Dm(b, p, cidx));
+                        } else {
+                            const cplx z1 = cmul(Dm(b, r, p), V[(size_t)d * n2 + p * nw + cidx]);
+                            const cplx z2 = cmul(Dm(d, r, p), V[(size_t)b * n2 + p * nw + cidx]);
+                            sum = cmake(sum.x - z1.x - z2.x, sum.y - z1.y - z2.y);
+                        }
+                    }
+                    res = cscale(-inv[r * nw + cidx], sum);
+                }
+                if (which == 0) T1[((size_t)r * g + cidx) * 9 + bd] = res;
+                else T2[((size_t)r * nw + cidx) * 9 + bd] = res;
+            }
+            // ---- T8 (p in out) / T9 (p in inn): sum_l V_pl^d X_lm^beta(c),  X = D over l in out / A over l in inn
+            for (int x = threadIdx.x; x < nw * g * 9; x += NT) {
+                int y = x;
+                const int dc = y % 9; y /= 9;
+                const int d = dc / 3, c = dc - 3 * d, be = WB_BETA(c);
+                const int m = y % g, p = y / g;
+                cplx sum = cmake(0., 0.);
+                if (!in_G(p)) {
+                    if (internal)
+                        for (int l = g; l < nw; l++) cfma(sum, V[(size_t)d * n2 + p * nw + l], Dm(be, l, m));
+                    T8[((size_t)p * g + m) * 9 + dc] = sum;
+                } else {
+                    if (external)
+                        for (int l = 0; l < g; l++) cfma(sum, V[(size_t)d * n2 + p * nw + l], A[(size_t)be * n2 + l * nw + m]);
+                    T9[((size_t)p * g + m) * 9 + dc] = sum;
+                }
+            }
+            if (external) {
+                // ---- T3 = dA.ln, T4 = dA.nn, T7 = dB.ln (Matrix_GenDer_ln)
+                for (int x = threadIdx.x; x < 2 * nw * g * 9; x += NT) {
+                    const int which = x / (nw * g * 9);   // 0: A, 1: B (ln block only)
+                    int y = x - which * (nw * g * 9);
+                    const int bd = y % 9; y /= 9;
+                    const int b = bd / 3, d = bd - 3 * b;
+                    const int n = y % g, l = y / g;
+                    const cplx* Xb = (which == 0 ? A : B) + (size_t)b * n2;
+                    cplx sum = (which == 0 ? dAc : dBc)[(size_t)bd * n2 + l * nw + n];
+                    if (!in_G(l)) {
+                        for (int p = 0; p < nw; p++) {
+                            if (in_G(p)) {
+                                const cplx z = cmul(Dm(d, l, p), Xb[p * nw + n]);
+                                sum = cmake(sum.x - z.x, sum.y - z.y);
+                            } else cfma(sum, Xb[l * nw + p], Dm(d, p, n));
+                        }
+                        (which == 0 ? T3 : T7)[((size_t)l * g + n) * 9 + bd] = sum;
+                    } else if (which == 0) {
+                        for (int q = g; q < nw; q++) {
+                            const cplx z = cmul(Dm(d, l, q), Xb[q * nw + n]);
+                            sum = cmake(sum.x - z.x, sum.y - z.y);
+                            cfma(sum, Xb[l * nw + q], Dm(d, q, n));
+                        }
+                        T4[((size_t)l * g + n) * 9 + bd] = sum;
+                    }
+                }
+            }
+            // ---- T10: Omega block of inn (covariant.py:161-203)
+            for (int x = threadIdx.x; x < g * g * 3; x += NT) {
+                const int comp = x % 3, mn = x / 3, m = mn / g, n = mn % g;
+                const int al = WB_ALPHA(comp), be = WB_BETA(comp);
+                cplx val = cmake(0., 0.);
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    const int M = side ? n : m, Lb = side ? m : n;
+                    cplx S = cmake(0., 0.);
+                    for (int l = 0; l < nw; l++) {
+                        if (in_G(l)) {
+                            if (external) {
+                                const cplx z = cmul(A[(size_t)al * n2 + M * nw + l], A[(size_t)be * n2 + l * nw + Lb]);
+                                S.x += z.y; S.y -= z.x;
+                            }
+                            continue;
+                        }
+                        const cplx DMa = Dm(al, M, l), DMb = Dm(be, M, l);
+                        if (internal) {
+                            const cplx z = cmul(DMa, Dm(be, l, Lb));
+                            S.x += z.y; S.y -= z.x;
+                        }
+                        if (external) {
+                            const cplx z = csub(cmul(DMb, A[(size_t)al * n2 + l * nw + Lb]), cmul(DMa, A[(size_t)be * n2 + l * nw + Lb]));
+                            S = cadd(S, z);
+                        }
+                    }
+                    if (external) {
+                        const cplx o = O[(size_t)comp * n2 + M * nw + Lb];
+                        S.x += 0.5 * o.x; S.y += 0.5 * o.y;
+                    }
+                    val = side ? cmake(val.x + S.x, val.y - S.y) : S;
+                }
+                T10[(size_t)(m * g + n) * 3 + comp] = val;
+            }
+            __syncthreads();
+            // ---- trace: one warp per (m in inn, c, d)
+            for (int item = warp; item < g * 9; item += nwarp) {
+                const int m = item / 9, cd = item % 9, c = cd / 3, d = cd - 3 * c;
+                const int dc = 3 * d + c, al = WB_ALPHA(c);
+                double SH = 0., SO = 0., OV = 0.;   // Re tr of DerMorb_H, of the DerOmega diagonal (before the factor 2), of Omega V
+                for (int l = lane; l < nw; l += 32) {
+                    const bool lG = in_G(l);
+                    if (!lG) {
+                        if (internal) SH += 2. * cmul(Dm(al, m, l), T8[((size_t)l * g + m) * 9 + dc]).y;   // Re(-2i z) = 2 Im z
+                        if (external) {
+                            SH += cmul(Cm[(size_t)c * n2 + m * nw + l], Dm(d, l, m)).x - cmul(Dm(d, m, l), Cm[(size_t)c * n2 + l * nw + m]).x;
+                            SO += 0.5 * (cmul(O[(size_t)c * n2 + m * nw + l], Dm(d, l, m)).x - cmul(Dm(d, m, l), O[(size_t)c * n2 + l * nw + m]).x);
+                        }
+                    } else {
+                        if (external) SH += 2. * cmul(A[(size_t)al * n2 + m * nw + l], T9[((size_t)l * g + m) * 9 + dc]).y;
+                        OV += cmul(T10[(size_t)(m * g + l) * 3 + c], V[(size_t)d * n2 + l * nw + m]).x;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        const int a = t ? WB_BETA(c) : WB_ALPHA(c), b = t ? WB_ALPHA(c) : WB_BETA(c);
+                        const double sg = t ? -1. : 1.;
+                        if (!lG) {
+                            const cplx Dml = Dm(a, m, l);
+                            const cplx t1 = T1[((size_t)l * g + m) * 9 + 3 * b + d];
+                            if (internal) {
+                                const double im = cmul(Dml, t1).y;
+                                SH += 2. * sg * Es[l] * im;   // Re(-2i s E_l D dD)
+                                SO += sg * im;                // Re(-i s D dD)
+                            }
+                            if (external) {
+                                SH -= 2. * sg * cmul(Dml, T7[((size_t)l * g + m) * 9 + 3 * b + d]).x;
+                                SH -= 2. * sg * cmulc(t1, B[(size_t)a * n2 + l * nw + m]).x;   // conj(B_lm^a) dD_lm
+                                SO -= sg * (cmul(Dml, T3[((size_t)l * g + m) * 9 + 3 * b + d]).x +
+                                            cmul(T2[((size_t)m * nw + l) * 9 + 3 * a + d], A[(size_t)b * n2 + l * nw + m]).x);
+                            }
+                        } else if (external) {
+                            const double im = cmul(A[(size_t)a * n2 + m * nw + l], T4[((size_t)l * g + m) * 9 + 3 * b + d]).y;
+                            SH += 2. * sg * Es[l] * im;       // Re(-2i s A_ml E_l dA_lm)
+                            SO += sg * im;                    // Re(-i s A_ml dA_lm)
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    SH += __shfl_xor_sync(0xffffffffu, SH, o);
+                    SO += __shfl_xor_sync(0xffffffffu, SO, o);
+                    OV += __shfl_xor_sync(0xffffffffu, OV, o);
+                }
+                if (lane == 0) {
+                    if (external) {
+                        SH += dCc[(size_t)cd * n2 + m * nw + m].x;
+                        SO += 0.5 * dOc[(size_t)cd * n2 + m * nw + m].x;
+                    }
+                    vals[m * 9 + cd] = SH + Es[m] * 2. * SO + OV;
+                }
+            }
+            __syncthreads();
+            for (int cd = threadIdx.x; cd < 9; cd += NT) {
+                double s = 0.;
+                for (int n = 0; n < g; n++) s += vals[n * 9 + cd];
+                Tedge[xe * 9 + cd] = s;
+            }
+            __syncthreads();
+        }
+        for (int x = threadIdx.x; x < nw * 9; x += NT) {
+            const int n0 = x / 9, cd = x - 9 * n0;
+            if (label[n0] != CUDART_INF) ev_val[((size_t)ik * nw + n0) * 9 + cd] = Tedge[g2[n0] * 9 + cd] - Tedge[n0 * 9 + cd];
+        }
+    }
+}

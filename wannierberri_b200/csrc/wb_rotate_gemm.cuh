@@ -17,8 +17,8 @@
 
 struct WbChanList {
     int n;
-    int off[40];    // record offset (complex elements) of the matrix
-    int herm[40];   // upper-triangle packed
+    int off[64];    // record offset (complex elements) of the matrix
+    int herm[64];   // upper-triangle packed
 };
 
 __device__ __forceinline__ void wb_dmma_acc(double& d0, double& d1, double a, double b) {

@@ -266,7 +266,7 @@ static int formula_rank(int f) {
         case WBGPU_IDENTITY: return 0;
         case WBGPU_OMEGA: case WBGPU_MORB_HPM: case WBGPU_SPIN: return 1;
         case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: case WBGPU_VEL_VEL: case WBGPU_INV_MASS:
-        case WBGPU_DER_OMEGA: case WBGPU_DER_SPIN: case WBGPU_OMEGA_S: case WBGPU_OMEGA_OMEGA: return 2;
+        case WBGPU_DER_OMEGA: case WBGPU_DER_SPIN: case WBGPU_OMEGA_S: case WBGPU_OMEGA_OMEGA: case WBGPU_DER_MORB: return 2;
         case WBGPU_SHC_RYOO: case WBGPU_SHC_QIAO: case WBGPU_SHC_SIMPLE:   // SpinOmega
         case WBGPU_VEL_VEL_VEL: case WBGPU_MASS_VEL: case WBGPU_DER3E: return 3;
         case WBGPU_MASS_MASS: case WBGPU_VEL_MASS_VEL: return 4;
@@ -349,10 +349,11 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
             prod_omega |= product_has(f, 3);
             prod_spin |= product_has(f, 4) || product_has(f, 5);
         }
-    need_dH = need_dH || prod_any || has(WBGPU_DER3E);
+    need_dH = need_dH || prod_any || has(WBGPU_DER3E) || has(WBGPU_DER_MORB);
+    const bool der_om = has(WBGPU_DER_OMEGA) || has(WBGPU_DER_MORB);   // channels of DerOmega
     bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) || has(WBGPU_KUBO);
-    bool need_A = (berry || shc || has(WBGPU_DER_OMEGA) || prod_omega || has(WBGPU_SHIFT_CURRENT)) && external_terms;
-    bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS)) && external_terms;
+    bool need_A = (berry || shc || der_om || prod_omega || has(WBGPU_SHIFT_CURRENT)) && external_terms;
+    bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS) || has(WBGPU_DER_MORB)) && external_terms;
     bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN) || shc || prod_spin;
     if (has(WBGPU_SHC_RYOO) && (!c->d_XR[WBGPU_SA] || !c->d_XR[WBGPU_SHA]))
         return set_err("wbgpu_plan: R-matrices 'SA','SHA' are not set (SHC_type='ryoo')");
@@ -400,18 +401,20 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     for (int a = 0; a < 3; a++) L.off_dH[a] = need_dH ? take(dH_herm) : -1;
     for (int a = 0; a < 3; a++) L.off_A[a] = need_A ? take(true) : -1;
     bool need_O = need_A && (has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) ||
-                             has(WBGPU_DER_OMEGA) || prod_omega);
+                             der_om || prod_omega);
     for (int a = 0; a < 3; a++) L.off_O[a] = need_O ? take(true) : -1;
     for (int a = 0; a < 3; a++) L.off_B[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_C[a] = need_BC ? take(false) : -1;
     for (int a = 0; a < 3; a++) L.off_S[a] = need_S ? take(true) : -1;
     for (int a = 0; a < 6; a++)
-        L.off_W[a] = (has(WBGPU_INV_MASS) || has(WBGPU_DER_OMEGA) || prod_mass || has(WBGPU_SHIFT_CURRENT) || has(WBGPU_DER3E))
+        L.off_W[a] = (has(WBGPU_INV_MASS) || der_om || prod_mass || has(WBGPU_SHIFT_CURRENT) || has(WBGPU_DER3E))
                          ? take(dH_herm) : -1;
     for (int a = 0; a < 10; a++) L.off_W3[a] = has(WBGPU_DER3E) ? take(dH_herm) : -1;
     for (int a = 0; a < 9; a++) L.off_dS[a] = has(WBGPU_DER_SPIN) ? take(true) : -1;
-    for (int a = 0; a < 9; a++) L.off_dA[a] = ((has(WBGPU_DER_OMEGA) || has(WBGPU_SHIFT_CURRENT)) && need_A) ? take(true) : -1;
-    for (int a = 0; a < 9; a++) L.off_dO[a] = (has(WBGPU_DER_OMEGA) && need_A) ? take(true) : -1;
+    for (int a = 0; a < 9; a++) L.off_dA[a] = ((der_om || has(WBGPU_SHIFT_CURRENT)) && need_A) ? take(true) : -1;
+    for (int a = 0; a < 9; a++) L.off_dO[a] = (der_om && need_A) ? take(true) : -1;
+    for (int a = 0; a < 9; a++) L.off_dB[a] = (has(WBGPU_DER_MORB) && need_BC) ? take(false) : -1;
+    for (int a = 0; a < 9; a++) L.off_dC[a] = (has(WBGPU_DER_MORB) && need_BC) ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_SA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_SHA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_SR[a] = has(WBGPU_SHC_QIAO) ? take(false) : -1;
@@ -939,6 +942,39 @@ static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
         }
         return 0;
     }
+    if (formula == WBGPU_DER_MORB) {
+        if (L.off_dH[0] < 0 || L.off_W[0] < 0 ||
+            (ext && (L.off_A[0] < 0 || L.off_O[0] < 0 || L.off_dA[0] < 0 || L.off_B[0] < 0 || L.off_dB[0] < 0)))
+            return set_err("scan: the plan does not hold the channels of DerMorb");
+        WbDerMorbChans C;
+        C.iA = C.iO = C.idA = C.idO = C.iB = C.idB = C.iC = C.idC = 0;
+        C.iV = addn(L.off_dH, 3, L.dH_herm);
+        C.iW = addn(L.off_W, 6, L.dH_herm);
+        if (ext) {
+            C.iA = addn(L.off_A, 3, 1); C.iO = addn(L.off_O, 3, 1); C.idA = addn(L.off_dA, 9, 1); C.idO = addn(L.off_dO, 9, 1);
+            C.iB = addn(L.off_B, 3, 0); C.idB = addn(L.off_dB, 9, 0); C.iC = addn(L.off_C, 3, 0); C.idC = addn(L.off_dC, 9, 0);
+        }
+        const long chunk = xbar_chunk(c, ch.n, nk);
+        if (ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * n2)) return 1;
+        const size_t per_cta = sizeof(cplx) * wb_dermorb_scratch_elems(nw);
+        const long nblk_max = std::max(32L, std::min((long)sms * 4, (long)(1.5e9 / (double)per_cta)));
+        if (ensure(&c->d_mx, &c->mx_cap, per_cta * (size_t)nblk_max)) return 1;
+        const size_t smem = wb_dermorb_smem_bytes(nw);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(wb_dermorb_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (long k0 = 0; k0 < nk; k0 += chunk) {
+            const long n = std::min(chunk, nk - k0);
+            if (rotate_gemm(c, ch, k0, n)) return 1;
+            WbWindow wloc = G.win;
+            if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
+            wb_dermorb_events_kernel<NT><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, C, G.ev.internal_terms, ext ? 1 : 0, (cplx*)c->d_mx,
+                c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * 9);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
+        return 0;
+    }
     if (formula == WBGPU_DER3E) {
         if (L.off_dH[0] < 0 || L.off_W[0] < 0 || L.off_W3[0] < 0) return set_err("scan: the plan does not hold the channels of Der3E");
         const int iV = addn(L.off_dH, 3, L.dH_herm), iW = addn(L.off_W, 6, L.dH_herm), iW3 = addn(L.off_W3, 10, L.dH_herm);
@@ -1317,7 +1353,7 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
     LH.nw = nw; LH.ntri = nw * (nw + 1) / 2; LH.E = LH.ntri; LH.off_H = 0; LH.dH_herm = 0;
     for (int a = 0; a < 3; a++) LH.off_dH[a] = LH.off_A[a] = LH.off_O[a] = LH.off_B[a] = LH.off_C[a] = LH.off_S[a] = -1;
     for (int a = 0; a < 6; a++) LH.off_W[a] = -1;
-    for (int a = 0; a < 9; a++) LH.off_SA[a] = LH.off_SHA[a] = LH.off_SR[a] = LH.off_SHR[a] = LH.off_dA[a] = LH.off_dO[a] = LH.off_dS[a] = -1;
+    for (int a = 0; a < 9; a++) LH.off_SA[a] = LH.off_SHA[a] = LH.off_SR[a] = LH.off_SHR[a] = LH.off_dA[a] = LH.off_dO[a] = LH.off_dS[a] = LH.off_dB[a] = LH.off_dC[a] = -1;
     for (int a = 0; a < 3; a++) LH.off_SH[a] = -1;
     for (int a = 0; a < 10; a++) LH.off_W3[a] = -1;
     const size_t ncell = (size_t)c->nbox.x * c->nbox.y * c->nbox.z;
