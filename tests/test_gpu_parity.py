@@ -1011,8 +1011,10 @@ def test_errors(wb, fe):
         eng.scan(np.zeros((1, 3)), np.ones(1), st.AHC(Efermi=np.linspace(0, 1, 3)).specs())  # not in the plan
     with pytest.raises(NotImplementedError):
         st.AHC(Efermi=np.linspace(0, 1, 3), tetra=True, hole_like=True)
-    with pytest.raises(NotImplementedError):
-        wb.calculators.dynamic.OpticalConductivity(Efermi=np.linspace(0, 1, 3), omega=np.linspace(0, 1, 3), kBT=0.01)
+    with pytest.raises(ValueError):
+        wb.calculators.dynamic.OpticalConductivity(Efermi=np.linspace(0, 1, 3), omega=np.linspace(0, 1, 3), kBT=-0.01)
+    with pytest.raises(NotImplementedError):   # the Fermi axis of a Kubo scan must be ascending
+        wb.calculators.dynamic.OpticalConductivity(Efermi=np.array([1., 0.]), omega=np.linspace(0, 1, 3))
     with pytest.raises(ValueError):
         bare = wb.System_R(fe.real_lattice, fe.rvec.iRvec, fe.wannier_centers_cart)
         bare.get_R_mat("Ham")
