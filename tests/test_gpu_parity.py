@@ -597,6 +597,37 @@ def test_full_size_properties(wb, fe):
     assert relerr(ahc_g, ahc) < 1e-10
 
 
+def test_full_size_properties_next_rows(wb, te):
+    """The kernels of the next-row formulae at BASELINE-size K-blocks (Te, 24 WF, NKFFT = 20^3): the rotated matrices of
+    one call are processed in several sub-batches (33 .. 57 matrices per k-point), so additivity over the K-blocks of a
+    call checks the sub-batch offsets; and physical identities: the generalised derivative of the Berry curvature summed
+    over ALL bands vanishes, the rank-3 Kubo scans are additive as well."""
+    st, dyn = wb.calculators.static, wb.calculators.dynamic
+    Ef = np.linspace(-5.0, 25.0, 301)   # brackets the whole band structure of the Te model
+    shifts, factors = wb.Grid(te, NKdiv=[10, 10, 10], NKFFT=[20, 20, 20]).K_arrays()
+    sel = slice(500, 503)
+    w = np.full(3, 1. / 3)
+    calcs = [st.BerryDipole_FermiSea(Efermi=Ef), st.GME_orb_FermiSea(Efermi=Ef), st.NLDrude_FermiSea(Efermi=Ef),
+             st.AHC_Zeeman_spin(Efermi=Ef), st.SHC(Efermi=Ef, kwargs_formula=dict(spin_current_type="simple"))]
+    specs = [s for c in calcs for s in c.specs()]
+    eng = wb.Engine(te)
+    eng.plan([20, 20, 20], [s.formula for s in specs])
+    whole = eng.scan(shifts[sel], w, specs)
+    parts = [eng.scan(shifts[500 + i:501 + i], w[:1], specs) for i in range(3)]
+    for i, s in enumerate(specs):
+        assert relerr(sum(p[i] for p in parts), whole[i]) < 1e-11, i
+    bd = whole[0]
+    assert np.abs(bd[-1]).max() < 1e-9 * np.abs(bd).max()   # all bands occupied: d_d Omega_c summed over all bands = 0
+    s32 = wb.synthetic_system(32, rmax=2, seed=20261017)
+    sh32, _ = wb.Grid(s32, NKdiv=[8, 8, 8], NKFFT=[16, 16, 16]).K_arrays()
+    sc = dyn.ShiftCurrent(Efermi=np.linspace(-1, 1, 20), omega=np.linspace(0, 5, 70), sc_eta=0.05, smr_fixed_width=0.1, kBT=0.02)
+    e32 = wb.Engine(s32)
+    e32.plan([16, 16, 16], [sc.spec().formula_flag], external_terms=True)
+    whole = e32.kubo_scan(sh32[7:9], np.ones(2), sc.spec(), sc.Efermi, sc.omega)
+    parts = [e32.kubo_scan(sh32[7 + i:8 + i], np.ones(1), sc.spec(), sc.Efermi, sc.omega) for i in range(2)]
+    assert relerr(parts[0] + parts[1], whole) < 1e-11
+
+
 def test_run_symmetric_vs_upstream_golden(wb):
     """The reference's default run mode (use_irred_kpt=True, symmetrize=True): symmetry-reduced K-list, results
     symmetrised over the 16 operations of the magnetic point group of bcc Fe -- against the reference's own golden
