@@ -150,3 +150,44 @@ def test_symmetry_reduced_k_list_bit_exact():
     assert np.allclose(r.symmetrized(fe.pointgroup).data, np.tile(np.array([0., 0., 3.]), (3, 1)), atol=1e-14)
     with pytest.raises(ValueError):
         wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"), pointgroup=["C3z"])   # not a symmetry of the bcc cell
+
+
+def test_adapt_reference_calculator_instances():
+    """run() accepts instances of the reference's own calculator classes: every static and Kubo
+    class is recognised by name and converted with the same constant factor, formula and options.  Container-only: skipped
+    where the reference tree is absent (GPU box)."""
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "wannierberri")):
+        pytest.skip("reference tree not present")
+    stubs = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "stubs")
+    sys.path[:0] = [ref, stubs]
+    try:
+        from wannierberri import calculators as calc
+    except Exception as err:   # pragma: no cover
+        pytest.skip(f"reference not importable: {err}")
+    finally:
+        sys.path.remove(ref)
+        sys.path.remove(stubs)
+    from wannierberri_b200.calculators import static as st, dynamic as dy
+    Ef, om = np.linspace(0, 1, 5), np.linspace(0, 1, 4)
+    S, D = calc.static, calc.dynamic
+    names = ["DOS", "CumDOS", "Spin", "AHC", "Morb", "BerryDipole_FermiSurf", "NLAHC_FermiSurf", "GME_orb_FermiSurf",
+             "GME_spin_FermiSurf", "Ohmic_FermiSurf", "Ohmic_FermiSea", "BerryDipole_FermiSea", "NLAHC_FermiSea", "GME_spin_FermiSea",
+             "GME_orb_FermiSea", "NLDrude_FermiSurf", "NLDrude_Fermider2", "NLDrude_FermiSea", "Hall_classic_FermiSurf",
+             "Hall_classic_FermiSea", "AHC_Zeeman_spin", "OmegaOmega"]
+    for name in names:
+        c = getattr(S, name)(Efermi=Ef, tetra=(name == "BerryDipole_FermiSea"), degen_thresh=0.01)
+        n = st.adapt(c)
+        assert type(n).__name__ == name and n.tetra == c.tetra and n.degen_thresh == 0.01 and n.fder == c.fder
+        assert abs(n.constant_factor - c.constant_factor) <= 1e-12 * abs(c.constant_factor), name
+    n = st.adapt(S.SHC(Efermi=Ef, kwargs_formula={"spin_current_type": "qiao"}))
+    assert [int(s.formula) for s in n.specs()] == [_lib.SHC_QIAO]
+    for c in (D.OpticalConductivity(Efermi=Ef, omega=om, kBT=0.01), D.JDOS(Efermi=Ef, omega=om),
+              D.SHC(Efermi=Ef, omega=om, SHC_type="qiao", shc_abc=(1, 2, 3)), D.ShiftCurrent(Efermi=Ef, omega=om, sc_eta=0.04),
+              D.InjectionCurrent(Efermi=Ef, omega=om)):
+        n = dy.adapt(c)
+        assert type(n).__name__ == type(c).__name__ and n.kBT == c.kBT
+        assert abs(n.constant_factor - c.constant_factor) <= 1e-12 * abs(c.constant_factor)
+    assert dy.adapt(D.ShiftCurrent(Efermi=Ef, omega=om, sc_eta=0.04)).spec().sc_eta == 0.04
+    assert dy.adapt(D.SHC(Efermi=Ef, omega=om, SHC_type="qiao")).spec().shc_type == _lib.SHC_QIAO
