@@ -926,6 +926,32 @@ def test_adaptive_refinement(wb, fe, orc):
         assert relerr(np.tensordot(factors, b, axes=(0, 0)), w) < 1e-12
 
 
+def test_adaptive_refinement_restart(wb, tmp_path):
+    """Restart files (run_grid.py:271-298,343-363): a run with `allow_restart` followed by `restart=True` for more
+    iterations gives the result of the straight run -- the reference's own test of this (tests/test_run.py:556-578)
+    against the same refinement fixture; also restarting from an earlier iteration of the saved history."""
+    g = np.load(os.path.join(GOLDEN, "golden_synth_adpt.npz"))
+    sysg = wb.synthetic_system(6, rmax=1, seed=4242)
+    st = wb.calculators.static
+    mk = lambda: dict(ahc=st.AHC(Efermi=g["Efermi"]), dos=st.DOS(Efermi=g["Efermi"]))
+    grid = lambda: wb.Grid(sysg, NKdiv=[2, 2, 2], NKFFT=[3, 3, 3])
+    kl = str(tmp_path / "klist")
+    kw = dict(adpt_fac=2, adpt_mesh=2, file_Klist_path=kl)
+    res = wb.run(sysg, grid(), mk(), adpt_num_iter=1, allow_restart=True, **kw)
+    for q in ("ahc", "dos"):
+        assert relerr(res.results[q].data, g[f"iter1_{q}"]) < RTOL, q
+    res = wb.run(sysg, grid(), mk(), adpt_num_iter=2, restart=True, allow_restart=True, **kw)
+    for q in ("ahc", "dos"):
+        assert relerr(res.results[q].data, g[f"iter3_{q}"]) < RTOL, q
+    assert sorted(os.listdir(kl)) == ["K_list.pickle"] + [f"factors_iter-{i:08d}.npy" for i in range(4)]
+    res = wb.run(sysg, grid(), mk(), adpt_num_iter=0, restart=True, restart_iteration=1, **kw)   # the state after iteration 1
+    for q in ("ahc", "dos"):
+        assert relerr(res.results[q].data, g[f"iter1_{q}"]) < RTOL, q
+    res = wb.run(sysg, grid(), mk(), adpt_num_iter=0, allow_restart=True, file_Klist_path=kl)   # plain run that can be continued
+    for q in ("ahc", "dos"):
+        assert relerr(res.results[q].data, g[f"iter0_{q}"]) < RTOL, q
+
+
 def test_adaptive_refinement_tetra_and_kubo(wb):
     """run(adpt_num_iter = 2) driven by tetrahedron-method and Kubo calculators (evaluated one K-point per call, the
     tetrahedron cell of a refined K-point is its own dK / NKFFT, grid/Kpoint.py:107-109) next to a plain static one,

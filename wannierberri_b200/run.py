@@ -2,6 +2,11 @@
 (`process`, run_grid.py:32-115) and its Ray fan-out are replaced by: shard the K-block list over the
 ranks of `torch.distributed` (one process per GPU), evaluate each shard with ONE call into
 libwbgpu.so, combine with ONE all-reduce of the Fermi-scan arrays."""
+import glob
+import os
+import pickle
+import shutil
+
 import numpy as np
 
 from .calculators.static import adapt as adapt_static
@@ -45,14 +50,15 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
         device=None, write_files=False):
     """Integrate `calculators` over the k-grid.  Returns a `ResultDict` of `EnergyResult`.
 
-    Not implemented on the GPU path (raise, never fall back to a CPU loop): restart files, symmetrisation of the
-    result, adaptive refinement together with symmetry-reduced K-lists / tetrahedron / Kubo calculators."""
-    if adpt_num_iter != 0:
+    Not implemented on the GPU path (raise, never fall back to a CPU loop): `dump_results`, `parameters_K`,
+    `data_k_class` other than this package's."""
+    if dump_results:
+        raise NotImplementedError("dump_results is not implemented on the GPU path")
+    if adpt_num_iter != 0 or restart or allow_restart:   # per-K-point results are kept: the refinement loop
         return _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac, fout_name, suffix, parallel,
-                             device, write_files, restart or allow_restart or dump_results, symmetrize, use_irred_kpt,
-                             parameters_K)
-    if restart or allow_restart or dump_results:
-        raise NotImplementedError("restart / dump_results are not implemented on the GPU path")
+                             device, write_files, symmetrize, use_irred_kpt, parameters_K,
+                             dict(restart=restart, allow_restart=allow_restart, restart_iteration=restart_iteration,
+                                  Klist_part=Klist_part, file_Klist_path=file_Klist_path))
     if parameters_K:
         raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
     system = as_system(system)
@@ -133,14 +139,29 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
     return res
 
 
+def _write_factors(path, factors, it):   # run_grid.py:420-422
+    with open(os.path.join(path, f"factors_iter-{it:08d}.npy"), "wb") as f:
+        np.save(f, factors)
+
+
+def _read_factors(path, it):   # run_grid.py:425-440
+    if it >= 0:
+        return it, np.load(os.path.join(path, f"factors_iter-{it:08d}.npy"))
+    have = sorted(int(f.split("-")[-1].split(".")[0]) for f in glob.glob(os.path.join(path, "factors_iter-*.npy")))
+    want = max(have[-1] + it + 1, 0)
+    return _read_factors(path, max(i for i in have if i <= want) if want > 0 else 0)
+
+
 def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac, fout_name, suffix, parallel, device,
-                  write_files, restart, symmetrize, use_irred_kpt, parameters_K):
+                  write_files, symmetrize, use_irred_kpt, parameters_K, restart_opts=None):
     """The refinement loop of the reference (run_grid.py:303-387) on per-K-block results from the GPU
     (`wbgpu_static_scan_blocks`): evaluate the new K-points, update the weighted sum, pick the `adpt_fac` points with
     the largest contribution by every criterion of `ResultDict.max`, divide them `adpt_mesh`-fold, repeat."""
     from .grid import KpointBZparallel, exclude_equiv_points
-    if restart:
-        raise NotImplementedError("restart / dump_results are not implemented on the GPU path")
+    ro = dict(restart=False, allow_restart=False, restart_iteration=-1, Klist_part=10, file_Klist_path=None)
+    ro.update(restart_opts or {})
+    Klist_dir = ro["file_Klist_path"] if ro["file_Klist_path"] is not None else "_tmp_wb"   # run_grid.py:244-246
+    file_Klist = os.path.join(Klist_dir, "K_list.pickle")
     if parameters_K:
         raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
     system = as_system(system)
@@ -167,6 +188,22 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
     dK0 = 1. / np.array(grid.div, dtype=float)
     K_list = [KpointBZparallel(s * NKFFT, dK0, NKFFT, f, pointgroup=pointgroup if use_irred_kpt else None)
               for s, f in zip(shifts, factors)]
+    start_iter, nk_saved = 0, 0
+    restored = None
+    if ro["restart"]:   # run_grid.py:271-288: the evaluated K-points with their results, the factors of the chosen iteration
+        K_list = []
+        with open(file_Klist, "rb") as fr:
+            while True:
+                try:
+                    K_list += pickle.load(fr)
+                except EOFError:
+                    break
+        nk_saved = len(K_list)
+        start_iter, fac = _read_factors(Klist_dir, ro["restart_iteration"])
+        fac = np.hstack([fac, np.zeros(len(K_list) - len(fac))])
+        for K, f in zip(K_list, fac):
+            K.factor = float(f)
+        restored = fac
     if adpt_num_iter < 0:  # run_grid.py:303-304
         adpt_num_iter = -adpt_num_iter * np.prod(grid.div) / np.prod(adpt_mesh) / adpt_fac / 3
     adpt_num_iter = int(round(adpt_num_iter))
@@ -206,6 +243,15 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
 
     result_all = None
     factors_old = None
+    if restored is not None:
+        for K in K_list:
+            contrib = K.result * K.factor
+            result_all = contrib if result_all is None else result_all + contrib
+        factors_old = restored
+    elif ro["allow_restart"] and rank == 0:   # run_grid.py:295-298
+        shutil.rmtree(Klist_dir, ignore_errors=True)
+        os.makedirs(Klist_dir)
+        _write_factors(Klist_dir, np.array([K.factor for K in K_list]), 0)
     for i_iter in range(adpt_num_iter + 1):
         new = [i for i, K in enumerate(K_list) if not K.was_evaluated_flag]
         # the new K-points are sharded over the ranks; every rank then holds all per-K-point results
@@ -258,6 +304,13 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
             contrib = res * K_list[i].factor
             result_sum_iter = contrib if result_sum_iter is None else result_sum_iter + contrib
         fac_now = np.array([K.factor for K in K_list])
+        if ro["allow_restart"] and rank == 0:   # run_grid.py:343-348: append the K-points evaluated in this iteration
+            with open(file_Klist, "ab") as fw:
+                for ink in range(nk_saved, len(K_list), int(ro["Klist_part"])):
+                    pickle.dump(K_list[ink:ink + int(ro["Klist_part"])], fw)
+            if result_all is not None:
+                _write_factors(Klist_dir, fac_now, i_iter + start_iter)
+        nk_saved = len(K_list)
         if result_all is None:
             result_all = result_sum_iter
         else:  # run_grid.py:352-360: the points divided in the previous iteration lost their weight
@@ -268,8 +321,8 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
                 if abs(d) > 1.e-8:
                     result_all = result_all + K_list[i].result * d
         factors_old = fac_now
-        if write_files and rank == 0:
-            result_all.savedata(prefix=fout_name, suffix=suffix, i_iter=i_iter)
+        if write_files and rank == 0 and not (ro["restart"] and i_iter == 0):
+            result_all.savedata(prefix=fout_name, suffix=suffix, i_iter=i_iter + start_iter)
         if i_iter >= adpt_num_iter:
             break
         Kmax = np.array([K.max for K in K_list]).T
