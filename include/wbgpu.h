@@ -76,7 +76,8 @@ enum {
     WBGPU_DER_MORB = 23,      /* DerMorb (sign = +1)  covariant.py:463-547 (generalised derivative of the orbital moment:
                                  GME_orb_FermiSea), rank 2 [c][d], not additive; needs the channels of DerOmega plus BB, CC and
                                  their comma-derivatives */
-    WBGPU_NFORMULA = 24
+    WBGPU_OMEGA_HPLUS = 24,   /* OmegaHplus  covariant.py:861-865 (Omega x Morb_Hpm blocks: AHC_Zeeman_orb) rank 2 */
+    WBGPU_NFORMULA = 25
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */

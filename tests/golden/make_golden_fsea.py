@@ -50,7 +50,9 @@ def main():
                  nldrude_sea_tetra=st.NLDrude_FermiSea(Efermi=Ef, tetra=True),
                  gme_orb_sea=st.GME_orb_FermiSea(Efermi=Ef), gme_orb_sea_thresh=st.GME_orb_FermiSea(Efermi=Ef, degen_thresh=0.3),
                  gme_orb_sea_int=st.GME_orb_FermiSea(Efermi=Ef, kwargs_formula=dict(external_terms=False)),
-                 gme_orb_sea_tetra=st.GME_orb_FermiSea(Efermi=Ef, tetra=True))
+                 gme_orb_sea_tetra=st.GME_orb_FermiSea(Efermi=Ef, tetra=True),
+                 ahc_zeeman_orb=st.AHC_Zeeman_orb(Efermi=Ef), ahc_zeeman_orb_thresh=st.AHC_Zeeman_orb(Efermi=Ef, degen_thresh=0.3),
+                 ahc_zeeman_orb_int=st.AHC_Zeeman_orb(Efermi=Ef, kwargs_formula=dict(external_terms=False)))
     grid, res = run_ref(rnd, [6, 6, 6], [3, 3, 3], calcs)
     out = dict(rnd_Efermi=Ef, rnd_NK=np.array([6, 6, 6]), rnd_NKFFT=np.array([3, 3, 3]))
     for q in calcs:

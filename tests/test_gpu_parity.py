@@ -784,6 +784,8 @@ FSEA_CASES = dict(
     gme_orb_sea=("GME_orb_FermiSea", {}), gme_orb_sea_thresh=("GME_orb_FermiSea", dict(degen_thresh=0.3)),
     gme_orb_sea_int=("GME_orb_FermiSea", dict(kwargs_formula=dict(external_terms=False))),
     gme_orb_sea_tetra=("GME_orb_FermiSea", dict(tetra=True)),
+    ahc_zeeman_orb=("AHC_Zeeman_orb", {}), ahc_zeeman_orb_thresh=("AHC_Zeeman_orb", dict(degen_thresh=0.3)),
+    ahc_zeeman_orb_int=("AHC_Zeeman_orb", dict(kwargs_formula=dict(external_terms=False))),
 )
 
 

@@ -175,7 +175,7 @@ def test_adapt_reference_calculator_instances():
     names = ["DOS", "CumDOS", "Spin", "AHC", "Morb", "BerryDipole_FermiSurf", "NLAHC_FermiSurf", "GME_orb_FermiSurf",
              "GME_spin_FermiSurf", "Ohmic_FermiSurf", "Ohmic_FermiSea", "BerryDipole_FermiSea", "NLAHC_FermiSea", "GME_spin_FermiSea",
              "GME_orb_FermiSea", "NLDrude_FermiSurf", "NLDrude_Fermider2", "NLDrude_FermiSea", "Hall_classic_FermiSurf",
-             "Hall_classic_FermiSea", "AHC_Zeeman_spin", "OmegaOmega"]
+             "Hall_classic_FermiSea", "AHC_Zeeman_spin", "AHC_Zeeman_orb", "OmegaOmega"]
     for name in names:
         c = getattr(S, name)(Efermi=Ef, tetra=(name == "BerryDipole_FermiSea"), degen_thresh=0.01)
         n = st.adapt(c)

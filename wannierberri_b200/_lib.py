@@ -10,12 +10,12 @@ LIB_PATH = os.path.join(_HERE, "libwbgpu.so")
 
 # enums of include/wbgpu.h
 (IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN, KUBO, VEL_VEL, INV_MASS, SHC_RYOO, SHC_QIAO,
- SHC_SIMPLE, DER_OMEGA, DER_SPIN, VEL_VEL_VEL, MASS_VEL, MASS_MASS, VEL_MASS_VEL, OMEGA_S, OMEGA_OMEGA, SHIFT_CURRENT, DER3E, DER_MORB) = range(24)
+ SHC_SIMPLE, DER_OMEGA, DER_SPIN, VEL_VEL_VEL, MASS_VEL, MASS_MASS, VEL_MASS_VEL, OMEGA_S, OMEGA_OMEGA, SHIFT_CURRENT, DER3E, DER_MORB, OMEGA_HPLUS) = range(25)
 SHC_TYPES = {"ryoo": SHC_RYOO, "qiao": SHC_QIAO, "simple": SHC_SIMPLE}
 KUBO_OPTCOND, KUBO_JDOS, KUBO_SHC, KUBO_SHIFT, KUBO_INJECTION = 0, 1, 2, 3, 4
 FORMULA_RANK = {IDENTITY: 0, OMEGA: 1, MORB_HPM: 1, SPIN: 1, VEL_OMEGA: 2, VEL_HPLUS: 2, VEL_SPIN: 2, VEL_VEL: 2,
                 INV_MASS: 2, DER_OMEGA: 2, SHC_RYOO: 3, SHC_QIAO: 3, SHC_SIMPLE: 3, DER_SPIN: 2, VEL_VEL_VEL: 3, MASS_VEL: 3,
-                MASS_MASS: 4, VEL_MASS_VEL: 4, OMEGA_S: 2, OMEGA_OMEGA: 2, DER3E: 3, DER_MORB: 2}
+                MASS_MASS: 4, VEL_MASS_VEL: 4, OMEGA_S: 2, OMEGA_OMEGA: 2, DER3E: 3, DER_MORB: 2, OMEGA_HPLUS: 2}
 KEYS = {"Ham": 0, "AA": 1, "BB": 2, "CC": 3, "SS": 4, "SA": 5, "SHA": 6, "SR": 7, "SH": 8, "SHR": 9}
 KEY_NCART = {"Ham": 1, "SA": 9, "SHA": 9, "SR": 9, "SHR": 9}   # default 3
 CHANNELS = {"Ham": 0, "dHam": 1, "AA": 2, "rotAA": 3, "BB": 4, "CC": 5, "SS": 6}

@@ -22,6 +22,7 @@ _TR_INV = {  # transformTR, transformInv of the formulae (covariant.py)
     _lib.DER_SPIN: ("ident", "odd"), _lib.VEL_VEL_VEL: ("odd", "odd"), _lib.MASS_VEL: ("odd", "odd"),
     _lib.MASS_MASS: ("ident", "ident"), _lib.VEL_MASS_VEL: ("ident", "ident"), _lib.OMEGA_S: ("ident", "ident"),
     _lib.OMEGA_OMEGA: ("ident", "ident"), _lib.DER3E: ("odd", "odd"), _lib.DER_MORB: ("ident", "odd"),
+    _lib.OMEGA_HPLUS: ("ident", "ident"),
 }
 _ALPHA, _BETA = np.array([1, 2, 0]), np.array([2, 0, 1])   # utility.py:45-46
 
@@ -391,6 +392,22 @@ class AHC_Zeeman_spin(StaticCalculator):
         super().__init__(constant_factor=constant_factor, **kwargs)
 
 
+class AHC_Zeeman_orb(StaticCalculator):
+    r"""AHC conductivity Zeeman correction term orbital part (:math:`S/m/T`), Fermi surface integral (static.py:626-645)"""
+
+    def __init__(self, constant_factor=factors.fac_orb_Z * factors.factor_ahc, **kwargs):
+        self.Formula = _lib.OMEGA_HPLUS
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+    def specs(self):   # OmegaHplus and OmegaOmega(constant_factor = same)
+        return [self._spec(), self._spec(formula=_lib.OMEGA_OMEGA)]
+
+    def combine(self, arrays, cell_volume):
+        Hplus, Om = arrays
+        return Hplus - 2 * Om * self.Efermi[:, None, None]
+
+
 class OmegaOmega(StaticCalculator):
     r"""static.py:618-623"""
 
@@ -403,7 +420,7 @@ class OmegaOmega(StaticCalculator):
 _BY_NAME = {c.__name__: c for c in (DOS, CumDOS, Spin, AHC, Morb, BerryDipole_FermiSurf, GME_orb_FermiSurf,
                                     GME_spin_FermiSurf, Ohmic_FermiSurf, Ohmic_FermiSea, BerryDipole_FermiSea,
                                     NLAHC_FermiSea, SHC, NLAHC_FermiSurf, GME_spin_FermiSea, Hall_classic_FermiSurf,
-                                    Hall_classic_FermiSea, NLDrude_FermiSurf, NLDrude_Fermider2, NLDrude_FermiSea, GME_orb_FermiSea, AHC_Zeeman_spin,
+                                    Hall_classic_FermiSea, NLDrude_FermiSurf, NLDrude_Fermider2, NLDrude_FermiSea, GME_orb_FermiSea, AHC_Zeeman_spin, AHC_Zeeman_orb,
                                     OmegaOmega)}
 
 

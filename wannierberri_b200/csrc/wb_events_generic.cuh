@@ -17,7 +17,7 @@
 
 struct WbEventLayout {
     int mask;          // bit f set: formula f requested
-    int off[24];       // offset of formula f inside the NC values of an event
+    int off[32];       // offset of formula f inside the NC values of an event
     int NC;            // values per event
     int internal_terms, external_terms;
 };

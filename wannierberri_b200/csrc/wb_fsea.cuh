@@ -250,12 +250,14 @@ wb_deromega_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long n
 //   kind 3  Om   Omega                                              rank 1  (covariant.py:161-203)
 //   kind 4  S    Spin                                               rank 1  (covariant.py:331-335)
 //   kind 5  dS   DerSpin = generalised derivative of S               rank 2  (covariant.py:338-342)
+//   kind 6  Hp   Morb_Hpm (sign = +1) = Morb_H + Eav Omega           rank 1  (covariant.py:375-449)
 // trace over the group of F1 F2 (F3), cartesian indices appended in order.  Covers VelVelVel, MassVel, MassMass,
 // VelMassVel, OmegaS, OmegaOmega (covariant.py:823-858) and the single-factor DerSpin.
 struct WbProductSpec {
     int nf;
     int kind[3];
     int iV, iW, iA, iO, iS, idS;   // matrix positions in the rotated record: d_a H [3] | d_b d_d H [6] | A [3] | rotA [3] | S [3] | d_d S_s [9]
+    int iB, iC;                    // B [3] | C [3] (kind 6 with external terms)
 };
 __host__ __device__ inline int wb_product_kind_ncomp(int kind) { return (kind == 2 || kind == 5) ? 9 : 3; }
 __host__ __device__ inline size_t wb_product_scratch_elems(int nw) { return (size_t)56 * nw * nw; }
@@ -318,17 +320,22 @@ wb_product_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
                 } else {
                     // Omega_c[m, n] = S(m, n) + conj(S(n, m)),
                     // S(M, L) = -i sum_l D_Ml^al D_lL^be + 1/2 O_ML - sum_l D_Ml^al A_lL^be + sum_l D_Ml^be A_lL^al - i sum_{m' in G} A_Mm'^al A_m'L^be
+                    // kind 6 adds Morb_H: the same sums weighted with E_l / E_m', B instead of A, C instead of O, and Eav Omega
                     const int al = WB_ALPHA(comp), be = WB_BETA(comp);
+                    const bool hp = (kind == 6);
+                    const cplx* Bm = X + (size_t)P.iB * n2;
                     val = cmake(0., 0.);
+                    cplx valh = cmake(0., 0.);
 #pragma unroll
                     for (int side = 0; side < 2; side++) {
                         const int M = side ? n : m, Lb = side ? m : n;
-                        cplx S = cmake(0., 0.);
+                        cplx S = cmake(0., 0.), Sh = cmake(0., 0.);
                         for (int l = 0; l < nw; l++) {
                             if (in_G(l)) {
                                 if (external) {
                                     const cplx z = cmul(A[(size_t)al * n2 + M * nw + l], A[(size_t)be * n2 + l * nw + Lb]);
                                     S.x += z.y; S.y -= z.x;
+                                    if (hp) { Sh.x += Es[l] * z.y; Sh.y -= Es[l] * z.x; }
                                 }
                                 continue;
                             }
@@ -336,17 +343,28 @@ wb_product_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
                             if (internal) {
                                 const cplx z = cmul(DMa, Dm(be, l, Lb));
                                 S.x += z.y; S.y -= z.x;
+                                if (hp) { Sh.x += Es[l] * z.y; Sh.y -= Es[l] * z.x; }
                             }
                             if (external) {
                                 const cplx z = csub(cmul(DMb, A[(size_t)al * n2 + l * nw + Lb]), cmul(DMa, A[(size_t)be * n2 + l * nw + Lb]));
                                 S = cadd(S, z);
+                                if (hp) Sh = cadd(Sh, csub(cmul(DMb, Bm[(size_t)al * n2 + l * nw + Lb]), cmul(DMa, Bm[(size_t)be * n2 + l * nw + Lb])));
                             }
                         }
                         if (external) {
                             const cplx o = X[(size_t)(P.iO + comp) * n2 + M * nw + Lb];
                             S.x += 0.5 * o.x; S.y += 0.5 * o.y;
+                            if (hp) {
+                                const cplx cc = X[(size_t)(P.iC + comp) * n2 + M * nw + Lb];
+                                Sh.x += 0.5 * cc.x; Sh.y += 0.5 * cc.y;
+                            }
                         }
                         val = side ? cmake(val.x + S.x, val.y - S.y) : S;
+                        valh = side ? cmake(valh.x + Sh.x, valh.y - Sh.y) : Sh;
+                    }
+                    if (hp) {
+                        const double eav = 0.5 * (Es[m] + Es[n]);
+                        val = cmake(valh.x + eav * val.x, valh.y + eav * val.y);
                     }
                 }
                 Fb[f][y] = val;

@@ -266,7 +266,8 @@ static int formula_rank(int f) {
         case WBGPU_IDENTITY: return 0;
         case WBGPU_OMEGA: case WBGPU_MORB_HPM: case WBGPU_SPIN: return 1;
         case WBGPU_VEL_OMEGA: case WBGPU_VEL_HPLUS: case WBGPU_VEL_SPIN: case WBGPU_VEL_VEL: case WBGPU_INV_MASS:
-        case WBGPU_DER_OMEGA: case WBGPU_DER_SPIN: case WBGPU_OMEGA_S: case WBGPU_OMEGA_OMEGA: case WBGPU_DER_MORB: return 2;
+        case WBGPU_DER_OMEGA: case WBGPU_DER_SPIN: case WBGPU_OMEGA_S: case WBGPU_OMEGA_OMEGA: case WBGPU_DER_MORB:
+        case WBGPU_OMEGA_HPLUS: return 2;
         case WBGPU_SHC_RYOO: case WBGPU_SHC_QIAO: case WBGPU_SHC_SIMPLE:   // SpinOmega
         case WBGPU_VEL_VEL_VEL: case WBGPU_MASS_VEL: case WBGPU_DER3E: return 3;
         case WBGPU_MASS_MASS: case WBGPU_VEL_MASS_VEL: return 4;
@@ -291,6 +292,7 @@ static bool formula_product(int f, WbProductSpec* P) {
         case WBGPU_VEL_MASS_VEL: n = 3; k[0] = 1; k[1] = 2; k[2] = 1; break;
         case WBGPU_OMEGA_S: n = 2; k[0] = 3; k[1] = 4; break;
         case WBGPU_OMEGA_OMEGA: n = 2; k[0] = k[1] = 3; break;
+        case WBGPU_OMEGA_HPLUS: n = 2; k[0] = 3; k[1] = 6; break;
         default: return false;
     }
     if (P) { P->nf = n; for (int i = 0; i < 3; i++) P->kind[i] = k[i]; }
@@ -343,17 +345,17 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     const bool shc = has(WBGPU_SHC_RYOO) || has(WBGPU_SHC_QIAO) || has(WBGPU_SHC_SIMPLE);
     bool prod_any = false, prod_mass = false, prod_omega = false, prod_spin = false;
     for (int f = WBGPU_DER_SPIN; f < WBGPU_NFORMULA; f++)
-        if (has(f)) {
+        if (has(f) && formula_product(f, nullptr)) {
             prod_any = true;
             prod_mass |= product_has(f, 2);
-            prod_omega |= product_has(f, 3);
+            prod_omega |= product_has(f, 3) || product_has(f, 6);
             prod_spin |= product_has(f, 4) || product_has(f, 5);
         }
     need_dH = need_dH || prod_any || has(WBGPU_DER3E) || has(WBGPU_DER_MORB);
     const bool der_om = has(WBGPU_DER_OMEGA) || has(WBGPU_DER_MORB);   // channels of DerOmega
     bool berry = has(WBGPU_OMEGA) || has(WBGPU_MORB_HPM) || has(WBGPU_VEL_OMEGA) || has(WBGPU_VEL_HPLUS) || has(WBGPU_KUBO);
     bool need_A = (berry || shc || der_om || prod_omega || has(WBGPU_SHIFT_CURRENT)) && external_terms;
-    bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS) || has(WBGPU_DER_MORB)) && external_terms;
+    bool need_BC = (has(WBGPU_MORB_HPM) || has(WBGPU_VEL_HPLUS) || has(WBGPU_DER_MORB) || has(WBGPU_OMEGA_HPLUS)) && external_terms;
     bool need_S = has(WBGPU_SPIN) || has(WBGPU_VEL_SPIN) || shc || prod_spin;
     if (has(WBGPU_SHC_RYOO) && (!c->d_XR[WBGPU_SA] || !c->d_XR[WBGPU_SHA]))
         return set_err("wbgpu_plan: R-matrices 'SA','SHA' are not set (SHC_type='ryoo')");
@@ -768,7 +770,7 @@ static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec)
             G.win = w;
             G.ev.mask = 0;
             G.ev.NC = 0;
-            for (int f = 0; f < 24; f++) G.ev.off[f] = 0;
+            for (int f = 0; f < 32; f++) G.ev.off[f] = 0;
             G.solo = formula_solo(s.formula);
             G.ev.internal_terms = s.internal_terms;
             G.ev.external_terms = s.external_terms;
@@ -1001,16 +1003,19 @@ static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
     }
     WbProductSpec P;
     if (formula_product(formula, &P)) {
-        const bool hasM = product_has(formula, 2), hasO = product_has(formula, 3), hasS = product_has(formula, 4) || product_has(formula, 5);
+        const bool hasM = product_has(formula, 2), hasO = product_has(formula, 3) || product_has(formula, 6),
+                   hasS = product_has(formula, 4) || product_has(formula, 5), hasH = product_has(formula, 6);
+        if (hasH && ext && (L.off_B[0] < 0 || L.off_C[0] < 0)) return set_err("scan: the plan does not hold the channels of formula %d", formula);
         if (L.off_dH[0] < 0 || (hasM && L.off_W[0] < 0) || (hasO && ext && (L.off_A[0] < 0 || L.off_O[0] < 0)) ||
             (hasS && L.off_S[0] < 0) || (formula == WBGPU_DER_SPIN && L.off_dS[0] < 0))
             return set_err("scan: the plan does not hold the channels of formula %d", formula);
-        P.iW = P.iA = P.iO = P.iS = P.idS = 0;
+        P.iW = P.iA = P.iO = P.iS = P.idS = P.iB = P.iC = 0;
         P.iV = addn(L.off_dH, 3, L.dH_herm);
         if (hasM) P.iW = addn(L.off_W, 6, L.dH_herm);
         if (hasO && ext) { P.iA = addn(L.off_A, 3, 1); P.iO = addn(L.off_O, 3, 1); }
         if (hasS) P.iS = addn(L.off_S, 3, 1);
         if (formula == WBGPU_DER_SPIN) P.idS = addn(L.off_dS, 9, 1);
+        if (hasH && ext) { P.iB = addn(L.off_B, 3, 0); P.iC = addn(L.off_C, 3, 0); }
         const int NC = formula_ncomp(formula);
         const long chunk = xbar_chunk(c, ch.n, nk);
         if (ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * n2)) return 1;

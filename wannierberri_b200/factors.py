@@ -20,3 +20,4 @@ factor_nldrude = -(elementary_charge ** 3 / hbar ** 2 * TAU_UNIT ** 2 * elementa
 from math import pi  # noqa: E402
 factor_shift_current = hbar / elementary_charge * pi * elementary_charge ** 3 / (4 * hbar ** 2)
 factor_injection_current = -pi * elementary_charge ** 3 / (hbar ** 2) * TAU_UNIT
+fac_orb_Z = elementary_charge / 2 / hbar * angstrom ** 2
