@@ -191,3 +191,47 @@ def test_adapt_reference_calculator_instances():
         assert abs(n.constant_factor - c.constant_factor) <= 1e-12 * abs(c.constant_factor)
     assert dy.adapt(D.ShiftCurrent(Efermi=Ef, omega=om, sc_eta=0.04)).spec().sc_eta == 0.04
     assert dy.adapt(D.SHC(Efermi=Ef, omega=om, SHC_type="qiao")).spec().shc_type == _lib.SHC_QIAO
+
+
+def test_smoothers():
+    """wannierberri_b200.smoother against direct sums; EnergyResult.dataSmooth / .max use the smoother of every energy axis;
+    the reference's own smoother classes give the same numbers (container-only part)."""
+    import sys
+    from wannierberri_b200.smoother import FermiDiracSmoother, GaussianSmoother, VoidSmoother, get_smoother
+    rng = np.random.default_rng(3)
+    E = np.linspace(-1., 1., 81)
+    A = rng.standard_normal((81, 3, 2)) + 1j * rng.standard_normal((81, 3, 2))
+    sm = GaussianSmoother(E, 0.06, maxdE=5)
+    got = sm(A)
+    for i in (0, 7, 40, 80):   # direct evaluation incl. the renormalised windows at both ends
+        j = np.arange(max(0, i - sm.NE1), min(81, i + sm.NE1 + 1))
+        w = np.exp(-((E[j] - E[i]) / 0.06) ** 2)
+        assert np.allclose(got[i], np.tensordot(w / w.sum(), A[j], axes=(0, 0)), rtol=1e-13, atol=1e-15)
+    assert np.allclose(sm(A.transpose(1, 0, 2), axis=1), got.transpose(1, 0, 2))
+    assert np.allclose(sm(np.ones(81)), 1.)   # normalised
+    assert isinstance(get_smoother(E, 0, "Gaussian"), VoidSmoother) and get_smoother(E, 300, "Fermi-Dirac") == FermiDiracSmoother(E, 300)
+    with pytest.raises(ValueError):
+        get_smoother(E, 1., "other")
+    r = wb.EnergyResult(E, A.real, smoothers=[sm])
+    assert np.allclose(r.dataSmooth, sm(A.real)) and np.allclose(r.max[0], np.abs(sm(A.real)).max())
+    assert np.allclose((r + r * 2.).dataSmooth, 3 * sm(A.real))
+    with pytest.raises(RuntimeError):
+        r + wb.EnergyResult(E, A.real, smoothers=[GaussianSmoother(E, 0.1)])
+    c = wb.calculators.static.AHC(Efermi=E, smoother=sm)
+    assert c.result([np.zeros((81, 3))], 1.).smoothers == [sm]
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "wannierberri")):
+        return
+    sys.path.insert(0, ref)
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_smoother", os.path.join(ref, "wannierberri", "smoother.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(ref)
+    assert np.allclose(mod.GaussianSmoother(E, 0.06, maxdE=5)(A), got, rtol=1e-12, atol=1e-14)
+    assert np.allclose(mod.FermiDiracSmoother(E, 400.)(A.real), FermiDiracSmoother(E, 400.)(A.real), rtol=1e-12, atol=1e-14)
+    # a reference smoother object is accepted as is
+    r2 = wb.EnergyResult(E, A.real, smoothers=[mod.FermiDiracSmoother(E, 400.)])
+    assert np.allclose(r2.dataSmooth, FermiDiracSmoother(E, 400.)(A.real), rtol=1e-12, atol=1e-14)

@@ -9,5 +9,7 @@ from .result import EnergyResult, ResultDict  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .data_K import Data_K_R  # noqa: F401
 from .run import run  # noqa: F401
+from . import smoother  # noqa: F401
+from .smoother import get_smoother  # noqa: F401
 
 __version__ = "0.1.0"

@@ -59,8 +59,8 @@ class StaticCalculator(Calculator):
             raise NotImplementedError("k_resolved=True is not implemented on the GPU path")
         if select_bands is not None:
             raise NotImplementedError("select_bands is not implemented on the GPU path")
-        if smoother is not None:
-            raise NotImplementedError("smoothers are post-processing, out of scope of the GPU path")
+        if smoother is not None and not callable(smoother):
+            raise ValueError("smoother must be callable as smoother(A, axis=0) (wannierberri_b200.smoother or the reference's)")
         if Emin != -np.inf or Emax != np.inf:
             raise NotImplementedError("Emin/Emax band selection is not implemented on the GPU path")
         self.kwargs_formula = copy(kwargs_formula) if kwargs_formula is not None else {}
@@ -112,7 +112,7 @@ class StaticCalculator(Calculator):
     def result(self, arrays, cell_volume):
         tr, inv = _TR_INV[self.Formula]
         return EnergyResult(self.Efermi, self.combine(arrays, cell_volume), transformTR=tr, transformInv=inv,
-                            comment=self.comment, save_mode=self.save_mode)
+                            comment=self.comment, save_mode=self.save_mode, smoothers=[self.smoother])
 
     def __call__(self, data_K):
         """Per-K-block evaluation with the reference's calling convention `calc(data_K)`; `data_K` is a

@@ -33,6 +33,9 @@ class EnergyResult:
         for a, b in zip(self.Energies, other.Energies):
             if not np.array_equal(a, b):
                 raise RuntimeError("Adding results with different energies")
+        for a, b in zip(self.smoothers, other.smoothers):   # energyresult.py:176-180
+            if not ((a is None and b is None) or a == b):
+                raise RuntimeError("Adding results with different smoothers")
         return EnergyResult(self.Energies, self.data + other.data, self.transformTR, self.transformInv, self.rank,
                             self.E_titles, self.comment, self.save_mode, self.smoothers)
 
@@ -64,7 +67,12 @@ class EnergyResult:
 
     @property
     def dataSmooth(self):
-        return self.data
+        """energyresult.py:120-131: every energy axis smoothed by its smoother (None = as is)"""
+        d = self.data
+        for i, sm in enumerate(self.smoothers):
+            if sm is not None:
+                d = sm(d, axis=i)
+        return d
 
     @property
     def max(self):
