@@ -355,6 +355,10 @@ def test_kubo_synthetic(wb, orc, nw, nEF, nom):
     kw = dict(smr_fixed_width=0.1, smr_type="Lorentzian")
     got = wb.calculators.dynamic.OpticalConductivity(Efermi=Ef, omega=om, **kw)(data).data
     assert relerr(got, orc.OpticalConductivity(odata, Ef, omega=om, **kw)) < RTOL
+    data.engine.set_option("kubo_method", 1)   # the per-(omega, re|im) accumulation kernel against the register-tiled one
+    got1 = wb.calculators.dynamic.OpticalConductivity(Efermi=Ef, omega=om, **kw)(data).data
+    data.engine.set_option("kubo_method", 0)
+    assert relerr(got1, got) < 1e-12
     got = wb.calculators.dynamic.JDOS(Efermi=Ef, omega=om, **kw)(data).data
     assert relerr(got, orc.JDOS(odata, Ef, omega=om, **kw)) < RTOL
 

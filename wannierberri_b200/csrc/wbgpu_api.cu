@@ -113,6 +113,7 @@ struct wbgpu_ctx {
                             // 3 = compile-time-NW DMMA kernel, 4 = batched DMMA GEMM to global memory + formula kernel
     int smem_optin = 0;
     int rot_r2 = -1;        // experiment: override of the step-2 warp rotation of the fused rotation kernel
+    int kubo_method = 0;    // 0 = register-tiled accumulation of the optical conductivity, 1 = per-(omega, re|im) kernel
     int rotate_trim = 1;    // 1 = form only the needed columns of the rotated matrices when they are hermitian
     int dh_packed = 1;      // 1 = pack d_a H as a triangle when it is hermitian in R-space, 0 = never
     std::vector<int> h_iRvec;
@@ -249,6 +250,7 @@ extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "fourier_method")) { c->fourier_method = (int)value; return 0; }
     if (!strcmp(name, "rot_r2")) { c->rot_r2 = (int)value; return 0; }
     if (!strcmp(name, "rotate_trim")) { c->rotate_trim = (int)value; return 0; }
+    if (!strcmp(name, "kubo_method")) { c->kubo_method = (int)value; return 0; }
     if (!strcmp(name, "dh_packed")) { c->dh_packed = (int)value; c->planned = false; return 0; }
     if (!strcmp(name, "timing")) {
         c->timing = (int)value;
@@ -1623,7 +1625,11 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
                 (const cplx*)c->d_shcJ);
             const int nsplit = (int)std::max(1L, std::min(n, (long)((6 * sms + nwtile - 1) / nwtile)));
             dim3 grid((unsigned)nwtile, (unsigned)nsplit);
-            if (optcond)
+            if (optcond && c->kubo_method != 1) {
+                const int ntile = (nom + WB_KUBO_TW - 1) / WB_KUBO_TW;
+                dim3 gridt((unsigned)ntile, (unsigned)std::max(1L, std::min(n, (long)((12 * sms + ntile - 1) / ntile))));
+                wb_kubo_accumulate_optcond_tiled_kernel<<<gridt, 144, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
+            } else if (optcond)
                 wb_kubo_accumulate_kernel<0><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
             else if (shc || shift)
                 wb_kubo_accumulate_kernel<2><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
