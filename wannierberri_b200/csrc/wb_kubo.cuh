@@ -424,19 +424,8 @@ wb_shift_agen_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, co
 
 // factor_omega of OpticalConductivity (dynamic.py:191-196) without the (E2 - E1) prefactor: 1/(d - i eta), the
 // imaginary part replaced by pi * Gaussian(d) for smr_type != Lorentzian
-// 1 / x for the frequency factors (millions per k-point): single-precision seed + two Newton steps (relative error
-// ~1e-16, not correctly rounded) instead of the IEEE division sequence; plain division outside the float range
-__device__ __forceinline__ double wb_rcp(double x) {
-    const float xf = (float)x;
-    if (!(xf > 1e-30f && xf < 1e30f)) return 1. / x;
-    double r = (double)__frcp_rn(xf);
-    r = fma(r, fma(-x, r, 1.0), r);
-    r = fma(r, fma(-x, r, 1.0), r);
-    return r;
-}
-
 __device__ __forceinline__ cplx wb_kubo_cfac(double d, double eta, int smr_type) {
-    const double den = wb_rcp(d * d + eta * eta);
+    const double den = 1. / (d * d + eta * eta);
     if (smr_type == 0) return cmake(d * den, eta * den);
     double g = 0.;
     if (fabs(d) < eta * sqrt(200.0)) g = 1.0 / (sqrt(CUDART_PI) * eta) * exp(-(d / eta) * (d / eta));
