@@ -833,7 +833,7 @@ def test_te_qe_berry_dipole_fermi_sea_vs_upstream_goldens(wb):
             assert relerr(res.results[q].data, g["te_upstream_golden_" + q]) < tol, q
 
 
-@pytest.mark.parametrize("nw,pairs", [(12, True), (35, False)])
+@pytest.mark.parametrize("nw,pairs", [(12, True), (35, False), (64, False)])
 def test_fermi_sea_formulae_synthetic(wb, orc, nw, pairs):
     """DerOmega and SpinOmega on synthetic models with the R <-> -R symmetry (hermitian-packed derivative channels):
     exactly degenerate pairs (groups of two bands, D = 0 inside a group) and more bands than a warp, against the oracle."""
