@@ -250,10 +250,8 @@ class Ohmic_FermiSea(StaticCalculator):
 
 
 class BerryDipole_FermiSea(StaticCalculator):
-    r"""Berry curvature dipole (dimensionless)
-
-        | With Fermi sea integral. Eq(29) in `Ref <https://www.nature.com/articles/s41524-021-00498-5>`__
-        | Output: :math:`D_{\beta\delta} = \int [dk] \partial_\beta \Omega_\delta f`"""
+    r"""Berry curvature dipole as a Fermi-sea integral of the generalised derivative of the Berry curvature
+    (static.py:472-487, formula DerOmega): data `[Efermi, beta, delta]`, dimensionless."""
 
     def __init__(self, **kwargs):
         self.Formula = _lib.DER_OMEGA
@@ -265,10 +263,7 @@ class BerryDipole_FermiSea(StaticCalculator):
 
 
 class NLAHC_FermiSea(BerryDipole_FermiSea):
-    r"""Nonlinear anomalous Hall conductivity  (:math:`S^2/A`)
-
-        | With Fermi sea integral. Eq(29) in `Ref <https://www.nature.com/articles/s41524-021-00498-5>`__
-        | Output: :math:`D_{\beta\delta} = e^3/\hbar^2 \tau \int [dk] \partial_\beta \Omega_\delta f`"""
+    r"""BerryDipole_FermiSea in the units of the nonlinear anomalous Hall conductivity, S^2/A (static.py:490-498)."""
 
     def __init__(self, constant_factor=factors.factor_nlahc, **kwargs):
         super().__init__(constant_factor=constant_factor, **kwargs)
@@ -296,9 +291,8 @@ class NLAHC_FermiSurf(BerryDipole_FermiSurf):
 
 
 class GME_spin_FermiSea(StaticCalculator):
-    r"""Gyrotropic tensor spin part (:math:`A`), Fermi sea integral (static.py:322-337)
-
-        | Output: :math:`K^{spin}_{\alpha :\mu} = -\int [dk] \partial_\alpha s_\mu f`"""
+    r"""Spin part of the gyrotropic tensor as a Fermi-sea integral of the generalised derivative of the spin
+    (static.py:322-337, formula DerSpin): data `[Efermi, alpha, mu]`, Ampere."""
 
     def __init__(self, constant_factor=factors.factor_gme_spin, **kwargs):
         self.Formula = _lib.DER_SPIN
@@ -348,9 +342,8 @@ class NLDrude_FermiSurf(StaticCalculator):
 
 
 class GME_orb_FermiSea(StaticCalculator):
-    r"""Gyrotropic tensor orbital part (:math:`A`), Fermi sea integral (static.py:284-300)
-
-        | Output: :math:`K^{orb}_{\alpha :\mu} = -\int [dk] \partial_\alpha m_\mu f`, :math:`m = H + G - 2E_f \cdot \Omega`"""
+    r"""Orbital part of the gyrotropic tensor as a Fermi-sea integral (static.py:284-300): DerMorb scan minus
+    2 E_F times the BerryDipole_FermiSea scan with the same prefactor; data `[Efermi, alpha, mu]`, Ampere."""
 
     def __init__(self, constant_factor=factors.factor_gme_orb, **kwargs):
         self.Formula = _lib.DER_MORB
