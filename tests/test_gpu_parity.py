@@ -958,6 +958,35 @@ def test_adaptive_refinement_restart(wb, tmp_path):
         assert relerr(res.results[q].data, g[f"iter0_{q}"]) < RTOL, q
 
 
+def test_adaptive_refinement_dump_results(wb, tmp_path):
+    """`dump_results=True` (run_grid.py:62-63, 242-243; grid/Kpoint.py:56-67): every K-point's result goes to its own
+    `_Kp-<ik>.pickle` and leaves the memory, the refinement re-reads the divided points' results from there; the run
+    and its restart reproduce the reference's refinement fixture."""
+    import pickle
+    g = np.load(os.path.join(GOLDEN, "golden_synth_adpt.npz"))
+    sysg = wb.synthetic_system(6, rmax=1, seed=4242)
+    st = wb.calculators.static
+    mk = lambda: dict(ahc=st.AHC(Efermi=g["Efermi"]), dos=st.DOS(Efermi=g["Efermi"]))
+    grid = lambda: wb.Grid(sysg, NKdiv=[2, 2, 2], NKFFT=[3, 3, 3])
+    kl = str(tmp_path / "klist")
+    kw = dict(adpt_fac=2, adpt_mesh=2, file_Klist_path=kl, dump_results=True)
+    res = wb.run(sysg, grid(), mk(), adpt_num_iter=1, **kw)
+    for q in ("ahc", "dos"):
+        assert relerr(res.results[q].data, g[f"iter1_{q}"]) < RTOL, q
+    files = sorted(os.listdir(kl))
+    nK = sum(f.startswith("_Kp-") for f in files)
+    assert nK > 8 and "K_list.pickle" in files and "factors_iter-00000001.npy" in files
+    with open(os.path.join(kl, "_Kp-0.pickle"), "rb") as f:
+        r0 = pickle.load(f)
+    assert set(r0.results) == {"ahc", "dos"} and r0.results["ahc"].data.shape == (len(g["Efermi"]), 3)
+    with open(os.path.join(kl, "K_list.pickle"), "rb") as f:
+        part = pickle.load(f)
+    assert all(K.result is None and K.res_dumped_flag and K.was_evaluated_flag for K in part)
+    res = wb.run(sysg, grid(), mk(), adpt_num_iter=2, restart=True, **kw)
+    for q in ("ahc", "dos"):
+        assert relerr(res.results[q].data, g[f"iter3_{q}"]) < RTOL, q
+
+
 def test_adaptive_refinement_tetra_and_kubo(wb):
     """run(adpt_num_iter = 2) driven by tetrahedron-method and Kubo calculators (evaluated one K-point per call, the
     tetrahedron cell of a refined K-point is its own dK / NKFFT, grid/Kpoint.py:107-109) next to a plain static one,

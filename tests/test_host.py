@@ -235,3 +235,28 @@ def test_smoothers():
     # a reference smoother object is accepted as is
     r2 = wb.EnergyResult(E, A.real, smoothers=[mod.FermiDiracSmoother(E, 400.)])
     assert np.allclose(r2.dataSmooth, FermiDiracSmoother(E, 400.)(A.real), rtol=1e-12, atol=1e-14)
+
+
+def test_kpoint_dump_result(tmp_path):
+    """`dump_results` of run(): KpointBZparallel.dump_result / get_result (grid/Kpoint.py:40-67) -- the result leaves
+    the memory, the K-point stays "evaluated", `max` and the pickled K-list keep working, absorb() reads it back."""
+    import pickle
+    from wannierberri_b200.grid import KpointBZparallel
+    from wannierberri_b200.result import EnergyResult, ResultDict
+    Ef = np.linspace(0, 1, 5)
+    res = ResultDict(dict(q=EnergyResult(Ef, np.arange(15.).reshape(5, 3), rank=1)))
+    K = KpointBZparallel([0.5, 0, 0], [1, 1, 1], [2, 2, 2], 0.25)
+    with pytest.raises(RuntimeError):
+        K.get_result()
+    K.set_result(res)
+    mx = np.array(K.max)
+    K.set_storage_path(str(tmp_path / "_Kp-0.pickle"))
+    K.dump_result()
+    K.dump_result()   # idempotent
+    assert K.result is None and K.res_dumped_flag and K.was_evaluated_flag
+    assert np.array_equal(np.array(K.max), mx)
+    K2 = pickle.loads(pickle.dumps(K))
+    assert np.array_equal(K2.get_result().results["q"].data, res.results["q"].data)
+    K3 = KpointBZparallel([0.5, 0, 0], [1, 1, 1], [2, 2, 2], 0.25)
+    K3.absorb(K2)
+    assert K3.factor == 0.5 and np.array_equal(K3.result.results["q"].data, res.results["q"].data)

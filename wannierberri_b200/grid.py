@@ -3,6 +3,7 @@ grid/grid.py:68-75,149-172,196-266 and grid/Kpoint.py:75-77 of the reference; sy
 K-lists follow grid/grid.py:169-189 with the star of symmetry.py)."""
 import warnings
 
+import pickle
 import numpy as np
 
 
@@ -121,6 +122,8 @@ class KpointBZparallel:
         self.refinement_level = refinement_level
         self.pointgroup = pointgroup
         self.result = None
+        self.result_storage_path = None
+        self.res_dumped_flag = False
         self._max = None
         self._star = None
         self._distGamma = None
@@ -135,11 +138,32 @@ class KpointBZparallel:
 
     @property
     def was_evaluated_flag(self):
-        return self.result is not None
+        return self.result is not None or self.res_dumped_flag
 
     def set_result(self, res):
         self.result = res
         self._max = res.max
+
+    def set_storage_path(self, path):  # grid/Kpoint.py:31-32
+        self.result_storage_path = path
+
+    def dump_result(self):
+        """`dump_results=True` of run(): the result of this K-point goes to its own pickle file and leaves the
+        memory (grid/Kpoint.py:56-62); `get_result` reads it back when a later iteration re-weights the point."""
+        if self.res_dumped_flag:
+            return
+        with open(self.result_storage_path, "wb") as f:
+            pickle.dump(self.result, f)
+        self.result = None
+        self.res_dumped_flag = True
+
+    def get_result(self):  # grid/Kpoint.py:40-50
+        if self.result is not None:
+            return self.result
+        if self.res_dumped_flag:
+            with open(self.result_storage_path, "rb") as f:
+                return pickle.load(f)
+        raise RuntimeError("result for a K-point is called, which was never evaluated")
 
     @property
     def max(self):
@@ -176,7 +200,7 @@ class KpointBZparallel:
         if other.was_evaluated_flag:
             if self.was_evaluated_flag:
                 raise RuntimeError("combining two K-points with calculated result should not happen")
-            self.set_result(other.result)
+            self.set_result(other.get_result())
         self.factor += other.factor
 
     def divide(self, ndiv, periodic=(True, True, True), use_symmetry=False):

@@ -50,15 +50,18 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
         device=None, write_files=False):
     """Integrate `calculators` over the k-grid.  Returns a `ResultDict` of `EnergyResult`.
 
-    Not implemented on the GPU path (raise, never fall back to a CPU loop): `dump_results`, `parameters_K`,
+    `dump_results=True` (run_grid.py:62-63, 242-243): per-K-point results are pickled to
+    `<file_Klist_path>/_Kp-<ik>.pickle` and dropped from memory; implies `allow_restart`.
+
+    Not implemented on the GPU path (raise, never fall back to a CPU loop): `parameters_K`,
     `data_k_class` other than this package's."""
     if dump_results:
-        raise NotImplementedError("dump_results is not implemented on the GPU path")
+        allow_restart = True
     if adpt_num_iter != 0 or restart or allow_restart:   # per-K-point results are kept: the refinement loop
         return _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac, fout_name, suffix, parallel,
                              device, write_files, symmetrize, use_irred_kpt, parameters_K,
                              dict(restart=restart, allow_restart=allow_restart, restart_iteration=restart_iteration,
-                                  Klist_part=Klist_part, file_Klist_path=file_Klist_path))
+                                  Klist_part=Klist_part, file_Klist_path=file_Klist_path, dump_results=dump_results))
     if parameters_K:
         raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
     system = as_system(system)
@@ -158,7 +161,8 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
     (`wbgpu_static_scan_blocks`): evaluate the new K-points, update the weighted sum, pick the `adpt_fac` points with
     the largest contribution by every criterion of `ResultDict.max`, divide them `adpt_mesh`-fold, repeat."""
     from .grid import KpointBZparallel, exclude_equiv_points
-    ro = dict(restart=False, allow_restart=False, restart_iteration=-1, Klist_part=10, file_Klist_path=None)
+    ro = dict(restart=False, allow_restart=False, restart_iteration=-1, Klist_part=10, file_Klist_path=None,
+              dump_results=False)
     ro.update(restart_opts or {})
     Klist_dir = ro["file_Klist_path"] if ro["file_Klist_path"] is not None else "_tmp_wb"   # run_grid.py:244-246
     file_Klist = os.path.join(Klist_dir, "K_list.pickle")
@@ -245,7 +249,7 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
     factors_old = None
     if restored is not None:
         for K in K_list:
-            contrib = K.result * K.factor
+            contrib = K.get_result() * K.factor
             result_all = contrib if result_all is None else result_all + contrib
         factors_old = restored
     elif ro["allow_restart"] and rank == 0:   # run_grid.py:295-298
@@ -302,6 +306,12 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
             res = ResultDict(res)
             K_list[i].set_result(res)
             contrib = res * K_list[i].factor
+            if ro["dump_results"]:   # run_grid.py:62-63, 321, 416-417; every rank holds all results, rank 0 writes
+                K_list[i].set_storage_path(os.path.join(Klist_dir, f"_Kp-{i}.pickle"))
+                if rank == 0:
+                    K_list[i].dump_result()
+                else:
+                    K_list[i].result, K_list[i].res_dumped_flag = None, True
             result_sum_iter = contrib if result_sum_iter is None else result_sum_iter + contrib
         fac_now = np.array([K.factor for K in K_list])
         if ro["allow_restart"] and rank == 0:   # run_grid.py:343-348: append the K-points evaluated in this iteration
@@ -319,7 +329,7 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
                 result_all = result_all + result_sum_iter
             for i, d in enumerate(diff):
                 if abs(d) > 1.e-8:
-                    result_all = result_all + K_list[i].result * d
+                    result_all = result_all + K_list[i].get_result() * d
         factors_old = fac_now
         if write_files and rank == 0 and not (ro["restart"] and i_iter == 0):
             result_all.savedata(prefix=fout_name, suffix=suffix, i_iter=i_iter + start_iter)
