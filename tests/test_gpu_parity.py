@@ -969,7 +969,8 @@ def test_adaptive_refinement_dump_results(wb, tmp_path):
     mk = lambda: dict(ahc=st.AHC(Efermi=g["Efermi"]), dos=st.DOS(Efermi=g["Efermi"]))
     grid = lambda: wb.Grid(sysg, NKdiv=[2, 2, 2], NKFFT=[3, 3, 3])
     kl = str(tmp_path / "klist")
-    kw = dict(adpt_fac=2, adpt_mesh=2, file_Klist_path=kl, dump_results=True)
+    kw = dict(adpt_fac=2, adpt_mesh=2, file_Klist_path=kl, dump_results=True, parameters_K=dict(fftlib="numpy"),
+              data_k_class=wb.Data_K_R)
     res = wb.run(sysg, grid(), mk(), adpt_num_iter=1, **kw)
     for q in ("ahc", "dos"):
         assert relerr(res.results[q].data, g[f"iter1_{q}"]) < RTOL, q

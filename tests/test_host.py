@@ -260,3 +260,23 @@ def test_kpoint_dump_result(tmp_path):
     K3 = KpointBZparallel([0.5, 0, 0], [1, 1, 1], [2, 2, 2], 0.25)
     K3.absorb(K2)
     assert K3.factor == 0.5 and np.array_equal(K3.result.results["q"].data, res.results["q"].data)
+
+
+def test_parameters_K_and_data_k_class():
+    """run(parameters_K=..., data_k_class=...): `fftlib` is validated as in the reference (fourier/fft.py:63) and has
+    no effect, defaults pass, anything that would need another code path raises before any GPU work."""
+    from wannierberri_b200.data_K import check_parameters_K
+    check_parameters_K(None)
+    check_parameters_K(dict(fftlib="numpy", Emin=-np.inf, Emax=np.inf, random_gauge=False, degen_thresh_random_gauge=1e-4))
+    with pytest.raises(ValueError):
+        check_parameters_K(dict(fftlib="cufft"))
+    for bad in (dict(random_gauge=True), dict(Emin=0.), dict(k_list=[[0, 0, 0]])):
+        with pytest.raises(NotImplementedError):
+            check_parameters_K(bad)
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+    calcs = dict(dos=wb.calculators.static.DOS(Efermi=np.linspace(17, 18, 3)))
+    grid = wb.Grid(fe, NKdiv=[1, 1, 1], NKFFT=[2, 2, 2])
+    with pytest.raises(NotImplementedError):
+        wb.run(fe, grid, calcs, data_k_class=object)
+    with pytest.raises(ValueError):
+        wb.run(fe, grid, calcs, parameters_K=dict(fftlib="cufft"))

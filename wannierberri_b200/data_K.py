@@ -22,12 +22,28 @@ def engine_for(system, device=0):
     return eng
 
 
+def check_parameters_K(parameters_K):
+    """`parameters_K` of run() / keyword arguments of Data_K (data_K/data_K.py:73-83).  `fftlib` names the CPU FFT
+    backend of the reference: there is one R->k transform here (the CUDA one), so a valid name is accepted and has no
+    effect, an unknown one raises as in fourier/fft.py:63; defaults of the other parameters are accepted, anything
+    else raises (no CPU fallback)."""
+    parameters_K = dict(parameters_K or {})
+    lib = parameters_K.pop("fftlib", "fftw")
+    if str(lib).lower() not in ("fftw", "numpy", "slow"):
+        raise ValueError(f"fftlib '{lib}' is unknown/not supported")
+    defaults = dict(Emin=-np.inf, Emax=np.inf, random_gauge=False)
+    for key in list(parameters_K):
+        if key in defaults and parameters_K[key] == defaults[key]:
+            parameters_K.pop(key)
+    parameters_K.pop("degen_thresh_random_gauge", None)   # read only with random_gauge=True
+    if parameters_K:
+        raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
+
+
 class Data_K_R:
 
     def __init__(self, system, dK, grid, Kpoint=None, device=0, **parameters_K):
-        unknown = set(parameters_K) - {"fftlib"}
-        if unknown:
-            raise NotImplementedError(f"parameters_K {sorted(unknown)} are not implemented on the GPU path")
+        check_parameters_K(parameters_K)
         self.system = system
         self.grid = grid
         self.Kpoint = Kpoint

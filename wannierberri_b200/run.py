@@ -12,7 +12,7 @@ import numpy as np
 from .calculators.static import adapt as adapt_static
 from .calculators import dynamic as _dyn
 from . import _lib
-from .data_K import engine_for
+from .data_K import engine_for, check_parameters_K, Data_K_R
 from .result import ResultDict
 from .system import as_system
 
@@ -53,8 +53,11 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
     `dump_results=True` (run_grid.py:62-63, 242-243): per-K-point results are pickled to
     `<file_Klist_path>/_Kp-<ik>.pickle` and dropped from memory; implies `allow_restart`.
 
-    Not implemented on the GPU path (raise, never fall back to a CPU loop): `parameters_K`,
-    `data_k_class` other than this package's."""
+    `parameters_K`: `fftlib` is accepted (and has no effect: the R->k transform is the CUDA one); non-default
+    `Emin` / `Emax` / `random_gauge` raise, as does a `data_k_class` other than this package's (no CPU fallback)."""
+    if data_k_class is not None and data_k_class is not Data_K_R:
+        raise NotImplementedError(f"data_k_class {getattr(data_k_class, '__name__', data_k_class)}: only this package's "
+                                  "Data_K_R runs on the GPU path")
     if dump_results:
         allow_restart = True
     if adpt_num_iter != 0 or restart or allow_restart:   # per-K-point results are kept: the refinement loop
@@ -62,8 +65,7 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
                              device, write_files, symmetrize, use_irred_kpt, parameters_K,
                              dict(restart=restart, allow_restart=allow_restart, restart_iteration=restart_iteration,
                                   Klist_part=Klist_part, file_Klist_path=file_Klist_path, dump_results=dump_results))
-    if parameters_K:
-        raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
+    check_parameters_K(parameters_K)
     system = as_system(system)
     pointgroup = getattr(system, "pointgroup", None)
     if (symmetrize or use_irred_kpt) and pointgroup is None:
@@ -166,8 +168,7 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
     ro.update(restart_opts or {})
     Klist_dir = ro["file_Klist_path"] if ro["file_Klist_path"] is not None else "_tmp_wb"   # run_grid.py:244-246
     file_Klist = os.path.join(Klist_dir, "K_list.pickle")
-    if parameters_K:
-        raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
+    check_parameters_K(parameters_K)
     system = as_system(system)
     pointgroup = getattr(system, "pointgroup", None)
     if (symmetrize or use_irred_kpt) and pointgroup is None:
