@@ -988,6 +988,26 @@ def test_adaptive_refinement_dump_results(wb, tmp_path):
         assert relerr(res.results[q].data, g[f"iter3_{q}"]) < RTOL, q
 
 
+def test_window_arguments_and_hole_like(wb):
+    """Emin / Emax / hole_like of StaticCalculator against the reference's own run (fixture of
+    tests/golden/make_golden_window.py): without the tetrahedron method Emin / Emax do not act (data_K.py:172-185),
+    hole_like flips the sign of Fermi-sea quantities (static.py:51-52); with tetra=True Emax acts on the inverse Fermi
+    sea only and neither edge on a Fermi-surface quantity."""
+    g = np.load(os.path.join(GOLDEN, "golden_synth_window.npz"))
+    sysg = wb.synthetic_system(6, rmax=1, seed=4242)
+    st = wb.calculators.static
+    Ef, win = g["Efermi"], dict(Emin=float(g["Emin"]), Emax=float(g["Emax"]))
+    calcs = dict(ahc_win_hole=st.AHC(Efermi=Ef, hole_like=True, **win),
+                 cumdos_win_hole=st.CumDOS(Efermi=Ef, hole_like=True, **win),
+                 dos_win_hole=st.DOS(Efermi=Ef, hole_like=True, **win),
+                 ahc_tetra_Emax=st.AHC(Efermi=Ef, tetra=True, Emax=win["Emax"]),
+                 dos_tetra_win=st.DOS(Efermi=Ef, tetra=True, **win))
+    res = wb.run(sysg, wb.Grid(sysg, NKdiv=[2, 2, 2], NKFFT=[3, 3, 3]), calcs)
+    for q in calcs:
+        tol = 1e-6 if q == "dos_tetra_win" else RTOL   # der = 1 tetrahedron weights (see TETRA_CASES)
+        assert relerr(res.results[q].data, g[q]) < tol, q
+
+
 def test_adaptive_refinement_tetra_and_kubo(wb):
     """run(adpt_num_iter = 2) driven by tetrahedron-method and Kubo calculators (evaluated one K-point per call, the
     tetrahedron cell of a refined K-point is its own dK / NKFFT, grid/Kpoint.py:107-109) next to a plain static one,

@@ -85,11 +85,14 @@ def test_calculator_windows_and_errors():
     assert [x.formula for x in m.specs()] == [_lib.MORB_HPM, _lib.OMEGA]
     assert st.AHC(Efermi=Ef, hole_like=True).constant_factor == -a.constant_factor
     assert st.AHC(Efermi=Ef, use_factor=False).specs()[0].factor == -1.0
-    for bad in (dict(tetra=True, hole_like=True), dict(k_resolved=True), dict(select_bands=[1]), dict(Emin=0.)):
+    for bad in (dict(tetra=True, hole_like=True), dict(k_resolved=True), dict(select_bands=[1]), dict(tetra=True, Emin=0.)):
         with pytest.raises(NotImplementedError):
             st.AHC(Efermi=Ef, **bad)
     with pytest.raises(ValueError):
         st.AHC(Efermi=5.0)
+    w = st.AHC(Efermi=Ef, Emin=13., Emax=20.)   # read by the tetrahedron method only (as in the reference)
+    assert (w.Emin, w.Emax) == (13., 20.) and w.specs()[0].factor == a.specs()[0].factor
+    st.DOS(Efermi=Ef, tetra=True, Emin=13., Emax=20.)   # fder = 1: neither edge acts
 
 
 def test_shard_bounds():

@@ -61,8 +61,6 @@ class StaticCalculator(Calculator):
             raise NotImplementedError("select_bands is not implemented on the GPU path")
         if smoother is not None and not callable(smoother):
             raise ValueError("smoother must be callable as smoother(A, axis=0) (wannierberri_b200.smoother or the reference's)")
-        if Emin != -np.inf or Emax != np.inf:
-            raise NotImplementedError("Emin/Emax band selection is not implemented on the GPU path")
         self.kwargs_formula = copy(kwargs_formula) if kwargs_formula is not None else {}
         unknown = set(self.kwargs_formula) - {"internal_terms", "external_terms"} - set(self.extra_kwargs_formula)
         if unknown:
@@ -78,6 +76,13 @@ class StaticCalculator(Calculator):
         assert hasattr(self, "Formula"), "Formula not set"
         if self.fder not in (0, 1, 2, 3):
             raise NotImplementedError(f"Derivatives  d^{self.fder}f/dE^{self.fder} is not implemented")
+        # Emin / Emax: the reference hands them to the band grouping, which reads them in the tetrahedron method only
+        # (data_K/data_K.py:172-185 ignores them; grid/tetrahedron.py:246-263: Emin = lower edge of the Fermi-sea
+        # group for fder = 0, Emax = upper edge of the inverse Fermi sea of hole_like).  Same here: no effect without
+        # tetra; the one case in which they would act raises.
+        self.Emin, self.Emax = Emin, Emax
+        if tetra and self.fder == 0 and Emin != -np.inf:
+            raise NotImplementedError("tetra=True with Emin (lower edge of the Fermi-sea group) is not implemented on the GPU path")
         self.constant_factor = constant_factor
         if self.hole_like and self.fder == 0:
             self.constant_factor *= -1
@@ -425,8 +430,11 @@ def adapt(calc):
     name = type(calc).__name__
     if name not in _BY_NAME:
         raise ValueError(f"calculator {name} is not available on the GPU path")
+    if calc.tetra and getattr(calc, "hole_like", False):
+        raise NotImplementedError("tetra=True with hole_like (inverse Fermi sea, der=-1) is not implemented on the GPU path")
     kw = dict(Efermi=np.array(calc.Efermi), tetra=calc.tetra, smoother=calc.smoother, use_factor=calc.use_factor,
               kwargs_formula=calc.kwargs_formula, hole_like=False, k_resolved=calc.k_resolved,
+              Emin=getattr(calc, "Emin", -np.inf), Emax=getattr(calc, "Emax", np.inf),
               select_bands=calc.select_bands, degen_thresh=calc.degen_thresh, degen_Kramers=calc.degen_Kramers,
               save_mode=calc.save_mode)
     fixed = ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf", "BerryDipole_FermiSea", "OmegaOmega")   # no constant_factor argument
