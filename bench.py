@@ -144,7 +144,7 @@ def _oracle_init():
     _oracle_block.sys = orc.OracleSystem.from_npz(FE)
 
 
-def cpu_baseline_1core(nkfft=(16, 16, 16)):
+def cpu_baseline_1core(nkfft=(20, 20, 20)):
     """oracle on 1 core, one K-block of the same workload (same system, same 2000 Fermi levels)."""
     _oracle_init()
     t0 = time.perf_counter()
@@ -156,18 +156,22 @@ def cpu_baseline_1core(nkfft=(16, 16, 16)):
 
 
 def run_reference_arm(args):
-    """`--impl reference`: the CPU port on all host cores; each step = one K-block of 8^3 k-points per core."""
+    """`--impl reference`: the CPU port on all host cores, on the SAME K-blocks the GPU arm evaluates (NKFFT = 20^3
+    sub-grids at the shifts of the 400^3 grid's K-list, same calculators and Fermi levels); each step = one K-block
+    per core (the reference parallelises over K-blocks, run_grid.py:258-265)."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import wannierberri_b200 as wb   # host-side grid only (K-list); no GPU work in this arm
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    nkfft = [8, 8, 8]
-    rng = np.random.default_rng(0)
+    shifts, factors = wb.Grid(wb.System_R.from_npz(FE), NKdiv=NKDIV, NKFFT=NKFFT).K_arrays()
+    cursor = [0]
     with mp.Pool(cores, initializer=_oracle_init) as pool:
         def step():
-            jobs = [(rng.random(3) / 400, nkfft) for _ in range(cores)]
-            return sum(pool.map(_oracle_block, jobs))
+            idx = (cursor[0] + np.arange(cores)) % len(factors)   # the GPU arm's K-list, consecutive K-blocks
+            cursor[0] += cores
+            return sum(pool.map(_oracle_block, [(shifts[i], NKFFT) for i in idx], chunksize=1))
         for _ in range(args.warmup):
             step()
         t0 = time.perf_counter()
@@ -176,12 +180,15 @@ def run_reference_arm(args):
             nk += step()
         dt = time.perf_counter() - t0
     value = nk / dt
-    sample = f"{cores} K-blocks of NKFFT={nkfft} per step (one per core), multiprocessing.Pool({cores}), BLAS threads = 1"
+    sample = (f"{cores} K-blocks of NKFFT={NKFFT} ({int(np.prod(NKFFT))} k-points each) per step, consecutive entries of the "
+              f"400^3 grid's K-list (the GPU arm's list), one per core: multiprocessing.Pool({cores}), BLAS threads = 1")
+    cfg = config(args.blocks, args.gpus)
+    cfg["reference_arm_step"] = {"blocks_per_step": cores, "NKFFT": NKFFT, "kpoints_per_step": cores * int(np.prod(NKFFT))}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "tests-data system (Fe_W90 of the reference), synthetic K-block shifts",
-        "config": config(args.blocks, args.gpus),
+        "vs_baseline": None, "dtype": "f64", "data": "tests-data system (Fe_W90 of the reference); K-block shifts of the 400^3 grid",
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))

@@ -16,3 +16,10 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _scratch_cwd(tmp_path, monkeypatch):
+    """run() writes `<fout_name>-<key>_iter-NNNN.{npz,dat}` and `_tmp_wb/` relative to the working directory, as the
+    reference does (run_grid.py:244-246,368): every test runs in its own scratch directory."""
+    monkeypatch.chdir(tmp_path)

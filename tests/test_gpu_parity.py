@@ -601,6 +601,104 @@ def test_full_size_properties(wb, fe):
     assert relerr(ahc_g, ahc) < 1e-10
 
 
+def _oracle_blocks(path, calcs, dKs, NKFFT):
+    """The oracle on a list of K-blocks, one process per block (each block is seconds of per-k Python loops):
+    list over blocks of {key: data}."""
+    import multiprocessing as mp
+    jobs = [(path, calcs, np.asarray(dK, dtype=float), list(NKFFT)) for dK in dKs]
+    if len(jobs) == 1:
+        return [_oracle_block_job(jobs[0])]
+    with mp.get_context("spawn").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+        return pool.map(_oracle_block_job, jobs)
+
+
+def _oracle_block_job(job):
+    path, calcs, dK, NKFFT = job
+    from oracle import wb_oracle as o
+    data = o.OracleDataK(o.OracleSystem.from_npz(path), dK, NKFFT)
+    return {key: o.CALCULATORS[name](data, Ef, **kw) for key, (name, Ef, kw) in calcs.items()}
+
+
+BENCH_EF = np.linspace(12.0, 22.0, 2000)   # bench.py EFERMI
+
+
+@pytest.mark.parametrize("rotate_method", [0, 4])
+def test_bench_config_block_vs_oracle(wb, fe, rotate_method):
+    """The EXACT configuration bench.py times (BASELINE config 2 split: K-blocks of NKFFT = 20^3 of the 400^3 K-list,
+    AHC + DOS, 2000 Fermi levels over 12..22 eV, default rotation method = the fused column-trimmed DMMA kernel)
+    against the oracle on identical inputs at 1e-8: one K-block alone, and a call over 3 K-blocks with unequal weights
+    (weighted sum and batch offsets)."""
+    st = wb.calculators.static
+    grid = wb.Grid(fe, NKdiv=[20, 20, 20], NKFFT=[20, 20, 20])
+    shifts, factors = grid.K_arrays()
+    sel = [0, 1234, 7999]
+    w = np.array([0.5, 0.2, 0.3])
+    calcs = dict(ahc=st.AHC(Efermi=BENCH_EF), dos=st.DOS(Efermi=BENCH_EF))
+    specs = [s for c in calcs.values() for s in c.specs()]
+    eng = wb.Engine(fe)
+    eng.set_option("rotate_method", rotate_method)
+    eng.plan([20, 20, 20], [s.formula for s in specs], external_terms=True)
+    ref = _oracle_blocks(os.path.join(GOLDEN, "fe_system.npz"),
+                         dict(ahc=("AHC", BENCH_EF, {}), dos=("DOS", BENCH_EF, {})), shifts[sel], [20, 20, 20])
+    one = eng.scan(shifts[sel[1:2]], np.ones(1), specs)
+    got = dict(ahc=calcs["ahc"].result(one[:1], fe.cell_volume).data, dos=calcs["dos"].result(one[1:], fe.cell_volume).data)
+    for q in got:
+        assert got[q].shape == ref[1][q].shape
+        assert relerr(got[q], ref[1][q]) < RTOL, (q, "single block")
+    three = eng.scan(shifts[sel], w, specs)
+    got = dict(ahc=calcs["ahc"].result(three[:1], fe.cell_volume).data, dos=calcs["dos"].result(three[1:], fe.cell_volume).data)
+    for q in got:
+        want = sum(wi * r[q] for wi, r in zip(w, ref))
+        assert relerr(got[q], want) < RTOL, (q, "three blocks")
+
+
+def test_baseline_config1_block_vs_oracle(wb, fe):
+    """BASELINE config 1 (48^3 grid as NKdiv = 4 x NKFFT = 12, AHC + DOS, 1001 Fermi levels 12..22 eV, no symmetry):
+    two K-blocks of 12^3 through run()'s engine path against the oracle at 1e-8."""
+    st = wb.calculators.static
+    Ef = np.linspace(12.0, 22.0, 1001)
+    shifts, factors = wb.Grid(fe, NKdiv=[4, 4, 4], NKFFT=[12, 12, 12]).K_arrays()
+    sel = [5, 63]
+    calcs = dict(ahc=st.AHC(Efermi=Ef), dos=st.DOS(Efermi=Ef))
+    specs = [s for c in calcs.values() for s in c.specs()]
+    eng = wb.Engine(fe)
+    eng.plan([12, 12, 12], [s.formula for s in specs], external_terms=True)
+    ref = _oracle_blocks(os.path.join(GOLDEN, "fe_system.npz"), dict(ahc=("AHC", Ef, {}), dos=("DOS", Ef, {})),
+                         shifts[sel], [12, 12, 12])
+    arr = eng.scan(shifts[sel], factors[sel], specs)
+    got = dict(ahc=calcs["ahc"].result(arr[:1], fe.cell_volume).data, dos=calcs["dos"].result(arr[1:], fe.cell_volume).data)
+    for q in got:
+        assert relerr(got[q], sum(f * r[q] for f, r in zip(factors[sel], ref))) < RTOL, q
+
+
+def test_baseline_config2_ahc_morb_block_vs_oracle(wb, fe):
+    """BASELINE config 2 as written: AHC + Morb (BB, CC channels, non-additive Morb_Hpm) on a 20^3 K-block of the 400^3
+    K-list, 2000 Fermi levels, against the oracle at 1e-8."""
+    st = wb.calculators.static
+    shifts, _ = wb.Grid(fe, NKdiv=[20, 20, 20], NKFFT=[20, 20, 20]).K_arrays()
+    calcs = dict(ahc=st.AHC(Efermi=BENCH_EF), morb=st.Morb(Efermi=BENCH_EF))
+    data = wb.Data_K_R(fe, shifts[4321], wb.Grid(fe, NKdiv=[20, 20, 20], NKFFT=[20, 20, 20]))
+    ref = _oracle_blocks(os.path.join(GOLDEN, "fe_system.npz"),
+                         dict(ahc=("AHC", BENCH_EF, {}), morb=("Morb", BENCH_EF, {})), shifts[4321:4322], [20, 20, 20])[0]
+    for q, c in calcs.items():
+        assert relerr(c(data).data, ref[q]) < RTOL, q
+
+
+def test_baseline_config3_te_block_vs_oracle(wb, te):
+    """BASELINE config 3: Te (24 WF, spinor), BerryDipole_FermiSurf + GME_orb_FermiSurf + GME_spin_FermiSurf, tetra=False,
+    one 20^3 K-block of the 200^3 K-list (NKdiv = 10), 401 Fermi levels 4..8 eV, against the oracle at 1e-8."""
+    st = wb.calculators.static
+    Ef = np.linspace(4.0, 8.0, 401)
+    grid = wb.Grid(te, NKdiv=[10, 10, 10], NKFFT=[20, 20, 20])
+    shifts, _ = grid.K_arrays()
+    names = ["BerryDipole_FermiSurf", "GME_orb_FermiSurf", "GME_spin_FermiSurf"]
+    data = wb.Data_K_R(te, shifts[321], grid)
+    ref = _oracle_blocks(os.path.join(GOLDEN, "te_system.npz"), {n: (n, Ef, {}) for n in names}, shifts[321:322],
+                         [20, 20, 20])[0]
+    for n in names:
+        assert relerr(getattr(st, n)(Efermi=Ef)(data).data, ref[n]) < RTOL, n
+
+
 def test_full_size_properties_next_rows(wb, te):
     """The kernels of the next-row formulae at BASELINE-size K-blocks (Te, 24 WF, NKFFT = 20^3): the rotated matrices of
     one call are processed in several sub-batches (33 .. 57 matrices per k-point), so additivity over the K-blocks of a

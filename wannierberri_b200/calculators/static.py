@@ -92,6 +92,10 @@ class StaticCalculator(Calculator):
         self.EFmin = self.Efermi[0] - self.extraEf * self.dEF
         self.EFmax = self.Efermi[-1] + self.extraEf * self.dEF
         self.nEF_extra = self.Efermi.shape[0] + 2 * self.extraEf
+        # the tetrahedron kernels evaluate the weights at Efermi[0] + i * dEF; the reference's weights_tetra takes the
+        # levels as they are (grid/tetrahedron.py:270-281), so anything but a uniform axis must not pass silently
+        if tetra and len(self.Efermi) > 2 and not np.allclose(np.diff(self.Efermi), self.dEF, rtol=1e-9, atol=1e-12 * abs(self.dEF)):
+            raise NotImplementedError("tetra=True needs uniformly spaced Efermi on the GPU path")
 
     # ---- what the engine must evaluate
     def _spec(self, formula=None, fder=None):

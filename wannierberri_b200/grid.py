@@ -17,6 +17,10 @@ def _one2three(x):
     return x
 
 
+def _iterate_vector(v1, v2):   # grid/grid.py:192-193
+    return ((x, y, z) for x in range(v1[0], v2[0]) for y in range(v1[1], v2[1]) for z in range(v1[2], v2[2]))
+
+
 class KpointBZ:
     """One K-block: `K` (reduced coordinates of the K-grid), shift of the FFT sub-grid `Kp_fullBZ`,
     weight `factor` (grid/Kpoint.py:20-38,75-77)."""
@@ -35,20 +39,45 @@ class KpointBZ:
 
 class Grid:
 
-    def __init__(self, system=None, NK=None, NKFFT=None, NKdiv=None, length=None, use_symmetry=False):
+    def __init__(self, system=None, NK=None, NKFFT=None, NKdiv=None, length=None, length_FFT=None, use_symmetry=True):
+        """grid/grid.py:129-139 + determineNK / autoNK (:196-266): every given grid must respect the point group of the
+        system (`PointGroup.symmetric_grid`), the automatic FFT grid is searched among the symmetric ones only, and
+        non-periodic directions get one k-point."""
         NKdiv, NKFFT, NK = _one2three(NKdiv), _one2three(NKFFT), _one2three(NK)
-        if length is not None and NK is None:
-            recip = 2 * np.pi * np.linalg.inv(system.real_lattice).T
-            NK = np.array(np.round(length / (2 * np.pi) * np.linalg.norm(recip, axis=1)), dtype=int)
-        if (NKdiv is not None) and (NKFFT is not None):
-            pass
-        elif NK is not None:
+        # GridAbstract.__init__ (grid.py:44-57): without `use_symmetry` the grid carries the trivial point group
+        pointgroup = getattr(system, "pointgroup", None) if use_symmetry else None
+        recip = 2 * np.pi * np.linalg.inv(system.real_lattice).T
+
+        def symmetric(nk):
+            return pointgroup is None or bool(pointgroup.symmetric_grid(nk))
+
+        if length is not None:
+            if NK is None:
+                NK = np.array(np.round(length / (2 * np.pi) * np.linalg.norm(recip, axis=1)), dtype=int)
+            else:
+                warnings.warn("length is disregarded in presence of NK")
+        if length_FFT is not None:
             if NKFFT is None:
-                # autoNK (grid.py:196-212) without point-group constraints: the smallest FFT grid
-                # between NKFFT_recommended and 2x that whose multiple is closest to NK
+                NKFFT = np.array(np.round(length_FFT / (2 * np.pi) * np.linalg.norm(recip, axis=1)), dtype=int)
+            else:
+                warnings.warn("length_FFT is disregarded in presence of NKFFT")
+        for name, nk in (("NKdiv", NKdiv), ("NK", NK), ("NKFFT", NKFFT)):
+            if nk is not None and not symmetric(nk):
+                raise AssertionError(f" {name}={nk} is not consistent with the given symmetry ")
+        if (NKdiv is not None) and (NKFFT is not None):
+            if NK is not None:
+                warnings.warn("NK is disregarded in presence of NKdiv,NKFFT")
+                NK = None
+        elif NK is not None:
+            if NKdiv is not None:
+                warnings.warn("NKdiv is disregarded in presence of NK or length")
+            if NKFFT is None:
+                # autoNK (grid.py:196-212): the smallest symmetric FFT grid in [rec, 3 rec), then among the symmetric
+                # grids in [min, 2 min) the one whose multiple is closest to NK
                 rec = np.array(system.NKFFT_recommended)
-                cands = np.array([[x, y, z] for x in range(rec[0], 2 * rec[0]) for y in range(rec[1], 2 * rec[1])
-                                  for z in range(rec[2], 2 * rec[2])])
+                sym1 = np.array([f for f in _iterate_vector(rec, rec * 3) if symmetric(f)])
+                fmin = sym1[np.argmin(sym1.prod(axis=1))]
+                cands = np.array([f for f in _iterate_vector(fmin, fmin * 2) if symmetric(f)])
                 div = np.array(np.round(NK[None, :] / cands), dtype=int)
                 div[div <= 0] = 1
                 change = div * cands / NK[None, :]
@@ -61,9 +90,13 @@ class Grid:
                              f"found NK={NK}, NKdiv={NKdiv}, NKFFT={NKFFT} ")
         if NK is not None and not np.all(NK == NKFFT * NKdiv):
             warnings.warn(f" the requested k-grid {NK} was adjusted to {NKFFT * NKdiv}. ")
+        notperiodic = np.logical_not(np.array(getattr(system, "periodic", (True, True, True)), dtype=bool))
+        NKdiv, NKFFT = np.array(NKdiv), np.array(NKFFT)
+        NKdiv[notperiodic] = 1
+        NKFFT[notperiodic] = 1
         self.div = NKdiv
         self.FFT = NKFFT
-        self.pointgroup = getattr(system, "pointgroup", None)
+        self.pointgroup = pointgroup
 
     @property
     def dense(self):
@@ -104,7 +137,7 @@ class Grid:
             K, factors = K[keep], fac.ravel()[keep]
         return K / self.FFT[None, :], factors
 
-    def get_K_list(self, use_symmetry=False, k_batch=None):
+    def get_K_list(self, use_symmetry=True, k_batch=None):
         dK = 1. / self.div
         shifts, factors = self.K_arrays(use_symmetry=use_symmetry)
         return [KpointBZ(K=s * self.FFT, dK=dK, NKFFT=self.FFT, factor=f) for s, f in zip(shifts, factors)]

@@ -15,7 +15,8 @@ class EnergyResult:
         self.transformTR, self.transformInv = transformTR, transformInv
         self.E_titles = list(E_titles)
         self.comment = comment
-        self.save_mode = save_mode
+        # result/result.py:7-11: the set of "bin" / "txt" named in the string (or an already parsed set)
+        self.save_mode = {m for m in ("bin", "txt") if m in save_mode}
         self.smoothers = list(smoothers)
 
     def __mul__(self, number):
@@ -82,20 +83,91 @@ class EnergyResult:
         return np.array([np.abs(d).max(), np.linalg.norm(d), np.linalg.norm(d[1:] - d[:-1])])
 
     def as_dict(self):
-        """same keys as energyresult.py:224-239."""
+        """same keys as energyresult.py:224-239; the transforms as the dictionaries of `Transform.as_dict`
+        (point_symmetry.py:459-460), so that the reference's `EnergyResult.from_npz` restores them."""
         d = {"E_titles": self.E_titles, "data": self.data, "rank": self.rank,
-             "transformTR": str(self.transformTR), "transformInv": str(self.transformInv), "comment": self.comment}
+             "transformTR": transform_as_dict(self.transformTR), "transformInv": transform_as_dict(self.transformInv),
+             "comment": self.comment}
         for i, E in enumerate(self.Energies):
             d[f"Energies_{i}"] = E
         return d
 
-    def save(self, name):
-        np.savez_compressed(name + ".npz", **self.as_dict())
+    def save(self, name):   # result/result.py:39-46
+        with open(name + ".npz", "wb") as f:
+            np.savez_compressed(f, **self.as_dict())
 
-    def savedata(self, name, prefix, suffix, i_iter):
+    def _write(self, data, datasm, i):   # energyresult.py:203-214
+        if i == len(self.Energies):
+            flat = list(data.reshape(-1)) + list(datasm.reshape(-1))
+            if np.iscomplexobj(data):
+                return ["    " + "    ".join(f"{x.real:15.6e} {x.imag:15.6e}" for x in flat)]
+            return ["    " + "    ".join(f"{x:15.6e}" for x in flat)]
+        return [f"{E:15.6e}    {line:s}" for j, E in enumerate(self.Energies[i]) for line in self._write(data[j], datasm[j], i + 1)]
+
+    def savetxt(self, name):
+        """the reference's text table (energyresult.py:216-224): energies, the data and the smoothed data per row"""
+        frmt = "{0:^31s}" if np.iscomplexobj(self.data) else "{0:^15s}"
+        head = "".join("#### " + line + "\n" for line in self.comment.split("\n"))
+        head += "#" + "    ".join(f"{t:^15s}" for t in self.E_titles) + " " * 8 + "    ".join(
+            frmt.format(b) for b in _get_head(self.rank) * 2) + "\n"
+        with open(name, "w") as f:
+            f.write(head + "\n".join(self._write(self.data, self.dataSmooth, 0)))
+
+    def savedata(self, name, prefix, suffix, i_iter):   # energyresult.py:241-248
         suffix = "-" + suffix if len(suffix) > 0 else ""
         prefix = prefix + "-" if len(prefix) > 0 else ""
-        self.save(prefix + name + suffix + f"_iter-{i_iter:04d}")
+        filename = prefix + name + suffix + f"_iter-{i_iter:04d}"
+        if "bin" in self.save_mode:
+            self.save(filename)
+        if "txt" in self.save_mode:
+            self.savetxt(filename + ".dat")
+
+    @classmethod
+    def from_npz(cls, file_npz):
+        """energyresult.py:83-112"""
+        res = np.load(file_npz, allow_pickle=True)
+        Energies = [res[f"Energies_{i}"] for i, _ in enumerate(res["E_titles"])]
+
+        def tr(key):
+            if key not in res.files or res[key] is None:
+                return None
+            return transform_from_dict(res[key].item())
+        return cls(Energies, res["data"], transformTR=tr("transformTR"), transformInv=tr("transformInv"),
+                   rank=int(res["rank"]), E_titles=list(res["E_titles"]),
+                   comment=str(res["comment"]) if "comment" in res.files else "undocumented")
+
+
+def _get_head(n):   # utility.py:96-100
+    return ["  "] if n <= 0 else [a + b for a in "xyz" for b in _get_head(n - 1)]
+
+
+# the pre-defined transforms of point_symmetry.py:504-509 under the names used in calculators/*.py of this package
+_TRANSFORMS = {"ident": dict(factor=1, conj=False, transpose_axes=None, swap_axes=None),
+               "odd": dict(factor=-1, conj=False, transpose_axes=None, swap_axes=None),
+               "trans": dict(factor=1, conj=False, transpose_axes=(1, 0), swap_axes=None),
+               "odd_trans_021": dict(factor=-1, conj=False, transpose_axes=(0, 2, 1), swap_axes=None)}
+
+
+def transform_as_dict(t):
+    """`Transform.as_dict()` (point_symmetry.py:459-460) of a transform given by name, or of the reference's object."""
+    if t is None:
+        return None
+    if hasattr(t, "as_dict"):
+        return t.as_dict()
+    return dict(_TRANSFORMS[t])
+
+
+def transform_from_dict(d):
+    """inverse of `transform_as_dict` for the pre-defined transforms (point_symmetry.py:512-527)"""
+    if d is None or isinstance(d, str):
+        return None
+    key = dict(factor=int(d.get("factor", 1)), conj=bool(d.get("conj", False)),
+               transpose_axes=None if d.get("transpose_axes") is None else tuple(d["transpose_axes"]),
+               swap_axes=None if d.get("swap_axes") is None else tuple(d["swap_axes"]))
+    for name, val in _TRANSFORMS.items():
+        if val == key:
+            return name
+    raise ValueError(f"transform {d} is not one of the pre-defined ones")
 
 
 class ResultDict:

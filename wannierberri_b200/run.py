@@ -43,12 +43,27 @@ def k_list_arrays(grid, use_irred_kpt):
             np.array([K.factor for K in K_list], dtype=float))
 
 
-def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetrize=False, fout_name="result",
+def _pointgroup_of(system):
+    """`system.pointgroup`; a system on which `set_pointgroup` was never called has the identity group (the reference's
+    `PointGroup()` with no generators, system/system.py:140-170), so `use_irred_kpt` / `symmetrize` are no-ops on it."""
+    pg = getattr(system, "pointgroup", None)
+    if pg is None:
+        from .symmetry import PointGroup
+        pg = PointGroup((), real_lattice=system.real_lattice)
+    return pg
+
+
+def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=True, symmetrize=True, fout_name="result",
         suffix="", parameters_K=None, file_Klist_path=None, restart=False, allow_restart=False, dump_results=False,
         restart_iteration=-1, Klist_part=10, parallel=True, print_Kpoints=False, adpt_mesh=2, adpt_fac=1,
         print_progress_step_time=5, print_progress_step_percent=1, data_k_class=None, k_batch=50,
-        device=None, write_files=False):
+        device=None, write_files=True):
     """Integrate `calculators` over the k-grid.  Returns a `ResultDict` of `EnergyResult`.
+
+    Signature and defaults of the reference (run_grid.py:118-142): symmetry-irreducible K-points and symmetrised
+    results by default (`use_irred_kpt=True` forces `symmetrize=True`, run_grid.py:233-234); after every iteration
+    each quantity is written to `<fout_name>-<key>[-<suffix>]_iter-NNNN.npz` / `.dat` by rank 0 (run_grid.py:368;
+    `write_files=False`, an extension of this package, switches that off).
 
     `dump_results=True` (run_grid.py:62-63, 242-243): per-K-point results are pickled to
     `<file_Klist_path>/_Kp-<ik>.pickle` and dropped from memory; implies `allow_restart`.
@@ -58,6 +73,8 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
     if data_k_class is not None and data_k_class is not Data_K_R:
         raise NotImplementedError(f"data_k_class {getattr(data_k_class, '__name__', data_k_class)}: only this package's "
                                   "Data_K_R runs on the GPU path")
+    if use_irred_kpt:   # run_grid.py:233-234: the irreducible wedge alone is meaningless without symmetrisation
+        symmetrize = True
     if dump_results:
         allow_restart = True
     if adpt_num_iter != 0 or restart or allow_restart:   # per-K-point results are kept: the refinement loop
@@ -67,9 +84,7 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
                                   Klist_part=Klist_part, file_Klist_path=file_Klist_path, dump_results=dump_results))
     check_parameters_K(parameters_K)
     system = as_system(system)
-    pointgroup = getattr(system, "pointgroup", None)
-    if (symmetrize or use_irred_kpt) and pointgroup is None:
-        raise ValueError("use_irred_kpt / symmetrize need system.pointgroup (System_R.set_pointgroup)")
+    pointgroup = _pointgroup_of(system)
     calcs, dyn_calcs = {}, {}
     for key, c in calculators.items():
         # static.SHC and dynamic.SHC share their class name: a Kubo calculator is the one that carries a frequency axis
@@ -136,7 +151,7 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=False, symmetr
         results[key] = c.result(mine, system.cell_volume)
     for (key, c), a, raw in zip(dyn_calcs.items(), arrays[nstatic:], karrays):
         results[key] = c.result(a.view(raw.dtype).reshape(raw.shape))
-    if symmetrize:  # linear: applied once to the weighted sum instead of per K-point (run_grid.py:258-265)
+    if symmetrize and pointgroup.size > 1:  # linear: applied once to the weighted sum instead of per K-point (run_grid.py:258-265)
         results = {key: r.symmetrized(pointgroup) for key, r in results.items()}
     res = ResultDict(results)
     if write_files and rank == 0:
@@ -170,9 +185,7 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
     file_Klist = os.path.join(Klist_dir, "K_list.pickle")
     check_parameters_K(parameters_K)
     system = as_system(system)
-    pointgroup = getattr(system, "pointgroup", None)
-    if (symmetrize or use_irred_kpt) and pointgroup is None:
-        raise ValueError("use_irred_kpt / symmetrize need system.pointgroup (System_R.set_pointgroup)")
+    pointgroup = _pointgroup_of(system)
     periodic = getattr(system, "periodic", (True, True, True))
     calcs, slow_calcs = {}, {}   # slow: tetrahedron / Kubo calculators, evaluated one K-point per call
     for key, c in calculators.items():
@@ -302,7 +315,7 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
             for key, c in slow_calcs.items():
                 arrs = slow[key][j - slow_lo]
                 res[key] = c.result(arrs[0]) if isinstance(c, _dyn.DynamicCalculator) else c.result(arrs, system.cell_volume)
-            if symmetrize:   # per K-point here: K.max must see the symmetrised result (run_grid.py:258-265)
+            if symmetrize and pointgroup.size > 1:   # per K-point here: K.max must see the symmetrised result (run_grid.py:258-265)
                 res = {key: r.symmetrized(pointgroup) for key, r in res.items()}
             res = ResultDict(res)
             K_list[i].set_result(res)
