@@ -760,6 +760,38 @@ def test_run_symmetric_vs_upstream_golden(wb):
     assert np.abs(a[:, :2]).max() < 1e-12 * np.abs(a[:, 2]).max()
 
 
+def test_run_defaults_are_the_references(wb, tmp_path):
+    """run(system, grid, calculators) with NO further arguments is the reference's default mode (run_grid.py:118-142,
+    233-234, 368): symmetry-irreducible K-list + symmetrised results (the upstream `Fe_W90_sym-*` goldens were made this
+    way), `use_irred_kpt=True` forces `symmetrize` on, the result files `<fout_name>-<key>_iter-0000.{npz,dat}` are
+    written, and a system without a point group runs as one with the identity group."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_sym.npz"))
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"), pointgroup=["C4z", "C2x*TimeReversal", "Inversion"])
+    Ef = g["Efermi"]
+    st = wb.calculators.static
+    calcs = dict(ahc=st.AHC(Efermi=Ef), Morb=st.Morb(Efermi=Ef, save_mode="bin"))
+    grid = wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2])
+    res = wb.run(fe, grid, calcs, fout_name=str(tmp_path / "out"))
+    for q in calcs:
+        assert relerr(res.results[q].data, g["upstream_golden_" + q]) < RTOL, q
+    forced = wb.run(fe, grid, calcs, use_irred_kpt=True, symmetrize=False, write_files=False)   # ADVICE r1: must not skip the symmetrisation
+    for q in calcs:
+        assert relerr(forced.results[q].data, g["upstream_golden_" + q]) < RTOL, q
+    from wannierberri_b200.result import EnergyResult
+    back = EnergyResult.from_npz(str(tmp_path / "out-ahc_iter-0000.npz"))
+    assert np.array_equal(back.data, res.results["ahc"].data) and back.transformTR == "odd"
+    assert (tmp_path / "out-ahc_iter-0000.dat").is_file() and (tmp_path / "out-Morb_iter-0000.npz").is_file()
+    assert not (tmp_path / "out-Morb_iter-0000.dat").exists()
+    bare = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"))     # no point group: identity
+    a = wb.run(bare, wb.Grid(bare, NK=[4, 4, 4], NKFFT=[2, 2, 2]), dict(ahc=calcs["ahc"]), write_files=False)
+    b = wb.run(bare, wb.Grid(bare, NK=[4, 4, 4], NKFFT=[2, 2, 2]), dict(ahc=calcs["ahc"]), use_irred_kpt=False, symmetrize=False,
+               write_files=False)
+    assert np.array_equal(a.results["ahc"].data, b.results["ahc"].data)
+    g0 = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    if "upstream_golden_ahc" in g0.files:
+        assert relerr(a.results["ahc"].data, g0["upstream_golden_ahc"]) < RTOL
+
+
 @pytest.mark.parametrize("fder", [0, 1, 2, 3])
 def test_fder_stencils_vs_upstream_files(wb, fe, fder):
     """StaticCalculator(Formula=Identity, fder=0..3): the finite-difference stencils of the scan (static.py:137-147)

@@ -283,3 +283,88 @@ def test_parameters_K_and_data_k_class():
         wb.run(fe, grid, calcs, data_k_class=object)
     with pytest.raises(ValueError):
         wb.run(fe, grid, calcs, parameters_K=dict(fftlib="cufft"))
+
+
+def _import_reference():
+    """the reference package from /root/reference (container only; absent on the GPU box)"""
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "wannierberri")):
+        pytest.skip("reference tree not present")
+    stubs = os.path.join(ROOT, "oracle", "stubs")
+    sys.path[:0] = [ref, stubs]
+    try:
+        import wannierberri
+        return wannierberri
+    except Exception as err:   # pragma: no cover
+        pytest.skip(f"reference not importable: {err}")
+    finally:
+        sys.path.remove(ref)
+        sys.path.remove(stubs)
+
+
+def test_result_files_interchangeable_with_reference(tmp_path):
+    """`EnergyResult.savedata` writes what the reference writes (energyresult.py:224-248): `<prefix>-<key>_iter-NNNN.npz`
+    with the transforms as `Transform.as_dict()` dictionaries, plus the `.dat` table when "txt" is in `save_mode`; the
+    reference's `EnergyResult.from_npz` reads the file back with its symmetry behaviour intact, and this package reads
+    a file written by the reference."""
+    from wannierberri_b200.result import EnergyResult
+    Ef = np.linspace(0., 1., 4)
+    data = np.arange(12.).reshape(4, 3)
+    r = EnergyResult(Ef, data, transformTR="odd", transformInv="ident", comment="two\nlines", save_mode="bin+txt")
+    r.savedata("ahc", str(tmp_path / "res"), "tag", 3)
+    npz, dat = tmp_path / "res-ahc-tag_iter-0003.npz", tmp_path / "res-ahc-tag_iter-0003.dat"
+    assert npz.is_file() and dat.is_file()
+    lines = dat.read_text().split("\n")
+    assert lines[0] == "#### two" and lines[1] == "#### lines" and lines[2].startswith("#") and len(lines) == 3 + 4
+    assert np.allclose(np.array(lines[3].split(), dtype=float), [0., 0., 1., 2., 0., 1., 2.])
+    back = EnergyResult.from_npz(str(npz))
+    assert back.transformTR == "odd" and back.transformInv == "ident" and np.array_equal(back.data, data)
+    EnergyResult(Ef, data, transformTR="odd", transformInv="ident", save_mode="bin").savedata("x", str(tmp_path / "b"), "", 0)
+    assert (tmp_path / "b-x_iter-0000.npz").is_file() and not (tmp_path / "b-x_iter-0000.dat").exists()
+    wberri = _import_reference()
+    from wannierberri.symmetry.point_symmetry import transform_odd, transform_ident
+    ref = wberri.result.EnergyResult.from_npz(str(npz))
+    assert ref.transformTR == transform_odd and ref.transformInv == transform_ident
+    assert np.array_equal(ref.data, data) and ref.rank == 1
+    ref.save(str(tmp_path / "fromref"))
+    mine = EnergyResult.from_npz(str(tmp_path / "fromref.npz"))
+    assert mine.transformTR == "odd" and mine.transformInv == "ident" and np.array_equal(mine.data, data)
+
+
+def test_grid_respects_point_group_and_periodicity():
+    """determineNK / autoNK (grid/grid.py:196-266): grids that break the point group are refused, the automatic FFT
+    grid is searched among the symmetric ones, non-periodic directions get one k-point; against the reference's Grid
+    where it is importable."""
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"), pointgroup=["C4z", "C2x*TimeReversal", "Inversion"])
+    with pytest.raises(AssertionError):
+        wb.Grid(fe, NKdiv=[2, 3, 2], NKFFT=[4, 4, 4])     # C4z maps x on y: 2 != 3
+    with pytest.raises(AssertionError):
+        wb.Grid(fe, NK=[8, 8, 8], NKFFT=[4, 2, 4])
+    wb.Grid(fe, NKdiv=[2, 3, 2], NKFFT=[4, 4, 4], use_symmetry=False)   # trivial group: anything goes
+    g = wb.Grid(fe, NK=[30, 30, 30])
+    assert fe.pointgroup.symmetric_grid(g.FFT) and fe.pointgroup.symmetric_grid(g.div)
+    te = wb.System_R.from_npz(os.path.join(GOLDEN, "te_system.npz"), pointgroup=["C3z", "C2x", "TimeReversal"])
+    gt = wb.Grid(te, NK=[30, 30, 40])
+    assert gt.FFT[0] == gt.FFT[1] and gt.div[0] == gt.div[1]
+    slab = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+    slab.periodic = np.array([True, True, False])
+    gs = wb.Grid(slab, NKdiv=[2, 2, 2], NKFFT=[4, 4, 4])
+    assert list(gs.div) == [2, 2, 1] and list(gs.FFT) == [4, 4, 1]
+    wberri = _import_reference()
+    from wannierberri.grid.grid import determineNK
+    from wannierberri.symmetry.point_symmetry import PointGroup
+    for system, gens, NK in ((fe, ["C4z", "C2x*TimeReversal", "Inversion"], [30, 30, 30]), (fe, ["C4z", "C2x*TimeReversal", "Inversion"], [48, 48, 48]),
+                             (te, ["C3z", "C2x", "TimeReversal"], [30, 30, 40]), (te, ["C3z", "C2x", "TimeReversal"], [17, 17, 9])):
+        pg = PointGroup(gens, real_lattice=system.real_lattice)
+        div, fft = determineNK(np.array([True] * 3), None, None, np.array(NK), np.array(system.NKFFT_recommended), pg)
+        mine = wb.Grid(system, NK=NK)
+        assert np.array_equal(mine.div, div) and np.array_equal(mine.FFT, fft), (NK, mine.div, mine.FFT, div, fft)
+
+
+def test_tetra_needs_uniform_fermi_axis():
+    st = wb.calculators.static
+    st.DOS(Efermi=np.linspace(0, 1, 11), tetra=True)
+    st.DOS(Efermi=np.array([0., 0.1, 0.3]))                 # plain scan: the reference does not check either
+    with pytest.raises(NotImplementedError):
+        st.DOS(Efermi=np.array([0., 0.1, 0.3]), tetra=True)
+    assert wb.calculators.dynamic.JDOS(Efermi=np.linspace(0, 1, 3), omega=np.linspace(0, 1, 3)).spec().external_terms == 0

@@ -72,6 +72,12 @@ class JDOS(DynamicCalculator):
         super().__init__(**kwargs)
         self.sigma = self.smr_fixed_width
 
+    @property
+    def external_terms(self):
+        """JDOS reads band energies only (dynamic.py:146-162): no AA channel is asked of the plan, so it runs on a
+        system that holds nothing but Ham, as in the reference."""
+        return False
+
 
 class OpticalConductivity(DynamicCalculator):
     r"""Optical conductivity :math:`\sigma_{ab}(\omega)` (Kubo-Greenwood), S/m"""
