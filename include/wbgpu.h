@@ -189,6 +189,11 @@ int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* spec);
 int wbgpu_kubo_scan(wbgpu_ctx* ctx, int nblocks, const double* dK, const double* weight, const wbgpu_kubo_spec* spec,
                     const double* Efermi, const double* omega, double* out);
 
+/* Same with dK / weight / out resident in device memory (DEVICE pointers; Efermi / omega stay HOST pointers: they are
+ * parameters of the scan like the spec); asynchronous on the context's stream. */
+int wbgpu_kubo_scan_dev(wbgpu_ctx* ctx, int nblocks, const double* dK_dev, const double* weight_dev,
+                        const wbgpu_kubo_spec* spec, const double* Efermi, const double* omega, double* out_dev);
+
 /* Parity probes (HOST output pointers). One K-block each. */
 int wbgpu_kpoints(wbgpu_ctx* ctx, const double dK[3], double* kpoints /*[nk][3]*/);
 int wbgpu_eig(wbgpu_ctx* ctx, const double dK[3], double* E /*[nk][nw]*/, double* U /*[nk][nw][nw] c128 or NULL*/);

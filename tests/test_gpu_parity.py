@@ -786,7 +786,7 @@ def test_run_defaults_are_the_references(wb, tmp_path):
     a = wb.run(bare, wb.Grid(bare, NK=[4, 4, 4], NKFFT=[2, 2, 2]), dict(ahc=calcs["ahc"]), write_files=False)
     b = wb.run(bare, wb.Grid(bare, NK=[4, 4, 4], NKFFT=[2, 2, 2]), dict(ahc=calcs["ahc"]), use_irred_kpt=False, symmetrize=False,
                write_files=False)
-    assert np.array_equal(a.results["ahc"].data, b.results["ahc"].data)
+    assert relerr(a.results["ahc"].data, b.results["ahc"].data) < 1e-12   # (the scan sums with atomics: not bit-reproducible)
     g0 = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
     if "upstream_golden_ahc" in g0.files:
         assert relerr(a.results["ahc"].data, g0["upstream_golden_ahc"]) < RTOL

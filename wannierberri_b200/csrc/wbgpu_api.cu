@@ -76,8 +76,8 @@ struct wbgpu_ctx {
     double *d_E = nullptr, *d_evlabel = nullptr, *d_evval = nullptr;
     double *d_hist = nullptr, *d_cum = nullptr;
     size_t hist_cap = 0;
-    double *d_dK = nullptr, *d_weight = nullptr, *d_out = nullptr;
-    size_t dK_cap = 0, out_cap = 0;
+    double *d_dK = nullptr, *d_weight = nullptr, *d_out = nullptr, *d_axes = nullptr;
+    size_t dK_cap = 0, out_cap = 0, axes_cap = 0;
     int* d_sweeps = nullptr;
     // rotated matrices in global memory (generic DMMA GEMM path), per sub-batch of k-points
     double* d_xbar = nullptr;
@@ -225,7 +225,7 @@ extern "C" int wbgpu_destroy(wbgpu_ctx* c) {
     cudaFree(c->d_iRvec); cudaFree(c->d_T); cudaFree(c->d_sweeps);
     for (int k = 0; k < WBGPU_NKEYS; k++) cudaFree(c->d_XR[k]);
     cudaFree(c->d_xbar); cudaFree(c->d_mx); cudaFree(c->d_kent); cudaFree(c->d_kacc); cudaFree(c->d_shcJ); cudaFree(c->d_Ec);
-    cudaFree(c->d_hist); cudaFree(c->d_cum); cudaFree(c->d_dK); cudaFree(c->d_weight); cudaFree(c->d_out);
+    cudaFree(c->d_hist); cudaFree(c->d_cum); cudaFree(c->d_dK); cudaFree(c->d_weight); cudaFree(c->d_out); cudaFree(c->d_axes);
     delete c;
     return 0;
 }
@@ -1493,9 +1493,9 @@ extern "C" int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* s) {
     return -1;
 }
 
-extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, const double* weight, const wbgpu_kubo_spec* spec,
-                               const double* Efermi, const double* omega, double* out) {
-    if (!c || !dK || !weight || !spec || !Efermi || !omega || !out) return set_err("wbgpu_kubo_scan: null pointer argument");
+// dK_dev / weight_dev / out_dev: DEVICE pointers; Efermi / omega: HOST pointers (scan parameters, like the spec)
+static int kubo_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, const double* weight_dev, const wbgpu_kubo_spec* spec,
+                          const double* Efermi, const double* omega, double* out_dev) {
     if (!c->planned) return set_err("wbgpu_kubo_scan: call wbgpu_plan first");
     const int64_t nout = wbgpu_kubo_size(spec);
     if (nout < 0) return set_err("wbgpu_kubo_scan: bad spec (kind=%d nEF=%d nomega=%d)", spec->kind, spec->nEF, spec->nomega);
@@ -1541,14 +1541,11 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     win.degen_Kramers = spec->degen_Kramers; win.sea = 0; win.nEFx = nEF;
     win.Ebmin = win.Ebmax = nullptr;
 
-    // device copies: dK | weight | Efermi | omega, accumulator D[nomega][nEF][NC] + output
-    const int nbk = std::max(nblocks, 1);
-    if (ensure(&c->d_dK, &c->dK_cap, sizeof(double) * (4 * (size_t)nbk + nEF + nom))) return 1;
-    double* d_w = c->d_dK + 3 * (size_t)nbk;
-    double* d_Ef = d_w + nbk;
+    // device copies of the axes: Efermi | omega; accumulator D[nomega][nEF][NC] + output
+    if (ensure(&c->d_axes, &c->axes_cap, sizeof(double) * ((size_t)nEF + nom))) return 1;
+    const double* d_w = weight_dev;
+    double* d_Ef = c->d_axes;
     double* d_om = d_Ef + nEF;
-    CK(cudaMemcpyAsync(c->d_dK, dK, sizeof(double) * 3 * nblocks, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_w, weight, sizeof(double) * nblocks, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_Ef, Efermi, sizeof(double) * nEF, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_om, omega, sizeof(double) * nom, cudaMemcpyHostToDevice, c->stream));
     const size_t nacc = (size_t)nom * nEF * NC;
@@ -1591,7 +1588,7 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
         const int nb = std::min(c->nb_max, nblocks - b0);
         const long nk = (long)nb * c->nk_block;
         stage_begin(c, WBGPU_STAGE_FOURIER);
-        if (run_fourier(c, c->d_dK + 3 * (size_t)b0, nb)) return 1;
+        if (run_fourier(c, dK_dev + 3 * (size_t)b0, nb)) return 1;
         stage_end(c);
         stage_begin(c, WBGPU_STAGE_EIGH);
         if (run_eigh(c, nk, rotated)) return 1;
@@ -1647,9 +1644,33 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
                                                                                                     c->d_kacc + nacc, shift ? 1 : 0);
     c->launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, c->d_kacc + nacc, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyAsync(out_dev, c->d_kacc + nacc, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToDevice, c->stream));
     stage_collect(c);
+    return 0;
+}
+
+extern "C" int wbgpu_kubo_scan_dev(wbgpu_ctx* c, int nblocks, const double* dK_dev, const double* weight_dev,
+                                   const wbgpu_kubo_spec* spec, const double* Efermi, const double* omega, double* out_dev) {
+    if (!c || !dK_dev || !weight_dev || !spec || !Efermi || !omega || !out_dev)
+        return set_err("wbgpu_kubo_scan_dev: null pointer argument");
+    return kubo_scan_impl(c, nblocks, dK_dev, weight_dev, spec, Efermi, omega, out_dev);
+}
+
+extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, const double* weight, const wbgpu_kubo_spec* spec,
+                               const double* Efermi, const double* omega, double* out) {
+    if (!c || !dK || !weight || !spec || !Efermi || !omega || !out) return set_err("wbgpu_kubo_scan: null pointer argument");
+    const int64_t nout = wbgpu_kubo_size(spec);
+    if (nout < 0) return set_err("wbgpu_kubo_scan: bad spec (kind=%d nEF=%d nomega=%d)", spec->kind, spec->nEF, spec->nomega);
+    CK(cudaSetDevice(c->device));
+    const int nbk = std::max(nblocks, 1);
+    if (ensure(&c->d_dK, &c->dK_cap, sizeof(double) * 4 * (size_t)nbk)) return 1;
+    if (ensure(&c->d_out, &c->out_cap, sizeof(double) * (size_t)nout)) return 1;
+    double* d_w = c->d_dK + 3 * (size_t)nbk;
+    CK(cudaMemcpyAsync(c->d_dK, dK, sizeof(double) * 3 * nblocks, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_w, weight, sizeof(double) * nblocks, cudaMemcpyHostToDevice, c->stream));
+    if (kubo_scan_impl(c, nblocks, c->d_dK, d_w, spec, Efermi, omega, c->d_out)) return 1;
+    CK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -129,6 +129,14 @@ class Engine:
             return out.view(np.complex128).reshape(spec.shape)
         return out.reshape(spec.shape)
 
+    def kubo_scan_dev(self, dK_dev, weight_dev, spec, Efermi, omega, out_dev):
+        """Device-resident variant of `kubo_scan`: torch CUDA tensors (float64) for dK[nb,3], weight[nb] and the flat
+        output (complex as re, im pairs); asynchronous on the context's stream."""
+        Efermi, omega = as_f64(Efermi), as_f64(omega)
+        check(self._L.wbgpu_kubo_scan_dev(self._ctx, int(dK_dev.shape[0]), C.c_void_p(dK_dev.data_ptr()),
+                                          C.c_void_p(weight_dev.data_ptr()), C.byref(spec), dptr(Efermi), dptr(omega),
+                                          C.c_void_p(out_dev.data_ptr())))
+
     # ------------------------------------------------------------------ parity probes
     def kpoints(self, dK):
         dK = as_f64(dK)
