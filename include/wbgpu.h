@@ -223,7 +223,11 @@ int wbgpu_fp64_peak(int device, int kind, double* tflops);
 int64_t wbgpu_kernel_launches(const wbgpu_ctx* ctx);
 /* last eigensolver launch: max Jacobi sweeps over k-points (diagnostic) */
 int wbgpu_last_eig_sweeps(const wbgpu_ctx* ctx);
-/* set / get which eigensolver is used: 0 = automatic, 1 = Jacobi (generic), 2 = Householder+QL */
+/* last wbgpu_eig call: k-points that the fast eigensolver handed to the Jacobi kernel (diagnostic) */
+int wbgpu_last_eig_resolved(const wbgpu_ctx* ctx);
+/* options; "eig_method": 0 = automatic (Householder + QL eigenvalues + twisted-factorisation eigenvectors for
+ * num_wann <= 24, Householder + QL with accumulated rotations above), 1 = Jacobi, 2 / 3 = Householder + QL with
+ * accumulated rotations (3: one k-point per warp in the reduction), 4 = as 0 with the thread-per-matrix reduction */
 int wbgpu_set_option(wbgpu_ctx* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus

@@ -164,7 +164,9 @@ def test_eigh_sizes_and_degeneracies(wb, nw, degenerate):
     # (method 3), on an odd number of k-points
     NKFFT, dK = ([3, 1, 3] if nw == 18 else [3, 2, 4]), [0.03, 0.01, 0.2]
     from wannierberri_b200 import _lib
-    for method in ((2, 3, 1) if nw == 18 else (2, 1) if nw <= 32 else (0, 1) if nw <= 40 else (0,)):
+    # method 0 = twisted-factorisation eigenvectors (nw <= 24), 2 / 3 = accumulated QL rotations, 4 = thread-per-matrix
+    # reduction, 1 = Jacobi
+    for method in ((0, 2, 3, 4, 1) if nw == 18 else (0, 2, 1) if nw <= 32 else (0, 1) if nw <= 40 else (0,)):
         eng = wb.Engine(sysg)
         eng.set_option("eig_method", method)
         eng.plan(NKFFT, [_lib.IDENTITY])

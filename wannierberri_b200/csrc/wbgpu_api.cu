@@ -31,6 +31,7 @@
 #include "wb_fsea.cuh"
 #include "wb_tetra.cuh"
 #include "wb_probe.cuh"
+#include "wb_launch.h"
 
 static thread_local std::string g_err;
 
@@ -104,7 +105,7 @@ struct wbgpu_ctx {
     double2* d_rot = nullptr;
     int *d_hdr = nullptr, *d_nsweep = nullptr, *d_faillist = nullptr, *d_nfail = nullptr;
     int64_t eig_fallbacks = 0;
-    int last_sweeps = 0;
+    int last_sweeps = 0, last_resolved = 0;
     int64_t launches = 0;
     int eig_method = 0;
     int ev_ncmax = 1;
@@ -211,7 +212,7 @@ extern "C" int wbgpu_create(wbgpu_ctx** out, int device, int nw, int nR, const i
     CK(cudaMemcpy(c->d_iRvec, iRvec, sizeof(int) * 3 * nR, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_T, cRvec_shifted, sizeof(double) * 3 * (size_t)nR * nw * nw, cudaMemcpyHostToDevice));
     c->h_iRvec.assign(iRvec, iRvec + 3 * (size_t)nR);
-    CK(cudaMalloc(&c->d_sweeps, sizeof(int)));
+    CK(cudaMalloc(&c->d_sweeps, 2 * sizeof(int)));   // [0] max Jacobi sweeps, [1] k-points re-solved by Jacobi
     CK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     *out = c;
     return 0;
@@ -262,6 +263,7 @@ extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
 
 extern "C" int64_t wbgpu_kernel_launches(const wbgpu_ctx* c) { return c ? c->launches : 0; }
 extern "C" int wbgpu_last_eig_sweeps(const wbgpu_ctx* c) { return c ? c->last_sweeps : 0; }
+extern "C" int wbgpu_last_eig_resolved(const wbgpu_ctx* c) { return c ? c->last_resolved : 0; }
 
 static int formula_rank(int f) {
     switch (f) {
@@ -610,8 +612,11 @@ static int run_fourier(wbgpu_ctx* c, const double* dK_dev, int nb) {
     return 0;
 }
 
+__global__ void wb_count_resolved_kernel(const int* __restrict__ nlist, int* __restrict__ total) { *total += *nlist; }
+
 static int launch_jacobi(wbgpu_ctx* c, long k0, long nk, bool want_U, const int* list, const int* nlist, long nblk_cap) {
     const int nw = c->nw;
+    if (nlist) wb_count_resolved_kernel<<<1, 1, 0, c->stream>>>(nlist, c->d_sweeps + 1);
     constexpr int WARPS = 4;
     int npair = (nw + 1) / 2;
     size_t smem = sizeof(cplx) * WARPS * (size_t)(2 * nw * (nw + 1) + 2 * npair + nw);
@@ -630,7 +635,15 @@ static int launch_ql(wbgpu_ctx* c, long k0, long nk, bool want_U) {
     const int nw = c->nw;
     constexpr int WARPS = 4;
     CK(cudaMemsetAsync(c->d_nfail, 0, sizeof(int), c->stream));
-    if constexpr (EXACT && NWP > 16 && NWP <= 18) {
+    // eig_method 0: tridiagonalisation, then eigenvalues + twisted-factorisation eigenvectors with a thread per matrix and
+    // the back-transformation with a lane per (matrix, vector) (wb_eigh_tf.cuh; 4 <= nw <= 24); 2 / 3: the rotation-stream
+    // QL kernels below (3 = one k-point per warp in the reduction); 4: as 0 with the thread-per-matrix reduction
+    // (wb_eigh_tpm.cuh, nw <= 20; measured slower than the two-k-points-per-warp kernel)
+    const bool tf = (c->eig_method == 0 || c->eig_method == 4) && nw >= 4 && nw <= 24;
+    int tpm = (c->eig_method == 4) ? wb_launch_tridiag_tpm(nw, c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U, c->stream) : -1;
+    if (tpm > 0) return set_err("CUDA error %s launching the thread-per-matrix tridiagonalisation", cudaGetErrorName((cudaError_t)tpm));
+    if (tpm == 0) {
+    } else if constexpr (EXACT && NWP > 16 && NWP <= 18) {
         if (c->eig_method != 3)   // two k-points per warp
             wb_tridiag2_kernel<NWP, WARPS><<<(unsigned)((nk + 2 * WARPS - 1) / (2 * WARPS)), WARPS * 32, 0, c->stream>>>(
                 c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U);
@@ -640,6 +653,21 @@ static int launch_ql(wbgpu_ctx* c, long k0, long nk, bool want_U) {
     } else {
         wb_tridiag_kernel<NWP, WARPS, EXACT><<<(unsigned)((nk + WARPS - 1) / WARPS), WARPS * 32, 0, c->stream>>>(
             c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U);
+    }
+    CK(cudaGetLastError());
+    if (tf) {
+        // (the eigenvector matrix Z of the tridiagonal, nw^2 doubles per k-point, borrows the rotation-stream buffer)
+        int rc = wb_launch_trideig(nw, want_U, k0, nk, c->d_dw, c->d_ew, c->d_E, (double*)c->d_rot, c->d_faillist, c->d_nfail,
+                                   c->stream);
+        if (rc) return set_err("CUDA error %s launching the tridiagonal eigensolver", cudaGetErrorName((cudaError_t)rc));
+        c->launches += 2;
+        if (want_U) {
+            rc = wb_launch_backtransform(nw, k0, nk, (const double*)c->d_rot, c->d_tau, c->d_U, c->stream);
+            if (rc) return set_err("CUDA error %s launching the back-transformation", cudaGetErrorName((cudaError_t)rc));
+            c->launches++;
+        }
+        // multiple eigenvalues beyond what the twisted factorisation resolves, unconverged QL: Jacobi (normally none)
+        return launch_jacobi(c, k0, nk, want_U, c->d_faillist, c->d_nfail, 148);
     }
     CK(cudaGetLastError());
     if (nw <= 24) {
@@ -712,7 +740,7 @@ static int launch_ql_large(wbgpu_ctx* c, long k0, long nk, bool want_U) {
 
 static int run_eigh(wbgpu_ctx* c, long nk, bool want_U) {
     const int nw = c->nw;
-    CK(cudaMemsetAsync(c->d_sweeps, 0, sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->d_sweeps, 0, 2 * sizeof(int), c->stream));
     if (nw > 32) {
         if (c->eig_method == 1) return launch_jacobi(c, 0, nk, want_U, nullptr, nullptr, 148L * 64);
         for (long k0 = 0; k0 < nk; k0 += c->eig_chunk)
@@ -1706,6 +1734,7 @@ extern "C" int wbgpu_eig(wbgpu_ctx* c, const double dK[3], double* E, double* U)
     CK(cudaMemcpyAsync(E, c->d_E, sizeof(double) * nk * c->nw, cudaMemcpyDeviceToHost, c->stream));
     if (U) CK(cudaMemcpyAsync(U, c->d_U, sizeof(cplx) * nk * c->nw * c->nw, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&c->last_sweeps, c->d_sweeps, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&c->last_resolved, c->d_sweeps + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -173,3 +173,8 @@ class Engine:
     @property
     def last_eig_sweeps(self):
         return int(self._L.wbgpu_last_eig_sweeps(self._ctx))
+
+    @property
+    def last_eig_resolved(self):
+        """k-points of the last `eig` call that the fast eigensolver handed to the Jacobi kernel"""
+        return int(self._L.wbgpu_last_eig_resolved(self._ctx))
