@@ -2,26 +2,37 @@
 #include "wb_launch.h"
 #include "wb_eigh_tf.cuh"
 
-template <int NW, bool VEC>
+template <int NW, bool VEC, int MINB_ = 0>
 static int launch_trideig(long k0, long nk, const double* d, const double* e, double* E, double* Z, int* fail_list, int* nfail,
                           cudaStream_t stream) {
-    constexpr int NT = 64;
+    constexpr int NT = 128;
+    constexpr int MINB = MINB_ ? MINB_ : !VEC ? 4 : (NW <= 18) ? 4 : (NW <= 24) ? 3 : 2;   // 128 / 168 / 255 registers per thread
     constexpr int smem = (NT / 32) * wb_trideig_smem_doubles_per_warp<NW>() * 8;
-    cudaError_t err = cudaFuncSetAttribute(wb_trideig_kernel<NW, NT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    auto kern = wb_trideig_kernel<NW, NT, MINB, VEC>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (err != cudaSuccess) return (int)err;
-    wb_trideig_kernel<NW, NT, VEC><<<(unsigned)((nk + NT - 1) / NT), NT, smem, stream>>>(k0, nk, d, e, E, Z, fail_list, nfail);
+    kern<<<(unsigned)((nk + NT - 1) / NT), NT, smem, stream>>>(k0, nk, d, e, E, Z, fail_list, nfail);
+    return (int)cudaGetLastError();
+}
+
+template <int NW, int MB, int MINB>
+static int launch_backtransform_t(long k0, long nk, const double* Z, const cplx* tau, cplx* VU, cudaStream_t stream) {
+    constexpr int smem = wb_backtransform_smem_bytes<NW, MB>();
+    constexpr int NT = (MB * NW + 31) / 32 * 32;
+    auto kern = wb_backtransform_kernel<NW, MB, MINB>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (err != cudaSuccess) return (int)err;
+    kern<<<(unsigned)((nk + MB - 1) / MB), NT, smem, stream>>>(k0, nk, Z, tau, VU);
     return (int)cudaGetLastError();
 }
 
 template <int NW>
 static int launch_backtransform(long k0, long nk, const double* Z, const cplx* tau, cplx* VU, cudaStream_t stream) {
-    constexpr int MB = 16;
-    constexpr int smem = wb_backtransform_smem_bytes<NW, MB>();
-    constexpr int NT = (MB * NW + 31) / 32 * 32;
-    cudaError_t err = cudaFuncSetAttribute(wb_backtransform_kernel<NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (err != cudaSuccess) return (int)err;
-    wb_backtransform_kernel<NW, MB><<<(unsigned)((nk + MB - 1) / MB), NT, smem, stream>>>(k0, nk, Z, tau, VU);
-    return (int)cudaGetLastError();
+    // 4.5 warps per CTA; three CTAs per SM at 128 registers per thread (nw <= 20: the 18 complex components of a vector
+    // and the staged reflector loads fit with ~0.4 KB of spills), measured faster than 7- and 9-warp CTAs at nw = 18
+    return launch_backtransform_t<NW, (144 / NW > 0 ? 144 / NW : 1), (NW <= 20) ? 3 : 2>(k0, nk, Z, tau, VU, stream);
 }
 
 #define WB_TF_SIZES WB_CASE(4) WB_CASE(5) WB_CASE(6) WB_CASE(7) WB_CASE(8) WB_CASE(9) WB_CASE(10) WB_CASE(11) WB_CASE(12) \

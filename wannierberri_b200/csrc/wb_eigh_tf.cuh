@@ -26,120 +26,221 @@
 #include "wb_tma.cuh"
 
 // ------------------------------------------------------------------------------------------ K2
+// Shared memory: two lane-minor arrays per warp (element i of lane's matrix at [32 i + lane]: conflict-free whatever
+// element the lanes touch) -- the QL working copy of (d, e), then the pristine (d, e) for the factorisations.
 template <int NW>
-__host__ __device__ constexpr int wb_trideig_smem_doubles_per_warp() { return 3 * NW * 32 + 32 * (NW + 1); }
+__host__ __device__ constexpr int wb_trideig_smem_doubles_per_warp() { return 2 * NW * 32; }
 
 #define WB_TF_RESTOL 64.      // residual bound of a vector, in units of eps |T|
 #define WB_TF_CTOL 0.03       // Gram-Schmidt window, in units of |T|
 #define WB_TF_ACCEPT 0.5      // component outside the earlier vectors below which the other twists are tried
 #define WB_TF_ACCEPT2 0.05    // ... below which the matrix goes to the Jacobi list
 
-// the vector of the twist index r from the multipliers of the two factorisations (z_r = 1); returns |z|^2
+// Z is stored in pairs of components, lane-minor per group of 32 matrices:
+//     Z[(((g NW + j) NP + i/2) 32 + lane) 2 + (i & 1)],   matrix = 32 g + lane from the start of the chunk, NP = ceil(NW/2),
+// eigenvector j (ascending), component i.  The thread-per-matrix kernel moves a vector with fully coalesced 16-byte
+// accesses (512 contiguous bytes per warp instruction); the back-transformation reads 16-byte pieces (half sectors).
+__host__ __device__ __forceinline__ size_t wb_tf_zsize(long nk, int nw) {
+    return (size_t)((nk + 31) / 32) * nw * ((nw + 1) / 2) * 64;
+}
 template <int NW>
-__device__ __forceinline__ double wb_tf_vector(const double (&lp)[NW - 1], const double (&um)[NW - 1], int r, double (&z)[NW]) {
+__device__ __forceinline__ const double2* wb_tf_zvec(const double* Z, long t, int j) {
+    constexpr int NP = (NW + 1) / 2;
+    return reinterpret_cast<const double2*>(Z) + (((size_t)(t >> 5) * NW + j) * NP) * 32 + (t & 31);
+}
+template <int NW>
+__device__ __forceinline__ void wb_tf_load_vec(const double2* __restrict__ zg, double (&v)[NW]) {
 #pragma unroll
-    for (int i = 0; i < NW; i++) z[i] = (i == r) ? 1. : 0.;
+    for (int i = 0; i < NW; i += 2) {
+        const double2 q = zg[(size_t)(i / 2) * 32];
+        v[i] = q.x;
+        if (i + 1 < NW) v[i + 1] = q.y;
+    }
+}
+template <int NW>
+__device__ __forceinline__ void wb_tf_store_vec(double2* __restrict__ zg, const double (&v)[NW]) {
 #pragma unroll
-    for (int i = NW - 2; i >= 0; i--)
-        if (i < r) z[i] = -lp[i] * z[i + 1];
+    for (int i = 0; i < NW; i += 2) zg[(size_t)(i / 2) * 32] = make_double2(v[i], (i + 1 < NW) ? v[i + 1] : 0.);
+}
+
+// One twisted factorisation of T - sigma (d, e in shared memory, lane-minor) and the vector of the twist index r =
+// argmin |gamma_i| among the indices that come AFTER (glast, rlast) in the order of increasing (|gamma|, index)
+// (glast < 0: the overall minimum).  Returns r (-1: none left), |gamma_r| in *gabs, |z|^2 in *n2, z (z_r = 1) in A.
+template <int NW>
+__device__ __forceinline__ int wb_tf_attempt(const double* __restrict__ dp, const double* __restrict__ ep, double sigma,
+                                             double pivmin, double glast, int rlast, double (&A)[NW], double (&B)[NW],
+                                             double* gabs, double* n2) {
+    // top-down: A[i] = l_i = e_i / D+_i, A[NW-1] = D+_{NW-1}
+    {
+        double dcur = dp[0] - sigma;
 #pragma unroll
-    for (int i = 0; i < NW - 1; i++)
-        if (i >= r) z[i + 1] = -um[i] * z[i];
+        for (int i = 0; i < NW - 1; i++) {
+            if (fabs(dcur) < pivmin) dcur = -pivmin;
+            const double ei = ep[i * 32];
+            const double l = ei * __drcp_rn(dcur);
+            A[i] = l;
+            dcur = fma(-l, ei, dp[(i + 1) * 32] - sigma);
+        }
+        A[NW - 1] = dcur;
+    }
+    // bottom-up: B[i] = u_i = e_i / D-_{i+1};  gamma_i = D-_i - l_{i-1} e_{i-1}  (gamma_{NW-1} = D+_{NW-1})
+    int r = -1;
+    double gr = CUDART_INF;
+    {
+        const double g = fabs(A[NW - 1]);
+        if ((g > glast) || (g == glast && NW - 1 > rlast)) { gr = g; r = NW - 1; }
+        double dcur = dp[(NW - 1) * 32] - sigma;
+#pragma unroll
+        for (int i = NW - 2; i >= 0; i--) {
+            if (fabs(dcur) < pivmin) dcur = -pivmin;
+            const double ei = ep[i * 32];
+            const double u = ei * __drcp_rn(dcur);
+            B[i] = u;
+            dcur = fma(-u, ei, dp[i * 32] - sigma);
+            const double ga = fabs((i > 0) ? fma(-A[i - 1], ep[(i - 1) * 32], dcur) : dcur);
+            const bool after = (ga > glast) || (ga == glast && i > rlast);
+            if (after && ga <= gr) { gr = ga; r = i; }   // (<=: ties resolve to the lower index, which comes first)
+        }
+    }
+    *gabs = gr;
+    if (r < 0) return r;
+    // the vector, in place: z_i (i < r) over l_i, z_{i+1} (i >= r) over u_i
+    {
+        double zn = 1.;
+#pragma unroll
+        for (int i = NW - 2; i >= 0; i--)
+            if (i < r) { zn = -A[i] * zn; A[i] = zn; }
+        zn = 1.;
+#pragma unroll
+        for (int i = 0; i < NW - 1; i++)
+            if (i >= r) { zn = -B[i] * zn; B[i] = zn; }
+#pragma unroll
+        for (int i = NW - 1; i >= 1; i--) A[i] = (i < r) ? A[i] : ((i == r) ? 1. : B[i - 1]);
+        if (r == 0) A[0] = 1.;
+    }
     double s0 = 0., s1 = 0.;
 #pragma unroll
     for (int i = 0; i + 1 < NW; i += 2) {
-        s0 = fma(z[i], z[i], s0);
-        s1 = fma(z[i + 1], z[i + 1], s1);
+        s0 = fma(A[i], A[i], s0);
+        s1 = fma(A[i + 1], A[i + 1], s1);
     }
-    if (NW & 1) s0 = fma(z[NW - 1], z[NW - 1], s0);
-    return s0 + s1;
+    if (NW & 1) s0 = fma(A[NW - 1], A[NW - 1], s0);
+    *n2 = s0 + s1;
+    return r;
 }
 
 // VEC = false: eigenvalues only (Zout unused)
-template <int NW, int NT, bool VEC>
-__global__ void __launch_bounds__(NT)
+template <int NW, int NT, int MINB, bool VEC>
+__global__ void __launch_bounds__(NT, MINB)
 wb_trideig_kernel(long k0, long nk, const double* __restrict__ din, const double* __restrict__ ein, double* __restrict__ Eout,
                   double* __restrict__ Zout, int* __restrict__ fail_list, int* __restrict__ nfail) {
+    static_assert(NW >= 2 && NW <= 31, "the split mask of the QL phase is one 32-bit word");
     extern __shared__ double smem_tf[];
-    constexpr int PW = wb_trideig_smem_doubles_per_warp<NW>();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* const base = smem_tf + (size_t)warp * PW;
-    double* const dp = base + lane;                 // pristine diagonal, element i at dp[32 i]
-    double* const ep = base + NW * 32 + lane;       // pristine off-diagonal
-    double* const dw = base + 2 * NW * 32 + lane;   // QL working diagonal -> sorted eigenvalues
-    double* const tile = base + 3 * NW * 32;        // [32][NW + 1]: QL working off-diagonal (as ew[32 i]), then the
-    double* const ew = tile + lane;                 //               transposition buffer of the vector stores
+    double* const dw = smem_tf + (size_t)warp * wb_trideig_smem_doubles_per_warp<NW>() + lane;
+    double* const ew = dw + NW * 32;
     long t = (long)blockIdx.x * NT + threadIdx.x;
     const bool live = t < nk;
     if ((long)blockIdx.x * NT + (threadIdx.x & ~31) >= nk) return;   // a warp without matrices (no CTA-wide barriers here)
-    if (!live) t = nk - 1;                          // idle lanes mirror the last matrix and write nothing
+    if (!live) t = nk - 1;                          // idle lanes mirror the last matrix through the QL phase
+    const double* const dg = din + t * NW;
+    const double* const eg = ein + t * NW;
     double tnorm = 0.;
     {
-        const double* dg = din + t * NW;
-        const double* eg = ein + t * NW;
         double eprev = 0.;
 #pragma unroll
         for (int i = 0; i < NW; i++) {
             const double di = dg[i], ei = (i < NW - 1) ? eg[i] : 0.;
-            dp[i * 32] = di;
-            ep[i * 32] = ei;
             dw[i * 32] = di;
             ew[i * 32] = ei;
             tnorm = fmax(tnorm, fabs(di) + fabs(ei) + fabs(eprev));
             eprev = ei;
         }
     }
-    // ---- implicit QL, eigenvalues only (EISPACK tql1 / "tqli" recurrences; the rotations are not kept)
+    // ---- implicit QL with Wilkinson shift, eigenvalues only (the recurrences of EISPACK tql1), organised in ROUNDS: in
+    // a round every lane runs ONE sweep of its own matrix at its own deflation level l, the warp iterates over the
+    // longest sweep.  A lane's split points (negligible e_i) live in a bit mask that the sweep itself updates -- the
+    // rotation that produces e_{i+1} tests it -- so there is no scan of the off-diagonal between sweeps.
     bool fail = false;
-    for (int l = 0; l < NW && !fail; l++) {
-        int iter = 0;
+    {
+        unsigned mask = 1u << (NW - 1);             // bit i: e_i is negligible (bit NW-1: sentinel)
+#pragma unroll
+        for (int i = 0; i < NW - 1; i++) {
+            const double dd = fabs(dw[i * 32]) + fabs(dw[(i + 1) * 32]);
+            if (fabs(ew[i * 32]) + dd == dd) mask |= 1u << i;
+        }
+        int l = 0, iter = 0;
         while (true) {
+            // deflate: d_l is an eigenvalue while e_l is negligible
+            {
+                const int adv = __ffs(~(mask >> l)) - 1;   // number of consecutive set bits from bit l
+                if (adv > 0) { l += adv; iter = 0; }
+            }
+            bool active = (l < NW - 1) && !fail;
+            if (active && ++iter > 40) { fail = true; active = false; }
+            if (!__any_sync(0xffffffffu, active)) break;
             int m = l;
-            for (; m < NW - 1; m++) {
-                const double dd = fabs(dw[m * 32]) + fabs(dw[(m + 1) * 32]);
-                if (fabs(ew[m * 32]) + dd == dd) break;
+            double s = 1., c = 1., p = 0., g = 0., dnext = 0., dd2 = 0.;
+            if (active) {
+                m = l + __ffs(mask >> (l + 1));     // first split above l (the sentinel bounds it)
+                const double el = ew[l * 32], dl = dw[l * 32];
+                g = (dw[(l + 1) * 32] - dl) * (0.5 * __drcp_rn(el));
+                const double r = sqrt(fma(g, g, 1.));
+                dnext = dw[m * 32];                  // d_{i+1} of the first rotation
+                g = dnext - dl + el * __drcp_rn(g + copysign(r, g));
+                mask &= ~(((1u << m) - 1u) & ~((1u << l) - 1u));    // bits l .. m-1 are decided again by this sweep
             }
-            if (m == l) break;
-            if (++iter > 40) { fail = true; break; }
-            const double el = ew[l * 32];
-            double g = (dw[(l + 1) * 32] - dw[l * 32]) * (0.5 * __drcp_rn(el));
-            double r = sqrt(fma(g, g, 1.));
-            g = dw[m * 32] - dw[l * 32] + el * __drcp_rn(g + copysign(r, g));
-            double s = 1., c = 1., p = 0.;
+            const int len = __reduce_max_sync(0xffffffffu, active ? (m - l) : 0);
             int i = m - 1;
-            for (; i >= l; i--) {
-                const double ei = ew[i * 32];
-                const double f = s * ei, b = c * ei;
-                const double h2 = fma(f, f, g * g);
-                double rinv;
-                if (h2 > 1e-280 && h2 < 1e280) {
-                    rinv = rsqrt(h2);
-                    r = h2 * rinv;
-                } else {                                 // out of the safe range of the plain formula
-                    r = hypot(f, g);
-                    rinv = (r != 0.) ? 1. / r : 0.;
+            for (int q = 0; q < len; q++, i--) {
+                if (active && i >= l) {
+                    const double ei = ew[i * 32], di = dw[i * 32];
+                    const double f = s * ei, b = c * ei;
+                    const double h2 = fma(f, f, g * g);
+                    double r, rinv;
+                    if (h2 > 1e-280 && h2 < 1e280) {
+                        rinv = rsqrt(h2);
+                        r = h2 * rinv;
+                    } else {                         // out of the safe range of the plain formula
+                        r = hypot(f, g);
+                        rinv = (r != 0.) ? 1. / r : 0.;
+                    }
+                    ew[(i + 1) * 32] = r;
+                    if (r == 0.) {                   // underflow: the sweep ends here (tql1)
+                        dw[(i + 1) * 32] = dnext - p;
+                        ew[m * 32] = 0.;
+                        mask |= 1u << (i + 1);
+                        active = false;              // (the next round starts from the same l)
+                    } else {
+                        s = f * rinv;
+                        c = g * rinv;
+                        g = dnext - p;
+                        const double r2 = (di - g) * s + 2. * c * b;
+                        p = s * r2;
+                        const double dnew = g + p;
+                        dw[(i + 1) * 32] = dnew;
+                        g = c * r2 - b;
+                        // e_{i+1} = r against the final d_{i+1}, d_{i+2} (i + 1 < m: e_m is set to zero below)
+                        if (i + 1 < m) {
+                            const double dd = fabs(dnew) + dd2;
+                            if (r + dd == dd) mask |= 1u << (i + 1);
+                        }
+                        dd2 = fabs(dnew);
+                        dnext = di;
+                        if (i == l) {                // end of the sweep
+                            const double dl = di - p;
+                            dw[l * 32] = dl;
+                            ew[l * 32] = g;
+                            ew[m * 32] = 0.;
+                            const double dd = fabs(dl) + dd2;
+                            if (fabs(g) + dd == dd) mask |= 1u << l;
+                        }
+                    }
                 }
-                ew[(i + 1) * 32] = r;
-                if (r == 0.) {                           // recover from underflow
-                    dw[(i + 1) * 32] -= p;
-                    ew[m * 32] = 0.;
-                    break;
-                }
-                s = f * rinv;
-                c = g * rinv;
-                g = dw[(i + 1) * 32] - p;
-                r = (dw[i * 32] - g) * s + 2. * c * b;
-                p = s * r;
-                dw[(i + 1) * 32] = g + p;
-                g = c * r - b;
             }
-            if (i >= l) continue;
-            dw[l * 32] -= p;
-            ew[l * 32] = g;
-            ew[m * 32] = 0.;
         }
     }
-    // ---- sort ascending (odd-even transposition network on registers)
+    // ---- sort ascending (odd-even transposition network on registers), write E
     {
         double w[NW];
 #pragma unroll
@@ -156,173 +257,118 @@ wb_trideig_kernel(long k0, long nk, const double* __restrict__ din, const double
 #pragma unroll
         for (int i = 0; i < NW; i++) {
             if (!(w[i] == w[i])) fail = true;        // NaN input
-            dw[i * 32] = w[i];
             if (live) Eout[(k0 + t) * NW + i] = w[i];
         }
     }
-    if (!VEC) {
-        if (fail && live) fail_list[atomicAdd(nfail, 1)] = (int)t;
+    if (!live) return;
+    if (!VEC || fail) {
+        if (fail) fail_list[atomicAdd(nfail, 1)] = (int)t;
         return;
     }
-    __syncwarp();   // the working off-diagonal is dead: its storage becomes the transposition buffer
+    // ---- eigenvectors.  The pristine (d, e) replace the QL working copy (this lane's slots only: no barrier).
+    double* const dp = dw;
+    double* const ep = ew;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        dp[i * 32] = dg[i];
+        ep[i * 32] = (i < NW - 1) ? eg[i] : 0.;
+    }
     const double eps = 2.220446049250313e-16;
     const double pivmin = fmax(eps * tnorm * 0.0009765625, 1e-290);
     const double ctol = WB_TF_CTOL * tnorm;
     const double restol = WB_TF_RESTOL * eps * tnorm;
-    double* const myrow = tile + lane * (NW + 1);
-    const long blk0 = (long)blockIdx.x * NT + (threadIdx.x & ~31);   // first matrix of this warp (chunk-relative)
-    double* const Zme = Zout + t * NW * NW;
+    const double* const Eme = Eout + (k0 + t) * NW;   // (this thread's own stores above)
+    // One loop iteration = ONE factorisation (a single inlined copy of it keeps the register allocation of the common
+    // path free of the rare one).  mode 0: the twist of smallest |gamma| for eigenvalue j; accepted unless the
+    // projection cancels it.  mode 1 (numerically multiple eigenvalue): the vectors of the other twists span the rest
+    // of the eigenspace -- try them by increasing |gamma| (decreasing weight in the eigenspace), remember the one with
+    // the largest component outside the earlier vectors.  mode 2: rebuild that one and store it.
+    int j = 0, mode = 0, rlast = -1, rbest = -1, ntrial = 0;
+    double glast = -1., best = 0., gbest = -1.;
 #pragma unroll 1
-    for (int j = 0; j < NW; j++) {
-        const double sigma = dw[j * 32];
-        double gam[NW], lp[NW - 1], um[NW - 1], z[NW];
-        // top-down pivots D+ (kept in gam until gamma is formed) and multipliers l+
-        {
-            double dcur = dp[0] - sigma;
-#pragma unroll
-            for (int i = 0; i < NW - 1; i++) {
-                if (fabs(dcur) < pivmin) dcur = -pivmin;
-                gam[i] = dcur;
-                const double ei = ep[i * 32];
-                const double l = ei * __drcp_rn(dcur);
-                lp[i] = l;
-                dcur = fma(-l, ei, dp[(i + 1) * 32] - sigma);
-            }
-            gam[NW - 1] = dcur;
-        }
-        // bottom-up pivots D-, multipliers u-, gamma_i = D+_i + D-_i - (d_i - sigma); r = argmin |gamma|
-        int r = NW - 1;
-        double gr = gam[NW - 1];
-        {
-            double dcur = dp[(NW - 1) * 32] - sigma;
-#pragma unroll
-            for (int i = NW - 2; i >= 0; i--) {
-                if (fabs(dcur) < pivmin) dcur = -pivmin;
-                const double ei = ep[i * 32];
-                const double u = ei * __drcp_rn(dcur);
-                um[i] = u;
-                const double di = dp[i * 32] - sigma;
-                dcur = fma(-u, ei, di);
-                const double g = gam[i] + (dcur - di);
-                gam[i] = g;
-                if (fabs(g) < fabs(gr)) { gr = g; r = i; }
-            }
-        }
-        double n2 = wb_tf_vector<NW>(lp, um, r, z);
-        double res = fabs(gr) * rsqrt(n2);           // |(T - sigma) z| / |z|
-        double scale = rsqrt(n2);
-#pragma unroll
-        for (int i = 0; i < NW; i++) z[i] *= scale;
-        // Gram-Schmidt window: earlier vectors with eigenvalues within ctol
+    while (j < NW) {
+        const double sigma = Eme[j];
+        double A[NW], B[NW];
+        double gabs, n2;
+        const int r = wb_tf_attempt<NW>(dp, ep, sigma, pivmin, glast, rlast, A, B, &gabs, &n2);
+        bool final = (mode == 2);
+        double keep = 1., res = 0.;
         int p0 = j;
-        while (p0 > 0 && sigma - dw[(p0 - 1) * 32] < ctol) p0--;
-        double keep = 1.;                            // norm left after the projection
-        if (p0 < j) {
-            // one projection pass over the window; the latest vector is still in this lane's row of the tile
-            auto project = [&](double(&v)[NW]) {
-                for (int p = j - 1; p >= p0; p--) {
-                    double dot = 0.;
-                    if (p == j - 1) {
+        auto project = [&]() {                       // A <- A minus its components along the vectors p0 .. j-1; |A|^2
+            for (int p = j - 1; p >= p0; p--) {
+                wb_tf_load_vec<NW>(wb_tf_zvec<NW>(Zout, t, p), B);
+                double dot = 0.;
 #pragma unroll
-                        for (int i = 0; i < NW; i++) dot = fma(myrow[i], v[i], dot);
+                for (int i = 0; i < NW; i++) dot = fma(B[i], A[i], dot);
 #pragma unroll
-                        for (int i = 0; i < NW; i++) v[i] = fma(-dot, myrow[i], v[i]);
-                    } else {
-                        const double* zg = Zme + (size_t)p * NW;
-#pragma unroll
-                        for (int i = 0; i < NW; i++) dot = fma(__ldcg(zg + i), v[i], dot);
-#pragma unroll
-                        for (int i = 0; i < NW; i++) v[i] = fma(-dot, __ldcg(zg + i), v[i]);
-                    }
-                }
-                double s = 0.;
-#pragma unroll
-                for (int i = 0; i < NW; i++) s = fma(v[i], v[i], s);
-                return s;
-            };
-            double k2 = project(z);
-            keep = sqrt(k2);
-            if (!(keep >= WB_TF_ACCEPT)) {
-                // numerically multiple eigenvalue: the vectors of the other twists span the rest of the eigenspace.
-                // Try them by increasing |gamma| (decreasing weight in the eigenspace); keep the best.
-                double best = (keep == keep) ? keep : 0., bres = res;
-                int rbest = r;
-                double glast = fabs(gr);
-                int rlast = r;
-                for (int trial = 1; trial < NW && best < WB_TF_ACCEPT; trial++) {
-                    // next twist: smallest |gamma| above the last one (ties by index)
-                    int rn = -1;
-                    double gn = CUDART_INF;
-#pragma unroll
-                    for (int i = 0; i < NW; i++) {
-                        const double a = fabs(gam[i]);
-                        const bool after = (a > glast) || (a == glast && i > rlast);
-                        if (after && (a < gn)) { gn = a; rn = i; }
-                    }
-                    if (rn < 0) break;
-                    glast = gn;
-                    rlast = rn;
-                    const double m2 = wb_tf_vector<NW>(lp, um, rn, z);   // (z is rebuilt from the best twist below)
-                    const double rc = gn * rsqrt(m2);
-                    if (!(rc <= restol)) continue;
-                    const double sc = rsqrt(m2);
-#pragma unroll
-                    for (int i = 0; i < NW; i++) z[i] *= sc;
-                    const double kc = sqrt(project(z));
-                    if (kc > best) { best = kc; bres = rc; rbest = rn; }
-                }
-                {
-                    n2 = wb_tf_vector<NW>(lp, um, rbest, z);
-                    scale = rsqrt(n2);
-#pragma unroll
-                    for (int i = 0; i < NW; i++) z[i] *= scale;
-                    k2 = project(z);
-                    res = bres;
-                }
-                keep = sqrt(k2);
-                if (!(keep == keep)) keep = 0.;
-                if (keep > 0.) {                         // second pass ("twice is enough") after a large cancellation
-                    const double s1 = 1. / keep;
-#pragma unroll
-                    for (int i = 0; i < NW; i++) z[i] *= s1;
-                    const double k3 = project(z);
-                    const double s2 = rsqrt(k3);
-#pragma unroll
-                    for (int i = 0; i < NW; i++) z[i] *= s2;
-                    res *= s1;
-                }
-            } else {
-                const double s1 = rsqrt(k2);
-#pragma unroll
-                for (int i = 0; i < NW; i++) z[i] *= s1;
-                res *= s1;
+                for (int i = 0; i < NW; i++) A[i] = fma(-dot, B[i], A[i]);
             }
+            double sq = 0.;
+#pragma unroll
+            for (int i = 0; i < NW; i++) sq = fma(A[i], A[i], sq);
+            return sq;
+        };
+        if (r >= 0) {
+            const double scale = rsqrt(n2);
+            res = gabs * scale;                      // |(T - sigma) z| / |z|
+#pragma unroll
+            for (int i = 0; i < NW; i++) A[i] *= scale;
+            // Gram-Schmidt window: earlier vectors with eigenvalues within ctol
+            while (p0 > 0 && sigma - Eme[p0 - 1] < ctol) p0--;
+            if (p0 < j) {
+                keep = sqrt(project());
+                if (!(keep == keep)) keep = 0.;
+            }
+            if (mode == 0 && keep >= WB_TF_ACCEPT) final = true;
         }
-        if (!(keep >= WB_TF_ACCEPT2) || !(res <= restol)) fail = true;
-        // ---- store vector j of the 32 matrices of the warp: Z[matrix][j][0..NW)
-        __syncwarp();
+        if (final) {
+            if (keep < 1.) {
+                const double s1 = (keep > 0.) ? 1. / keep : 0.;
 #pragma unroll
-        for (int i = 0; i < NW; i++) myrow[i] = z[i];
-        __syncwarp();
+                for (int i = 0; i < NW; i++) A[i] *= s1;
+                res *= s1;
+                if (keep < WB_TF_ACCEPT && keep > 0.) {   // second pass ("twice is enough") after a large cancellation
+                    const double s2 = rsqrt(project());
 #pragma unroll
-        for (int q = 0; q < NW; q++) {
-            const int idx = q * 32 + lane;
-            const int mm = idx / NW, ii = idx - mm * NW;
-            if (blk0 + mm < nk) Zout[((blk0 + mm) * NW + j) * NW + ii] = tile[mm * (NW + 1) + ii];
+                    for (int i = 0; i < NW; i++) A[i] *= s2;
+                }
+            }
+            if (r < 0 || !(keep >= WB_TF_ACCEPT2) || !(res <= restol)) fail = true;
+            wb_tf_store_vec<NW>(const_cast<double2*>(wb_tf_zvec<NW>(Zout, t, j)), A);
+            j++;
+            mode = 0; glast = -1.; rlast = -1; best = 0.; rbest = -1; gbest = -1.; ntrial = 0;
+        } else {
+            bool exhausted = (r < 0);
+            if (!exhausted) {
+                if (res <= restol) {
+                    if (keep > best) { best = keep; gbest = gabs; rbest = r; }
+                } else if (mode == 1) exhausted = true;     // |gamma| only grows from here
+                glast = gabs;
+                rlast = r;
+                mode = 1;
+                if (++ntrial >= NW) exhausted = true;
+            }
+            if (exhausted || best >= WB_TF_ACCEPT) {
+                // the attempt that follows (gbest, rbest - 1) in the order is (gbest, rbest); none found: the overall minimum
+                mode = 2;
+                glast = gbest;
+                rlast = rbest - 1;
+                if (rbest < 0) { glast = -1.; rlast = -1; fail = true; }
+            }
         }
     }
-    if (fail && live) fail_list[atomicAdd(nfail, 1)] = (int)t;
+    if (fail) fail_list[atomicAdd(nfail, 1)] = (int)t;
 }
 
 // ------------------------------------------------------------------------------------------ K3
 // U = H(0) H(1) ... H(NW-2) Z  for MB matrices per CTA; V (Householder vectors below the sub-diagonal, column k = vector k,
 // LAPACK zhetd2 UPLO = 'L' as written by wb_tridiag*_kernel) and U share the buffer VU: the CTA stages V in shared memory
-// before it writes U.  Z[matrix][j][i] real, eigenvector j ascending; U[matrix][i][j].
+// before it writes U.  Z real in the paired lane-minor layout above, eigenvector j ascending; U[matrix][i][j].
 template <int NW, int MB>
 __host__ __device__ constexpr int wb_backtransform_smem_bytes() { return MB * (NW * NW + 1) * 16 + MB * NW * 16 + 16; }
 
-template <int NW, int MB>
-__global__ void __launch_bounds__((MB * NW + 31) / 32 * 32)
+template <int NW, int MB, int MINB>
+__global__ void __launch_bounds__((MB * NW + 31) / 32 * 32, MINB)
 wb_backtransform_kernel(long k0, long nk, const double* __restrict__ Z, const cplx* __restrict__ tauin, cplx* __restrict__ VU) {
     extern __shared__ __align__(16) cplx smem_bt[];
     constexpr int VS = NW * NW + 1;                    // stride of a matrix (16-byte units): 2-3 neighbours in distinct banks
@@ -345,9 +391,10 @@ wb_backtransform_kernel(long k0, long nk, const double* __restrict__ Z, const cp
     const bool live = (m < nm);
     cplx u[NW];
     if (live) {
-        const double* zg = Z + ((m0 + m) * NW + j) * NW;
+        double zr[NW];
+        wb_tf_load_vec<NW>(wb_tf_zvec<NW>(Z, m0 + m, j), zr);
 #pragma unroll
-        for (int i = 0; i < NW; i++) u[i] = cmake(zg[i], 0.);
+        for (int i = 0; i < NW; i++) u[i] = cmake(zr[i], 0.);
     } else {
 #pragma unroll
         for (int i = 0; i < NW; i++) u[i] = cmake(0., 0.);
@@ -377,8 +424,7 @@ wb_backtransform_kernel(long k0, long nk, const double* __restrict__ Z, const cp
             u[i].y = fma(-ts.y, vv.x, u[i].y);
         }
     }
-    __syncthreads();   // (every thread is past its last read of the staged V of this CTA's own matrices)
-    if (live) {
+    if (live) {   // (in place: V of this CTA's own matrices was staged in shared memory before anything is written)
         cplx* Uo = VU + (k0 + m0 + m) * NW * NW;
 #pragma unroll
         for (int i = 0; i < NW; i++) Uo[i * NW + j] = u[i];

@@ -504,7 +504,8 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
         CK(cudaMalloc(&c->d_dw, sizeof(double) * ch * nw));
         CK(cudaMalloc(&c->d_ew, sizeof(double) * ch * nw));
         CK(cudaMalloc(&c->d_tau, sizeof(cplx) * ch * nw));
-        CK(cudaMalloc(&c->d_rot, sizeof(double2) * ch * c->capR));
+        // (also holds the tridiagonal eigenvector matrices of wb_eigh_tf.cuh: groups of 32 k-points x nw x 2 ceil(nw/2) doubles)
+        CK(cudaMalloc(&c->d_rot, std::max(sizeof(double2) * ch * c->capR, sizeof(double) * ((ch + 31) / 32) * 64 * nw * ((nw + 1) / 2))));
         CK(cudaMalloc(&c->d_hdr, sizeof(int) * ch * c->capS));
         CK(cudaMalloc(&c->d_nsweep, sizeof(int) * ch));
         CK(cudaMalloc(&c->d_faillist, sizeof(int) * ch));
