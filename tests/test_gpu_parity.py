@@ -134,6 +134,11 @@ def test_r_to_k(wb, fe, fe_orc, orc, NKFFT, dK):
     assert relerr(O, data._R_to_k(data._rotAA_R(), True)) < 1e-13
 
 
+def _lib_formula(name):
+    from wannierberri_b200 import _lib
+    return getattr(_lib, name)
+
+
 @pytest.mark.parametrize("which", ["fe", "te"])
 def test_eigh(wb, fe, te, fe_orc, te_orc, orc, which):
     sysg, syso = (fe, fe_orc) if which == "fe" else (te, te_orc)
@@ -238,6 +243,34 @@ def test_dh_full_channel_path(wb, fe, rotate_method):
         eng.close()
     for a, r in zip(*out):
         assert relerr(a, r) < 1e-11
+
+
+@pytest.mark.parametrize("nw", [4, 6, 8, 10, 12, 14, 16, 20, 22, 24])
+def test_fused_rotation_kernel_sizes(wb, nw):
+    """The compile-time-num_wann DMMA rotation + formula kernel (rotate_method 3; every even num_wann <= 24) against the
+    size-generic GEMM + formula kernels (rotate_method 4): AHC + Morb with all R-matrices random, with the d_a H channels
+    packed (columns trimmed to the bands below EFmax) and full, and on a spectrum of exactly degenerate pairs."""
+    st = wb.calculators.static
+    for degenerate in (False, True):
+        sysg = wb.synthetic_system(nw, rmax=1, seed=100 + nw, matrices=("Ham", "AA", "BB", "CC"), degenerate_pairs=degenerate)
+        eng = wb.Engine(sysg)
+        eng.plan([2, 3, 2], [_lib_formula("IDENTITY")])
+        E = eng.eig([0.01, 0.02, 0.03])
+        eng.close()
+        Ef = np.linspace(np.percentile(E, 20), np.percentile(E, 70), 41)
+        # (AHC + Morb at num_wann >= 22 exceeds the shared memory of an SM: the automatic choice falls back to method 4)
+        specs = st.AHC(Efermi=Ef).specs() + (st.Morb(Efermi=Ef).specs() if nw <= 20 else [])
+        res = {}
+        for method, packed in ((4, 1), (3, 1), (3, 0)):
+            eng = wb.Engine(sysg)
+            eng.set_option("rotate_method", method)
+            eng.set_option("dh_packed", packed)
+            eng.plan([2, 3, 2], [s.formula for s in specs])
+            res[(method, packed)] = eng.scan(np.array([[0.01, 0.02, 0.03], [0.3, 0.1, 0.2]]), np.array([0.5, 0.5]), specs)
+            eng.close()
+        for key in ((3, 1), (3, 0)):
+            for a, r in zip(res[key], res[(4, 1)]):
+                assert relerr(a, r) < 1e-10, (nw, degenerate, key)
 
 
 BLOCK_CASES = dict(

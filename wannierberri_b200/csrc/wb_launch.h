@@ -15,3 +15,11 @@ int wb_launch_tridiag_tpm(int nw, const cplx* rec, const WbLayout& L, long k0, l
 int wb_launch_trideig(int nw, bool vectors, long k0, long nk, const double* d, const double* e, double* E, double* Z,
                       int* fail_list, int* nfail, cudaStream_t stream);
 int wb_launch_backtransform(int nw, long k0, long nk, const double* Z, const cplx* tau, cplx* VU, cudaStream_t stream);
+
+// wb_rotate_mma.cuh: fused DMMA rotation + Omega / Morb_Hpm formulae, compile-time num_wann (even, 4 .. 24).
+// Returns -1 when the kernel does not cover the request (formula mask, num_wann, shared memory).
+struct WbWindow;
+struct WbEventLayout;
+int wb_launch_mma_events(int nw, bool trim, int rot_r2, const cplx* rec, const WbLayout& L, long nk, const double* E,
+                         const cplx* U, const WbWindow& win, const WbEventLayout& ev, double* label, double* val,
+                         int smem_optin, int sms, cudaStream_t stream);

@@ -143,8 +143,10 @@ wb_events_mma_kernel(const cplx* __restrict__ rec, WbLayout L, WbMmaPlan P, long
     static_assert(NW % 2 == 0 && NW <= 24, "even num_wann <= 24 (E rows are fetched by 16-byte-granular bulk copies)");
     constexpr int N2 = M::N2, NTRI = M::NTRI, KS = M::KS, K2 = M::K2, MT2 = M::MT2, NT3 = M::NT3, TPW = M::TPW,
                   LDY = M::LDY, LDC = M::LDC;
-    constexpr int LG = 7;                                  // partner-band groups of the formula stage
-    static_assert(NW * LG <= 128 && 128 * 6 <= K2 * LDY, "formula stage mapping");
+    // partner-band groups of the formula stage: thread = (band, group), NW x LG threads whose 6 partial sums fit Y[0]
+    constexpr int LG_T = 128 / NW, LG_Y = (K2 * LDY) / (6 * NW);
+    constexpr int LG = (LG_T < 7 ? LG_T : 7) < LG_Y ? (LG_T < 7 ? LG_T : 7) : LG_Y;
+    static_assert(LG >= 1 && NW * LG <= 128 && NW * LG * 6 <= K2 * LDY, "formula stage mapping");
     extern __shared__ __align__(16) double smem_m[];
     cplx* const Ustg = (cplx*)(smem_m + M::OFF_U);
     double* const Yp = smem_m + M::OFF_Y;
@@ -463,10 +465,12 @@ wb_events_mma_kernel(const cplx* __restrict__ rec, WbLayout L, WbMmaPlan P, long
                     }
                 }
             }
+            if (n < NW) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                part[threadIdx.x * 6 + c] = om[c];
-                part[threadIdx.x * 6 + 3 + c] = tt[c];
+                for (int c = 0; c < 3; c++) {
+                    part[threadIdx.x * 6 + c] = om[c];
+                    part[threadIdx.x * 6 + 3 + c] = tt[c];
+                }
             }
         }
         __syncthreads();

@@ -24,7 +24,6 @@
 #include "wb_rotate_formula.cuh"
 #include "wb_rotate_dmma.cuh"
 #include "wb_events_generic.cuh"
-#include "wb_rotate_mma.cuh"
 #include "wb_rotate_gemm.cuh"
 #include "wb_scan.cuh"
 #include "wb_kubo.cuh"
@@ -819,37 +818,15 @@ static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec)
     return groups;
 }
 
-template <int NW, bool TRIM>
-static int launch_mma_t(wbgpu_ctx* c, const EvGroup& G, long nk, WbMmaPlan P) {
-    size_t smem = wb_mma_smem_bytes<NW>(P);
-    if ((int)smem > c->smem_optin) return -1;
-    CK(cudaFuncSetAttribute(wb_events_mma_kernel<NW, TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+// fused DMMA rotation + formula kernel (translation units wb_rotate_mma_*.cu); returns -1 when it does not cover the request
+static int launch_mma_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    long nblk = std::min(nk, (long)sms * 2);
-    wb_events_mma_kernel<NW, TRIM><<<(unsigned)nblk, 128, smem, c->stream>>>(c->d_X, c->L, P, nk, c->d_E, c->d_U, G.win, G.ev,
-                                                                         c->d_evlabel, c->d_evval);
-    c->launches++;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-// returns -1 when this kernel does not cover the request
-static int launch_mma_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
-    WbMmaPlan P;
-#define WB_MMA_CASE(NWC)                                                                            \
-    case NWC:                                                                                       \
-        if (!wb_mma_make_plan<NWC>(c->L, G.ev.mask, G.ev.external_terms, &P)) return -1;            \
-        /* with trimmed columns step 2 has 5 stacked tiles (warp w2 == 0 carries two): give that warp the single  \
-           step-1 tile of the NEXT item (w1 == 3), they run between the same pair of barriers */           \
-        if (c->L.dH_herm && c->rotate_trim) for (int i = 0; i < P.nitem; i++) P.r2[i] = 2;              \
-        for (int i = 0; i < P.nitem; i++) if (c->rot_r2 >= 0) P.r2[i] = c->rot_r2;                  \
-        return (c->L.dH_herm && c->rotate_trim) ? launch_mma_t<NWC, true>(c, G, nk, P) : launch_mma_t<NWC, false>(c, G, nk, P);
-    switch (c->nw) {
-        WB_MMA_CASE(18)
-        default: return -1;
-    }
-#undef WB_MMA_CASE
+    const int rc = wb_launch_mma_events(c->nw, c->rotate_trim != 0, c->rot_r2, c->d_X, c->L, nk, c->d_E, c->d_U, G.win, G.ev,
+                                        c->d_evlabel, c->d_evval, c->smem_optin, sms, c->stream);
+    if (rc > 0) return set_err("CUDA error %s launching the fused rotation kernel", cudaGetErrorName((cudaError_t)rc));
+    if (rc == 0) c->launches++;
+    return rc;
 }
 
 static int ensure(double** p, size_t* cap, size_t need);
