@@ -23,6 +23,7 @@
  *                                         (run_grid.py:258-265,59-72; calculators/static.py:60-169)
  *   wbgpu_static_scan_tetra            <- the same with tetra=True (Data_K.tetraWeights, grid/tetrahedron.py)
  *   wbgpu_eig                          <- Data_K.E_K (data_K/data_K.py:211-218)
+ *   wbgpu_xbar                         <- Data_K_R.Xbar / Data_K._rotate (data_K/data_K_R.py:69-97, data_K/data_K.py:130-132)
  *   wbgpu_xk                           <- Rvectors.R_to_k / FFT_R_to_k.__call__
  *                                         (fourier/rvectors.py:496-506, fourier/fft.py:133-192)
  *   wbgpu_band_traces                  <- Formula_ln.trace per band group (formula/formula.py:76-79)
@@ -198,6 +199,10 @@ int wbgpu_kubo_scan_dev(wbgpu_ctx* ctx, int nblocks, const double* dK_dev, const
 int wbgpu_kpoints(wbgpu_ctx* ctx, const double dK[3], double* kpoints /*[nk][3]*/);
 int wbgpu_eig(wbgpu_ctx* ctx, const double dK[3], double* E /*[nk][nw]*/, double* U /*[nk][nw][nw] c128 or NULL*/);
 int wbgpu_xk(wbgpu_ctx* ctx, const double dK[3], int channel, double* X /*complex128, see enum*/);
+/* Hamiltonian-gauge matrices of one K-block for plug-in formulae:  Xbar(name, der) = U^dagger (d^der X) U
+ * (Data_K_R.Xbar, data_K/data_K_R.py:69-97).  channel: WBGPU_CH_HAM (der 0..3), WBGPU_CH_AA / ROTAA / BB / CC / SS
+ * (der 0..1); the plan must hold the channel.  X[nk][nw][nw][3]^(ncart + der) complex128, value components first. */
+int wbgpu_xbar(wbgpu_ctx* ctx, const double dK[3], int channel, int der, double* X);
 /* per-k, per-band-group traces of a formula: E_label[nk][nw], value[nk][nw][3^rank]; slot b is
  * used iff a kept group starts at band b (label -inf for the Fermi-sea group), else label=+inf */
 int wbgpu_band_traces(wbgpu_ctx* ctx, const double dK[3], const wbgpu_scan_spec* spec,

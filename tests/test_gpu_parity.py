@@ -245,6 +245,66 @@ def test_dh_full_channel_path(wb, fe, rotate_method):
         assert relerr(a, r) < 1e-11
 
 
+def test_data_k_plugin_attributes(wb, fe, fe_orc, orc):
+    """Plug-in hook #1 (data_K/data_K_R.py:69-97, data_K/data_K.py:211-326): what a user formula
+    reads from `Data_K_R` -- `E_K`, `UU_K`, `Xbar(name, der)`, `D_H`, `dEig_inv`, `delE_K`, `kpoints_all`, band groups
+    -- served by the CUDA kernels (`wbgpu_eig`, `wbgpu_xbar`).  Gauge-independent check of every matrix:
+    U Xbar U^dagger must be the Wannier-gauge matrix of the oracle."""
+    grid = wb.Grid(fe, NK=[6, 4, 4], NKFFT=[3, 2, 2])
+    dK = np.array([0.05, 0.125, 0.0625])
+    dk = wb.Data_K_R(fe, dK, grid)
+    data = orc.OracleDataK(fe_orc, dK, grid.FFT)
+    assert dk.nk == 12 and dk.num_wann == 18 and dk.nbands == 18
+    assert np.array_equal(dk.kpoints_all, orc.kpoints_all(grid.FFT, dK))
+    E, U = dk.E_K, dk.UU_K
+    assert relerr(E, data.E_K) < 1e-12
+    T = fe_orc.cRvec_shifted
+
+    def wannier(name, der):
+        X = data._rotAA_R() if name == "rotAA" else fe_orc.XX_R[name]
+        for _ in range(der):
+            X = orc.derivative(X, T)
+        return data._R_to_k(X, name in ("AA", "SS", "rotAA"))
+
+    for name, ders in (("Ham", (0, 1, 2, 3)), ("AA", (0, 1)), ("rotAA", (0, 1)), ("BB", (0, 1)), ("CC", (0, 1)), ("SS", (0, 1))):
+        for der in ders:
+            Xbar = dk.Xbar(name, der)
+            Xw = wannier(name, der)
+            assert Xbar.shape == Xw.shape, (name, der)
+            back = np.einsum("kia,kab...,kjb->kij...", U, Xbar, U.conj())
+            assert relerr(back, Xw) < 1e-11, (name, der)
+    assert relerr(np.einsum("kii->ki", dk.Xbar("Ham", 0)).real, E) < 1e-12
+    dE = E[:, :, None] - E[:, None, :]
+    inv = dk.dEig_inv
+    assert np.all(inv[np.abs(dE) < 1e-7] == 0.) and np.allclose(inv[np.abs(dE) > 1e-7] * dE[np.abs(dE) > 1e-7], 1.)
+    assert relerr(dk.D_H, -dk.Xbar("Ham", 1) * inv[..., None]) < 1e-14
+    assert relerr(dk.delE_K, np.einsum("kiia->kia", dk.Xbar("Ham", 1)).real) == 0.
+    for ik in (0, 7):
+        for kw in (dict(sea=True), dict(degen_thresh=0.05, degen_Kramers=True), dict(degen_thresh=0.3)):
+            got = dk.get_bands_in_range_groups_ik(ik, 16., 19., **kw)
+            want = orc.band_groups(data.E_K[ik], 16., 19., kw.get("degen_thresh", -1), kw.get("degen_Kramers", False),
+                                   sea=kw.get("sea", False))
+            assert set(got) == set(want) and all(abs(got[g] - want[g]) < 1e-9 or got[g] == want[g] for g in got)
+
+
+def test_plugin_formula_through_run(wb, fe):
+    """A user-defined Formula class (tests/plugin_formula.py, written against the plug-in interface only) evaluated by
+    `run()` on the GPU-resident Data_K_R, against the fixture that the UNMODIFIED reference produced with the same
+    source on its own Data_K_R (tests/golden/make_golden_plugin.py): Fermi-sea, Fermi-surface and a non-additive case."""
+    from plugin_formula import make_calculators
+    g = np.load(os.path.join(GOLDEN, "golden_plugin.npz"))
+    calcs = make_calculators(wb.calculators.static.StaticCalculator, g["Efermi"])
+    calcs["ahc"] = wb.calculators.static.AHC(Efermi=g["Efermi"])   # a fused scan next to the plug-ins in one run
+    res = wb.run(fe, wb.Grid(fe, NK=g["NK"], NKFFT=g["NKFFT"]), calcs, use_irred_kpt=False, symmetrize=False,
+                 write_files=False)
+    for key in ("user_sea", "user_surf", "user_weighted"):
+        assert res.results[key].data.shape == g[key].shape
+        assert relerr(res.results[key].data, g[key]) < RTOL, key
+    g0 = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))
+    if "Efermi" in g0.files and np.array_equal(g0["Efermi"], g["Efermi"]):
+        assert relerr(res.results["ahc"].data, g0["ahc"]) < RTOL
+
+
 @pytest.mark.parametrize("nw", [4, 6, 8, 10, 12, 14, 16, 20, 22, 24])
 def test_fused_rotation_kernel_sizes(wb, nw):
     """The compile-time-num_wann DMMA rotation + formula kernel (rotate_method 3; every even num_wann <= 24) against the

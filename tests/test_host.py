@@ -368,3 +368,54 @@ def test_tetra_needs_uniform_fermi_axis():
     with pytest.raises(NotImplementedError):
         st.DOS(Efermi=np.array([0., 0.1, 0.3]), tetra=True)
     assert wb.calculators.dynamic.JDOS(Efermi=np.linspace(0, 1, 3), omega=np.linspace(0, 1, 3)).spec().external_terms == 0
+
+
+def test_reference_calculators_on_datak_host():
+    """Plug-in hook #1: UNMODIFIED calculators and formulae of the reference evaluate on this
+    package's `DataKHost` interface -- `E_K`, `Xbar`, `D_H`, `dEig_inv`, `Dcov`, `covariant()` with comma- and
+    generalised derivatives, `get_bands_in_range_groups` -- and give what they give on the reference's own `Data_K_R`.
+    Here (no GPU) the three primitives of `DataKHost` are taken from the reference's Data_K_R of the same K-block, so
+    that the test isolates the host logic; on the GPU box the primitives of `wannierberri_b200.Data_K_R` are checked
+    against the oracle and a user-defined formula runs end to end (tests/test_gpu_parity.py)."""
+    wberri = _import_reference()
+    sys.path[:0] = ["/root/reference", os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, "tests", "golden")]
+    try:
+        from make_golden import build_fe
+        from wannierberri.data_K import Data_K_R as RefDataK
+        from wannierberri.calculators import static as rst
+    finally:
+        del sys.path[:3]
+    from wannierberri_b200.data_K import DataKHost
+    from plugin_formula import make_calculators
+    system = build_fe()
+    grid = wberri.Grid(system, NK=[4, 4, 4], NKFFT=[2, 2, 2])
+    dK = np.array([0.125, 0.0, 0.125])
+
+    class Host(DataKHost):
+        def __init__(self, ref):
+            self.ref, self.system = ref, ref.system
+            self.nk, self.num_wann, self.cell_volume = ref.nk, ref.num_wann, ref.cell_volume
+            self.force_internal_terms_only = ref.force_internal_terms_only
+
+        def _eig(self):
+            return self.ref.E_K, self.ref.UU_K
+
+        def _xbar(self, name, der):
+            return self.ref.Xbar(name, der)
+
+    Ef = np.linspace(15., 19., 9)
+    calcs = dict(ahc=rst.AHC(Efermi=Ef), morb=rst.Morb(Efermi=Ef), bcd_sea=rst.BerryDipole_FermiSea(Efermi=Ef),
+                 gme_spin_sea=rst.GME_spin_FermiSea(Efermi=Ef), ohmic_sea=rst.Ohmic_FermiSea(Efermi=Ef),
+                 ahc_kramers=rst.AHC(Efermi=Ef, degen_thresh=0.05, degen_Kramers=True),
+                 zeeman_spin=rst.AHC_Zeeman_spin(Efermi=Ef))
+    calcs.update(make_calculators(rst.StaticCalculator, Ef))
+    for key, c in calcs.items():
+        want = c(RefDataK(system, dK=dK, grid=grid)).data
+        got = c(Host(RefDataK(system, dK=dK, grid=grid))).data
+        assert np.abs(got - want).max() <= 1e-12 * max(np.abs(want).max(), 1e-300), key
+    # this package's plug-in calculator (host loop of StaticCalculator._call_plugin) against the reference's loop
+    mine = make_calculators(wb.calculators.static.StaticCalculator, Ef)
+    for key, c in mine.items():
+        want = calcs[key](RefDataK(system, dK=dK, grid=grid)).data
+        got = c(Host(RefDataK(system, dK=dK, grid=grid))).data
+        assert np.abs(got - want).max() <= 1e-12 * max(np.abs(want).max(), 1e-300), key

@@ -92,6 +92,7 @@ def lib():
     L.wbgpu_kpoints.argtypes = [vp, pd, pd]
     L.wbgpu_eig.argtypes = [vp, pd, pd, pd]
     L.wbgpu_xk.argtypes = [vp, pd, C.c_int, pd]
+    L.wbgpu_xbar.argtypes = [vp, pd, C.c_int, C.c_int, pd]
     L.wbgpu_band_traces.argtypes = [vp, pd, C.POINTER(ScanSpec), pd, pd]
     L.wbgpu_kernel_launches.argtypes = [vp]
     L.wbgpu_kernel_launches.restype = i64
@@ -102,7 +103,7 @@ def lib():
     L.wbgpu_stage_times.argtypes = [vp, pd, C.POINTER(i64)]
     L.wbgpu_fp64_peak.argtypes = [C.c_int, C.c_int, pd]
     for name in ("wbgpu_create", "wbgpu_destroy", "wbgpu_set_R_matrix", "wbgpu_plan", "wbgpu_static_scan",
-                 "wbgpu_static_scan_dev", "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_band_traces",
+                 "wbgpu_static_scan_dev", "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_xbar", "wbgpu_band_traces",
                  "wbgpu_last_eig_sweeps", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak", "wbgpu_kubo_scan",
                  "wbgpu_static_scan_tetra", "wbgpu_static_scan_blocks", "wbgpu_kubo_scan_dev"):
         getattr(L, name).restype = C.c_int
@@ -112,7 +113,7 @@ def lib():
 
 EXPORTED = ["wbgpu_last_error", "wbgpu_version", "wbgpu_device_count", "wbgpu_create", "wbgpu_destroy",
             "wbgpu_set_R_matrix", "wbgpu_plan", "wbgpu_static_scan", "wbgpu_static_scan_dev", "wbgpu_spec_size",
-            "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_band_traces", "wbgpu_kernel_launches",
+            "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_xbar", "wbgpu_band_traces", "wbgpu_kernel_launches",
             "wbgpu_last_eig_sweeps", "wbgpu_last_eig_resolved", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak",
             "wbgpu_kubo_size",
             "wbgpu_kubo_scan", "wbgpu_static_scan_tetra", "wbgpu_static_scan_blocks", "wbgpu_kubo_scan_dev"]

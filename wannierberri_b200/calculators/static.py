@@ -62,14 +62,16 @@ class StaticCalculator(Calculator):
         if smoother is not None and not callable(smoother):
             raise ValueError("smoother must be callable as smoother(A, axis=0) (wannierberri_b200.smoother or the reference's)")
         self.kwargs_formula = copy(kwargs_formula) if kwargs_formula is not None else {}
+        if Formula is not None:
+            self.Formula = Formula
         unknown = set(self.kwargs_formula) - {"internal_terms", "external_terms"} - set(self.extra_kwargs_formula)
-        if unknown:
+        if unknown and not self.is_plugin:
             raise NotImplementedError(f"kwargs_formula {sorted(unknown)} are not implemented on the GPU path")
+        if tetra and self.is_plugin:
+            raise NotImplementedError("tetra=True with a plug-in Formula class is not implemented")
         self.use_factor = use_factor
         self.hole_like = hole_like
         self.tetra, self.smoother, self.k_resolved, self.select_bands = tetra, smoother, k_resolved, select_bands
-        if Formula is not None:
-            self.Formula = Formula
         if fder is not None:
             self.fder = fder
         assert hasattr(self, "fder"), "fder not set"
@@ -96,6 +98,12 @@ class StaticCalculator(Calculator):
         # levels as they are (grid/tetrahedron.py:270-281), so anything but a uniform axis must not pass silently
         if tetra and len(self.Efermi) > 2 and not np.allclose(np.diff(self.Efermi), self.dEF, rtol=1e-9, atol=1e-12 * abs(self.dEF)):
             raise NotImplementedError("tetra=True needs uniformly spaced Efermi on the GPU path")
+
+    @property
+    def is_plugin(self):
+        """`Formula` is a user's class `Formula(data_K, **kwargs_formula)` (plug-in hook #2 of SURVEY.md section 8(b))
+        instead of one of the scans that the CUDA kernels evaluate"""
+        return not isinstance(getattr(self, "Formula", 0), (int, np.integer))
 
     # ---- what the engine must evaluate
     def _spec(self, formula=None, fder=None):
@@ -126,8 +134,47 @@ class StaticCalculator(Calculator):
     def __call__(self, data_K):
         """Per-K-block evaluation with the reference's calling convention `calc(data_K)`; `data_K` is a
         `wannierberri_b200.Data_K_R` (GPU resident).  static.py:60-169."""
+        if self.is_plugin:
+            return self._call_plugin(data_K)
         arrays = data_K.scan(self.specs(), external_terms=self.external_terms, tetra=self.tetra)
         return self.result(arrays, data_K.cell_volume)
+
+    def _call_plugin(self, data_K):
+        """Fermi scan of a user-supplied formula object on one K-block (the loop of static.py:60-169 over the band
+        groups of every k-point).  Eigenvalues and Hamiltonian-gauge matrices come from the GPU through `data_K`; the
+        formula's own `trace()` is the user's code."""
+        from math import ceil
+        formula = self.Formula(data_K, **self.kwargs_formula)
+        shape = (3,) * formula.ndim
+        nb = data_K.num_wann
+        groups_k = data_K.get_bands_in_range_groups(self.EFmin, self.EFmax, degen_thresh=self.degen_thresh,
+                                                    degen_Kramers=self.degen_Kramers, sea=(self.fder == 0),
+                                                    Emin=self.Emin, Emax=self.Emax, select_bands=self.select_bands)
+        steps = np.zeros((self.nEF_extra + 1,) + shape)   # value added from level i on: summed up at the end
+        for ik, groups in enumerate(groups_k):
+            if getattr(formula, "additive", True):
+                values = {g: formula.trace(ik, np.arange(g[0], g[1]),
+                                           np.concatenate((np.arange(0, g[0]), np.arange(g[1], nb)))) for g in groups}
+            else:   # e.g. the orbital moment: trace over [0, edge) at every group edge, a group = difference of its edges
+                edge = {x: formula.trace(ik, np.arange(0, x), np.arange(x, nb)) for x in {e for g in groups for e in g}}
+                values = {g: edge[g[1]] - edge[g[0]] for g in groups}
+            for g, E in groups.items():
+                if E < self.EFmin:
+                    steps[0] += values[g]
+                elif E <= self.EFmax:
+                    steps[ceil((E - self.EFmin) / self.dEF)] += values[g]
+        tot = np.cumsum(steps[:-1], axis=0)
+        d = self.dEF
+        if self.fder == 1:
+            tot = (tot[2:] - tot[:-2]) / (2 * d)
+        elif self.fder == 2:
+            tot = (tot[2:] + tot[:-2] - 2 * tot[1:-1]) / d ** 2
+        elif self.fder == 3:
+            tot = (tot[4:] - tot[:-4] - 2 * (tot[3:-1] - tot[1:-3])) / (2 * d ** 3)
+        tot = tot / (data_K.cell_volume * data_K.nk)
+        tot = tot * (self.constant_factor if self.use_factor else np.sign(self.constant_factor))
+        return EnergyResult(self.Efermi, tot, transformTR=formula.transformTR, transformInv=formula.transformInv,
+                            comment=self.comment, save_mode=self.save_mode, smoothers=[self.smoother])
 
 
 class _DOS(StaticCalculator):
@@ -433,7 +480,7 @@ def adapt(calc):
         return calc
     name = type(calc).__name__
     if name not in _BY_NAME:
-        raise ValueError(f"calculator {name} is not available on the GPU path")
+        raise KeyError(f"calculator {name} is not available on the GPU path")
     if calc.tetra and getattr(calc, "hole_like", False):
         raise NotImplementedError("tetra=True with hole_like (inverse Fermi sea, der=-1) is not implemented on the GPU path")
     kw = dict(Efermi=np.array(calc.Efermi), tetra=calc.tetra, smoother=calc.smoother, use_factor=calc.use_factor,

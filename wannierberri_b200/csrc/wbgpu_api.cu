@@ -1756,6 +1756,90 @@ extern "C" int wbgpu_xk(wbgpu_ctx* c, const double dK[3], int channel, double* X
     return 0;
 }
 
+// index of the sorted triple (b <= c <= d) in off_W3: xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
+static int sym10(int b, int c, int d) {
+    int t[3] = {b, c, d};
+    std::sort(t, t + 3);
+    static const int first[3] = {0, 6, 9};
+    const int within = (t[1] - t[0]) * (2 * (3 - t[0]) - (t[1] - t[0]) + 1) / 2 + (t[2] - t[1]);   // pairs (c, d) >= t0, row-major
+    return first[t[0]] + within;
+}
+
+// Parity / plug-in probe: the Hamiltonian-gauge matrix  Xbar(name, der) = U^dagger (d^der X) U  of one K-block
+// (Data_K_R.Xbar, data_K/data_K_R.py:69-97; the rotation of data_K.py:130-132 runs in wb_rotate_gemm_kernel).
+// X[nk][nw][nw][3]^ncart, ncart = (name != Ham) + der: value components first, derivative components after them.
+extern "C" int wbgpu_xbar(wbgpu_ctx* c, const double dK[3], int channel, int der, double* X) {
+    if (!X) return set_err("wbgpu_xbar: null pointer argument");
+    if (probe_prepare(c, dK)) return 1;
+    const WbLayout& L = c->L;
+    const int nw = c->nw, n2 = nw * nw;
+    std::vector<int> comp_off;   // record offset per output component
+    int herm = 0;
+    auto need = [&](const int* offs, int n, int h, const char* what) {
+        if (offs[0] < 0) return set_err("wbgpu_xbar: %s is not part of the current plan", what);
+        for (int a = 0; a < n; a++) comp_off.push_back(offs[a]);
+        herm = h;
+        return 0;
+    };
+    int rc = 0;
+    if (channel == WBGPU_CH_HAM) {
+        if (der == 0) rc = need(&L.off_H, 1, 1, "Ham");
+        else if (der == 1) rc = need(L.off_dH, 3, L.dH_herm, "d Ham");
+        else if (der == 2) {
+            if (L.off_W[0] < 0) return set_err("wbgpu_xbar: d^2 Ham is not part of the current plan");
+            for (int b = 0; b < 3; b++) for (int d = 0; d < 3; d++) comp_off.push_back(L.off_W[wb_sym6(b, d)]);
+            herm = L.dH_herm;
+        } else if (der == 3) {
+            if (L.off_W3[0] < 0) return set_err("wbgpu_xbar: d^3 Ham is not part of the current plan");
+            for (int b = 0; b < 3; b++) for (int cc = 0; cc < 3; cc++) for (int d = 0; d < 3; d++)
+                comp_off.push_back(L.off_W3[sym10(b, cc, d)]);
+            herm = L.dH_herm;
+        } else return set_err("wbgpu_xbar: Ham has comma-derivatives up to order 3");
+    } else {
+        if (der < 0 || der > 1) return set_err("wbgpu_xbar: comma-derivatives of order 0 and 1 only");
+        switch (channel) {
+            case WBGPU_CH_AA: rc = der ? need(L.off_dA, 9, 1, "d AA") : need(L.off_A, 3, 1, "AA"); break;
+            case WBGPU_CH_ROTAA: rc = der ? need(L.off_dO, 9, 1, "d rotAA") : need(L.off_O, 3, 1, "rotAA"); break;
+            case WBGPU_CH_BB: rc = der ? need(L.off_dB, 9, 0, "d BB") : need(L.off_B, 3, 0, "BB"); break;
+            case WBGPU_CH_CC: rc = der ? need(L.off_dC, 9, 0, "d CC") : need(L.off_C, 3, 0, "CC"); break;
+            case WBGPU_CH_SS: rc = der ? need(L.off_dS, 9, 1, "d SS") : need(L.off_S, 3, 1, "SS"); break;
+            default: return set_err("wbgpu_xbar: unknown channel %d", channel);
+        }
+    }
+    if (rc) return rc;
+    // rotate every distinct record channel once
+    WbChanList ch;
+    ch.n = 0;
+    std::vector<int> which(comp_off.size());
+    for (size_t a = 0; a < comp_off.size(); a++) {
+        int found = -1;
+        for (int i = 0; i < ch.n; i++) if (ch.off[i] == comp_off[a]) found = i;
+        if (found < 0) { found = ch.n; ch.off[ch.n] = comp_off[a]; ch.herm[ch.n] = herm; ch.n++; }
+        which[a] = found;
+    }
+    const long nk = c->nk_block;
+    const int ncomp = (int)comp_off.size();
+    if (run_fourier(c, c->d_dK, 1)) return 1;
+    if (run_eigh(c, nk, true)) return 1;
+    const long chunk = xbar_chunk(c, ch.n, nk);
+    if (ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * n2)) return 1;
+    std::vector<cplx> host((size_t)chunk * ch.n * n2);
+    cplx* out = (cplx*)X;
+    for (long k0 = 0; k0 < nk; k0 += chunk) {
+        const long n = std::min(chunk, nk - k0);
+        if (rotate_gemm(c, ch, k0, n)) return 1;
+        CK(cudaMemcpyAsync(host.data(), c->d_xbar, sizeof(cplx) * (size_t)n * ch.n * n2, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (long k = 0; k < n; k++)          // re-ordering of the probe's output (layout only, no arithmetic)
+            for (int a = 0; a < ncomp; a++) {
+                const cplx* src = host.data() + ((size_t)k * ch.n + which[a]) * n2;
+                cplx* dst = out + (size_t)(k0 + k) * n2 * ncomp + a;
+                for (int x = 0; x < n2; x++) dst[(size_t)x * ncomp] = src[x];
+            }
+    }
+    return 0;
+}
+
 extern "C" int wbgpu_band_traces(wbgpu_ctx* c, const double dK[3], const wbgpu_scan_spec* spec, double* E_label,
                                  double* value) {
     if (!spec || !E_label || !value) return set_err("wbgpu_band_traces: null pointer argument");

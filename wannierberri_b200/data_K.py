@@ -40,7 +40,142 @@ def check_parameters_K(parameters_K):
         raise NotImplementedError(f"parameters_K {sorted(parameters_K)} are not implemented on the GPU path")
 
 
-class Data_K_R:
+class DataKHost:
+    """What calculators and plug-in formulae read from a `Data_K` beyond the scans (data_K/data_K.py:138-334): derived
+    host-side quantities of the three primitives `E_K`, `UU_K` and `Xbar(name, der)` that a subclass supplies."""
+
+    _xbar_cache = None
+    _cov_cache = None
+    is_phonon = False
+    Emin, Emax = -np.inf, np.inf
+
+    # ---- primitives (subclass)
+    def _eig(self):
+        raise NotImplementedError
+
+    def _xbar(self, name, der):
+        raise NotImplementedError
+
+    # ---- basic variables
+    @property
+    def nbands(self):
+        return self.num_wann
+
+    @property
+    def real_lattice(self):
+        return self.system.real_lattice
+
+    @property
+    def E_K(self):
+        if getattr(self, "_E_K", None) is None:
+            self._E_K, self._UU_K = self._eig()
+        return self._E_K
+
+    @property
+    def UU_K(self):
+        self.E_K
+        return self._UU_K
+
+    def Xbar(self, name, der=0):
+        """U^dagger (d^der X) U, `[nk][nw][nw][3]^(ncart + der)` (data_K/data_K_R.py:69-97)"""
+        if self._xbar_cache is None:
+            self._xbar_cache = {}
+        key = (name, der)
+        if key not in self._xbar_cache:
+            self._xbar_cache[key] = self._xbar(name, der)
+        return self._xbar_cache[key]
+
+    @property
+    def delE_K(self):
+        """band velocities: the diagonal of Xbar('Ham', 1) (data_K.py:236-242)"""
+        d = np.einsum("klla->kla", self.Xbar("Ham", 1))
+        worst = np.abs(d.imag).max()
+        if worst > 1e-10:
+            raise RuntimeError(f"The band derivatives have considerable imaginary part: {worst}")
+        return d.real
+
+    @property
+    def dEig_inv(self):
+        """1 / (E_m - E_n), zero where the two energies are closer than 1e-7 (data_K.py:290-298)"""
+        dE = self.E_K[:, :, None] - self.E_K[:, None, :]
+        close = np.abs(dE) < 1e-7
+        dE[close] = 1.
+        inv = 1. / dE
+        inv[close] = 0.
+        return inv
+
+    @property
+    def D_H(self):
+        """D^H_a = -Vbar_a / (E_m - E_n) (data_K.py:324-326)"""
+        return -self.Xbar("Ham", 1) * self.dEig_inv[:, :, :, None]
+
+    def get_A_H(self, external_terms=True):
+        """generalised Berry connection i D^H (+ Abar) (data_K.py:328-334)"""
+        A = 1j * self.D_H
+        if external_terms:
+            A = A + self.Xbar("AA")
+        return A
+
+    @property
+    def Dcov(self):
+        from .formula import Dcov
+        return Dcov(self)
+
+    @property
+    def V_covariant(self):
+        from .formula import Velocity_ln
+        return Velocity_ln(self.Xbar("Ham", 1))
+
+    def covariant(self, name, commader=0, gender=0, save=True):
+        """the matrix `name` with `commader` comma-derivatives, or its generalised derivative (`gender` = 1), as an
+        object with `nn` / `ln` / `nl` / `ll` blocks (data_K.py:244-271)"""
+        from . import formula
+        assert commader * gender == 0, "cannot mix comm and generalized derivatives"
+        if self._cov_cache is None:
+            self._cov_cache = {}
+        key = (name, commader, gender)
+        if key in self._cov_cache:
+            return self._cov_cache[key]
+        if gender == 0:
+            res = formula.Matrix_ln(self.Xbar(name, commader), transformTR=formula.transform_TR(name, commader),
+                                    transformInv=formula.transform_Inv(name, commader))
+        elif gender == 1:
+            if name == "Ham":
+                res = self.V_covariant
+            else:
+                res = formula.Matrix_GenDer_ln(self.covariant(name), self.covariant(name, commader=1), self.Dcov,
+                                               transformTR=formula.transform_TR(name, gender),
+                                               transformInv=formula.transform_Inv(name, gender))
+        else:
+            raise NotImplementedError()
+        if save:
+            self._cov_cache[key] = res
+        return res
+
+    def get_bands_in_range_groups_ik(self, ik, emin, emax, degen_thresh=-1, degen_Kramers=False, sea=False,
+                                     Emin=-np.inf, Emax=np.inf, select_bands=None):
+        from .formula import band_groups
+        return band_groups(self.E_K[ik], emin, emax, degen_thresh, degen_Kramers, sea, select_bands)
+
+    def get_bands_in_range_groups(self, emin, emax, degen_thresh=-1, degen_Kramers=False, sea=False, Emin=-np.inf,
+                                  Emax=np.inf, select_bands=None):
+        return [self.get_bands_in_range_groups_ik(ik, emin, emax, degen_thresh, degen_Kramers, sea, Emin, Emax, select_bands)
+                for ik in range(self.nk)]
+
+
+# which scan formula makes wbgpu_plan keep the channel that Xbar(name, der) reads
+def _xbar_plan_formula(name, der):
+    from . import _lib
+    table = {("Ham", 0): _lib.IDENTITY, ("Ham", 1): _lib.VEL_VEL, ("Ham", 2): _lib.INV_MASS, ("Ham", 3): _lib.DER3E,
+             ("AA", 0): _lib.OMEGA, ("AA", 1): _lib.DER_OMEGA, ("rotAA", 0): _lib.OMEGA, ("rotAA", 1): _lib.DER_OMEGA,
+             ("BB", 0): _lib.MORB_HPM, ("BB", 1): _lib.DER_MORB, ("CC", 0): _lib.MORB_HPM, ("CC", 1): _lib.DER_MORB,
+             ("SS", 0): _lib.SPIN, ("SS", 1): _lib.DER_SPIN}
+    if (name, der) not in table:
+        raise NotImplementedError(f"Xbar('{name}', der={der}) is not available on the GPU path")
+    return table[(name, der)]
+
+
+class Data_K_R(DataKHost):
 
     def __init__(self, system, dK, grid, Kpoint=None, device=0, **parameters_K):
         check_parameters_K(parameters_K)
@@ -54,10 +189,32 @@ class Data_K_R:
         self.cell_volume = system.cell_volume
         self.force_internal_terms_only = getattr(system, "force_internal_terms_only", False)
         self.engine = engine_for(system, device)
+        self._formulae = set()
+        self._external = False
 
     def _plan(self, formulae, external_terms=True):
         from . import _lib
         self.engine.plan(self.NKFFT, set(formulae) | {_lib.IDENTITY}, external_terms=external_terms)
+
+    def _plan_more(self, formula, external_terms):
+        """plans of the probes accumulate, so that a formula that reads several matrices re-plans once per new channel"""
+        self._formulae.add(formula)
+        self._external = self._external or external_terms
+        self._plan(self._formulae, self._external)
+
+    # ---- primitives of DataKHost, evaluated by the CUDA kernels
+    def _eig(self):
+        self._plan_more(_xbar_plan_formula("Ham", 0), False)
+        return self.engine.eig(self.dK, vectors=True)
+
+    def _xbar(self, name, der):
+        self._plan_more(_xbar_plan_formula(name, der), name in ("AA", "rotAA", "BB", "CC"))
+        return self.engine.xbar(self.dK, name, der)
+
+    @property
+    def HH_K(self):
+        self._plan_more(_xbar_plan_formula("Ham", 0), False)
+        return self.engine.xk(self.dK, "Ham")
 
     def scan(self, specs, external_terms=True, tetra=False):
         if self.force_internal_terms_only:
@@ -83,7 +240,3 @@ class Data_K_R:
         self._plan([])
         return self.engine.kpoints(self.dK)
 
-    @property
-    def E_K(self):
-        self._plan([])
-        return self.engine.eig(self.dK)

@@ -158,6 +158,14 @@ class Engine:
         check(self._L.wbgpu_xk(self._ctx, dptr(dK), _lib.CHANNELS[channel], dptr(X.view(np.float64))))
         return X
 
+    def xbar(self, dK, name, der=0):
+        """Hamiltonian-gauge matrix U^dagger (d^der X) U of one K-block, `[nk][nw][nw][3]^(ncart + der)`"""
+        dK = as_f64(dK)
+        ncart = (0 if name == "Ham" else 1) + int(der)
+        X = np.zeros((self.nk, self.nw, self.nw) + (3,) * ncart, dtype=np.complex128)
+        check(self._L.wbgpu_xbar(self._ctx, dptr(dK), _lib.CHANNELS[name], int(der), dptr(X.view(np.float64))))
+        return X
+
     def band_traces(self, dK, spec):
         dK = as_f64(dK)
         rank = _lib.FORMULA_RANK[int(spec.formula)]

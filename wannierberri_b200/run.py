@@ -85,15 +85,28 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=True, symmetri
     check_parameters_K(parameters_K)
     system = as_system(system)
     pointgroup = _pointgroup_of(system)
-    calcs, dyn_calcs = {}, {}
+    calcs, dyn_calcs, plug_calcs = {}, {}, {}
     for key, c in calculators.items():
         # static.SHC and dynamic.SHC share their class name: a Kubo calculator is the one that carries a frequency axis
         dynamic = isinstance(c, _dyn.DynamicCalculator) or (type(c).__name__ in _dyn._BY_NAME and hasattr(c, "omega")
                                                              and not hasattr(c, "fder"))
-        c = _dyn.adapt(c) if dynamic else adapt_static(c)
+        if not dynamic:
+            try:
+                c = adapt_static(c)
+            except KeyError:   # not one of the scans of the CUDA kernels: a user's calculator, called per K-block
+                if not callable(c):
+                    raise ValueError(f"calculator {key} ({type(c).__name__}) is neither available on the GPU path nor callable")
+            if not getattr(c, "allow_grid", True):
+                raise ValueError(f"Calculator {key} is not compatible with a grid")
+            if getattr(c, "is_plugin", True):
+                plug_calcs[key] = c
+            else:
+                calcs[key] = c
+            continue
+        c = _dyn.adapt(c)
         if not c.allow_grid:
             raise ValueError(f"Calculator {key} is not compatible with a grid")
-        (dyn_calcs if dynamic else calcs)[key] = c
+        dyn_calcs[key] = c
 
     dist = _dist() if parallel else None
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
@@ -130,8 +143,25 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=True, symmetri
     # Kubo scans: one call each (their accumulators are large; they do not share the event pass of the static scans)
     karrays = [engine.kubo_scan(shifts[lo:hi], factors[lo:hi], ks, dyn_calcs[key].Efermi, dyn_calcs[key].omega)
                for key, ks in kspecs.items()]
+    # plug-in calculators (user formulae / calculators: SURVEY.md section 8(b), hooks #1 and #2): called K-block by
+    # K-block on a GPU-resident Data_K_R as the reference's `process` does (run_grid.py:32-115, 258-265)
+    plug_res = {key: None for key in plug_calcs}
+    for i in range(lo, hi):
+        if not plug_calcs:
+            break
+        data_K = Data_K_R(system, shifts[i], grid, device=device)
+        for key, c in plug_calcs.items():
+            r = c(data_K) * factors[i]
+            plug_res[key] = r if plug_res[key] is None else plug_res[key] + r
+    if plug_calcs and any(r is None for r in plug_res.values()):   # a rank without K-blocks: the shape comes from K-block 0
+        data_K = Data_K_R(system, shifts[0], grid, device=device)
+        for key, c in plug_calcs.items():
+            if plug_res[key] is None:
+                plug_res[key] = c(data_K) * 0.
     nstatic = len(arrays)
     arrays = arrays + [np.ascontiguousarray(a).view(np.float64) for a in karrays]
+    nkubo = len(karrays)
+    arrays = arrays + [np.ascontiguousarray(plug_res[key].data, dtype=np.float64) for key in plug_calcs]
 
     if dist and world > 1:
         import torch
@@ -149,14 +179,33 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=True, symmetri
     for key, c in calcs.items():
         mine = [a for a, o in zip(arrays[:nstatic], owner) if o == key]
         results[key] = c.result(mine, system.cell_volume)
-    for (key, c), a, raw in zip(dyn_calcs.items(), arrays[nstatic:], karrays):
+    for (key, c), a, raw in zip(dyn_calcs.items(), arrays[nstatic:nstatic + nkubo], karrays):
         results[key] = c.result(a.view(raw.dtype).reshape(raw.shape))
+    for key, a in zip(plug_calcs, arrays[nstatic + nkubo:]):
+        results[key] = _as_energy_result(plug_res[key], a)
     if symmetrize and pointgroup.size > 1:  # linear: applied once to the weighted sum instead of per K-point (run_grid.py:258-265)
         results = {key: r.symmetrized(pointgroup) for key, r in results.items()}
     res = ResultDict(results)
     if write_files and rank == 0:
         res.savedata(prefix=fout_name, suffix=suffix, i_iter=0)
     return res
+
+
+def _as_energy_result(r, data):
+    """the summed result of a plug-in calculator with the all-reduced data, as this package's EnergyResult (a result
+    object of the reference is recognised by its attributes)"""
+    from .result import EnergyResult
+    if isinstance(r, EnergyResult):
+        out = r * 1.
+        out.data = np.asarray(data).reshape(r.data.shape)
+        return out
+    for attr in ("Energies", "data", "transformTR", "transformInv"):
+        if not hasattr(r, attr):
+            raise ValueError(f"the result of a plug-in calculator must be an EnergyResult (got {type(r).__name__})")
+    return EnergyResult(list(r.Energies), np.asarray(data).reshape(np.shape(r.data)), transformTR=r.transformTR,
+                        transformInv=r.transformInv, rank=getattr(r, "rank", None),
+                        E_titles=getattr(r, "E_titles", ("Efermi",)), comment=getattr(r, "comment", "undocumented"),
+                        save_mode=getattr(r, "save_mode", "bin+txt"), smoothers=getattr(r, "smoothers", (None,)))
 
 
 def _write_factors(path, factors, it):   # run_grid.py:420-422
