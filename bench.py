@@ -101,10 +101,22 @@ class Workload:
         return {"fourier": 5 * np.log2(self.nk_block) * nw * nw * self.nmat, "eigh": 36. * nw ** 3,
                 "rotate": 16. * nw ** 3 * self.rot_mats + self.formula_flops, "scan": self.scan_flops(nw)}
 
+    pairs_per_k = None   # Kubo: band pairs whose Fermi-factor difference is non-zero somewhere on the Efermi axis (probed)
+
     def scan_flops(self, nw):
+        """Kubo accumulation in the kernel's own (difference) form: per frequency and contributing band pair one complex
+        frequency factor (~30 flops) and 9 complex multiply-adds at each end of the pair's Efermi interval (2 x 9 x 8
+        flops).  The reference's dense [n_omega x npair] @ [npair x nEF 9] contraction (dynamic.py:79-100) would be
+        8 n_omega npair nEF 9 flops -- nEF / 2 times more; it is reported as `reference_dense_flops_per_k`."""
         if self.kubo is None:
             return 0.
-        # reference contraction [n_omega x npair] @ [npair x nEF 9] per k-point (dynamic.py:79-100), complex
+        _, Ef, om, _ = self.kubo
+        pairs = self.pairs_per_k if self.pairs_per_k is not None else nw * (nw - 1) / 2
+        return len(om) * pairs * (30. + 2 * 9 * 8)
+
+    def scan_dense_flops(self, nw):
+        if self.kubo is None:
+            return 0.
         _, Ef, om, _ = self.kubo
         return 8. * len(om) * (nw * (nw - 1) / 2) * len(Ef) * 9
 
@@ -506,6 +518,11 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    if kspec:   # contributing band pairs per k-point of the Kubo scan, from the eigenvalues of this rank's first K-block
+        Eprobe = eng.eig(dK_h[0])
+        lo_e, hi_e = float(np.min(kcalc.Efermi)), float(np.max(kcalc.Efermi))
+        occ = (Eprobe <= hi_e)[:, :, None] & (Eprobe > lo_e)[:, None, :] & (np.arange(nw)[:, None] < np.arange(nw)[None, :])[None]
+        W.pairs_per_k = float(occ.sum(axis=(1, 2)).mean())
     for _ in range(max(args.warmup, 3)):
         step_dev()
     sampler = ClockSampler(local)
@@ -572,8 +589,8 @@ def main():
         note = ("stage = the kernels between two CUDA events on the library's stream; algorithmic flops per k-point of "
                 "SURVEY.md section 8(d)")
         if dominant == "scan":
-            note += (" (scan: the reference's dense [n_omega x npair] @ [npair x nEF 9] contraction, which the difference-form "
-                     "kernel does not perform)")
+            note += (f" (scan: difference-form Kubo accumulation, {W.pairs_per_k:.1f} contributing band pairs per k-point probed "
+                     f"from one K-block; the reference's dense contraction would be {W.scan_dense_flops(nw):.3g} flops per k-point)")
         roofline = {"kernel": dominant, "bound": "tensor", "pipe": pipe, "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
                     "frac": achieved / peak64, "traffic": None,
                     "peak_source": f"measured in this run: DFMA {fp64['dfma']:.1f}, DMMA(m8n8k4) {fp64['dmma']:.1f} TFLOP/s "
