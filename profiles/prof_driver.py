@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=32)
     ap.add_argument("--scans", type=int, default=2)
     ap.add_argument("--workload", default="ahc_dos", choices=["ahc_dos", "ahc_morb", "te_fsurf"])
+    ap.add_argument("--eig-method", type=int, default=0)
     args = ap.parse_args()
     import wannierberri_b200 as wb
     st = wb.calculators.static
@@ -39,6 +40,7 @@ def main():
             calcs = dict(ahc=st.AHC(Efermi=Ef), morb=st.Morb(Efermi=Ef))
     specs = [s for c in calcs.values() for s in c.specs()]
     eng = wb.Engine(system, device=0)
+    eng.set_option("eig_method", args.eig_method)
     eng.plan([20, 20, 20], [s.formula for s in specs], external_terms=True)
     grid = wb.Grid(system, NKdiv=[20, 20, 20], NKFFT=[20, 20, 20])
     shifts, factors = grid.K_arrays()

@@ -169,9 +169,9 @@ def test_eigh_sizes_and_degeneracies(wb, nw, degenerate):
     # (method 3), on an odd number of k-points
     NKFFT, dK = ([3, 1, 3] if nw == 18 else [3, 2, 4]), [0.03, 0.01, 0.2]
     from wannierberri_b200 import _lib
-    # method 0 = twisted-factorisation eigenvectors (nw <= 24), 2 / 3 = accumulated QL rotations, 4 = thread-per-matrix
-    # reduction, 1 = Jacobi
-    for method in ((0, 2, 3, 4, 1) if nw == 18 else (0, 2, 1) if nw <= 32 else (0, 1) if nw <= 40 else (0,)):
+    # method 0 = twisted-factorisation eigenvectors (nw <= 24), 2 / 3 = accumulated QL rotations, 4 / 5 = thread- /
+    # lane-pair-per-matrix reduction, 1 = Jacobi
+    for method in ((0, 2, 3, 4, 5, 1) if nw == 18 else (0, 5, 2, 1) if nw <= 20 else (0, 2, 1) if nw <= 32 else (0, 1) if nw <= 40 else (0,)):
         eng = wb.Engine(sysg)
         eng.set_option("eig_method", method)
         eng.plan(NKFFT, [_lib.IDENTITY])
@@ -243,6 +243,20 @@ def test_dh_full_channel_path(wb, fe, rotate_method):
         eng.close()
     for a, r in zip(*out):
         assert relerr(a, r) < 1e-11
+
+
+def test_soc_system_vs_reference_data_k_soc(wb):
+    """`run()` on a SOC system (scalar up / down systems + spin-orbit term on different R-vector sets; the reference
+    evaluates it with Data_K_soc, data_K/data_K_soc.py:7-62) against the fixture of the unmodified reference
+    (tests/golden/make_golden_soc.py): DOS, CumDOS, AHC with and without external terms, Spin, Ohmic, GME_spin."""
+    from conftest import soc_system_from_fixture, SOC_CALCS
+    g = np.load(os.path.join(GOLDEN, "golden_soc.npz"))
+    soc = soc_system_from_fixture(wb, g)
+    st = wb.calculators.static
+    calcs = {k: getattr(st, name)(Efermi=g["Efermi"], **kw) for k, (name, kw) in SOC_CALCS.items()}
+    res = wb.run(soc, wb.Grid(soc, NK=g["NK"], NKFFT=g["NKFFT"]), calcs, use_irred_kpt=False, symmetrize=False, write_files=False)
+    for key in calcs:
+        assert relerr(res.results[key].data, g["res_" + key]) < RTOL, key
 
 
 def test_data_k_plugin_attributes(wb, fe, fe_orc, orc):

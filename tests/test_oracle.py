@@ -372,3 +372,25 @@ def test_kubo_finite_temperature_random_system():
     for k in KBT_CASES:
         assert res[k].shape == g[k].shape, k
         assert relerr(res[k], g[k]) < RTOL, k
+
+
+def test_soc_system_flattening_vs_reference_data_k_soc():
+    """Data_K_soc (data_K/data_K_soc.py:7-62): a SOC system -- scalar up / down systems on the even / odd Wannier
+    functions plus a spin-orbit term, each on its own R-vector set -- is flattened by `wannierberri_b200.system.flatten_soc`
+    into ONE System_R; the oracle on that system must reproduce what the unmodified reference computed with its
+    Data_K_soc (fixture: tests/golden/make_golden_soc.py)."""
+    import wannierberri_b200 as wb
+    from wannierberri_b200.system import flatten_soc, as_system
+    from conftest import soc_system_from_fixture, SOC_CALCS
+    g = np.load(os.path.join(GOLDEN, "golden_soc.npz"))
+    soc = soc_system_from_fixture(wb, g)
+    flat = flatten_soc(soc)
+    assert as_system(soc) is as_system(soc) and as_system(soc).num_wann == 6
+    assert flat.num_wann == 6 and flat.rvec.nRvec == len({tuple(R) for k in ("up", "dw", "soc") for R in g["iRvec_" + k]})
+    assert set(flat._XX_R) == {"Ham", "AA", "SS"}
+    osys = orc.OracleSystem(flat.rvec.iRvec, flat.real_lattice, flat.wannier_centers_cart, flat._XX_R)
+    NKdiv = (g["NK"] // g["NKFFT"]).tolist()
+    res = orc.run(osys, NKdiv, g["NKFFT"].tolist(), {k: (name, g["Efermi"], kw) for k, (name, kw) in SOC_CALCS.items()})
+    for key in SOC_CALCS:
+        want = g["res_" + key]
+        assert np.abs(res[key] - want).max() <= RTOL * np.abs(want).max(), key

@@ -9,6 +9,10 @@
 int wb_launch_tridiag_tpm(int nw, const cplx* rec, const WbLayout& L, long k0, long nk, double* d, double* e, cplx* tau,
                           cplx* V, cudaStream_t stream);
 
+// the same with a pair of lanes per matrix (16 matrices per warp, half the shared memory per warp)
+int wb_launch_tridiag_tpm2(int nw, const cplx* rec, const WbLayout& L, long k0, long nk, double* d, double* e, cplx* tau,
+                           cplx* V, cudaStream_t stream);
+
 // wb_eigh_tf.cuh: eigenvalues (implicit QL) and eigenvectors (twisted factorisation) of the tridiagonal matrices, thread
 // per matrix, and the back-transformation with one lane per (matrix, eigenvector); 4 <= nw <= 24.
 // d, e, tau, Z are indexed from the start of the chunk, E and VU from k0.

@@ -639,8 +639,9 @@ static int launch_ql(wbgpu_ctx* c, long k0, long nk, bool want_U) {
     // the back-transformation with a lane per (matrix, vector) (wb_eigh_tf.cuh; 4 <= nw <= 24); 2 / 3: the rotation-stream
     // QL kernels below (3 = one k-point per warp in the reduction); 4: as 0 with the thread-per-matrix reduction
     // (wb_eigh_tpm.cuh, nw <= 20; measured slower than the two-k-points-per-warp kernel)
-    const bool tf = (c->eig_method == 0 || c->eig_method == 4) && nw >= 4 && nw <= 24;
-    int tpm = (c->eig_method == 4) ? wb_launch_tridiag_tpm(nw, c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U, c->stream) : -1;
+    const bool tf = (c->eig_method == 0 || c->eig_method == 4 || c->eig_method == 5) && nw >= 4 && nw <= 24;
+    int tpm = (c->eig_method == 4) ? wb_launch_tridiag_tpm(nw, c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U, c->stream)
+            : (c->eig_method == 5) ? wb_launch_tridiag_tpm2(nw, c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_U, c->stream) : -1;
     if (tpm > 0) return set_err("CUDA error %s launching the thread-per-matrix tridiagonalisation", cudaGetErrorName((cudaError_t)tpm));
     if (tpm == 0) {
     } else if constexpr (EXACT && NWP > 16 && NWP <= 18) {

@@ -129,9 +129,86 @@ def synthetic_system(num_wann, rmax=2, seed=20261017, lattice_const=4.0, matrice
     return s
 
 
+class SystemSOC(System_R):
+    """Container with the attributes of the reference's `SystemSOC` that the K-block path reads (system/system_soc.py:
+    14-70, 232-270): scalar `system_up` / `system_down` (the same object for nspin = 1), the spin-orbit term `Ham_SOC`
+    and the spin matrix `SS` of the combined system on R-vectors of their own.  Wannier function 2i is the up copy of
+    scalar function i, 2i + 1 the down copy."""
+
+    def __init__(self, system_up, system_down=None, iRvec=None, Ham_SOC=None, SS=None):
+        self.system_up = system_up
+        self.system_down = system_up if system_down is None else system_down
+        self.nspin = 1 if system_down is None else 2
+        self.num_wann_scalar = system_up.num_wann
+        centres = np.zeros((2 * self.num_wann_scalar, 3))
+        centres[::2] = self.system_up.wannier_centers_cart
+        centres[1::2] = self.system_down.wannier_centers_cart
+        if iRvec is None:
+            iRvec = np.zeros((1, 3), dtype=int)
+        super().__init__(system_up.real_lattice, iRvec, centres,
+                         force_internal_terms_only=(system_up.force_internal_terms_only or self.system_down.force_internal_terms_only),
+                         periodic=system_up.periodic)
+        self.has_soc = Ham_SOC is not None
+        if Ham_SOC is not None:
+            self.set_R_mat("Ham_SOC", Ham_SOC)
+        if SS is not None:
+            self.set_R_mat("SS", SS)
+
+
+def is_soc_system(obj):
+    """a system with non-self-consistent spin-orbit coupling on top of scalar up / down systems (system/system_soc.py)"""
+    return all(hasattr(obj, a) for a in ("system_up", "system_down", "num_wann_scalar", "nspin"))
+
+
+def flatten_soc(soc):
+    """The System_R that is equivalent to a SOC system, for the K-block path of `Data_K_soc` (data_K/data_K_soc.py:7-62).
+
+    Data_K_soc builds, per K-block, H(k) and every other matrix from three R-space sets: the scalar up system on the
+    even Wannier functions, the scalar down system on the odd ones, and the spin-orbit term `Ham_SOC` (plus the spin
+    matrix `SS`) of the combined system.  All of that is linear in R-space and the derivative factors R + t_j - t_i of
+    the three sets agree (the combined Wannier centres interleave the up and down ones), so the K-block arithmetic is
+    that of ONE system on the union of the three R-vector sets: Ham = up (+) down + Ham_SOC, AA / BB / CC / ... = up (+)
+    down, SS = the combined system's.  Done once on the host; the GPU path then runs unchanged."""
+    up, down = soc.system_up, soc.system_down
+    parts = [soc.rvec, up.rvec, down.rvec] if getattr(soc, "rvec", None) is not None else [up.rvec, down.rvec]
+    merged = sorted({tuple(int(x) for x in R) for rv in parts for R in rv.iRvec})
+    index = {R: i for i, R in enumerate(merged)}
+    maps = [np.array([index[tuple(int(x) for x in R)] for R in rv.iRvec]) for rv in parts]
+    m_up, m_down = maps[-2], maps[-1]
+    nw = int(soc.num_wann)
+    flat = System_R(soc.real_lattice, np.array(merged, dtype=int), soc.wannier_centers_cart,
+                    force_internal_terms_only=getattr(soc, "force_internal_terms_only", False),
+                    periodic=getattr(soc, "periodic", (True,) * 3))
+    flat.pointgroup = getattr(soc, "pointgroup", None)
+    up_keys = [k for k in ("Ham", "AA", "BB", "CC") if up.has_R_mat(k) and down.has_R_mat(k)]
+    for key in up_keys:
+        Xu, Xd = np.asarray(up.get_R_mat(key)), np.asarray(down.get_R_mat(key))
+        X = np.zeros((len(merged), nw, nw) + Xu.shape[3:], dtype=complex)
+        X[m_up, ::2, ::2] += Xu
+        X[m_down, 1::2, 1::2] += Xd
+        if key == "Ham" and getattr(soc, "has_soc", False):
+            X[maps[0]] += np.asarray(soc.get_R_mat("Ham_SOC"))
+        flat.set_R_mat(key, X)
+    if getattr(soc, "rvec", None) is not None and soc.has_R_mat("SS"):
+        S = np.zeros((len(merged), nw, nw, 3), dtype=complex)
+        S[maps[0]] = np.asarray(soc.get_R_mat("SS"))
+        flat.set_R_mat("SS", S)
+    return flat
+
+
+_FLAT_SOC = {}
+
+
 def as_system(obj):
     """Accept this package's `System_R` or the reference's (duck typing on the attributes read by
-    the path: SURVEY.md section 2, row 9)."""
+    the path: SURVEY.md section 2, row 9); a SOC system (`SystemSOC`: scalar up / down systems + spin-orbit term) is
+    flattened once into the equivalent System_R (`flatten_soc`)."""
+    if is_soc_system(obj):
+        key = id(obj)
+        if key not in _FLAT_SOC or _FLAT_SOC[key][0] is not obj:
+            _FLAT_SOC.clear()   # one at a time: the flattened copy holds full R-space matrices
+            _FLAT_SOC[key] = (obj, flatten_soc(obj))
+        return _FLAT_SOC[key][1]
     for attr in ("rvec", "get_R_mat", "has_R_mat", "num_wann", "cell_volume"):
         if not hasattr(obj, attr):
             raise ValueError(f"system object lacks attribute '{attr}' needed by the GPU path")
