@@ -78,7 +78,9 @@ enum {
                                  GME_orb_FermiSea), rank 2 [c][d], not additive; needs the channels of DerOmega plus BB, CC and
                                  their comma-derivatives */
     WBGPU_OMEGA_HPLUS = 24,   /* OmegaHplus  covariant.py:861-865 (Omega x Morb_Hpm blocks: AHC_Zeeman_orb) rank 2 */
-    WBGPU_NFORMULA = 25
+    WBGPU_XBAR_DER2 = 25,     /* no scan: makes wbgpu_plan keep the SECOND comma-derivatives of AA, rotAA, BB, CC, SS (of those that are
+                                 set) for wbgpu_xbar(..., der = 2), i.e. Data_K_R.Xbar(name, 2) of plug-in formulae */
+    WBGPU_NFORMULA = 26
 };
 
 /* R-space matrices a context can hold (System_R._XX_R keys) */
@@ -201,7 +203,7 @@ int wbgpu_eig(wbgpu_ctx* ctx, const double dK[3], double* E /*[nk][nw]*/, double
 int wbgpu_xk(wbgpu_ctx* ctx, const double dK[3], int channel, double* X /*complex128, see enum*/);
 /* Hamiltonian-gauge matrices of one K-block for plug-in formulae:  Xbar(name, der) = U^dagger (d^der X) U
  * (Data_K_R.Xbar, data_K/data_K_R.py:69-97).  channel: WBGPU_CH_HAM (der 0..3), WBGPU_CH_AA / ROTAA / BB / CC / SS
- * (der 0..1); the plan must hold the channel.  X[nk][nw][nw][3]^(ncart + der) complex128, value components first. */
+ * (der 0..2; der 2 needs WBGPU_XBAR_DER2 in the plan); the plan must hold the channel.  X[nk][nw][nw][3]^(ncart + der) complex128, value components first. */
 int wbgpu_xbar(wbgpu_ctx* ctx, const double dK[3], int channel, int der, double* X);
 /* per-k, per-band-group traces of a formula: E_label[nk][nw], value[nk][nw][3^rank]; slot b is
  * used iff a kept group starts at band b (label -inf for the Fermi-sea group), else label=+inf */

@@ -43,13 +43,41 @@ class UserFormula:
         return np.einsum("nn...->...", self.nn(ik, inn, out)).real
 
 
+class UserFormula2:
+    """rank-3 test quantity that reads SECOND comma-derivatives:
+        G^{bde}_{nn'} = S^{b,de}_{nn'} + i sum_{l in out} (D^d_{nl} A^{b,e}_{ln'} - A^{b,e}_{nl} D^d_{ln'}) + w A^{b,de}_{nn'}"""
+
+    def __init__(self, data_K, w=0.3, **unused):
+        self.D = data_K.Dcov
+        self.dA = data_K.covariant("AA", commader=1)
+        self.ddA = data_K.covariant("AA", commader=2)
+        self.ddS = data_K.covariant("SS", commader=2)
+        self.w = w
+        self.ndim = 3
+        self.transformTR = self.ddS.transformTR
+        self.transformInv = self.ddS.transformInv
+        self.additive = True
+
+    def nn(self, ik, inn, out):
+        res = np.array(self.ddS.nn(ik, inn, out))
+        res = res + 1j * np.einsum("mld,lnbe->mnbde", self.D.nl(ik, inn, out), self.dA.ln(ik, inn, out))
+        res = res - 1j * np.einsum("mlbe,lnd->mnbde", self.dA.nl(ik, inn, out), self.D.ln(ik, inn, out))
+        return res + self.w * self.ddA.nn(ik, inn, out)
+
+    def ln(self, ik, inn, out):
+        raise NotImplementedError()
+
+    def trace(self, ik, inn, out):
+        return np.einsum("nn...->...", self.nn(ik, inn, out)).real
+
+
 def make_calculators(StaticCalculator, Efermi):
     """{key: calculator} on top of the given `StaticCalculator` base class (the reference's or this package's)"""
 
-    def cls(fder_, name):
+    def cls(fder_, name, frm=UserFormula):
         class C(StaticCalculator):
             def __init__(self, **kwargs):
-                self.Formula = UserFormula
+                self.Formula = frm
                 self.fder = fder_
                 self.comment = name
                 super().__init__(**kwargs)
@@ -60,4 +88,5 @@ def make_calculators(StaticCalculator, Efermi):
         user_sea=cls(0, "UserSea")(Efermi=Efermi, kwargs_formula=dict(scale=0.7)),
         user_surf=cls(1, "UserSurf")(Efermi=Efermi, kwargs_formula=dict(scale=1.3, w=-0.2), degen_thresh=0.05),
         user_weighted=cls(0, "UserWeighted")(Efermi=Efermi, kwargs_formula=dict(weighted=True), constant_factor=2.5),
+        user_der2=cls(1, "UserDer2", UserFormula2)(Efermi=Efermi, kwargs_formula=dict(w=0.3)),
     )

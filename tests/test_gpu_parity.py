@@ -280,7 +280,7 @@ def test_data_k_plugin_attributes(wb, fe, fe_orc, orc):
             X = orc.derivative(X, T)
         return data._R_to_k(X, name in ("AA", "SS", "rotAA"))
 
-    for name, ders in (("Ham", (0, 1, 2, 3)), ("AA", (0, 1)), ("rotAA", (0, 1)), ("BB", (0, 1)), ("CC", (0, 1)), ("SS", (0, 1))):
+    for name, ders in (("Ham", (0, 1, 2, 3)), ("AA", (0, 1, 2)), ("rotAA", (0, 1, 2)), ("BB", (0, 1, 2)), ("CC", (0, 1, 2)), ("SS", (0, 1, 2))):
         for der in ders:
             Xbar = dk.Xbar(name, der)
             Xw = wannier(name, der)
@@ -288,6 +288,9 @@ def test_data_k_plugin_attributes(wb, fe, fe_orc, orc):
             back = np.einsum("kia,kab...,kjb->kij...", U, Xbar, U.conj())
             assert relerr(back, Xw) < 1e-11, (name, der)
     assert relerr(np.einsum("kii->ki", dk.Xbar("Ham", 0)).real, E) < 1e-12
+    ab = dk.Xbar("rotAAab", 1)                      # derived names: antisymmetric rank-2 forms of curl A / C
+    assert ab.shape == (12, 18, 18, 3, 3, 3) and relerr(ab[:, :, :, 1, 2], -0.5j * dk.Xbar("rotAA", 1)[:, :, :, 0]) < 1e-15
+    assert relerr(dk.Xbar("CCab_antisym")[:, :, :, 0, 2], 0.5j * dk.Xbar("CC")[:, :, :, 1]) < 1e-15
     dE = E[:, :, None] - E[:, None, :]
     inv = dk.dEig_inv
     assert np.all(inv[np.abs(dE) < 1e-7] == 0.) and np.allclose(inv[np.abs(dE) > 1e-7] * dE[np.abs(dE) > 1e-7], 1.)
@@ -311,7 +314,7 @@ def test_plugin_formula_through_run(wb, fe):
     calcs["ahc"] = wb.calculators.static.AHC(Efermi=g["Efermi"])   # a fused scan next to the plug-ins in one run
     res = wb.run(fe, wb.Grid(fe, NK=g["NK"], NKFFT=g["NKFFT"]), calcs, use_irred_kpt=False, symmetrize=False,
                  write_files=False)
-    for key in ("user_sea", "user_surf", "user_weighted"):
+    for key in ("user_sea", "user_surf", "user_weighted", "user_der2"):
         assert res.results[key].data.shape == g[key].shape
         assert relerr(res.results[key].data, g[key]) < RTOL, key
     g0 = np.load(os.path.join(GOLDEN, "golden_fe_nk4.npz"))

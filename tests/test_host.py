@@ -407,7 +407,13 @@ def test_reference_calculators_on_datak_host():
     calcs = dict(ahc=rst.AHC(Efermi=Ef), morb=rst.Morb(Efermi=Ef), bcd_sea=rst.BerryDipole_FermiSea(Efermi=Ef),
                  gme_spin_sea=rst.GME_spin_FermiSea(Efermi=Ef), ohmic_sea=rst.Ohmic_FermiSea(Efermi=Ef),
                  ahc_kramers=rst.AHC(Efermi=Ef, degen_thresh=0.05, degen_Kramers=True),
-                 zeeman_spin=rst.AHC_Zeeman_spin(Efermi=Ef))
+                 zeeman_spin=rst.AHC_Zeeman_spin(Efermi=Ef),
+                 # second-order formulae of the reference (Der2Spin / Der2Omega / Der2Morb, eMChA, quantum metric with
+                 # FF = rotAAab): second comma-derivatives through Xbar(name, 2), evaluated by the reference's own classes
+                 nldrude_z_spin=rst.NLDrude_Zeeman_spin(Efermi=Ef), nldrude_z_orb=rst.NLDrude_Zeeman_orb(Efermi=Ef),
+                 emcha=rst.eMChA_FermiSurf(Efermi=Ef),
+                 qmetric=rst.QuantumMetric_FermiSea(Efermi=Ef, kwargs_formula=dict(FF_rotAA=True)),
+                 qmetric_dip=rst.QuantumMetric_Vel_DQ(Efermi=Ef, kwargs_formula=dict(FF_rotAA=True)))
     calcs.update(make_calculators(rst.StaticCalculator, Ef))
     for key, c in calcs.items():
         want = c(RefDataK(system, dK=dK, grid=grid)).data
@@ -419,3 +425,53 @@ def test_reference_calculators_on_datak_host():
         want = calcs[key](RefDataK(system, dK=dK, grid=grid)).data
         got = c(Host(RefDataK(system, dK=dK, grid=grid))).data
         assert np.abs(got - want).max() <= 1e-12 * max(np.abs(want).max(), 1e-300), key
+
+
+def test_run_plugin_loop_with_reference_calculators():
+    """`run()` with calculators that are NOT scans of the library -- here unmodified objects of the reference
+    (NLDrude_Zeeman_spin: second-order formula; a user class) -- loops over the K-blocks itself, calls
+    `calc(data_k_class(system, dK, grid))`, weights, sums and symmetrises (run_grid.py:258-265, 59-72).  With a
+    `DataKHost` subclass whose primitives come from the reference's Data_K_R no GPU is touched, so the loop is checked
+    here against the reference's own `run()` with the same calculators (incl. the irreducible K-list + symmetrisation)."""
+    wberri = _import_reference()
+    sys.path[:0] = ["/root/reference", os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, "tests", "golden")]
+    try:
+        from make_golden import build_fe
+        from wannierberri.data_K import Data_K_R as RefDataK
+        from wannierberri.calculators import static as rst
+    finally:
+        del sys.path[:3]
+    from wannierberri_b200.data_K import DataKHost
+    from plugin_formula import make_calculators
+    ref_system = build_fe()
+    ref_grid = wberri.Grid(ref_system, NK=[4, 4, 4], NKFFT=[2, 2, 2])
+
+    class Host(DataKHost):
+        def __init__(self, system, dK, grid, device=0, **kw):
+            self.ref = RefDataK(ref_system, dK=np.array(dK), grid=ref_grid)
+            self.system, self.grid, self.dK = system, grid, np.array(dK)
+            self.nk, self.num_wann, self.cell_volume = self.ref.nk, self.ref.num_wann, self.ref.cell_volume
+            self.force_internal_terms_only = False
+
+        def _eig(self):
+            return self.ref.E_K, self.ref.UU_K
+
+        def _xbar(self, name, der):
+            return self.ref.Xbar(name, der)
+
+    Ef = np.linspace(16., 18., 5)
+    calcs = dict(z_spin=rst.NLDrude_Zeeman_spin(Efermi=Ef), ahc=rst.AHC(Efermi=Ef, kwargs_formula=dict(external_terms=False)))
+    calcs.update({k: v for k, v in make_calculators(rst.StaticCalculator, Ef).items() if k == "user_surf"})
+    fe = wb.System_R.from_npz(os.path.join(GOLDEN, "fe_system.npz"), pointgroup=["C4z", "C2x*TimeReversal", "Inversion"])
+    scale = {}   # a quantity that vanishes by symmetry is compared on the scale of its unsymmetrised value
+    for sym in (False, True):
+        want = wberri.run(ref_system, grid=ref_grid, calculators=calcs, adpt_num_iter=0, use_irred_kpt=sym, symmetrize=sym,
+                          parallel=False, fout_name=os.path.join("/tmp", "plugloop"), print_progress_step_time=1e9)
+        # `ahc` has the name of a library scan: hand it over as a plain callable so that it takes the plug-in loop too
+        mine = dict(calcs, ahc=(lambda c: (lambda data_K: c(data_K)))(calcs["ahc"]))
+        got = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), mine, use_irred_kpt=sym, symmetrize=sym,
+                     data_k_class=Host, write_files=False, parallel=False)
+        for key in calcs:
+            a, b = got.results[key].data, want.results[key].data
+            scale.setdefault(key, np.abs(b).max())
+            assert a.shape == b.shape and np.abs(a - b).max() <= 1e-10 * scale[key], (key, sym)

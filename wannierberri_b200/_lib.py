@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libwbgpu.so")
 
 # enums of include/wbgpu.h
 (IDENTITY, OMEGA, MORB_HPM, VEL_OMEGA, VEL_HPLUS, VEL_SPIN, SPIN, KUBO, VEL_VEL, INV_MASS, SHC_RYOO, SHC_QIAO,
- SHC_SIMPLE, DER_OMEGA, DER_SPIN, VEL_VEL_VEL, MASS_VEL, MASS_MASS, VEL_MASS_VEL, OMEGA_S, OMEGA_OMEGA, SHIFT_CURRENT, DER3E, DER_MORB, OMEGA_HPLUS) = range(25)
+ SHC_SIMPLE, DER_OMEGA, DER_SPIN, VEL_VEL_VEL, MASS_VEL, MASS_MASS, VEL_MASS_VEL, OMEGA_S, OMEGA_OMEGA, SHIFT_CURRENT, DER3E, DER_MORB, OMEGA_HPLUS,
+ XBAR_DER2) = range(26)   # XBAR_DER2: no scan; keeps the second comma-derivatives for Data_K_R.Xbar(name, 2)
 SHC_TYPES = {"ryoo": SHC_RYOO, "qiao": SHC_QIAO, "simple": SHC_SIMPLE}
 KUBO_OPTCOND, KUBO_JDOS, KUBO_SHC, KUBO_SHIFT, KUBO_INJECTION = 0, 1, 2, 3, 4
 FORMULA_RANK = {IDENTITY: 0, OMEGA: 1, MORB_HPM: 1, SPIN: 1, VEL_OMEGA: 2, VEL_HPLUS: 2, VEL_SPIN: 2, VEL_VEL: 2,

@@ -65,6 +65,9 @@ struct WbLayout {
     int off_dS[9];   // d_d S_s, hermitian
     int off_dB[9], off_dC[9];   // d_d B_b, d_d C_c (full)
     int off_W3[10];  // d_b d_c d_d H, sorted triples xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz; packed like d_a H
+    // second comma-derivatives d_d d_e X_b (index 6 b + wb_sym6(d, e)) for plug-in formulae (Data_K_R.Xbar(name, 2)):
+    // A, rotA, S hermitian-packed; B, C full
+    int off_d2A[18], off_d2O[18], off_d2S[18], off_d2B[18], off_d2C[18];
 };
 
 // index of the symmetric pair (b, d) in off_W

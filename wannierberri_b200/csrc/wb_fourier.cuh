@@ -136,6 +136,38 @@ __global__ void wb_build_rtable_kernel(WbRInputs in, WbLayout L, int nR, int3 rm
             const cplx sv = in.SS[idx * 3 + a];
             for (int d = 0; d < 3; d++) add_herm(table, cellR, cellmR, E, L.off_dS[3 * a + d], i, j, nw, cmake(-T[d] * sv.y, T[d] * sv.x));
         }
+    // second comma-derivatives  i T_e (i T_d X_b) = -T_d T_e X_b  (plug-in formulae; rvectors.py:487-494 twice)
+    if (in.AA && L.off_d2A[0] >= 0)
+        for (int b = 0; b < 3; b++) {
+            const cplx a = in.AA[idx * 3 + b];
+            const int al = WB_ALPHA(b), be = WB_BETA(b);
+            const cplx Aal = in.AA[idx * 3 + al], Abe = in.AA[idx * 3 + be];
+            const cplx r0 = cmake(T[al] * Abe.x - T[be] * Aal.x, T[al] * Abe.y - T[be] * Aal.y);
+            const cplx rot = cmake(-r0.y, r0.x);   // (curl A)_b in R-space
+            for (int d = 0; d < 3; d++)
+                for (int e = d; e < 3; e++) {
+                    const double f = -(T[d] * T[e]);
+                    add_herm(table, cellR, cellmR, E, L.off_d2A[6 * b + wb_sym6(d, e)], i, j, nw, cscale(f, a));
+                    if (L.off_d2O[0] >= 0) add_herm(table, cellR, cellmR, E, L.off_d2O[6 * b + wb_sym6(d, e)], i, j, nw, cscale(f, rot));
+                }
+        }
+    if (in.SS && L.off_d2S[0] >= 0)
+        for (int b = 0; b < 3; b++) {
+            const cplx sv = in.SS[idx * 3 + b];
+            for (int d = 0; d < 3; d++)
+                for (int e = d; e < 3; e++)
+                    add_herm(table, cellR, cellmR, E, L.off_d2S[6 * b + wb_sym6(d, e)], i, j, nw, cscale(-(T[d] * T[e]), sv));
+        }
+    if (in.BB && in.CC && L.off_d2B[0] >= 0)
+        for (int b = 0; b < 3; b++) {
+            const cplx bv = in.BB[idx * 3 + b], cv = in.CC[idx * 3 + b];
+            for (int d = 0; d < 3; d++)
+                for (int e = d; e < 3; e++) {
+                    const double f = -(T[d] * T[e]);
+                    atomic_cadd(&table[cellR * E + L.off_d2B[6 * b + wb_sym6(d, e)] + i * nw + j], cscale(f, bv));
+                    atomic_cadd(&table[cellR * E + L.off_d2C[6 * b + wb_sym6(d, e)] + i * nw + j], cscale(f, cv));
+                }
+        }
     // spin-current matrices: not hermitised (data_K_R.py:84-87)
     if (in.SA && L.off_SA[0] >= 0)
         for (int a = 0; a < 9; a++) atomic_cadd(&table[cellR * E + L.off_SA[a] + i * nw + j], in.SA[idx * 9 + a]);

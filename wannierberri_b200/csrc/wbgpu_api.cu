@@ -420,6 +420,15 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     for (int a = 0; a < 9; a++) L.off_dO[a] = (der_om && need_A) ? take(true) : -1;
     for (int a = 0; a < 9; a++) L.off_dB[a] = (has(WBGPU_DER_MORB) && need_BC) ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_dC[a] = (has(WBGPU_DER_MORB) && need_BC) ? take(false) : -1;
+    // second comma-derivatives for Xbar(name, 2) of plug-in formulae: of the matrices that are set
+    const bool x2 = has(WBGPU_XBAR_DER2);
+    const bool x2A = x2 && external_terms && c->d_XR[WBGPU_AA], x2BC = x2 && external_terms && c->d_XR[WBGPU_BB] && c->d_XR[WBGPU_CC],
+               x2S = x2 && c->d_XR[WBGPU_SS];
+    for (int a = 0; a < 18; a++) L.off_d2A[a] = x2A ? take(true) : -1;
+    for (int a = 0; a < 18; a++) L.off_d2O[a] = x2A ? take(true) : -1;
+    for (int a = 0; a < 18; a++) L.off_d2S[a] = x2S ? take(true) : -1;
+    for (int a = 0; a < 18; a++) L.off_d2B[a] = x2BC ? take(false) : -1;
+    for (int a = 0; a < 18; a++) L.off_d2C[a] = x2BC ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_SA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_SHA[a] = has(WBGPU_SHC_RYOO) ? take(false) : -1;
     for (int a = 0; a < 9; a++) L.off_SR[a] = has(WBGPU_SHC_QIAO) ? take(false) : -1;
@@ -438,10 +447,10 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
     CK(cudaMemsetAsync(c->d_table, 0, sizeof(cplx) * ncell * L.E, c->stream));
     WbRInputs in;
     in.Ham = c->d_XR[WBGPU_HAM];
-    in.AA = need_A ? c->d_XR[WBGPU_AA] : nullptr;
-    in.BB = need_BC ? c->d_XR[WBGPU_BB] : nullptr;
-    in.CC = need_BC ? c->d_XR[WBGPU_CC] : nullptr;
-    in.SS = need_S ? c->d_XR[WBGPU_SS] : nullptr;
+    in.AA = (need_A || x2A) ? c->d_XR[WBGPU_AA] : nullptr;
+    in.BB = (need_BC || x2BC) ? c->d_XR[WBGPU_BB] : nullptr;
+    in.CC = (need_BC || x2BC) ? c->d_XR[WBGPU_CC] : nullptr;
+    in.SS = (need_S || x2S) ? c->d_XR[WBGPU_SS] : nullptr;
     in.SA = has(WBGPU_SHC_RYOO) ? c->d_XR[WBGPU_SA] : nullptr;
     in.SHA = has(WBGPU_SHC_RYOO) ? c->d_XR[WBGPU_SHA] : nullptr;
     in.SR = has(WBGPU_SHC_QIAO) ? c->d_XR[WBGPU_SR] : nullptr;
@@ -1797,7 +1806,22 @@ extern "C" int wbgpu_xbar(wbgpu_ctx* c, const double dK[3], int channel, int der
             herm = L.dH_herm;
         } else return set_err("wbgpu_xbar: Ham has comma-derivatives up to order 3");
     } else {
-        if (der < 0 || der > 1) return set_err("wbgpu_xbar: comma-derivatives of order 0 and 1 only");
+        if (der == 2) {   // [b][d][e] from the 6 symmetric (d, e) pairs per value component
+            const int* offs = nullptr;
+            int h2 = 1;
+            switch (channel) {
+                case WBGPU_CH_AA: offs = L.off_d2A; break;
+                case WBGPU_CH_ROTAA: offs = L.off_d2O; break;
+                case WBGPU_CH_SS: offs = L.off_d2S; break;
+                case WBGPU_CH_BB: offs = L.off_d2B; h2 = 0; break;
+                case WBGPU_CH_CC: offs = L.off_d2C; h2 = 0; break;
+                default: return set_err("wbgpu_xbar: unknown channel %d", channel);
+            }
+            if (offs[0] < 0) return set_err("wbgpu_xbar: second comma-derivatives of channel %d are not part of the current plan (WBGPU_XBAR_DER2)", channel);
+            for (int b = 0; b < 3; b++) for (int d = 0; d < 3; d++) for (int e = 0; e < 3; e++) comp_off.push_back(offs[6 * b + wb_sym6(d, e)]);
+            herm = h2;
+        } else {
+        if (der < 0 || der > 2) return set_err("wbgpu_xbar: comma-derivatives of order 0, 1 and 2 only");
         switch (channel) {
             case WBGPU_CH_AA: rc = der ? need(L.off_dA, 9, 1, "d AA") : need(L.off_A, 3, 1, "AA"); break;
             case WBGPU_CH_ROTAA: rc = der ? need(L.off_dO, 9, 1, "d rotAA") : need(L.off_O, 3, 1, "rotAA"); break;
@@ -1805,6 +1829,7 @@ extern "C" int wbgpu_xbar(wbgpu_ctx* c, const double dK[3], int channel, int der
             case WBGPU_CH_CC: rc = der ? need(L.off_dC, 9, 0, "d CC") : need(L.off_C, 3, 0, "CC"); break;
             case WBGPU_CH_SS: rc = der ? need(L.off_dS, 9, 1, "d SS") : need(L.off_S, 3, 1, "SS"); break;
             default: return set_err("wbgpu_xbar: unknown channel %d", channel);
+        }
         }
     }
     if (rc) return rc;

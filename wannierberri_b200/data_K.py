@@ -82,7 +82,17 @@ class DataKHost:
             self._xbar_cache = {}
         key = (name, der)
         if key not in self._xbar_cache:
-            self._xbar_cache[key] = self._xbar(name, der)
+            if name in ("rotAAab", "CCab_antisym"):
+                # antisymmetric rank-2 forms of curl A / C (data_K_R.py:53-66): X_ab = -+ i/2 eps_abc X_c, linear, so the
+                # same in the Hamiltonian gauge and after any number of comma-derivatives
+                X = self.Xbar("rotAA" if name == "rotAAab" else "CC", der)
+                res = np.zeros(X.shape[:3] + (3, 3) + X.shape[4:], dtype=complex)
+                al, be = np.array([1, 2, 0]), np.array([2, 0, 1])
+                res[:, :, :, al, be] = -0.5j * X
+                res[:, :, :, be, al] = 0.5j * X
+                self._xbar_cache[key] = res
+            else:
+                self._xbar_cache[key] = self._xbar(name, der)
         return self._xbar_cache[key]
 
     @property
@@ -169,7 +179,9 @@ def _xbar_plan_formula(name, der):
     table = {("Ham", 0): _lib.IDENTITY, ("Ham", 1): _lib.VEL_VEL, ("Ham", 2): _lib.INV_MASS, ("Ham", 3): _lib.DER3E,
              ("AA", 0): _lib.OMEGA, ("AA", 1): _lib.DER_OMEGA, ("rotAA", 0): _lib.OMEGA, ("rotAA", 1): _lib.DER_OMEGA,
              ("BB", 0): _lib.MORB_HPM, ("BB", 1): _lib.DER_MORB, ("CC", 0): _lib.MORB_HPM, ("CC", 1): _lib.DER_MORB,
-             ("SS", 0): _lib.SPIN, ("SS", 1): _lib.DER_SPIN}
+             ("SS", 0): _lib.SPIN, ("SS", 1): _lib.DER_SPIN,
+             ("AA", 2): _lib.XBAR_DER2, ("rotAA", 2): _lib.XBAR_DER2, ("BB", 2): _lib.XBAR_DER2, ("CC", 2): _lib.XBAR_DER2,
+             ("SS", 2): _lib.XBAR_DER2}
     if (name, der) not in table:
         raise NotImplementedError(f"Xbar('{name}', der={der}) is not available on the GPU path")
     return table[(name, der)]

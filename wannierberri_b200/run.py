@@ -70,9 +70,12 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=True, symmetri
 
     `parameters_K`: `fftlib` is accepted (and has no effect: the R->k transform is the CUDA one); non-default
     `Emin` / `Emax` / `random_gauge` raise, as does a `data_k_class` other than this package's (no CPU fallback)."""
-    if data_k_class is not None and data_k_class is not Data_K_R:
+    from .data_K import DataKHost
+    if data_k_class is not None and not (isinstance(data_k_class, type) and issubclass(data_k_class, DataKHost)):
         raise NotImplementedError(f"data_k_class {getattr(data_k_class, '__name__', data_k_class)}: only this package's "
-                                  "Data_K_R runs on the GPU path")
+                                  "Data_K_R (or a subclass of its DataKHost interface, for plug-in calculators) runs here")
+    if data_k_class is None:
+        data_k_class = Data_K_R
     if use_irred_kpt:   # run_grid.py:233-234: the irreducible wedge alone is meaningless without symmetrisation
         symmetrize = True
     if dump_results:
@@ -133,8 +136,11 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=True, symmetri
         kspecs[key] = ks
     external = any(s.external_terms for s in specs + tspecs) or any(ks.external_terms for ks in kspecs.values())
     formulae = {int(s.formula) for s in specs + tspecs} | {ks.formula_flag for ks in kspecs.values()} | {_lib.IDENTITY}
-    engine = engine_for(system, device)
-    engine.plan(np.array(grid.FFT, dtype=int), formulae, external_terms=external)
+    if (calcs or dyn_calcs) and data_k_class is not Data_K_R:
+        raise NotImplementedError("the library's calculators run on this package's Data_K_R only (no CPU fallback)")
+    engine = engine_for(system, device) if (calcs or dyn_calcs) else None
+    if engine is not None:
+        engine.plan(np.array(grid.FFT, dtype=int), formulae, external_terms=external)
     arrays = engine.scan(shifts[lo:hi], factors[lo:hi], specs) if specs else []
     if tspecs:  # tetrahedron method: the cell around every k-point is KpointBZparallel.dK_fullBZ
         dK_cell = 1. / (np.array(grid.div, dtype=float) * np.array(grid.FFT, dtype=float))
@@ -149,12 +155,12 @@ def run(system, grid, calculators, adpt_num_iter=0, use_irred_kpt=True, symmetri
     for i in range(lo, hi):
         if not plug_calcs:
             break
-        data_K = Data_K_R(system, shifts[i], grid, device=device)
+        data_K = data_k_class(system, shifts[i], grid, device=device)
         for key, c in plug_calcs.items():
             r = c(data_K) * factors[i]
             plug_res[key] = r if plug_res[key] is None else plug_res[key] + r
     if plug_calcs and any(r is None for r in plug_res.values()):   # a rank without K-blocks: the shape comes from K-block 0
-        data_K = Data_K_R(system, shifts[0], grid, device=device)
+        data_K = data_k_class(system, shifts[0], grid, device=device)
         for key, c in plug_calcs.items():
             if plug_res[key] is None:
                 plug_res[key] = c(data_K) * 0.
