@@ -683,6 +683,29 @@ def test_odd_grid_shapes(wb, fe, fe_orc, orc, NKFFT, nEF):
     assert empty[0].shape == specs[0].shape and not empty[0].any()
 
 
+@pytest.mark.parametrize("rmax,NKFFT", [(1, [4, 3, 5]), (2, [6, 6, 2]), (3, [5, 8, 3]), (4, [3, 2, 4])])
+def test_r_to_k_variants(wb, orc, rmax, NKFFT):
+    """The three implementations of the axes-1+0 pass of the R -> k transform (option fourier_method: 0 = partial sums in
+    registers, R-box edges up to 8; 2 = array of accumulators; 1 = two separate passes) against the oracle's transform
+    (fourier/fft.py:133-192) on R-boxes of 3, 5, 7 and 9 cells per edge (9: the default falls back to variant 2)."""
+    nw = 5
+    sysg = wb.synthetic_system(nw, rmax=rmax, seed=7 + rmax, matrices=("Ham", "AA"))
+    osys = orc.OracleSystem(sysg.rvec.iRvec, sysg.real_lattice, sysg.wannier_centers_cart, sysg._XX_R)
+    dK = np.array([0.11, 0.02, 0.31])
+    data = orc.OracleDataK(osys, dK, NKFFT)
+    T = osys.cRvec_shifted
+    want = dict(Ham=data._R_to_k(osys.XX_R["Ham"], True), AA=data._R_to_k(osys.XX_R["AA"], True),
+                dHam=data._R_to_k(orc.derivative(osys.XX_R["Ham"], T), False))
+    from wannierberri_b200 import _lib
+    for method in (0, 2, 1):
+        eng = wb.Engine(sysg)
+        eng.set_option("fourier_method", method)
+        eng.plan(NKFFT, [_lib.OMEGA])
+        for name, ref in want.items():
+            assert relerr(eng.xk(dK, name), ref) < 1e-13, (method, name)
+        eng.close()
+
+
 def test_full_size_properties(wb, fe):
     """BASELINE-size launches (K-blocks of 20^3 from the 400^3 grid, 2000 Fermi levels, 16 blocks = 128 000 k-points
     per call) through size-independent properties: the band-counting sum rule, linearity in the K-block weights,

@@ -336,6 +336,66 @@ wb_axis10_fused_kernel(const cplx* __restrict__ Z, cplx* __restrict__ X, const c
     }
 }
 
+// Same pass with the loops re-ordered for a small register footprint (more CTAs per SM): per k1 the n0 partial sums
+//   y[r0] = sum_{r1} W1[k1][r1] Z[r0][r1][t]
+// go to REGISTERS (n0 <= NR0, compile time), then every k0 is one short dot product  X[k0][k1][t] = sum_{r0} W0[k0][r0] y[r0]
+// that is stored at once -- no array of N0 accumulators.  Same arithmetic, same order of the r1 / r0 sums.
+template <int NR0, int TB, int KSPLIT, int MINB, int UK>
+__global__ void __launch_bounds__(TB * KSPLIT, MINB)
+wb_axis10_fused_y_kernel(const cplx* __restrict__ Z, cplx* __restrict__ X, const cplx* __restrict__ W1,
+                         const cplx* __restrict__ W0, int n0, int n1, int N0, int N1, long S2, long z_bstride,
+                         long x_bstride) {
+    extern __shared__ cplx sm_fy[];
+    cplx* Zs = sm_fy;                         // [n0*n1][TB]
+    cplx* W1s = Zs + (size_t)n0 * n1 * TB;    // [N1][n1]
+    cplx* W0s = W1s + N1 * n1;                // [N0][NR0], zero beyond n0
+    const int b = blockIdx.z;
+    const int el = threadIdx.x % TB, h = threadIdx.x / TB;
+    const long t = (long)blockIdx.x * TB + el;
+    for (int x = threadIdx.x; x < N1 * n1; x += TB * KSPLIT) W1s[x] = W1[(long)b * N1 * n1 + x];
+    for (int x = threadIdx.x; x < N0 * NR0; x += TB * KSPLIT) {
+        const int k = x / NR0, r = x - k * NR0;
+        W0s[x] = (r < n0) ? W0[((long)b * N0 + k) * n0 + r] : cmake(0., 0.);
+    }
+    const cplx* zsrc = Z + (long)b * z_bstride + t;
+    for (int x = h; x < n0 * n1; x += KSPLIT) Zs[x * TB + el] = (t < S2) ? __ldg(zsrc + (long)x * S2) : cmake(0., 0.);
+    __syncthreads();
+    if (t >= S2) return;
+    cplx* dst = X + (long)b * x_bstride + t;
+    const int k1lo = (int)((long)N1 * h / KSPLIT), k1hi = (int)((long)N1 * (h + 1) / KSPLIT);
+    for (int k1 = k1lo; k1 < k1hi; k1++) {
+        const cplx* w1 = W1s + k1 * n1;
+        cplx y[NR0];
+#pragma unroll
+        for (int r0 = 0; r0 < NR0; r0++) {
+            cplx y0 = cmake(0., 0.), y1 = cmake(0., 0.);
+            if (r0 < n0) {
+                const cplx* zrow = Zs + (size_t)r0 * n1 * TB + el;
+                int r1 = 0;
+                for (; r1 + 1 < n1; r1 += 2) {
+                    cfma(y0, w1[r1], zrow[r1 * TB]);
+                    cfma(y1, w1[r1 + 1], zrow[(r1 + 1) * TB]);
+                }
+                if (r1 < n1) cfma(y0, w1[r1], zrow[r1 * TB]);
+            }
+            y[r0] = cadd(y0, y1);
+        }
+        cplx* d1 = dst + (long)k1 * S2;
+#pragma unroll UK
+        for (int k0 = 0; k0 < N0; k0++) {
+            const cplx* w0 = W0s + k0 * NR0;
+            cplx a0 = cmake(0., 0.), a1 = cmake(0., 0.);
+#pragma unroll
+            for (int r0 = 0; r0 + 1 < NR0; r0 += 2) {
+                cfma(a0, w0[r0], y[r0]);
+                cfma(a1, w0[r0 + 1], y[r0 + 1]);
+            }
+            if (NR0 & 1) cfma(a0, w0[NR0 - 1], y[NR0 - 1]);
+            d1[(long)k0 * N1 * S2] = cadd(a0, a1);
+        }
+    }
+}
+
 // k-points of a K-block, bit-identical to the reference:
 //   points_FFT = ix * (1./N)   (grid/grid.py:68-75) ;  kpoints_all = (points_FFT + dK) % 1  (data_K.py:146-151)
 __global__ void wb_kpoints_kernel(const double* __restrict__ dK, int3 N, double* __restrict__ kpts) {

@@ -570,8 +570,33 @@ static int launch_fused10(wbgpu_ctx* c, int nb, size_t smem) {
     return 0;
 }
 
+template <int NR0, int TB, int KSPLIT, int MINB, int UK>
+static int launch_fused10_y(wbgpu_ctx* c, int nb) {
+    const int n0 = c->nbox.x, n1 = c->nbox.y;
+    const int* N = c->N;
+    const long S2 = (long)N[2] * c->L.E;
+    const size_t smem = sizeof(cplx) * ((size_t)n0 * n1 * TB + (size_t)N[1] * n1 + (size_t)N[0] * NR0);
+    if ((int)smem > c->smem_optin) return -1;
+    auto kern = wb_axis10_fused_y_kernel<NR0, TB, KSPLIT, MINB, UK>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    dim3 grid((unsigned)((S2 + TB - 1) / TB), 1, (unsigned)nb);
+    kern<<<grid, TB * KSPLIT, smem, c->stream>>>(c->d_Z, c->d_X, c->d_W[1], c->d_W[0], n0, n1, N[0], N[1], S2,
+                                                 (long)n0 * n1 * S2, (long)N[0] * N[1] * S2);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // returns -1 when the fused kernel does not apply
 static int fused_axis10(wbgpu_ctx* c, int nb) {
+    // default: the low-register kernel (partial sums over r1 in registers; 80 registers, three 256-thread CTAs per SM):
+    // measured 2.34 ms against 2.88 ms per 256k k-points for the KC-accumulator kernel below (fourier_method 2)
+    if (c->fourier_method != 2 && c->nbox.x <= 8) {
+        int rc = c->nbox.x <= 4 ? launch_fused10_y<4, 64, 4, 3, 5>(c, nb)
+               : c->nbox.x <= 6 ? launch_fused10_y<6, 64, 4, 3, 5>(c, nb) : launch_fused10_y<8, 64, 4, 3, 5>(c, nb);
+        if (rc >= 0) return rc;
+    }
     const int n0 = c->nbox.x, n1 = c->nbox.y;
     const int* N = c->N;
     const int KC = N[0] <= 8 ? 8 : N[0] <= 12 ? 12 : N[0] <= 16 ? 16 : 20;
