@@ -150,6 +150,148 @@ wb_rotate_gemm_kernel(const cplx* __restrict__ rec, long recE, WbChanList ch, in
     }
 }
 
+// Small matrices (nw <= 8 NTL <= 32: one column panel holds the whole matrix): a 64-row MMA tile of the kernel above is
+// mostly padding -- 24 of 64 rows at nw = 24 -- while every CTA pays the same staging steps and barriers.  Here a CTA
+// rotates CG channels of a k-point at once: step 1 stacks their rows along M ([X_1; X_2; ..] U, CG nw <= 64 rows), step 2
+// stacks the Y panels along N (U^dagger [Y_1 | Y_2 | ..]); U is staged once per CG channels.
+template <int NTL, int KC, int CG>
+__host__ __device__ constexpr int wb_gemm_cg_ldp() { return 8 * NTL * CG + 2; }
+
+template <int NTL, int KC, int CG>
+__host__ inline size_t wb_gemm_cg_smem_bytes(int nw) {
+    int nwp = (nw + KC - 1) / KC * KC;
+    return sizeof(cplx) * ((size_t)nwp * wb_gemm_cg_ldp<NTL, KC, CG>() + 64 * (KC + 4) + (size_t)KC * (8 * NTL + 2));
+}
+
+template <int NTL, int KC, int CG>
+__global__ void __launch_bounds__(128)
+wb_rotate_gemm_cg_kernel(const cplx* __restrict__ rec, long recE, WbChanList ch, int nw, long nk,
+                         const cplx* __restrict__ Uall, cplx* __restrict__ xbar) {
+    constexpr int TN = 8 * NTL, LDP = wb_gemm_cg_ldp<NTL, KC, CG>(), LDA = KC + 4, LDB = TN + 2;
+    extern __shared__ __align__(16) cplx smem_rc[];
+    const int nwp = (nw + KC - 1) / KC * KC;
+    cplx* Yp = smem_rc;                     // [nwp][CG * TN (+2)]: Y of channel cc in columns cc TN ..
+    cplx* As = Yp + (size_t)nwp * LDP;      // [64][LDA]
+    cplx* Bs = As + 64 * LDA;               // [KC][LDB]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int ic0 = blockIdx.y * CG;
+    const int ncg = (ch.n - ic0 < CG) ? (ch.n - ic0) : CG;   // channels of this CTA
+    const int n2 = nw * nw, M = ncg * nw;
+    for (long ik = blockIdx.z; ik < nk; ik += gridDim.z) {
+        const cplx* r = rec + ik * recE;
+        const cplx* U = Uall + ik * n2;
+        __syncthreads();
+        for (int x = threadIdx.x; x < nwp * LDP; x += 128) Yp[x] = cmake(0., 0.);
+        // ---- step 1: Y_cc = X_cc U, rows of the channels stacked
+#pragma unroll 1
+        for (int m0 = 0; m0 < M; m0 += 64) {
+            double are[2][NTL][2], aim[2][NTL][2];
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int t = 0; t < NTL; t++) are[i][t][0] = are[i][t][1] = aim[i][t][0] = aim[i][t][1] = 0.;
+            const bool act0 = m0 + 8 * warp < M, act1 = m0 + 8 * (warp + 4) < M;
+#pragma unroll 1
+            for (int j0 = 0; j0 < nw; j0 += KC) {
+                __syncthreads();
+                for (int x = threadIdx.x; x < 64 * KC; x += 128) {
+                    const int c = x % KC, rr = x / KC;
+                    const int R = m0 + rr, j = j0 + c;
+                    cplx v = cmake(0., 0.);
+                    if (R < M && j < nw) {
+                        const int cc = R / nw, m = R - cc * nw;
+                        const int off = ch.off[ic0 + cc];
+                        v = ch.herm[ic0 + cc] ? load_herm(r, off, m, j, nw) : r[off + m * nw + j];
+                    }
+                    As[rr * LDA + c] = v;
+                }
+                for (int x = threadIdx.x; x < KC * TN; x += 128) {
+                    const int c = x % TN, rr = x / TN;
+                    const int j = j0 + rr;
+                    Bs[rr * LDB + c] = (j < nw && c < nw) ? U[j * nw + c] : cmake(0., 0.);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < KC; kk += 4) {
+                    cplx b[NTL];
+#pragma unroll
+                    for (int t = 0; t < NTL; t++) b[t] = Bs[(kk + q) * LDB + 8 * t + g];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if (i == 0 ? act0 : act1) {
+                            const cplx a = As[(8 * (warp + 4 * i) + g) * LDA + kk + q];
+#pragma unroll
+                            for (int t = 0; t < NTL; t++) {
+                                wb_dmma_acc(are[i][t][0], are[i][t][1], a.x, b[t].x);
+                                wb_dmma_acc(are[i][t][0], are[i][t][1], -a.y, b[t].y);
+                                wb_dmma_acc(aim[i][t][0], aim[i][t][1], a.x, b[t].y);
+                                wb_dmma_acc(aim[i][t][0], aim[i][t][1], a.y, b[t].x);
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int R = m0 + 8 * (warp + 4 * i) + g;
+                if (R < M) {
+                    const int cc = R / nw, m = R - cc * nw;
+                    cplx* yrow = Yp + (size_t)m * LDP + cc * TN;
+#pragma unroll
+                    for (int t = 0; t < NTL; t++) {
+                        yrow[8 * t + 2 * q] = cmake(are[i][t][0], aim[i][t][0]);
+                        yrow[8 * t + 2 * q + 1] = cmake(are[i][t][1], aim[i][t][1]);
+                    }
+                }
+            }
+        }
+        // ---- step 2: C_cc = U^dagger Y_cc, the Y panels stacked along N; the nw <= 32 rows n are one 8-row tile per warp
+        {
+            double are[NTL * CG][2], aim[NTL * CG][2];
+#pragma unroll
+            for (int t = 0; t < NTL * CG; t++) are[t][0] = are[t][1] = aim[t][0] = aim[t][1] = 0.;
+            const bool act = 8 * warp < nw;
+#pragma unroll 1
+            for (int j0 = 0; j0 < nw; j0 += KC) {
+                __syncthreads();   // (first pass: Y complete)
+                for (int x = threadIdx.x; x < 32 * KC; x += 128) {
+                    const int rr = x % 32, c = x / 32;
+                    const int i = j0 + c;
+                    As[rr * LDA + c] = (rr < nw && i < nw) ? cconj(U[i * nw + rr]) : cmake(0., 0.);
+                }
+                __syncthreads();
+                const cplx* Bsrc = Yp + (size_t)j0 * LDP;
+                if (act) {
+#pragma unroll
+                    for (int kk = 0; kk < KC; kk += 4) {
+                        const cplx a = As[(8 * warp + g) * LDA + kk + q];
+#pragma unroll
+                        for (int t = 0; t < NTL * CG; t++) {
+                            const cplx bt = Bsrc[(kk + q) * LDP + 8 * t + g];
+                            wb_dmma_acc(are[t][0], are[t][1], a.x, bt.x);
+                            wb_dmma_acc(are[t][0], are[t][1], -a.y, bt.y);
+                            wb_dmma_acc(aim[t][0], aim[t][1], a.x, bt.y);
+                            wb_dmma_acc(aim[t][0], aim[t][1], a.y, bt.x);
+                        }
+                    }
+                }
+            }
+            const int n = 8 * warp + g;
+            if (n < nw) {
+#pragma unroll
+                for (int t = 0; t < NTL * CG; t++) {
+                    const int cc = t / NTL, l = 8 * (t - cc * NTL) + 2 * q;
+                    if (cc < ncg) {
+                        cplx* out = xbar + ((size_t)ik * ch.n + ic0 + cc) * n2 + (size_t)n * nw;
+                        if (l < nw) out[l] = cmake(are[t][0], aim[t][0]);
+                        if (l + 1 < nw) out[l + 1] = cmake(are[t][1], aim[t][1]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Formula stage on rotated matrices held in global memory: one CTA per k-point.
 // xbar[k][nch][nw][nw]; the channel triples are ordered V | A | B | O | C | S (those present) and are read in place
 // (L2): staging them in shared memory was measured and does not pay, the kernel is bound by its sums, not by latency.

@@ -116,6 +116,7 @@ struct wbgpu_ctx {
     int kubo_method = 0;    // 0 = register-tiled accumulation of the optical conductivity, 1 = per-(omega, re|im) kernel
     int rotate_trim = 1;    // 1 = form only the needed columns of the rotated matrices when they are hermitian
     int dh_packed = 1;      // 1 = pack d_a H as a triangle when it is hermitian in R-space, 0 = never
+    int gemm_stack = 1;     // 1 = the size-generic rotation stacks several channels per CTA when nw <= 32
     std::vector<int> h_iRvec;
     // optional per-stage device timing (option "timing"): events around each stage of each batch
     int timing = 0;
@@ -248,6 +249,7 @@ extern "C" int wbgpu_set_option(wbgpu_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "eig_method")) { c->eig_method = (int)value; return 0; }
     if (!strcmp(name, "rotate_method")) { c->rotate_method = (int)value; return 0; }
     if (!strcmp(name, "fourier_method")) { c->fourier_method = (int)value; return 0; }
+    if (!strcmp(name, "gemm_stack")) { c->gemm_stack = (int)value; return 0; }
     if (!strcmp(name, "rot_r2")) { c->rot_r2 = (int)value; return 0; }
     if (!strcmp(name, "rotate_trim")) { c->rotate_trim = (int)value; return 0; }
     if (!strcmp(name, "kubo_method")) { c->kubo_method = (int)value; return 0; }
@@ -880,9 +882,32 @@ static int launch_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n) {
     return 0;
 }
 
+template <int NTL, int KC, int CG>
+static int launch_gemm_cg(wbgpu_ctx* c, const WbChanList& ch, long k0, long n) {
+    const int nw = c->nw;
+    size_t smem = wb_gemm_cg_smem_bytes<NTL, KC, CG>(nw);
+    if ((int)smem > c->smem_optin) return set_err("rotate(gemm): num_wann=%d needs %zu B shared memory", nw, smem);
+    CK(cudaFuncSetAttribute(wb_rotate_gemm_cg_kernel<NTL, KC, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(1, (unsigned)((ch.n + CG - 1) / CG), (unsigned)std::min(n, 16384L));
+    wb_rotate_gemm_cg_kernel<NTL, KC, CG><<<grid, 128, smem, c->stream>>>(c->d_X + (size_t)k0 * c->L.E, (long)c->L.E, ch, nw, n,
+                                                                        c->d_U + (size_t)k0 * nw * nw, (cplx*)c->d_xbar);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // U^dagger X U of the listed channels for k-points [k0, k0 + n) -> c->d_xbar[n][ch.n][nw][nw]
 static int rotate_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n) {
     const int nw = c->nw;
+    if (c->gemm_stack) {   // several channels per CTA for small matrices (option gemm_stack, default on)
+        // (NTL, KC, CG) by size; measured per 128k k-points: Te (24 WF, 18 channels) 33.6 -> 26.5 ms with (3, 8, 2) against
+        // one channel per CTA -- (3, 24, 2) is slower, 3 CTAs per SM; Fe (18 WF, 15 channels) 33.7 -> 25.0 ms with (3, 20, 3)
+        if (nw <= 8) return launch_gemm_cg<1, 8, 4>(c, ch, k0, n);
+        if (nw <= 16) return launch_gemm_cg<2, 8, 4>(c, ch, k0, n);
+        if (nw <= 20) return launch_gemm_cg<3, 20, 3>(c, ch, k0, n);
+        if (nw <= 24) return launch_gemm_cg<3, 8, 2>(c, ch, k0, n);
+        if (nw <= 32) return launch_gemm_cg<4, 16, 2>(c, ch, k0, n);
+    }
     if (nw <= 8) return launch_gemm<1, 8>(c, ch, k0, n);
     if (nw <= 16) return launch_gemm<2, 8>(c, ch, k0, n);
     if (nw <= 24) return launch_gemm<3, 8>(c, ch, k0, n);
