@@ -100,7 +100,7 @@ enum {
 };
 
 /* One Fermi-level scan = one StaticCalculator.__call__ (calculators/static.py:26-169),
- * tetra=False, k_resolved=False, select_bands=None. */
+ * tetra=False, k_resolved=False. */
 typedef struct wbgpu_scan_spec {
     int32_t formula;         /* WBGPU_*                                                     */
     int32_t fder;            /* 0 Fermi sea, 1..3 derivatives of f (static.py:137-147)        */
@@ -113,6 +113,12 @@ typedef struct wbgpu_scan_spec {
     double dEF;              /* Efermi[1]-Efermi[0]  (0.001 if nEF == 1), static.py:55       */
     double degen_thresh;     /* calculator.py:20                                             */
     double factor;           /* constant_factor (or its sign), hole_like already applied     */
+    /* select_bands (static.py:93-100, 129-136; utility.py:398-403): bit b of select_mask[b / 64] set = band b selected.
+     * A band group counts with the fraction of its bands that is selected (groups without a selected band drop out).
+     * use_select = 0: all bands.  Fermi-surface scans only (fder >= 1), as in the reference (data_K.py:179-180). */
+    uint64_t select_mask[2];
+    int32_t use_select;
+    int32_t reserved;
 } wbgpu_scan_spec;
 
 const char* wbgpu_last_error(void);

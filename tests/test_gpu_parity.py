@@ -259,6 +259,30 @@ def test_soc_system_vs_reference_data_k_soc(wb):
         assert relerr(res.results[key].data, g["res_" + key]) < RTOL, key
 
 
+def test_select_bands(wb, fe):
+    """`select_bands` of the Fermi-surface calculators (static.py:93-100, 129-136) against the fixture of the unmodified
+    reference; the band-resolved results add up to the unrestricted one (the reference's tests/test_calc.py:231-248); the
+    Fermi sea and the tetrahedron method refuse it."""
+    from test_oracle import SELECT_CASES, select_of
+    g = np.load(os.path.join(GOLDEN, "golden_select.npz"))
+    st = wb.calculators.static
+    Ef = g["Efermi"]
+    calcs = {k: getattr(st, name)(Efermi=Ef, select_bands=select_of(g, k), **kw) for k, (name, kw) in SELECT_CASES.items()}
+    grid = wb.Grid(fe, NK=g["NK"], NKFFT=g["NKFFT"])
+    res = wb.run(fe, grid, calcs, use_irred_kpt=False, symmetrize=False, write_files=False)
+    for key in calcs:
+        assert relerr(res.results[key].data, g[key]) < RTOL, key
+    bands = {f"{i:02d}": st.Ohmic_FermiSurf(Efermi=Ef, select_bands=(i,)) for i in range(fe.num_wann)}
+    bands["all"] = st.Ohmic_FermiSurf(Efermi=Ef)
+    rb = wb.run(fe, grid, bands, use_irred_kpt=False, symmetrize=False, write_files=False)
+    total = sum(rb.results[k].data for k in bands if k != "all")
+    assert relerr(total, rb.results["all"].data) < 1e-10
+    with pytest.raises(NotImplementedError):
+        wb.run(fe, grid, dict(a=st.AHC(Efermi=Ef, select_bands=(1,))), write_files=False)
+    with pytest.raises(NotImplementedError):
+        st.Ohmic_FermiSurf(Efermi=Ef, select_bands=(1,), tetra=True)
+
+
 def test_data_k_plugin_attributes(wb, fe, fe_orc, orc):
     """Plug-in hook #1 (data_K/data_K_R.py:69-97, data_K/data_K.py:211-326): what a user formula
     reads from `Data_K_R` -- `E_K`, `UU_K`, `Xbar(name, der)`, `D_H`, `dEig_inv`, `delE_K`, `kpoints_all`, band groups

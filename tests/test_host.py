@@ -85,9 +85,13 @@ def test_calculator_windows_and_errors():
     assert [x.formula for x in m.specs()] == [_lib.MORB_HPM, _lib.OMEGA]
     assert st.AHC(Efermi=Ef, hole_like=True).constant_factor == -a.constant_factor
     assert st.AHC(Efermi=Ef, use_factor=False).specs()[0].factor == -1.0
-    for bad in (dict(tetra=True, hole_like=True), dict(k_resolved=True), dict(select_bands=[1]), dict(tetra=True, Emin=0.)):
+    for bad in (dict(tetra=True, hole_like=True), dict(k_resolved=True), dict(select_bands=[1], tetra=True), dict(tetra=True, Emin=0.)):
         with pytest.raises(NotImplementedError):
             st.AHC(Efermi=Ef, **bad)
+    with pytest.raises(NotImplementedError):   # "Selection of bands for Fermi sea is not implemented" (data_K.py:179-180)
+        st.AHC(Efermi=Ef, select_bands=[1]).specs()
+    sel = st.Ohmic_FermiSurf(Efermi=Ef, select_bands=(3, 70, 3)).specs()[0]
+    assert sel.use_select == 1 and sel.select_mask[0] == 1 << 3 and sel.select_mask[1] == 1 << 6
     with pytest.raises(ValueError):
         st.AHC(Efermi=5.0)
     w = st.AHC(Efermi=Ef, Emin=13., Emax=20.)   # read by the tetrahedron method only (as in the reference)

@@ -394,3 +394,28 @@ def test_soc_system_flattening_vs_reference_data_k_soc():
     for key in SOC_CALCS:
         want = g["res_" + key]
         assert np.abs(res[key] - want).max() <= RTOL * np.abs(want).max(), key
+
+
+SELECT_CASES = dict(ohmic_sel=("Ohmic_FermiSurf", dict(degen_thresh=0.3)), dos_sel=("DOS", {}),
+                    bcd_sel=("BerryDipole_FermiSurf", dict(degen_thresh=0.3, degen_Kramers=True)),
+                    gme_sel=("GME_orb_FermiSurf", {}), ohmic_all=("Ohmic_FermiSurf", dict(degen_thresh=0.3)))
+
+
+def select_of(g, key):
+    return None if key == "ohmic_all" else np.array([5]) if key == "gme_sel" else g["select"]
+
+
+def test_select_bands_vs_reference():
+    """`select_bands` (calculators/static.py:93-100, 129-136; utility.py:398-403): band groups count with the fraction of
+    their bands that is selected; fixture from the unmodified reference (tests/golden/make_golden_select.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_select.npz"))
+    osys = orc.OracleSystem.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+    NKdiv = (g["NK"] // g["NKFFT"]).tolist()
+    calcs = {k: (name, g["Efermi"], dict(kw, **({} if select_of(g, k) is None else dict(select_bands=select_of(g, k)))))
+             for k, (name, kw) in SELECT_CASES.items()}
+    res = orc.run(osys, NKdiv, g["NKFFT"].tolist(), calcs)
+    for key in calcs:
+        assert np.abs(res[key] - g[key]).max() <= RTOL * np.abs(g[key]).max(), key
+    data = orc.OracleDataK(osys, [0., 0., 0.], g["NKFFT"])
+    with pytest.raises(NotImplementedError):
+        orc.CALCULATORS["AHC"](data, g["Efermi"], select_bands=np.array([1]))

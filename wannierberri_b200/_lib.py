@@ -26,7 +26,8 @@ class ScanSpec(C.Structure):
     _fields_ = [("formula", C.c_int32), ("fder", C.c_int32), ("nEF", C.c_int32), ("degen_Kramers", C.c_int32),
                 ("internal_terms", C.c_int32), ("external_terms", C.c_int32),
                 ("Ef_first", C.c_double), ("Ef_last", C.c_double), ("dEF", C.c_double),
-                ("degen_thresh", C.c_double), ("factor", C.c_double)]
+                ("degen_thresh", C.c_double), ("factor", C.c_double),
+                ("select_mask", C.c_uint64 * 2), ("use_select", C.c_int32), ("reserved", C.c_int32)]
 
     @property
     def size(self):

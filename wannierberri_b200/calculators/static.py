@@ -58,7 +58,12 @@ class StaticCalculator(Calculator):
         if k_resolved:
             raise NotImplementedError("k_resolved=True is not implemented on the GPU path")
         if select_bands is not None:
-            raise NotImplementedError("select_bands is not implemented on the GPU path")
+            # static.py:93-100, 129-136: band groups count with the fraction of their bands that is selected
+            select_bands = np.array(sorted(set(int(b) for b in np.atleast_1d(select_bands))), dtype=int)
+            if tetra:
+                raise NotImplementedError("select_bands with tetra=True is not implemented on the GPU path")
+            if len(select_bands) and (select_bands[0] < 0 or select_bands[-1] >= 128):
+                raise ValueError("select_bands: band indices must lie in [0, 128)")
         if smoother is not None and not callable(smoother):
             raise ValueError("smoother must be callable as smoother(A, axis=0) (wannierberri_b200.smoother or the reference's)")
         self.kwargs_formula = copy(kwargs_formula) if kwargs_formula is not None else {}
@@ -109,12 +114,19 @@ class StaticCalculator(Calculator):
     def _spec(self, formula=None, fder=None):
         f = self.Formula if formula is None else formula
         factor = self.constant_factor if self.use_factor else float(np.sign(self.constant_factor))
-        return ScanSpec(formula=f, fder=self.fder if fder is None else fder, nEF=len(self.Efermi),
+        spec = ScanSpec(formula=f, fder=self.fder if fder is None else fder, nEF=len(self.Efermi),
                         degen_Kramers=int(bool(self.degen_Kramers)),
                         internal_terms=int(bool(self.kwargs_formula.get("internal_terms", True))),
                         external_terms=int(bool(self.kwargs_formula.get("external_terms", True))),
                         Ef_first=float(self.Efermi[0]), Ef_last=float(self.Efermi[-1]), dEF=float(self.dEF),
                         degen_thresh=float(self.degen_thresh), factor=float(factor))
+        if self.select_bands is not None:
+            if spec.fder == 0:   # data_K.py:179-180
+                raise NotImplementedError("Selection of bands for Fermi sea is not implemented")
+            spec.use_select = 1
+            for b in self.select_bands:
+                spec.select_mask[int(b) // 64] |= 1 << (int(b) % 64)
+        return spec
 
     def specs(self):
         return [self._spec()]
@@ -159,10 +171,13 @@ class StaticCalculator(Calculator):
                 edge = {x: formula.trace(ik, np.arange(0, x), np.arange(x, nb)) for x in {e for g in groups for e in g}}
                 values = {g: edge[g[1]] - edge[g[0]] for g in groups}
             for g, E in groups.items():
+                w = 1.   # utility.py:398-403: fraction of the group's bands that is selected
+                if self.select_bands is not None:
+                    w = np.sum((self.select_bands >= g[0]) & (self.select_bands < g[1])) / (g[1] - g[0])
                 if E < self.EFmin:
-                    steps[0] += values[g]
+                    steps[0] += values[g] * w
                 elif E <= self.EFmax:
-                    steps[ceil((E - self.EFmin) / self.dEF)] += values[g]
+                    steps[ceil((E - self.EFmin) / self.dEF)] += values[g] * w
         tot = np.cumsum(steps[:-1], axis=0)
         d = self.dEF
         if self.fder == 1:

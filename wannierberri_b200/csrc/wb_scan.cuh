@@ -37,7 +37,9 @@ __global__ void wb_identity_events_kernel(const double* __restrict__ Eall, int n
 __global__ void __launch_bounds__(256)
 wb_scan_accumulate_kernel(const double* __restrict__ ev_label, const double* __restrict__ ev_val, int ev_stride,
                           long nslots, int slots_per_block /* nk_block * nw */, const double* __restrict__ weight,
-                          int ncomp, WbWindow win, double* __restrict__ hist, int use_smem, long per_block_stride) {
+                          int ncomp, WbWindow win, double* __restrict__ hist, int use_smem, long per_block_stride,
+                          const double* __restrict__ Eall = nullptr, int nw = 0, unsigned long long sel0 = 0ull,
+                          unsigned long long sel1 = 0ull) {
     extern __shared__ double hist_s[];
     const int nrow = win.nEFx + 1;
     long s_begin = 0, s_end = nslots;
@@ -64,6 +66,19 @@ wb_scan_accumulate_kernel(const double* __restrict__ ev_label, const double* __r
             row = 1 + iEf;
         } else continue;
         double w = (per_block_stride > 0) ? 1. : weight[s / slots_per_block];
+        if (Eall) {
+            // select_bands: the group that starts at band x ends at the next border (gap > degen_thresh, on an even band
+            // with degen_Kramers: grid/tetrahedron.py:131-136); weight = selected bands of the group / its size
+            const long k = s / nw;
+            const int x = (int)(s - k * nw);
+            const double* Ek = Eall + k * nw;
+            int b = x + 1;
+            while (b < nw && !((Ek[b] - Ek[b - 1] > win.degen_thresh) && (!win.degen_Kramers || (b & 1) == 0))) b++;
+            int cnt = 0;
+            for (int j = x; j < b; j++) cnt += (int)(((j < 64 ? sel0 >> j : sel1 >> (j - 64)) & 1ull));
+            if (cnt == 0) continue;
+            w *= (double)cnt / (double)(b - x);
+        }
         for (int c = 0; c < ncomp; c++) atomicAdd(&h[row * ncomp + c], w * ev_val[s * ev_stride + c]);
     }
     if (use_smem) {

@@ -1219,6 +1219,7 @@ static int check_spec(const wbgpu_ctx* c, const wbgpu_scan_spec& s) {
     if (s.nEF < 1) return set_err("scan: nEF=%d", s.nEF);
     if (!(s.dEF > 0)) return set_err("scan: dEF must be positive (Efermi must be an increasing uniform grid)");
     if (!((c->mask >> s.formula) & 1u)) return set_err("scan: formula %d was not declared in wbgpu_plan", s.formula);
+    if (s.use_select && s.fder == 0) return set_err("scan: Selection of bands for Fermi sea is not implemented");
     return 0;
 }
 
@@ -1289,12 +1290,14 @@ static int static_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, con
                               (unsigned)nb);
                     wb_scan_accumulate_kernel<<<grid, 256, use_smem ? hbytes : 0, c->stream>>>(
                         c->d_evlabel, c->d_evval + G.ev.off[s.formula], G.ev.NC, nslots, (int)(c->nk_block * nw), nullptr, ncomp,
-                        G.win, c->d_hist + hoff[i], use_smem, (long)hoff[nspec]);
+                        G.win, c->d_hist + hoff[i], use_smem, (long)hoff[nspec], s.use_select ? c->d_E : nullptr, nw,
+                        (unsigned long long)s.select_mask[0], (unsigned long long)s.select_mask[1]);
                 } else {
                     long nblk = std::min((nslots + 255) / 256, 148L * 2);
                     wb_scan_accumulate_kernel<<<(unsigned)nblk, 256, use_smem ? hbytes : 0, c->stream>>>(
                         c->d_evlabel, c->d_evval + G.ev.off[s.formula], G.ev.NC, nslots, (int)(c->nk_block * nw), weight_dev + b0,
-                        ncomp, G.win, c->d_hist + hoff[i], use_smem, 0L);
+                        ncomp, G.win, c->d_hist + hoff[i], use_smem, 0L, s.use_select ? c->d_E : nullptr, nw,
+                        (unsigned long long)s.select_mask[0], (unsigned long long)s.select_mask[1]);
                 }
                 c->launches++;
             }
@@ -1414,6 +1417,7 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
     std::vector<size_t> hoff(nspec + 1, 0);
     for (int i = 0; i < nspec; i++) {
         if (check_spec(c, specs[i])) return 1;
+        if (specs[i].use_select) return set_err("scan: select_bands with the tetrahedron method is not implemented");
         size_t sz = (size_t)specs[i].nEF * formula_ncomp(specs[i].formula);
         hoff[i + 1] = hoff[i] + 2 * sz;   // direct | suffix
         nout += sz;
