@@ -118,7 +118,13 @@ typedef struct wbgpu_scan_spec {
      * use_select = 0: all bands.  Fermi-surface scans only (fder >= 1), as in the reference (data_K.py:179-180). */
     uint64_t select_mask[2];
     int32_t use_select;
-    int32_t reserved;
+    /* tetrahedron method only (wbgpu_static_scan_tetra; grid/tetrahedron.py:197-198, 246-266; static.py:84-91):
+     * bit 0 = hole_like: weights 1 - occupation, plus the group of the bands above Efermi[-1] (up to tetra_Emax if bit 2);
+     * bit 1 = tetra_Emin is set: the Fermi-sea group starts at the first band that reaches it;  bit 2 = tetra_Emax is set.
+     * The plain scans ignore them, as the reference does (data_K.py:172-185). */
+    int32_t tetra_flags;
+    double tetra_Emin;
+    double tetra_Emax;
 } wbgpu_scan_spec;
 
 const char* wbgpu_last_error(void);

@@ -669,6 +669,21 @@ def test_tetra_block_vs_reference(wb, fe, case):
     assert relerr(res.data, g["block_" + case]) < TETRA_RTOL.get(case, RTOL)
 
 
+def test_tetra_hole_like_and_emin(wb, fe):
+    """tetra=True with hole_like (weights 1 - occupation and the group of the bands above the Fermi axis, up to Emax) and
+    with Emin on Fermi-sea quantities (grid/tetrahedron.py:197-198, 246-266; static.py:50-52, 84-91) against the fixture of
+    the unmodified reference (tests/golden/make_golden_tetra_holes.py)."""
+    from test_oracle import TETRA_HOLE_CASES
+    g = np.load(os.path.join(GOLDEN, "golden_fe_tetra_holes.npz"))
+    st = wb.calculators.static
+    calcs = {k: getattr(st, name)(Efermi=g["Efermi"], tetra=True, **kw) for k, (name, kw) in TETRA_HOLE_CASES.items()}
+    res = wb.run(fe, wb.Grid(fe, NK=g["NK"], NKFFT=g["NKFFT"]), calcs, use_irred_kpt=False, symmetrize=False, write_files=False)
+    for key in calcs:
+        assert relerr(res.results[key].data, g[key]) < RTOL, key
+    with pytest.raises(NotImplementedError):
+        st.DOS(Efermi=g["Efermi"], tetra=True, hole_like=True)
+
+
 def test_tetra_run_vs_reference(wb, fe):
     """run() mixing tetrahedron and plain calculators on a whole (small) grid against the reference's run()."""
     g = np.load(os.path.join(GOLDEN, "golden_fe_tetra.npz"))

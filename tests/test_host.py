@@ -85,9 +85,14 @@ def test_calculator_windows_and_errors():
     assert [x.formula for x in m.specs()] == [_lib.MORB_HPM, _lib.OMEGA]
     assert st.AHC(Efermi=Ef, hole_like=True).constant_factor == -a.constant_factor
     assert st.AHC(Efermi=Ef, use_factor=False).specs()[0].factor == -1.0
-    for bad in (dict(tetra=True, hole_like=True), dict(k_resolved=True), dict(select_bands=[1], tetra=True), dict(tetra=True, Emin=0.)):
+    for bad in (dict(k_resolved=True), dict(select_bands=[1], tetra=True)):
         with pytest.raises(NotImplementedError):
             st.AHC(Efermi=Ef, **bad)
+    with pytest.raises(NotImplementedError):   # hole_like weights of the tetrahedron method: Fermi-sea quantities only
+        st.DOS(Efermi=Ef, tetra=True, hole_like=True)
+    t = st.AHC(Efermi=Ef, tetra=True, hole_like=True, Emax=30.).specs()[0]
+    assert t.tetra_flags == 5 and t.tetra_Emax == 30. and st.AHC(Efermi=Ef, tetra=True, Emin=13.).specs()[0].tetra_flags == 2
+    assert st.AHC(Efermi=Ef, Emin=13.).specs()[0].tetra_flags == 0   # not read without tetra
     with pytest.raises(NotImplementedError):   # "Selection of bands for Fermi sea is not implemented" (data_K.py:179-180)
         st.AHC(Efermi=Ef, select_bands=[1]).specs()
     sel = st.Ohmic_FermiSurf(Efermi=Ef, select_bands=(3, 70, 3)).specs()[0]

@@ -419,3 +419,22 @@ def test_select_bands_vs_reference():
     data = orc.OracleDataK(osys, [0., 0., 0.], g["NKFFT"])
     with pytest.raises(NotImplementedError):
         orc.CALCULATORS["AHC"](data, g["Efermi"], select_bands=np.array([1]))
+
+
+TETRA_HOLE_CASES = dict(ahc_holes=("AHC", dict(hole_like=True)), cumdos_holes=("CumDOS", dict(hole_like=True)),
+                        morb_holes=("Morb", dict(hole_like=True)), ahc_holes_emax=("AHC", dict(hole_like=True, Emax=30.)),
+                        ahc_emin=("AHC", dict(Emin=12.5)), cumdos_emin=("CumDOS", dict(Emin=11.)),
+                        ohmic_sea_emin=("Ohmic_FermiSea", dict(Emin=12.5, degen_thresh=0.05)), ahc_plain=("AHC", {}))
+
+
+def test_tetra_hole_like_and_emin_vs_reference():
+    """tetra=True with hole_like (weights 1 - occupation and the group of the bands above the Fermi axis, up to Emax) and
+    with Emin on Fermi-sea quantities (grid/tetrahedron.py:197-198, 246-266; static.py:50-52, 84-91) against the fixture of
+    the unmodified reference (tests/golden/make_golden_tetra_holes.py)."""
+    g = np.load(os.path.join(GOLDEN, "golden_fe_tetra_holes.npz"))
+    osys = orc.OracleSystem.from_npz(os.path.join(GOLDEN, "fe_system.npz"))
+    NKdiv = (g["NK"] // g["NKFFT"]).tolist()
+    calcs = {k: (name, g["Efermi"], dict(kw, tetra=True)) for k, (name, kw) in TETRA_HOLE_CASES.items()}
+    res = orc.run(osys, NKdiv, g["NKFFT"].tolist(), calcs)
+    for key in calcs:
+        assert np.abs(res[key] - g[key]).max() <= RTOL * np.abs(g[key]).max(), key

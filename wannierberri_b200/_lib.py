@@ -27,7 +27,8 @@ class ScanSpec(C.Structure):
                 ("internal_terms", C.c_int32), ("external_terms", C.c_int32),
                 ("Ef_first", C.c_double), ("Ef_last", C.c_double), ("dEF", C.c_double),
                 ("degen_thresh", C.c_double), ("factor", C.c_double),
-                ("select_mask", C.c_uint64 * 2), ("use_select", C.c_int32), ("reserved", C.c_int32)]
+                ("select_mask", C.c_uint64 * 2), ("use_select", C.c_int32), ("tetra_flags", C.c_int32),
+                ("tetra_Emin", C.c_double), ("tetra_Emax", C.c_double)]
 
     @property
     def size(self):

@@ -53,8 +53,6 @@ class StaticCalculator(Calculator):
         self.Efermi = np.array(Efermi)
         if self.Efermi.ndim != 1 or len(self.Efermi) < 1:
             raise ValueError("Efermi must be a 1-d array")
-        if tetra and hole_like:
-            raise NotImplementedError("tetra=True with hole_like (inverse Fermi sea, der=-1) is not implemented on the GPU path")
         if k_resolved:
             raise NotImplementedError("k_resolved=True is not implemented on the GPU path")
         if select_bands is not None:
@@ -88,8 +86,10 @@ class StaticCalculator(Calculator):
         # group for fder = 0, Emax = upper edge of the inverse Fermi sea of hole_like).  Same here: no effect without
         # tetra; the one case in which they would act raises.
         self.Emin, self.Emax = Emin, Emax
-        if tetra and self.fder == 0 and Emin != -np.inf:
-            raise NotImplementedError("tetra=True with Emin (lower edge of the Fermi-sea group) is not implemented on the GPU path")
+        if tetra and hole_like and self.fder != 0:
+            # the reference takes the der = -1 weights whatever fder is (static.py:84-88); only the inverse Fermi SEA is
+            # a defined quantity
+            raise NotImplementedError("tetra=True with hole_like is implemented for Fermi-sea quantities (fder = 0) only")
         self.constant_factor = constant_factor
         if self.hole_like and self.fder == 0:
             self.constant_factor *= -1
@@ -120,6 +120,10 @@ class StaticCalculator(Calculator):
                         external_terms=int(bool(self.kwargs_formula.get("external_terms", True))),
                         Ef_first=float(self.Efermi[0]), Ef_last=float(self.Efermi[-1]), dEF=float(self.dEF),
                         degen_thresh=float(self.degen_thresh), factor=float(factor))
+        if self.tetra:   # read by the tetrahedron method only (grid/tetrahedron.py:246-266)
+            spec.tetra_flags = (1 if self.hole_like else 0) | (2 if self.Emin != -np.inf else 0) | (4 if self.Emax != np.inf else 0)
+            spec.tetra_Emin = float(self.Emin) if self.Emin != -np.inf else 0.
+            spec.tetra_Emax = float(self.Emax) if self.Emax != np.inf else 0.
         if self.select_bands is not None:
             if spec.fder == 0:   # data_K.py:179-180
                 raise NotImplementedError("Selection of bands for Fermi sea is not implemented")
@@ -496,8 +500,6 @@ def adapt(calc):
     name = type(calc).__name__
     if name not in _BY_NAME:
         raise KeyError(f"calculator {name} is not available on the GPU path")
-    if calc.tetra and getattr(calc, "hole_like", False):
-        raise NotImplementedError("tetra=True with hole_like (inverse Fermi sea, der=-1) is not implemented on the GPU path")
     kw = dict(Efermi=np.array(calc.Efermi), tetra=calc.tetra, smoother=calc.smoother, use_factor=calc.use_factor,
               kwargs_formula=calc.kwargs_formula, hole_like=False, k_resolved=calc.k_resolved,
               Emin=getattr(calc, "Emin", -np.inf), Emax=getattr(calc, "Emax", np.inf),
@@ -509,4 +511,8 @@ def adapt(calc):
     new = _BY_NAME[name](**kw)
     if name in fixed:
         new.constant_factor = calc.constant_factor
+    if calc.tetra and getattr(calc, "hole_like", False):   # (its sign is in constant_factor already; the weights need the flag)
+        if new.fder != 0:
+            raise NotImplementedError("tetra=True with hole_like is implemented for Fermi-sea quantities (fder = 0) only")
+        new.hole_like = True
     return new

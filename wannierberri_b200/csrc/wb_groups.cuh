@@ -14,6 +14,10 @@ struct WbWindow {
     // energy over the k-point's cell (centre + 8 corners), [nk][nw]; nullptr = plain rule on the centre energies
     const double* Ebmin;
     const double* Ebmax;
+    // tetrahedron method: hole_like (der = -1: no Fermi-sea group, but the group of the bands ABOVE EFmax, up to Emax_holes),
+    // lower edge of the Fermi-sea group (tetrahedron.py:246-266)
+    int holes;
+    double Emin_sea, Emax_holes;
 };
 
 // For every band n: g1[n], g2[n] = [ib1, ib2) of the kept group (or of the Fermi-sea group) that
@@ -40,14 +44,30 @@ __device__ inline void wb_band_groups_tetra(const double* E, const double* __res
         }
         prev = pos;
     }
-    if (w.sea) {   // get_bands_below_range(eFermi[0], Ebandmax = Emax)
-        int bandmax = 0;
-        for (int n = 0; n < nw; n++)
+    if (w.sea && !w.holes) {   // get_bands_below_range(eFermi[0] | Emin, Ebandmax = Emax)  (tetrahedron.py:246-256)
+        int bandmax = 0, bandmin = 0;
+        for (int n = 0; n < nw; n++) {
             if (emax[n] < w.EFmin) bandmax = n + 1;
+            if (emax[n] < w.Emin_sea) bandmin = n + 1;
+        }
         if (first_kept >= 0) bandmax = min(bandmax, first_kept);
-        if (bandmax > 0) {
-            label[0] = -CUDART_INF;
-            for (int n = 0; n < bandmax; n++) { g1[n] = 0; g2[n] = (short)bandmax; }
+        if (bandmax > bandmin) {
+            label[bandmin] = -CUDART_INF;
+            for (int n = bandmin; n < bandmax; n++) { g1[n] = (short)bandmin; g2[n] = (short)bandmax; }
+        }
+    }
+    if (w.holes) {   // get_bands_above_range(eFermi[-1] | Emax, Ebandmin = Emin)  (tetrahedron.py:258-266)
+        int bandmin = nw, bandmax = nw, last_end = -1;
+        for (int n = nw - 1; n >= 0; n--) {
+            if (emin[n] > w.EFmax) bandmin = n;
+            if (emin[n] > w.Emax_holes) bandmax = n;
+        }
+        for (int n = 0; n < nw; n++)
+            if (g1[n] >= 0) last_end = g2[n];
+        if (last_end >= 0) bandmin = max(bandmin, last_end);
+        if (bandmax > bandmin) {
+            label[bandmin] = -CUDART_INF;
+            for (int n = bandmin; n < bandmax; n++) { g1[n] = (short)bandmin; g2[n] = (short)bandmax; }
         }
     }
 }

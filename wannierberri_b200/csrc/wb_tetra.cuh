@@ -172,19 +172,29 @@ wb_tetra_accumulate_kernel(const double* __restrict__ ev_val, int ev_stride, int
                 return Ecorner[(size_t)c * corner_stride + ik * nw + ib];
             };
             WbTetra T;
-            wb_tetra_setup(Es[ib], corner(0, 0), tri == 0 ? corner(0, 1) : corner(1, 0), corner(1, 1), der, T);
+            const int der_w = (der < 0) ? 0 : der;   // hole_like (der = -1): 1 - occupation (tetrahedron.py:197-198)
+            wb_tetra_setup(Es[ib], corner(0, 0), tri == 0 ? corner(0, 1) : corner(1, 0), corner(1, 1), der_w, T);
             const int lo = wb_ef_lower_bound(Ef0, dEF, nEF, T.e1), hi = wb_ef_lower_bound(Ef0, dEF, nEF, T.e4);
             const double* v = ev_val + (size_t)(ik * nw + a) * ev_stride;
             for (int i = lo; i < hi; i++) {
-                const double w = coef * wb_tetra_weight(T, wb_ef_at(Ef0, dEF, i), der);
+                double w = wb_tetra_weight(T, wb_ef_at(Ef0, dEF, i), der_w);
+                if (der < 0) w = 1. - w;
+                w *= coef;
                 for (int c = 0; c < ncomp; c++) atomicAdd(&hd[(size_t)i * ncomp + c], w * v[c]);
             }
             if (der == 0 && hi < nEF)
                 for (int c = 0; c < ncomp; c++) atomicAdd(&hs[(size_t)hi * ncomp + c], coef * v[c]);
+            if (der < 0 && lo > 0)   // weight one below e1: +X at level 0, -X at level lo of the running sum
+                for (int c = 0; c < ncomp; c++) {
+                    atomicAdd(&hs[c], coef * v[c]);
+                    if (lo < nEF) atomicAdd(&hs[(size_t)lo * ncomp + c], -(coef * v[c]));
+                }
         }
-        // ---- Fermi-sea group: weight one at every Fermi level
-        if (label[0] == -CUDART_INF && threadIdx.x < ncomp)
-            atomicAdd(&hs[threadIdx.x], wk * ev_val[(size_t)(ik * nw) * ev_stride + threadIdx.x]);
+        // ---- Fermi-sea group / hole_like: group above the Fermi axis: weight one at every Fermi level
+        for (int x = threadIdx.x; x < nw * ncomp; x += blockDim.x) {
+            const int n = x / ncomp, cc = x - n * ncomp;
+            if (label[n] == -CUDART_INF) atomicAdd(&hs[cc], wk * ev_val[(size_t)(ik * nw + n) * ev_stride + cc]);
+        }
     }
     if (use_smem) {
         __syncthreads();

@@ -328,6 +328,9 @@ static WbWindow make_window(const wbgpu_scan_spec& s) {
     w.degen_Kramers = s.degen_Kramers;
     w.sea = (s.fder == 0);
     w.Ebmin = w.Ebmax = nullptr;
+    w.holes = 0;
+    w.Emin_sea = -INFINITY;
+    w.Emax_holes = INFINITY;
     return w;
 }
 
@@ -814,14 +817,20 @@ struct EvGroup {
 
 static bool same_window(const WbWindow& a, const WbWindow& b) {
     return a.EFmin == b.EFmin && a.EFmax == b.EFmax && a.dEF == b.dEF && a.degen_thresh == b.degen_thresh &&
-           a.degen_Kramers == b.degen_Kramers && a.sea == b.sea && a.nEFx == b.nEFx && a.Ebmin == b.Ebmin;
+           a.degen_Kramers == b.degen_Kramers && a.sea == b.sea && a.nEFx == b.nEFx && a.Ebmin == b.Ebmin &&
+           a.holes == b.holes && a.Emin_sea == b.Emin_sea && a.Emax_holes == b.Emax_holes;
 }
 
-static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec) {
+static std::vector<EvGroup> make_groups(const wbgpu_scan_spec* specs, int nspec, bool tetra = false) {
     std::vector<EvGroup> groups;
     for (int i = 0; i < nspec; i++) {
         const wbgpu_scan_spec& s = specs[i];
         WbWindow w = make_window(s);
+        if (tetra) {   // hole_like / Emin / Emax act in the tetrahedron method only (data_K.py:172-185)
+            w.holes = s.tetra_flags & 1;
+            if (s.tetra_flags & 2) w.Emin_sea = s.tetra_Emin;
+            if (s.tetra_flags & 4) w.Emax_holes = s.tetra_Emax;
+        }
         bool ident = (s.formula == WBGPU_IDENTITY);
         int found = -1;
         for (size_t g = 0; g < groups.size() && !formula_solo(s.formula); g++) {
@@ -1418,6 +1427,8 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
     for (int i = 0; i < nspec; i++) {
         if (check_spec(c, specs[i])) return 1;
         if (specs[i].use_select) return set_err("scan: select_bands with the tetrahedron method is not implemented");
+        if ((specs[i].tetra_flags & 1) && specs[i].fder != 0)
+            return set_err("scan: hole_like with the tetrahedron method is not implemented for derivatives of the occupation (fder = %d)", specs[i].fder);
         size_t sz = (size_t)specs[i].nEF * formula_ncomp(specs[i].formula);
         hoff[i + 1] = hoff[i] + 2 * sz;   // direct | suffix
         nout += sz;
@@ -1472,7 +1483,7 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
 
     // event groups with the tetrahedron window: [Efermi[0], Efermi[-1]], no widening (tetrahedron.py:232-241)
     std::vector<wbgpu_scan_spec> tsp(specs, specs + nspec);
-    std::vector<EvGroup> groups = make_groups(tsp.data(), nspec);
+    std::vector<EvGroup> groups = make_groups(tsp.data(), nspec, true);
     for (EvGroup& G : groups) {
         const wbgpu_scan_spec& s0 = specs[G.specs[0]];
         G.win.EFmin = s0.Ef_first;
@@ -1530,7 +1541,7 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
                 const long nblk = std::min(nk, (long)sms * 2);
                 wb_tetra_accumulate_kernel<<<(unsigned)nblk, 128, smem, c->stream>>>(
                     c->d_evval + G.ev.off[s.formula], G.ev.NC, nw, nk, c->nk_block, c->d_E, c->d_Ec, (long)(nkl * nw), G.win, d_w + b0,
-                    ncomp, s.fder, s.nEF, s.Ef_first, s.dEF, c->d_hist + hoff[i], use_smem);
+                    ncomp, (s.tetra_flags & 1) ? -1 : s.fder, s.nEF, s.Ef_first, s.dEF, c->d_hist + hoff[i], use_smem);
                 c->launches++;
             }
             stage_end(c);
@@ -1610,6 +1621,7 @@ static int kubo_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, const
     win.EFmin = -INFINITY; win.EFmax = INFINITY; win.dEF = 1.; win.degen_thresh = spec->degen_thresh;
     win.degen_Kramers = spec->degen_Kramers; win.sea = 0; win.nEFx = nEF;
     win.Ebmin = win.Ebmax = nullptr;
+    win.holes = 0; win.Emin_sea = -INFINITY; win.Emax_holes = INFINITY;
 
     // device copies of the axes: Efermi | omega; accumulator D[nomega][nEF][NC] + output
     if (ensure(&c->d_axes, &c->axes_cap, sizeof(double) * ((size_t)nEF + nom))) return 1;
