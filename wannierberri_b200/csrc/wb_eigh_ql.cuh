@@ -197,12 +197,14 @@ wb_tridiag2_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk, d
         cplx tau = cmake(0., 0.);
         double beta = alpha.x;
         cplx v = cmake(0., 0.);
-        if (xnorm2 != 0. || alpha.y != 0.) {  // zlarfg
-            beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xnorm2), alpha.x);
-            const double binv = 1. / beta;
+        if (xnorm2 != 0. || alpha.y != 0.) {  // zlarfg (rsqrt / reciprocal instead of sqrt and two divisions)
+            const double n2 = alpha.x * alpha.x + alpha.y * alpha.y + xnorm2;
+            const double rinv = rsqrt(n2);
+            beta = -copysign(n2 * rinv, alpha.x);
+            const double binv = -copysign(rinv, alpha.x);
             tau = cmake((beta - alpha.x) * binv, -alpha.y * binv);
             cplx den = cmake(alpha.x - beta, alpha.y);
-            double dn = 1. / (den.x * den.x + den.y * den.y);
+            double dn = __drcp_rn(den.x * den.x + den.y * den.y);
             cplx scale = cmake(den.x * dn, -den.y * dn);
             if (row > k + 1) v = cmul(xk, scale);
         }
