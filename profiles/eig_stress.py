@@ -38,3 +38,5 @@ for nw in (4, 8, 12, 18, 24):
     for deg in (False, True):
         s = wb.synthetic_system(nw, rmax=1, seed=nw, matrices=("Ham",), degenerate_pairs=deg)
         case(f"synthetic nw={nw} deg={deg}", s, [6, 6, 6], [0.03, 0.01, 0.2])
+for nw in (6, 12, 18, 24):
+    case(f"PT-symmetric (Kramers) nw={nw}", wb.kramers_system(nw, seed=nw), [8, 8, 8], [0.03, 0.01, 0.2])

@@ -3,7 +3,7 @@
 System_R / run() / calculators interface.  Arithmetic runs in libwbgpu.so (hand-written sm_100a
 CUDA behind a C-ABI, include/wbgpu.h); there is no CPU fallback."""
 from . import calculators  # noqa: F401
-from .system import System_R, SystemSOC, synthetic_system  # noqa: F401
+from .system import System_R, SystemSOC, synthetic_system, kramers_system  # noqa: F401
 from .grid import Grid  # noqa: F401
 from .result import EnergyResult, ResultDict  # noqa: F401
 from .engine import Engine  # noqa: F401

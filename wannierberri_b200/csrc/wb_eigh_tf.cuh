@@ -333,7 +333,19 @@ wb_trideig_kernel(long k0, long nk, const double* __restrict__ din, const double
                     for (int i = 0; i < NW; i++) A[i] *= s2;
                 }
             }
-            if (r < 0 || !(keep >= WB_TF_ACCEPT2) || !(res <= restol)) fail = true;
+            // |gamma_r| / |z| is the residual only as far as the pivots of T - sigma carry no element growth, and the
+            // projection adds |dot| |sigma_p - sigma| per earlier vector: measure |(T - sigma) z| of the vector that is
+            // stored (z normalised; exactly degenerate, coupled spectra -- Kramers pairs -- are where the two differ)
+            double r2 = 0., below = 0.;
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                const double ei = ep[i * 32];
+                double v = fma(dp[i * 32] - sigma, A[i], below);
+                if (i + 1 < NW) v = fma(ei, A[i + 1], v);
+                below = ei * A[i];
+                r2 = fma(v, v, r2);
+            }
+            if (r < 0 || !(keep >= WB_TF_ACCEPT2) || !(res <= restol) || !(r2 <= restol * restol)) fail = true;
             wb_tf_store_vec<NW>(const_cast<double2*>(wb_tf_zvec<NW>(Zout, t, j)), A);
             j++;
             mode = 0; glast = -1.; rlast = -1; best = 0.; rbest = -1; gbest = -1.; ntrial = 0;

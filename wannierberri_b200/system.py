@@ -199,6 +199,34 @@ def flatten_soc(soc):
 _FLAT_SOC = {}
 
 
+def kramers_system(num_wann, rmax=1, seed=20261018, lattice_const=4.0):
+    """Seeded random model with PT symmetry: H(k) = [[A(k), B(k)], [-B(k)^*, A(k)^*]] with A hermitian and B antisymmetric, so
+    every level of every k-point is EXACTLY doubly degenerate although the two halves of the basis are coupled (unlike
+    `synthetic_system(degenerate_pairs=True)`, which is block diagonal) -- the hard case for an eigensolver that builds
+    eigenvectors one eigenvalue at a time."""
+    assert num_wann % 2 == 0
+    nh = num_wann // 2
+    rng = np.random.default_rng(seed)
+    rr = np.arange(-rmax, rmax + 1)
+    iRvec = np.array([[x, y, z] for x in rr for y in rr for z in rr], dtype=int)
+    index = {tuple(R): i for i, R in enumerate(iRvec)}
+    decay = np.exp(-np.linalg.norm(iRvec, axis=1))[:, None, None]
+    A = (rng.standard_normal((len(iRvec), nh, nh)) + 1j * rng.standard_normal((len(iRvec), nh, nh))) * decay
+    B = (rng.standard_normal((len(iRvec), nh, nh)) + 1j * rng.standard_normal((len(iRvec), nh, nh))) * decay
+    B = B - B.swapaxes(1, 2)                                   # antisymmetric for every R
+    minus = np.array([index[tuple(-R)] for R in iRvec])
+    A = 0.5 * (A + A[minus].swapaxes(1, 2).conj())              # A(-R) = A(R)^dagger
+    H = np.zeros((len(iRvec), num_wann, num_wann), dtype=complex)
+    H[:, :nh, :nh] = A
+    H[:, :nh, nh:] = B
+    H[:, nh:, :nh] = -B[minus].conj()
+    H[:, nh:, nh:] = A.swapaxes(1, 2)                          # A(-R)^* = A(R)^T
+    centres = rng.random((nh, 3)) * lattice_const
+    s = System_R(np.eye(3) * lattice_const, iRvec, np.concatenate([centres, centres]))
+    s.set_R_mat("Ham", H)
+    return s
+
+
 def as_system(obj):
     """Accept this package's `System_R` or the reference's (duck typing on the attributes read by
     the path: SURVEY.md section 2, row 9); a SOC system (`SystemSOC`: scalar up / down systems + spin-orbit term) is
