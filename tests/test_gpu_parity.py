@@ -368,6 +368,25 @@ def test_plugin_formula_through_run(wb, fe):
         assert relerr(res.results["ahc"].data, g0["ahc"]) < RTOL
 
 
+def test_second_order_calculators_through_run(wb, fe):
+    """NLDrude_Zeeman_{spin, orb_Omega, orb}, eMChA_FermiSurf, QuantumMetric_FermiSea / _Vel_DQ (Der2Spin / Der2Omega /
+    Der2Morb / emcha_surf / tildeFab(_d)): this package's calculators -- matrices with up
+    to three comma-derivatives from the CUDA kernels, batched block algebra of formula_gpu.py on the device -- through
+    `run()` against the fixture of the UNMODIFIED reference (tests/golden/make_golden_second_order.py): with and without
+    external terms, with wide (multi-band, Kramers-paired) groups, with use_factor=False."""
+    from second_order_calcs import make_calculators
+    g = np.load(os.path.join(GOLDEN, "golden_second_order.npz"))
+    calcs = make_calculators(wb.calculators.static, g["Efermi"])
+    res = wb.run(fe, wb.Grid(fe, NK=g["NK"], NKFFT=g["NKFFT"]), calcs, use_irred_kpt=False, symmetrize=False,
+                 write_files=False)
+    parity = {1: "ident", -1: "odd"}
+    for key in calcs:
+        r = res.results[key]
+        assert r.data.shape == g[key].shape, key
+        assert relerr(r.data, g[key]) < RTOL, (key, relerr(r.data, g[key]))
+        assert r.transformTR == parity[int(g[key + "_TR"])] and r.transformInv == parity[int(g[key + "_Inv"])], key
+
+
 @pytest.mark.parametrize("nw", [4, 6, 8, 10, 12, 14, 16, 20, 22, 24])
 def test_fused_rotation_kernel_sizes(wb, nw):
     """The compile-time-num_wann DMMA rotation + formula kernel (rotate_method 3; every even num_wann <= 24) against the

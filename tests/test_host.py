@@ -436,6 +436,57 @@ def test_reference_calculators_on_datak_host():
         assert np.abs(got - want).max() <= 1e-12 * max(np.abs(want).max(), 1e-300), key
 
 
+def test_second_order_block_algebra_vs_reference(monkeypatch):
+    """formula_gpu.py (full-matrix block algebra with partition masks, batched over the (k-point, band group) pairs of a
+    K-block) against the reference's per-group numpy formulae -- Der2Spin / Der2Omega / Der2Morb with Der3E, Omega,
+    Morb_Hpm (NLDrude_Z_*), emcha_surf, tildeFab / tildeFab_d (quantum metric) -- and this package's calculators of them
+    against the reference's, on the reference's Data_K_R of one Fe K-block.  The tensors live on the CPU here (torch),
+    the product evaluates the same code on the CUDA device (tests/test_gpu_parity.py: through run() vs a fixture)."""
+    wberri = _import_reference()
+    sys.path[:0] = ["/root/reference", os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, "tests", "golden")]
+    try:
+        from make_golden import build_fe
+        from wannierberri.data_K import Data_K_R as RefDataK
+        from wannierberri.calculators import static as rst
+        from wannierberri.formula import covariant as frml
+    finally:
+        del sys.path[:3]
+    import functools
+    from wannierberri_b200 import formula_gpu as fg
+    system = build_fe()
+    grid = wberri.Grid(system, NK=[4, 4, 4], NKFFT=[2, 2, 2])
+    dk = RefDataK(system, dK=np.array([0.125, 0.0, 0.125]), grid=grid)
+    nw = dk.num_wann
+    ref_cls = dict(NLDrude_Z_spin=frml.NLDrude_Z_spin, NLDrude_Z_orb_Omega=frml.NLDrude_Z_orb_Omega,
+                   NLDrude_Z_orb_Hplus=frml.NLDrude_Z_orb_Hplus, emcha_surf=frml.emcha_surf,
+                   QuantumMetric_ab=frml.QuantumMetric_ab, VelDQM=frml.VelDQM)
+    # band sets: single bands, wide Kramers-paired groups, and the Fermi-sea set [0, bandmax)
+    for kw_groups in (dict(degen_thresh=1e-4, sea=False), dict(degen_thresh=0.3, degen_Kramers=True, sea=True)):
+        groups = dk.get_bands_in_range_groups(15., 19., **kw_groups)
+        pairs = [(ik, g) for ik, gs in enumerate(groups) for g in gs][::3]
+        kidx, a, b = (np.array(x) for x in zip(*[(ik, g[0], g[1]) for ik, g in pairs]))
+        for ext in (True, False):
+            for name, cls in ref_cls.items():
+                kw = dict(external_terms=ext)
+                if name in ("QuantumMetric_ab", "VelDQM"):
+                    kw["FF_rotAA"] = True
+                f = cls(dk, **kw)
+                want = np.array([f.trace(ik, np.arange(x, y), np.concatenate((np.arange(0, x), np.arange(y, nw))))
+                                 for ik, x, y in zip(kidx, a, b)])
+                got = fg.batch_traces(name, dk, kidx, a, b, internal=True, external=ext, device="cpu")
+                assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), (name, ext, kw_groups)
+    # the calculators (scan, factors, the Hplus - 2 E_F Omega combination) on the same K-block
+    from second_order_calcs import make_calculators
+    Ef = np.linspace(15., 19., 9)
+    monkeypatch.setattr(fg, "batch_traces", functools.partial(fg.batch_traces, device="cpu"))
+    mine, theirs = make_calculators(wb.calculators.static, Ef), make_calculators(rst, Ef)
+    for key in ("z_spin", "z_orb", "emcha_wide", "qmetric", "qmetric_dip"):
+        want, got = theirs[key](dk).data, mine[key](dk).data
+        assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max(), key
+    with pytest.raises(NotImplementedError):   # FF_R is not transformed on the GPU path
+        wb.calculators.static.QuantumMetric_FermiSea(Efermi=Ef)
+
+
 def test_run_plugin_loop_with_reference_calculators():
     """`run()` with calculators that are NOT scans of the library -- here unmodified objects of the reference
     (NLDrude_Zeeman_spin: second-order formula; a user class) -- loops over the K-blocks itself, calls

@@ -68,7 +68,7 @@ class StaticCalculator(Calculator):
         if Formula is not None:
             self.Formula = Formula
         unknown = set(self.kwargs_formula) - {"internal_terms", "external_terms"} - set(self.extra_kwargs_formula)
-        if unknown and not self.is_plugin:
+        if unknown and (not self.is_plugin or isinstance(self.Formula, str)):
             raise NotImplementedError(f"kwargs_formula {sorted(unknown)} are not implemented on the GPU path")
         if tetra and self.is_plugin:
             raise NotImplementedError("tetra=True with a plug-in Formula class is not implemented")
@@ -160,15 +160,32 @@ class StaticCalculator(Calculator):
         groups of every k-point).  Eigenvalues and Hamiltonian-gauge matrices come from the GPU through `data_K`; the
         formula's own `trace()` is the user's code."""
         from math import ceil
-        formula = self.Formula(data_K, **self.kwargs_formula)
-        shape = (3,) * formula.ndim
         nb = data_K.num_wann
         groups_k = data_K.get_bands_in_range_groups(self.EFmin, self.EFmax, degen_thresh=self.degen_thresh,
                                                     degen_Kramers=self.degen_Kramers, sea=(self.fder == 0),
                                                     Emin=self.Emin, Emax=self.Emax, select_bands=self.select_bands)
+        batched = isinstance(self.Formula, str)   # a formula of formula_gpu.py: all (k-point, group) pairs in one go
+        if batched:
+            from .. import formula_gpu
+            _, rank, (tTR, tInv) = formula_gpu.TRACES[self.Formula]
+            shape = (3,) * rank
+            pairs = [(ik, g) for ik, groups in enumerate(groups_k) for g in groups]
+            vals = formula_gpu.batch_traces(self.Formula, data_K, np.array([p[0] for p in pairs], dtype=int),
+                                            np.array([p[1][0] for p in pairs], dtype=int),
+                                            np.array([p[1][1] for p in pairs], dtype=int),
+                                            internal=bool(self.kwargs_formula.get("internal_terms", True)),
+                                            external=bool(self.kwargs_formula.get("external_terms", True))
+                                            and not getattr(data_K, "force_internal_terms_only", False))
+            pair_value = {p: v for p, v in zip(pairs, vals)}
+        else:
+            formula = self.Formula(data_K, **self.kwargs_formula)
+            shape = (3,) * formula.ndim
+            tTR, tInv = formula.transformTR, formula.transformInv
         steps = np.zeros((self.nEF_extra + 1,) + shape)   # value added from level i on: summed up at the end
         for ik, groups in enumerate(groups_k):
-            if getattr(formula, "additive", True):
+            if batched:
+                values = {g: pair_value[(ik, g)] for g in groups}
+            elif getattr(formula, "additive", True):
                 values = {g: formula.trace(ik, np.arange(g[0], g[1]),
                                            np.concatenate((np.arange(0, g[0]), np.arange(g[1], nb)))) for g in groups}
             else:   # e.g. the orbital moment: trace over [0, edge) at every group edge, a group = difference of its edges
@@ -192,7 +209,7 @@ class StaticCalculator(Calculator):
             tot = (tot[4:] - tot[:-4] - 2 * (tot[3:-1] - tot[1:-3])) / (2 * d ** 3)
         tot = tot / (data_K.cell_volume * data_K.nk)
         tot = tot * (self.constant_factor if self.use_factor else np.sign(self.constant_factor))
-        return EnergyResult(self.Efermi, tot, transformTR=formula.transformTR, transformInv=formula.transformInv,
+        return EnergyResult(self.Efermi, tot, transformTR=tTR, transformInv=tInv,
                             comment=self.comment, save_mode=self.save_mode, smoothers=[self.smoother])
 
 
@@ -485,7 +502,89 @@ class OmegaOmega(StaticCalculator):
         super().__init__(**kwargs)
 
 
-_BY_NAME = {c.__name__: c for c in (DOS, CumDOS, Spin, AHC, Morb, BerryDipole_FermiSurf, GME_orb_FermiSurf,
+# ---- second-order formulae: evaluated K-block by K-block on the GPU-resident Data_K_R by
+# the batched block algebra of formula_gpu.py (torch on the device, matrices with up to three comma-derivatives from the
+# CUDA kernels); `Formula` is the name of the trace there
+
+class eMChA_FermiSurf(StaticCalculator):
+    r"""electrical magnetochiral anisotropy, Fermi-surface term (static.py:560-566; formula covariant.py:868-890)"""
+    extra_kwargs_formula = ()
+
+    def __init__(self, constant_factor=factors.factor_emcha, **kwargs):
+        self.Formula = "emcha_surf"
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+class NLDrude_Zeeman_spin(StaticCalculator):
+    r"""Zeeman (spin) correction of the non-linear Drude conductivity (static.py:569-575; covariant.py:893-899)"""
+
+    def __init__(self, constant_factor=factors.fac_spin_Z * factors.factor_nldrude, **kwargs):
+        self.Formula = "NLDrude_Z_spin"
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+class NLDrude_Zeeman_orb_Omega(StaticCalculator):
+    r"""Berry-curvature part of the orbital Zeeman correction (static.py:578-584; covariant.py:909-914)"""
+
+    def __init__(self, **kwargs):
+        self.Formula = "NLDrude_Z_orb_Omega"
+        self.fder = 1
+        super().__init__(**kwargs)
+
+
+class NLDrude_Zeeman_orb(StaticCalculator):
+    r"""Zeeman (orbital) correction of the non-linear Drude conductivity: Hplus part - 2 E_F x Omega part
+    (static.py:587-603; covariant.py:901-907)"""
+
+    def __init__(self, **kwargs):
+        self.Formula = "NLDrude_Z_orb_Hplus"
+        self.fder = 1
+        super().__init__(**kwargs)
+
+    def __call__(self, data_K):
+        Hplus = super().__call__(data_K)
+        Om = NLDrude_Zeeman_orb_Omega(Efermi=self.Efermi, tetra=self.tetra, smoother=self.smoother, use_factor=False,
+                                      kwargs_formula=self.kwargs_formula)(data_K).mul_array(self.Efermi)
+        final_factor = factors.fac_orb_Z * factors.factor_nldrude
+        if not self.use_factor:
+            final_factor = np.sign(final_factor)
+        return (Hplus - Om * 2.) * final_factor
+
+
+class _QuantumMetric(StaticCalculator):
+    extra_kwargs_formula = ("FF_rotAA",)
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        if self.kwargs_formula.get("external_terms", True) and not self.kwargs_formula.get("FF_rotAA", False):
+            raise NotImplementedError("the external terms of the quantum metric need FF_R, which the GPU path does not "
+                                      "transform: pass kwargs_formula=dict(FF_rotAA=True) or external_terms=False")
+
+
+class QuantumMetric_FermiSea(_QuantumMetric):
+    r"""quantum metric of the occupied states (static.py:663-670; basic.py:19-51, covariant.py:916-922)"""
+
+    def __init__(self, constant_factor=1., **kwargs):
+        self.Formula = "QuantumMetric_ab"
+        self.fder = 0
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+class QuantumMetric_Vel_DQ(_QuantumMetric):
+    r"""quantum-metric dipole with the velocity (static.py:673-680; basic.py:59-95, covariant.py:925-936)"""
+
+    def __init__(self, constant_factor=1., **kwargs):
+        self.Formula = "VelDQM"
+        self.fder = 1
+        super().__init__(constant_factor=constant_factor, **kwargs)
+
+
+_BATCHED = (eMChA_FermiSurf, NLDrude_Zeeman_spin, NLDrude_Zeeman_orb_Omega, NLDrude_Zeeman_orb, QuantumMetric_FermiSea,
+            QuantumMetric_Vel_DQ)
+
+_BY_NAME = {c.__name__: c for c in _BATCHED + (DOS, CumDOS, Spin, AHC, Morb, BerryDipole_FermiSurf, GME_orb_FermiSurf,
                                     GME_spin_FermiSurf, Ohmic_FermiSurf, Ohmic_FermiSea, BerryDipole_FermiSea,
                                     NLAHC_FermiSea, SHC, NLAHC_FermiSurf, GME_spin_FermiSea, Hall_classic_FermiSurf,
                                     Hall_classic_FermiSea, NLDrude_FermiSurf, NLDrude_Fermider2, NLDrude_FermiSea, GME_orb_FermiSea, AHC_Zeeman_spin, AHC_Zeeman_orb,
@@ -505,7 +604,8 @@ def adapt(calc):
               Emin=getattr(calc, "Emin", -np.inf), Emax=getattr(calc, "Emax", np.inf),
               select_bands=calc.select_bands, degen_thresh=calc.degen_thresh, degen_Kramers=calc.degen_Kramers,
               save_mode=calc.save_mode)
-    fixed = ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf", "BerryDipole_FermiSea", "OmegaOmega")   # no constant_factor argument
+    fixed = ("DOS", "CumDOS", "Spin", "BerryDipole_FermiSurf", "BerryDipole_FermiSea", "OmegaOmega", "NLDrude_Zeeman_orb_Omega",
+             "NLDrude_Zeeman_orb")   # no constant_factor argument
     if name not in fixed:
         kw["constant_factor"] = calc.constant_factor  # hole_like sign already folded in by the reference
     new = _BY_NAME[name](**kw)

@@ -21,3 +21,4 @@ from math import pi  # noqa: E402
 factor_shift_current = hbar / elementary_charge * pi * elementary_charge ** 3 / (4 * hbar ** 2)
 factor_injection_current = -pi * elementary_charge ** 3 / (hbar ** 2) * TAU_UNIT
 fac_orb_Z = elementary_charge / 2 / hbar * angstrom ** 2
+factor_emcha = -(elementary_charge ** 4 / hbar ** 3 * angstrom ** 2 * TAU_UNIT ** 2 * elementary_charge / hbar)
