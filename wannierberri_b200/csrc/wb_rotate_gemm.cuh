@@ -14,6 +14,7 @@
 // Warp w owns the 8-row tiles w, w + 4 of every 64-row chunk.
 #pragma once
 #include "wb_common.cuh"
+#include "wb_groups.cuh"
 
 struct WbChanList {
     int n;
@@ -163,132 +164,203 @@ __host__ inline size_t wb_gemm_cg_smem_bytes(int nw) {
     return sizeof(cplx) * ((size_t)nwp * wb_gemm_cg_ldp<NTL, KC, CG>() + 64 * (KC + 4) + (size_t)KC * (8 * NTL + 2));
 }
 
+// Column window (TRIM): the formula stage of wb_events_xbar_kernel reads a rotated matrix only in ROWS and COLUMNS of
+// the bands that belong to a band group of the k-point (X_{nl}, X_{ln}, X_{nn'} with n, n' in a group) -- a "cross" of the
+// matrix; for Fermi-surface quantities that is 8-12 of the 24 bands of Te.  With `colwin[ik] = [c0, c1)` (the range of
+// those bands, wb_band_window_kernel) the CTA multiplies by the columns c0 .. c1-1 of U only (NTA <= NTL column tiles,
+// compile-time variants of the body), writes the columns of the result and, for a hermitian channel, their mirror
+// images as the rows; everything outside the cross is left untouched and never read.  Non-hermitian channels (B; C
+// inside a group) are read by columns only.
+template <int NTL, int KC, int CG, int NTA>
+__device__ __forceinline__ void wb_gemm_cg_kpoint(const cplx* __restrict__ r, const cplx* __restrict__ U, const WbChanList& ch,
+                                                  int nw, int ic0, int ncg, int c0, int ncols, bool mirror, cplx* Yp, cplx* As,
+                                                  cplx* Bs, cplx* __restrict__ outk) {
+    constexpr int TN = 8 * NTL, LDP = wb_gemm_cg_ldp<NTL, KC, CG>(), LDA = KC + 4, LDB = TN + 2;
+    const int nwp = (nw + KC - 1) / KC * KC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int n2 = nw * nw, M = ncg * nw;
+    __syncthreads();
+    for (int x = threadIdx.x; x < nwp * LDP; x += 128) Yp[x] = cmake(0., 0.);
+    // ---- step 1: Y_cc = X_cc U[:, c0 ..], rows of the channels stacked
+#pragma unroll 1
+    for (int m0 = 0; m0 < M; m0 += 64) {
+        double are[2][NTA][2], aim[2][NTA][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int t = 0; t < NTA; t++) are[i][t][0] = are[i][t][1] = aim[i][t][0] = aim[i][t][1] = 0.;
+        const bool act0 = m0 + 8 * warp < M, act1 = m0 + 8 * (warp + 4) < M;
+#pragma unroll 1
+        for (int j0 = 0; j0 < nw; j0 += KC) {
+            __syncthreads();
+            for (int x = threadIdx.x; x < 64 * KC; x += 128) {
+                const int c = x % KC, rr = x / KC;
+                const int R = m0 + rr, j = j0 + c;
+                cplx v = cmake(0., 0.);
+                if (R < M && j < nw) {
+                    const int cc = R / nw, m = R - cc * nw;
+                    const int off = ch.off[ic0 + cc];
+                    v = ch.herm[ic0 + cc] ? load_herm(r, off, m, j, nw) : r[off + m * nw + j];
+                }
+                As[rr * LDA + c] = v;
+            }
+            for (int x = threadIdx.x; x < KC * 8 * NTA; x += 128) {
+                const int c = x % (8 * NTA), rr = x / (8 * NTA);
+                const int j = j0 + rr;
+                Bs[rr * LDB + c] = (j < nw && c0 + c < nw) ? U[j * nw + c0 + c] : cmake(0., 0.);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < KC; kk += 4) {
+                cplx b[NTA];
+#pragma unroll
+                for (int t = 0; t < NTA; t++) b[t] = Bs[(kk + q) * LDB + 8 * t + g];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    if (i == 0 ? act0 : act1) {
+                        const cplx a = As[(8 * (warp + 4 * i) + g) * LDA + kk + q];
+#pragma unroll
+                        for (int t = 0; t < NTA; t++) {
+                            wb_dmma_acc(are[i][t][0], are[i][t][1], a.x, b[t].x);
+                            wb_dmma_acc(are[i][t][0], are[i][t][1], -a.y, b[t].y);
+                            wb_dmma_acc(aim[i][t][0], aim[i][t][1], a.x, b[t].y);
+                            wb_dmma_acc(aim[i][t][0], aim[i][t][1], a.y, b[t].x);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int R = m0 + 8 * (warp + 4 * i) + g;
+            if (R < M) {
+                const int cc = R / nw, m = R - cc * nw;
+                cplx* yrow = Yp + (size_t)m * LDP + cc * TN;
+#pragma unroll
+                for (int t = 0; t < NTA; t++) {
+                    yrow[8 * t + 2 * q] = cmake(are[i][t][0], aim[i][t][0]);
+                    yrow[8 * t + 2 * q + 1] = cmake(are[i][t][1], aim[i][t][1]);
+                }
+            }
+        }
+    }
+    // ---- step 2: C_cc = U^dagger Y_cc, the Y panels stacked along N; the nw <= 32 rows n are one 8-row tile per warp
+    {
+        double are[NTA * CG][2], aim[NTA * CG][2];
+#pragma unroll
+        for (int t = 0; t < NTA * CG; t++) are[t][0] = are[t][1] = aim[t][0] = aim[t][1] = 0.;
+        const bool act = 8 * warp < nw;
+#pragma unroll 1
+        for (int j0 = 0; j0 < nw; j0 += KC) {
+            __syncthreads();   // (first pass: Y complete)
+            for (int x = threadIdx.x; x < 32 * KC; x += 128) {
+                const int rr = x % 32, c = x / 32;
+                const int i = j0 + c;
+                As[rr * LDA + c] = (rr < nw && i < nw) ? cconj(U[i * nw + rr]) : cmake(0., 0.);
+            }
+            __syncthreads();
+            const cplx* Bsrc = Yp + (size_t)j0 * LDP;
+            if (act) {
+#pragma unroll
+                for (int kk = 0; kk < KC; kk += 4) {
+                    const cplx a = As[(8 * warp + g) * LDA + kk + q];
+#pragma unroll
+                    for (int t = 0; t < NTA * CG; t++) {
+                        const cplx bt = Bsrc[(kk + q) * LDP + (t / NTA) * TN + 8 * (t % NTA) + g];
+                        wb_dmma_acc(are[t][0], are[t][1], a.x, bt.x);
+                        wb_dmma_acc(are[t][0], are[t][1], -a.y, bt.y);
+                        wb_dmma_acc(aim[t][0], aim[t][1], a.x, bt.y);
+                        wb_dmma_acc(aim[t][0], aim[t][1], a.y, bt.x);
+                    }
+                }
+            }
+        }
+        const int n = 8 * warp + g;
+        if (n < nw) {
+            const bool n_outside = (n < c0) || (n >= c0 + ncols);
+#pragma unroll
+            for (int t = 0; t < NTA * CG; t++) {
+                const int cc = t / NTA, l = 8 * (t - cc * NTA) + 2 * q;
+                if (cc < ncg) {
+                    cplx* outm = outk + (size_t)(ic0 + cc) * n2;
+                    const bool mir = mirror && n_outside && ch.herm[ic0 + cc];
+                    const cplx v0 = cmake(are[t][0], aim[t][0]), v1 = cmake(are[t][1], aim[t][1]);
+                    if (l < ncols) {
+                        outm[(size_t)n * nw + c0 + l] = v0;
+                        if (mir) outm[(size_t)(c0 + l) * nw + n] = cconj(v0);
+                    }
+                    if (l + 1 < ncols) {
+                        outm[(size_t)n * nw + c0 + l + 1] = v1;
+                        if (mir) outm[(size_t)(c0 + l + 1) * nw + n] = cconj(v1);
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int NTL, int KC, int CG>
 __global__ void __launch_bounds__(128)
 wb_rotate_gemm_cg_kernel(const cplx* __restrict__ rec, long recE, WbChanList ch, int nw, long nk,
-                         const cplx* __restrict__ Uall, cplx* __restrict__ xbar) {
-    constexpr int TN = 8 * NTL, LDP = wb_gemm_cg_ldp<NTL, KC, CG>(), LDA = KC + 4, LDB = TN + 2;
+                         const cplx* __restrict__ Uall, cplx* __restrict__ xbar, const int2* __restrict__ colwin) {
+    constexpr int LDP = wb_gemm_cg_ldp<NTL, KC, CG>(), LDA = KC + 4;
     extern __shared__ __align__(16) cplx smem_rc[];
     const int nwp = (nw + KC - 1) / KC * KC;
     cplx* Yp = smem_rc;                     // [nwp][CG * TN (+2)]: Y of channel cc in columns cc TN ..
     cplx* As = Yp + (size_t)nwp * LDP;      // [64][LDA]
     cplx* Bs = As + 64 * LDA;               // [KC][LDB]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
     const int ic0 = blockIdx.y * CG;
     const int ncg = (ch.n - ic0 < CG) ? (ch.n - ic0) : CG;   // channels of this CTA
-    const int n2 = nw * nw, M = ncg * nw;
+    const int n2 = nw * nw;
     for (long ik = blockIdx.z; ik < nk; ik += gridDim.z) {
         const cplx* r = rec + ik * recE;
         const cplx* U = Uall + ik * n2;
-        __syncthreads();
-        for (int x = threadIdx.x; x < nwp * LDP; x += 128) Yp[x] = cmake(0., 0.);
-        // ---- step 1: Y_cc = X_cc U, rows of the channels stacked
-#pragma unroll 1
-        for (int m0 = 0; m0 < M; m0 += 64) {
-            double are[2][NTL][2], aim[2][NTL][2];
-#pragma unroll
-            for (int i = 0; i < 2; i++)
-#pragma unroll
-                for (int t = 0; t < NTL; t++) are[i][t][0] = are[i][t][1] = aim[i][t][0] = aim[i][t][1] = 0.;
-            const bool act0 = m0 + 8 * warp < M, act1 = m0 + 8 * (warp + 4) < M;
-#pragma unroll 1
-            for (int j0 = 0; j0 < nw; j0 += KC) {
-                __syncthreads();
-                for (int x = threadIdx.x; x < 64 * KC; x += 128) {
-                    const int c = x % KC, rr = x / KC;
-                    const int R = m0 + rr, j = j0 + c;
-                    cplx v = cmake(0., 0.);
-                    if (R < M && j < nw) {
-                        const int cc = R / nw, m = R - cc * nw;
-                        const int off = ch.off[ic0 + cc];
-                        v = ch.herm[ic0 + cc] ? load_herm(r, off, m, j, nw) : r[off + m * nw + j];
-                    }
-                    As[rr * LDA + c] = v;
-                }
-                for (int x = threadIdx.x; x < KC * TN; x += 128) {
-                    const int c = x % TN, rr = x / TN;
-                    const int j = j0 + rr;
-                    Bs[rr * LDB + c] = (j < nw && c < nw) ? U[j * nw + c] : cmake(0., 0.);
-                }
-                __syncthreads();
-#pragma unroll
-                for (int kk = 0; kk < KC; kk += 4) {
-                    cplx b[NTL];
-#pragma unroll
-                    for (int t = 0; t < NTL; t++) b[t] = Bs[(kk + q) * LDB + 8 * t + g];
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        if (i == 0 ? act0 : act1) {
-                            const cplx a = As[(8 * (warp + 4 * i) + g) * LDA + kk + q];
-#pragma unroll
-                            for (int t = 0; t < NTL; t++) {
-                                wb_dmma_acc(are[i][t][0], are[i][t][1], a.x, b[t].x);
-                                wb_dmma_acc(are[i][t][0], are[i][t][1], -a.y, b[t].y);
-                                wb_dmma_acc(aim[i][t][0], aim[i][t][1], a.x, b[t].y);
-                                wb_dmma_acc(aim[i][t][0], aim[i][t][1], a.y, b[t].x);
-                            }
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const int R = m0 + 8 * (warp + 4 * i) + g;
-                if (R < M) {
-                    const int cc = R / nw, m = R - cc * nw;
-                    cplx* yrow = Yp + (size_t)m * LDP + cc * TN;
-#pragma unroll
-                    for (int t = 0; t < NTL; t++) {
-                        yrow[8 * t + 2 * q] = cmake(are[i][t][0], aim[i][t][0]);
-                        yrow[8 * t + 2 * q + 1] = cmake(are[i][t][1], aim[i][t][1]);
-                    }
-                }
-            }
+        cplx* outk = xbar + (size_t)ik * ch.n * n2;
+        int c0 = 0, ncols = nw;
+        if (colwin) {
+            const int2 w = colwin[ik];
+            c0 = w.x;
+            ncols = w.y - w.x;
+            if (ncols <= 0) continue;   // no band group at this k-point: nothing is read (uniform over the CTA)
         }
-        // ---- step 2: C_cc = U^dagger Y_cc, the Y panels stacked along N; the nw <= 32 rows n are one 8-row tile per warp
-        {
-            double are[NTL * CG][2], aim[NTL * CG][2];
+        const int nta = (ncols + 7) >> 3;
+        const bool mirror = colwin != nullptr;
+        if (nta >= NTL) wb_gemm_cg_kpoint<NTL, KC, CG, NTL>(r, U, ch, nw, ic0, ncg, c0, ncols, mirror, Yp, As, Bs, outk);
+        else if (nta == 1) wb_gemm_cg_kpoint<NTL, KC, CG, 1>(r, U, ch, nw, ic0, ncg, c0, ncols, mirror, Yp, As, Bs, outk);
+        else if (nta == 2) wb_gemm_cg_kpoint<NTL, KC, CG, (NTL > 2 ? 2 : NTL)>(r, U, ch, nw, ic0, ncg, c0, ncols, mirror, Yp, As, Bs, outk);
+        else wb_gemm_cg_kpoint<NTL, KC, CG, (NTL > 3 ? 3 : NTL)>(r, U, ch, nw, ic0, ncg, c0, ncols, mirror, Yp, As, Bs, outk);
+    }
+}
+
+// [c0, c1) of wb_rotate_gemm_cg_kernel's column window: the range of the bands of k-point ik that belong to a band group
+// (the groups of the formula stage: same functions, same window).  One warp per k-point.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+wb_band_window_kernel(const double* __restrict__ Eall, int nw, long nk, WbWindow win, int2* __restrict__ colwin) {
+    extern __shared__ __align__(16) double smem_w[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* Es = smem_w + (size_t)warp * (2 * nw + (nw + 3) / 4 * 2);
+    double* label = Es + nw;
+    short* g1 = (short*)(label + nw);
+    short* g2 = g1 + nw;
+    for (long ik = (long)blockIdx.x * WARPS + warp; ik < nk; ik += (long)gridDim.x * WARPS) {
+        __syncwarp();
+        for (int x = lane; x < nw; x += 32) Es[x] = Eall[ik * nw + x];
+        __syncwarp();
+        if (win.Ebmin) {
+            if (lane == 0) wb_band_groups_tetra(Es, win.Ebmin + ik * nw, win.Ebmax + ik * nw, nw, win, g1, g2, label);
+        } else if (nw <= 32) wb_band_groups_warp(Es, nw, win, g1, g2, label, lane);
+        else if (lane == 0) wb_band_groups(Es, nw, win, g1, g2, label);
+        __syncwarp();
+        int lo = nw, hi = 0;
+        for (int m = lane; m < nw; m += 32)
+            if (g1[m] >= 0) { lo = min(lo, m); hi = max(hi, m + 1); }
 #pragma unroll
-            for (int t = 0; t < NTL * CG; t++) are[t][0] = are[t][1] = aim[t][0] = aim[t][1] = 0.;
-            const bool act = 8 * warp < nw;
-#pragma unroll 1
-            for (int j0 = 0; j0 < nw; j0 += KC) {
-                __syncthreads();   // (first pass: Y complete)
-                for (int x = threadIdx.x; x < 32 * KC; x += 128) {
-                    const int rr = x % 32, c = x / 32;
-                    const int i = j0 + c;
-                    As[rr * LDA + c] = (rr < nw && i < nw) ? cconj(U[i * nw + rr]) : cmake(0., 0.);
-                }
-                __syncthreads();
-                const cplx* Bsrc = Yp + (size_t)j0 * LDP;
-                if (act) {
-#pragma unroll
-                    for (int kk = 0; kk < KC; kk += 4) {
-                        const cplx a = As[(8 * warp + g) * LDA + kk + q];
-#pragma unroll
-                        for (int t = 0; t < NTL * CG; t++) {
-                            const cplx bt = Bsrc[(kk + q) * LDP + 8 * t + g];
-                            wb_dmma_acc(are[t][0], are[t][1], a.x, bt.x);
-                            wb_dmma_acc(are[t][0], are[t][1], -a.y, bt.y);
-                            wb_dmma_acc(aim[t][0], aim[t][1], a.x, bt.y);
-                            wb_dmma_acc(aim[t][0], aim[t][1], a.y, bt.x);
-                        }
-                    }
-                }
-            }
-            const int n = 8 * warp + g;
-            if (n < nw) {
-#pragma unroll
-                for (int t = 0; t < NTL * CG; t++) {
-                    const int cc = t / NTL, l = 8 * (t - cc * NTL) + 2 * q;
-                    if (cc < ncg) {
-                        cplx* out = xbar + ((size_t)ik * ch.n + ic0 + cc) * n2 + (size_t)n * nw;
-                        if (l < nw) out[l] = cmake(are[t][0], aim[t][0]);
-                        if (l + 1 < nw) out[l + 1] = cmake(are[t][1], aim[t][1]);
-                    }
-                }
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
+        if (lane == 0) colwin[ik] = make_int2(lo, hi);
     }
 }
 

@@ -84,6 +84,8 @@ struct wbgpu_ctx {
     size_t xbar_cap = 0;
     double* d_mx = nullptr;
     size_t mx_cap = 0;
+    double* d_colwin = nullptr;   // int2 per k-point: band range of the band groups (column window of the GEMM rotation)
+    size_t colwin_cap = 0;
     // Kubo path: entry lists of a sub-batch, global accumulator, axes
     double* d_kent = nullptr;
     size_t kent_cap = 0;
@@ -225,7 +227,7 @@ extern "C" int wbgpu_destroy(wbgpu_ctx* c) {
     free_plan(c);
     cudaFree(c->d_iRvec); cudaFree(c->d_T); cudaFree(c->d_sweeps);
     for (int k = 0; k < WBGPU_NKEYS; k++) cudaFree(c->d_XR[k]);
-    cudaFree(c->d_xbar); cudaFree(c->d_mx); cudaFree(c->d_kent); cudaFree(c->d_kacc); cudaFree(c->d_shcJ); cudaFree(c->d_Ec);
+    cudaFree(c->d_xbar); cudaFree(c->d_mx); cudaFree(c->d_colwin); cudaFree(c->d_kent); cudaFree(c->d_kacc); cudaFree(c->d_shcJ); cudaFree(c->d_Ec);
     cudaFree(c->d_hist); cudaFree(c->d_cum); cudaFree(c->d_dK); cudaFree(c->d_weight); cudaFree(c->d_out); cudaFree(c->d_axes);
     delete c;
     return 0;
@@ -892,30 +894,31 @@ static int launch_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n) {
 }
 
 template <int NTL, int KC, int CG>
-static int launch_gemm_cg(wbgpu_ctx* c, const WbChanList& ch, long k0, long n) {
+static int launch_gemm_cg(wbgpu_ctx* c, const WbChanList& ch, long k0, long n, const int2* colwin) {
     const int nw = c->nw;
     size_t smem = wb_gemm_cg_smem_bytes<NTL, KC, CG>(nw);
     if ((int)smem > c->smem_optin) return set_err("rotate(gemm): num_wann=%d needs %zu B shared memory", nw, smem);
     CK(cudaFuncSetAttribute(wb_rotate_gemm_cg_kernel<NTL, KC, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(1, (unsigned)((ch.n + CG - 1) / CG), (unsigned)std::min(n, 16384L));
     wb_rotate_gemm_cg_kernel<NTL, KC, CG><<<grid, 128, smem, c->stream>>>(c->d_X + (size_t)k0 * c->L.E, (long)c->L.E, ch, nw, n,
-                                                                        c->d_U + (size_t)k0 * nw * nw, (cplx*)c->d_xbar);
+                                                                        c->d_U + (size_t)k0 * nw * nw, (cplx*)c->d_xbar, colwin);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
-// U^dagger X U of the listed channels for k-points [k0, k0 + n) -> c->d_xbar[n][ch.n][nw][nw]
-static int rotate_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n) {
+// U^dagger X U of the listed channels for k-points [k0, k0 + n) -> c->d_xbar[n][ch.n][nw][nw]; with `colwin` (per k-point
+// column range, nw <= 32) only the rows and columns of that range are formed
+static int rotate_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n, const int2* colwin = nullptr) {
     const int nw = c->nw;
     if (c->gemm_stack) {   // several channels per CTA for small matrices (option gemm_stack, default on)
         // (NTL, KC, CG) by size; measured per 128k k-points: Te (24 WF, 18 channels) 33.6 -> 26.5 ms with (3, 8, 2) against
         // one channel per CTA -- (3, 24, 2) is slower, 3 CTAs per SM; Fe (18 WF, 15 channels) 33.7 -> 25.0 ms with (3, 20, 3)
-        if (nw <= 8) return launch_gemm_cg<1, 8, 4>(c, ch, k0, n);
-        if (nw <= 16) return launch_gemm_cg<2, 8, 4>(c, ch, k0, n);
-        if (nw <= 20) return launch_gemm_cg<3, 20, 3>(c, ch, k0, n);
-        if (nw <= 24) return launch_gemm_cg<3, 8, 2>(c, ch, k0, n);
-        if (nw <= 32) return launch_gemm_cg<4, 16, 2>(c, ch, k0, n);
+        if (nw <= 8) return launch_gemm_cg<1, 8, 4>(c, ch, k0, n, colwin);
+        if (nw <= 16) return launch_gemm_cg<2, 8, 4>(c, ch, k0, n, colwin);
+        if (nw <= 20) return launch_gemm_cg<3, 20, 3>(c, ch, k0, n, colwin);
+        if (nw <= 24) return launch_gemm_cg<3, 8, 2>(c, ch, k0, n, colwin);
+        if (nw <= 32) return launch_gemm_cg<4, 16, 2>(c, ch, k0, n, colwin);
     }
     if (nw <= 8) return launch_gemm<1, 8>(c, ch, k0, n);
     if (nw <= 16) return launch_gemm<2, 8>(c, ch, k0, n);
@@ -954,12 +957,24 @@ static int run_events_xbar(wbgpu_ctx* c, const EvGroup& G, long nk) {
     if (ensure(&c->d_mx, &c->mx_cap, sizeof(double) * (size_t)nblk_max * 3 * nw * nw)) return 1;
     size_t smem = wb_xbar_events_smem_bytes(nw);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(wb_events_xbar_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the formula stage reads rows / columns of the bands of a band group only (wb_rotate_gemm.cuh, TRIM); not so the
+    // non-additive Morb evaluation (all pairs), nor a non-hermitian d_a H (its rows are not the mirror of its columns)
+    const bool trim = c->rotate_trim && c->gemm_stack && nw <= 32 && !((G.ev.mask >> 2) & 1) && (L.dH_herm || !need.V);
+    if (trim && ensure(&c->d_colwin, &c->colwin_cap, sizeof(int2) * (size_t)chunk)) return 1;
     for (long k0 = 0; k0 < nk; k0 += chunk) {
         long n = std::min(chunk, nk - k0);
-        if (rotate_gemm(c, ch, k0, n)) return 1;
-        long nblk = std::min(n, nblk_max);
         WbWindow wloc = G.win;
         if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
+        if (trim) {
+            constexpr int WW = 4;
+            const size_t smw = sizeof(double) * WW * (2 * (size_t)nw + (nw + 3) / 4 * 2);
+            wb_band_window_kernel<WW><<<(unsigned)std::min((n + WW - 1) / WW, 148L * 16), WW * 32, smw, c->stream>>>(
+                c->d_E + k0 * nw, nw, n, wloc, (int2*)c->d_colwin);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
+        if (rotate_gemm(c, ch, k0, n, trim ? (const int2*)c->d_colwin : nullptr)) return 1;
+        long nblk = std::min(n, nblk_max);
         wb_events_xbar_kernel<NT><<<(unsigned)nblk, NT, smem, c->stream>>>((const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, G.ev,
                                                                        c->d_mx, c->d_evlabel + k0 * nw,
                                                                        c->d_evval + (size_t)k0 * nw * G.ev.NC);
