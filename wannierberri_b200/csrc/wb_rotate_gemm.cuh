@@ -368,7 +368,7 @@ wb_band_window_kernel(const double* __restrict__ Eall, int nw, long nk, WbWindow
 // xbar[k][nch][nw][nw]; the channel triples are ordered V | A | B | O | C | S (those present) and are read in place
 // (L2): staging them in shared memory was measured and does not pay, the kernel is bound by its sums, not by latency.
 template <int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 8)
 wb_events_xbar_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall, WbWindow win,
                       WbEventLayout ev, double* __restrict__ mx_scratch, double* __restrict__ ev_label,
                       double* __restrict__ ev_val) {
