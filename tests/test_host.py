@@ -527,8 +527,10 @@ def test_run_plugin_loop_with_reference_calculators():
     for sym in (False, True):
         want = wberri.run(ref_system, grid=ref_grid, calculators=calcs, adpt_num_iter=0, use_irred_kpt=sym, symmetrize=sym,
                           parallel=False, fout_name=os.path.join("/tmp", "plugloop"), print_progress_step_time=1e9)
-        # `ahc` has the name of a library scan: hand it over as a plain callable so that it takes the plug-in loop too
-        mine = dict(calcs, ahc=(lambda c: (lambda data_K: c(data_K)))(calcs["ahc"]))
+        # `ahc` and `z_spin` have the names of calculators of this package (which would replace them by its own: a scan of
+        # the CUDA kernels / the batched device algebra): hand them over as plain callables so that they take the plug-in loop
+        wrap = lambda c: (lambda data_K: c(data_K))   # noqa: E731
+        mine = dict(calcs, ahc=wrap(calcs["ahc"]), z_spin=wrap(calcs["z_spin"]))
         got = wb.run(fe, wb.Grid(fe, NK=[4, 4, 4], NKFFT=[2, 2, 2]), mine, use_irred_kpt=sym, symmetrize=sym,
                      data_k_class=Host, write_files=False, parallel=False)
         for key in calcs:
