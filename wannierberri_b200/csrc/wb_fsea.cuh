@@ -34,6 +34,28 @@ __device__ __forceinline__ void wb_fsea_groups(const double* __restrict__ Eall, 
     __syncthreads();
 }
 
+// The velocity matrices V_a and D_a = -V_a / (E_p - E_q) of a k-point are read O(nw) times per element by the generalised
+// derivatives below; from global memory (L2) the kernels spent 65 % of their time waiting for those loads (ncu,
+// profiles/r2/fsea_kernels.txt).  When the launch reserves 2 x 3 x (nw^2 + 1) complex of dynamic shared memory behind
+// the arrays of wb_fsea_smem_bytes (`stage` != 0), both are staged there once per k-point; the component stride nw^2 + 1
+// keeps the three Cartesian components in different banks.
+__host__ __device__ inline size_t wb_fsea_stage_offset(int nw, int ncomp) {   // in bytes, 16-byte aligned
+    return (sizeof(double) * (2 * (size_t)nw + (size_t)nw * nw + (size_t)nw * ncomp) + 2 * nw * sizeof(short) + 64 + 15) / 16 * 16;
+}
+__host__ inline size_t wb_fsea_stage_bytes(int nw) { return sizeof(cplx) * 6 * ((size_t)nw * nw + 1); }
+// (the kernels are templated on STAGE so that the staged accesses compile to shared-memory loads, not generic ones)
+template <int NT>
+__device__ __forceinline__ void wb_fsea_stage(const cplx* __restrict__ Vg, const double* inv, int nw, cplx* Vs, cplx* Ds) {
+    const int n2 = nw * nw;
+    for (int x = threadIdx.x; x < 3 * n2; x += NT) {
+        const int a = x / n2, e = x - a * n2;
+        const cplx v = Vg[x];
+        Vs[a * (n2 + 1) + e] = v;
+        Ds[a * (n2 + 1) + e] = cscale(-inv[e], v);
+    }
+    __syncthreads();
+}
+
 // trace_G[a][b][s] = sum_{m in G} sum_{l notin G} -2 Im( J_ml^{as} / (E_m - E_l) * (D_lm^b - i A_lm^b) )
 template <int NT>
 __global__ void __launch_bounds__(NT)
@@ -91,7 +113,7 @@ wb_spinomega_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long 
 
 __host__ __device__ inline size_t wb_deromega_scratch_elems(int nw) { return (size_t)36 * nw * nw; }   // complex elements per CTA
 
-template <int NT>
+template <int NT, bool STAGE>
 __global__ void __launch_bounds__(NT)
 wb_deromega_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall,
                           WbWindow win, WbDerOmegaChans C, int internal, int external, cplx* __restrict__ scratch,
@@ -114,13 +136,17 @@ wb_deromega_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long n
         wb_fsea_groups<NT>(Eall, ik, nw, win, Es, label, inv, g1, g2);
         const cplx* X = xbar + (size_t)ik * nch * n2;
         const cplx* V = X + (size_t)C.iV * n2;
+        cplx* const Vs = (cplx*)((char*)smem_f + wb_fsea_stage_offset(nw, 9));   // [3][n2 + 1], then D likewise (STAGE)
+        cplx* const Ds = Vs + 3 * (n2 + 1);
+        if (STAGE) wb_fsea_stage<NT>(V, inv, nw, Vs, Ds);
+        auto Vel = [&](int a, int e) { return STAGE ? Vs[a * (n2 + 1) + e] : V[(size_t)a * n2 + e]; };
         const cplx* A = X + (size_t)C.iA * n2;
         const cplx* O = X + (size_t)C.iO * n2;
         const cplx* W = X + (size_t)C.iW * n2;
         const cplx* dAc = X + (size_t)C.idA * n2;
         const cplx* dOc = X + (size_t)C.idO * n2;
         auto Dm = [&](int a, int p, int q) {   // D_pq,a = -V_pq,a / (E_p - E_q)
-            return cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]);
+            return STAGE ? Ds[a * (n2 + 1) + p * nw + q] : cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]);
         };
         for (int x = threadIdx.x; x < nw; x += NT) ev_label[ik * nw + x] = label[x];
         for (int ga = 0; ga < nw; ga++) {
@@ -131,60 +157,93 @@ wb_deromega_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long n
             //                                              - sum_{q in cols} (D_rq^b V_qc^d + D_rq^d V_qc^b) )
             //      T1: rows = out, cols = G;  T2: rows = G, cols = out (needed by the external terms only)
             const int nT12 = external ? 2 : 1;
-            for (int x = threadIdx.x; x < nT12 * nw * g * 9; x += NT) {
-                const int which = x / (nw * g * 9);
-                int y = x - which * (nw * g * 9);
-                const int bd = y % 9; y /= 9;
-                const int b = bd / 3, d = bd - 3 * b;
+            // thread = one element (r, c) with all six symmetric (b, d): three V / three D loads per partner band serve nine
+            // products (a thread per (r, c, b, d) re-read them for every component pair and computed b <-> d twice)
+            for (int x = threadIdx.x; x < nT12 * nw * g; x += NT) {
+                const int which = x / (nw * g);
+                const int y = x - which * (nw * g);
                 int r, cidx;
                 if (which == 0) { cidx = ga + y % g; r = y / g; }    // r = l (any band), c in G
                 else { cidx = y % nw; r = ga + y / nw; }             // r = m in G, c = l
                 const bool rG = in_G(r), cG = in_G(cidx);
-                cplx res = cmake(0., 0.);
-                if (rG != cG) {
-                    cplx sum = W[(size_t)wb_sym6(b, d) * n2 + r * nw + cidx];
+                const bool live = (rG != cG);
+                cplx acc[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) acc[i] = cmake(0., 0.);
+                if (live) {
                     for (int p = 0; p < nw; p++) {
-                        if (in_G(p) == rG) {      // p in the row set
-                            cfma(sum, V[(size_t)b * n2 + r * nw + p], Dm(d, p, cidx));
-                            cfma(sum, V[(size_t)d * n2 + r * nw + p], Dm(b, p, cidx));
-                        } else {                  // p in the column set
-                            const cplx z1 = cmul(Dm(b, r, p), V[(size_t)d * n2 + p * nw + cidx]);
-                            const cplx z2 = cmul(Dm(d, r, p), V[(size_t)b * n2 + p * nw + cidx]);
-                            sum = cmake(sum.x - z1.x - z2.x, sum.y - z1.y - z2.y);
+                        const bool prow = (in_G(p) == rG);   // p in the row set: + V_rp D_pc, else: - D_rp V_pc
+                        cplx Xv[3], Yv[3];
+                        if (prow) {   // (uniform over the live threads of a warp)
+#pragma unroll
+                            for (int a3 = 0; a3 < 3; a3++) { Xv[a3] = Vel(a3, r * nw + p); Yv[a3] = Dm(a3, p, cidx); }
+                        } else {
+#pragma unroll
+                            for (int a3 = 0; a3 < 3; a3++) {
+                                const cplx dr = Dm(a3, r, p);
+                                Xv[a3] = cmake(-dr.x, -dr.y);
+                                Yv[a3] = Vel(a3, p * nw + cidx);
+                            }
                         }
+                        int i = 0;
+#pragma unroll
+                        for (int b3 = 0; b3 < 3; b3++)
+#pragma unroll
+                            for (int d3 = b3; d3 < 3; d3++, i++) {
+                                cfma(acc[i], Xv[b3], Yv[d3]);
+                                cfma(acc[i], Xv[d3], Yv[b3]);
+                            }
                     }
-                    res = cscale(-inv[r * nw + cidx], sum);
                 }
-                if (which == 0) T1[((size_t)r * g + (cidx - ga)) * 9 + bd] = res;
-                else T2[((size_t)(r - ga) * nw + cidx) * 9 + bd] = res;
+                const double mi = live ? -inv[r * nw + cidx] : 0.;
+                cplx* const dst = (which == 0) ? T1 + ((size_t)r * g + (cidx - ga)) * 9 : T2 + ((size_t)(r - ga) * nw + cidx) * 9;
+                int i = 0;
+#pragma unroll
+                for (int b3 = 0; b3 < 3; b3++)
+#pragma unroll
+                    for (int d3 = b3; d3 < 3; d3++, i++) {
+                        cplx res = cmake(0., 0.);
+                        if (live) res = cscale(mi, cadd(W[(size_t)i * n2 + r * nw + cidx], acc[i]));
+                        dst[3 * b3 + d3] = res;
+                        dst[3 * d3 + b3] = res;
+                    }
             }
             // ---- Matrix_GenDer_ln of A:  T3 = dA.ln (l in out, n in G),  T4 = dA.nn (p, n in G)
             if (external) {
-                for (int x = threadIdx.x; x < nw * g * 9; x += NT) {
-                    int y = x;
-                    const int bd = y % 9; y /= 9;
-                    const int b = bd / 3, d = bd - 3 * b;
-                    const int n = ga + y % g, l = y / g;
-                    cplx sum = dAc[(size_t)bd * n2 + l * nw + n];
-                    if (!in_G(l)) {
-                        // dA_ln = A,d_ln - sum_{m' in G} D_lm'^d A_m'n^b + sum_{p in out} A_lp^b D_pn^d
-                        for (int p = 0; p < nw; p++) {
-                            if (in_G(p)) {
-                                const cplx z = cmul(Dm(d, l, p), A[(size_t)b * n2 + p * nw + n]);
-                                sum = cmake(sum.x - z.x, sum.y - z.y);
-                            } else cfma(sum, A[(size_t)b * n2 + l * nw + p], Dm(d, p, n));
+                for (int x = threadIdx.x; x < nw * g; x += NT) {   // thread = (l, n), all nine (b, d)
+                    const int n = ga + x % g, l = x / g;
+                    const bool lG = in_G(l);
+                    cplx acc[9];
+#pragma unroll
+                    for (int bd = 0; bd < 9; bd++) acc[bd] = dAc[(size_t)bd * n2 + l * nw + n];
+                    // l in out:  dA_ln = A,d_ln - sum_{m' in G} D_lm'^d A_m'n^b + sum_{p in out} A_lp^b D_pn^d
+                    // l in G:    dA_pn (p = l) = A,d_pn - sum_{q in out} D_pq^d A_qn^b + sum_{q in out} A_pq^b D_qn^d
+                    for (int p = 0; p < nw; p++) {
+                        const bool pG = in_G(p);
+                        if (lG && pG) continue;
+                        const bool minus = lG || pG, plus = lG || !pG;
+                        cplx Dl[3], Ap[3], Al[3], Dp[3];
+#pragma unroll
+                        for (int a3 = 0; a3 < 3; a3++) {
+                            Dl[a3] = Dm(a3, l, p);
+                            Ap[a3] = A[(size_t)a3 * n2 + p * nw + n];
+                            Al[a3] = A[(size_t)a3 * n2 + l * nw + p];
+                            Dp[a3] = Dm(a3, p, n);
                         }
-                        T3[((size_t)l * g + (n - ga)) * 9 + bd] = sum;
-                    } else {
-                        // dA_pn (p = l in G) = A,d_pn - sum_{q in out} D_pq^d A_qn^b + sum_{q in out} A_pq^b D_qn^d
-                        for (int q = 0; q < nw; q++) {
-                            if (in_G(q)) continue;
-                            const cplx z = cmul(Dm(d, l, q), A[(size_t)b * n2 + q * nw + n]);
-                            sum = cmake(sum.x - z.x, sum.y - z.y);
-                            cfma(sum, A[(size_t)b * n2 + l * nw + q], Dm(d, q, n));
-                        }
-                        T4[((size_t)(l - ga) * g + (n - ga)) * 9 + bd] = sum;
+#pragma unroll
+                        for (int b3 = 0; b3 < 3; b3++)
+#pragma unroll
+                            for (int d3 = 0; d3 < 3; d3++) {
+                                if (minus) {
+                                    const cplx z = cmul(Dl[d3], Ap[b3]);
+                                    acc[3 * b3 + d3] = cmake(acc[3 * b3 + d3].x - z.x, acc[3 * b3 + d3].y - z.y);
+                                }
+                                if (plus) cfma(acc[3 * b3 + d3], Al[b3], Dp[d3]);
+                            }
                     }
+                    cplx* const dst = lG ? T4 + ((size_t)(l - ga) * g + (n - ga)) * 9 : T3 + ((size_t)l * g + (n - ga)) * 9;
+#pragma unroll
+                    for (int bd = 0; bd < 9; bd++) dst[bd] = acc[bd];
                 }
             }
             __syncthreads();

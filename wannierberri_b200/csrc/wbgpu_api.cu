@@ -1020,15 +1020,24 @@ static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
         const size_t per_cta = sizeof(cplx) * wb_deromega_scratch_elems(nw);
         const long nblk_max = std::max(32L, std::min((long)sms * 4, (long)(1.5e9 / (double)per_cta)));
         if (ensure(&c->d_mx, &c->mx_cap, per_cta * (size_t)nblk_max)) return 1;
-        const size_t smem = wb_fsea_smem_bytes(nw, 9);
+        size_t smem = wb_fsea_smem_bytes(nw, 9);
+        // V_a and D_a of the k-point staged in shared memory when two CTAs per SM still fit (wb_fsea_stage)
+        const int stage = (wb_fsea_stage_offset(nw, 9) + wb_fsea_stage_bytes(nw) <= (size_t)c->smem_optin / 2 - 1024) ? 1 : 0;
+        if (stage) smem = wb_fsea_stage_offset(nw, 9) + wb_fsea_stage_bytes(nw);
         if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(wb_deromega_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(stage ? wb_deromega_events_kernel<NT, true> : wb_deromega_events_kernel<NT, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         for (long k0 = 0; k0 < nk; k0 += chunk) {
             const long n = std::min(chunk, nk - k0);
             if (rotate_gemm(c, ch, k0, n)) return 1;
             WbWindow wloc = G.win;
             if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
-            wb_deromega_events_kernel<NT><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+            if (stage)
+                wb_deromega_events_kernel<NT, true><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, C, G.ev.internal_terms, ext ? 1 : 0, (cplx*)c->d_mx,
+                c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * 9);
+            else
+                wb_deromega_events_kernel<NT, false><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
                 (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, C, G.ev.internal_terms, ext ? 1 : 0, (cplx*)c->d_mx,
                 c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * 9);
             c->launches++;
