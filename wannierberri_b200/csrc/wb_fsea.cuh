@@ -321,10 +321,10 @@ struct WbProductSpec {
 __host__ __device__ inline int wb_product_kind_ncomp(int kind) { return (kind == 2 || kind == 5) ? 9 : 3; }
 __host__ __device__ inline size_t wb_product_scratch_elems(int nw) { return (size_t)56 * nw * nw; }
 
-template <int NT>
+template <int NT, bool STAGE>
 __global__ void __launch_bounds__(NT)
 wb_product_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall,
-                         WbWindow win, WbProductSpec P, int internal, int external, cplx* __restrict__ scratch,
+                         WbWindow win, WbProductSpec P, int internal, int external, int stage_off, cplx* __restrict__ scratch,
                          double* __restrict__ ev_label, double* __restrict__ ev_val) {
     extern __shared__ __align__(16) double smem_f[];
     const int n2 = nw * nw;
@@ -342,8 +342,14 @@ wb_product_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
         wb_fsea_groups<NT>(Eall, ik, nw, win, Es, label, inv, g1, g2);
         const cplx* X = xbar + (size_t)ik * nch * n2;
         const cplx* V = X + (size_t)P.iV * n2;
+        cplx* const Vs = (cplx*)((char*)smem_f + stage_off);   // [3][n2 + 1], then D likewise (STAGE: wb_fsea_stage)
+        cplx* const Ds = Vs + 3 * (n2 + 1);
+        if (STAGE) wb_fsea_stage<NT>(V, inv, nw, Vs, Ds);
+        auto Vel = [&](int a, int e) { return STAGE ? Vs[a * (n2 + 1) + e] : V[(size_t)a * n2 + e]; };
         const cplx* A = X + (size_t)P.iA * n2;
-        auto Dm = [&](int a, int p, int q) { return cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]); };
+        auto Dm = [&](int a, int p, int q) {
+            return STAGE ? Ds[a * (n2 + 1) + p * nw + q] : cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]);
+        };
         for (int x = threadIdx.x; x < nw; x += NT) ev_label[ik * nw + x] = label[x];
         for (int ga = 0; ga < nw; ga++) {
             if (label[ga] == CUDART_INF) continue;   // uniform
@@ -363,7 +369,7 @@ wb_product_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
                 const int mn = y / nc[f], m = ga + mn / g, n = ga + mn % g;
                 const int kind = P.kind[f];
                 cplx val;
-                if (kind == 1) val = V[(size_t)comp * n2 + m * nw + n];
+                if (kind == 1) val = Vel(comp, m * nw + n);
                 else if (kind == 4) val = X[(size_t)(P.iS + comp) * n2 + m * nw + n];
                 else if (kind == 2 || kind == 5) {
                     // X^{b:d}_mn = X,d_mn - sum_{l notin G} D_ml^d X_ln^b + sum_l X_ml^b D_ln^d
@@ -477,10 +483,10 @@ __host__ __device__ __forceinline__ int wb_sym10(int a, int b, int c) {
     return base[lo] + ((lo == 0) ? (mid == 0 ? hi : (mid == 1 ? 2 + hi : 5)) : (lo == 1) ? (mid == 1 ? hi - 1 : 2) : 0);
 }
 
-template <int NT>
+template <int NT, bool STAGE>
 __global__ void __launch_bounds__(NT)
 wb_der3e_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall, WbWindow win,
-                       int iV, int iW, int iW3, cplx* __restrict__ scratch, double* __restrict__ ev_label,
+                       int iV, int iW, int iW3, int stage_off, cplx* __restrict__ scratch, double* __restrict__ ev_label,
                        double* __restrict__ ev_val) {
     extern __shared__ __align__(16) double smem_f[];
     const int n2 = nw * nw;
@@ -500,9 +506,15 @@ wb_der3e_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
         wb_fsea_groups<NT>(Eall, ik, nw, win, Es, label, inv, g1, g2);
         const cplx* X = xbar + (size_t)ik * nch * n2;
         const cplx* V = X + (size_t)iV * n2;
+        cplx* const Vs = (cplx*)((char*)smem_f + stage_off);   // [3][n2 + 1], then D likewise (STAGE: wb_fsea_stage)
+        cplx* const Ds = Vs + 3 * (n2 + 1);
+        if (STAGE) wb_fsea_stage<NT>(V, inv, nw, Vs, Ds);
+        auto Vel = [&](int a, int e) { return STAGE ? Vs[a * (n2 + 1) + e] : V[(size_t)a * n2 + e]; };
         const cplx* W = X + (size_t)iW * n2;
         const cplx* W3 = X + (size_t)iW3 * n2;
-        auto Dm = [&](int a, int p, int q) { return cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]); };
+        auto Dm = [&](int a, int p, int q) {
+            return STAGE ? Ds[a * (n2 + 1) + p * nw + q] : cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]);
+        };
         for (int x = threadIdx.x; x < nw; x += NT) ev_label[ik * nw + x] = label[x];
         for (int ga = 0; ga < nw; ga++) {
             if (label[ga] == CUDART_INF) continue;   // uniform
@@ -525,20 +537,20 @@ wb_der3e_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
                     if (which < 2) {   // DerDcov
                         for (int p = 0; p < nw; p++) {
                             if (in_G(p) == rG) {
-                                cfma(sum, V[(size_t)b * n2 + r * nw + p], Dm(d, p, cidx));
-                                cfma(sum, V[(size_t)d * n2 + r * nw + p], Dm(b, p, cidx));
+                                cfma(sum, Vel(b, r * nw + p), Dm(d, p, cidx));
+                                cfma(sum, Vel(d, r * nw + p), Dm(b, p, cidx));
                             } else {
-                                const cplx z1 = cmul(Dm(b, r, p), V[(size_t)d * n2 + p * nw + cidx]);
-                                const cplx z2 = cmul(Dm(d, r, p), V[(size_t)b * n2 + p * nw + cidx]);
+                                const cplx z1 = cmul(Dm(b, r, p), Vel(d, p * nw + cidx));
+                                const cplx z2 = cmul(Dm(d, r, p), Vel(b, p * nw + cidx));
                                 sum = cmake(sum.x - z1.x - z2.x, sum.y - z1.y - z2.y);
                             }
                         }
                         res = cscale(-inv[r * nw + cidx], sum);
                     } else {           // InvMass: V^{b:d}_rc = W_rc^{bd} - sum_{q in cols} D_rq^d V_qc^b + sum_{p in rows} V_rp^b D_pc^d
                         for (int p = 0; p < nw; p++) {
-                            if (in_G(p) == rG) cfma(sum, V[(size_t)b * n2 + r * nw + p], Dm(d, p, cidx));
+                            if (in_G(p) == rG) cfma(sum, Vel(b, r * nw + p), Dm(d, p, cidx));
                             else {
-                                const cplx z = cmul(Dm(d, r, p), V[(size_t)b * n2 + p * nw + cidx]);
+                                const cplx z = cmul(Dm(d, r, p), Vel(b, p * nw + cidx));
                                 sum = cmake(sum.x - z.x, sum.y - z.y);
                             }
                         }
@@ -560,8 +572,8 @@ wb_der3e_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, 
                     const int ab6 = wb_sym6(a, b);
                     re += cmul(W[(size_t)ab6 * n2 + m * nw + l], Dlm_c).x - cmul(Dml_c, W[(size_t)ab6 * n2 + l * nw + m]).x;
                     re += cmul(T5[((size_t)(m - ga) * nw + l) * 9 + 3 * a + c], Dlm_b).x;
-                    re += cmul(V[(size_t)a * n2 + m * nw + l], T1[((size_t)l * g + (m - ga)) * 9 + 3 * b + c]).x;
-                    re -= cmul(T2[((size_t)(m - ga) * nw + l) * 9 + 3 * b + c], V[(size_t)a * n2 + l * nw + m]).x;
+                    re += cmul(Vel(a, m * nw + l), T1[((size_t)l * g + (m - ga)) * 9 + 3 * b + c]).x;
+                    re -= cmul(T2[((size_t)(m - ga) * nw + l) * 9 + 3 * b + c], Vel(a, l * nw + m)).x;
                     re -= cmul(Dml_b, T6[((size_t)l * g + (m - ga)) * 9 + 3 * a + c]).x;
                 }
 #pragma unroll
@@ -593,10 +605,10 @@ __host__ inline size_t wb_dermorb_smem_bytes(int nw) {
            (nw + 1) * sizeof(int) + 64;
 }
 
-template <int NT>
+template <int NT, bool STAGE>
 __global__ void __launch_bounds__(NT)
 wb_dermorb_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall,
-                         WbWindow win, WbDerMorbChans C, int internal, int external, cplx* __restrict__ scratch,
+                         WbWindow win, WbDerMorbChans C, int internal, int external, int stage_off, cplx* __restrict__ scratch,
                          double* __restrict__ ev_label, double* __restrict__ ev_val) {
     extern __shared__ __align__(16) double smem_f[];
     const int n2 = nw * nw;
@@ -629,6 +641,10 @@ wb_dermorb_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
         __syncthreads();
         const cplx* X = xbar + (size_t)ik * nch * n2;
         const cplx* V = X + (size_t)C.iV * n2;
+        cplx* const Vs = (cplx*)((char*)smem_f + stage_off);   // [3][n2 + 1], then D likewise (STAGE: wb_fsea_stage)
+        cplx* const Ds = Vs + 3 * (n2 + 1);
+        if (STAGE) wb_fsea_stage<NT>(V, inv, nw, Vs, Ds);
+        auto Vel = [&](int a, int e) { return STAGE ? Vs[a * (n2 + 1) + e] : V[(size_t)a * n2 + e]; };
         const cplx* W = X + (size_t)C.iW * n2;
         const cplx* A = X + (size_t)C.iA * n2;
         const cplx* O = X + (size_t)C.iO * n2;
@@ -638,7 +654,9 @@ wb_dermorb_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
         const cplx* dBc = X + (size_t)C.idB * n2;
         const cplx* Cm = X + (size_t)C.iC * n2;
         const cplx* dCc = X + (size_t)C.idC * n2;
-        auto Dm = [&](int a, int p, int q) { return cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]); };
+        auto Dm = [&](int a, int p, int q) {
+            return STAGE ? Ds[a * (n2 + 1) + p * nw + q] : cscale(-inv[p * nw + q], V[(size_t)a * n2 + p * nw + q]);
+        };
         for (int x = threadIdx.x; x < nw; x += NT) ev_label[ik * nw + x] = label[x];
         for (int xe = 1; xe <= nw; xe++) {
             if (!edge[xe]) continue;   // uniform
@@ -659,11 +677,11 @@ wb_dermorb_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
                     cplx sum = W[(size_t)wb_sym6(b, d) * n2 + r * nw + cidx];
                     for (int p = 0; p < nw; p++) {
                         if (in_G(p) == rG) {
-                            cfma(sum, V[(size_t)b * n2 + r * nw + p], Dm(d, p, cidx));
-                            cfma(sum, V[(size_t)d * n2 + r * nw + p], Dm(b, p, cidx));
+                            cfma(sum, Vel(b, r * nw + p), Dm(d, p, cidx));
+                            cfma(sum, Vel(d, r * nw + p), Dm(b, p, cidx));
                         } else {
-                            const cplx z1 = cmul(Dm(b, r, p), V[(size_t)d * n2 + p * nw + cidx]);
-                            const cplx z2 = cmul(Dm(d, r, p), V[(size_t)b * n2 + p * nw + cidx]);
+                            const cplx z1 = cmul(Dm(b, r, p), Vel(d, p * nw + cidx));
+                            const cplx z2 = cmul(Dm(d, r, p), Vel(b, p * nw + cidx));
                             sum = cmake(sum.x - z1.x - z2.x, sum.y - z1.y - z2.y);
                         }
                     }
@@ -681,11 +699,11 @@ wb_dermorb_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
                 cplx sum = cmake(0., 0.);
                 if (!in_G(p)) {
                     if (internal)
-                        for (int l = g; l < nw; l++) cfma(sum, V[(size_t)d * n2 + p * nw + l], Dm(be, l, m));
+                        for (int l = g; l < nw; l++) cfma(sum, Vel(d, p * nw + l), Dm(be, l, m));
                     T8[((size_t)p * g + m) * 9 + dc] = sum;
                 } else {
                     if (external)
-                        for (int l = 0; l < g; l++) cfma(sum, V[(size_t)d * n2 + p * nw + l], A[(size_t)be * n2 + l * nw + m]);
+                        for (int l = 0; l < g; l++) cfma(sum, Vel(d, p * nw + l), A[(size_t)be * n2 + l * nw + m]);
                     T9[((size_t)p * g + m) * 9 + dc] = sum;
                 }
             }
@@ -768,7 +786,7 @@ wb_dermorb_events_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk
                         }
                     } else {
                         if (external) SH += 2. * cmul(A[(size_t)al * n2 + m * nw + l], T9[((size_t)l * g + m) * 9 + dc]).y;
-                        OV += cmul(T10[(size_t)(m * g + l) * 3 + c], V[(size_t)d * n2 + l * nw + m]).x;
+                        OV += cmul(T10[(size_t)(m * g + l) * 3 + c], Vel(d, l * nw + m)).x;
                     }
 #pragma unroll
                     for (int t = 0; t < 2; t++) {

@@ -1003,6 +1003,7 @@ static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     constexpr int NT = 256;
     if (formula == WBGPU_DER_OMEGA) {
+        constexpr int NT = 128;   // (shadows the 256 of the other kernels: 3 CTAs per SM, less idling in the small band groups)
         if (L.off_dH[0] < 0 || L.off_W[0] < 0 || (ext && (L.off_A[0] < 0 || L.off_O[0] < 0 || L.off_dA[0] < 0)))
             return set_err("scan: the plan does not hold the channels of DerOmega");
         WbDerOmegaChans C;
@@ -1018,11 +1019,11 @@ static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
         const long chunk = xbar_chunk(c, ch.n, nk);
         if (ensure(&c->d_xbar, &c->xbar_cap, sizeof(cplx) * (size_t)chunk * ch.n * n2)) return 1;
         const size_t per_cta = sizeof(cplx) * wb_deromega_scratch_elems(nw);
-        const long nblk_max = std::max(32L, std::min((long)sms * 4, (long)(1.5e9 / (double)per_cta)));
+        const long nblk_max = std::max(32L, std::min((long)sms * 6, (long)(1.5e9 / (double)per_cta)));
         if (ensure(&c->d_mx, &c->mx_cap, per_cta * (size_t)nblk_max)) return 1;
         size_t smem = wb_fsea_smem_bytes(nw, 9);
         // V_a and D_a of the k-point staged in shared memory when two CTAs per SM still fit (wb_fsea_stage)
-        const int stage = (wb_fsea_stage_offset(nw, 9) + wb_fsea_stage_bytes(nw) <= (size_t)c->smem_optin / 2 - 1024) ? 1 : 0;
+        const int stage = (wb_fsea_stage_offset(nw, 9) + wb_fsea_stage_bytes(nw) <= (size_t)c->smem_optin / 3 - 1024) ? 1 : 0;
         if (stage) smem = wb_fsea_stage_offset(nw, 9) + wb_fsea_stage_bytes(nw);
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(stage ? wb_deromega_events_kernel<NT, true> : wb_deromega_events_kernel<NT, false>,
@@ -1062,16 +1063,25 @@ static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
         const size_t per_cta = sizeof(cplx) * wb_dermorb_scratch_elems(nw);
         const long nblk_max = std::max(32L, std::min((long)sms * 4, (long)(1.5e9 / (double)per_cta)));
         if (ensure(&c->d_mx, &c->mx_cap, per_cta * (size_t)nblk_max)) return 1;
-        const size_t smem = wb_dermorb_smem_bytes(nw);
+        size_t smem = wb_dermorb_smem_bytes(nw);
+        // V_a and D_a of the k-point staged in shared memory when two CTAs per SM still fit (wb_fsea_stage)
+        const int stage_off = (int)((smem + 15) / 16 * 16);
+        const bool stage = stage_off + wb_fsea_stage_bytes(nw) <= (size_t)c->smem_optin / 2 - 1024;
+        if (stage) smem = stage_off + wb_fsea_stage_bytes(nw);
         if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(wb_dermorb_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(stage ? wb_dermorb_events_kernel<NT, true> : wb_dermorb_events_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         for (long k0 = 0; k0 < nk; k0 += chunk) {
             const long n = std::min(chunk, nk - k0);
             if (rotate_gemm(c, ch, k0, n)) return 1;
             WbWindow wloc = G.win;
             if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
-            wb_dermorb_events_kernel<NT><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
-                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, C, G.ev.internal_terms, ext ? 1 : 0, (cplx*)c->d_mx,
+            if (stage)
+                wb_dermorb_events_kernel<NT, true><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, C, G.ev.internal_terms, ext ? 1 : 0, stage_off, (cplx*)c->d_mx,
+                c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * 9);
+            else
+                wb_dermorb_events_kernel<NT, false><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, C, G.ev.internal_terms, ext ? 1 : 0, stage_off, (cplx*)c->d_mx,
                 c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * 9);
             c->launches++;
             CK(cudaGetLastError());
@@ -1086,16 +1096,25 @@ static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
         const size_t per_cta = sizeof(cplx) * wb_deromega_scratch_elems(nw);
         const long nblk_max = std::max(32L, std::min((long)sms * 4, (long)(1.5e9 / (double)per_cta)));
         if (ensure(&c->d_mx, &c->mx_cap, per_cta * (size_t)nblk_max)) return 1;
-        const size_t smem = wb_fsea_smem_bytes(nw, 27);
+        size_t smem = wb_fsea_smem_bytes(nw, 27);
+        // V_a and D_a of the k-point staged in shared memory when two CTAs per SM still fit (wb_fsea_stage)
+        const int stage_off = (int)((smem + 15) / 16 * 16);
+        const bool stage = stage_off + wb_fsea_stage_bytes(nw) <= (size_t)c->smem_optin / 2 - 1024;
+        if (stage) smem = stage_off + wb_fsea_stage_bytes(nw);
         if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(wb_der3e_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(stage ? wb_der3e_events_kernel<NT, true> : wb_der3e_events_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         for (long k0 = 0; k0 < nk; k0 += chunk) {
             const long n = std::min(chunk, nk - k0);
             if (rotate_gemm(c, ch, k0, n)) return 1;
             WbWindow wloc = G.win;
             if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
-            wb_der3e_events_kernel<NT><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
-                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, iV, iW, iW3, (cplx*)c->d_mx, c->d_evlabel + k0 * nw,
+            if (stage)
+                wb_der3e_events_kernel<NT, true><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, iV, iW, iW3, stage_off, (cplx*)c->d_mx, c->d_evlabel + k0 * nw,
+                c->d_evval + (size_t)k0 * nw * 27);
+            else
+                wb_der3e_events_kernel<NT, false><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, iV, iW, iW3, stage_off, (cplx*)c->d_mx, c->d_evlabel + k0 * nw,
                 c->d_evval + (size_t)k0 * nw * 27);
             c->launches++;
             CK(cudaGetLastError());
@@ -1123,16 +1142,25 @@ static int run_events_solo(wbgpu_ctx* c, const EvGroup& G, long nk) {
         const size_t per_cta = sizeof(cplx) * wb_product_scratch_elems(nw);
         const long nblk_max = std::max(32L, std::min((long)sms * 4, (long)(1.5e9 / (double)per_cta)));
         if (ensure(&c->d_mx, &c->mx_cap, per_cta * (size_t)nblk_max)) return 1;
-        const size_t smem = wb_fsea_smem_bytes(nw, 0);
+        size_t smem = wb_fsea_smem_bytes(nw, 0);
+        // V_a and D_a of the k-point staged in shared memory when two CTAs per SM still fit (wb_fsea_stage)
+        const int stage_off = (int)((smem + 15) / 16 * 16);
+        const bool stage = stage_off + wb_fsea_stage_bytes(nw) <= (size_t)c->smem_optin / 2 - 1024;
+        if (stage) smem = stage_off + wb_fsea_stage_bytes(nw);
         if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(wb_product_events_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(stage ? wb_product_events_kernel<NT, true> : wb_product_events_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         for (long k0 = 0; k0 < nk; k0 += chunk) {
             const long n = std::min(chunk, nk - k0);
             if (rotate_gemm(c, ch, k0, n)) return 1;
             WbWindow wloc = G.win;
             if (wloc.Ebmin) { wloc.Ebmin += k0 * nw; wloc.Ebmax += k0 * nw; }
-            wb_product_events_kernel<NT><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
-                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, P, G.ev.internal_terms, ext ? 1 : 0, (cplx*)c->d_mx,
+            if (stage)
+                wb_product_events_kernel<NT, true><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, P, G.ev.internal_terms, ext ? 1 : 0, stage_off, (cplx*)c->d_mx,
+                c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * NC);
+            else
+                wb_product_events_kernel<NT, false><<<(unsigned)std::min(n, nblk_max), NT, smem, c->stream>>>(
+                (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, wloc, P, G.ev.internal_terms, ext ? 1 : 0, stage_off, (cplx*)c->d_mx,
                 c->d_evlabel + k0 * nw, c->d_evval + (size_t)k0 * nw * NC);
             c->launches++;
             CK(cudaGetLastError());
