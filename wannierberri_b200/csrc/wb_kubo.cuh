@@ -566,13 +566,14 @@ wb_kubo_accumulate_kernel(const double* __restrict__ entries, const int* __restr
 // complex multiply-adds: 16 DFMA per 5 shared-memory loads instead of 2 per 4 (the per-(omega, re|im) kernel above is
 // bound by its shared-memory loads).  Same entries, same difference array, same flush rule (owner bin / Fermi-Dirac).
 constexpr int WB_KUBO_TW = 64;       // frequencies per CTA
-constexpr int WB_KUBO_TCHUNK = 16;   // entries staged per step
+constexpr int WB_KUBO_TCHUNK = 16;   // entries staged per step (18 = 8 full rounds of factor items was measured: slower, 30.3 -> 32.9 ms)
 
 __global__ void __launch_bounds__(144)
 wb_kubo_accumulate_optcond_tiled_kernel(const double* __restrict__ entries, const int* __restrict__ count, int cap, long nk,
                                         WbKuboParams P, const double* __restrict__ omega, const double* __restrict__ Ef,
                                         double* __restrict__ Dglob) {
     constexpr int WT = WB_KUBO_TW, CH = WB_KUBO_TCHUNK, NT = 144, ENT = WB_KUBO_ENT, NC = 18;
+    static_assert(WT == 64, "layout of Wb: 16 frequency groups of 4");
     __shared__ __align__(16) double ent[CH * ENT];
     __shared__ __align__(16) double Wb[CH * WT * 4];
     const int w0 = blockIdx.x * WT, nwt = min(WT, P.nomega - w0);
@@ -615,21 +616,40 @@ wb_kubo_accumulate_optcond_tiled_kernel(const double* __restrict__ entries, cons
             __syncthreads();
             for (int x = tid; x < np * ENT; x += NT) ent[x] = src[(size_t)p0 * ENT + x];
             __syncthreads();
-            for (int x = tid; x < np * WT; x += NT) {   // frequency factors, zero beyond the end of the axis
-                const int p = x / WT, w = x - p * WT;
-                double* o = Wb + (p * WT + w) * 4;
+            // frequency factors, zero beyond the end of the axis.  Layout: the factor of frequency w = 4 grp + q sits at
+            // position 16 q + grp of its entry's row, so that the four frequency groups of a warp read ONE 128-byte line per
+            // q (rows in frequency order put them 128 bytes apart: 4-way bank conflicts, 43 % of the wavefronts in ncu)
+            for (int x = tid; x < np * WT; x += NT) {
+                const int p = x / WT, pos = x - p * WT;
+                const int w = ((pos & 15) << 2) + (pos >> 4);
+                double* o = Wb + (p * WT + pos) * 4;
                 if (w < nwt) {
                     const double dl = ent[p * ENT], om = omega[w0 + w];
-                    const cplx c1 = wb_kubo_cfac(dl - om, P.eta, P.smr_type);
-                    const cplx c2 = wb_kubo_cfac(-dl - om, P.eta, P.smr_type);
+                    cplx c1, c2;
+                    if (P.smr_type == 0) {   // both Lorentzians from ONE division: 1/x1 = x2 / (x1 x2), 1/x2 = x1 / (x1 x2)
+                        const double d1 = dl - om, d2 = -dl - om, e2 = P.eta * P.eta;
+                        const double x1 = fma(d1, d1, e2), x2 = fma(d2, d2, e2);
+                        const double r = 1. / (x1 * x2);
+                        const double den1 = r * x2, den2 = r * x1;
+                        c1 = cmake(d1 * den1, P.eta * den1);
+                        c2 = cmake(d2 * den2, P.eta * den2);
+                    } else {
+                        c1 = wb_kubo_cfac(dl - om, P.eta, P.smr_type);
+                        c2 = wb_kubo_cfac(-dl - om, P.eta, P.smr_type);
+                    }
                     const double w1x = dl * c1.x, w1y = dl * c1.y, w2x = -dl * c2.x, w2y = -dl * c2.y;
                     o[0] = w2x - w1x; o[1] = w2y - w1y;
                     o[2] = -(w1x + w2x); o[3] = -(w1y + w2y);
                 } else o[0] = o[1] = o[2] = o[3] = 0.;
             }
             __syncthreads();
-            for (int p = 0; p < np; p++) {
-                const double own = ent[p * ENT + 1];
+            double owns[CH];   // owner bins of the chunk, loaded ahead of the loop (the branch below waited for each load)
+#pragma unroll
+            for (int p = 0; p < CH; p++) owns[p] = ent[(p < np ? p : 0) * ENT + 1];
+#pragma unroll
+            for (int p = 0; p < CH; p++) {
+                if (p >= np) break;
+                const double own = owns[p];
                 if (!have || own != curown) {   // uniform
                     flush();
                     curown = own;
@@ -638,10 +658,10 @@ wb_kubo_accumulate_optcond_tiled_kernel(const double* __restrict__ entries, cons
                     for (int q = 0; q < 4; q++) Yr[q] = Yi[q] = 0.;
                 }
                 const double2 M = *reinterpret_cast<const double2*>(ent + p * ENT + 2 + 2 * ab);
-                const double* Wp = Wb + (p * WT + 4 * grp) * 4 + wsel;
+                const double* Wp = Wb + (p * WT + grp) * 4 + wsel;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const double2 W = *reinterpret_cast<const double2*>(Wp + 4 * q);
+                    const double2 W = *reinterpret_cast<const double2*>(Wp + 64 * q);
                     Yr[q] += W.x * M.x - W.y * M.y;
                     Yi[q] += W.x * M.y + W.y * M.x;
                 }
