@@ -185,11 +185,11 @@ wb_tridiag_cta_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk
 
 __host__ inline size_t wb_eigvec_cta_smem_bytes(int n) {
     const int ldu = n | 1;
-    return sizeof(double) * (((size_t)n * n + 1) & ~(size_t)1) + sizeof(cplx) * ((size_t)16 * ldu + 2 * n + n + 2 * 128) +
+    return sizeof(double) * (((size_t)n * n + 1) & ~(size_t)1) + sizeof(cplx) * ((size_t)16 * ldu + 8 * n + n + 2 * 128) +
            sizeof(double) * n + sizeof(int) * 2 * n + 16;
 }
 
-template <int NT>
+template <int NT, int EMAX>
 __global__ void __launch_bounds__(NT)
 wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, const cplx* __restrict__ tauin,
                      const cplx* __restrict__ Vh, const double2* __restrict__ rot, int capR, const int* __restrict__ hdr,
@@ -200,8 +200,8 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
     const int ldu = n | 1;
     double* Zs = smem_e;                          // [col][row]
     cplx* up = (cplx*)(Zs + (((size_t)n * n + 1) & ~(size_t)1));   // [16][ldu]
-    cplx* vbuf = up + 16 * ldu;                   // [2][n]
-    cplx* taus = vbuf + 2 * n;                    // [n]
+    cplx* vbuf = up + 16 * ldu;                   // [2][4][n]: two stages of four reflectors
+    cplx* taus = vbuf + 8 * n;                    // [n]
     double2* rs = (double2*)(taus + n);           // [2][128]
     double* dsm = (double*)(rs + 2 * 128);        // [n]
     int* rank = (int*)(dsm + n);                  // [n]
@@ -234,10 +234,14 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
                 const int h = myhdr[s];
                 const int l = h & 255, m = h >> 8, len = m - l;
                 __syncthreads();
+                // the next sweep's rotations: loaded into a register here, stored to shared memory after this sweep (a
+                // `smem = global` prefetch would stall the in-order warp at the store for the whole memory latency)
+                double2 nextrot = make_double2(0., 0.);
+                int len2 = 0;
                 if (s + 1 < ns) {
                     const int h2 = myhdr[s + 1];
-                    const int len2 = (h2 >> 8) - (h2 & 255);
-                    if (tid < len2) rs[((s + 1) & 1) * 128 + tid] = myrot[r0 + len + tid];
+                    len2 = (h2 >> 8) - (h2 & 255);
+                    if (tid < len2) nextrot = myrot[r0 + len + tid];
                 }
                 if (tid < n) {
                     // rotation i touches columns i, i+1 of this thread's row; the loads of a batch of four columns
@@ -270,6 +274,7 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
                     }
                     Zs[l * n + tid] = carry;
                 }
+                if (tid < len2) rs[((s + 1) & 1) * 128 + tid] = nextrot;
                 r0 += len;
             }
         }
@@ -291,45 +296,90 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
         // ---- back-transformation  u <- H(0) H(1) ... H(n-2) u  in panels of 16 eigenvectors (sorted order)
         const cplx* Vt = Vh + (size_t)t * n * n;
         const int c = tid >> 3, sl = tid & 7;
+        // Thread (c, sl) keeps the elements i = sl + 8 e of eigenvector c of the panel in REGISTERS for all n - 1 reflectors
+        // (EMAX = ceil(n / 8) complex values) and reads every reflector element once per step: the shared-memory traffic
+        // is the reflector only.  (With u in shared memory the kernel moved 80 bytes per 16 flops: 55 % of its time, ncu
+        // profiles/r2/cfg5_eig_kernels.txt.)
         for (int p0 = 0; p0 < n; p0 += 16) {
             __syncthreads();
-            for (int x = tid; x < 16 * n; x += NT) {
-                const int cc = x / n, i = x - cc * n;
-                up[cc * ldu + i] = cmake((p0 + cc < n) ? Zs[inv[p0 + cc] * n + i] : 0., 0.);
-            }
-            {   // reflector n-2 into vbuf[0]
-                const int k = n - 2;
-                for (int i = tid; i < n; i += NT)
-                    vbuf[i] = (i > k + 1) ? Vt[k * n + i] : ((i == k + 1) ? cmake(1., 0.) : cmake(0., 0.));
-            }
-            int cur = 0;
-            for (int k = n - 2; k >= 0; k--, cur ^= 1) {
-                __syncthreads();
-                if (k > 0) {   // prefetch reflector k-1 into the other buffer
-                    cplx* nb = vbuf + (cur ^ 1) * n;
-                    const int k1 = k - 1;
-                    for (int i = tid; i < n; i += NT)
-                        nb[i] = (i > k1 + 1) ? Vt[k1 * n + i] : ((i == k1 + 1) ? cmake(1., 0.) : cmake(0., 0.));
-                }
-                const cplx tau = taus[k];
-                if (tau.x == 0. && tau.y == 0.) continue;   // uniform
-                const cplx* v = vbuf + cur * n;
-                cplx* u = up + c * ldu;
-                cplx sd = cmake(0., 0.);
-                for (int i = k + 1 + sl; i < n; i += 8) cfma_conj(sd, v[i], u[i]);
+            cplx u[EMAX];
+            {
+                const bool colok = (p0 + c < n);
+                const double* zcol = Zs + (size_t)(colok ? inv[p0 + c] : 0) * n;
 #pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    sd.x += __shfl_xor_sync(0xffffffffu, sd.x, o);
-                    sd.y += __shfl_xor_sync(0xffffffffu, sd.y, o);
+                for (int e = 0; e < EMAX; e++) {
+                    const int i = sl + 8 * e;
+                    u[e] = cmake((colok && i < n) ? zcol[i] : 0., 0.);
                 }
-                const cplx ts = cmul(tau, sd);
-                for (int i = k + 1 + sl; i < n; i += 8) {
-                    const cplx vv = v[i];
-                    cplx uu = u[i];
-                    uu.x -= ts.x * vv.x - ts.y * vv.y;
-                    uu.y -= ts.x * vv.y + ts.y * vv.x;
-                    u[i] = uu;
+            }
+            // Reflectors are staged RB at a time (double buffer).  The next group is loaded into REGISTERS before the RB
+            // steps of the current one and stored to shared memory after them: a warp issues in order, so a prefetch
+            // written as `smem = global` stalls at the store and exposes the full memory latency in every step (what the
+            // one-reflector-per-barrier loop did: ~1800 clocks per step, 55 % of the kernel).  n <= NT: element i = tid.
+            constexpr int RB = 4;
+            static_assert(NT >= 128, "one reflector element per thread");
+            auto fetch_group = [&](int kb, cplx (&pre)[RB]) {
+#pragma unroll
+                for (int r = 0; r < RB; r++) {
+                    const int k = kb - r;
+                    pre[r] = cmake(0., 0.);
+                    if (k >= 0 && tid < n) pre[r] = (tid > k + 1) ? Vt[(size_t)k * n + tid] : ((tid == k + 1) ? cmake(1., 0.) : cmake(0., 0.));
                 }
+            };
+            auto store_group = [&](const cplx (&pre)[RB], cplx* dst) {
+                if (tid < n) {
+#pragma unroll
+                    for (int r = 0; r < RB; r++) dst[r * n + tid] = pre[r];
+                }
+            };
+            cplx pre[RB];
+            fetch_group(n - 2, pre);
+            store_group(pre, vbuf);
+            int cur = 0;
+            for (int kb = n - 2; kb >= 0; kb -= RB, cur ^= 1) {
+                __syncthreads();
+                const bool more = (kb - RB >= 0);
+                if (more) fetch_group(kb - RB, pre);
+#pragma unroll 1
+                for (int r = 0; r < RB; r++) {
+                    const int k = kb - r;
+                    if (k < 0) break;
+                    const cplx tau = taus[k];
+                    if (tau.x == 0. && tau.y == 0.) continue;   // uniform
+                    const cplx* v = vbuf + (cur * RB + r) * n;   // zero up to element k, one at k + 1
+                    cplx vr[EMAX];
+                    cplx s0 = cmake(0., 0.), s1 = cmake(0., 0.);
+#pragma unroll
+                    for (int e = 0; e < EMAX; e++) {
+                        vr[e] = cmake(0., 0.);
+                        if (8 * e + 7 > k) {   // (uniform: below, every element of the block is zero)
+                            const int i = sl + 8 * e;
+                            if (i < n) vr[e] = v[i];
+                            if (e & 1) cfma_conj(s1, vr[e], u[e]);
+                            else cfma_conj(s0, vr[e], u[e]);
+                        }
+                    }
+                    cplx sd = cadd(s0, s1);
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        sd.x += __shfl_xor_sync(0xffffffffu, sd.x, o);
+                        sd.y += __shfl_xor_sync(0xffffffffu, sd.y, o);
+                    }
+                    const cplx ts = cmul(tau, sd);
+#pragma unroll
+                    for (int e = 0; e < EMAX; e++) {
+                        if (8 * e + 7 > k) {
+                            u[e].x -= ts.x * vr[e].x - ts.y * vr[e].y;
+                            u[e].y -= ts.x * vr[e].y + ts.y * vr[e].x;
+                        }
+                    }
+                }
+                if (more) store_group(pre, vbuf + (cur ^ 1) * RB * n);
+            }
+#pragma unroll
+            for (int e = 0; e < EMAX; e++) {
+                const int i = sl + 8 * e;
+                if (i < n) up[c * ldu + i] = u[e];
             }
             __syncthreads();
             cplx* Uo = Uout + (size_t)ik * n * n;

@@ -765,11 +765,20 @@ static int launch_ql_large(wbgpu_ctx* c, long k0, long nk, bool want_U) {
     constexpr int NT3 = 128;
     size_t smem3 = wb_eigvec_cta_smem_bytes(nw);
     if ((int)smem3 > c->smem_optin) return set_err("eigh: num_wann=%d needs %zu B shared memory", nw, smem3);
-    CK(cudaFuncSetAttribute(wb_eigvec_cta_kernel<NT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
     int per_sm3 = std::max(1, std::min(4, (int)((size_t)c->smem_optin / smem3)));
-    wb_eigvec_cta_kernel<NT3><<<(unsigned)std::min(nk, (long)sms * per_sm3), NT3, smem3, c->stream>>>(
-        nw, k0, nk, c->d_dw, c->d_tau, c->d_Vh, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep, want_U ? 1 : 0, c->d_E,
-        c->d_U, c->d_nfail);
+    // EMAX = elements of an eigenvector per thread of the back-transformation (8 threads per vector)
+#define WB_EIGVEC_CTA(EM)                                                                                                     \
+    do {                                                                                                                      \
+        CK(cudaFuncSetAttribute(wb_eigvec_cta_kernel<NT3, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));     \
+        wb_eigvec_cta_kernel<NT3, EM><<<(unsigned)std::min(nk, (long)sms * per_sm3), NT3, smem3, c->stream>>>(                \
+            nw, k0, nk, c->d_dw, c->d_tau, c->d_Vh, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep, want_U ? 1 : 0, c->d_E, \
+            c->d_U, c->d_nfail);                                                                                              \
+    } while (0)
+    if (nw <= 48) WB_EIGVEC_CTA(6);
+    else if (nw <= 64) WB_EIGVEC_CTA(8);
+    else if (nw <= 96) WB_EIGVEC_CTA(12);
+    else WB_EIGVEC_CTA(16);
+#undef WB_EIGVEC_CTA
     c->launches += 3;
     CK(cudaGetLastError());
     // there is no second solver for these sizes: a QL iteration that did not converge is an error
