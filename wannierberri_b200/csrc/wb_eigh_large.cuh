@@ -183,9 +183,9 @@ wb_tridiag_cta_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk
     }
 }
 
-__host__ inline size_t wb_eigvec_cta_smem_bytes(int n) {
+__host__ inline size_t wb_eigvec_cta_smem_bytes(int n, int pw) {   // pw = eigenvectors per panel = threads / 8
     const int ldu = n | 1;
-    return sizeof(double) * (((size_t)n * n + 1) & ~(size_t)1) + sizeof(cplx) * ((size_t)16 * ldu + 8 * n + n + 2 * 128) +
+    return sizeof(double) * (((size_t)n * n + 1) & ~(size_t)1) + sizeof(cplx) * ((size_t)pw * ldu + 8 * n + n + 2 * 128) +
            sizeof(double) * n + sizeof(int) * 2 * n + 16;
 }
 
@@ -195,12 +195,13 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
                      const cplx* __restrict__ Vh, const double2* __restrict__ rot, int capR, const int* __restrict__ hdr,
                      int capS, const int* __restrict__ nsweep, int want_U, double* __restrict__ Eout,
                      cplx* __restrict__ Uout, int* __restrict__ nfail) {
-    static_assert(NT == 128, "thread = row of Z, n <= 128; 16 panel columns x 8 row slices");
+    static_assert(NT >= 128 && NT % 32 == 0, "threads 0 .. n-1 = rows of Z (n <= 128); NT / 8 panel columns x 8 row slices");
+    constexpr int PW = NT / 8;   // eigenvectors per panel of the back-transformation
     extern __shared__ __align__(16) double smem_e[];
     const int ldu = n | 1;
     double* Zs = smem_e;                          // [col][row]
-    cplx* up = (cplx*)(Zs + (((size_t)n * n + 1) & ~(size_t)1));   // [16][ldu]
-    cplx* vbuf = up + 16 * ldu;                   // [2][4][n]: two stages of four reflectors
+    cplx* up = (cplx*)(Zs + (((size_t)n * n + 1) & ~(size_t)1));   // [PW][ldu]
+    cplx* vbuf = up + PW * ldu;                   // [2][4][n]: two stages of four reflectors
     cplx* taus = vbuf + 8 * n;                    // [n]
     double2* rs = (double2*)(taus + n);           // [2][128]
     double* dsm = (double*)(rs + 2 * 128);        // [n]
@@ -300,7 +301,7 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
         // (EMAX = ceil(n / 8) complex values) and reads every reflector element once per step: the shared-memory traffic
         // is the reflector only.  (With u in shared memory the kernel moved 80 bytes per 16 flops: 55 % of its time, ncu
         // profiles/r2/cfg5_eig_kernels.txt.)
-        for (int p0 = 0; p0 < n; p0 += 16) {
+        for (int p0 = 0; p0 < n; p0 += PW) {
             __syncthreads();
             cplx u[EMAX];
             {
@@ -383,8 +384,8 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
             }
             __syncthreads();
             cplx* Uo = Uout + (size_t)ik * n * n;
-            for (int x = tid; x < 16 * n; x += NT) {
-                const int cc = x & 15, i = x >> 4;
+            for (int x = tid; x < PW * n; x += NT) {
+                const int cc = x % PW, i = x / PW;
                 if (p0 + cc < n) Uo[i * n + p0 + cc] = up[cc * ldu + i];
             }
         }

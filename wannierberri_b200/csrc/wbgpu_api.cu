@@ -762,8 +762,8 @@ static int launch_ql_large(wbgpu_ctx* c, long k0, long nk, bool want_U) {
     wb_tql_kernel<NT2><<<(unsigned)((nk + NT2 - 1) / NT2), NT2, smem2, c->stream>>>(nw, nk, c->d_dw, c->d_ew, c->d_rot, c->capR,
                                                                                  c->d_hdr, c->capS, c->d_nsweep);
     CK(cudaGetLastError());
-    constexpr int NT3 = 128;
-    size_t smem3 = wb_eigvec_cta_smem_bytes(nw);
+    constexpr int NT3 = 256;   // replay: threads 0 .. nw-1 = rows; back-transformation: 32 eigenvectors x 8 slices
+    size_t smem3 = wb_eigvec_cta_smem_bytes(nw, NT3 / 8);
     if ((int)smem3 > c->smem_optin) return set_err("eigh: num_wann=%d needs %zu B shared memory", nw, smem3);
     int per_sm3 = std::max(1, std::min(4, (int)((size_t)c->smem_optin / smem3)));
     // EMAX = elements of an eigenvector per thread of the back-transformation (8 threads per vector)
