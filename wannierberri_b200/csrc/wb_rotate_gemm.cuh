@@ -40,7 +40,7 @@ __host__ inline size_t wb_gemm_smem_bytes(int nw) {
 template <int NTL, int KC>
 __global__ void __launch_bounds__(128)
 wb_rotate_gemm_kernel(const cplx* __restrict__ rec, long recE, WbChanList ch, int nw, long nk,
-                      const cplx* __restrict__ Uall, cplx* __restrict__ xbar) {
+                      const cplx* __restrict__ Uall, cplx* __restrict__ xbar, const int2* __restrict__ colwin) {
     constexpr int TN = 8 * NTL, LDP = wb_gemm_ldp<NTL, KC>(), LDA = KC + 4;
     extern __shared__ __align__(16) cplx smem_r[];
     const int nwp = (nw + KC - 1) / KC * KC;
@@ -57,6 +57,14 @@ wb_rotate_gemm_kernel(const cplx* __restrict__ rec, long recE, WbChanList ch, in
     for (long ik = blockIdx.z; ik < nk; ik += gridDim.z) {
         const cplx* r = rec + ik * recE;
         const cplx* U = Uall + ik * n2;
+        // column window (see wb_rotate_gemm_cg_kernel): panels without a band of a band group are skipped, the others
+        // are formed whole; hermitian channels are mirrored into the rows of the window
+        int c0 = 0, c1 = nw;
+        if (colwin) {
+            const int2 w = colwin[ik];
+            c0 = w.x; c1 = w.y;
+            if (l0 >= c1 || l0 + TN <= c0) continue;   // (uniform over the CTA)
+        }
         for (int x = threadIdx.x; x < (nwp - nw) * LDP; x += 128) Yp[(size_t)nw * LDP + x] = cmake(0., 0.);
 #pragma unroll 1
         for (int phase = 0; phase < 2; phase++) {
@@ -136,11 +144,20 @@ wb_rotate_gemm_kernel(const cplx* __restrict__ rec, long recE, WbChanList ch, in
                     for (int i = 0; i < 2; i++) {
                         const int n = m0 + 8 * (warp + 4 * i) + g;
                         if (n < nw) {
+                            // mirror: row l of a hermitian channel for the bands n outside the computed panels
+                            const bool mir = colwin && herm && (n < (c0 / TN) * TN || n >= ((c1 + TN - 1) / TN) * TN);
 #pragma unroll
                             for (int t = 0; t < NTL; t++) {
                                 const int l = l0 + 8 * t + 2 * q;
-                                if (l < nw) out[n * nw + l] = cmake(are[i][t][0], aim[i][t][0]);
-                                if (l + 1 < nw) out[n * nw + l + 1] = cmake(are[i][t][1], aim[i][t][1]);
+                                const cplx v0 = cmake(are[i][t][0], aim[i][t][0]), v1 = cmake(are[i][t][1], aim[i][t][1]);
+                                if (l < nw) {
+                                    out[n * nw + l] = v0;
+                                    if (mir) out[l * nw + n] = cconj(v0);
+                                }
+                                if (l + 1 < nw) {
+                                    out[n * nw + l + 1] = v1;
+                                    if (mir) out[(l + 1) * nw + n] = cconj(v1);
+                                }
                             }
                         }
                     }

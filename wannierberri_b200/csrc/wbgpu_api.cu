@@ -889,14 +889,14 @@ static int launch_mma_events(wbgpu_ctx* c, const EvGroup& G, long nk) {
 static int ensure(double** p, size_t* cap, size_t need);
 
 template <int NTL, int KC>
-static int launch_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n) {
+static int launch_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n, const int2* colwin) {
     const int nw = c->nw;
     size_t smem = wb_gemm_smem_bytes<NTL, KC>(nw);
     if ((int)smem > c->smem_optin) return set_err("rotate(gemm): num_wann=%d needs %zu B shared memory", nw, smem);
     CK(cudaFuncSetAttribute(wb_rotate_gemm_kernel<NTL, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((nw + 8 * NTL - 1) / (8 * NTL)), (unsigned)ch.n, (unsigned)std::min(n, 16384L));
     wb_rotate_gemm_kernel<NTL, KC><<<grid, 128, smem, c->stream>>>(c->d_X + (size_t)k0 * c->L.E, (long)c->L.E, ch, nw, n,
-                                                                 c->d_U + (size_t)k0 * nw * nw, (cplx*)c->d_xbar);
+                                                                 c->d_U + (size_t)k0 * nw * nw, (cplx*)c->d_xbar, colwin);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -929,10 +929,10 @@ static int rotate_gemm(wbgpu_ctx* c, const WbChanList& ch, long k0, long n, cons
         if (nw <= 24) return launch_gemm_cg<3, 8, 2>(c, ch, k0, n, colwin);
         if (nw <= 32) return launch_gemm_cg<4, 16, 2>(c, ch, k0, n, colwin);
     }
-    if (nw <= 8) return launch_gemm<1, 8>(c, ch, k0, n);
-    if (nw <= 16) return launch_gemm<2, 8>(c, ch, k0, n);
-    if (nw <= 24) return launch_gemm<3, 8>(c, ch, k0, n);
-    return launch_gemm<4, 16>(c, ch, k0, n);
+    if (nw <= 8) return launch_gemm<1, 8>(c, ch, k0, n, colwin);
+    if (nw <= 16) return launch_gemm<2, 8>(c, ch, k0, n, colwin);
+    if (nw <= 24) return launch_gemm<3, 8>(c, ch, k0, n, colwin);
+    return launch_gemm<4, 16>(c, ch, k0, n, colwin);
 }
 
 static long xbar_chunk(wbgpu_ctx* c, int nch, long nk) {
@@ -968,7 +968,7 @@ static int run_events_xbar(wbgpu_ctx* c, const EvGroup& G, long nk) {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(wb_events_xbar_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // the formula stage reads rows / columns of the bands of a band group only (wb_rotate_gemm.cuh, TRIM); not so the
     // non-additive Morb evaluation (all pairs), nor a non-hermitian d_a H (its rows are not the mirror of its columns)
-    const bool trim = c->rotate_trim && c->gemm_stack && nw <= 32 && !((G.ev.mask >> 2) & 1) && (L.dH_herm || !need.V);
+    const bool trim = c->rotate_trim && !((G.ev.mask >> 2) & 1) && (L.dH_herm || !need.V);
     if (trim && ensure(&c->d_colwin, &c->colwin_cap, sizeof(int2) * (size_t)chunk)) return 1;
     for (long k0 = 0; k0 < nk; k0 += chunk) {
         long n = std::min(chunk, nk - k0);
