@@ -186,7 +186,7 @@ wb_tridiag_cta_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk
 __host__ inline size_t wb_eigvec_cta_smem_bytes(int n, int pw) {   // pw = eigenvectors per panel = threads / 8
     const int ldu = n | 1;
     return sizeof(double) * (((size_t)n * n + 1) & ~(size_t)1) + sizeof(cplx) * ((size_t)pw * ldu + 8 * n + n + 2 * 128) +
-           sizeof(double) * n + sizeof(int) * 2 * n + 16;
+           sizeof(double) * 4 * n + sizeof(int) * 2 * n + 16;
 }
 
 template <int NT, int EMAX>
@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(NT)
 wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, const cplx* __restrict__ tauin,
                      const cplx* __restrict__ Vh, const double2* __restrict__ rot, int capR, const int* __restrict__ hdr,
                      int capS, const int* __restrict__ nsweep, int want_U, double* __restrict__ Eout,
-                     cplx* __restrict__ Uout, int* __restrict__ nfail) {
+                     cplx* __restrict__ Uout, int* __restrict__ nfail, const double* __restrict__ d0,
+                     const double* __restrict__ e0, int* __restrict__ nreplay) {
     static_assert(NT >= 128 && NT % 32 == 0, "threads 0 .. n-1 = rows of Z (n <= 128); NT / 8 panel columns x 8 row slices");
     constexpr int PW = NT / 8;   // eigenvectors per panel of the back-transformation
     extern __shared__ __align__(16) double smem_e[];
@@ -205,7 +206,10 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
     cplx* taus = vbuf + 8 * n;                    // [n]
     double2* rs = (double2*)(taus + n);           // [2][128]
     double* dsm = (double*)(rs + 2 * 128);        // [n]
-    int* rank = (int*)(dsm + n);                  // [n]
+    double* esm = dsm + n;                        // [n] eigenvalues, ascending
+    double* td = esm + n;                         // [n] diagonal of the tridiagonal matrix (as reduced: d0)
+    double* te = td + n;                          // [n] its off-diagonal (e0)
+    int* rank = (int*)(te + n);                   // [n]
     int* inv = rank + n;                          // [n]
     const int tid = threadIdx.x;
     for (long t = blockIdx.x; t < nk; t += gridDim.x) {
@@ -217,8 +221,137 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
         }
         const int ns = nsr & 4095;
         __syncthreads();
-        if (tid < n) { dsm[tid] = dvals[t * n + tid]; taus[tid] = tauin[t * n + tid]; }
-        if (want_U) {
+        if (tid < n) {
+            dsm[tid] = dvals[t * n + tid];
+            taus[tid] = tauin[t * n + tid];
+            if (d0) { td[tid] = d0[t * n + tid]; te[tid] = (tid < n - 1) ? e0[t * n + tid] : 0.; }
+        }
+        __syncthreads();
+        // ---- sort
+        if (tid < n) {
+            const double myd = dsm[tid];
+            int rk = 0;
+            for (int j = 0; j < n; j++) {
+                const double dj = dsm[j];
+                rk += (dj < myd) || (dj == myd && j < tid);
+            }
+            rank[tid] = rk;
+            inv[rk] = tid;
+            esm[rk] = myd;
+            Eout[ik * n + rk] = myd;
+        }
+        if (!want_U) continue;
+        __syncthreads();
+        // ---- eigenvectors of T, first choice: ONE twisted factorisation per eigenvalue (Fernando; Parlett-Dhillon; the
+        // scheme of wb_eigh_tf.cuh), thread j = eigenvalue j (ascending), workspace and result = column j of Zt[i][j]
+        // (component-major: conflict free).  O(n^2) per matrix instead of the O(n^3) replay of the QL rotations.
+        // Vectors of eigenvalues closer than 5e-3 |T| are orthogonalised against each other in the order of the
+        // eigenvalues; a run of more than 16, a vector that the projection cancels (numerically multiple eigenvalue)
+        // or a residual above 256 eps |T| sends the WHOLE matrix to the replay below (uniform decision).
+        bool tf_done = false;
+        if (d0) {
+            int myfail = 0;
+            double tnorm = 0.;
+            for (int i = 0; i < n; i++) tnorm = fmax(tnorm, fabs(td[i]) + fabs(te[i]) + ((i > 0) ? fabs(te[i - 1]) : 0.));
+            const double eps = 2.220446049250313e-16;
+            const double pivmin = fmax(eps * tnorm * 0.0009765625, 1e-290);
+            const double ctol = 5e-3 * tnorm;   // orthogonality of neighbours ~ 4 eps |T| / gap: 2e-13 at the edge of the window
+            if (tid < n) {
+                const double sigma = esm[tid];
+                double* W = Zs + tid;   // element i at W[i * n]
+                double dcur = td[0] - sigma;
+                for (int i = 0; i < n - 1; i++) {          // top-down: l_i = e_i / D+_i
+                    if (fabs(dcur) < pivmin) dcur = -pivmin;
+                    const double ei = te[i];
+                    const double l = ei / dcur;
+                    W[i * n] = l;
+                    dcur = fma(-l, ei, td[i + 1] - sigma);
+                }
+                int r = n - 1;
+                double gr = fabs(dcur);                     // gamma_{n-1} = D+_{n-1}
+                dcur = td[n - 1] - sigma;
+                for (int i = n - 2; i >= 0; i--) {          // bottom-up: gamma_i = D-_i - l_{i-1} e_{i-1}; twist = argmin
+                    if (fabs(dcur) < pivmin) dcur = -pivmin;
+                    const double ei = te[i];
+                    const double u = ei / dcur;
+                    dcur = fma(-u, ei, td[i] - sigma);
+                    const double ga = fabs((i > 0) ? fma(-W[(i - 1) * n], te[i - 1], dcur) : dcur);
+                    if (ga <= gr) { gr = ga; r = i; }
+                }
+                dcur = td[n - 1] - sigma;
+                for (int i = n - 2; i >= r; i--) {          // bottom-up again: u_i = e_i / D-_{i+1} kept for i >= r
+                    if (fabs(dcur) < pivmin) dcur = -pivmin;
+                    const double ei = te[i];
+                    const double u = ei / dcur;
+                    W[i * n] = u;
+                    dcur = fma(-u, ei, td[i] - sigma);
+                }
+                // the vector in place: z_r = 1, z_i = -l_i z_{i+1} (i < r), z_{i+1} = -u_i z_i (i >= r)
+                double nrm2 = 1.;
+                {
+                    double zn = 1.;
+                    for (int i = r - 1; i >= 0; i--) { zn = -W[i * n] * zn; W[i * n] = zn; nrm2 = fma(zn, zn, nrm2); }
+                    double ucur = (r <= n - 2) ? W[r * n] : 0.;
+                    W[r * n] = 1.;
+                    zn = 1.;
+                    for (int i = r; i <= n - 2; i++) {
+                        zn = -ucur * zn;
+                        ucur = (i + 1 <= n - 2) ? W[(i + 1) * n] : 0.;
+                        W[(i + 1) * n] = zn;
+                        nrm2 = fma(zn, zn, nrm2);
+                    }
+                }
+                if (!(nrm2 > 0.) || !(nrm2 < 1e300)) myfail = 1;
+                const double sc = rsqrt(nrm2);
+                for (int i = 0; i < n; i++) W[i * n] *= sc;
+            }
+            __syncthreads();
+            // ---- clusters: position of eigenvalue j inside its run of gaps < ctol
+            int pos = 0;
+            if (tid < n) {
+                while (pos < 17 && tid - pos > 0 && esm[tid - pos] - esm[tid - pos - 1] < ctol) pos++;
+                if (pos > 16) myfail = 1;
+            }
+            for (int round = 1; round <= 16; round++) {
+                if (!__syncthreads_or(tid < n && pos >= round)) break;   // (also orders the rounds)
+                if (tid < n && pos == round && !myfail) {
+                    double* W = Zs + tid;
+                    for (int pass = 0; pass < 2; pass++) {             // "twice is enough"
+                        for (int p = tid - round; p < tid; p++) {
+                            const double* Wp = Zs + p;
+                            double dot = 0.;
+                            for (int i = 0; i < n; i++) dot = fma(W[i * n], Wp[i * n], dot);
+                            for (int i = 0; i < n; i++) W[i * n] = fma(-dot, Wp[i * n], W[i * n]);
+                        }
+                        double nn = 0.;
+                        for (int i = 0; i < n; i++) nn = fma(W[i * n], W[i * n], nn);
+                        if (pass == 0 && !(nn > 0.0025)) myfail = 1;      // cancelled: numerically multiple eigenvalue
+                        const double sc = rsqrt(nn);
+                        if (!myfail)
+                            for (int i = 0; i < n; i++) W[i * n] *= sc;
+                    }
+                }
+            }
+            // ---- residual |(T - sigma) z| of what is stored
+            if (tid < n && !myfail) {
+                const double sigma = esm[tid];
+                const double* W = Zs + tid;
+                double r2 = 0., below = 0., zi = W[0];
+                for (int i = 0; i < n; i++) {
+                    const double znext = (i + 1 < n) ? W[(i + 1) * n] : 0.;
+                    const double v = fma(td[i] - sigma, zi, below) + te[i] * znext;
+                    below = te[i] * zi;
+                    zi = znext;
+                    r2 = fma(v, v, r2);
+                }
+                const double restol = 256. * eps * tnorm;
+                if (!(r2 <= restol * restol)) myfail = 1;
+            }
+            tf_done = !__syncthreads_or(myfail);
+            if (!tf_done && tid == 0 && nreplay) atomicAdd(nreplay, 1);
+        }
+        if (!tf_done) {
+            __syncthreads();
             for (int x = tid; x < n * n; x += NT) Zs[x] = 0.;
             __syncthreads();
             if (tid < n) Zs[tid * n + tid] = 1.;
@@ -280,20 +413,6 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
             }
         }
         __syncthreads();
-        // ---- sort
-        if (tid < n) {
-            const double myd = dsm[tid];
-            int rk = 0;
-            for (int j = 0; j < n; j++) {
-                const double dj = dsm[j];
-                rk += (dj < myd) || (dj == myd && j < tid);
-            }
-            rank[tid] = rk;
-            inv[rk] = tid;
-            Eout[ik * n + rk] = myd;
-        }
-        if (!want_U) continue;
-        __syncthreads();
         // ---- back-transformation  u <- H(0) H(1) ... H(n-2) u  in panels of 16 eigenvectors (sorted order)
         const cplx* Vt = Vh + (size_t)t * n * n;
         const int c = tid >> 3, sl = tid & 7;
@@ -306,11 +425,13 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
             cplx u[EMAX];
             {
                 const bool colok = (p0 + c < n);
-                const double* zcol = Zs + (size_t)(colok ? inv[p0 + c] : 0) * n;
+                // replay: Z[column of the QL order][row]; twisted factorisation: Zt[component][eigenvalue, ascending]
+                const double* zcol = tf_done ? Zs + (colok ? p0 + c : 0) : Zs + (size_t)(colok ? inv[p0 + c] : 0) * n;
+                const int zstride = tf_done ? n : 1;
 #pragma unroll
                 for (int e = 0; e < EMAX; e++) {
                     const int i = sl + 8 * e;
-                    u[e] = cmake((colok && i < n) ? zcol[i] : 0., 0.);
+                    u[e] = cmake((colok && i < n) ? zcol[(size_t)i * zstride] : 0., 0.);
                 }
             }
             // Reflectors are staged RB at a time (double buffer).  The next group is loaded into REGISTERS before the RB

@@ -84,6 +84,7 @@ struct wbgpu_ctx {
     size_t xbar_cap = 0;
     double* d_mx = nullptr;
     size_t mx_cap = 0;
+    double *d_d0 = nullptr, *d_e0 = nullptr;   // tridiagonal matrices as reduced (nw > 32: the QL kernel works in place)
     double* d_colwin = nullptr;   // int2 per k-point: band range of the band groups (column window of the GEMM rotation)
     size_t colwin_cap = 0;
     // Kubo path: entry lists of a sub-batch, global accumulator, axes
@@ -166,6 +167,8 @@ static void free_plan(wbgpu_ctx* c) {
     cudaFree(c->d_E); cudaFree(c->d_evlabel); cudaFree(c->d_evval);
     cudaFree(c->d_dw); cudaFree(c->d_ew); cudaFree(c->d_tau); cudaFree(c->d_rot); cudaFree(c->d_hdr); cudaFree(c->d_Vh);
     c->d_Vh = nullptr;
+    cudaFree(c->d_d0); cudaFree(c->d_e0);
+    c->d_d0 = c->d_e0 = nullptr;
     cudaFree(c->d_nsweep); cudaFree(c->d_faillist); cudaFree(c->d_nfail);
     c->d_dw = c->d_ew = nullptr; c->d_tau = nullptr; c->d_rot = nullptr;
     c->d_hdr = c->d_nsweep = c->d_faillist = c->d_nfail = nullptr;
@@ -525,7 +528,11 @@ extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula
         CK(cudaMalloc(&c->d_nsweep, sizeof(int) * ch));
         CK(cudaMalloc(&c->d_faillist, sizeof(int) * ch));
         CK(cudaMalloc(&c->d_nfail, sizeof(int)));
-        if (nw > 32) CK(cudaMalloc(&c->d_Vh, sizeof(cplx) * ch * nw * nw));
+        if (nw > 32) {
+            CK(cudaMalloc(&c->d_Vh, sizeof(cplx) * ch * nw * nw));
+            CK(cudaMalloc(&c->d_d0, sizeof(double) * ch * nw));
+            CK(cudaMalloc(&c->d_e0, sizeof(double) * ch * nw));
+        }
     }
     CK(cudaStreamSynchronize(c->stream));
     c->planned = true;
@@ -756,6 +763,12 @@ static int launch_ql_large(wbgpu_ctx* c, long k0, long nk, bool want_U) {
     wb_tridiag_cta_kernel<NT1><<<(unsigned)std::min(nk, (long)sms * per_sm1), NT1, smem1, c->stream>>>(
         c->d_X, c->L, k0, nk, c->d_dw, c->d_ew, c->d_tau, c->d_Vh);
     CK(cudaGetLastError());
+    // eig_method 2 = eigenvectors by replaying the QL rotations only; default: twisted factorisation first (needs T as reduced)
+    const bool tf = want_U && c->eig_method != 2;
+    if (tf) {
+        CK(cudaMemcpyAsync(c->d_d0, c->d_dw, sizeof(double) * nk * nw, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_e0, c->d_ew, sizeof(double) * nk * nw, cudaMemcpyDeviceToDevice, c->stream));
+    }
     constexpr int NT2 = 32;
     size_t smem2 = sizeof(double) * 2 * nw * NT2;
     CK(cudaFuncSetAttribute(wb_tql_kernel<NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -772,7 +785,7 @@ static int launch_ql_large(wbgpu_ctx* c, long k0, long nk, bool want_U) {
         CK(cudaFuncSetAttribute(wb_eigvec_cta_kernel<NT3, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));     \
         wb_eigvec_cta_kernel<NT3, EM><<<(unsigned)std::min(nk, (long)sms * per_sm3), NT3, smem3, c->stream>>>(                \
             nw, k0, nk, c->d_dw, c->d_tau, c->d_Vh, c->d_rot, c->capR, c->d_hdr, c->capS, c->d_nsweep, want_U ? 1 : 0, c->d_E, \
-            c->d_U, c->d_nfail);                                                                                              \
+            c->d_U, c->d_nfail, tf ? c->d_d0 : nullptr, tf ? c->d_e0 : nullptr, c->d_sweeps + 1);                             \
     } while (0)
     if (nw <= 48) WB_EIGVEC_CTA(6);
     else if (nw <= 64) WB_EIGVEC_CTA(8);
