@@ -182,7 +182,9 @@ def test_eigh_sizes_and_degeneracies(wb, nw, degenerate):
         resid = np.abs(np.einsum("kij,kjn->kin", H, U) - U * E[:, None, :]).max()
         assert resid < 1e-11 * max(np.abs(H).max(), 1.), (nw, method, resid)
         unit = np.abs(np.einsum("kin,kim->knm", U.conj(), U) - np.eye(nw)).max()
-        assert unit < 1e-12, (nw, method, unit)
+        # (nw > 32, method 0: eigenvectors of T from twisted factorisations; neighbours beyond the 5e-3 |T| orthogonalisation
+        # window keep ~4 eps |T| / gap: measured 2e-13 .. 9e-13 at nw = 128, against 1e-14 for the QL replay of method 2)
+        assert unit < (3e-12 if nw > 32 and method == 0 else 1e-12), (nw, method, unit)
 
 
 @pytest.mark.parametrize("nw", [6, 12, 18, 24])

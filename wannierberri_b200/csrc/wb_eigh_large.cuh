@@ -31,7 +31,7 @@ __device__ __forceinline__ double2 wb_block_sum2(double a, double b, double2* re
 }
 
 __host__ inline size_t wb_tridiag_cta_smem_bytes(int n) {
-    return sizeof(cplx) * ((size_t)n * (n + 1) / 2 + 4 * (size_t)n) + sizeof(double2) * 64;
+    return sizeof(cplx) * ((size_t)n * (n + 1) / 2 + 10 * (size_t)n) + sizeof(double2) * 64;
 }
 
 // Output: d[t][n], e[t][n] (e[n-1] = 0), tau[t][n], Vh[t][k][i] = component i (> k+1) of Householder vector k.
@@ -41,13 +41,11 @@ wb_tridiag_cta_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk
                       double* __restrict__ eout, cplx* __restrict__ tauout, cplx* __restrict__ Vh) {
     extern __shared__ __align__(16) cplx smem_t[];
     const int n = L.nw, ntri = n * (n + 1) / 2;
-    constexpr int RN = NT / 2;          // rows per pass: thread pair (row, half)
     cplx* P = smem_t;                   // packed lower triangle, column major
     cplx* vs = P + ntri;                // [n]
     cplx* ws = vs + n;                  // [n]
-    cplx* xs = ws + n;                  // [2][n] partial matvec sums
-    double2* red = (double2*)(xs + 2 * n);
-    const int row = threadIdx.x % RN, half = threadIdx.x / RN;
+    cplx* xs = ws + n;                  // [8][n] partial matvec sums
+    double2* red = (double2*)(xs + 8 * n);
     const int nwarps = NT / 32;
     int phase = 0;
     for (long t = blockIdx.x; t < nk; t += gridDim.x) {
@@ -94,12 +92,17 @@ wb_tridiag_cta_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk
             if (!active) continue;
             __syncthreads();
             // ---- x = tau A v  (rows > k): row r = sum_{j=k+1..r} L(r,j) v_j + sum_{i>r} conj(L(i,r)) v_i
-            const int m = n - k - 1;              // elements per row
-            const int mh = (m + 1) >> 1;
-            for (int rb = 0; rb < n; rb += RN) {
-                const int r = rb + row;
-                if (r > k && r < n) {
-                    const int e0 = half * mh, e1 = min(m, e0 + mh);
+            const int m = n - k - 1;              // active rows k+1 .. n-1, m elements per row
+            // S threads per row, S = 2 / 4 / 8 as the active block shrinks (m S <= NT): a fixed thread pair per matrix row
+            // left the rows <= k idle -- half of the CTA on average
+            const int S = (m > NT / 4) ? 2 : ((m > NT / 8) ? 4 : 8);
+            {
+                const int R = NT / S;
+                const int rho = threadIdx.x % R, h = threadIdx.x / R;
+                if (rho < m) {
+                    const int r = k + 1 + rho;
+                    const int Lr = (m + S - 1) / S;
+                    const int e0 = h * Lr, e1 = min(m, e0 + Lr);
                     const int rowcnt = r - k;
                     cplx a0 = cmake(0., 0.), a1 = cmake(0., 0.);
                     {
@@ -119,7 +122,7 @@ wb_tridiag_cta_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk
                             cfma_conj((ee & 1) ? a1 : a0, P[csr + i - r], vs[i]);
                         }
                     }
-                    xs[half * n + r] = cadd(a0, a1);
+                    xs[h * n + r] = cadd(a0, a1);
                 }
             }
             __syncthreads();
@@ -130,7 +133,9 @@ wb_tridiag_cta_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk
                 const int r = threadIdx.x + u * NT;
                 xr[u] = cmake(0., 0.);
                 if (r > k && r < n) {
-                    xr[u] = cmul(tau, cadd(xs[r], xs[n + r]));
+                    cplx xsum = cadd(xs[r], xs[n + r]);
+                    for (int h = 2; h < S; h++) xsum = cadd(xsum, xs[h * n + r]);
+                    xr[u] = cmul(tau, xsum);
                     cplx pd = cconjmul(xr[u], vs[r]);
                     pdx += pd.x;
                     pdy += pd.y;
@@ -144,28 +149,38 @@ wb_tridiag_cta_kernel(const cplx* __restrict__ rec, WbLayout L, long k0, long nk
                 if (r > k && r < n) ws[r] = cadd(xr[u], cmul(al2, vs[r]));
             }
             __syncthreads();
-            // ---- L(r, j) -= v_r conj(w_j) + w_r conj(v_j),  k < j <= r
-            for (int rb = 0; rb < n; rb += RN) {
-                const int r = rb + row;
-                if (r > k && r < n) {
-                    const int cnt = r - k, ch = (cnt + 1) >> 1;
-                    const int ja = k + 1 + half * ch, jb = min(r + 1, ja + ch);
-                    const cplx v = vs[r], w = ws[r];
-                    int cj = wb_cs(ja, n);
-                    for (int j = ja; j < jb; j++) {
-                        const cplx wj = ws[j], vj = vs[j];
-                        cplx a = P[cj + r - j];
-                        a.x = fma(-v.x, wj.x, a.x);
-                        a.y = fma(-v.y, wj.x, a.y);
-                        a.x = fma(-v.y, wj.y, a.x);
-                        a.y = fma(v.x, wj.y, a.y);
-                        a.x = fma(-w.x, vj.x, a.x);
-                        a.y = fma(-w.y, vj.x, a.y);
-                        a.x = fma(-w.y, vj.y, a.x);
-                        a.y = fma(w.x, vj.y, a.y);
-                        P[cj + r - j] = a;
-                        cj += n - j;
-                    }
+            // ---- L(r, j) -= v_r conj(w_j) + w_r conj(v_j),  k < j <= r.  Row r has r - k elements: rows k+1+u and n-1-u are
+            // paired (m + 1 elements together) and every pair is split over S2 = NT / R2 threads -- all threads busy, equal work
+            {
+                const int J = (m + 1) >> 1;
+                const int R2 = (J > NT / 8) ? NT / 4 : ((J > NT / 16) ? NT / 8 : NT / 16);
+                const int S2 = NT / R2;
+                const int u = threadIdx.x % R2, h = threadIdx.x / R2;
+                if (u < J) {
+                    const int rA = k + 1 + u, rB = n - 1 - u;
+                    const int cntA = u + 1, cntB = (rB > rA) ? (m - u) : 0;
+                    const int C = cntA + cntB, L2 = (C + S2 - 1) / S2;
+                    const int e0 = h * L2, e1 = min(C, e0 + L2);
+                    auto update = [&](int r, int ja, int jb) {
+                        const cplx v = vs[r], w = ws[r];
+                        int cj = wb_cs(ja, n);
+                        for (int j = ja; j < jb; j++) {
+                            const cplx wj = ws[j], vj = vs[j];
+                            cplx a = P[cj + r - j];
+                            a.x = fma(-v.x, wj.x, a.x);
+                            a.y = fma(-v.y, wj.x, a.y);
+                            a.x = fma(-v.y, wj.y, a.x);
+                            a.y = fma(v.x, wj.y, a.y);
+                            a.x = fma(-w.x, vj.x, a.x);
+                            a.y = fma(-w.y, vj.x, a.y);
+                            a.x = fma(-w.y, vj.y, a.x);
+                            a.y = fma(w.x, vj.y, a.y);
+                            P[cj + r - j] = a;
+                            cj += n - j;
+                        }
+                    };
+                    if (e0 < cntA) update(rA, k + 1 + e0, k + 1 + min(e1, cntA));
+                    if (cntB > 0 && e1 > cntA) update(rB, k + 1 + max(e0 - cntA, 0), k + 1 + (e1 - cntA));
                 }
             }
         }
