@@ -171,7 +171,7 @@ def test_eigh_sizes_and_degeneracies(wb, nw, degenerate):
     from wannierberri_b200 import _lib
     # method 0 = twisted-factorisation eigenvectors (nw <= 24), 2 / 3 = accumulated QL rotations, 4 / 5 = thread- /
     # lane-pair-per-matrix reduction, 1 = Jacobi
-    for method in ((0, 2, 3, 4, 5, 1) if nw == 18 else (0, 5, 2, 1) if nw <= 20 else (0, 2, 1) if nw <= 32 else (0, 1) if nw <= 40 else (0,)):
+    for method in ((0, 2, 3, 4, 5, 1) if nw == 18 else (0, 5, 2, 1) if nw <= 20 else (0, 2, 1) if nw <= 40 else (0, 2)):   # nw > 32: 0 = twisted factorisation (QL replay as fallback), 2 = replay only
         eng = wb.Engine(sysg)
         eng.set_option("eig_method", method)
         eng.plan(NKFFT, [_lib.IDENTITY])
