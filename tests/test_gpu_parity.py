@@ -187,7 +187,7 @@ def test_eigh_sizes_and_degeneracies(wb, nw, degenerate):
         assert unit < (3e-12 if nw > 32 and method == 0 else 1e-12), (nw, method, unit)
 
 
-@pytest.mark.parametrize("nw", [6, 12, 18, 24])
+@pytest.mark.parametrize("nw", [6, 12, 18, 24, 40, 64])
 def test_eigh_kramers_pairs(wb, nw):
     """PT-symmetric model: every level exactly doubly degenerate with the two halves of the basis coupled (the tridiagonal
     form is numerically reducible).  The twisted-factorisation solver hands the k-points it cannot resolve to the Jacobi
@@ -195,7 +195,8 @@ def test_eigh_kramers_pairs(wb, nw):
     from wannierberri_b200 import _lib
     sysg = wb.kramers_system(nw, seed=nw)
     NKFFT, dK = [8, 8, 8], [0.03, 0.01, 0.2]
-    for method in (0, 1, 2):
+    # (nw > 32: method 0 = twisted factorisation, every matrix falls back to the QL replay here; 1 = Jacobi up to 40 WF)
+    for method in ((0, 1, 2) if nw <= 40 else (0, 2)):
         eng = wb.Engine(sysg)
         eng.set_option("eig_method", method)
         eng.plan(NKFFT, [_lib.IDENTITY])
@@ -415,6 +416,41 @@ def test_fused_rotation_kernel_sizes(wb, nw):
         for key in ((3, 1), (3, 0)):
             for a, r in zip(res[key], res[(4, 1)]):
                 assert relerr(a, r) < 1e-10, (nw, degenerate, key)
+
+
+@pytest.mark.parametrize("nw,which", [(18, "fe"), (24, "te"), (10, "synth"), (40, "synth"), (64, "synth")])
+def test_column_window_matches_full_rotation(wb, fe, te, nw, which):
+    """Size-generic rotation with the per-k-point column window (only rows / columns of the bands of a band group are
+    formed; hermitian channels mirrored; wb_rotate_gemm.cuh) against the full rotation (option rotate_trim = 0): the
+    Fermi-surface product formulae, a Fermi-sea scan (window from band 0) and wide band groups, in both GEMM kernels
+    (several channels per CTA for num_wann <= 32, one channel per CTA above)."""
+    st = wb.calculators.static
+    if which == "synth":
+        sysg = wb.synthetic_system(nw, rmax=1, seed=300 + nw, matrices=("Ham", "AA", "BB", "CC", "SS"))
+        eng = wb.Engine(sysg)
+        eng.plan([2, 3, 2], [_lib_formula("IDENTITY")])
+        E = eng.eig([0.01, 0.02, 0.03])
+        eng.close()
+        Ef = np.linspace(np.percentile(E, 45), np.percentile(E, 60), 31)
+    else:
+        sysg, Ef = (fe, np.linspace(15., 19., 31)) if which == "fe" else (te, np.linspace(4., 8., 31))
+    calcs = [st.BerryDipole_FermiSurf(Efermi=Ef), st.GME_orb_FermiSurf(Efermi=Ef), st.GME_spin_FermiSurf(Efermi=Ef),
+             st.Ohmic_FermiSurf(Efermi=Ef), st.Ohmic_FermiSea(Efermi=Ef), st.BerryDipole_FermiSurf(Efermi=Ef, degen_thresh=0.3),
+             st.AHC(Efermi=Ef, degen_thresh=0.2, degen_Kramers=True)]
+    dK = np.array([[0.01, 0.02, 0.03], [0.3, 0.1, 0.2]])
+    for c in calcs:
+        specs = c.specs()
+        res = {}
+        for trim in (0, 1):
+            eng = wb.Engine(sysg)
+            eng.set_option("rotate_method", 4)
+            eng.set_option("rotate_trim", trim)
+            eng.plan([3, 2, 3], [s.formula for s in specs])
+            res[trim] = eng.scan(dK, np.array([0.5, 0.5]), specs)
+            eng.close()
+        for a, r in zip(res[1], res[0]):
+            assert np.abs(r).max() > 0
+            assert relerr(a, r) < 1e-11, (nw, which, type(c).__name__)
 
 
 BLOCK_CASES = dict(
