@@ -1,6 +1,9 @@
+"""Large-num_wann eigensolver check (33 .. 128 WF, with exactly degenerate spectra): method 0 (twisted factorisation, QL replay as
+fallback) vs method 2 (replay only): errors against LAPACK and the number of matrices that took the fallback.
+   python profiles/eig_large.py"""
 import os, sys
 import numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import wannierberri_b200 as wb
 from wannierberri_b200 import _lib
 for nw, deg in ((33, False), (40, False), (40, True), (64, False), (96, True), (127, False), (128, False)):

@@ -1,3 +1,5 @@
+# End-of-round check on one GPU box: GPU tests, smoke, bench lines of the headline and of BASELINE configs 1-5, reference arm,
+# ncu launch list of the default bench command, workload family timings.   bash profiles/final_runs.sh   (outputs in gpurun_out/)
 set -x
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/final_gpu_tests.log
 python bench.py > gpurun_out/final_bench_headline.json 2> gpurun_out/final_bench_headline.err

@@ -1,5 +1,8 @@
+"""numpy emulation of wb_eigh_jacobi_kernel (round-robin two-sided Jacobi) on PT-symmetric (Kramers-degenerate) matrices: the
+sequence of off-diagonal norms per sweep -- the evidence behind the convergence rule of the kernel (one sweep after 1e-10 |A| is not
+enough: 3e-12 -> 3e-21 -> 3e-25 -> 3e-37 was seen).   python profiles/jacobi_emulation.py"""
 import numpy as np, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from wannierberri_b200.system import kramers_system
 s = kramers_system(6, seed=6)
 iR = s.rvec.iRvec; HR = s._XX_R["Ham"]

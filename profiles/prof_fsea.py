@@ -1,9 +1,11 @@
+"""Driver for ncu captures of the Fermi-sea formula kernels on Te (24 WF, K-blocks of 20^3):
+   python profiles/prof_fsea.py {bd_sea|gme_orb_sea|nldrude_sea} [blocks]"""
 import os, sys
 import numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import wannierberri_b200 as wb
 st = wb.calculators.static
-te = wb.System_R.from_npz("/root/repo/tests/golden/te_system.npz")
+te = wb.System_R.from_npz(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "te_system.npz"))
 Ef = np.linspace(4.0, 8.0, 401)
 which = sys.argv[1] if len(sys.argv) > 1 else "bd_sea"
 calc = dict(bd_sea=st.BerryDipole_FermiSea, gme_orb_sea=st.GME_orb_FermiSea, nldrude_sea=st.NLDrude_FermiSea)[which](Efermi=Ef)
