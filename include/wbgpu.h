@@ -174,6 +174,10 @@ int64_t wbgpu_spec_size(const wbgpu_scan_spec* spec);
  * are Ef_first + i * dEF.  The band energies at the 8 cell corners are evaluated inside the call.  HOST pointers. */
 int wbgpu_static_scan_tetra(wbgpu_ctx* ctx, int nblocks, const double* dK, const double* weight, const double* dK_cell,
                             const wbgpu_scan_spec* specs, int nspec, double* out);
+/* Per-K-block results of the tetrahedron scans for the refinement loop (run_grid.py:343-375): out[nblocks][total] without
+ * weights; dK_cell[nblocks][3] -- refined K-points have smaller cells (grid/Kpoint.py:107-109,145-175).  HOST pointers. */
+int wbgpu_static_scan_tetra_blocks(wbgpu_ctx* ctx, int nblocks, const double* dK, const double* dK_cell,
+                                   const wbgpu_scan_spec* specs, int nspec, double* out);
 
 /* One (Efermi x omega) scan = one DynamicCalculator.__call__ (calculators/dynamic.py:26-114). */
 enum { WBGPU_KUBO_OPTCOND = 0,  /* OpticalConductivity dynamic.py:184-196: complex128 data[nEF][nomega][3][3]    */
@@ -208,6 +212,10 @@ int wbgpu_kubo_scan(wbgpu_ctx* ctx, int nblocks, const double* dK, const double*
  * parameters of the scan like the spec); asynchronous on the context's stream. */
 int wbgpu_kubo_scan_dev(wbgpu_ctx* ctx, int nblocks, const double* dK_dev, const double* weight_dev,
                         const wbgpu_kubo_spec* spec, const double* Efermi, const double* omega, double* out_dev);
+/* Per-K-block results of a Kubo scan for the refinement loop (run_grid.py:343-375): out[nblocks][wbgpu_kubo_size] without
+ * weights.  HOST pointers. */
+int wbgpu_kubo_scan_blocks(wbgpu_ctx* ctx, int nblocks, const double* dK, const wbgpu_kubo_spec* spec, const double* Efermi,
+                           const double* omega, double* out);
 
 /* Parity probes (HOST output pointers). One K-block each. */
 int wbgpu_kpoints(wbgpu_ctx* ctx, const double dK[3], double* kpoints /*[nk][3]*/);

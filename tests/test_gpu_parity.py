@@ -453,6 +453,39 @@ def test_column_window_matches_full_rotation(wb, fe, te, nw, which):
             assert relerr(a, r) < 1e-11, (nw, which, type(c).__name__)
 
 
+def test_per_block_tetra_and_kubo_scans(wb, fe):
+    """wbgpu_static_scan_tetra_blocks / wbgpu_kubo_scan_blocks (per-K-block results of one batched call: what the refinement
+    loop asks for) against one call per K-block of the summed entry points; K-blocks with cells of different sizes, as
+    after a refinement step."""
+    st, dyn = wb.calculators.static, wb.calculators.dynamic
+    Ef = np.linspace(15., 19., 21)
+    tcalcs = [st.AHC(Efermi=Ef, tetra=True), st.DOS(Efermi=Ef, tetra=True), st.BerryDipole_FermiSurf(Efermi=Ef, tetra=True)]
+    specs = [s for c in tcalcs for s in c.specs()]
+    dK = np.array([[0.01, 0.02, 0.03], [0.3, 0.1, 0.2], [0.15, 0.05, 0.4], [0.0, 0.25, 0.125], [0.4, 0.4, 0.1]])
+    cells = np.array([[0.25, 0.25, 0.25]] * 3 + [[0.125, 0.125, 0.125]] * 2)
+    for max_k in (0, 16):   # 16 k-points per launch = batches of two K-blocks: histograms cleared between the batches
+        eng = wb.Engine(fe)
+        eng.plan([2, 2, 2], [s.formula for s in specs], max_kpoints_per_launch=max_k)
+        got = eng.scan_tetra_blocks(dK, cells, specs)
+        for b in range(len(dK)):
+            want = eng.scan_tetra(dK[b:b + 1], np.ones(1), cells[b], specs)
+            for g, w in zip(got, want):
+                assert relerr(g[b], w) < 1e-12, (max_k, b)
+        eng.close()
+    oc = dyn.OpticalConductivity(Efermi=Ef, omega=np.linspace(0., 3., 17), smr_fixed_width=0.2)
+    shc = dyn.SHC(Efermi=Ef, omega=np.linspace(0., 3., 9), smr_fixed_width=0.2, SHC_type="simple")
+    for c in (oc, shc):
+        sp = c.spec()
+        for max_k in (0, 16):
+            eng = wb.Engine(fe)
+            eng.plan([2, 2, 2], [_lib_formula("IDENTITY"), sp.formula_flag], max_kpoints_per_launch=max_k)
+            got = eng.kubo_scan_blocks(dK, sp, c.Efermi, c.omega)
+            for b in range(len(dK)):
+                want = eng.kubo_scan(dK[b:b + 1], np.ones(1), sp, c.Efermi, c.omega)
+                assert got[b].shape == want.shape and relerr(got[b], want) < 1e-11, (type(c).__name__, max_k, b)
+            eng.close()
+
+
 BLOCK_CASES = dict(
     ahc=("AHC", {}), dos=("DOS", {}), cumdos=("CumDOS", {}), Morb=("Morb", {}),
     ahc_kramers=("AHC", dict(degen_Kramers=True)), ahc_thresh=("AHC", dict(degen_thresh=0.05)),

@@ -86,12 +86,14 @@ def lib():
     L.wbgpu_static_scan_dev.argtypes = [vp, C.c_int, vp, vp, C.POINTER(ScanSpec), C.c_int, vp]
     L.wbgpu_static_scan_blocks.argtypes = [vp, C.c_int, pd, C.POINTER(ScanSpec), C.c_int, pd]
     L.wbgpu_static_scan_tetra.argtypes = [vp, C.c_int, pd, pd, pd, C.POINTER(ScanSpec), C.c_int, pd]
+    L.wbgpu_static_scan_tetra_blocks.argtypes = [vp, C.c_int, pd, pd, C.POINTER(ScanSpec), C.c_int, pd]
     L.wbgpu_spec_size.argtypes = [C.POINTER(ScanSpec)]
     L.wbgpu_spec_size.restype = i64
     L.wbgpu_kubo_size.argtypes = [C.POINTER(KuboSpec)]
     L.wbgpu_kubo_size.restype = i64
     L.wbgpu_kubo_scan.argtypes = [vp, C.c_int, pd, pd, C.POINTER(KuboSpec), pd, pd, pd]
     L.wbgpu_kubo_scan_dev.argtypes = [vp, C.c_int, vp, vp, C.POINTER(KuboSpec), pd, pd, vp]
+    L.wbgpu_kubo_scan_blocks.argtypes = [vp, C.c_int, pd, C.POINTER(KuboSpec), pd, pd, pd]
     L.wbgpu_kpoints.argtypes = [vp, pd, pd]
     L.wbgpu_eig.argtypes = [vp, pd, pd, pd]
     L.wbgpu_xk.argtypes = [vp, pd, C.c_int, pd]
@@ -108,7 +110,8 @@ def lib():
     for name in ("wbgpu_create", "wbgpu_destroy", "wbgpu_set_R_matrix", "wbgpu_plan", "wbgpu_static_scan",
                  "wbgpu_static_scan_dev", "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_xbar", "wbgpu_band_traces",
                  "wbgpu_last_eig_sweeps", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak", "wbgpu_kubo_scan",
-                 "wbgpu_static_scan_tetra", "wbgpu_static_scan_blocks", "wbgpu_kubo_scan_dev"):
+                 "wbgpu_static_scan_tetra", "wbgpu_static_scan_blocks", "wbgpu_kubo_scan_dev", "wbgpu_static_scan_tetra_blocks",
+                 "wbgpu_kubo_scan_blocks"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -119,7 +122,8 @@ EXPORTED = ["wbgpu_last_error", "wbgpu_version", "wbgpu_device_count", "wbgpu_cr
             "wbgpu_kpoints", "wbgpu_eig", "wbgpu_xk", "wbgpu_xbar", "wbgpu_band_traces", "wbgpu_kernel_launches",
             "wbgpu_last_eig_sweeps", "wbgpu_last_eig_resolved", "wbgpu_set_option", "wbgpu_stage_times", "wbgpu_fp64_peak",
             "wbgpu_kubo_size",
-            "wbgpu_kubo_scan", "wbgpu_static_scan_tetra", "wbgpu_static_scan_blocks", "wbgpu_kubo_scan_dev"]
+            "wbgpu_kubo_scan", "wbgpu_static_scan_tetra", "wbgpu_static_scan_blocks", "wbgpu_kubo_scan_dev",
+            "wbgpu_static_scan_tetra_blocks", "wbgpu_kubo_scan_blocks"]
 
 
 def check(status):

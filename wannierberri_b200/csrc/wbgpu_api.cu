@@ -1487,9 +1487,11 @@ extern "C" int wbgpu_static_scan_blocks(wbgpu_ctx* c, int nblocks, const double*
 }
 
 // ------------------------------------------------------------------------------------------ tetrahedron method
-extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* dK, const double* weight, const double* dK_cell,
-                                       const wbgpu_scan_spec* specs, int nspec, double* out) {
-    if (!c || !dK || !weight || !dK_cell || !specs || !out) return set_err("wbgpu_static_scan_tetra: null pointer argument");
+// per_block: one histogram per K-block (no weights), out[nblocks][total]; dK_cell[nblocks][3] then (cell_stride = 3): the
+// K-points of a refinement iteration have cells of different sizes (grid/Kpoint.py:107-109, 145-175)
+static int tetra_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK, const double* weight, const double* dK_cell, int cell_stride,
+                           const wbgpu_scan_spec* specs, int nspec, double* out, bool per_block) {
+    if (!c || !dK || (!weight && !per_block) || !dK_cell || !specs || !out) return set_err("wbgpu_static_scan_tetra: null pointer argument");
     if (!c->planned) return set_err("wbgpu_static_scan_tetra: call wbgpu_plan first");
     if (nblocks < 0 || nspec < 1) return set_err("wbgpu_static_scan_tetra: nblocks=%d nspec=%d", nblocks, nspec);
     CK(cudaSetDevice(c->device));
@@ -1507,9 +1509,10 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
         hoff[i + 1] = hoff[i] + 2 * sz;   // direct | suffix
         nout += sz;
     }
-    if (ensure(&c->d_hist, &c->hist_cap, sizeof(double) * hoff[nspec])) return 1;
-    CK(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * hoff[nspec], c->stream));
-    if (ensure(&c->d_out, &c->out_cap, sizeof(double) * nout)) return 1;
+    const size_t nhist = per_block ? (size_t)c->nb_max : 1;
+    if (ensure(&c->d_hist, &c->hist_cap, sizeof(double) * nhist * hoff[nspec])) return 1;
+    CK(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * nhist * hoff[nspec], c->stream));
+    if (ensure(&c->d_out, &c->out_cap, sizeof(double) * nout * (per_block ? std::max(nblocks, 1) : 1))) return 1;
     // H-only R-space table for the corner energies
     WbLayout LH;
     LH.nw = nw; LH.ntri = nw * (nw + 1) / 2; LH.E = LH.ntri; LH.off_H = 0; LH.dH_herm = 0;
@@ -1541,9 +1544,9 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
         for (int cr = 0; cr < 8; cr++) {
             const int bit[3] = {(cr >> 2) & 1, (cr >> 1) & 1, cr & 1};
             for (int d = 0; d < 3; d++)
-                hdk[3 * ((size_t)(1 + cr) * nbk + b) + d] = dK[3 * b + d] + (bit[d] ? 0.5 : -0.5) * dK_cell[d];
+                hdk[3 * ((size_t)(1 + cr) * nbk + b) + d] = dK[3 * b + d] + (bit[d] ? 0.5 : -0.5) * dK_cell[(size_t)cell_stride * b + d];
         }
-        hdk[(size_t)27 * nbk + b] = weight[b];
+        hdk[(size_t)27 * nbk + b] = per_block ? 1. : weight[b];
     }
     if (ensure(&c->d_dK, &c->dK_cap, sizeof(double) * hdk.size())) return 1;
     CK(cudaMemcpyAsync(c->d_dK, hdk.data(), sizeof(double) * hdk.size(), cudaMemcpyHostToDevice, c->stream));
@@ -1612,18 +1615,50 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
                 const size_t smem = wb_tetra_acc_smem_bytes(nw, s.nEF, ncomp, use_smem);
                 if (smem > 48 * 1024)
                     CK(cudaFuncSetAttribute(wb_tetra_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                const long nblk = std::min(nk, (long)sms * 2);
-                wb_tetra_accumulate_kernel<<<(unsigned)nblk, 128, smem, c->stream>>>(
-                    c->d_evval + G.ev.off[s.formula], G.ev.NC, nw, nk, c->nk_block, c->d_E, c->d_Ec, (long)(nkl * nw), G.win, d_w + b0,
-                    ncomp, (s.tetra_flags & 1) ? -1 : s.fder, s.nEF, s.Ef_first, s.dEF, c->d_hist + hoff[i], use_smem);
-                c->launches++;
+                if (!per_block) {
+                    const long nblk = std::min(nk, (long)sms * 2);
+                    wb_tetra_accumulate_kernel<<<(unsigned)nblk, 128, smem, c->stream>>>(
+                        c->d_evval + G.ev.off[s.formula], G.ev.NC, nw, nk, c->nk_block, c->d_E, c->d_Ec, (long)(nkl * nw), G.win, d_w + b0,
+                        ncomp, (s.tetra_flags & 1) ? -1 : s.fder, s.nEF, s.Ef_first, s.dEF, c->d_hist + hoff[i], use_smem);
+                    c->launches++;
+                    continue;
+                }
+                // one launch per K-block on ITS k-points and ITS histogram (transforms, eigensolves and the event pass above
+                // stay batched over the K-blocks)
+                for (int bk = 0; bk < nb; bk++) {
+                    const size_t ko = (size_t)bk * c->nk_block;
+                    WbWindow wb = G.win;
+                    wb.Ebmin += ko * nw;
+                    wb.Ebmax += ko * nw;
+                    const long nblk = std::min((long)c->nk_block, (long)sms * 2);
+                    wb_tetra_accumulate_kernel<<<(unsigned)nblk, 128, smem, c->stream>>>(
+                        c->d_evval + ko * nw * G.ev.NC + G.ev.off[s.formula], G.ev.NC, nw, (long)c->nk_block, c->nk_block, c->d_E + ko * nw,
+                        c->d_Ec + ko * nw, (long)(nkl * nw), wb, d_w + b0 + bk, ncomp, (s.tetra_flags & 1) ? -1 : s.fder, s.nEF, s.Ef_first,
+                        s.dEF, c->d_hist + (size_t)bk * hoff[nspec] + hoff[i], use_smem);
+                    c->launches++;
+                }
             }
             stage_end(c);
             CK(cudaGetLastError());
         }
+        if (per_block) {   // the histograms of this batch -> out[b0 + bk][...], then cleared for the next batch
+            for (int bk = 0; bk < nb; bk++) {
+                size_t ooff = 0;
+                for (int i = 0; i < nspec; i++) {
+                    const wbgpu_scan_spec& s = specs[i];
+                    const int ncomp = formula_ncomp(s.formula);
+                    const double scale = s.factor / (c->cell_volume * (double)c->nk_block);
+                    wb_tetra_finalize_kernel<<<(unsigned)((ncomp + 31) / 32), 32, 0, c->stream>>>(
+                        c->d_hist + (size_t)bk * hoff[nspec] + hoff[i], s.nEF, ncomp, scale, c->d_out + (size_t)(b0 + bk) * nout + ooff);
+                    c->launches++;
+                    ooff += (size_t)s.nEF * ncomp;
+                }
+            }
+            CK(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * nhist * hoff[nspec], c->stream));
+        }
     }
     size_t ooff = 0;
-    for (int i = 0; i < nspec; i++) {
+    for (int i = 0; i < nspec && !per_block; i++) {
         const wbgpu_scan_spec& s = specs[i];
         const int ncomp = formula_ncomp(s.formula);
         const double scale = s.factor / (c->cell_volume * (double)c->nk_block);
@@ -1632,10 +1667,20 @@ extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* 
         ooff += (size_t)s.nEF * ncomp;
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * nout * (per_block ? nblocks : 1), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     stage_collect(c);
     return 0;
+}
+
+extern "C" int wbgpu_static_scan_tetra(wbgpu_ctx* c, int nblocks, const double* dK, const double* weight, const double* dK_cell,
+                                       const wbgpu_scan_spec* specs, int nspec, double* out) {
+    return tetra_scan_impl(c, nblocks, dK, weight, dK_cell, 0, specs, nspec, out, false);
+}
+
+extern "C" int wbgpu_static_scan_tetra_blocks(wbgpu_ctx* c, int nblocks, const double* dK, const double* dK_cell,
+                                              const wbgpu_scan_spec* specs, int nspec, double* out) {
+    return tetra_scan_impl(c, nblocks, dK, nullptr, dK_cell, 3, specs, nspec, out, true);
 }
 
 // ------------------------------------------------------------------------------------------ Kubo
@@ -1649,8 +1694,9 @@ extern "C" int64_t wbgpu_kubo_size(const wbgpu_kubo_spec* s) {
 }
 
 // dK_dev / weight_dev / out_dev: DEVICE pointers; Efermi / omega: HOST pointers (scan parameters, like the spec)
+// per_block: one accumulator per K-block of a batch, out_dev[nblocks][nout] (weights must be 1): the refinement loop
 static int kubo_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, const double* weight_dev, const wbgpu_kubo_spec* spec,
-                          const double* Efermi, const double* omega, double* out_dev) {
+                          const double* Efermi, const double* omega, double* out_dev, bool per_block = false) {
     if (!c->planned) return set_err("wbgpu_kubo_scan: call wbgpu_plan first");
     const int64_t nout = wbgpu_kubo_size(spec);
     if (nout < 0) return set_err("wbgpu_kubo_scan: bad spec (kind=%d nEF=%d nomega=%d)", spec->kind, spec->nEF, spec->nomega);
@@ -1705,8 +1751,12 @@ static int kubo_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, const
     CK(cudaMemcpyAsync(d_Ef, Efermi, sizeof(double) * nEF, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_om, omega, sizeof(double) * nom, cudaMemcpyHostToDevice, c->stream));
     const size_t nacc = (size_t)nom * nEF * NC;
-    if (ensure(&c->d_kacc, &c->kacc_cap, sizeof(double) * 2 * nacc)) return 1;
-    CK(cudaMemsetAsync(c->d_kacc, 0, sizeof(double) * nacc, c->stream));
+    // accumulators of the K-blocks of a batch (per_block: at most 1 GB of them at a time) + one array for the finalised values
+    const int nbacc = per_block ? (int)std::max<size_t>(1, std::min<size_t>((size_t)c->nb_max, (size_t)(1.0e9 / (8.0 * nacc)))) : 1;
+    if (ensure(&c->d_kacc, &c->kacc_cap, sizeof(double) * ((size_t)nbacc + 1) * nacc)) return 1;
+    CK(cudaMemsetAsync(c->d_kacc, 0, sizeof(double) * (size_t)nbacc * nacc, c->stream));
+    double* const d_fin = c->d_kacc + (size_t)nbacc * nacc;
+    const double scale = spec->factor / (c->cell_volume * (double)c->nk_block);
 
     const int nwtile = (nom + WB_KUBO_WT - 1) / WB_KUBO_WT;
     const int nthreads = wb_kubo_tpw(spec->kind) * WB_KUBO_WT;
@@ -1740,8 +1790,9 @@ static int kubo_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, const
     if (smem_ent > 48 * 1024)
         CK(cudaFuncSetAttribute(wb_kubo_entries_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ent));
 
-    for (int b0 = 0; b0 < nblocks; b0 += c->nb_max) {
-        const int nb = std::min(c->nb_max, nblocks - b0);
+    const int nbstep = per_block ? std::min(c->nb_max, nbacc) : c->nb_max;
+    for (int b0 = 0; b0 < nblocks; b0 += nbstep) {
+        const int nb = std::min(nbstep, nblocks - b0);
         const long nk = (long)nb * c->nk_block;
         stage_begin(c, WBGPU_STAGE_FOURIER);
         if (run_fourier(c, dK_dev + 3 * (size_t)b0, nb)) return 1;
@@ -1776,31 +1827,54 @@ static int kubo_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, const
             wb_kubo_entries_kernel<128><<<(unsigned)std::min(n, (long)sms * 8), 128, smem_ent, c->stream>>>(
                 (const cplx*)c->d_xbar, ch.n, nw, n, k0, c->d_E + k0 * nw, win, P, d_Ef, d_w + b0, c->nk_block, c->d_kent, d_count, cap,
                 (const cplx*)c->d_shcJ);
-            const int nsplit = (int)std::max(1L, std::min(n, (long)((6 * sms + nwtile - 1) / nwtile)));
-            dim3 grid((unsigned)nwtile, (unsigned)nsplit);
-            if (optcond && c->kubo_method != 1) {
-                const int ntile = (nom + WB_KUBO_TW - 1) / WB_KUBO_TW;
-                dim3 gridt((unsigned)ntile, (unsigned)std::max(1L, std::min(n, (long)((12 * sms + ntile - 1) / ntile))));
-                wb_kubo_accumulate_optcond_tiled_kernel<<<gridt, 144, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
-            } else if (optcond)
-                wb_kubo_accumulate_kernel<0><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
-            else if (shc || shift)
-                wb_kubo_accumulate_kernel<2><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
-            else if (inject)
-                wb_kubo_accumulate_kernel<3><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
-            else
-                wb_kubo_accumulate_kernel<1><<<grid, nthreads, 0, c->stream>>>(c->d_kent, d_count, cap, n, P, d_om, d_Ef, c->d_kacc);
-            c->launches += 2;
+            // accumulation of the k-points [ka, ka + na) of this chunk into `acc`
+            auto accumulate = [&](long ka, long na, double* acc) {
+                const double* ent = c->d_kent + (size_t)ka * cap * ENT;
+                const int* cnt = d_count + ka;
+                const int nsplit = (int)std::max(1L, std::min(na, (long)((6 * sms + nwtile - 1) / nwtile)));
+                dim3 grid((unsigned)nwtile, (unsigned)nsplit);
+                if (optcond && c->kubo_method != 1) {
+                    const int ntile = (nom + WB_KUBO_TW - 1) / WB_KUBO_TW;
+                    dim3 gridt((unsigned)ntile, (unsigned)std::max(1L, std::min(na, (long)((12 * sms + ntile - 1) / ntile))));
+                    wb_kubo_accumulate_optcond_tiled_kernel<<<gridt, 144, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
+                } else if (optcond)
+                    wb_kubo_accumulate_kernel<0><<<grid, nthreads, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
+                else if (shc || shift)
+                    wb_kubo_accumulate_kernel<2><<<grid, nthreads, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
+                else if (inject)
+                    wb_kubo_accumulate_kernel<3><<<grid, nthreads, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
+                else
+                    wb_kubo_accumulate_kernel<1><<<grid, nthreads, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
+                c->launches++;
+            };
+            if (!per_block) accumulate(0, n, c->d_kacc);
+            else   // the part of every K-block of the batch that lies in this chunk, into that block's accumulator
+                for (long bk = k0 / c->nk_block; bk * c->nk_block < k0 + n; bk++) {
+                    const long ka = std::max(k0, bk * (long)c->nk_block), kb = std::min(k0 + n, (bk + 1) * (long)c->nk_block);
+                    accumulate(ka - k0, kb - ka, c->d_kacc + (size_t)bk * nacc);
+                }
+            c->launches++;
             stage_end(c);
             CK(cudaGetLastError());
         }
+        if (per_block) {   // this batch's accumulators -> out_dev[b0 + bk][nout], then cleared
+            for (int bk = 0; bk < nb; bk++) {
+                wb_kubo_finalize_kernel<<<(unsigned)(((size_t)nom * NC + 127) / 128), 128, 0, c->stream>>>(
+                    c->d_kacc + (size_t)bk * nacc, nom, nEF, NC, scale, d_fin, shift ? 1 : 0);
+                c->launches++;
+                CK(cudaMemcpyAsync(out_dev + (size_t)(b0 + bk) * nout, d_fin, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            CK(cudaMemsetAsync(c->d_kacc, 0, sizeof(double) * (size_t)nbacc * nacc, c->stream));
+        }
     }
-    const double scale = spec->factor / (c->cell_volume * (double)c->nk_block);
-    wb_kubo_finalize_kernel<<<(unsigned)(((size_t)nom * NC + 127) / 128), 128, 0, c->stream>>>(c->d_kacc, nom, nEF, NC, scale,
-                                                                                                    c->d_kacc + nacc, shift ? 1 : 0);
-    c->launches++;
+    if (!per_block) {
+        wb_kubo_finalize_kernel<<<(unsigned)(((size_t)nom * NC + 127) / 128), 128, 0, c->stream>>>(c->d_kacc, nom, nEF, NC, scale, d_fin,
+                                                                                                        shift ? 1 : 0);
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out_dev, d_fin, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToDevice, c->stream));
+    }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out_dev, c->d_kacc + nacc, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToDevice, c->stream));
     stage_collect(c);
     return 0;
 }
@@ -1826,6 +1900,25 @@ extern "C" int wbgpu_kubo_scan(wbgpu_ctx* c, int nblocks, const double* dK, cons
     CK(cudaMemcpyAsync(d_w, weight, sizeof(double) * nblocks, cudaMemcpyHostToDevice, c->stream));
     if (kubo_scan_impl(c, nblocks, c->d_dK, d_w, spec, Efermi, omega, c->d_out)) return 1;
     CK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int wbgpu_kubo_scan_blocks(wbgpu_ctx* c, int nblocks, const double* dK, const wbgpu_kubo_spec* spec, const double* Efermi,
+                                      const double* omega, double* out) {
+    if (!c || !dK || !spec || !Efermi || !omega || !out) return set_err("wbgpu_kubo_scan_blocks: null pointer argument");
+    const int64_t nout = wbgpu_kubo_size(spec);
+    if (nout < 0) return set_err("wbgpu_kubo_scan: bad spec (kind=%d nEF=%d nomega=%d)", spec->kind, spec->nEF, spec->nomega);
+    CK(cudaSetDevice(c->device));
+    const int nbk = std::max(nblocks, 1);
+    if (ensure(&c->d_dK, &c->dK_cap, sizeof(double) * 4 * (size_t)nbk)) return 1;
+    if (ensure(&c->d_out, &c->out_cap, sizeof(double) * (size_t)nout * nbk)) return 1;
+    double* d_w = c->d_dK + 3 * (size_t)nbk;
+    std::vector<double> ones((size_t)nbk, 1.);
+    CK(cudaMemcpyAsync(c->d_dK, dK, sizeof(double) * 3 * nblocks, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_w, ones.data(), sizeof(double) * nblocks, cudaMemcpyHostToDevice, c->stream));
+    if (kubo_scan_impl(c, nblocks, c->d_dK, d_w, spec, Efermi, omega, c->d_out, true)) return 1;
+    CK(cudaMemcpyAsync(out, c->d_out, sizeof(double) * (size_t)nout * nblocks, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -106,6 +106,21 @@ class Engine:
             off += s.size
         return res
 
+    def scan_tetra_blocks(self, dK, dK_cell, specs):
+        """Per-K-block tetrahedron scans (refinement loop): `dK_cell[nblocks][3]`, list of `[nblocks, nEF, 3^rank]`."""
+        dK = as_f64(dK).reshape(-1, 3)
+        nb = dK.shape[0]
+        dK_cell = as_f64(np.broadcast_to(np.asarray(dK_cell, dtype=float), (nb, 3)))
+        arr = (ScanSpec * len(specs))(*specs)
+        total = sum(s.size for s in specs)
+        out = np.zeros((nb, total))
+        check(self._L.wbgpu_static_scan_tetra_blocks(self._ctx, nb, dptr(dK), dptr(dK_cell), arr, len(specs), dptr(out)))
+        res, off = [], 0
+        for s in specs:
+            res.append(out[:, off:off + s.size].reshape((nb,) + s.shape).copy())
+            off += s.size
+        return res
+
     def scan_dev(self, dK_dev, weight_dev, specs, out_dev):
         """Device-resident variant: torch CUDA tensors (float64) for dK[nb,3], weight[nb], out[sum sizes];
         asynchronous on the context's stream."""
@@ -128,6 +143,18 @@ class Engine:
         if spec.is_complex:
             return out.view(np.complex128).reshape(spec.shape)
         return out.reshape(spec.shape)
+
+    def kubo_scan_blocks(self, dK, spec, Efermi, omega):
+        """Per-K-block Kubo scans (refinement loop): `[nblocks, nEF, nomega, ...]`."""
+        dK = as_f64(dK).reshape(-1, 3)
+        nb = dK.shape[0]
+        Efermi, omega = as_f64(Efermi), as_f64(omega)
+        n = int(self._L.wbgpu_kubo_size(C.byref(spec)))
+        out = np.zeros((nb, n))
+        check(self._L.wbgpu_kubo_scan_blocks(self._ctx, nb, dptr(dK), C.byref(spec), dptr(Efermi), dptr(omega), dptr(out)))
+        if spec.is_complex:
+            return [out[b].view(np.complex128).reshape(spec.shape).copy() for b in range(nb)]
+        return [out[b].reshape(spec.shape).copy() for b in range(nb)]
 
     def kubo_scan_dev(self, dK_dev, weight_dev, spec, Efermi, omega, out_dev):
         """Device-resident variant of `kubo_scan`: torch CUDA tensors (float64) for dK[nb,3], weight[nb] and the flat

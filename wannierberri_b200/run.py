@@ -242,7 +242,7 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
     system = as_system(system)
     pointgroup = _pointgroup_of(system)
     periodic = getattr(system, "periodic", (True, True, True))
-    calcs, slow_calcs = {}, {}   # slow: tetrahedron / Kubo calculators, evaluated one K-point per call
+    calcs, slow_calcs = {}, {}   # slow: tetrahedron / Kubo calculators (their own per-K-block entry points)
     for key, c in calculators.items():
         if isinstance(c, _dyn.DynamicCalculator) or (type(c).__name__ in _dyn._BY_NAME and hasattr(c, "omega")
                                                        and not hasattr(c, "fder")):
@@ -306,13 +306,18 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
     engine = engine_for(system, device)
     engine.plan(NKFFT, flags, external_terms=external)
 
-    def eval_slow(key, K):
-        """one K-point through the tetrahedron / Kubo scans (per-K-point cell K.dK_fullBZ, grid/Kpoint.py:107-109)"""
+    def eval_slow_batch(key, Ks):
+        """all new K-points of this rank through the tetrahedron / Kubo scans in ONE call (per-K-block histograms /
+        accumulators in the library: wbgpu_static_scan_tetra_blocks, wbgpu_kubo_scan_blocks)"""
+        if not Ks:
+            return []
         c, sp = slow_calcs[key], slow_specs[key]
-        dK = np.array(K.Kp_fullBZ, dtype=float)[None, :]
+        dK = np.array([K.Kp_fullBZ for K in Ks], dtype=float).reshape(-1, 3)
         if isinstance(c, _dyn.DynamicCalculator):
-            return [np.ascontiguousarray(engine.kubo_scan(dK, np.ones(1), sp[0], c.Efermi, c.omega))]
-        return engine.scan_tetra(dK, np.ones(1), np.array(K.dK_fullBZ, dtype=float), sp)
+            return [[np.ascontiguousarray(a)] for a in engine.kubo_scan_blocks(dK, sp[0], c.Efermi, c.omega)]
+        cells = np.array([K.dK_fullBZ for K in Ks], dtype=float).reshape(-1, 3)
+        per_spec = engine.scan_tetra_blocks(dK, cells, sp)
+        return [[a[j] for a in per_spec] for j in range(len(Ks))]
 
     result_all = None
     factors_old = None
@@ -333,7 +338,7 @@ def _run_adaptive(system, grid, calculators, adpt_num_iter, adpt_mesh, adpt_fac,
         mine = engine.scan_blocks(dK_new[lo:hi], specs) if (hi > lo and specs) else [np.zeros((0,) + s.shape) for s in specs]
         slow = {}   # key -> list over the new K-points of this rank's shard of [array per spec]
         for key in slow_calcs:
-            slow[key] = [eval_slow(key, K_list[i]) for i in new[lo:hi]]
+            slow[key] = eval_slow_batch(key, [K_list[i] for i in new[lo:hi]])
         if dist and world > 1 and slow_calcs:
             import torch
             dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
