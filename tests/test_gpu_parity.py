@@ -390,6 +390,24 @@ def test_second_order_calculators_through_run(wb, fe):
         assert r.transformTR == parity[int(g[key + "_TR"])] and r.transformInv == parity[int(g[key + "_Inv"])], key
 
 
+def test_second_order_calculators_vs_oracle(wb, te, te_orc, orc):
+    """the second-order calculators on ANOTHER system and grid than the fixture (Te, 24 WF, 2 x 2 x 3 K-blocks of 2 x 2 x 1):
+    GPU path against the oracle's per-group restatement (oracle/wb_oracle.py: _Cov, Der2Spin, Der2Omega, emcha_surf, tildeFab,
+    VelDQM), which is itself pinned on the reference fixture (tests/test_oracle.py::test_second_order_formulae_vs_reference)"""
+    st = wb.calculators.static
+    Ef = np.linspace(5.0, 7.0, 9)
+    ff = dict(FF_rotAA=True)
+    calcs = dict(z_spin=st.NLDrude_Zeeman_spin(Efermi=Ef), z_orb_omega=st.NLDrude_Zeeman_orb_Omega(Efermi=Ef),
+                 emcha=st.eMChA_FermiSurf(Efermi=Ef), qmetric=st.QuantumMetric_FermiSea(Efermi=Ef, kwargs_formula=ff),
+                 qmetric_dip=st.QuantumMetric_Vel_DQ(Efermi=Ef, kwargs_formula=ff))
+    names = dict(z_spin="NLDrude_Zeeman_spin", z_orb_omega="NLDrude_Zeeman_orb_Omega", emcha="eMChA_FermiSurf",
+                 qmetric="QuantumMetric_FermiSea", qmetric_dip="QuantumMetric_Vel_DQ")
+    res = wb.run(te, wb.Grid(te, NKdiv=[2, 2, 3], NKFFT=[2, 2, 1]), calcs, use_irred_kpt=False, symmetrize=False, write_files=False)
+    ref = orc.run(te_orc, [2, 2, 3], [2, 2, 1], {k: (names[k], Ef, {}) for k in calcs})
+    for key in calcs:
+        assert relerr(res.results[key].data, ref[key]) < RTOL, (key, relerr(res.results[key].data, ref[key]))
+
+
 @pytest.mark.parametrize("nw", [4, 6, 8, 10, 12, 14, 16, 20, 22, 24])
 def test_fused_rotation_kernel_sizes(wb, nw):
     """The compile-time-num_wann DMMA rotation + formula kernel (rotate_method 3; every even num_wann <= 24) against the
