@@ -398,9 +398,10 @@ def test_second_order_calculators_vs_oracle(wb, te, te_orc, orc):
     Ef = np.linspace(5.0, 7.0, 9)
     ff = dict(FF_rotAA=True)
     calcs = dict(z_spin=st.NLDrude_Zeeman_spin(Efermi=Ef), z_orb_omega=st.NLDrude_Zeeman_orb_Omega(Efermi=Ef),
+                 z_orb=st.NLDrude_Zeeman_orb(Efermi=Ef),
                  emcha=st.eMChA_FermiSurf(Efermi=Ef), qmetric=st.QuantumMetric_FermiSea(Efermi=Ef, kwargs_formula=ff),
                  qmetric_dip=st.QuantumMetric_Vel_DQ(Efermi=Ef, kwargs_formula=ff))
-    names = dict(z_spin="NLDrude_Zeeman_spin", z_orb_omega="NLDrude_Zeeman_orb_Omega", emcha="eMChA_FermiSurf",
+    names = dict(z_spin="NLDrude_Zeeman_spin", z_orb_omega="NLDrude_Zeeman_orb_Omega", z_orb="NLDrude_Zeeman_orb", emcha="eMChA_FermiSurf",
                  qmetric="QuantumMetric_FermiSea", qmetric_dip="QuantumMetric_Vel_DQ")
     res = wb.run(te, wb.Grid(te, NKdiv=[2, 2, 3], NKFFT=[2, 2, 1]), calcs, use_irred_kpt=False, symmetrize=False, write_files=False)
     ref = orc.run(te_orc, [2, 2, 3], [2, 2, 1], {k: (names[k], Ef, {}) for k in calcs})

@@ -441,14 +441,15 @@ def test_tetra_hole_like_and_emin_vs_reference():
 
 
 def test_second_order_formulae_vs_reference(fe):
-    """Der2Spin / Der2Omega (Der2Dcov, Der2A, Der2O) / emcha_surf / tildeFab / tildeFab_d and the calculators built on them
-    (NLDrude_Zeeman_spin, NLDrude_Zeeman_orb_Omega, eMChA_FermiSurf, QuantumMetric_FermiSea, QuantumMetric_Vel_DQ) against the
+    """Der2Spin / Der2Omega (Der2Dcov, Der2A, Der2O) / Der2Morb (Der2B, Der2H) / emcha_surf / tildeFab / tildeFab_d and the calculators built on them
+    (NLDrude_Zeeman_spin, NLDrude_Zeeman_orb_Omega, NLDrude_Zeeman_orb, eMChA_FermiSurf, QuantumMetric_FermiSea, QuantumMetric_Vel_DQ) against the
     fixture of the unmodified reference (tests/golden/make_golden_second_order.py): external terms on and off, wide
     Kramers-paired band groups."""
     g = np.load(os.path.join(GOLDEN, "golden_second_order.npz"))
     Ef = g["Efermi"]
     cases = dict(z_spin=("NLDrude_Zeeman_spin", {}), z_orb_omega=("NLDrude_Zeeman_orb_Omega", {}), emcha=("eMChA_FermiSurf", {}),
                  qmetric=("QuantumMetric_FermiSea", {}), qmetric_dip=("QuantumMetric_Vel_DQ", {}),
+                 z_orb=("NLDrude_Zeeman_orb", {}), z_orb_int=("NLDrude_Zeeman_orb", dict(kwargs_formula=dict(external_terms=False))),
                  emcha_int=("eMChA_FermiSurf", dict(kwargs_formula=dict(external_terms=False))),
                  qmetric_int=("QuantumMetric_FermiSea", dict(kwargs_formula=dict(external_terms=False))),
                  z_spin_wide=("NLDrude_Zeeman_spin", dict(degen_thresh=0.3, degen_Kramers=True)),
