@@ -1,12 +1,14 @@
 // Batched complex Hermitian eigensolver for 32 < nw <= 128: the same zhetd2 + tql2 + zunm2l sequence as
 // wb_eigh_ql.cuh, with ONE CTA PER K-POINT for the two matrix phases (the matrix lives in shared memory):
 //
-//   K1L  wb_tridiag_cta_kernel   packed lower triangle of H(k) in shared memory (132 KB at nw = 128), thread pair per
-//                                row; Hermitian matvec + rank-2 update per Householder step.
-//   K2   wb_tql_kernel           (wb_eigh_ql.cuh) thread per k-point implicit QL, streams its Givens rotations.
-//   K3L  wb_eigvec_cta_kernel    real Z (nw x nw doubles, 128 KB at nw = 128) in shared memory, thread = row: replay of
-//                                the rotation stream; sort; back-transformation by the Householder reflectors in
-//                                panels of 16 eigenvectors; writes E (ascending) and U.
+//   K1L  wb_tridiag_cta_kernel   packed lower triangle of H(k) in shared memory (132 KB at nw = 128); Hermitian matvec (2 / 4 /
+//                                8 threads per ACTIVE row) + rank-2 update (complementary row pairs) per Householder step.
+//   K2   wb_tql_kernel           (wb_eigh_ql.cuh) thread per k-point implicit QL: eigenvalues; streams its Givens rotations
+//                                (used by the fallback of K3L only).
+//   K3L  wb_eigvec_cta_kernel    eigenvectors of T by twisted factorisation (thread per eigenvalue, Zt in shared memory,
+//                                128 KB at nw = 128); matrices it cannot resolve: replay of the rotation stream (thread =
+//                                row of Z); back-transformation by the Householder reflectors with the eigenvector slices
+//                                in registers, panels of NT / 8 eigenvectors; writes E (ascending) and U.
 //
 // Replaces  E_K, UU_K = np.linalg.eigh(HH_K)   (data_K/data_K.py:211-218, 309-322).
 #pragma once
@@ -428,7 +430,7 @@ wb_eigvec_cta_kernel(int n, long k0, long nk, const double* __restrict__ dvals, 
             }
         }
         __syncthreads();
-        // ---- back-transformation  u <- H(0) H(1) ... H(n-2) u  in panels of 16 eigenvectors (sorted order)
+        // ---- back-transformation  u <- H(0) H(1) ... H(n-2) u  in panels of PW eigenvectors (sorted order)
         const cplx* Vt = Vh + (size_t)t * n * n;
         const int c = tid >> 3, sl = tid & 7;
         // Thread (c, sl) keeps the elements i = sl + 8 e of eigenvector c of the panel in REGISTERS for all n - 1 reflectors
