@@ -733,8 +733,20 @@ def test_shift_and_injection_current_synthetic(wb, orc, nw, nom):
     kw = dict(smr_fixed_width=0.1, smr_type="Lorentzian")
     got = wb.calculators.dynamic.ShiftCurrent(Efermi=Ef, omega=om, sc_eta=0.05, **kw)(data).data
     assert relerr(got, orc.ShiftCurrent(odata, Ef, omega=om, sc_eta=0.05, **kw)) < RTOL
-    got = wb.calculators.dynamic.InjectionCurrent(Efermi=Ef, omega=om, **kw)(data).data
-    assert relerr(got, orc.InjectionCurrent(odata, Ef, omega=om, **kw)) < RTOL
+    got2 = wb.calculators.dynamic.InjectionCurrent(Efermi=Ef, omega=om, **kw)(data).data
+    assert relerr(got2, orc.InjectionCurrent(odata, Ef, omega=om, **kw)) < RTOL
+    # the per-(omega, component) accumulation kernel (kubo_method 1) against the register-tiled one (default), also at kBT > 0
+    for kbt in (0., 0.05):
+        res = {}
+        for method in (0, 1):
+            data.engine.set_option("kubo_method", method)
+            res[method] = [wb.calculators.dynamic.ShiftCurrent(Efermi=Ef, omega=om, sc_eta=0.05, kBT=kbt, **kw)(data).data,
+                           wb.calculators.dynamic.InjectionCurrent(Efermi=Ef, omega=om, kBT=kbt, **kw)(data).data,
+                           wb.calculators.dynamic.SHC(Efermi=Ef, omega=om, SHC_type="simple", kBT=kbt, **kw)(data).data
+                           if sysg.has_R_mat("SS") else np.ones(1)]
+        data.engine.set_option("kubo_method", 0)
+        for a, b in zip(res[0], res[1]):
+            assert relerr(a, b) < 1e-11, kbt
 
 
 KBT_CASES = dict(

@@ -671,6 +671,121 @@ wb_kubo_accumulate_optcond_tiled_kernel(const double* __restrict__ entries, cons
     }
 }
 
+// Rank-3 kinds (spin Hall / shift current: KIND 2, injection current: KIND 3), register-tiled like the kernel above:
+// thread = (group of 4 frequencies, component c of 27), CTA = 64 frequencies x 27 components = 432 threads; per entry a
+// thread loads its component's two matrix elements once and the frequency factors of its 4 frequencies (group-minor
+// layout, broadcast among the 27 threads of a group): 10 shared-memory loads per 16 DFMA instead of 4 per 4.
+template <int KIND>
+__global__ void __launch_bounds__(432)
+wb_kubo_accumulate_rank3_tiled_kernel(const double* __restrict__ entries, const int* __restrict__ count, int cap, long nk,
+                                      WbKuboParams P, const double* __restrict__ omega, const double* __restrict__ Ef,
+                                      double* __restrict__ Dglob) {
+    static_assert(KIND == 2 || KIND == 3, "spin Hall / shift current (2), injection current (3)");
+    constexpr int WT = WB_KUBO_TW, CH = WB_KUBO_TCHUNK, NT = 432, ENT = WB_SHC_ENT, NC = 54;
+    static_assert(WT == 64, "layout of Wb: 16 frequency groups of 4");
+    __shared__ __align__(16) double ent[CH * ENT];
+    __shared__ __align__(16) double Wb[CH * WT * 4];
+    const int w0 = blockIdx.x * WT, nwt = min(WT, P.nomega - w0);
+    const int tid = threadIdx.x;
+    const int grp = tid / 27, c = tid - 27 * grp;            // frequencies w0 + 4 grp .. + 3
+    const int ct = (c / 9) * 9 + (c % 3) * 3 + (c / 3) % 3;   // KIND 3: component (a, c, b) of (a, b, c)
+    const int nmine = max(0, min(4, nwt - 4 * grp));
+    for (long ik = blockIdx.y; ik < nk; ik += gridDim.y) {
+        const int cnt = count[ik];
+        const double* src = entries + (size_t)ik * cap * ENT;
+        double Yr[4] = {0., 0., 0., 0.}, Yi[4] = {0., 0., 0., 0.};
+        double curown = -CUDART_INF;
+        bool have = false;
+        auto flush = [&]() {
+            if (!have) return;
+            for (int q = 0; q < nmine; q++) {
+                if (Yr[q] == 0. && Yi[q] == 0.) continue;
+                double* col = Dglob + ((size_t)(w0 + 4 * grp + q) * P.nEF) * NC + 2 * c;
+                if (P.kBT == 0.) {
+                    const size_t o = (size_t)(int)curown * NC;
+                    if (Yr[q] != 0.) atomicAdd(col + o, Yr[q]);
+                    if (Yi[q] != 0.) atomicAdd(col + o + 1, Yi[q]);
+                    continue;
+                }
+                const double E = curown, top = E + 30. * P.kBT;
+                double prev = 0.;
+                for (int i = wb_lower_bound(Ef, P.nEF, E - 30. * P.kBT); i < P.nEF; i++) {
+                    const double mu = Ef[i];
+                    const double f = (mu > top) ? 1. : 1. / (exp((E - mu) / P.kBT) + 1.);
+                    const double d = f - prev;
+                    prev = f;
+                    atomicAdd(col + (size_t)i * NC, Yr[q] * d);
+                    atomicAdd(col + (size_t)i * NC + 1, Yi[q] * d);
+                    if (mu > top) break;
+                }
+            }
+        };
+        for (int p0 = 0; p0 < cnt; p0 += CH) {
+            const int np = min(CH, cnt - p0);
+            __syncthreads();
+            for (int x = tid; x < np * ENT; x += NT) ent[x] = src[(size_t)p0 * ENT + x];
+            __syncthreads();
+            // frequency factors (the formulas of wb_kubo_accumulate_kernel), zero beyond the end of the axis; position
+            // 16 q + grp of the row holds frequency 4 grp + q
+            for (int x = tid; x < np * WT; x += NT) {
+                const int p = x / WT, pos = x - p * WT;
+                const int w = ((pos & 15) << 2) + (pos >> 4);
+                double* o = Wb + (p * WT + pos) * 4;
+                o[0] = o[1] = o[2] = o[3] = 0.;
+                if (w < nwt) {
+                    const double dl = ent[p * ENT], om = omega[w0 + w];
+                    if (KIND == 2 && P.kind == 3) {          // ShiftCurrent.factor_omega (dynamic.py:319-322)
+                        o[0] = wb_kubo_smear(-dl - om, P.eta, P.smr_type) + wb_kubo_smear(dl - om, P.eta, P.smr_type);
+                    } else if (KIND == 2) {                  // SHC.factor_omega (dynamic.py:232-237)
+                        const cplx c1 = wb_kubo_cfac(-dl - om, P.eta, P.smr_type);
+                        const cplx c2 = wb_kubo_cfac(dl - om, P.eta, P.smr_type);
+                        o[0] = -0.5 * c1.x; o[1] = -0.5 * c1.y;
+                        o[2] = 0.5 * c2.x; o[3] = 0.5 * c2.y;
+                    } else {                                 // InjectionCurrent.factor_omega (dynamic.py:363-365)
+                        o[0] = -wb_kubo_smear(-dl - om, P.eta, P.smr_type);
+                        o[1] = -wb_kubo_smear(dl - om, P.eta, P.smr_type);
+                    }
+                }
+            }
+            __syncthreads();
+            if (grp < 16) {
+                for (int p = 0; p < np; p++) {
+                    const double* e = ent + p * ENT;
+                    const double own = e[1];
+                    if (!have || own != curown) {   // uniform
+                        flush();
+                        curown = own;
+                        have = true;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) Yr[q] = Yi[q] = 0.;
+                    }
+                    const double* Wp = Wb + (p * WT + grp) * 4;
+                    if (KIND == 2) {
+                        const double m1 = e[2 + c], m2 = e[29 + c];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const double2 Wa = *reinterpret_cast<const double2*>(Wp + 64 * q);
+                            const double2 Wc = *reinterpret_cast<const double2*>(Wp + 64 * q + 2);
+                            Yr[q] += Wa.x * m1 + Wc.x * m2;
+                            Yi[q] += Wa.y * m1 + Wc.y * m2;
+                        }
+                    } else {
+                        const double2 M = *reinterpret_cast<const double2*>(e + 2 + 2 * c);
+                        const double2 Mt = *reinterpret_cast<const double2*>(e + 2 + 2 * ct);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const double2 Wa = *reinterpret_cast<const double2*>(Wp + 64 * q);
+                            Yr[q] += Wa.x * M.x + Wa.y * Mt.x;
+                            Yi[q] += Wa.x * M.y + Wa.y * Mt.y;
+                        }
+                    }
+                }
+            }
+        }
+        if (grp < 16) flush();
+    }
+}
+
 // D holds differences along Efermi: value[iw][iEf][c] = sum_{f <= iEf} D[iw][f][c].  JDOS (NC = 1) and spin Hall
 // (NC = 54 = [a][b][s][re | im]): out = scale * value.
 // Optical conductivity (NC = 18): slots (ab, ba), a < b hold P = X[ab] + X[ba] and Q = X[ab] - X[ba]:

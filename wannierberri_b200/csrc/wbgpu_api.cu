@@ -116,7 +116,7 @@ struct wbgpu_ctx {
                             // 3 = compile-time-NW DMMA kernel, 4 = batched DMMA GEMM to global memory + formula kernel
     int smem_optin = 0;
     int rot_r2 = -1;        // experiment: override of the step-2 warp rotation of the fused rotation kernel
-    int kubo_method = 0;    // 0 = register-tiled accumulation of the optical conductivity, 1 = per-(omega, re|im) kernel
+    int kubo_method = 0;    // 0 = register-tiled accumulation kernels, 1 = per-(omega, component) kernel
     int rotate_trim = 1;    // 1 = form only the needed columns of the rotated matrices when they are hermitian
     int dh_packed = 1;      // 1 = pack d_a H as a triangle when it is hermitian in R-space, 0 = never
     int gemm_stack = 1;     // 1 = the size-generic rotation stacks several channels per CTA when nw <= 32
@@ -1839,7 +1839,12 @@ static int kubo_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, const
                     wb_kubo_accumulate_optcond_tiled_kernel<<<gridt, 144, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
                 } else if (optcond)
                     wb_kubo_accumulate_kernel<0><<<grid, nthreads, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
-                else if (shc || shift)
+                else if ((shc || shift || inject) && c->kubo_method != 1) {
+                    const int ntile = (nom + WB_KUBO_TW - 1) / WB_KUBO_TW;
+                    dim3 gridt((unsigned)ntile, (unsigned)std::max(1L, std::min(na, (long)((8 * sms + ntile - 1) / ntile))));
+                    if (inject) wb_kubo_accumulate_rank3_tiled_kernel<3><<<gridt, 432, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
+                    else wb_kubo_accumulate_rank3_tiled_kernel<2><<<gridt, 432, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
+                } else if (shc || shift)
                     wb_kubo_accumulate_kernel<2><<<grid, nthreads, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
                 else if (inject)
                     wb_kubo_accumulate_kernel<3><<<grid, nthreads, 0, c->stream>>>(ent, cnt, cap, na, P, d_om, d_Ef, acc);
