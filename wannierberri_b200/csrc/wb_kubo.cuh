@@ -363,7 +363,7 @@ wb_shc_spinvel_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, c
 template <int NT>
 __global__ void __launch_bounds__(NT)
 wb_shift_agen_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, const double* __restrict__ Eall, int iW, int iA,
-                     int idA, double sc_eta, cplx* __restrict__ Gout) {
+                     int idA, double sc_eta, cplx* __restrict__ Gout, int stage) {
     extern __shared__ __align__(16) double smem_sv[];
     double* Es = smem_sv;
     const int n2 = nw * nw;
@@ -375,7 +375,19 @@ wb_shift_agen_kernel(const cplx* __restrict__ xbar, int nch, int nw, long nk, co
         const cplx* X = xbar + (size_t)ik * nch * n2;
         const cplx* V = X;   // d_a H is the first triple of the record
         cplx* Gk = Gout + (size_t)ik * 9 * n2;
+        // P_lq^a once per k-point in shared memory when the launch reserved 3 nw^2 complex behind Es (`stage`): the inner
+        // loop below evaluated it -- a division each -- twice per partner band
+        cplx* const Ps = (cplx*)(Es + ((nw + 1) & ~1));
+        if (stage) {
+            for (int x = threadIdx.x; x < 3 * n2; x += NT) {
+                const int lq = x % n2;
+                const double d = Es[lq / nw] - Es[lq % nw];
+                Ps[x] = cscale(-d / (d * d + eta2), V[x]);
+            }
+            __syncthreads();
+        }
         auto Pv = [&](int a, int l, int q) {
+            if (stage) return Ps[a * n2 + l * nw + q];
             const double d = Es[l] - Es[q];
             return cscale(-d / (d * d + eta2), V[(size_t)a * n2 + l * nw + q]);
         };

@@ -1817,8 +1817,14 @@ static int kubo_scan_impl(wbgpu_ctx* c, int nblocks, const double* dK_dev, const
                     c->launches++;
                 }
                 if (shift) {
-                    wb_shift_agen_kernel<256><<<(unsigned)std::min(n, (long)sms * 8), 256, sizeof(double) * nw, c->stream>>>(
-                        (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, iW, sc.iA, idA, spec->sc_eta, (cplx*)c->d_shcJ);
+                    // (P_lq^a staged in shared memory when four CTAs per SM still fit)
+                    const size_t sm_p = sizeof(double) * ((nw + 1) & ~1) + sizeof(cplx) * 3 * (size_t)nw * nw;
+                    const int stage = sm_p <= (size_t)c->smem_optin / 4 - 1024;
+                    const size_t sm_agen = stage ? sm_p : sizeof(double) * nw;
+                    if (sm_agen > 48 * 1024)
+                        CK(cudaFuncSetAttribute(wb_shift_agen_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_agen));
+                    wb_shift_agen_kernel<256><<<(unsigned)std::min(n, (long)sms * 8), 256, sm_agen, c->stream>>>(
+                        (const cplx*)c->d_xbar, ch.n, nw, n, c->d_E + k0 * nw, iW, sc.iA, idA, spec->sc_eta, (cplx*)c->d_shcJ, stage);
                     c->launches++;
                 }
                 stage_end(c);
