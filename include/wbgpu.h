@@ -22,6 +22,9 @@
  *   wbgpu_static_scan(_dev)            <- paralfunc + StaticCalculator.__call__ over a list of K-blocks
  *                                         (run_grid.py:258-265,59-72; calculators/static.py:60-169)
  *   wbgpu_static_scan_tetra            <- the same with tetra=True (Data_K.tetraWeights, grid/tetrahedron.py)
+ *   wbgpu_static_scan_blocks, wbgpu_static_scan_tetra_blocks, wbgpu_kubo_scan_blocks
+ *                                      <- the same per K-block: Kpoint.set_result of the refinement loop
+ *                                         (run_grid.py:59-72,343-375; grid/Kpoint.py:35-38,85-92,145-175)
  *   wbgpu_eig                          <- Data_K.E_K (data_K/data_K.py:211-218)
  *   wbgpu_xbar                         <- Data_K_R.Xbar / Data_K._rotate (data_K/data_K_R.py:69-97, data_K/data_K.py:130-132)
  *   wbgpu_xk                           <- Rvectors.R_to_k / FFT_R_to_k.__call__
