@@ -187,6 +187,8 @@ extern "C" int wbgpu_device_count(void) {
     return n;
 }
 
+static int create_fill(wbgpu_ctx* c, int device, int nw, int nR, const int32_t* iRvec, const double* cRvec_shifted);
+
 extern "C" int wbgpu_create(wbgpu_ctx** out, int device, int nw, int nR, const int32_t* iRvec,
                             const double* cRvec_shifted, double cell_volume, void* stream) {
     if (!out || !iRvec || !cRvec_shifted) return set_err("wbgpu_create: null pointer argument");
@@ -212,6 +214,15 @@ extern "C" int wbgpu_create(wbgpu_ctx** out, int device, int nw, int nR, const i
         }
     c->rmin = make_int3(lo[0], lo[1], lo[2]);
     c->nbox = make_int3(hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, hi[2] - lo[2] + 1);
+    if (create_fill(c, device, nw, nR, iRvec, cRvec_shifted)) {   // nothing of a half-built context survives an error
+        wbgpu_destroy(c);
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+static int create_fill(wbgpu_ctx* c, int device, int nw, int nR, const int32_t* iRvec, const double* cRvec_shifted) {
     CK(cudaMalloc(&c->d_iRvec, sizeof(int) * 3 * nR));
     CK(cudaMalloc(&c->d_T, sizeof(double) * 3 * (size_t)nR * nw * nw));
     CK(cudaMemcpy(c->d_iRvec, iRvec, sizeof(int) * 3 * nR, cudaMemcpyHostToDevice));
@@ -219,7 +230,6 @@ extern "C" int wbgpu_create(wbgpu_ctx** out, int device, int nw, int nR, const i
     c->h_iRvec.assign(iRvec, iRvec + 3 * (size_t)nR);
     CK(cudaMalloc(&c->d_sweeps, 2 * sizeof(int)));   // [0] max Jacobi sweeps, [1] k-points re-solved by Jacobi
     CK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    *out = c;
     return 0;
 }
 
@@ -340,8 +350,22 @@ static WbWindow make_window(const wbgpu_scan_spec& s) {
 }
 
 // ------------------------------------------------------------------------------------------ plan
+static int plan_impl(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula_mask, int external_terms, int64_t max_kpoints_per_launch);
+
 extern "C" int wbgpu_plan(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula_mask, int external_terms,
                           int64_t max_kpoints_per_launch) {
+    const int rc = plan_impl(c, NKFFT, formula_mask, external_terms, max_kpoints_per_launch);
+    if (rc && c && !c->planned) {   // failed after the old plan was released: no half-allocated work space stays behind
+        const std::string msg = g_err;
+        cudaGetLastError();
+        free_plan(c);
+        c->planned = false;
+        g_err = msg;
+    }
+    return rc;
+}
+
+static int plan_impl(wbgpu_ctx* c, const int32_t NKFFT[3], uint32_t formula_mask, int external_terms, int64_t max_kpoints_per_launch) {
     if (!c || !NKFFT) return set_err("wbgpu_plan: null pointer argument");
     for (int d = 0; d < 3; d++)
         if (NKFFT[d] < 1) return set_err("wbgpu_plan: NKFFT[%d]=%d", d, NKFFT[d]);
